@@ -1,0 +1,184 @@
+/*
+ * particles_b200.h -- C ABI of libparticles_b200.so
+ *
+ * B200-native (sm_100a) implementation of ONE hot path of kleinschmidt/Particles.jl:
+ * the online particle-filter step for Dirichlet-process mixture clustering
+ * (fit!/filter! on FearnheadParticles and ChenLiuParticles with NormalInverseChisq and
+ * NormalInverseWishart priors under a ChineseRestaurantProcess state prior).
+ *
+ * The reference is pure Julia and has no FFI of its own; the boundary it offers is its
+ * generic-function surface.  Each entry point below names the reference method it stands
+ * behind (file:line in the reference repository).  The Julia shim that binds these with
+ * `ccall` is particles.jl_b200/julia/Particles.jl; the Python mirror used by the tests is
+ * particles.jl_b200/particles_b200/.
+ *
+ * Conventions
+ *   - every function returns an int32 status (PF_OK = 0); pf_last_error(h) gives the text;
+ *   - the caller owns all host buffers and keeps them alive for the duration of the call;
+ *     the library owns all device memory;
+ *   - arrays are column-major Float64; indices cross the ABI 0-based (the shim adds 1);
+ *   - one handle is driven from one host thread at a time;
+ *   - there is NO CPU fallback: every entry point that computes needs a CUDA device and
+ *     fails with PF_ERR_CUDA if none is usable.
+ */
+#ifndef PARTICLES_B200_H
+#define PARTICLES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pf_filter_s *pf_handle;
+
+enum { PF_OK = 0, PF_ERR_ARG = 1, PF_ERR_CUDA = 2, PF_ERR_STATE = 3, PF_ERR_HISTORY = 4,
+       PF_ERR_OVERFLOW = 5, PF_ERR_NCCL = 6 };
+
+enum { PF_FEARNHEAD = 0,   /* FearnheadParticles, src/fearnhead.jl:13-30 */
+       PF_CHENLIU = 1 };   /* ChenLiuParticles,  src/chenliu.jl:7-26    */
+enum { PF_NIX2 = 0,        /* NormalInverseChisq(mu, sigma2, kappa, nu)  (ConjugatePriors) */
+       PF_NIW = 1 };       /* NormalInverseWishart(mu, kappa, Lambda, nu)                 */
+enum { PF_F64 = 0, PF_F32 = 1 };
+/* Traversal order of the low-weight partition in Fearnhead's resampling step:
+ * PF_ORDER_SORTED reproduces the reference literally (ascending weight after sort!,
+ * src/fearnhead.jl:148, ties broken by putative index; output [resampled ; kept]);
+ * PF_ORDER_INDEX is the sort-free variant the reference's TODO proposes
+ * (src/fearnhead.jl:140-145): same kept set, same sampler, putative-index order. */
+enum { PF_ORDER_INDEX = 0, PF_ORDER_SORTED = 1 };
+
+typedef struct {
+    int32_t filter_kind;      /* PF_FEARNHEAD | PF_CHENLIU */
+    int32_t prior_kind;       /* PF_NIX2 | PF_NIW */
+    int32_t d;                /* observation dimension (NIX2: 1) */
+    int32_t precision;        /* PF_F64 (PF_F32: reserved) */
+    int64_t n_particles;      /* N: particle budget (src/fearnhead.jl:15, src/chenliu.jl:9) */
+    int32_t k_max;            /* cluster slots per particle (reference: unbounded, src/particle.jl:142-143);
+                                 at K == k_max the new-cluster candidate is dropped and counted */
+    int32_t order;            /* PF_ORDER_INDEX | PF_ORDER_SORTED (Fearnhead only) */
+    int64_t history;          /* generations of (ancestor, assignment) kept for assignments(); 0 = none */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t reserved0;
+    double alpha;             /* ChineseRestaurantProcess(alpha), src/statepriors.jl:47-52 */
+    double rejuv_threshold;   /* ChenLiuParticles rejuvination_threshold (percent CV), src/chenliu.jl:25 */
+    double kappa0, nu0;
+    double sigma2_0;          /* NIX2 only */
+    const double *mu0;        /* [d] */
+    const double *lambda0;    /* NIW only: [d*d] column-major, symmetric positive definite */
+    uint64_t seed;            /* device uniform stream, used when a step is given uniforms == NULL */
+} pf_config;
+
+typedef struct {
+    int64_t step;             /* observations filtered so far */
+    int64_t n_in;             /* population before the step */
+    int64_t n_putative;       /* M, src/fearnhead.jl:135 */
+    int64_t n_kept;           /* src/fearnhead.jl:154 */
+    int64_t n_resamp_req;     /* src/fearnhead.jl:157 */
+    int64_t n_resamp_got;     /* src/fearnhead.jl:165-167 */
+    int64_t n_out;            /* population after the step */
+    int64_t overflow;         /* new-cluster candidates dropped because K == k_max (cumulative) */
+    double log_total_w;       /* log(total_w): the log-evidence increment of this observation */
+    double log_w_resamp;      /* log(w_resamp / total_w), src/fearnhead.jl:173 */
+    double threshold;         /* kept set = {w >= threshold} (linear putative weight) */
+    double cv;                /* Chen-Liu coefficient of variation, src/chenliu.jl:49-52 */
+    int32_t resampled;        /* Fearnhead: M > N ; Chen-Liu: cv > threshold */
+    int32_t select_rounds;    /* bracket rounds the threshold search needed */
+    int64_t n_candidates;     /* putatives inside the first bracket */
+} pf_step_stats;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+/* FearnheadParticles(n, prior, stateprior) src/fearnhead.jl:29-30 (ONE empty particle);
+ * ChenLiuParticles(n, prior, stateprior; rejuv) src/chenliu.jl:25-26 (N empty particles). */
+int32_t pf_create(const pf_config *cfg, pf_handle *out);
+int32_t pf_destroy(pf_handle h);
+/* Text of the last error on this handle (h == NULL: last pf_create failure). */
+const char *pf_last_error(pf_handle h);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* fit!(ps, y): src/fearnhead.jl:130-184, src/chenliu.jl:54-69.
+ * y[d].  uniforms: Fearnhead consumes 1 (the rand() of src/fearnhead.jl:99); Chen-Liu
+ * consumes n_particles (the categorical draw of src/chenliu.jl:35) followed by n_particles
+ * more (stratified rejuvenation, read only when cv > threshold).  uniforms == NULL draws
+ * them from the device stream pf_uniform(seed, step, stream, i) defined below. */
+int32_t pf_step(pf_handle h, const double *y, const double *uniforms, int64_t n_uniforms);
+/* filter!(ps, ys, false): src/filters.jl:6-13 for the no-callback case.  ys[d x T]
+ * column-major; uniforms[uniforms_per_step x T] or NULL; log_evidence[T] or NULL receives
+ * log(total_w) per observation.  Runs asynchronously on the handle's stream and
+ * synchronises before returning. */
+int32_t pf_filter(pf_handle h, const double *ys, int64_t T, const double *uniforms,
+                  int64_t uniforms_per_step, double *log_evidence);
+
+/* ---- read-out (each synchronises) ---------------------------------------------------- */
+int64_t pf_n_particles(pf_handle h);          /* length(particles(ps)), src/filters.jl:15 */
+int64_t pf_n_steps(pf_handle h);
+int32_t pf_get_logweights(pf_handle h, double *out);      /* log(weight(p)), src/particle.jl:19 */
+int32_t pf_get_ncomponents(pf_handle h, int32_t *out);    /* ncomponents(p), src/particle.jl:157-158 */
+/* One particle, for materialising particles(ps)[i] lazily (src/filters.jl:15):
+ * counts[K] = CRP N (src/statepriors.jl:49) = nobs per component; means[d x K] = sample
+ * means (NormalStats.m / MvNormalStats.m); chol[d x d x K] = lower Cholesky factor of the
+ * posterior Lambda_n (NIX2: sqrt(nu_n sigma2_n)); logdet[K] = log det Lambda_n.
+ * Buffers sized for k_max components. */
+int32_t pf_get_particle(pf_handle h, int64_t i, int32_t *K, double *counts, double *means,
+                        double *chol, double *logdet);
+/* assignments(ps), src/filters.jl:26-34: out[T x n] column-major (column = particle),
+ * 0-based component labels.  Needs history >= steps. */
+int32_t pf_get_assignments(pf_handle h, int32_t *out);
+int32_t pf_get_last_step(pf_handle h, pf_step_stats *out);
+
+/* ---- debugging taps used by the parity tests ------------------------------------------ */
+/* Putative weights exp(logweight) of the LAST step (src/particle.jl:114) in
+ * particle-major / candidate-minor order (src/fearnhead.jl:132); *M receives their count. */
+int32_t pf_get_putative_weights(pf_handle h, double *out, int64_t cap, int64_t *M);
+int32_t pf_get_last_ancestors(pf_handle h, int32_t *out);    /* p.ancestor as 0-based index */
+int32_t pf_get_last_assignments(pf_handle h, int32_t *out);  /* p.assignment - 1 */
+
+/* The selection step of fit!(::FearnheadParticles) (cutoff_ascending + sample_stratified!,
+ * src/fearnhead.jl:59-77, 97-114, 146-179) on caller-supplied weights w[M]: the same device
+ * kernels the filter runs, exposed so that "identical weights and uniforms => identical
+ * survivors" can be tested directly.  survivors[<= N] receives 0-based indices into w in
+ * output order, resampled[<= N] is 1 where the survivor came from the resampled partition.
+ * stats: n_kept, n_resamp_req, n_resamp_got, n_out, threshold, log_w_resamp (= log c,
+ * unnormalised), log_total_w. */
+int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t N, double u, int32_t order,
+                  int64_t *survivors, uint8_t *resampled, pf_step_stats *stats);
+
+/* ---- multi-GPU: particles block-sharded, one process (rank) per GPU ------------------ */
+/* nccl_unique_id: the 128 bytes of an ncclUniqueId created by rank 0 and distributed by the
+ * host program (torch.distributed / MPI).  After this call n_particles is the GLOBAL budget
+ * and this handle owns the shard of rank `rank`. */
+int32_t pf_comm_init(pf_handle h, int32_t rank, int32_t nranks, const void *nccl_unique_id);
+int32_t pf_comm_unique_id(void *out128);
+
+/* ---- instrumentation ------------------------------------------------------------------ */
+/* Device milliseconds (CUDA events on the handle's stream) and kernel launches of the last
+ * pf_filter / pf_step call. */
+int32_t pf_last_timing(pf_handle h, double *device_ms, int64_t *kernel_launches);
+/* Raw stream pointer (cudaStream_t) so that a host program can order its own work. */
+void *pf_stream(pf_handle h);
+const char *pf_version(void);
+
+/* Device uniform stream (SplitMix64 finaliser), reproducible on the host:
+ *   u = (mix(mix(seed + step * 0xD1342543DE82EF95 + stream) + i) >> 11) * 2^-53
+ * stream 0: Fearnhead comb offset (i = 0); 1: Chen-Liu categorical draw; 2: rejuvenation. */
+#ifdef __CUDACC__
+#define PF_HD __host__ __device__
+#else
+#define PF_HD
+#endif
+PF_HD static inline uint64_t pf_mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+PF_HD static inline double pf_uniform(uint64_t seed, uint64_t step, uint64_t stream, uint64_t i)
+{
+    uint64_t k = pf_mix64(seed + step * 0xD1342543DE82EF95ull + stream);
+    return (double)(pf_mix64(k + i) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARTICLES_B200_H */

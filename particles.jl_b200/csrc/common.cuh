@@ -1,0 +1,168 @@
+// common.cuh -- shared device helpers: 128-bit fixed point, block reductions, layouts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PF_MAX_D 8
+#define PF_MAX_SLOTS 64          // k_max + 1 <= 64
+#define PF_INF_BITS 0x7FF0000000000000ull
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ------------------------------------------------------------------ 128-bit unsigned
+struct u128 {
+    u64 lo, hi;
+};
+__host__ __device__ __forceinline__ u128 mk128(u64 lo, u64 hi = 0) { u128 r; r.lo = lo; r.hi = hi; return r; }
+__host__ __device__ __forceinline__ u128 add128(u128 a, u128 b)
+{
+    u128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+__host__ __device__ __forceinline__ u128 sub128(u128 a, u128 b)
+{
+    u128 r;
+    r.lo = a.lo - b.lo;
+    r.hi = a.hi - b.hi - (a.lo < b.lo ? 1ull : 0ull);
+    return r;
+}
+__host__ __device__ __forceinline__ bool lt128(u128 a, u128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+__host__ __device__ __forceinline__ bool le128(u128 a, u128 b) { return !lt128(b, a); }
+__host__ __device__ __forceinline__ bool isz128(u128 a) { return (a.lo | a.hi) == 0; }
+__host__ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b)
+{
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+// a (128 bit) * b (64 bit), low 128 bits (callers guarantee no overflow)
+__host__ __device__ __forceinline__ u128 mul128_64(u128 a, u64 b)
+{
+    u128 r;
+    r.lo = a.lo * b;
+    r.hi = mulhi64(a.lo, b) + a.hi * b;
+    return r;
+}
+__host__ __device__ __forceinline__ u128 shr128(u128 a, int s)
+{
+    if (s <= 0) return a;
+    if (s >= 128) return mk128(0, 0);
+    if (s >= 64) return mk128(a.hi >> (s - 64), 0);
+    return mk128((a.lo >> s) | (a.hi << (64 - s)), a.hi >> s);
+}
+__host__ __device__ __forceinline__ u128 shl128(u128 a, int s)
+{
+    if (s <= 0) return a;
+    if (s >= 128) return mk128(0, 0);
+    if (s >= 64) return mk128(0, a.lo << (s - 64));
+    return mk128(a.lo << s, (a.hi << s) | (a.lo >> (64 - s)));
+}
+// round-to-nearest conversion (hi*2^64 is exact for hi < 2^53, one rounding in the add)
+__host__ __device__ __forceinline__ double to_double128(u128 a)
+{
+    return (double)a.hi * 18446744073709551616.0 + (double)a.lo;
+}
+
+// Fixed point: q = floor(v * 2^s) for a finite v >= 0 given by its bit pattern.
+// Callers guarantee v * 2^s < 2^127.
+__host__ __device__ __forceinline__ u128 fx128(u64 bits, int s)
+{
+    int e = (int)(bits >> 52) & 0x7FF;
+    u64 m = bits & 0x000FFFFFFFFFFFFFull;
+    if (e == 0) e = 1; else m |= 0x0010000000000000ull;
+    int sh = e - 1075 + s;                 // v = m * 2^(e-1075)
+    if (sh >= 0) return shl128(mk128(m, 0), sh);
+    if (sh <= -64) return mk128(0, 0);
+    return mk128(m >> (-sh), 0);
+}
+// unbiased exponent E with 2^E <= v < 2^(E+1) (subnormals: -1022)
+__host__ __device__ __forceinline__ int exp_of_bits(u64 bits)
+{
+    int e = (int)(bits >> 52) & 0x7FF;
+    return (e == 0 ? 1 : e) - 1023;
+}
+
+// number of comb teeth strictly below X:  #{k >= 0 : U + k T < X}  (T > 0)
+__host__ __device__ inline u64 teeth_below(u128 X, u128 U, u128 T)
+{
+    if (!lt128(U, X)) return 0;
+    u128 R = sub128(sub128(X, U), mk128(1, 0));      // X - U - 1 >= 0
+    // floor(R / T) + 1 ; quotient < 2^40 by construction, FP estimate + exact correction
+    double est = to_double128(R) / to_double128(T);
+    u64 q = est >= 1.0 ? (u64)est : 0;
+    if (q > 0) q -= 1;
+    u128 qt = mul128_64(T, q);
+    while (lt128(R, qt)) { q--; qt = sub128(qt, T); }           // q*T <= R
+    u128 rem = sub128(R, qt);
+    while (le128(T, rem)) { q++; rem = sub128(rem, T); }        // rem < T
+    return q + 1;
+}
+
+// ------------------------------------------------------------------ warp / block helpers
+__device__ __forceinline__ u128 shfl_up128(u128 v, int d)
+{
+    u128 r;
+    r.lo = __shfl_up_sync(0xffffffffu, v.lo, d);
+    r.hi = __shfl_up_sync(0xffffffffu, v.hi, d);
+    return r;
+}
+__device__ __forceinline__ u128 shfl_xor128(u128 v, int d)
+{
+    u128 r;
+    r.lo = __shfl_xor_sync(0xffffffffu, v.lo, d);
+    r.hi = __shfl_xor_sync(0xffffffffu, v.hi, d);
+    return r;
+}
+__device__ __forceinline__ u128 warp_sum128(u128 v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = add128(v, shfl_xor128(v, d));
+    return v;
+}
+__device__ __forceinline__ u64 warp_sum64(u64 v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ u64 warp_max64(u64 v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        u64 o = __shfl_xor_sync(0xffffffffu, v, d);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+// 128-bit global accumulation through two 64-bit atomics on 3 limbs would lose carries;
+// instead accumulate four 32-bit limbs in four u64 cells (exact for < 2^32 contributions).
+struct acc128 {
+    u64 l[4];
+};
+__device__ __forceinline__ void atomic_add_acc(acc128 *a, u128 v)
+{
+    if (v.lo & 0xffffffffull) atomicAdd(&a->l[0], v.lo & 0xffffffffull);
+    if (v.lo >> 32) atomicAdd(&a->l[1], v.lo >> 32);
+    if (v.hi & 0xffffffffull) atomicAdd(&a->l[2], v.hi & 0xffffffffull);
+    if (v.hi >> 32) atomicAdd(&a->l[3], v.hi >> 32);
+}
+__host__ __device__ __forceinline__ u128 acc_value(const volatile acc128 *a)
+{
+    u128 r = mk128(a->l[0], 0);
+    r = add128(r, shl128(mk128(a->l[1], 0), 32));
+    r = add128(r, mk128(0, a->l[2]));
+    r = add128(r, mk128(0, a->l[3] << 32));
+    return r;
+}
+
+#define CUDA_TRY(x)                                                                      \
+    do {                                                                                 \
+        cudaError_t e_ = (x);                                                            \
+        if (e_ != cudaSuccess) return set_cuda_error(h, e_, #x, __LINE__);               \
+    } while (0)

@@ -1,0 +1,738 @@
+// pf_api.cu -- C ABI of libparticles_b200.so (see include/particles_b200.h) and the host
+// orchestration of the per-observation kernel sequence.  No CPU fallback: every compute
+// entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/particles_b200.h"
+#include "fearnhead.cuh"
+#include "chenliu.cuh"
+#include "sort.cuh"
+
+static thread_local std::string g_create_error;
+
+struct pf_filter_s {
+    pf_config cfg;
+    int d, F, k_max;
+    long long N, cap;
+    std::vector<double> mu0, lam0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // particle store (ping-pong)
+    double *S[2] = {nullptr, nullptr};
+    double *logw[2] = {nullptr, nullptr};
+    int *Kc[2] = {nullptr, nullptr};
+    int cur = 0;
+    // step scratch
+    double *V = nullptr;
+    unsigned char *cnt = nullptr;
+    unsigned int *surv_parent = nullptr;
+    unsigned char *surv_slot = nullptr;
+    TileDesc *tiles = nullptr;
+    TileIncl *incl = nullptr;
+    double *cand = nullptr;
+    long long cand_cap = 0;
+    SelScratch *sc = nullptr;
+    SelResult *res = nullptr;
+    StepState *st = nullptr;
+    PriorConst *pc = nullptr;
+    StepConst *stc = nullptr;
+    NRow *tab = nullptr;
+    long long tab_cap = 0;
+    NRow row0;
+    StepLog *slog = nullptr;
+    long long slog_cap = 0;
+    double *ys_dev = nullptr, *u_dev = nullptr;
+    long long ys_cap = 0, u_cap = 0;
+    // Chen-Liu scratch
+    ClState *cl = nullptr;
+    double *W = nullptr;
+    u128 *cum = nullptr;
+    unsigned char *asg_tmp = nullptr;
+    double *cl_part = nullptr;
+    // genealogy
+    unsigned int *gen_anc = nullptr;
+    unsigned char *gen_asg = nullptr;
+    long long hist_cap = 0;
+    // host mirrors
+    long long steps = 0;
+    long long n_host = 0;                 // population size after the last synchronised step
+    long long ub_live = 1;                // host upper bound on n_live (grid sizing)
+    std::vector<StepLog> logs;            // records of the last call
+    StepLog last{};
+    bool have_last = false;
+    int sel_grid = 0;
+    int num_sms = 0;
+    double last_ms = 0.0;
+    long long last_launches = 0;
+    long long launches = 0;
+    unsigned int epoch = 0;
+    std::string err;
+};
+
+static int32_t set_error(pf_handle h, int32_t code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+static int32_t set_cuda_error(pf_handle h, cudaError_t e, const char *what, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %s at pf_api.cu:%d: %s", cudaGetErrorName(e), line, what);
+    cudaGetLastError();
+    return set_error(h, PF_ERR_CUDA, buf);
+}
+
+// ------------------------------------------------------------------ host-side model setup
+static const long double LOGPI_L = 1.1447298858494001741434273513530587116473L;
+
+static NRow make_row(const pf_filter_s *f, long long n)
+{
+    long double k0 = f->cfg.kappa0, nu0 = f->cfg.nu0, d = f->d;
+    long double kn = k0 + n, nn = nu0 + n;
+    long double h = (nn + 1.0L) / 2.0L;
+    long double r = kn / (kn + 1.0L);
+    long double lp = n == 0 ? logl((long double)f->cfg.alpha) : logl((long double)n);
+    long double C = lp + lgammal(h) - lgammal(h - d / 2.0L) - d / 2.0L * LOGPI_L + d / 2.0L * logl(r);
+    NRow row;
+    row.C = (double)C; row.r = (double)r; row.h = (double)h; row.g = (double)((long double)n / kn);
+    return row;
+}
+
+static int32_t ensure_table(pf_handle h, long long need)
+{
+    if (need <= h->tab_cap) return PF_OK;
+    long long ncap = h->tab_cap ? h->tab_cap : 4096;
+    while (ncap < need) ncap *= 2;
+    std::vector<NRow> rows(ncap);
+    for (long long n = 0; n < ncap; n++) rows[n] = make_row(h, n);
+    NRow *nt = nullptr;
+    CUDA_TRY(cudaMalloc(&nt, sizeof(NRow) * ncap));
+    CUDA_TRY(cudaMemcpyAsync(nt, rows.data(), sizeof(NRow) * ncap, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->tab) cudaFree(h->tab);
+    h->tab = nt; h->tab_cap = ncap;
+    return PF_OK;
+}
+
+static bool chol_lower(int d, const double *A /*col-major*/, double *Lo /*col-major*/)
+{
+    std::fill(Lo, Lo + d * d, 0.0);
+    for (int j = 0; j < d; j++)
+        for (int i = j; i < d; i++) {
+            double acc = A[i + j * d];
+            for (int k = 0; k < j; k++) acc -= Lo[i + k * d] * Lo[j + k * d];
+            if (i == j) { if (!(acc > 0.0)) return false; Lo[i + j * d] = std::sqrt(acc); }
+            else Lo[i + j * d] = acc / Lo[j + j * d];
+        }
+    return true;
+}
+
+template <typename T>
+static cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+
+#define DISPATCH_D(dd, CALL)                                         \
+    switch (dd) {                                                    \
+    case 1: { constexpr int D = 1; CALL; } break;                    \
+    case 2: { constexpr int D = 2; CALL; } break;                    \
+    case 3: { constexpr int D = 3; CALL; } break;                    \
+    case 4: { constexpr int D = 4; CALL; } break;                    \
+    case 8: { constexpr int D = 8; CALL; } break;                    \
+    default: break;                                                  \
+    }
+
+static bool supported_d(int d) { return d == 1 || d == 2 || d == 3 || d == 4 || d == 8; }
+
+extern "C" const char *pf_version(void) { return "particles_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *pf_last_error(pf_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int32_t pf_destroy(pf_handle h)
+{
+    if (!h) return PF_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
+                    h->surv_slot, h->tiles, h->incl, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
+                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
+{
+    if (!cfg || !out) return set_error(nullptr, PF_ERR_ARG, "pf_create: null argument");
+    *out = nullptr;
+    if (cfg->filter_kind != PF_FEARNHEAD && cfg->filter_kind != PF_CHENLIU)
+        return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown filter_kind");
+    if (cfg->prior_kind != PF_NIX2 && cfg->prior_kind != PF_NIW)
+        return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown prior_kind");
+    int d = cfg->prior_kind == PF_NIX2 ? 1 : cfg->d;
+    if (!supported_d(d)) return set_error(nullptr, PF_ERR_ARG, "pf_create: d must be one of 1, 2, 3, 4, 8");
+    if (cfg->precision != PF_F64) return set_error(nullptr, PF_ERR_ARG, "pf_create: only PF_F64 is implemented");
+    if (cfg->n_particles < 1 || cfg->n_particles > (1ll << 27)) return set_error(nullptr, PF_ERR_ARG, "pf_create: n_particles out of range [1, 2^27]");
+    if (cfg->k_max < 1 || cfg->k_max + 1 > PF_MAX_SLOTS) return set_error(nullptr, PF_ERR_ARG, "pf_create: k_max out of range [1, 63]");
+    if (!(cfg->alpha > 0.0) || !(cfg->kappa0 > 0.0)) return set_error(nullptr, PF_ERR_ARG, "pf_create: alpha and kappa0 must be positive");
+    if (!(cfg->nu0 > d - 1.0)) return set_error(nullptr, PF_ERR_ARG, "pf_create: nu0 must exceed d - 1");
+    if (!cfg->mu0) return set_error(nullptr, PF_ERR_ARG, "pf_create: mu0 is null");
+    if (cfg->order != PF_ORDER_INDEX && cfg->order != PF_ORDER_SORTED) return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown order");
+    if (cfg->history < 0) return set_error(nullptr, PF_ERR_ARG, "pf_create: history must be >= 0");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(nullptr, PF_ERR_CUDA, "pf_create: no CUDA device (this library has no CPU fallback)"); }
+    if (cfg->device < 0 || cfg->device >= ndev) return set_error(nullptr, PF_ERR_ARG, "pf_create: bad device ordinal");
+
+    pf_filter_s *h = new pf_filter_s();
+    h->cfg = *cfg;
+    h->d = d; h->k_max = cfg->k_max; h->N = cfg->n_particles; h->cap = cfg->n_particles;
+    h->F = 2 + d + d * (d + 1) / 2;
+    h->mu0.assign(cfg->mu0, cfg->mu0 + d);
+    h->lam0.assign(d * d, 0.0);
+    if (cfg->prior_kind == PF_NIX2) {
+        if (!(cfg->sigma2_0 > 0.0)) { delete h; return set_error(nullptr, PF_ERR_ARG, "pf_create: sigma2_0 must be positive"); }
+        h->lam0[0] = cfg->nu0 * cfg->sigma2_0;        // NIW(d=1) == NIX2, test/niw.jl:5-6
+    } else {
+        if (!cfg->lambda0) { delete h; return set_error(nullptr, PF_ERR_ARG, "pf_create: lambda0 is null"); }
+        h->lam0.assign(cfg->lambda0, cfg->lambda0 + d * d);
+    }
+    h->cfg.mu0 = nullptr; h->cfg.lambda0 = nullptr;
+    std::vector<double> L0(d * d);
+    if (!chol_lower(d, h->lam0.data(), L0.data())) { delete h; return set_error(nullptr, PF_ERR_ARG, "pf_create: lambda0 is not positive definite"); }
+
+#define CT(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { int32_t rc_ = set_cuda_error(nullptr, e_, #x, __LINE__); g_create_error = h->err.empty() ? g_create_error : h->err; pf_destroy(h); return rc_; } } while (0)
+    CT(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CT(cudaGetDeviceProperties(&prop, cfg->device));
+    h->num_sms = prop.multiProcessorCount;
+    CT(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CT(cudaEventCreate(&h->ev0));
+    CT(cudaEventCreate(&h->ev1));
+    const long long cap = h->cap;
+    const size_t store = (size_t)h->k_max * h->F * cap;
+    for (int b = 0; b < 2; b++) {
+        CT(dmalloc(&h->S[b], store));
+        CT(dmalloc(&h->logw[b], cap));
+        CT(dmalloc(&h->Kc[b], cap));
+    }
+    CT(dmalloc(&h->V, (size_t)(h->k_max + 1) * cap));
+    CT(dmalloc(&h->cnt, cap));
+    CT(dmalloc(&h->surv_parent, cap));
+    CT(dmalloc(&h->surv_slot, cap));
+    long long ntiles = (cap + SCAN_THREADS - 1) / SCAN_THREADS;
+    CT(dmalloc(&h->tiles, ntiles));
+    CT(dmalloc(&h->incl, ntiles));
+    CT(cudaMemsetAsync(h->tiles, 0, sizeof(TileDesc) * ntiles, h->stream));
+    CT(dmalloc(&h->sc, 1));
+    CT(dmalloc(&h->res, 1));
+    CT(dmalloc(&h->st, 1));
+    CT(dmalloc(&h->pc, 1));
+    CT(dmalloc(&h->stc, 1));
+    CT(cudaMemsetAsync(h->sc, 0, sizeof(SelScratch), h->stream));
+    CT(cudaMemsetAsync(h->res, 0, sizeof(SelResult), h->stream));
+    // cooperative grid of the threshold search
+    CT(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SAMPLE_CAP * 8));
+    int occ = 0;
+    CT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SAMPLE_CAP * 8));
+    if (occ < 1) { pf_destroy(h); return set_error(nullptr, PF_ERR_CUDA, "pf_create: k_select does not fit on an SM"); }
+    h->sel_grid = h->num_sms * (occ > 2 ? 2 : occ);
+    h->cand_cap = (long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
+    CT(dmalloc(&h->cand, (size_t)h->cand_cap));
+    if (cfg->history > 0) {
+        h->hist_cap = cfg->history;
+        CT(dmalloc(&h->gen_anc, (size_t)h->hist_cap * cap));
+        CT(dmalloc(&h->gen_asg, (size_t)h->hist_cap * cap));
+    }
+    // prior constants
+    PriorConst pc;
+    memset(&pc, 0, sizeof pc);
+    for (int i = 0; i < d; i++) { pc.mu0[i] = h->mu0[i]; pc.L0_dinv[i] = 1.0 / L0[i + i * d]; }
+    for (int i = 1, o = 0; i < d; i++) for (int k = 0; k < i; k++) pc.L0_off[o++] = L0[i + k * d];
+    pc.kappa0 = cfg->kappa0; pc.nu0 = cfg->nu0; pc.alpha = cfg->alpha;
+    double ld = 0.0;
+    for (int i = 0; i < d; i++) ld += std::log(L0[i + i * d]);
+    pc.logdet0 = 2.0 * ld;
+    h->row0 = make_row(h, 0);
+    pc.row0 = h->row0;
+    CT(cudaMemcpyAsync(h->pc, &pc, sizeof pc, cudaMemcpyHostToDevice, h->stream));
+    {
+        int32_t rc = ensure_table(h, 4096);
+        if (rc != PF_OK) { g_create_error = h->err; pf_destroy(h); return rc; }
+    }
+    // initial population
+    StepState st0;
+    memset(&st0, 0, sizeof st0);
+    if (cfg->filter_kind == PF_FEARNHEAD) {
+        st0.n_live = 1; st0.n_next = 1;              // src/fearnhead.jl:29-30
+        h->n_host = 1; h->ub_live = 1;
+    } else {
+        st0.n_live = h->N; st0.n_next = h->N;        // src/chenliu.jl:25-26
+        h->n_host = h->N; h->ub_live = h->N;
+        CT(dmalloc(&h->cl, 1));
+        CT(cudaMemsetAsync(h->cl, 0, sizeof(ClState), h->stream));
+        CT(dmalloc(&h->W, cap));
+        CT(dmalloc(&h->cum, cap));
+        CT(dmalloc(&h->asg_tmp, cap));
+        CT(dmalloc(&h->cl_part, 4096));
+    }
+    CT(cudaMemcpyAsync(h->st, &st0, sizeof st0, cudaMemcpyHostToDevice, h->stream));
+    CT(cudaMemsetAsync(h->logw[0], 0, sizeof(double) * cap, h->stream));   // weight 1.0, src/particle.jl:62
+    CT(cudaMemsetAsync(h->Kc[0], 0, sizeof(int) * cap, h->stream));
+    CT(cudaStreamSynchronize(h->stream));
+#undef CT
+    *out = h;
+    return PF_OK;
+}
+
+// ------------------------------------------------------------------ the step sequences
+static inline int grid_for(long long n, int bs) { long long g = (n + bs - 1) / bs; return (int)(g < 1 ? 1 : g); }
+
+static int32_t launch_select(pf_handle h, const double *V, const unsigned char *cnt, long long cap, const long long *n_live,
+                             const long long *M, const u64 *vmax, long long N, const double *u_dev, double *cand,
+                             long long cand_cap, SelScratch *sc, SelResult *res)
+{
+    SelArgs a;
+    a.V = V; a.cnt = cnt; a.cap = cap; a.n_live = n_live; a.M = M; a.vmax_bits = vmax; a.N = N; a.u = u_dev;
+    a.cand = cand; a.cand_cap = cand_cap; a.sc = sc; a.res = res;
+    void *args[] = {&a};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SAMPLE_CAP * 8, h->stream));
+    h->launches++;
+    return PF_OK;
+}
+
+template <int D>
+static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_dev, StepLog *log_dev)
+{
+    const long long cap = h->cap;
+    const int cur = h->cur, nxt = cur ^ 1;
+    const long long ub = h->ub_live;                                     // n_live <= ub
+    long long ub_next = ub * (long long)(std::min<long long>(h->k_max, h->steps + 1) + 1);
+    if (ub_next > h->N || ub_next < 0) ub_next = h->N;
+    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
+    if (h->hist_cap) {
+        if (h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
+        ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap;
+    }
+    h->epoch++;
+    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0);
+    k_expand<D><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                            h->stc, h->st, h->V, h->cnt);
+    h->launches += 2;
+    int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
+                               h->cand_cap, h->sc, h->res);
+    if (rc != PF_OK) return rc;
+    k_scan<<<grid_for(ub, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->st, h->res, h->tiles, h->incl,
+                                                                         h->surv_parent, h->surv_slot, h->epoch);
+    k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
+                                                                      h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
+                                                                      h->surv_slot, ga, gs);
+    k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->N);
+    h->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    h->cur = nxt;
+    h->ub_live = ub_next;
+    h->steps++;
+    return PF_OK;
+}
+
+template <int D>
+static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_dev /* 2N or null */, StepLog *log_dev)
+{
+    const long long cap = h->cap, N = h->N;
+    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
+    if (h->hist_cap) {
+        if (h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
+        ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap;
+    }
+    const int g256 = grid_for(N, 256);
+    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1);
+    k_cl_propagate<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], cap, N, h->k_max,
+                                                     h->tab, h->pc, h->stc, h->st, h->cl, u_dev, h->cfg.seed, (u64)h->steps, h->W,
+                                                     h->asg_tmp);
+    int gstat = h->num_sms * 2;
+    if (gstat > 1024) gstat = 1024;
+    k_cl_sum<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl);
+    k_cl_var<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl, h->cl_part);
+    k_cl_decide<<<1, 32, 0, h->stream>>>(h->cl, h->cl_part, gstat, N, h->cfg.rejuv_threshold);
+    k_cl_scan<<<1, 1024, 0, h->stream>>>(h->W, N, h->cl, h->cum);
+    k_cl_finish<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->Kc[0], h->Kc[1], h->logw[0], h->logw[1], cap, N, h->cl, h->W,
+                                                  h->cum, u_dev ? u_dev + N : nullptr, h->cfg.seed, (u64)h->steps, h->asg_tmp, ga, gs);
+    k_cl_steplog<<<1, 32, 0, h->stream>>>(h->st, h->cl, log_dev, N);
+    h->launches += 8;
+    CUDA_TRY(cudaGetLastError());
+    h->steps++;
+    return PF_OK;
+}
+
+static int32_t run_steps(pf_handle h, const double *ys, long long T, const double *uniforms, long long ups, double *log_evidence)
+{
+    if (!h) return PF_ERR_ARG;
+    if (T < 0 || (!ys && T > 0)) return set_error(h, PF_ERR_ARG, "pf_filter: bad ys/T");
+    if (T == 0) return PF_OK;
+    const bool fh = h->cfg.filter_kind == PF_FEARNHEAD;
+    if (uniforms) {
+        long long need = fh ? 1 : 2 * h->N;
+        if (ups < need) return set_error(h, PF_ERR_ARG, fh ? "pf_filter: Fearnhead needs 1 uniform per step" : "pf_filter: Chen-Liu needs 2*N uniforms per step");
+    }
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int32_t rc = ensure_table(h, h->steps + T + 2);
+    if (rc != PF_OK) return rc;
+    const int d = h->d;
+    if (T * d > h->ys_cap) {
+        if (h->ys_dev) cudaFree(h->ys_dev);
+        h->ys_cap = T * d;
+        CUDA_TRY(dmalloc(&h->ys_dev, (size_t)h->ys_cap));
+    }
+    if (T > h->slog_cap) {
+        if (h->slog) cudaFree(h->slog);
+        h->slog_cap = T;
+        CUDA_TRY(dmalloc(&h->slog, (size_t)T));
+    }
+    // uniforms: Fearnhead T doubles; Chen-Liu is staged step by step (2N per step)
+    long long un = fh ? T : 2 * h->N;
+    if (un > h->u_cap) {
+        if (h->u_dev) cudaFree(h->u_dev);
+        h->u_cap = un;
+        CUDA_TRY(dmalloc(&h->u_dev, (size_t)un));
+    }
+    h->launches = 0;
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->ys_dev, ys, sizeof(double) * T * d, cudaMemcpyHostToDevice, h->stream));
+    if (fh) {
+        std::vector<double> ubuf(T);
+        for (long long t = 0; t < T; t++)
+            ubuf[t] = uniforms ? uniforms[t * ups] : pf_uniform(h->cfg.seed, (uint64_t)(h->steps + t), 0, 0);
+        CUDA_TRY(cudaMemcpyAsync(h->u_dev, ubuf.data(), sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));      // ubuf goes out of scope
+        CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    }
+    for (long long t = 0; t < T; t++) {
+        if (fh) {
+            DISPATCH_D(d, rc = fearnhead_step<D>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t));
+        } else {
+            const double *ud = nullptr;
+            if (uniforms) {
+                CUDA_TRY(cudaMemcpyAsync(h->u_dev, uniforms + t * ups, sizeof(double) * 2 * h->N, cudaMemcpyHostToDevice, h->stream));
+                ud = h->u_dev;
+            }
+            DISPATCH_D(d, rc = chenliu_step<D>(h, h->ys_dev + t * d, ud, h->slog + t));
+        }
+        if (rc != PF_OK) { cudaStreamSynchronize(h->stream); return rc; }
+    }
+    h->logs.resize(T);
+    CUDA_TRY(cudaMemcpyAsync(h->logs.data(), h->slog, sizeof(StepLog) * T, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms; h->last_launches = h->launches;
+    h->last = h->logs.back(); h->have_last = true;
+    h->n_host = h->last.n_out;
+    if (!fh) {
+        ClState cs;
+        CUDA_TRY(cudaMemcpy(&cs, h->cl, sizeof cs, cudaMemcpyDeviceToHost));
+        h->cur = cs.cur;
+    }
+    if (fh && h->n_host < h->ub_live && h->n_host >= 1) { /* keep the conservative bound */ }
+    if (log_evidence) for (long long t = 0; t < T; t++) log_evidence[t] = h->logs[t].log_total;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_step(pf_handle h, const double *y, const double *uniforms, int64_t n_uniforms)
+{
+    return run_steps(h, y, 1, uniforms, n_uniforms, nullptr);
+}
+
+extern "C" int32_t pf_filter(pf_handle h, const double *ys, int64_t T, const double *uniforms, int64_t uniforms_per_step,
+                             double *log_evidence)
+{
+    return run_steps(h, ys, T, uniforms, uniforms_per_step, log_evidence);
+}
+
+// ------------------------------------------------------------------ read-out
+extern "C" int64_t pf_n_particles(pf_handle h) { return h ? h->n_host : -1; }
+extern "C" int64_t pf_n_steps(pf_handle h) { return h ? h->steps : -1; }
+extern "C" void *pf_stream(pf_handle h) { return h ? (void *)h->stream : nullptr; }
+
+extern "C" int32_t pf_last_timing(pf_handle h, double *device_ms, int64_t *kernel_launches)
+{
+    if (!h) return PF_ERR_ARG;
+    if (device_ms) *device_ms = h->last_ms;
+    if (kernel_launches) *kernel_launches = h->last_launches;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_logweights(pf_handle h, double *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(out, h->logw[h->cur], sizeof(double) * h->n_host, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_ncomponents(pf_handle h, int32_t *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(out, h->Kc[h->cur], sizeof(int) * h->n_host, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_particle(pf_handle h, int64_t i, int32_t *K_out, double *counts, double *means, double *chol, double *logdet)
+{
+    if (!h) return PF_ERR_ARG;
+    if (i < 0 || i >= h->n_host) return set_error(h, PF_ERR_ARG, "pf_get_particle: index out of range");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int d = h->d, F = h->F;
+    int K = 0;
+    CUDA_TRY(cudaMemcpyAsync(&K, h->Kc[h->cur] + i, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::vector<double> rec((size_t)std::max(K, 1) * F);
+    if (K > 0) {
+        // strided gather: element (j*F+f) lives at S[(j*F+f)*cap + i]
+        CUDA_TRY(cudaMemcpy2DAsync(rec.data(), sizeof(double), h->S[h->cur] + i, sizeof(double) * h->cap, sizeof(double),
+                                   (size_t)K * F, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (K_out) *K_out = K;
+    for (int j = 0; j < K; j++) {
+        const double *r = rec.data() + (size_t)j * F;
+        if (counts) counts[j] = r[0];
+        if (logdet) logdet[j] = r[1];
+        if (means) for (int k = 0; k < d; k++) means[(size_t)j * d + k] = r[2 + k];
+        if (chol) {
+            double *Lj = chol + (size_t)j * d * d;
+            std::fill(Lj, Lj + d * d, 0.0);
+            for (int k = 0; k < d; k++) Lj[k + k * d] = 1.0 / r[2 + d + k];
+            for (int a = 1, o = 0; a < d; a++) for (int b = 0; b < a; b++) Lj[a + b * d] = r[2 + 2 * d + o++];
+        }
+    }
+    return PF_OK;
+}
+
+__global__ void k_backtrack(const unsigned int *__restrict__ gen_anc, const unsigned char *__restrict__ gen_asg, long long cap,
+                            long long T, long long n, int *__restrict__ out /* [T][n] */)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long k = i;
+    for (long long t = T - 1; t >= 0; t--) {          // assignments(p), src/particle.jl:25-32
+        out[t * n + i] = gen_asg[t * cap + k];
+        k = gen_anc[t * cap + k];
+    }
+}
+
+extern "C" int32_t pf_get_assignments(pf_handle h, int32_t *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    if (!h->hist_cap) return set_error(h, PF_ERR_HISTORY, "pf_get_assignments: history is disabled (pf_config.history = 0)");
+    const long long T = h->steps, n = h->n_host;
+    if (T == 0 || n == 0) return PF_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int *tmp = nullptr;
+    CUDA_TRY(dmalloc(&tmp, (size_t)T * n));
+    k_backtrack<<<grid_for(n, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, n, tmp);
+    std::vector<int> host((size_t)T * n);
+    cudaError_t e = cudaMemcpyAsync(host.data(), tmp, sizeof(int) * T * n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return set_cuda_error(h, e, "pf_get_assignments", __LINE__);
+    for (long long i = 0; i < n; i++)                  // -> column-major T x n
+        for (long long t = 0; t < T; t++) out[i * T + t] = host[t * n + i];
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_last_step(pf_handle h, pf_step_stats *o)
+{
+    if (!h || !o) return PF_ERR_ARG;
+    if (!h->have_last) return set_error(h, PF_ERR_STATE, "pf_get_last_step: no step has run");
+    const StepLog &r = h->last;
+    memset(o, 0, sizeof *o);
+    o->step = h->steps; o->n_in = r.n_in; o->n_putative = r.M; o->n_kept = r.n_kept; o->n_resamp_req = r.n_req;
+    o->n_resamp_got = r.n_got; o->n_out = r.n_out; o->overflow = r.overflow; o->log_total_w = r.log_total;
+    o->log_w_resamp = r.lw_resamp; o->threshold = r.thr; o->cv = r.cv; o->resampled = r.resampled;
+    o->select_rounds = r.rounds; o->n_candidates = r.n_cand;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_putative_weights(pf_handle h, double *out, int64_t cap_out, int64_t *M_out)
+{
+    if (!h || !M_out) return PF_ERR_ARG;
+    if (!h->have_last || h->cfg.filter_kind != PF_FEARNHEAD) return set_error(h, PF_ERR_STATE, "pf_get_putative_weights: needs a Fearnhead step");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const long long n_in = h->last.n_in, slots = h->k_max + 1;
+    std::vector<unsigned char> c(n_in);
+    CUDA_TRY(cudaMemcpyAsync(c.data(), h->cnt, n_in, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<double> v((size_t)slots * n_in);
+    CUDA_TRY(cudaMemcpy2DAsync(v.data(), sizeof(double) * n_in, h->V, sizeof(double) * h->cap, sizeof(double) * n_in, slots,
+                               cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    long long M = 0;
+    for (long long i = 0; i < n_in; i++)
+        for (int j = 0; j < c[i]; j++, M++)
+            if (out && M < cap_out) out[M] = v[(size_t)j * n_in + i];
+    *M_out = M;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_last_ancestors(pf_handle h, int32_t *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    if (!h->hist_cap || h->steps == 0) return set_error(h, PF_ERR_HISTORY, "pf_get_last_ancestors: needs history >= 1 and one step");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    static_assert(sizeof(int32_t) == sizeof(unsigned int), "");
+    CUDA_TRY(cudaMemcpyAsync(out, h->gen_anc + (size_t)(h->steps - 1) * h->cap, sizeof(int) * h->n_host, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_last_assignments(pf_handle h, int32_t *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    if (!h->hist_cap || h->steps == 0) return set_error(h, PF_ERR_HISTORY, "pf_get_last_assignments: needs history >= 1 and one step");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    std::vector<unsigned char> a(h->n_host);
+    CUDA_TRY(cudaMemcpyAsync(a.data(), h->gen_asg + (size_t)(h->steps - 1) * h->cap, h->n_host, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (long long i = 0; i < h->n_host; i++) out[i] = a[i];
+    return PF_OK;
+}
+
+// ------------------------------------------------------------------ stand-alone selection
+__global__ void k_vmax(const double *w, long long M, StepState *st)
+{
+    u64 v = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        u64 b = (u64)__double_as_longlong(w[i]);
+        v = b > v ? b : v;
+    }
+    v = warp_max64(v);
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(&st->vmax_bits, v);
+}
+
+extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t N, double u, int32_t order,
+                             int64_t *survivors, uint8_t *resampled, pf_step_stats *stats)
+{
+    pf_filter_s tmp;             // only for error text / stream bookkeeping
+    pf_handle h = &tmp;
+    if (!w || M < 1 || N < 1 || !survivors || M > (1ll << 28)) return set_error(nullptr, PF_ERR_ARG, "pf_select: bad argument");
+    if (!(u >= 0.0 && u < 1.0)) return set_error(nullptr, PF_ERR_ARG, "pf_select: u must be in [0, 1)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(nullptr, PF_ERR_CUDA, "pf_select: no CUDA device (no CPU fallback)"); }
+    int32_t rc = PF_OK;
+    double *dW = nullptr, *dU = nullptr, *cand = nullptr;
+    StepState *st = nullptr; SelScratch *sc = nullptr; SelResult *res = nullptr;
+    TileDesc *tiles = nullptr; TileIncl *incl = nullptr;
+    unsigned int *sp = nullptr; unsigned char *ss = nullptr;
+    u64 *keys = nullptr, *keys2 = nullptr; unsigned int *vals = nullptr, *vals2 = nullptr;
+    unsigned int *hist = nullptr;
+    std::vector<unsigned int> perm_host;
+#define ST(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = set_cuda_error(h, e_, #x, __LINE__); g_create_error = h->err; goto done; } } while (0)
+    {
+        ST(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        ST(cudaGetDeviceProperties(&prop, device));
+        h->num_sms = prop.multiProcessorCount;
+        ST(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        ST(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SAMPLE_CAP * 8));
+        int occ = 0;
+        ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SAMPLE_CAP * 8));
+        h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
+        long long cand_cap = M + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
+        long long ntiles = (M + SCAN_THREADS - 1) / SCAN_THREADS;
+        ST(dmalloc(&dW, (size_t)M)); ST(dmalloc(&dU, 1)); ST(dmalloc(&cand, (size_t)cand_cap));
+        ST(dmalloc(&st, 1)); ST(dmalloc(&sc, 1)); ST(dmalloc(&res, 1));
+        ST(dmalloc(&tiles, (size_t)ntiles)); ST(dmalloc(&incl, (size_t)ntiles));
+        ST(dmalloc(&sp, (size_t)M)); ST(dmalloc(&ss, (size_t)M));
+        ST(cudaMemsetAsync(tiles, 0, sizeof(TileDesc) * ntiles, h->stream));
+        ST(cudaMemsetAsync(sc, 0, sizeof(SelScratch), h->stream));
+        ST(cudaMemsetAsync(res, 0, sizeof(SelResult), h->stream));
+        StepState s0; memset(&s0, 0, sizeof s0);
+        s0.n_live = M; s0.M = M;
+        ST(cudaMemcpyAsync(st, &s0, sizeof s0, cudaMemcpyHostToDevice, h->stream));
+        ST(cudaMemcpyAsync(dW, w, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
+        ST(cudaMemcpyAsync(dU, &u, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const double *Vsel = dW;
+        if (order == PF_ORDER_SORTED) {
+            // literal reference order: stable ascending sort by weight (src/fearnhead.jl:148)
+            ST(dmalloc(&keys, (size_t)M)); ST(dmalloc(&keys2, (size_t)M));
+            ST(dmalloc(&vals, (size_t)M)); ST(dmalloc(&vals2, (size_t)M));
+            int nblk = grid_for(M, RS_TILE);
+            ST(dmalloc(&hist, (size_t)256 * nblk + 256));
+            rc = radix_sort_pairs(h->stream, (const u64 *)dW, keys, keys2, vals, vals2, hist, M, &h->launches);
+            if (rc != PF_OK) { rc = set_error(nullptr, PF_ERR_CUDA, "pf_select: radix sort failed"); goto done; }
+            Vsel = (const double *)keys;           // sorted weights (bit patterns are the doubles)
+        }
+        k_vmax<<<h->num_sms * 4, 256, 0, h->stream>>>(Vsel, M, st);
+        rc = launch_select(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res);
+        if (rc != PF_OK) { g_create_error = h->err; goto done; }
+        k_scan<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, st, res, tiles, incl, sp, ss, 1u);
+        ST(cudaGetLastError());
+        StepState s1; SelResult r1;
+        ST(cudaMemcpyAsync(&s1, st, sizeof s1, cudaMemcpyDeviceToHost, h->stream));
+        ST(cudaMemcpyAsync(&r1, res, sizeof r1, cudaMemcpyDeviceToHost, h->stream));
+        ST(cudaStreamSynchronize(h->stream));
+        long long n_out = s1.n_next;
+        std::vector<unsigned int> p(n_out > 0 ? n_out : 1);
+        std::vector<unsigned char> sl(n_out > 0 ? n_out : 1);
+        if (n_out > 0) {
+            ST(cudaMemcpyAsync(p.data(), sp, sizeof(unsigned int) * n_out, cudaMemcpyDeviceToHost, h->stream));
+            ST(cudaMemcpyAsync(sl.data(), ss, n_out, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (order == PF_ORDER_SORTED) {
+            perm_host.resize(M);
+            ST(cudaMemcpyAsync(perm_host.data(), vals, sizeof(unsigned int) * M, cudaMemcpyDeviceToHost, h->stream));
+        }
+        ST(cudaStreamSynchronize(h->stream));
+        if (order == PF_ORDER_SORTED) {
+            // output order of the reference: [resampled (ascending) ; kept (ascending)], src/fearnhead.jl:172-179
+            long long k = 0;
+            for (int pass = 0; pass < 2; pass++)
+                for (long long t = 0; t < n_out; t++) {
+                    bool picked = sl[t] & 0x80;
+                    if (picked == (pass == 0)) { survivors[k] = perm_host[p[t]]; if (resampled) resampled[k] = picked; k++; }
+                }
+        } else {
+            for (long long t = 0; t < n_out; t++) { survivors[t] = p[t]; if (resampled) resampled[t] = (sl[t] & 0x80) ? 1 : 0; }
+        }
+        if (stats) {
+            memset(stats, 0, sizeof *stats);
+            stats->n_in = M; stats->n_putative = M; stats->n_kept = s1.n_kept; stats->n_resamp_req = r1.keep_all ? 0 : r1.n;
+            stats->n_resamp_got = s1.n_picked; stats->n_out = n_out; stats->log_total_w = r1.log_total;
+            stats->log_w_resamp = r1.log_c; stats->threshold = r1.thr_value; stats->resampled = r1.keep_all ? 0 : 1;
+            stats->select_rounds = r1.rounds; stats->n_candidates = r1.n_cand_first;
+        }
+    }
+done:
+#undef ST
+    if (h->stream) { cudaStreamSynchronize(h->stream); }
+    {
+        void *ptrs[] = {dW, dU, cand, st, sc, res, tiles, incl, sp, ss, keys, keys2, vals, vals2, hist};
+        for (void *p : ptrs) if (p) cudaFree(p);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    h->stream = nullptr;
+    return rc;
+}
+
+// ------------------------------------------------------------------ multi-GPU (see comm.cuh)
+extern "C" int32_t pf_comm_unique_id(void *out128)
+{
+    (void)out128;
+    return set_error(nullptr, PF_ERR_NCCL, "pf_comm_unique_id: multi-GPU sharding is not built yet");
+}
+extern "C" int32_t pf_comm_init(pf_handle h, int32_t rank, int32_t nranks, const void *id)
+{
+    (void)rank; (void)nranks; (void)id;
+    return set_error(h, PF_ERR_NCCL, "pf_comm_init: multi-GPU sharding is not built yet");
+}

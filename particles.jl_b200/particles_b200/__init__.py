@@ -1,0 +1,377 @@
+"""Host-side mirror of the Particles.jl API for the accelerated path.
+
+Julia is not available in this image, so the reference-facing host code is this Python
+module; the Julia shim with the same surface is particles.jl_b200/julia/Particles.jl.
+Names and argument meaning follow the reference (src/Particles.jl:23-56); Julia's `fit!` /
+`filter!` are spelled `fit_` / `filter_` here.  All arithmetic happens in
+libparticles_b200.so on the GPU; nothing in this module computes the filter on the CPU.
+
+    ps = FearnheadParticles(100, NormalInverseChisq(0., 1., 0.1, 1.0), ChineseRestaurantProcess(1.))
+    filter_(ps, ys)
+    assignments(ps)          # T x n matrix of 1-based component labels
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import (PF_CHENLIU, PF_FEARNHEAD, PF_NIW, PF_NIX2, PF_ORDER_INDEX, PF_ORDER_SORTED, PFError, pf_config,
+                   pf_step_stats)
+
+__all__ = ["NormalInverseChisq", "NormalInverseWishart", "ChineseRestaurantProcess", "Component",
+           "InfiniteParticle", "ParticleFilter", "FearnheadParticles", "ChenLiuParticles", "fit_", "filter_",
+           "particles", "weight", "nobs", "ncomponents", "components", "assignments", "ncomponents_dist",
+           "assignment_similarity", "randindex", "select", "PF_ORDER_INDEX", "PF_ORDER_SORTED", "PFError"]
+
+_dp = C.POINTER(C.c_double)
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+# ------------------------------------------------------------------ priors (ConjugatePriors.jl)
+class NormalInverseChisq:
+    """NormalInverseChisq(mu, sigma2, kappa, nu) (re-exported by the reference, src/Particles.jl:29)."""
+
+    def __init__(self, mu=0.0, sigma2=1.0, kappa=1.0, nu=1.0):
+        self.mu, self.sigma2, self.kappa, self.nu = float(mu), float(sigma2), float(kappa), float(nu)
+        self.dim = 1
+
+    def params(self):
+        return self.mu, self.sigma2, self.kappa, self.nu
+
+
+class NormalInverseWishart:
+    """NormalInverseWishart(mu, kappa, Lambda, nu) (ConjugatePriors; used by bench/2d.jl:18)."""
+
+    def __init__(self, mu, kappa, Lam, nu):
+        self.mu = np.atleast_1d(np.asarray(mu, dtype=np.float64)).copy()
+        self.dim = len(self.mu)
+        self.kappa, self.nu = float(kappa), float(nu)
+        self.Lam = np.asarray(Lam, dtype=np.float64).reshape(self.dim, self.dim).copy()
+
+
+class ChineseRestaurantProcess:
+    """ChineseRestaurantProcess(alpha) (src/statepriors.jl:47-52)."""
+
+    def __init__(self, alpha, N=None):
+        self.alpha = float(alpha)
+        self.N = np.zeros(0) if N is None else np.asarray(N, dtype=np.float64)
+
+
+class Component:
+    """A cluster: prior + posterior statistics read back from the device store
+    (src/component.jl:1-4).  `n` = nobs, `mean` = sample mean, `chol` = lower Cholesky factor
+    of the posterior scale Lambda_n, from which the reference's suffstats follow."""
+
+    def __init__(self, prior, n=0, mean=None, chol=None, logdet=None):
+        self.prior, self.n = prior, int(n)
+        self.mean, self.chol, self.logdet = mean, chol, logdet
+
+    def nobs(self):
+        return self.n
+
+    def isempty(self):
+        return self.n == 0
+
+    def params(self):
+        """params(posterior_canon(prior, suffstats)) (src/component.jl:28)."""
+        p = self.prior
+        if self.n == 0:
+            return p.params() if isinstance(p, NormalInverseChisq) else (p.mu, p.Lam, p.kappa, p.nu)
+        kn, nn = p.kappa + self.n, p.nu + self.n
+        if isinstance(p, NormalInverseChisq):
+            mun = (p.kappa * p.mu + self.n * self.mean[0]) / kn
+            return mun, self.chol[0, 0] ** 2 / nn, kn, nn
+        mun = (p.kappa * p.mu + self.n * self.mean) / kn
+        return mun, self.chol @ self.chol.T, kn, nn
+
+
+class InfiniteParticle:
+    """Lazy view of one particle of a device-resident population (src/particle.jl:38-45)."""
+
+    def __init__(self, ps, i, logweight, K):
+        self._ps, self._i = ps, i
+        self.logweight = float(logweight)
+        self.K = int(K)
+        self._comps = None
+
+    @property
+    def weight(self):
+        return math.exp(self.logweight)
+
+    @property
+    def components(self):
+        if self._comps is None:
+            self._comps = self._ps._read_particle(self._i)
+        return self._comps
+
+    @property
+    def stateprior(self):
+        return ChineseRestaurantProcess(self._ps.stateprior.alpha, [c.n for c in self.components])
+
+
+# ------------------------------------------------------------------ filters
+class ParticleFilter:
+    """abstract type ParticleFilter (src/filters.jl:4) over a device-resident population."""
+
+    _kind = None
+
+    def __init__(self, n, prior, stateprior, *, k_max=16, order=PF_ORDER_INDEX, history=0, device=0, seed=0,
+                 rejuv=50.0):
+        if isinstance(prior, tuple):
+            prior = NormalInverseChisq(*prior)                      # Component(params::NTuple), src/component.jl:8
+        if not isinstance(stateprior, ChineseRestaurantProcess):
+            raise ValueError("only ChineseRestaurantProcess state priors are on the accelerated path")
+        self.N, self.prior, self.stateprior = int(n), prior, stateprior
+        self.k_max, self.order, self.history = int(k_max), order, int(history)
+        self.rejuvination_threshold = float(rejuv)
+        L = _lib.load()
+        cfg = pf_config()
+        cfg.filter_kind = self._kind
+        cfg.precision = 0
+        cfg.n_particles = self.N
+        cfg.k_max = self.k_max
+        cfg.order = order
+        cfg.history = self.history
+        cfg.device = device
+        cfg.alpha = stateprior.alpha
+        cfg.rejuv_threshold = self.rejuvination_threshold
+        cfg.seed = seed
+        if isinstance(prior, NormalInverseChisq):
+            cfg.prior_kind, cfg.d = PF_NIX2, 1
+            self._mu0 = np.array([prior.mu])
+            self._lam0 = np.zeros((1, 1))
+            cfg.kappa0, cfg.nu0, cfg.sigma2_0 = prior.kappa, prior.nu, prior.sigma2
+        elif isinstance(prior, NormalInverseWishart):
+            cfg.prior_kind, cfg.d = PF_NIW, prior.dim
+            self._mu0 = prior.mu.copy()
+            self._lam0 = np.asfortranarray(prior.Lam)
+            cfg.kappa0, cfg.nu0, cfg.sigma2_0 = prior.kappa, prior.nu, 0.0
+        else:
+            raise ValueError("prior must be NormalInverseChisq or NormalInverseWishart")
+        self.d = cfg.d
+        cfg.mu0 = self._mu0.ctypes.data_as(_dp)
+        cfg.lambda0 = self._lam0.ctypes.data_as(_dp)
+        h = C.c_void_p()
+        _lib.check(L.pf_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._L = L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- stepping
+    def fit_(self, y, uniforms=None):
+        """fit!(ps, y) (src/fearnhead.jl:130, src/chenliu.jl:54)."""
+        y, py = _d(np.atleast_1d(y))
+        if len(y) != self.d:
+            raise ValueError(f"observation has {len(y)} entries, the prior has dimension {self.d}")
+        if uniforms is None:
+            _lib.check(self._L.pf_step(self._h, py, None, 0), self._h)
+        else:
+            u, pu = _d(np.atleast_1d(uniforms))
+            _lib.check(self._L.pf_step(self._h, py, pu, len(u)), self._h)
+        return self
+
+    def filter_(self, ys, progress=False, cb=None, uniforms=None):
+        """filter!(ps, ys, progress; cb) (src/filters.jl:6-13).  Without a callback the whole
+        stream is one library call; with one, the callback sees the filter after every y."""
+        ys = np.asarray(ys, dtype=np.float64)
+        if ys.ndim == 1 and self.d == 1:
+            ys = ys.reshape(-1, 1)
+        if ys.ndim != 2 or ys.shape[1] != self.d:
+            raise ValueError(f"ys must be T x {self.d}")
+        T = ys.shape[0]
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(T, -1)
+        if cb is not None:
+            for t in range(T):
+                self.fit_(ys[t], None if uniforms is None else uniforms[t])
+                cb(self, ys[t])
+            return self
+        ysc, pys = _d(ys)                    # row t = observation t == column-major d x T
+        le = np.empty(T)
+        if uniforms is None:
+            _lib.check(self._L.pf_filter(self._h, pys, T, None, 0, le.ctypes.data_as(_dp)), self._h)
+        else:
+            _lib.check(self._L.pf_filter(self._h, pys, T, uniforms.ctypes.data_as(_dp), uniforms.shape[1],
+                                         le.ctypes.data_as(_dp)), self._h)
+        self.log_evidence = le
+        return self
+
+    # --- read-out
+    def __len__(self):
+        return int(self._L.pf_n_particles(self._h))
+
+    @property
+    def n_steps(self):
+        return int(self._L.pf_n_steps(self._h))
+
+    def logweights(self):
+        out = np.empty(len(self))
+        _lib.check(self._L.pf_get_logweights(self._h, out.ctypes.data_as(_dp)), self._h)
+        return out
+
+    def weights(self):
+        return np.exp(self.logweights())
+
+    def ncomponents(self):
+        out = np.empty(len(self), dtype=np.int32)
+        _lib.check(self._L.pf_get_ncomponents(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
+        return out
+
+    def _read_particle(self, i):
+        d, km = self.d, self.k_max
+        K = C.c_int32()
+        counts, means = np.empty(km), np.empty((km, d))
+        chol, logdet = np.empty((km, d, d)), np.empty(km)
+        _lib.check(self._L.pf_get_particle(self._h, i, C.byref(K), counts.ctypes.data_as(_dp),
+                                           means.ctypes.data_as(_dp), chol.ctypes.data_as(_dp),
+                                           logdet.ctypes.data_as(_dp)), self._h)
+        return [Component(self.prior, counts[j], means[j].copy(), chol[j].T.copy(), logdet[j])
+                for j in range(K.value)]
+
+    def particles(self):
+        """particles(ps) (src/filters.jl:15)."""
+        lw, K = self.logweights(), self.ncomponents()
+        return [InfiniteParticle(self, i, lw[i], K[i]) for i in range(len(self))]
+
+    def assignments(self):
+        """assignments(ps) (src/filters.jl:26-34): T x n matrix, 1-based labels."""
+        T, n = self.n_steps, len(self)
+        out = np.empty((n, T), dtype=np.int32)
+        _lib.check(self._L.pf_get_assignments(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
+        return out.T.astype(np.int64) + 1
+
+    def last_step(self):
+        s = pf_step_stats()
+        _lib.check(self._L.pf_get_last_step(self._h, C.byref(s)), self._h)
+        return s.asdict()
+
+    def putative_weights(self):
+        M = C.c_int64()
+        cap = len(self) * (self.k_max + 1) + self.N * (self.k_max + 1)
+        out = np.empty(cap)
+        _lib.check(self._L.pf_get_putative_weights(self._h, out.ctypes.data_as(_dp), cap, C.byref(M)), self._h)
+        return out[:M.value].copy()
+
+    def last_ancestors(self):
+        out = np.empty(len(self), dtype=np.int32)
+        _lib.check(self._L.pf_get_last_ancestors(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
+        return out
+
+    def last_assignments(self):
+        out = np.empty(len(self), dtype=np.int32)
+        _lib.check(self._L.pf_get_last_assignments(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
+        return out
+
+    def timing(self):
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self._L.pf_last_timing(self._h, C.byref(ms), C.byref(n)), self._h)
+        return ms.value, n.value
+
+
+class FearnheadParticles(ParticleFilter):
+    """FearnheadParticles(n, prior, stateprior) (src/fearnhead.jl:13-30)."""
+    _kind = PF_FEARNHEAD
+
+
+class ChenLiuParticles(ParticleFilter):
+    """ChenLiuParticles(n, prior, stateprior; rejuv=50.) (src/chenliu.jl:7-26)."""
+    _kind = PF_CHENLIU
+
+
+# ------------------------------------------------------------------ generic functions
+def fit_(ps, y, uniforms=None):
+    return ps.fit_(y, uniforms)
+
+
+def filter_(ps, ys, progress=False, cb=None, uniforms=None):
+    return ps.filter_(ys, progress, cb, uniforms)
+
+
+def particles(ps):
+    return ps.particles()
+
+
+def weight(p):
+    return p.weight
+
+
+def components(p):
+    return p.components
+
+
+def ncomponents(p):
+    return p.K
+
+
+def nobs(x):
+    return x.nobs() if isinstance(x, Component) else sum(c.n for c in x.components)
+
+
+def assignments(ps):
+    return ps.assignments()
+
+
+def ncomponents_dist(ps):
+    """ncomponents_dist(ps) (src/filters.jl:36-37): weighted distribution of K."""
+    K, w = ps.ncomponents(), ps.weights()
+    p = np.bincount(K, weights=w / w.sum())
+    return p
+
+
+def assignment_similarity(ps):
+    """assignment_similarity(ps) (src/filters.jl:39-42): 1 - Hamming distance between rows."""
+    a = ps.assignments()
+    T = a.shape[0]
+    out = np.empty((T, T))
+    for t in range(T):
+        out[t] = (a == a[t]).mean(axis=1)
+    return out
+
+
+def randindex(ps, truth, kind="adjusted"):
+    """randindex(ps, truth, type) (src/filters.jl:53-80)."""
+    truth = np.asarray(truth)
+    ps_sim = assignment_similarity(ps)
+    truth_sim = (truth[:, None] == truth[None, :]).astype(np.float64)
+    if truth_sim.shape != ps_sim.shape:
+        raise ValueError("Ground truth and particles have different number of obs!")   # DimensionMismatch
+    Np = ps_sim.size
+    nis, njs = ps_sim.sum(), truth_sim.sum()
+    both_same = (ps_sim * truth_sim).sum()
+    both_diff = Np - nis - njs + both_same
+    if kind == "adjusted":
+        n = len(truth)
+        nc = (n * (n ** 2 + 1) - (n + 1) * nis - (n + 1) * njs + 2 * (nis * njs) / n) / (2 * (n - 1))
+        return (both_same + both_diff - nc) / (Np - nc)
+    return (both_same + both_diff) / Np
+
+
+def select(w, N, u, order=PF_ORDER_INDEX, device=0):
+    """Fearnhead-Clifford selection (cutoff_ascending + sample_stratified!, src/fearnhead.jl:59-114)
+    on given weights, on the GPU.  Returns (survivors, resampled_flag, stats)."""
+    L = _lib.load()
+    w, pw = _d(w)
+    surv = np.empty(max(int(N), 1) + 1, dtype=np.int64)
+    flag = np.empty(max(int(N), 1) + 1, dtype=np.uint8)
+    st = pf_step_stats()
+    _lib.check(L.pf_select(device, pw, len(w), int(N), float(u), order, surv.ctypes.data_as(C.POINTER(C.c_int64)),
+                           flag.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st)))
+    n = st.n_out
+    return surv[:n].copy(), flag[:n].astype(bool), st.asdict()
