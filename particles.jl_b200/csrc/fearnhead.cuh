@@ -13,7 +13,7 @@ struct StepState {
     long long step;         // observations consumed so far
     u64 vmax_bits;          // max putative weight (bit pattern)
     unsigned int ticket;    // tile ticket of k_scan
-    unsigned int pad;
+    unsigned int ticket2;   // tile ticket of the second k_scan of a sorted-order step
     long long n_picked;     // resampled survivors
     long long n_kept;       // kept survivors
 };
@@ -35,7 +35,7 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
     using L = Layout<D>;
     if (!first) st->n_live = st->n_next;
     st->n_next = 0;
-    st->M = 0; st->vmax_bits = 0; st->ticket = 0; st->n_picked = 0; st->n_kept = 0;
+    st->M = 0; st->vmax_bits = 0; st->ticket = 0; st->ticket2 = 0; st->n_picked = 0; st->n_kept = 0;
     StepConst c;
     double dx[D], z[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1];
 #pragma unroll
@@ -162,16 +162,22 @@ __device__ __forceinline__ unsigned int ld_vu32(const unsigned int *p) { return 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
                                                        long long cap, StepState *st, const SelResult *__restrict__ res,
                                                        TileDesc *tiles, TileIncl *incl, unsigned int *__restrict__ surv_parent,
-                                                       unsigned char *__restrict__ surv_slot, unsigned int epoch)
+                                                       unsigned char *__restrict__ surv_slot, unsigned int epoch,
+                                                       const long long *n_items_ptr, unsigned int *ticket, int mode)
 {
+    // mode 0: index-order filter step (always runs); mode 1: flat sorted list, runs only when
+    // the step resamples, writes the PICKED positions only (kept = suffix of the sorted list);
+    // mode 2: index-order pass of a sorted-order filter, runs only when the step keeps all.
+    if (mode == 1 && res->keep_all) return;
+    if (mode == 2 && !res->keep_all) return;
     __shared__ u128 s_warp[33];
     __shared__ unsigned int s_wc[33];
     __shared__ unsigned int s_tile;
     __shared__ u128 s_preX;
     __shared__ unsigned int s_preK, s_preP;
-    const long long n_live = st->n_live;
+    const long long n_live = *n_items_ptr;
     const long long ntiles = (n_live + SCAN_THREADS - 1) / SCAN_THREADS;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket, 1u);
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned int tile = s_tile;
     if (tile >= ntiles) return;
@@ -303,10 +309,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const double *__restrict_
     __syncthreads();
     // write survivors in index order
     if (c > 0) {
-        long long pos = (long long)s_preK + exK + (long long)s_preP + exP;
+        long long pos = (mode == 1) ? (long long)s_preP + exP : (long long)s_preK + exK + (long long)s_preP + exP;
         for (int j = 0; j < c; j++) {
             u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
-            bool kept = bits >= thr;
+            bool kept = (mode == 1) ? false : bits >= thr;
             bool picked = (pickmask >> j) & 1ull;
             if (kept || picked) {
                 surv_parent[pos] = (unsigned int)i;
@@ -386,6 +392,39 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
 #pragma unroll
         for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = scp->newslot[f];
     }
+}
+
+// ------------------------------------------------------------------ reference-literal order
+// flat (particle-major, candidate-minor) key list; dead slots and dead particles get the
+// all-ones pattern so that a stable ascending sort leaves the M live putatives first, ties
+// in putative-index order (the declared tie-break of sort!, src/fearnhead.jl:148).
+__global__ void k_flat_keys(const double *__restrict__ V, const unsigned char *__restrict__ cnt, long long cap,
+                            const StepState *__restrict__ st, int slots, long long n_pad, u64 *__restrict__ keys)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pad) return;
+    long long i = k / slots;
+    int j = (int)(k - i * slots);
+    u64 key = ~0ull;
+    if (i < st->n_live && j < cnt[i]) key = (u64)__double_as_longlong(V[(long long)j * cap + i]);
+    keys[k] = key;
+}
+
+// survivors of a sorted-order step in the reference's output order
+// [resampled (ascending weight) ; kept (ascending weight)] (src/fearnhead.jl:172-179)
+__global__ void k_sorted_finalize(const StepState *__restrict__ st, const SelResult *__restrict__ res,
+                                  const unsigned int *__restrict__ pick_pos, const unsigned int *__restrict__ vals, int slots,
+                                  unsigned int *__restrict__ surv_parent, unsigned char *__restrict__ surv_slot)
+{
+    if (res->keep_all) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= st->n_next) return;
+    const long long np = st->n_picked;
+    const bool picked = t < np;
+    const long long flat = picked ? (long long)pick_pos[t] : (st->M - res->A) + (t - np);
+    const unsigned int code = vals[flat];
+    surv_parent[t] = code / (unsigned int)slots;
+    surv_slot[t] = (unsigned char)((code % (unsigned int)slots) | (picked ? 0x80 : 0));
 }
 
 // fill the per-step log record (one thread)

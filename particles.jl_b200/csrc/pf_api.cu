@@ -48,6 +48,9 @@ struct pf_filter_s {
     long long slog_cap = 0;
     double *ys_dev = nullptr, *u_dev = nullptr;
     long long ys_cap = 0, u_cap = 0;
+    // reference-literal order scratch
+    u64 *keys = nullptr, *keys2 = nullptr;
+    unsigned int *vals = nullptr, *vals2 = nullptr, *hist = nullptr, *pick_pos = nullptr;
     // Chen-Liu scratch
     ClState *cl = nullptr;
     double *W = nullptr;
@@ -158,7 +161,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->incl, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
-                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part};
+                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -228,6 +231,14 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->surv_parent, cap));
     CT(dmalloc(&h->surv_slot, cap));
     long long ntiles = (cap + SCAN_THREADS - 1) / SCAN_THREADS;
+    if (cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_SORTED) {
+        const long long n_pad = cap * (h->k_max + 1);
+        ntiles = (n_pad + SCAN_THREADS - 1) / SCAN_THREADS;
+        CT(dmalloc(&h->keys, (size_t)n_pad)); CT(dmalloc(&h->keys2, (size_t)n_pad));
+        CT(dmalloc(&h->vals, (size_t)n_pad)); CT(dmalloc(&h->vals2, (size_t)n_pad));
+        CT(dmalloc(&h->hist, (size_t)256 * ((n_pad + RS_TILE - 1) / RS_TILE) + 256));
+        CT(dmalloc(&h->pick_pos, (size_t)cap));
+    }
     CT(dmalloc(&h->tiles, ntiles));
     CT(dmalloc(&h->incl, ntiles));
     CT(cudaMemsetAsync(h->tiles, 0, sizeof(TileDesc) * ntiles, h->stream));
@@ -329,8 +340,29 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
                                h->cand_cap, h->sc, h->res);
     if (rc != PF_OK) return rc;
-    k_scan<<<grid_for(ub, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->st, h->res, h->tiles, h->incl,
-                                                                         h->surv_parent, h->surv_slot, h->epoch);
+    if (h->cfg.order == PF_ORDER_SORTED) {
+        const int slots = h->k_max + 1;
+        const long long n_pad = ub * slots;
+        k_flat_keys<<<grid_for(n_pad, 256), 256, 0, h->stream>>>(h->V, h->cnt, cap, h->st, slots, n_pad, h->keys2);
+        h->launches++;
+        if (radix_sort_pairs(h->stream, h->keys2, h->keys, h->keys2, h->vals, h->vals2, h->hist, n_pad, &h->launches))
+            return set_error(h, PF_ERR_CUDA, "radix sort launch failed");
+        // resampling step: comb over the sorted list; exhaustive step: index order
+        k_scan<<<grid_for(n_pad, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->st, h->res,
+                                                                                h->tiles, h->incl, h->pick_pos, h->surv_slot, h->epoch,
+                                                                                &h->st->M, &h->st->ticket, 1);
+        k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
+                                                                           h->surv_slot);
+        h->epoch++;
+        k_scan<<<grid_for(ub, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->st, h->res, h->tiles, h->incl,
+                                                                             h->surv_parent, h->surv_slot, h->epoch, &h->st->n_live,
+                                                                             &h->st->ticket2, 2);
+        h->launches += 2;
+    } else {
+        k_scan<<<grid_for(ub, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->st, h->res, h->tiles, h->incl,
+                                                                             h->surv_parent, h->surv_slot, h->epoch, &h->st->n_live,
+                                                                             &h->st->ticket, 0);
+    }
     k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                       h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
                                                                       h->surv_slot, ga, gs);
@@ -663,6 +695,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         ST(cudaMemcpyAsync(dW, w, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
         ST(cudaMemcpyAsync(dU, &u, sizeof(double), cudaMemcpyHostToDevice, h->stream));
         const double *Vsel = dW;
+        if (M <= N) order = PF_ORDER_INDEX;          // exhaustive step: no sort (src/fearnhead.jl:135-138)
         if (order == PF_ORDER_SORTED) {
             // literal reference order: stable ascending sort by weight (src/fearnhead.jl:148)
             ST(dmalloc(&keys, (size_t)M)); ST(dmalloc(&keys2, (size_t)M));
@@ -676,7 +709,8 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         k_vmax<<<h->num_sms * 4, 256, 0, h->stream>>>(Vsel, M, st);
         rc = launch_select(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res);
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
-        k_scan<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, st, res, tiles, incl, sp, ss, 1u);
+        k_scan<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, st, res, tiles, incl, sp, ss, 1u, &st->n_live,
+                                                                            &st->ticket, 0);
         ST(cudaGetLastError());
         StepState s1; SelResult r1;
         ST(cudaMemcpyAsync(&s1, st, sizeof s1, cudaMemcpyDeviceToHost, h->stream));

