@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- particle-observation updates/s of the Fearnhead 2-D NIW filter (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...      # the CPU restatement arm
+
+A "step" is one observation filtered through the whole particle population
+(fit!(ps, y), src/fearnhead.jl:130-184), i.e. N particle-observation updates.  The
+workload is BASELINE.json configs[3] (the configuration the metric is quoted on): 2-D
+NormalInverseWishart(0, 0.1, I, 3) prior, CRP(1), synthetic 8-cluster Gaussian mixture on a
+circle of radius 6, 2^24 particles in total (strong scaling over the GPUs).  The population
+is first brought to steady state (burn-in observations, untimed: the exhaustive phase and
+the growth of the cluster count), then W warm-up steps, then EXACTLY K timed steps.
+
+value  : device time of the K steps (CUDA events on the library's stream, max over ranks),
+         state resident in HBM.
+e2e    : the same K steps through the public host API (FearnheadParticles.filter_) with
+         host (numpy) observation / uniform buffers: H2D copies of the inputs and the D2H
+         read of the per-step results (log-evidence, counts) are inside the timed region.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "particles.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "particle_obs_updates_per_sec"
+UNIT = "updates/s"
+D = 2
+K_MAX = 16
+
+
+def mixture(rng, T, k=8, radius=6.0):
+    ang = 2 * np.pi * rng.integers(0, k, T) / k
+    return radius * np.stack([np.cos(ang), np.sin(ang)], axis=1) + rng.standard_normal((T, 2))
+
+
+def rec_bytes(d):
+    return 8 * (2 + d + d * (d + 1) // 2)
+
+
+def bytes_per_update(kbar, d=D):
+    """Algorithmic bytes of one Fearnhead particle-observation update:
+    B_F = (3 Kbar + 1) b + 16 Kbar + 53."""
+    b = rec_bytes(d)
+    return (3 * kbar + 1) * b + 16 * kbar + 53
+
+
+def kernel_bytes(kbar, d=D):
+    """Algorithmic bytes per particle of each kernel of the step."""
+    b = rec_bytes(d)
+    return {
+        "expand": kbar * b + 16 + 8 * (kbar + 1),          # read live slots + header, write putative weights
+        "select": 8 * (kbar + 1),                          # read putative weights once
+        "scan": 8 * (kbar + 1) + 5,                        # read putative weights, write survivor codes
+        "instantiate": kbar * b + 8 + 5 + (kbar + 1) * b + 16 + 5,   # gather parent, write child + header + genealogy
+    }
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag = device, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = float(s[1])
+                for nm, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_leg(n_cpu, burn, timed, seed=100):
+    """The reference's CPU path (the literal C restatement in oracle/, 1 thread because
+    the reference is single-threaded) on a bounded sample of the same workload."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(seed)
+    ys = mixture(rng, burn + timed)
+    us = rng.random(burn + timed)
+    f = orc.OracleFilter(orc.FEARNHEAD, n_cpu, orc.Prior.niw(np.zeros(2), 0.1, np.eye(2), 3.0), 1.0,
+                         order=orc.ORDER_SORTED, keep_history=False)
+    for t in range(burn):
+        f.fh_step(ys[t], us[t])
+    t0 = time.perf_counter()
+    for t in range(burn, burn + timed):
+        f.fh_step(ys[t], us[t])
+    dt = time.perf_counter() - t0
+    kbar = float(f.ncomponents().mean())
+    return {"value": n_cpu * timed / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_cpu} particles x {timed} observations after {burn} burn-in (same model and data stream), "
+                      f"literal C restatement of src/fearnhead.jl (sort + 2 mll per putative), mean K {kbar:.2f}",
+            "seconds": dt}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--log2n", type=int, default=24, help="log2 of the TOTAL particle budget")
+    ap.add_argument("--burnin", type=int, default=96)
+    ap.add_argument("--cpu-n", type=int, default=16384)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--order", default="index", choices=["index", "sorted"])
+    a = ap.parse_args()
+    K, W = a.steps, max(a.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    N = 1 << a.log2n
+    config = {"workload": f"2-D NIW Fearnhead filter, 2^{a.log2n} particles, 8-cluster synthetic mixture "
+                          f"(BASELINE configs[3]); inputs >> L2 (particle store {N * 8 * rec_bytes(D) / 1e9:.1f} GB at K=8)",
+              "n_particles": N, "d": D, "k_max": K_MAX, "prior": "NIW(0, 0.1, I, 3)", "alpha": 1.0,
+              "burnin_obs": a.burnin, "order": a.order, "sharding": f"particles block-sharded over {a.gpus} GPU(s)",
+              "l2_policy": "inputs larger than L2"}
+
+    # ---------------------------------------------------------------- reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_leg(a.cpu_n, 48, max(K, 1) * 2)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": K,
+                "warmup": W, "ms_per_step": 1e3 * cb["seconds"] / (max(K, 1) * 2), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "Julia is not installed in this image: the reference arm is the literal C restatement "
+                        "(oracle/particles_oracle.c), single-threaded like the reference"}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- this repo's arm
+    import particles_b200 as pb
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    if world > 1:
+        # multi-GPU sharding is wired through pf_comm_init; see DESIGN.md section 6
+        raise SystemExit("bench.py: --gpus > 1 needs the sharded path (pf_comm_init), not built in this round")
+
+    rng = np.random.default_rng(100)
+    T_all = a.burnin + W + 3 * K
+    ys = mixture(rng, T_all)
+    us = rng.random(T_all)
+    order = pb.PF_ORDER_INDEX if a.order == "index" else pb.PF_ORDER_SORTED
+    ps = pb.FearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
+                               pb.ChineseRestaurantProcess(1.0), k_max=K_MAX, history=T_all, device=local, order=order)
+    o = 0
+    ps.filter_(ys[o:o + a.burnin], uniforms=us[o:o + a.burnin]); o += a.burnin
+    if W:
+        ps.filter_(ys[o:o + W], uniforms=us[o:o + W]); o += W
+    kbar0 = float(ps.ncomponents().mean())
+    n_live0 = len(ps)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # (1) device-timed K steps
+    ps.filter_(ys[o:o + K], uniforms=us[o:o + K]); o += K
+    dev_ms, launches = ps.timing()
+    # (2) end to end through the public API with host buffers
+    t0 = time.perf_counter()
+    ps.filter_(ys[o:o + K], uniforms=us[o:o + K])
+    le = ps.log_evidence.copy()
+    e2e_s = time.perf_counter() - t0
+    o += K
+    # (3) per-kernel CUDA-event times over K more steps
+    ps.set_profiling(True)
+    ps.filter_(ys[o:o + K], uniforms=us[o:o + K]); o += K
+    prof_ms, _ = ps.timing()
+    kt = ps.kernel_times()
+    ps.set_profiling(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    kbar1 = float(ps.ncomponents().mean())
+    kbar = 0.5 * (kbar0 + kbar1)
+    stats = ps.last_step()
+
+    value = n_live0 * K / (dev_ms / 1e3)
+    e2e = n_live0 * K / e2e_s
+    peak, peak_src = peaks()
+    kb = kernel_bytes(kbar)
+    per_kernel = {}
+    for name in ("expand", "select", "scan", "instantiate"):
+        ms, n = kt[name]
+        if n:
+            avg = ms / n
+            per_kernel[name] = {"avg_ms": avg, "share": ms / prof_ms, "alg_bytes_per_launch": kb[name] * n_live0,
+                                "achieved_gbs": kb[name] * n_live0 / (avg * 1e-3) / 1e9}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
+    roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": per_kernel[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "avg_launch_ms": per_kernel[dom]["avg_ms"], "share_of_step": per_kernel[dom]["share"],
+            "algorithmic_bytes_per_update": kb[dom], "per_kernel": per_kernel,
+            "whole_step": {"algorithmic_bytes_per_update": bytes_per_update(kbar),
+                           "achieved": bytes_per_update(kbar) * value / 1e9, "frac": bytes_per_update(kbar) * value / 1e9 / peak,
+                           "frac_of_nominal_8tbs": bytes_per_update(kbar) * value / 1e9 / 8000.0}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n_live0,
+                                                select_rounds_last=stats["select_rounds"], candidates_last=stats["n_candidates"],
+                                                select_phase_us_last=stats["select_phase_us"]),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
+                    "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le[-1])},
+            "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}
+    if not a.no_cpu:
+        cb = cpu_leg(a.cpu_n, 48, a.cpu_steps)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

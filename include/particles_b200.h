@@ -84,6 +84,7 @@ typedef struct {
     int32_t resampled;        /* Fearnhead: M > N ; Chen-Liu: cv > threshold */
     int32_t select_rounds;    /* bracket rounds the threshold search needed */
     int64_t n_candidates;     /* putatives inside the first bracket */
+    double select_phase_us[4]; /* threshold search: bracket, classify pass(es), descent + solve, total */
 } pf_step_stats;
 
 /* ---- life cycle ---------------------------------------------------------------------- */
@@ -153,6 +154,14 @@ int32_t pf_comm_unique_id(void *out128);
 /* Device milliseconds (CUDA events on the handle's stream) and kernel launches of the last
  * pf_filter / pf_step call. */
 int32_t pf_last_timing(pf_handle h, double *device_ms, int64_t *kernel_launches);
+/* Per-kernel-class device times: when profiling is on, every launch of the step sequence is
+ * bracketed by CUDA events on the handle's stream; times accumulate until the next
+ * pf_set_profiling call.  Classes: 0 prestep, 1 expand, 2 select, 3 scan, 4 instantiate,
+ * 5 steplog, 6 sort, 7 cl_propagate, 8 cl_stats, 9 cl_finish. */
+#define PF_KERNEL_CLASSES 10
+int32_t pf_set_profiling(pf_handle h, int32_t on);
+int32_t pf_get_kernel_times(pf_handle h, double *ms /* [PF_KERNEL_CLASSES] */, int64_t *launches /* [PF_KERNEL_CLASSES] */);
+const char *pf_kernel_class_name(int32_t k);
 /* Raw stream pointer (cudaStream_t) so that a host program can order its own work. */
 void *pf_stream(pf_handle h);
 const char *pf_version(void);

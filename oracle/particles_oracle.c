@@ -311,7 +311,8 @@ void orc_destroy(orc_filter *f)
     if (!f) return;
     pop_free(f->pop, f->n);
     free(f->put); free(f->upd_pool);
-    for (int t = 0; t < f->T; t++) { free(f->gens[t].anc); free(f->gens[t].asg); }
+    if (f->keep_history)
+        for (int t = 0; t < f->T; t++) { free(f->gens[t].anc); free(f->gens[t].asg); }
     free(f->gens);
     free(f);
 }

@@ -80,6 +80,36 @@ __host__ __device__ __forceinline__ u128 fx128(u64 bits, int s)
     if (sh <= -64) return mk128(0, 0);
     return mk128(m >> (-sh), 0);
 }
+// Fast path of fx128 for callers that guarantee v * 2^s < 2^71 (shift of the 53-bit mantissa
+// by at most 18 to the left): the hot loops of the threshold search and the survivor scan.
+__host__ __device__ __forceinline__ u128 fx70(u64 bits, int s)
+{
+    int e = (int)(bits >> 52);                      // sign bit is 0 for weights
+    u64 m = bits & 0x000FFFFFFFFFFFFFull;
+    if (e == 0) e = 1; else m |= 0x0010000000000000ull;
+    const int sh = e - 1075 + s;
+    u128 r;
+    if (sh > 0) { r.lo = m << sh; r.hi = m >> (64 - sh); }
+    else { r.lo = sh > -64 ? m >> (-sh) : 0ull; r.hi = 0ull; }
+    return r;
+}
+
+// a / n and a % n for a 128-bit a and a 32-bit n > 0 (schoolbook, 32-bit digits)
+__host__ __device__ __forceinline__ u128 divmod128_32(u128 a, unsigned int n, unsigned int *rem)
+{
+    unsigned int d[4] = {(unsigned int)(a.hi >> 32), (unsigned int)a.hi, (unsigned int)(a.lo >> 32), (unsigned int)a.lo};
+    unsigned int q[4];
+    u64 r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u64 cur = (r << 32) | d[k];
+        q[k] = (unsigned int)(cur / n);
+        r = cur % n;
+    }
+    *rem = (unsigned int)r;
+    return mk128(((u64)q[2] << 32) | q[3], ((u64)q[0] << 32) | q[1]);
+}
+
 // unbiased exponent E with 2^E <= v < 2^(E+1) (subnormals: -1022)
 __host__ __device__ __forceinline__ int exp_of_bits(u64 bits)
 {

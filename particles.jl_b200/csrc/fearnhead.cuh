@@ -12,8 +12,8 @@ struct StepState {
     long long overflow;     // cumulative dropped new-cluster candidates
     long long step;         // observations consumed so far
     u64 vmax_bits;          // max putative weight (bit pattern)
-    unsigned int ticket;    // tile ticket of k_scan
-    unsigned int ticket2;   // tile ticket of the second k_scan of a sorted-order step
+    unsigned int ticket;    // (unused)
+    unsigned int ticket2;
     long long n_picked;     // resampled survivors
     long long n_kept;       // kept survivors
 };
@@ -22,6 +22,7 @@ struct StepLog {            // one record per step, read back after pf_filter
     long long n_in, M, n_kept, n_req, n_got, n_out, overflow, n_cand;
     double log_total, lw_resamp, thr, cv;
     int resampled, rounds;
+    double sel_us[4];
 };
 
 // ------------------------------------------------------------------ k_prestep
@@ -86,21 +87,28 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
         for (int k = 0; k < D; k++) { y[k] = scp->y[k]; mu0[k] = pc->mu0[k]; }
         const int K = Kc[i];
         const double lw0 = logw[i];
+        // software pipeline: the fields of slot j+1 are in flight while slot j is evaluated
+        double fcur[L::F], fnxt[L::F];
+        if (K > 0) {
+            const double *base = S + i;
+#pragma unroll
+            for (int f = 0; f < L::F; f++) fcur[f] = base[(long long)f * cap];
+        }
         for (int j = 0; j < K; j++) {
-            const double *base = S + ((long long)j * L::F) * cap + i;
-            double n = base[(long long)L::F_N * cap];
-            double logdet = base[(long long)L::F_LOGDET * cap];
-            double m[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1], z[D], q;
+            if (j + 1 < K) {
+                const double *base = S + ((long long)(j + 1) * L::F) * cap + i;
 #pragma unroll
-            for (int k = 0; k < D; k++) { m[k] = base[(long long)(L::F_MEAN + k) * cap]; dinv[k] = base[(long long)(L::F_DINV + k) * cap]; }
-#pragma unroll
-            for (int k = 0; k < L::NOFF; k++) off[k] = base[(long long)(L::F_OFF + k) * cap];
-            const NRow row = tab[(int)n];
-            double lw = lw0 + slot_logw<D>(row, logdet, m, dinv, off, y, mu0, z, &q);
+                for (int f = 0; f < L::F; f++) fnxt[f] = base[(long long)f * cap];
+            }
+            double z[D], q;
+            const NRow row = tab[(int)fcur[L::F_N]];
+            double lw = lw0 + slot_logw<D>(row, fcur[L::F_LOGDET], fcur + L::F_MEAN, fcur + L::F_DINV, fcur + L::F_OFF, y, mu0, z, &q);
             double v = exp(lw);
             V[(long long)j * cap + i] = v;
             u64 b = (u64)__double_as_longlong(v);
             vmax = b > vmax ? b : vmax;
+#pragma unroll
+            for (int f = 0; f < L::F; f++) fcur[f] = fnxt[f];
         }
         int c = K;
         if (K < k_max) {
@@ -130,75 +138,125 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
     }
 }
 
-// ------------------------------------------------------------------ k_scan
-// Single pass over the putatives in (particle, slot) order with two decoupled look-back
-// chains: (1) the running fixed-point mass X = n * sum(q) of the low partition plus the
-// number kept, (2) the number picked.  Item picked <=> the number of comb teeth
-// {Uoff + k T} strictly below X grows (sample_stratified!, src/fearnhead.jl:97-114, in
-// exact integer arithmetic).  Survivors are written in index order.
+// ------------------------------------------------------------------ survivor scan
+// The systematic comb (sample_stratified!, src/fearnhead.jl:97-114) over the putatives in
+// (particle, slot) order, in exact integer arithmetic.  With X = n * (running fixed-point
+// mass of the low partition) the comb teeth sit at Uoff + k T; a low item receives as many
+// copies as teeth fall strictly below its running X but not below its predecessor's (one
+// at most, because every low weight is < c = T / n), so the number of resampled survivors
+// before an item is teeth_below(X_before) and the output position of every survivor is
+//     (#kept before it) + (#teeth before it)
+// -- one exclusive scan of (X, kept), no second dependent scan.  Three launches, no
+// spinning: per-tile sums, one-block prefix over the tiles, apply.
 #define SCAN_THREADS 256
-struct TileDesc {            // 32 bytes
+struct TileSum {
     u128 X;
     unsigned int kept;
-    unsigned int picked;
-    unsigned int flag1;   // 2*epoch: aggregate of chain 1 published, 2*epoch+1: inclusive prefix published
-    unsigned int flag2;   // same for chain 2 (picked); smaller values belong to earlier steps
-};
-struct TileIncl {
-    u128 X;
-    unsigned int kept;
-    unsigned int picked;
-    unsigned int pad[2];
+    unsigned int pad[3];
 };
 
-__device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) { return *(const volatile unsigned int *)p; }
-__device__ __forceinline__ u128 ld_v128(const u128 *p)
+// mode 0: index-order step (always runs); mode 1: flat sorted list, runs only when the step
+// resamples and emits the PICKED positions only (kept = suffix of the sorted list);
+// mode 2: index-order pass of a sorted-order filter, runs only when the step keeps all.
+__device__ __forceinline__ bool scan_mode_skips(int mode, const SelResult *res)
 {
-    const volatile u64 *q = (const volatile u64 *)p;
-    u128 r; r.lo = q[0]; r.hi = q[1]; return r;
+    return (mode == 1 && res->keep_all) || (mode == 2 && !res->keep_all);
 }
-__device__ __forceinline__ unsigned int ld_vu32(const unsigned int *p) { return *(const volatile unsigned int *)p; }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
-                                                       long long cap, StepState *st, const SelResult *__restrict__ res,
-                                                       TileDesc *tiles, TileIncl *incl, unsigned int *__restrict__ surv_parent,
-                                                       unsigned char *__restrict__ surv_slot, unsigned int epoch,
-                                                       const long long *n_items_ptr, unsigned int *ticket, int mode)
+__device__ __forceinline__ void thread_sums(const double *__restrict__ V, long long cap, long long i, int c, u64 thr, int scale,
+                                            bool comb, u128 &S, unsigned int &kept)
 {
-    // mode 0: index-order filter step (always runs); mode 1: flat sorted list, runs only when
-    // the step resamples, writes the PICKED positions only (kept = suffix of the sorted list);
-    // mode 2: index-order pass of a sorted-order filter, runs only when the step keeps all.
-    if (mode == 1 && res->keep_all) return;
-    if (mode == 2 && !res->keep_all) return;
+    S = mk128(0, 0); kept = 0;
+    for (int j = 0; j < c; j++) {
+        u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
+        if (bits >= thr) kept++;
+        else if (comb) S = add128(S, fx70(bits, scale));
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
+                                                            long long cap, const SelResult *__restrict__ res,
+                                                            const long long *__restrict__ n_items_ptr, TileSum *__restrict__ tiles,
+                                                            int mode)
+{
+    if (scan_mode_skips(mode, res)) return;
+    __shared__ u128 s_x[SCAN_THREADS / 32];
+    __shared__ unsigned int s_k[SCAN_THREADS / 32];
+    const long long n_items = *n_items_ptr;
+    const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
+    if (blockIdx.x >= ntiles) return;
+    const long long i = (long long)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const u64 n = (u64)res->n;
+    const bool comb = n > 0 && !isz128(res->T);
+    const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
+    u128 X; unsigned int kept;
+    thread_sums(V, cap, i, c, res->thr_bits, res->scale, comb, X, kept);
+    X = warp_sum128(X);
+    kept = (unsigned int)warp_sum64(kept);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_x[wid] = X; s_k[wid] = kept; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SCAN_THREADS / 32; w++) { X = add128(X, s_x[w]); kept += s_k[w]; }
+        tiles[blockIdx.x].X = X; tiles[blockIdx.x].kept = kept;
+    }
+}
+
+// exclusive prefix over the tiles (in place) and the step's survivor counts; one block
+__global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelResult *__restrict__ res,
+                                                      const long long *__restrict__ n_items_ptr, StepState *st, int mode)
+{
+    if (scan_mode_skips(mode, res)) return;
+    __shared__ u128 s_warp[33];
+    __shared__ unsigned int s_k[1024];
+    const long long n_items = *n_items_ptr;
+    const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
+    const long long per = (ntiles + blockDim.x - 1) / blockDim.x;
+    const long long b = (long long)threadIdx.x * per, e = b + per < ntiles ? b + per : ntiles;
+    u128 lx = mk128(0, 0); unsigned int lk = 0;
+    for (long long t = b; t < e; t++) { lx = add128(lx, tiles[t].X); lk += tiles[t].kept; }
+    u128 totX;
+    u128 runX = block_excl_scan128(lx, s_warp, &totX);
+    s_k[threadIdx.x] = lk;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned int run = 0; for (int t = 0; t < (int)blockDim.x; t++) { unsigned int x = s_k[t]; s_k[t] = run; run += x; } s_warp[0].lo = run; }
+    __syncthreads();
+    unsigned int runK = s_k[threadIdx.x];
+    const unsigned int totK = (unsigned int)s_warp[0].lo;
+    for (long long t = b; t < e; t++) {
+        u128 x = tiles[t].X; unsigned int k = tiles[t].kept;
+        tiles[t].X = runX; tiles[t].kept = runK;
+        runX = add128(runX, x); runK += k;
+    }
+    if (threadIdx.x == 0) {
+        const bool comb = res->n > 0 && !isz128(res->T);
+        long long picked = comb ? (long long)teeth_below(mul128_64(totX, (u64)res->n), res->Uoff, res->T) : 0;
+        st->n_kept = totK; st->n_picked = picked; st->n_next = (long long)totK + picked;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
+                                                             long long cap, const SelResult *__restrict__ res,
+                                                             const long long *__restrict__ n_items_ptr,
+                                                             const TileSum *__restrict__ tiles, unsigned int *__restrict__ surv_parent,
+                                                             unsigned char *__restrict__ surv_slot, int mode)
+{
+    if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
     __shared__ unsigned int s_wc[33];
-    __shared__ unsigned int s_tile;
-    __shared__ u128 s_preX;
-    __shared__ unsigned int s_preK, s_preP;
-    const long long n_live = *n_items_ptr;
-    const long long ntiles = (n_live + SCAN_THREADS - 1) / SCAN_THREADS;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned int tile = s_tile;
-    if (tile >= ntiles) return;
-    const unsigned int F_AGG = 2u * epoch, F_INC = 2u * epoch + 1u;
+    const long long n_items = *n_items_ptr;
+    const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
+    if (blockIdx.x >= ntiles) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long i = (long long)tile * SCAN_THREADS + tid;
+    const long long i = (long long)blockIdx.x * SCAN_THREADS + tid;
     const u64 thr = res->thr_bits;
     const int scale = res->scale;
     const u64 n = (u64)res->n;
     const u128 T = res->T, U = res->Uoff;
     const bool comb = n > 0 && !isz128(T);
-    const int c = (i < n_live) ? (cnt ? cnt[i] : 1) : 0;
-
-    // pass A: thread totals
-    u128 myX = mk128(0, 0);
-    unsigned int myKept = 0;
-    for (int j = 0; j < c; j++) {
-        u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
-        if (bits >= thr) myKept++;
-        else if (comb) myX = add128(myX, mul128_64(fx128(bits, scale), n));
-    }
+    const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
+    u128 myX; unsigned int myKept;
+    thread_sums(V, cap, i, c, thr, scale, comb, myX, myKept);
     u128 totX;
     u128 exX = block_excl_scan128(myX, s_warp, &totX);
     unsigned int incK = myKept;
@@ -211,113 +269,43 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const double *__restrict_
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
         s_wc[lane] = wi - w;
-        if (lane == 31) s_wc[32] = wi;
     }
     __syncthreads();
-    unsigned int exK = s_wc[wid] + incK - myKept;
-    unsigned int totK = s_wc[32];
-    __syncthreads();
-
-    // chain 1: publish the tile aggregate, look back for the exclusive prefix
-    if (tid == 0) {
-        TileDesc *td = &tiles[tile];
-        u128 pX = mk128(0, 0); unsigned int pK = 0;
-        if (tile > 0) {
-            td->X = totX; td->kept = totK;
-            __threadfence();
-            *(volatile unsigned int *)&td->flag1 = F_AGG;
-            long long t = (long long)tile - 1;
-            while (true) {
-                unsigned int f;
-                while ((f = ld_flag(&tiles[t].flag1)) < F_AGG) { }
-                __threadfence();
-                if (f == F_INC) { pX = add128(pX, ld_v128(&incl[t].X)); pK += ld_vu32(&incl[t].kept); break; }
-                pX = add128(pX, ld_v128(&tiles[t].X)); pK += ld_vu32(&tiles[t].kept);
-                t--;
-            }
-        }
-        incl[tile].X = add128(pX, totX); incl[tile].kept = pK + totK;
-        __threadfence();
-        *(volatile unsigned int *)&td->flag1 = F_INC;
-        s_preX = pX; s_preK = pK;
+    if (c == 0) return;
+    const unsigned int exK = s_wc[wid] + incK - myKept;
+    // running low-partition mass S (fixed point) and the next tooth k: tooth k is passed by S
+    // <=> Uoff + k T < n S <=> floor((Uoff + k T) / n) < S; (Q, R) = divmod(Uoff + k T, n) steps
+    // by (Tq, Tr) = divmod(T, n) from tooth to tooth.
+    u128 S = add128(tiles[blockIdx.x].X, exX);
+    long long kcount = (long long)tiles[blockIdx.x].kept + exK;
+    u64 t = 0;
+    u128 Q = mk128(0, 0);
+    unsigned int R = 0;
+    const unsigned int n32 = (unsigned int)n, Tr = res->Tr;
+    const u128 Tq = res->Tq;
+    if (comb) {
+        t = teeth_below(mul128_64(S, n), U, T);
+        Q = divmod128_32(add128(U, mul128_64(T, t)), n32, &R);
     }
-    __syncthreads();
-    const u128 X0 = add128(s_preX, exX);
-
-    // pass B: decide the picks among this thread's items
-    unsigned long long pickmask = 0;
-    unsigned int myPicked = 0;
-    if (comb && c > 0) {
-        u128 X = X0;
-        u64 t = teeth_below(X, U, T);
-        u128 P = add128(U, mul128_64(T, t));          // position of the next tooth not yet passed
-        for (int j = 0; j < c; j++) {
-            u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
-            if (bits < thr) {
-                X = add128(X, mul128_64(fx128(bits, scale), n));
-                if (lt128(P, X)) {
-                    pickmask |= 1ull << j; myPicked++;
-                    do { P = add128(P, T); } while (lt128(P, X));
-                }
-            }
-        }
-    }
-    unsigned int incP = myPicked;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, incP, d); if (lane >= d) incP += o; }
-    if (lane == 31) s_wc[wid] = incP;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned int w = lane < (SCAN_THREADS / 32) ? s_wc[lane] : 0, wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
-        s_wc[lane] = wi - w;
-        if (lane == 31) s_wc[32] = wi;
-    }
-    __syncthreads();
-    unsigned int exP = s_wc[wid] + incP - myPicked;
-    unsigned int totP = s_wc[32];
-
-    // chain 2: picked counts
-    if (tid == 0) {
-        TileDesc *td = &tiles[tile];
-        unsigned int pP = 0;
-        if (tile > 0) {
-            td->picked = totP;
-            __threadfence();
-            *(volatile unsigned int *)&td->flag2 = F_AGG;
-            long long t = (long long)tile - 1;
-            while (true) {
-                unsigned int f;
-                while ((f = ld_flag(&tiles[t].flag2)) < F_AGG) { }
-                __threadfence();
-                if (f == F_INC) { pP += ld_vu32(&incl[t].picked); break; }
-                pP += ld_vu32(&tiles[t].picked);
-                t--;
-            }
-        }
-        incl[tile].picked = pP + totP;
-        __threadfence();
-        *(volatile unsigned int *)&td->flag2 = F_INC;
-        s_preP = pP;
-        if (tile == ntiles - 1) {
-            st->n_kept = (long long)(s_preK + totK);
-            st->n_picked = (long long)(pP + totP);
-            st->n_next = (long long)(s_preK + totK) + (long long)(pP + totP);
-        }
-    }
-    __syncthreads();
-    // write survivors in index order
-    if (c > 0) {
-        long long pos = (mode == 1) ? (long long)s_preP + exP : (long long)s_preK + exK + (long long)s_preP + exP;
-        for (int j = 0; j < c; j++) {
-            u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
-            bool kept = (mode == 1) ? false : bits >= thr;
-            bool picked = (pickmask >> j) & 1ull;
-            if (kept || picked) {
+    for (int j = 0; j < c; j++) {
+        u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
+        if (bits >= thr) {
+            if (mode != 1) {
+                long long pos = kcount + (long long)t;
                 surv_parent[pos] = (unsigned int)i;
-                surv_slot[pos] = (unsigned char)(j | (picked ? 0x80 : 0));
-                pos++;
+                surv_slot[pos] = (unsigned char)j;
+            }
+            kcount++;
+        } else if (comb) {
+            S = add128(S, fx70(bits, scale));
+            while (lt128(Q, S)) {
+                long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
+                surv_parent[pos] = (unsigned int)i;
+                surv_slot[pos] = (unsigned char)(j | 0x80);
+                t++;
+                Q = add128(Q, Tq);
+                R += Tr;
+                if (R >= n32) { R -= n32; Q = add128(Q, mk128(1, 0)); }
             }
         }
     }
@@ -352,40 +340,50 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
     logw2[t] = picked ? res->lw_resamp : (log(v) - res->log_total);
     Kc2[t] = K + (j == K ? 1 : 0);
     if (gen_anc) { gen_anc[t] = par; gen_asg[t] = (unsigned char)j; }
-    for (int jj = 0; jj < K; jj++) {
-        const double *src = S + ((long long)jj * L::F) * cap + par;
-        double *dst = S2 + ((long long)jj * L::F) * cap + t;
-        if (jj != j) {
+    // copy the parent's slots (the chosen one is rewritten below)
+    {
+        const double *src = S + par;
+        double *dst = S2 + t;
+        const int nrows = K * L::F;
+        int r = 0;
+        for (; r + 8 <= nrows; r += 8) {
+            double tmp[8];
 #pragma unroll
-            for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = src[(long long)f * cap];
-        } else {
-            double n = src[(long long)L::F_N * cap];
-            double logdet = src[(long long)L::F_LOGDET * cap];
-            double m[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1], dx[D], z[D];
+            for (int k = 0; k < 8; k++) tmp[k] = src[(long long)(r + k) * cap];
 #pragma unroll
-            for (int k = 0; k < D; k++) { m[k] = src[(long long)(L::F_MEAN + k) * cap]; dinv[k] = src[(long long)(L::F_DINV + k) * cap]; }
-#pragma unroll
-            for (int k = 0; k < L::NOFF; k++) off[k] = src[(long long)(L::F_OFF + k) * cap];
-            const NRow row = tab[(int)n];
-#pragma unroll
-            for (int k = 0; k < D; k++) dx[k] = scp->y[k] - (pc->mu0[k] + row.g * (m[k] - pc->mu0[k]));
-            double q = quad_form<D>(dx, dinv, off, z);
-            double sr = sqrt(row.r);
-#pragma unroll
-            for (int k = 0; k < D; k++) dx[k] *= sr;
-            chol_rank1<D>(dinv, off, dx);
-            double tw = n + 1.0;
-            dst[(long long)L::F_N * cap] = tw;
-            dst[(long long)L::F_LOGDET * cap] = logdet + log1p(row.r * q);
-#pragma unroll
-            for (int k = 0; k < D; k++) {
-                double delta = scp->y[k] - m[k];                       // Welford, src/component.jl:46-47
-                dst[(long long)(L::F_MEAN + k) * cap] = m[k] + delta / tw;
-                dst[(long long)(L::F_DINV + k) * cap] = dinv[k];
-            }
-#pragma unroll
-            for (int k = 0; k < L::NOFF; k++) dst[(long long)(L::F_OFF + k) * cap] = off[k];
+            for (int k = 0; k < 8; k++) dst[(long long)(r + k) * cap] = tmp[k];
         }
+        for (; r < nrows; r++) dst[(long long)r * cap] = src[(long long)r * cap];
+    }
+    if (j < K) {
+        const double *src = S + ((long long)j * L::F) * cap + par;
+        double *dst = S2 + ((long long)j * L::F) * cap + t;
+        double n = src[(long long)L::F_N * cap];
+        double logdet = src[(long long)L::F_LOGDET * cap];
+        double m[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1], dx[D], z[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) { m[k] = src[(long long)(L::F_MEAN + k) * cap]; dinv[k] = src[(long long)(L::F_DINV + k) * cap]; }
+#pragma unroll
+        for (int k = 0; k < L::NOFF; k++) off[k] = src[(long long)(L::F_OFF + k) * cap];
+        const NRow row = tab[(int)n];
+#pragma unroll
+        for (int k = 0; k < D; k++) dx[k] = scp->y[k] - (pc->mu0[k] + row.g * (m[k] - pc->mu0[k]));
+        double q = quad_form<D>(dx, dinv, off, z);
+        double sr = sqrt(row.r);
+#pragma unroll
+        for (int k = 0; k < D; k++) dx[k] *= sr;
+        chol_rank1<D>(dinv, off, dx);
+        double tw = n + 1.0;
+        dst[(long long)L::F_N * cap] = tw;
+        dst[(long long)L::F_LOGDET * cap] = logdet + log1p(row.r * q);
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            double delta = scp->y[k] - m[k];                       // Welford, src/component.jl:46-47
+            dst[(long long)(L::F_MEAN + k) * cap] = m[k] + delta / tw;
+            dst[(long long)(L::F_DINV + k) * cap] = dinv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < L::NOFF; k++) dst[(long long)(L::F_OFF + k) * cap] = off[k];
     }
     if (j == K) {
         double *dst = S2 + ((long long)K * L::F) * cap + t;
@@ -436,6 +434,8 @@ __global__ void k_steplog(const StepState *st, const SelResult *res, StepLog *lg
     r.n_got = st->n_picked; r.n_out = st->n_next; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
     r.log_total = res->log_total; r.lw_resamp = res->lw_resamp; r.thr = res->thr_value; r.cv = 0.0;
     r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds;
+    r.sel_us[0] = (res->t_ns[1] - res->t_ns[0]) * 1e-3; r.sel_us[1] = (res->t_ns[2] - res->t_ns[1]) * 1e-3;
+    r.sel_us[2] = (res->t_ns[3] - res->t_ns[2]) * 1e-3; r.sel_us[3] = (res->t_ns[4] - res->t_ns[0]) * 1e-3;
     (void)N;
     *lg = r;
 }

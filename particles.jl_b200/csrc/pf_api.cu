@@ -32,8 +32,7 @@ struct pf_filter_s {
     unsigned char *cnt = nullptr;
     unsigned int *surv_parent = nullptr;
     unsigned char *surv_slot = nullptr;
-    TileDesc *tiles = nullptr;
-    TileIncl *incl = nullptr;
+    TileSum *tiles = nullptr;
     double *cand = nullptr;
     long long cand_cap = 0;
     SelScratch *sc = nullptr;
@@ -74,6 +73,13 @@ struct pf_filter_s {
     long long last_launches = 0;
     long long launches = 0;
     unsigned int epoch = 0;
+    // per-kernel-class CUDA-event timing (pf_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_cls;
+    size_t ev_used = 0;
+    double cls_ms[PF_KERNEL_CLASSES] = {0};
+    long long cls_launches[PF_KERNEL_CLASSES] = {0};
     std::string err;
 };
 
@@ -88,6 +94,38 @@ static int32_t set_cuda_error(pf_handle h, cudaError_t e, const char *what, int 
     snprintf(buf, sizeof buf, "CUDA error %s at pf_api.cu:%d: %s", cudaGetErrorName(e), line, what);
     cudaGetLastError();
     return set_error(h, PF_ERR_CUDA, buf);
+}
+
+// ------------------------------------------------------------------ per-kernel timing
+static const char *k_class_names[PF_KERNEL_CLASSES] = {"prestep", "expand", "select", "scan", "instantiate", "steplog",
+                                                        "sort", "cl_propagate", "cl_stats", "cl_finish"};
+enum { KC_PRESTEP = 0, KC_EXPAND, KC_SELECT, KC_SCAN, KC_INSTANTIATE, KC_STEPLOG, KC_SORT, KC_CL_PROP, KC_CL_STATS, KC_CL_FINISH };
+
+struct LaunchTimer {            // records an event pair around one launch (or launch group) when profiling
+    pf_handle h; int cls; size_t slot = 0; bool on;
+    LaunchTimer(pf_handle h_, int cls_, int nlaunch = 1) : h(h_), cls(cls_), on(h_->profiling)
+    {
+        h->launches += nlaunch;
+        h->cls_launches[cls] += nlaunch;
+        if (!on) return;
+        if (h->ev_used + 2 > h->ev_pool.size()) {
+            for (int k = 0; k < 64; k++) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+        }
+        slot = h->ev_used; h->ev_used += 2;
+        h->ev_cls.push_back(cls);
+        cudaEventRecord(h->ev_pool[slot], h->stream);
+    }
+    ~LaunchTimer() { if (on) cudaEventRecord(h->ev_pool[slot + 1], h->stream); }
+};
+
+static void collect_profile(pf_handle h)
+{
+    if (!h->profiling) return;
+    for (size_t k = 0; k < h->ev_cls.size(); k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[2 * k], h->ev_pool[2 * k + 1]) == cudaSuccess) h->cls_ms[h->ev_cls[k]] += ms;
+    }
+    h->ev_cls.clear(); h->ev_used = 0;
 }
 
 // ------------------------------------------------------------------ host-side model setup
@@ -160,7 +198,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
-                    h->surv_slot, h->tiles, h->incl, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
+                    h->surv_slot, h->tiles, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -240,8 +278,6 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         CT(dmalloc(&h->pick_pos, (size_t)cap));
     }
     CT(dmalloc(&h->tiles, ntiles));
-    CT(dmalloc(&h->incl, ntiles));
-    CT(cudaMemsetAsync(h->tiles, 0, sizeof(TileDesc) * ntiles, h->stream));
     CT(dmalloc(&h->sc, 1));
     CT(dmalloc(&h->res, 1));
     CT(dmalloc(&h->st, 1));
@@ -250,9 +286,9 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(cudaMemsetAsync(h->sc, 0, sizeof(SelScratch), h->stream));
     CT(cudaMemsetAsync(h->res, 0, sizeof(SelResult), h->stream));
     // cooperative grid of the threshold search
-    CT(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SAMPLE_CAP * 8));
+    CT(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SMEM_BYTES));
     int occ = 0;
-    CT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SAMPLE_CAP * 8));
+    CT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SMEM_BYTES));
     if (occ < 1) { pf_destroy(h); return set_error(nullptr, PF_ERR_CUDA, "pf_create: k_select does not fit on an SM"); }
     h->sel_grid = h->num_sms * (occ > 2 ? 2 : occ);
     h->cand_cap = (long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
@@ -314,8 +350,7 @@ static int32_t launch_select(pf_handle h, const double *V, const unsigned char *
     a.V = V; a.cnt = cnt; a.cap = cap; a.n_live = n_live; a.M = M; a.vmax_bits = vmax; a.N = N; a.u = u_dev;
     a.cand = cand; a.cand_cap = cand_cap; a.sc = sc; a.res = res;
     void *args[] = {&a};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SAMPLE_CAP * 8, h->stream));
-    h->launches++;
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
     return PF_OK;
 }
 
@@ -333,41 +368,61 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap;
     }
     h->epoch++;
-    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0);
-    k_expand<D><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                            h->stc, h->st, h->V, h->cnt);
-    h->launches += 2;
-    int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
-                               h->cand_cap, h->sc, h->res);
-    if (rc != PF_OK) return rc;
+    {
+        LaunchTimer lt(h, KC_PRESTEP);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0);
+    }
+    {
+        LaunchTimer lt(h, KC_EXPAND);
+        k_expand<D><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                h->stc, h->st, h->V, h->cnt);
+    }
+    {
+        LaunchTimer lt(h, KC_SELECT);
+        int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
+                                   h->cand_cap, h->sc, h->res);
+        if (rc != PF_OK) return rc;
+    }
     if (h->cfg.order == PF_ORDER_SORTED) {
         const int slots = h->k_max + 1;
         const long long n_pad = ub * slots;
-        k_flat_keys<<<grid_for(n_pad, 256), 256, 0, h->stream>>>(h->V, h->cnt, cap, h->st, slots, n_pad, h->keys2);
-        h->launches++;
-        if (radix_sort_pairs(h->stream, h->keys2, h->keys, h->keys2, h->vals, h->vals2, h->hist, n_pad, &h->launches))
-            return set_error(h, PF_ERR_CUDA, "radix sort launch failed");
+        {
+            LaunchTimer lt(h, KC_SORT, 1 + 1 + 3 * 8);
+            k_flat_keys<<<grid_for(n_pad, 256), 256, 0, h->stream>>>(h->V, h->cnt, cap, h->st, slots, n_pad, h->keys2);
+            if (radix_sort_pairs(h->stream, h->keys2, h->keys, h->keys2, h->vals, h->vals2, h->hist, n_pad, nullptr))
+                return set_error(h, PF_ERR_CUDA, "radix sort launch failed");
+        }
         // resampling step: comb over the sorted list; exhaustive step: index order
-        k_scan<<<grid_for(n_pad, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->st, h->res,
-                                                                                h->tiles, h->incl, h->pick_pos, h->surv_slot, h->epoch,
-                                                                                &h->st->M, &h->st->ticket, 1);
+        LaunchTimer lt(h, KC_SCAN, 7);
+        const int gflat = grid_for(n_pad, SCAN_THREADS), gidx = grid_for(ub, SCAN_THREADS);
+        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1);
+        k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles,
+                                                             h->pick_pos, h->surv_slot, 1);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
                                                                            h->surv_slot);
-        h->epoch++;
-        k_scan<<<grid_for(ub, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->st, h->res, h->tiles, h->incl,
-                                                                             h->surv_parent, h->surv_slot, h->epoch, &h->st->n_live,
-                                                                             &h->st->ticket2, 2);
-        h->launches += 2;
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2);
+        k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
+                                                            h->surv_slot, 2);
     } else {
-        k_scan<<<grid_for(ub, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->st, h->res, h->tiles, h->incl,
-                                                                             h->surv_parent, h->surv_slot, h->epoch, &h->st->n_live,
-                                                                             &h->st->ticket, 0);
+        LaunchTimer lt(h, KC_SCAN, 3);
+        const int gidx = grid_for(ub, SCAN_THREADS);
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0);
+        k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
+                                                            h->surv_slot, 0);
     }
-    k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
-                                                                      h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                      h->surv_slot, ga, gs);
-    k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->N);
-    h->launches += 3;
+    {
+        LaunchTimer lt(h, KC_INSTANTIATE);
+        k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
+                                                                          h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
+                                                                          h->surv_slot, ga, gs);
+    }
+    {
+        LaunchTimer lt(h, KC_STEPLOG);
+        k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->N);
+    }
     CUDA_TRY(cudaGetLastError());
     h->cur = nxt;
     h->ub_live = ub_next;
@@ -385,20 +440,34 @@ static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_de
         ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap;
     }
     const int g256 = grid_for(N, 256);
-    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1);
-    k_cl_propagate<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], cap, N, h->k_max,
-                                                     h->tab, h->pc, h->stc, h->st, h->cl, u_dev, h->cfg.seed, (u64)h->steps, h->W,
-                                                     h->asg_tmp);
+    {
+        LaunchTimer lt(h, KC_PRESTEP);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1);
+    }
+    {
+        LaunchTimer lt(h, KC_CL_PROP);
+        k_cl_propagate<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], cap, N, h->k_max,
+                                                         h->tab, h->pc, h->stc, h->st, h->cl, u_dev, h->cfg.seed, (u64)h->steps, h->W,
+                                                         h->asg_tmp);
+    }
     int gstat = h->num_sms * 2;
     if (gstat > 1024) gstat = 1024;
-    k_cl_sum<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl);
-    k_cl_var<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl, h->cl_part);
-    k_cl_decide<<<1, 32, 0, h->stream>>>(h->cl, h->cl_part, gstat, N, h->cfg.rejuv_threshold);
-    k_cl_scan<<<1, 1024, 0, h->stream>>>(h->W, N, h->cl, h->cum);
-    k_cl_finish<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->Kc[0], h->Kc[1], h->logw[0], h->logw[1], cap, N, h->cl, h->W,
-                                                  h->cum, u_dev ? u_dev + N : nullptr, h->cfg.seed, (u64)h->steps, h->asg_tmp, ga, gs);
-    k_cl_steplog<<<1, 32, 0, h->stream>>>(h->st, h->cl, log_dev, N);
-    h->launches += 8;
+    {
+        LaunchTimer lt(h, KC_CL_STATS, 4);
+        k_cl_sum<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl);
+        k_cl_var<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl, h->cl_part);
+        k_cl_decide<<<1, 32, 0, h->stream>>>(h->cl, h->cl_part, gstat, N, h->cfg.rejuv_threshold);
+        k_cl_scan<<<1, 1024, 0, h->stream>>>(h->W, N, h->cl, h->cum);
+    }
+    {
+        LaunchTimer lt(h, KC_CL_FINISH);
+        k_cl_finish<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->Kc[0], h->Kc[1], h->logw[0], h->logw[1], cap, N, h->cl, h->W,
+                                                      h->cum, u_dev ? u_dev + N : nullptr, h->cfg.seed, (u64)h->steps, h->asg_tmp, ga, gs);
+    }
+    {
+        LaunchTimer lt(h, KC_STEPLOG);
+        k_cl_steplog<<<1, 32, 0, h->stream>>>(h->st, h->cl, log_dev, N);
+    }
     CUDA_TRY(cudaGetLastError());
     h->steps++;
     return PF_OK;
@@ -466,6 +535,7 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms; h->last_launches = h->launches;
+    collect_profile(h);
     h->last = h->logs.back(); h->have_last = true;
     h->n_host = h->last.n_out;
     if (!fh) {
@@ -501,6 +571,23 @@ extern "C" int32_t pf_last_timing(pf_handle h, double *device_ms, int64_t *kerne
     if (kernel_launches) *kernel_launches = h->last_launches;
     return PF_OK;
 }
+
+extern "C" int32_t pf_set_profiling(pf_handle h, int32_t on)
+{
+    if (!h) return PF_ERR_ARG;
+    h->profiling = on != 0;
+    for (int k = 0; k < PF_KERNEL_CLASSES; k++) { h->cls_ms[k] = 0.0; h->cls_launches[k] = 0; }
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_kernel_times(pf_handle h, double *ms, int64_t *launches)
+{
+    if (!h) return PF_ERR_ARG;
+    for (int k = 0; k < PF_KERNEL_CLASSES; k++) { if (ms) ms[k] = h->cls_ms[k]; if (launches) launches[k] = h->cls_launches[k]; }
+    return PF_OK;
+}
+
+extern "C" const char *pf_kernel_class_name(int32_t k) { return (k >= 0 && k < PF_KERNEL_CLASSES) ? k_class_names[k] : ""; }
 
 extern "C" int32_t pf_get_logweights(pf_handle h, double *out)
 {
@@ -594,6 +681,7 @@ extern "C" int32_t pf_get_last_step(pf_handle h, pf_step_stats *o)
     o->n_resamp_got = r.n_got; o->n_out = r.n_out; o->overflow = r.overflow; o->log_total_w = r.log_total;
     o->log_w_resamp = r.lw_resamp; o->threshold = r.thr; o->cv = r.cv; o->resampled = r.resampled;
     o->select_rounds = r.rounds; o->n_candidates = r.n_cand;
+    for (int k = 0; k < 4; k++) o->select_phase_us[k] = r.sel_us[k];
     return PF_OK;
 }
 
@@ -664,7 +752,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
     int32_t rc = PF_OK;
     double *dW = nullptr, *dU = nullptr, *cand = nullptr;
     StepState *st = nullptr; SelScratch *sc = nullptr; SelResult *res = nullptr;
-    TileDesc *tiles = nullptr; TileIncl *incl = nullptr;
+    TileSum *tiles = nullptr;
     unsigned int *sp = nullptr; unsigned char *ss = nullptr;
     u64 *keys = nullptr, *keys2 = nullptr; unsigned int *vals = nullptr, *vals2 = nullptr;
     unsigned int *hist = nullptr;
@@ -676,17 +764,16 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         ST(cudaGetDeviceProperties(&prop, device));
         h->num_sms = prop.multiProcessorCount;
         ST(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        ST(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SAMPLE_CAP * 8));
+        ST(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SMEM_BYTES));
         int occ = 0;
-        ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SAMPLE_CAP * 8));
+        ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SMEM_BYTES));
         h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
         long long cand_cap = M + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
         long long ntiles = (M + SCAN_THREADS - 1) / SCAN_THREADS;
         ST(dmalloc(&dW, (size_t)M)); ST(dmalloc(&dU, 1)); ST(dmalloc(&cand, (size_t)cand_cap));
         ST(dmalloc(&st, 1)); ST(dmalloc(&sc, 1)); ST(dmalloc(&res, 1));
-        ST(dmalloc(&tiles, (size_t)ntiles)); ST(dmalloc(&incl, (size_t)ntiles));
+        ST(dmalloc(&tiles, (size_t)ntiles));
         ST(dmalloc(&sp, (size_t)M)); ST(dmalloc(&ss, (size_t)M));
-        ST(cudaMemsetAsync(tiles, 0, sizeof(TileDesc) * ntiles, h->stream));
         ST(cudaMemsetAsync(sc, 0, sizeof(SelScratch), h->stream));
         ST(cudaMemsetAsync(res, 0, sizeof(SelResult), h->stream));
         StepState s0; memset(&s0, 0, sizeof s0);
@@ -709,8 +796,9 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         k_vmax<<<h->num_sms * 4, 256, 0, h->stream>>>(Vsel, M, st);
         rc = launch_select(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res);
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
-        k_scan<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, st, res, tiles, incl, sp, ss, 1u, &st->n_live,
-                                                                            &st->ticket, 0);
+        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0);
+        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0);
         ST(cudaGetLastError());
         StepState s1; SelResult r1;
         ST(cudaMemcpyAsync(&s1, st, sizeof s1, cudaMemcpyDeviceToHost, h->stream));
@@ -751,7 +839,7 @@ done:
 #undef ST
     if (h->stream) { cudaStreamSynchronize(h->stream); }
     {
-        void *ptrs[] = {dW, dU, cand, st, sc, res, tiles, incl, sp, ss, keys, keys2, vals, vals2, hist};
+        void *ptrs[] = {dW, dU, cand, st, sc, res, tiles, sp, ss, keys, keys2, vals, vals2, hist};
         for (void *p : ptrs) if (p) cudaFree(p);
     }
     if (h->stream) cudaStreamDestroy(h->stream);

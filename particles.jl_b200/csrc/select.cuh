@@ -1,26 +1,38 @@
 // select.cuh -- Fearnhead-Clifford threshold search (cutoff_ascending, src/fearnhead.jl:59-77)
-// as ONE cooperative persistent kernel: sample -> bracket -> classify pass -> radix descent
-// on the bracket's candidates -> exact solve.  All sums that feed a decision are 128-bit
-// fixed-point integers (order-free, hence deterministic and shard-independent).
+// as ONE cooperative persistent kernel:
 //
-// Items are the putative weights of the current step, addressed as (particle i, slot j):
+//   phase 0  bracket   a strided sample of the putative weights (about 2^20 of them) is
+//                      solved approximately by the same radix descent that solves the real
+//                      problem, and widened by a sampling-error margin into [lo, hi);
+//   round r  classify  one pass over all putatives: exact fixed-point mass below lo, count
+//                      above hi, the few in between become the candidate list;
+//            verify    predicate false at lo and true at hi (else widen and redo);
+//            descend   1024-bin radix histogram levels over the candidate list until the
+//                      bracket holds <= 2048 values;
+//            solve     sort them, evaluate the predicate of src/fearnhead.jl:69 exactly;
+//            rescale   if the comb needs a finer scale than the threshold did, one more
+//                      classify pass at that scale.
+//
+// All sums that feed a decision are 128-bit fixed-point integers (order-free, hence
+// deterministic and shard-independent).  Items are addressed as (particle i, slot j):
 //     value = V[j * cap + i],   j < cnt[i]   (cnt == nullptr: one item per index)
-//
 // Result (SelResult): kept set = {v >= thr}; everything else is the low partition with
-// fixed-point total T at scale 2^scale; n = N - A particles are to be drawn from it by the
-// systematic comb of k_scan (sample_stratified!, src/fearnhead.jl:97-114).
+// fixed-point total T at scale 2^scale; n = N - A particles are drawn from it by the
+// systematic comb of the survivor scan (sample_stratified!, src/fearnhead.jl:97-114).
 #pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"
 namespace cg = cooperative_groups;
 
 #define SEL_THREADS 512
-#define SEL_SAMPLE_CAP 8192
+#define SEL_WARPS (SEL_THREADS / 32)
 #define SEL_FINAL_CAP 2048
 #define SEL_BINS 1024
 #define SEL_CHUNK 256
+#define SEL_SAMPLE_TARGET (1 << 20)
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax
+#define SEL_SMEM_BYTES (SEL_BINS * 4 + 3 * SEL_BINS * 8)
 
 struct SelResult {
     u64 thr_bits;                   // kept = {bits(v) >= thr_bits}; 0 = keep everything
@@ -28,6 +40,8 @@ struct SelResult {
     int keep_all;                   // M <= N (src/fearnhead.jl:135-138)
     u128 T;                         // sum of q over the low partition
     u128 Uoff;                      // floor(u * T): comb offset
+    u128 Tq;                        // floor(T / n): tooth spacing in units of the running mass
+    unsigned int Tr, pad0;          // T mod n
     long long A;                    // number kept
     long long n;                    // number to draw (N - A)
     double log_total;               // log(sum of all putative weights)
@@ -37,6 +51,7 @@ struct SelResult {
     int rounds;
     long long n_cand_first;
     int status;                     // 0 ok
+    unsigned long long t_ns[5];     // globaltimer at: start, bracket ready, first classify done, solve done, end
 };
 
 struct SelScratch {
@@ -45,17 +60,18 @@ struct SelScratch {
     int scale;
     int phase;                      // control word for the next loop iteration
     int mode;                       // 0 bracket round, 1 keep everything, 2 comb-rescale round (lo = hi = thr)
-    long long count_in;             // candidates inside [lo, hi)
+    long long count_in;             // list items inside [lo, hi)
+    long long mult;                 // sample stride while solving the sample, 1 otherwise
     // accumulators of the classify pass
     unsigned long long A_hi;        // #items >= hi
     unsigned long long n_cand;      // #items in [lo, hi)
     acc128 B_lo;                    // sum q of items < lo
     acc128 S_cand;                  // sum q of items in [lo, hi)
-    acc128 Tot;                     // sum of all items at scale SEL_TOT_BITS - e(vmax)
+    acc128 Tot;                     // sum of the items >= hi at scale SEL_TOT_BITS - e(vmax)
     // running totals of the descent
-    u128 B_run;                     // sum q of items < lo (after narrowing)
-    long long A_run;                // #items >= hi (after narrowing)
-    // candidate list
+    u128 B_run;                     // sum q of list items < lo (after narrowing)
+    long long A_run;                // #list items >= hi (after narrowing)
+    // candidate / sample list
     unsigned long long cand_chunks; // chunks handed out
     // final list
     unsigned int final_n;
@@ -63,7 +79,6 @@ struct SelScratch {
     // histogram of one descent level
     unsigned int h_cnt[SEL_BINS];
     u64 h_sum[3][SEL_BINS];
-    int h_shift;
 };
 
 struct SelArgs {
@@ -81,6 +96,14 @@ struct SelArgs {
     SelResult *res;
 };
 
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// predicate of cutoff_ascending (src/fearnhead.jl:69): tot <= (N - n_geq) * w
 __device__ __forceinline__ bool pred128(u128 B, long long N, long long A_geq, u128 qx)
 {
     long long dd = N - A_geq;
@@ -89,7 +112,7 @@ __device__ __forceinline__ bool pred128(u128 B, long long N, long long A_geq, u1
 }
 
 // exclusive scan of one u128 per thread over the block; returns exclusive prefix, *total = block sum
-__device__ inline u128 block_excl_scan128(u128 v, u128 *smem_warp /* >= 32 */, u128 *total)
+__device__ inline u128 block_excl_scan128(u128 v, u128 *smem_warp /* >= 33 */, u128 *total)
 {
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     u128 inc = v;
@@ -135,12 +158,175 @@ __device__ inline void bitonic_sort_smem(u64 *a, int n /* power of two */)
         }
 }
 
+// warp-aggregated append of the lanes with `flag` to a chunked list (chunks of SEL_CHUNK
+// doubles handed out by one atomic each; unused tails are padded with NaN-pattern ~0).
+struct ChunkWriter {
+    long long base;
+    int fill;
+    __device__ __forceinline__ void init() { base = -1; fill = SEL_CHUNK; }
+    __device__ __forceinline__ void push(bool flag, u64 bits, double *list, unsigned long long *chunks, int lane)
+    {
+        unsigned int bal = __ballot_sync(0xffffffffu, flag);
+        if (!bal) return;
+        int nb = __popc(bal);
+        if (fill + nb > SEL_CHUNK) {
+            if (base >= 0)
+                for (int t = fill + lane; t < SEL_CHUNK; t += 32) list[base + t] = __longlong_as_double(~0ll);
+            long long nb_ = 0;
+            if (lane == 0) nb_ = (long long)atomicAdd(chunks, 1ull) * SEL_CHUNK;
+            base = __shfl_sync(0xffffffffu, nb_, 0);
+            fill = 0;
+        }
+        if (flag) list[base + fill + __popc(bal & ((1u << lane) - 1))] = __longlong_as_double((long long)bits);
+        fill += nb;
+    }
+    __device__ __forceinline__ void finish(double *list, int lane)
+    {
+        if (base >= 0)
+            for (int t = fill + lane; t < SEL_CHUNK; t += 32) list[base + t] = __longlong_as_double(~0ll);
+    }
+};
+
+// one radix level: histogram (count, fixed-point sum) of the list items inside [blo, bhi)
+// into sc->h_* (which block 0 left zeroed), 1024 bins of width 2^shift bit patterns.
+__device__ inline void hist_level(const double *list, long long list_n, u64 blo, u64 bhi, int shift, int scale, SelScratch *sc,
+                                  unsigned char *smem_raw)
+{
+    unsigned int *h_cnt = reinterpret_cast<unsigned int *>(smem_raw);
+    u64 *h_s0 = reinterpret_cast<u64 *>(smem_raw + SEL_BINS * 4);
+    u64 *h_s1 = h_s0 + SEL_BINS, *h_s2 = h_s1 + SEL_BINS;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < SEL_BINS; t += SEL_THREADS) { h_cnt[t] = 0; h_s0[t] = 0; h_s1[t] = 0; h_s2[t] = 0; }
+    __syncthreads();
+    for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < list_n; t += (long long)gridDim.x * SEL_THREADS) {
+        u64 bits = (u64)__double_as_longlong(list[t]);
+        if (bits >= blo && bits < bhi) {
+            int b = (int)((bits - blo) >> shift);
+            u128 q = fx70(bits, scale);
+            atomicAdd(&h_cnt[b], 1u);
+            atomicAdd(&h_s0[b], q.lo & 0xffffffffull);
+            atomicAdd(&h_s1[b], q.lo >> 32);
+            atomicAdd(&h_s2[b], q.hi);
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < SEL_BINS; t += SEL_THREADS)
+        if (h_cnt[t]) {
+            atomicAdd(&sc->h_cnt[t], h_cnt[t]);
+            atomicAdd(&sc->h_sum[0][t], h_s0[t]);
+            atomicAdd(&sc->h_sum[1][t], h_s1[t]);
+            atomicAdd(&sc->h_sum[2][t], h_s2[t]);
+        }
+    __syncthreads();
+}
+
+__device__ __forceinline__ u128 hist_bin_sum(const SelScratch *sc, int b)
+{
+    return add128(add128(mk128(sc->h_sum[0][b], 0), shl128(mk128(sc->h_sum[1][b], 0), 32)), mk128(0, sc->h_sum[2][b]));
+}
+
+// Block 0 (all threads), after a histogram level: find the first bin whose UPPER boundary
+// satisfies the predicate and narrow the bracket to it.  With sampling != 0 the list is a
+// strided sample (sums and counts are multiplied by sc->mult): the level either narrows to
+// the bin and its two neighbours, or -- once the bin is finer than the sampling error --
+// ends the sample solve by widening the bin to `delta` sample items on each side
+// (sc->phase = 6).  Works on a shared-memory copy of the level's histogram.
+__device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi, int shift, int scale, int sampling,
+                                  unsigned char *smem_raw)
+{
+    unsigned int *pc = reinterpret_cast<unsigned int *>(smem_raw);            // inclusive count prefix
+    u128 *ps = reinterpret_cast<u128 *>(smem_raw + SEL_BINS * 4);            // inclusive sum prefix
+    __shared__ int s_found;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int b = tid; b < SEL_BINS; b += SEL_THREADS) {
+        pc[b] = sc->h_cnt[b];
+        ps[b] = add128(add128(mk128(sc->h_sum[0][b], 0), shl128(mk128(sc->h_sum[1][b], 0), 32)), mk128(0, sc->h_sum[2][b]));
+        sc->h_cnt[b] = 0; sc->h_sum[0][b] = 0; sc->h_sum[1][b] = 0; sc->h_sum[2][b] = 0;      // ready for the next level
+    }
+    __syncthreads();
+    const int per = SEL_BINS / 32;
+    const u64 width = bhi - blo;
+    const long long count_in = sc->count_in;
+    const long long mult = sc->mult;
+    const u128 B0 = sc->B_run; const long long A0 = sc->A_run;
+    const int last_bin = (int)((width - 1) >> shift);
+    if (wid == 0) {
+        u128 ls = mk128(0, 0);
+        unsigned int lc = 0;
+        for (int k = 0; k < per; k++) { int b = lane * per + k; ls = add128(ls, ps[b]); lc += pc[b]; }
+        u128 inc = ls; unsigned int incc = lc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u128 o = shfl_up128(inc, d);
+            unsigned int oc = __shfl_up_sync(0xffffffffu, incc, d);
+            if (lane >= d) { inc = add128(inc, o); incc += oc; }
+        }
+        u128 pre = sub128(inc, ls);
+        unsigned int prec = incc - lc;
+        int found = SEL_BINS;
+        for (int k = 0; k < per; k++) {
+            int b = lane * per + k;
+            pre = add128(pre, ps[b]); prec += pc[b];
+            ps[b] = pre; pc[b] = prec;
+            if (b <= last_bin) {
+                u64 off = ((u64)(b + 1)) << shift;
+                u64 x = (off >= width) ? bhi : blo + off;
+                bool ok = (x >= PF_INF_BITS) ? true
+                                             : pred128(mul128_64(add128(B0, pre), (u64)mult), N, (A0 + (count_in - (long long)prec)) * mult,
+                                                       fx70(x, scale));
+                if (ok && found == SEL_BINS) found = b;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, d));
+        if (found > last_bin) found = last_bin;
+        if (lane == 0) s_found = found;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int found = s_found;
+        int b_lo = found, b_hi = found;
+        int next_phase = 2;
+        const long long cnt_found = (long long)pc[found] - (found > 0 ? (long long)pc[found - 1] : 0);
+        if (sampling) {
+            const long long above = A0 + (count_in - (long long)pc[found]) + cnt_found;
+            const long long delta = (long long)(8.0 * sqrt((double)(above > 1 ? above : 1))) + 32;
+            if (cnt_found > 2 * delta && shift > 0) {
+                b_lo = found > 0 ? found - 1 : 0;
+                b_hi = found < last_bin ? found + 1 : last_bin;
+            } else {
+                const long long below_found = found > 0 ? (long long)pc[found - 1] : 0;
+                while (b_lo > 0 && below_found - (b_lo > 0 ? (long long)pc[b_lo - 1] : 0) < delta) b_lo--;
+                while (b_hi < last_bin && (long long)pc[b_hi] - (long long)pc[found] < delta) b_hi++;
+                next_phase = 6;
+            }
+        }
+        const u128 before = b_lo > 0 ? ps[b_lo - 1] : mk128(0, 0);
+        const long long cbefore = b_lo > 0 ? (long long)pc[b_lo - 1] : 0;
+        const long long cin = (long long)pc[b_hi] - cbefore;
+        const u64 nlo = blo + (((u64)b_lo) << shift);
+        const u64 off = ((u64)(b_hi + 1)) << shift;
+        const u64 nhi = (off >= width) ? bhi : blo + off;
+        sc->B_run = add128(B0, before);
+        sc->A_run = A0 + (count_in - cbefore - cin);
+        sc->lo = nlo; sc->hi = nhi; sc->count_in = cin;
+        sc->phase = next_phase;
+    }
+    __syncthreads();
+}
+
+__device__ inline void reset_round(SelScratch *sc)
+{
+    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0;
+    for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
+}
+
 // The comb needs the low partition's mass T at a scale fine relative to c = T / n (every
 // low weight is < c, so c bounds the items).  The threshold round's scale follows the
 // threshold instead, which can sit many binades above c when a gap separates the kept
 // group from the rest.  Returns true (and programs a mode-2 round: lo = hi = thr at a
 // finer scale) when T has fewer than 52 bits per drawn particle.
-__device__ inline bool comb_rescale(SelScratch *sc, const SelResult *res, long long N, u64 vmax)
+__device__ inline bool comb_rescale(SelScratch *sc, const SelResult *res, long long N)
 {
     const long long n = N - res->A;
     if (n <= 0) return false;
@@ -155,15 +341,13 @@ __device__ inline bool comb_rescale(SelScratch *sc, const SelResult *res, long l
         if (!lt128(T, shl128(mk128((u64)n, 0), 52))) return false;
         int blT = T.hi ? 128 - __clzll((long long)T.hi) : 64 - __clzll((long long)T.lo);
         int bln = 64 - __clzll(n);
-        int e_c = blT - bln + 1 - scale;                    // c < 2^(e_c + 1)
+        int e_c = blT - bln + 1 - scale;                    // c < 2^e_c
         nscale = SEL_ITEM_BITS - 3 - e_c;
         if (nscale <= scale) return false;
     }
     if (nscale > max_scale) nscale = max_scale;
-    (void)vmax;
-    sc->lo = res->thr_bits; sc->hi = res->thr_bits; sc->scale = nscale; sc->mode = 2;
-    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0;
-    for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
+    sc->lo = res->thr_bits; sc->hi = res->thr_bits; sc->scale = nscale; sc->mode = 2; sc->mult = 1;
+    reset_round(sc);
     return true;
 }
 
@@ -172,12 +356,11 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s_u64 = reinterpret_cast<u64 *>(smem_raw);               // SEL_SAMPLE_CAP u64 (sample / final sort)
+    u64 *s_u64 = reinterpret_cast<u64 *>(smem_raw);               // SEL_FINAL_CAP u64 for the final sort
     __shared__ u128 s_warp[33];
-    __shared__ unsigned int s_cnt;
     __shared__ long long s_ll[4];
-    __shared__ u128 s_red[3][SEL_THREADS / 32];
-    __shared__ unsigned long long s_redc[2][SEL_THREADS / 32];
+    __shared__ u128 s_red[3][SEL_WARPS];
+    __shared__ unsigned long long s_redc[2][SEL_WARPS];
 
     SelScratch *sc = a.sc;
     SelResult *res = a.res;
@@ -186,87 +369,80 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
     const u64 vmax = *a.vmax_bits;
     const long long N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long gwarp = (long long)blockIdx.x * (SEL_THREADS / 32) + wid;
-    const long long nwarps = (long long)gridDim.x * (SEL_THREADS / 32);
+    const long long gwarp = (long long)blockIdx.x * SEL_WARPS + wid;
+    const long long nwarps = (long long)gridDim.x * SEL_WARPS;
     const int e_vmax = exp_of_bits(vmax);
     const int tot_scale = SEL_TOT_BITS - e_vmax;
+    const int vmax_scale = SEL_ITEM_BITS - e_vmax;
+    const bool trivial = (M <= N || vmax == 0);
+    const bool sampled = !trivial && M > SEL_FINAL_CAP;
 
-    // ---------------- phase 0: first bracket (block 0)
-    if (blockIdx.x == 0) {
-        if (tid == 0) {
-            sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0;
-            for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; sc->Tot.l[k] = 0; }
-            res->rounds = 0; res->status = 0; res->n_cand_first = 0;
-        }
-        if (M <= N || vmax == 0) {
-            // keep everything (src/fearnhead.jl:135-138); an all-zero step keeps nothing
-            if (tid == 0) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = SEL_ITEM_BITS - e_vmax; sc->phase = 1; sc->mode = 1; }
-        } else if (M <= SEL_FINAL_CAP) {
-            if (tid == 0) { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = SEL_ITEM_BITS - e_vmax; sc->phase = 1; sc->mode = 0; }
-        } else {
-            // strided sample of whole particles
-            if (tid == 0) s_cnt = 0;
-            __syncthreads();
-            long long stride = (M + (SEL_SAMPLE_CAP * 7 / 8) - 1) / (SEL_SAMPLE_CAP * 7 / 8);
-            if (stride < 1) stride = 1;
-            for (long long p = tid; p * stride < n_live; p += SEL_THREADS) {
-                long long i = p * stride;
-                int c = a.cnt ? a.cnt[i] : 1;
-                for (int j = 0; j < c; j++) {
-                    unsigned int pos = atomicAdd(&s_cnt, 1u);
-                    if (pos < SEL_SAMPLE_CAP) s_u64[pos] = __double_as_longlong(a.V[(long long)j * a.cap + i]);
-                }
-            }
-            __syncthreads();
-            int m = min(s_cnt, (unsigned)SEL_SAMPLE_CAP);
-            for (int t = m + tid; t < SEL_SAMPLE_CAP; t += SEL_THREADS) s_u64[t] = ~0ull;
-            __syncthreads();
-            bitonic_sort_smem(s_u64, SEL_SAMPLE_CAP);
-            // approximate solve on the sample (FP64): rho = M / m
-            double rho = (double)M / (double)m;
-            const int per = SEL_SAMPLE_CAP / SEL_THREADS;
-            double loc = 0.0;
-            for (int k = 0; k < per; k++) { int t = tid * per + k; if (t < m) loc += __longlong_as_double(s_u64[t]); }
-            // block exclusive scan of doubles through the u128 helper is overkill: do it in smem
-            double *s_d = reinterpret_cast<double *>(s_red);
-            __shared__ double s_pref[SEL_THREADS];
-            s_pref[tid] = loc;
-            __syncthreads();
-            if (tid == 0) { double run = 0.0; for (int t = 0; t < SEL_THREADS; t++) { double x = s_pref[t]; s_pref[t] = run; run += x; } }
-            __syncthreads();
-            (void)s_d;
-            double run = s_pref[tid];
-            int first = m;
-            for (int k = 0; k < per; k++) {
-                int t = tid * per + k;
-                if (t < m) {
-                    double w = __longlong_as_double(s_u64[t]);
-                    if (w != 0.0 && first == m) {
-                        double ngeq = rho * (double)(m - t);
-                        if (rho * run <= ((double)N - ngeq) * w) first = t;
-                    }
-                    run += w;
-                }
-            }
-            if (tid == 0) s_ll[0] = m;
-            __syncthreads();
-            atomicMin(&s_ll[0], (long long)first);
-            __syncthreads();
-            if (tid == 0) {
-                int istar = (int)s_ll[0];
-                int delta = (int)(3.0 * sqrt((double)m)) + 8;
-                int il = istar - delta, ih = istar + delta;
-                u64 lo = il <= 0 ? 1ull : s_u64[il];
-                u64 hi = ih >= m ? PF_INF_BITS : s_u64[ih];
-                if (lo < 1) lo = 1;
-                if (hi <= lo) hi = lo + 1;
-                if (hi > PF_INF_BITS) hi = PF_INF_BITS;
-                sc->lo = lo; sc->hi = hi;
-                sc->scale = SEL_ITEM_BITS - exp_of_bits(hi >= PF_INF_BITS ? vmax : hi);
-                sc->phase = 1; sc->mode = 0;
-            }
+    // ---------------- phase 0: first bracket
+    if (blockIdx.x == 0 && tid == 0) {
+        reset_round(sc);
+        for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
+        res->rounds = 0; res->status = 0; res->n_cand_first = 0;
+        res->t_ns[0] = gtimer();
+        sc->mult = 1;
+        if (trivial) {             // keep everything (src/fearnhead.jl:135-138); an all-zero step keeps nothing
+            sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1;
+        } else {                   // direct solve, or the starting bracket of the sample solve
+            sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0;
         }
     }
+    grid.sync();
+    if (sampled) {
+        // strided sample of whole particles, appended to the (still unused) candidate list
+        const long long stride = (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
+        {
+            ChunkWriter cw; cw.init();
+            unsigned long long cnt_s = 0;
+            for (long long base = gwarp * 32; base * stride < n_live; base += nwarps * 32) {
+                long long i = (base + lane) * stride;
+                int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
+                int maxc = c;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+                for (int j = 0; j < maxc; j++) {
+                    bool have = j < c;
+                    u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
+                    have = have && bits != 0;             // zeros never decide anything
+                    cnt_s += have;
+                    cw.push(have, bits, a.cand, &sc->cand_chunks, lane);
+                }
+            }
+            cw.finish(a.cand, lane);
+            cnt_s = warp_sum64(cnt_s);
+            if (lane == 0 && cnt_s) atomicAdd(&sc->n_cand, cnt_s);
+        }
+        grid.sync();
+        if (blockIdx.x == 0 && tid == 0) {
+            sc->B_run = mk128(0, 0); sc->A_run = 0; sc->count_in = (long long)sc->n_cand; sc->mult = stride; sc->phase = 2;
+        }
+        grid.sync();
+        const long long list_n = (long long)sc->cand_chunks * SEL_CHUNK;
+        for (int level = 0; level < 8; level++) {
+            const u64 blo = sc->lo, bhi = sc->hi;
+            if (sc->count_in == 0 || (bhi - blo) <= 1) break;
+            const u64 width = bhi - blo;
+            int shift = 0;
+            while (((width - 1) >> shift) >= SEL_BINS) shift++;
+            hist_level(a.cand, list_n, blo, bhi, shift, vmax_scale, sc, smem_raw);
+            grid.sync();
+            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, vmax_scale, 1, smem_raw);
+            grid.sync();
+            if (sc->phase == 6) break;
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            u64 lo = sc->lo, hi = sc->hi;
+            if (lo < 1) lo = 1;
+            if (hi <= lo) hi = lo + 1;
+            sc->lo = lo; sc->hi = hi; sc->mode = 0; sc->mult = 1;
+            sc->scale = SEL_ITEM_BITS - exp_of_bits(hi >= PF_INF_BITS ? vmax : hi);
+            reset_round(sc);
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) res->t_ns[1] = gtimer();
     grid.sync();
 
     // ---------------- rounds
@@ -279,8 +455,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         {
             unsigned long long A_hi = 0, n_cand = 0;
             u128 B_lo = mk128(0, 0), S_c = mk128(0, 0), Tot = mk128(0, 0);
-            long long chunk_base = -1;
-            int chunk_fill = SEL_CHUNK;
+            ChunkWriter cw; cw.init();
             for (long long base = gwarp * 32; base < n_live; base += nwarps * 32) {
                 long long i = base + lane;
                 int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
@@ -292,43 +467,23 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
                     bool is_cand = false;
                     if (have) {
-                        if (round == 0) Tot = add128(Tot, fx128(bits, tot_scale));
-                        if (bits >= hi) A_hi++;
-                        else if (bits < lo) { if (!keep_all) B_lo = add128(B_lo, fx128(bits, scale)); }
-                        else { is_cand = true; n_cand++; S_c = add128(S_c, fx128(bits, scale)); }
+                        if (bits >= hi) { A_hi++; if (round == 0) Tot = add128(Tot, fx128(bits, tot_scale)); }
+                        else if (bits < lo) B_lo = add128(B_lo, fx70(bits, scale));
+                        else { is_cand = true; n_cand++; S_c = add128(S_c, fx70(bits, scale)); }
                     }
-                    unsigned int bal = __ballot_sync(0xffffffffu, is_cand);
-                    if (bal) {
-                        int nb = __popc(bal);
-                        if (chunk_fill + nb > SEL_CHUNK) {
-                            // pad the rest of the old chunk, take a new one
-                            if (chunk_base >= 0)
-                                for (int t = chunk_fill + lane; t < SEL_CHUNK; t += 32) a.cand[chunk_base + t] = __longlong_as_double(~0ll);
-                            long long nb_ = 0;
-                            if (lane == 0) nb_ = (long long)atomicAdd(&sc->cand_chunks, 1ull) * SEL_CHUNK;
-                            chunk_base = __shfl_sync(0xffffffffu, nb_, 0);
-                            chunk_fill = 0;
-                        }
-                        if (is_cand) {
-                            int r = __popc(bal & ((1u << lane) - 1));
-                            a.cand[chunk_base + chunk_fill + r] = __longlong_as_double((long long)bits);
-                        }
-                        chunk_fill += nb;
-                    }
+                    cw.push(is_cand, bits, a.cand, &sc->cand_chunks, lane);
                 }
             }
-            if (chunk_base >= 0)
-                for (int t = chunk_fill + lane; t < SEL_CHUNK; t += 32) a.cand[chunk_base + t] = __longlong_as_double(~0ll);
+            cw.finish(a.cand, lane);
             // block reduce, then one set of atomics per block
             A_hi = warp_sum64(A_hi); n_cand = warp_sum64(n_cand);
             B_lo = warp_sum128(B_lo); S_c = warp_sum128(S_c); Tot = warp_sum128(Tot);
             if (lane == 0) { s_redc[0][wid] = A_hi; s_redc[1][wid] = n_cand; s_red[0][wid] = B_lo; s_red[1][wid] = S_c; s_red[2][wid] = Tot; }
             __syncthreads();
             if (wid == 0) {
-                const int nw = SEL_THREADS / 32;
-                unsigned long long x0 = lane < nw ? s_redc[0][lane] : 0, x1 = lane < nw ? s_redc[1][lane] : 0;
-                u128 y0 = lane < nw ? s_red[0][lane] : mk128(0, 0), y1 = lane < nw ? s_red[1][lane] : mk128(0, 0),
-                     y2 = lane < nw ? s_red[2][lane] : mk128(0, 0);
+                unsigned long long x0 = lane < SEL_WARPS ? s_redc[0][lane] : 0, x1 = lane < SEL_WARPS ? s_redc[1][lane] : 0;
+                u128 y0 = lane < SEL_WARPS ? s_red[0][lane] : mk128(0, 0), y1 = lane < SEL_WARPS ? s_red[1][lane] : mk128(0, 0),
+                     y2 = lane < SEL_WARPS ? s_red[2][lane] : mk128(0, 0);
                 x0 = warp_sum64(x0); x1 = warp_sum64(x1);
                 y0 = warp_sum128(y0); y1 = warp_sum128(y1); y2 = warp_sum128(y2);
                 if (lane == 0) {
@@ -346,47 +501,46 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         // ---- block 0: verify the bracket, start the descent
         if (blockIdx.x == 0 && tid == 0) {
             res->rounds = round + 1;
-            if (round == 0) res->n_cand_first = (long long)sc->n_cand;
+            if (round == 0) {
+                res->n_cand_first = (long long)sc->n_cand; res->t_ns[2] = gtimer();
+                // total weight = kept side (>= hi, scale tot_scale) + low side (< hi, bracket scale)
+                u128 low = add128(acc_value(&sc->B_lo), acc_value(&sc->S_cand));
+                double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), tot_scale - scale);
+                res->log_total = log(tsum) - (double)tot_scale * 0.693147180559945309417232121458;
+            }
             int phase = 2;       // 2 = descend, 3 = redo classify with a new bracket, 4 = done
             if (keep_all) phase = 4;
             else if (mode == 2) {
                 // comb-rescale round: T at the new scale; lo = hi = thr so A_hi = A again
                 res->T = acc_value(&sc->B_lo); res->scale = scale;
-                phase = comb_rescale(sc, res, N, vmax) ? 3 : 4;
+                phase = comb_rescale(sc, res, N) ? 3 : 4;
             } else {
                 u128 B = acc_value(&sc->B_lo), Sc = acc_value(&sc->S_cand);
                 long long Ahi = (long long)sc->A_hi, nc = (long long)sc->n_cand;
-                bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc, fx128(lo, scale));
-                bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(B, Sc), N, Ahi, fx128(hi, scale));
+                bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc, fx70(lo, scale));
+                bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(B, Sc), N, Ahi, fx70(hi, scale));
                 if (fail_lo || fail_hi) {
                     u64 nlo = fail_lo ? 1ull : lo, nhi = fail_hi ? PF_INF_BITS : hi;
                     sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
                     sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
+                    reset_round(sc);
                     phase = 3;
                 } else {
                     sc->B_run = B; sc->A_run = Ahi; sc->count_in = nc;
                 }
             }
-            if (phase == 3) {
-                sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0;
-                for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
-            }
             sc->phase = phase;
         }
         grid.sync();
-        int phase = sc->phase;
-        if (phase == 3) continue;
-        if (phase == 4) break;
+        if (sc->phase == 3) continue;
+        if (sc->phase == 4) break;
 
         // ---- radix descent over the candidate list
         const long long list_n = (long long)sc->cand_chunks * SEL_CHUNK;
-        bool refine = false;
         for (int level = 0; level < 8; level++) {
             const u64 blo = sc->lo, bhi = sc->hi;
             const long long count_in = sc->count_in;
-            const bool to_final = count_in <= SEL_FINAL_CAP;
-            const bool single = (bhi - blo) == 1;
-            if (to_final) {
+            if (count_in <= SEL_FINAL_CAP) {
                 // compact the bracket's items into the final list
                 for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < list_n; t += (long long)gridDim.x * SEL_THREADS) {
                     u64 bits = (u64)__double_as_longlong(a.cand[t]);
@@ -398,101 +552,13 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 grid.sync();
                 break;
             }
-            if (single) break;             // one value with > SEL_FINAL_CAP ties: solved in closed form below
-            // histogram level
-            u64 width = bhi - blo;
+            if ((bhi - blo) == 1) break;       // one value with > SEL_FINAL_CAP ties: closed form below
+            const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            {
-                unsigned int *h_cnt = reinterpret_cast<unsigned int *>(smem_raw);
-                u64 *h_s0 = reinterpret_cast<u64 *>(smem_raw + SEL_BINS * 4);
-                u64 *h_s1 = h_s0 + SEL_BINS, *h_s2 = h_s1 + SEL_BINS;
-                for (int t = tid; t < SEL_BINS; t += SEL_THREADS) { h_cnt[t] = 0; h_s0[t] = 0; h_s1[t] = 0; h_s2[t] = 0; }
-                // global histogram is zeroed by block 0 before the level starts (see below)
-                __syncthreads();
-                for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < list_n; t += (long long)gridDim.x * SEL_THREADS) {
-                    u64 bits = (u64)__double_as_longlong(a.cand[t]);
-                    if (bits >= blo && bits < bhi) {
-                        int b = (int)((bits - blo) >> shift);
-                        u128 q = fx128(bits, scale);
-                        atomicAdd(&h_cnt[b], 1u);
-                        atomicAdd(&h_s0[b], q.lo & 0xffffffffull);
-                        atomicAdd(&h_s1[b], q.lo >> 32);
-                        atomicAdd(&h_s2[b], q.hi);
-                    }
-                }
-                __syncthreads();
-                for (int t = tid; t < SEL_BINS; t += SEL_THREADS)
-                    if (h_cnt[t]) {
-                        atomicAdd(&sc->h_cnt[t], h_cnt[t]);
-                        atomicAdd(&sc->h_sum[0][t], h_s0[t]);
-                        atomicAdd(&sc->h_sum[1][t], h_s1[t]);
-                        atomicAdd(&sc->h_sum[2][t], h_s2[t]);
-                    }
-                __syncthreads();
-            }
+            hist_level(a.cand, list_n, blo, bhi, shift, scale, sc, smem_raw);
             grid.sync();
-            if (blockIdx.x == 0 && wid == 0) {
-                // lane l owns bins [32 l, 32 l + 32)
-                const int per = SEL_BINS / 32;
-                u128 ls = mk128(0, 0);
-                long long lc = 0;
-                for (int k = 0; k < per; k++) {
-                    int b = lane * per + k;
-                    u128 s = add128(add128(mk128(sc->h_sum[0][b], 0), shl128(mk128(sc->h_sum[1][b], 0), 32)), mk128(0, sc->h_sum[2][b]));
-                    ls = add128(ls, s);
-                    lc += sc->h_cnt[b];
-                }
-                u128 inc = ls; long long incc = lc;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    u128 o = shfl_up128(inc, d);
-                    long long oc = __shfl_up_sync(0xffffffffu, incc, d);
-                    if (lane >= d) { inc = add128(inc, o); incc += oc; }
-                }
-                u128 pre = sub128(inc, ls);            // sum of bins before this lane's range
-                long long prec = incc - lc;
-                u128 B0 = sc->B_run; long long A0 = sc->A_run;
-                int found = SEL_BINS;                   // first bin whose UPPER boundary satisfies the predicate
-                for (int k = 0; k < per; k++) {
-                    int b = lane * per + k;
-                    u128 s = add128(add128(mk128(sc->h_sum[0][b], 0), shl128(mk128(sc->h_sum[1][b], 0), 32)), mk128(0, sc->h_sum[2][b]));
-                    pre = add128(pre, s);
-                    prec += sc->h_cnt[b];
-                    // boundary x = blo + (b+1) << shift (clamped to bhi)
-                    u64 off = ((u64)(b + 1)) << shift;
-                    u64 x = (off >= width) ? bhi : blo + off;
-                    bool ok;
-                    if (x >= PF_INF_BITS) ok = true;
-                    else ok = pred128(add128(B0, pre), N, A0 + (count_in - prec), fx128(x, scale));
-                    if (ok && found == SEL_BINS) found = b;
-                    if (off >= width) break;
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, d));
-                if (found >= SEL_BINS) found = (int)((width - 1) >> shift);      // cannot happen (bhi verified)
-                // totals strictly before / after the chosen bin
-                u128 before = mk128(0, 0); long long cbefore = 0, cin = 0;
-                for (int k = 0; k < per; k++) {
-                    int b = lane * per + k;
-                    u128 s = add128(add128(mk128(sc->h_sum[0][b], 0), shl128(mk128(sc->h_sum[1][b], 0), 32)), mk128(0, sc->h_sum[2][b]));
-                    if (b < found) { before = add128(before, s); cbefore += sc->h_cnt[b]; }
-                    if (b == found) cin = sc->h_cnt[b];
-                }
-                before = warp_sum128(before);
-                cbefore = (long long)warp_sum64((u64)cbefore);
-                cin = (long long)warp_sum64((u64)cin);
-                if (lane == 0) {
-                    u64 nlo = blo + (((u64)found) << shift);
-                    u64 off = ((u64)(found + 1)) << shift;
-                    u64 nhi = (off >= width) ? bhi : blo + off;
-                    sc->B_run = add128(B0, before);
-                    sc->A_run = A0 + (count_in - cbefore - cin);
-                    sc->lo = nlo; sc->hi = nhi; sc->count_in = cin;
-                }
-                __syncwarp();
-                for (int t = lane; t < SEL_BINS; t += 32) { sc->h_cnt[t] = 0; sc->h_sum[0][t] = 0; sc->h_sum[1][t] = 0; sc->h_sum[2][t] = 0; }
-            }
+            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, scale, 0, smem_raw);
             grid.sync();
         }
 
@@ -502,11 +568,10 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             const long long count_in = sc->count_in;
             const u128 B0 = sc->B_run;
             const long long A0 = sc->A_run;
-            u64 thr; u128 T; long long A;
             if (count_in > SEL_FINAL_CAP) {
                 // (bhi - blo) == 1: count_in copies of the single value blo
                 if (tid == 0) {
-                    u128 q = fx128(blo, scale);
+                    u128 q = fx70(blo, scale);
                     bool ok = pred128(B0, N, A0 + count_in, q);
                     s_ll[1] = ok ? (long long)blo : (long long)bhi;
                     s_ll[2] = ok ? A0 + count_in : A0;
@@ -515,14 +580,13 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 __syncthreads();
             } else {
                 int nf = (int)count_in;
-                int np2 = 1; while (np2 < nf) np2 <<= 1;
-                if (np2 < 2) np2 = 2;
+                int np2 = 2; while (np2 < nf) np2 <<= 1;
                 for (int t = tid; t < np2; t += SEL_THREADS) s_u64[t] = t < nf ? (u64)__double_as_longlong(sc->final_vals[t]) : ~0ull;
                 __syncthreads();
                 bitonic_sort_smem(s_u64, np2);
                 const int per = SEL_FINAL_CAP / SEL_THREADS;
                 u128 loc = mk128(0, 0);
-                for (int k = 0; k < per; k++) { int t = tid * per + k; if (t < nf) loc = add128(loc, fx128(s_u64[t], scale)); }
+                for (int k = 0; k < per; k++) { int t = tid * per + k; if (t < nf) loc = add128(loc, fx70(s_u64[t], scale)); }
                 u128 tot;
                 u128 pre = block_excl_scan128(loc, s_warp, &tot);
                 int first = nf;
@@ -531,8 +595,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     if (t < nf) {
                         u64 bits = s_u64[t];
                         bool head = (t == 0) || (s_u64[t - 1] != bits);
-                        if (head && first == nf && pred128(add128(B0, pre), N, A0 + (nf - t), fx128(bits, scale))) first = t;
-                        pre = add128(pre, fx128(bits, scale));
+                        if (head && first == nf && pred128(add128(B0, pre), N, A0 + (nf - t), fx70(bits, scale))) first = t;
+                        pre = add128(pre, fx70(bits, scale));
                     }
                 }
                 if (tid == 0) s_ll[0] = nf;
@@ -540,9 +604,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 atomicMin(&s_ll[0], (long long)first);
                 __syncthreads();
                 int p = (int)s_ll[0];
-                // T = B0 + sum of final items before p
                 u128 part = mk128(0, 0);
-                for (int k = 0; k < per; k++) { int t = tid * per + k; if (t < nf && t < p) part = add128(part, fx128(s_u64[t], scale)); }
+                for (int k = 0; k < per; k++) { int t = tid * per + k; if (t < nf && t < p) part = add128(part, fx70(s_u64[t], scale)); }
                 u128 tot2;
                 block_excl_scan128(part, s_warp, &tot2);
                 if (tid == 0) {
@@ -553,53 +616,48 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 __syncthreads();
             }
             if (tid == 0) {
-                thr = (u64)s_ll[1]; A = s_ll[2]; T = s_warp[0];
+                const u64 thr = (u64)s_ll[1];
+                const long long A = s_ll[2];
+                const u128 T = s_warp[0];
                 // precision: the scale must sit within 8 binades of the threshold
-                bool precise = (thr >= PF_INF_BITS) ? (scale == SEL_ITEM_BITS - e_vmax)
-                                                   : ((SEL_ITEM_BITS - scale) - exp_of_bits(thr) <= 8);
+                bool precise = (thr >= PF_INF_BITS) ? (scale == vmax_scale) : ((SEL_ITEM_BITS - scale) - exp_of_bits(thr) <= 8);
                 if (!precise && round < 30) {
-                    int e = (thr >= PF_INF_BITS) ? e_vmax : exp_of_bits(thr);
-                    // new bracket: [2^(e-1), 2^(e+2)) clipped; scale from its upper end
+                    int e = exp_of_bits(thr);
                     long long elo = e - 1 + 1023, ehi = e + 2 + 1023;
                     u64 nlo = elo <= 0 ? 1ull : ((u64)elo << 52);
                     u64 nhi = ehi >= 2047 ? PF_INF_BITS : ((u64)ehi << 52);
                     if (thr >= PF_INF_BITS) { nlo = 1; nhi = PF_INF_BITS; }
                     sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
                     sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
-                    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0;
-                    for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
+                    reset_round(sc);
                     sc->phase = 3;
                 } else {
                     res->thr_bits = thr; res->A = A; res->T = T; res->scale = scale;
-                    sc->phase = comb_rescale(sc, res, N, vmax) ? 3 : 4;
+                    sc->phase = comb_rescale(sc, res, N) ? 3 : 4;
                 }
             }
         }
-        (void)refine;
         grid.sync();
         if (sc->phase == 4) break;
     }
 
     // ---------------- outputs (block 0, thread 0)
     if (blockIdx.x == 0 && tid == 0) {
-        u128 Tot = acc_value(&sc->Tot);
-        double total = ldexp(to_double128(Tot), -tot_scale);
-        res->log_total = log(to_double128(Tot)) - (double)tot_scale * 0.693147180559945309417232121458;
-        (void)total;
-        if (M <= N || vmax == 0) {
-            res->keep_all = 1; res->thr_bits = (vmax == 0 && M > N) ? PF_INF_BITS : 0ull; res->A = (vmax == 0 && M > N) ? 0 : M; res->n = 0;
-            res->T = mk128(0, 0); res->Uoff = mk128(0, 0); res->scale = sc->scale;
+        res->t_ns[3] = gtimer();
+        if (trivial) {
+            const bool none = (vmax == 0 && M > N);
+            res->keep_all = 1; res->thr_bits = none ? PF_INF_BITS : 0ull; res->A = none ? 0 : M; res->n = 0;
+            res->T = mk128(0, 0); res->Uoff = mk128(0, 0); res->Tq = mk128(0, 0); res->Tr = 0; res->scale = sc->scale;
             res->lw_resamp = __longlong_as_double(0xFFF0000000000000ll); res->log_c = res->lw_resamp;
             res->thr_value = 0.0;
         } else {
             res->keep_all = 0;
-            long long n = N - res->A;
+            const long long n = N - res->A;
             res->n = n;
-            u128 T = res->T;
-            // Uoff = floor(mu * T / 2^53), mu = floor(u 2^53)
-            double u = *a.u;
-            u64 mu = (u64)(u * 9007199254740992.0);
-            // 192-bit product (T.hi:T.lo) * mu, then >> 53
+            const u128 T = res->T;
+            // Uoff = floor(mu * T / 2^53), mu = floor(u 2^53): 192-bit product, then >> 53
+            const double u = *a.u;
+            const u64 mu = (u64)(u * 9007199254740992.0);
             u64 p0 = T.lo * mu, p0h = mulhi64(T.lo, mu);
             u64 p1 = T.hi * mu, p1h = mulhi64(T.hi, mu);
             u64 w0 = p0, w1 = p0h + p1, w2 = p1h + (w1 < p0h ? 1ull : 0ull);
@@ -607,10 +665,13 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             U.lo = (w0 >> 53) | (w1 << 11);
             U.hi = (w1 >> 53) | (w2 << 11);
             res->Uoff = U;
-            double c = n > 0 ? ldexp(to_double128(T) / (double)n, -res->scale) : __longlong_as_double(0x7FF8000000000000ll);
+            if (n > 0) { unsigned int tr; res->Tq = divmod128_32(T, (unsigned int)n, &tr); res->Tr = tr; }
+            else { res->Tq = mk128(0, 0); res->Tr = 0; }
+            const double c = n > 0 ? ldexp(to_double128(T) / (double)n, -res->scale) : __longlong_as_double(0x7FF8000000000000ll);
             res->log_c = log(c);
             res->lw_resamp = res->log_c - res->log_total;
             res->thr_value = __longlong_as_double((long long)res->thr_bits);
         }
+        res->t_ns[4] = gtimer();
     }
 }

@@ -279,6 +279,16 @@ class ParticleFilter:
         _lib.check(self._L.pf_get_last_assignments(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
         return out
 
+    def set_profiling(self, on=True):
+        _lib.check(self._L.pf_set_profiling(self._h, int(on)), self._h)
+
+    def kernel_times(self):
+        """{class name: (device ms, launches)} accumulated since set_profiling."""
+        ms = np.zeros(10)
+        n = np.zeros(10, dtype=np.int64)
+        _lib.check(self._L.pf_get_kernel_times(self._h, ms.ctypes.data_as(_dp), n.ctypes.data_as(C.POINTER(C.c_int64))), self._h)
+        return {self._L.pf_kernel_class_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(10)}
+
     def timing(self):
         ms, n = C.c_double(), C.c_int64()
         _lib.check(self._L.pf_last_timing(self._h, C.byref(ms), C.byref(n)), self._h)

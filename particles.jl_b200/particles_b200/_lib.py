@@ -31,10 +31,13 @@ class pf_step_stats(C.Structure):
                 ("n_resamp_req", C.c_int64), ("n_resamp_got", C.c_int64), ("n_out", C.c_int64),
                 ("overflow", C.c_int64), ("log_total_w", C.c_double), ("log_w_resamp", C.c_double),
                 ("threshold", C.c_double), ("cv", C.c_double), ("resampled", C.c_int32),
-                ("select_rounds", C.c_int32), ("n_candidates", C.c_int64)]
+                ("select_rounds", C.c_int32), ("n_candidates", C.c_int64),
+                ("select_phase_us", C.c_double * 4)]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["select_phase_us"] = list(self.select_phase_us)
+        return d
 
 
 # every symbol include/particles_b200.h declares: (name, restype, argtypes)
@@ -59,6 +62,9 @@ SYMBOLS = [
     ("pf_comm_init", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     ("pf_comm_unique_id", C.c_int32, [C.c_void_p]),
     ("pf_last_timing", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
+    ("pf_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("pf_get_kernel_times", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
+    ("pf_kernel_class_name", C.c_char_p, [C.c_int32]),
     ("pf_stream", C.c_void_p, [C.c_void_p]),
     ("pf_version", C.c_char_p, []),
 ]
