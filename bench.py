@@ -134,6 +134,80 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def sharded_arm(a, dist, rank, world, local, N, K, W, config):
+    """N > 1: particles block-sharded over the ranks (one process per GPU), collectives through
+    torch.distributed / NCCL between the library's stages (particles_b200/distributed.py)."""
+    import torch
+    import particles_b200 as pb
+    from particles_b200.distributed import ShardedFearnheadParticles, TorchComm
+    dev = torch.device("cuda", local)
+    rng = np.random.default_rng(100)
+    T_all = a.burnin + W + 2 * K
+    ys = mixture(rng, T_all)
+    us = rng.random(T_all)
+    ps = ShardedFearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
+                                   pb.ChineseRestaurantProcess(1.0), TorchComm(), k_max=K_MAX, history=0, devices=[local])
+    o = 0
+    for t in range(a.burnin + W):
+        ps.fit_(ys[o], us[o]); o += 1
+    kbar0 = float(ps.ncomponents().mean())
+    n0 = len(ps)
+    launches0 = ps.shards[0].L.pf_last_timing  # noqa: F841  (kept for symmetry; launches read below)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ps.host_syncs = 0
+    ps.bytes_moved = 0
+    import ctypes as C
+    ms0, l0 = C.c_double(), C.c_int64()
+    ps.L.pf_last_timing(ps.shards[0].h, C.byref(ms0), C.byref(l0))
+    # (1) device-timed K steps: CUDA events on the stream every kernel and collective runs on
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize(dev)
+    ev0.record()
+    for t in range(K):
+        ps.fit_(ys[o], us[o]); o += 1
+    ev1.record()
+    torch.cuda.synchronize(dev); dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(ms.item())
+    ms1, l1 = C.c_double(), C.c_int64()
+    ps.L.pf_last_timing(ps.shards[0].h, C.byref(ms1), C.byref(l1))
+    syncs, moved = ps.host_syncs, ps.bytes_moved
+    # (2) end to end: wall clock around the same public call with host observation buffers
+    dist.barrier(); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for t in range(K):
+        ps.fit_(ys[o], us[o]); o += 1
+    le = ps.last_step()["log_total_w"]
+    torch.cuda.synchronize(dev); dist.barrier()
+    wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    e2e_s = float(wall.item())
+    sampler.stop_flag = True
+    kbar = 0.5 * (kbar0 + float(ps.ncomponents().mean()))
+    if rank != 0:
+        return 0
+    sampler.join(timeout=2)
+    value = n0 * K / (dev_ms / 1e3)
+    peak, peak_src = peaks()
+    bpu = bytes_per_update(kbar)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0,
+                                                host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K),
+            "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
+                    "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le)},
+            "gpu_launches": int(l1.value - l0.value) * world,
+            "roofline": {"bound": "hbm", "kernel": "whole step (per GPU)", "achieved": bpu * value / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": bpu * value / 1e9 / world / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_update": bpu},
+            "clocks": sampler.summary()}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,8 +258,7 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
     if world > 1:
-        # multi-GPU sharding is wired through pf_comm_init; see DESIGN.md section 6
-        raise SystemExit("bench.py: --gpus > 1 needs the sharded path (pf_comm_init), not built in this round")
+        return sharded_arm(a, dist, rank, world, local, N, K, W, config)
 
     rng = np.random.default_rng(100)
     T_all = a.burnin + W + 3 * K

@@ -59,6 +59,7 @@ typedef struct {
     int64_t history;          /* generations of (ancestor, assignment) kept for assignments(); 0 = none */
     int32_t device;           /* CUDA device ordinal */
     int32_t reserved0;
+    int32_t rank, nranks;     /* sharded run: this handle owns shard `rank` of `nranks` (0, 0 or 0, 1: unsharded) */
     double alpha;             /* ChineseRestaurantProcess(alpha), src/statepriors.jl:47-52 */
     double rejuv_threshold;   /* ChenLiuParticles rejuvination_threshold (percent CV), src/chenliu.jl:25 */
     double kappa0, nu0;
@@ -143,12 +144,59 @@ int32_t pf_get_last_assignments(pf_handle h, int32_t *out);  /* p.assignment - 1
 int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t N, double u, int32_t order,
                   int64_t *survivors, uint8_t *resampled, pf_step_stats *stats);
 
-/* ---- multi-GPU: particles block-sharded, one process (rank) per GPU ------------------ */
-/* nccl_unique_id: the 128 bytes of an ncclUniqueId created by rank 0 and distributed by the
- * host program (torch.distributed / MPI).  After this call n_particles is the GLOBAL budget
- * and this handle owns the shard of rank `rank`. */
-int32_t pf_comm_init(pf_handle h, int32_t rank, int32_t nranks, const void *nccl_unique_id);
-int32_t pf_comm_unique_id(void *out128);
+/* ---- multi-GPU: particles block-sharded, one process (rank) per GPU ------------------
+ * The population of a Fearnhead filter is block-sharded in global (rank-major) order; every
+ * rank runs the same kernels on its shard and the host program supplies the collectives
+ * between the stages below ("bring your own communicator": torch.distributed / NCCL in
+ * particles_b200/distributed.py, MPI.jl or NCCL.jl under the Julia shim).  What crosses the
+ * ranks per observation: two scalars (all-reduce), the strided sample and the bracket's
+ * candidates (all-gather of a few MB), one 32-byte total per rank (all-gather) and the
+ * records of the particles that change owner when the new population is re-partitioned
+ * (all-to-all-v).  All decisions are integer arithmetic on gathered data, so every rank
+ * reaches the same threshold and an N-rank run reproduces the 1-rank run bit for bit.
+ *
+ *   pf_mg_begin(y, u)                     expansion of the local shard
+ *   all_reduce(scalars[0] SUM, scalars[1] MAX)                       (M, max weight bits)
+ *   pf_mg_select(PF_MG_SAMPLE)            local strided sample -> list, acc
+ *   all_gather(acc) ; all_gather(list[0 : max chunks * 256])
+ *   pf_mg_select(PF_MG_BRACKET | PF_MG_CLASSIFY)   bracket from the gathered sample, classify the shard
+ *   all_gather(acc) ; all_gather(list ...)
+ *   pf_mg_select(PF_MG_SOLVE)             verify / descend / solve on the gathered candidates;
+ *                                         state[0] == 3 -> another PF_MG_CLASSIFY + gather + PF_MG_SOLVE
+ *   pf_mg_tiles()                         local survivor-scan totals -> local_total
+ *   all_gather(local_total)
+ *   pf_mg_finish(gathered totals)         offsets, survivor scan, instantiate (local + send buffer)
+ *   all_to_all_v(send buffer -> recv buffer, split sizes from pf_mg_plan)
+ *   pf_mg_unpack(recv buffer)             received particles -> local store; step done          */
+enum { PF_MG_SAMPLE = 1, PF_MG_BRACKET = 2, PF_MG_CLASSIFY = 4, PF_MG_SOLVE = 8 };
+typedef struct {
+    void *scalars;          /* int64[2] device: {M (sum), max weight bit pattern (max)} */
+    void *acc;              /* device: accumulator block of the threshold search, acc_bytes bytes */
+    int64_t acc_bytes;
+    void *list;             /* device: local sample / candidate list (doubles), list_capacity entries */
+    int64_t list_capacity;
+    void *local_total;      /* device: 32-byte survivor-scan total of this shard */
+    int64_t total_bytes;
+    void *send_buffer;      /* device: packed records of emigrating particles (doubles) */
+    void *recv_buffer;      /* device: packed records of immigrating particles (doubles) */
+    int64_t buffer_capacity;   /* doubles in each of send_buffer / recv_buffer */
+    int64_t rows_per_particle; /* doubles per migrating particle */
+    int64_t local_capacity;    /* particles this shard can hold */
+} pf_mg_ptrs;
+int32_t pf_set_stream(pf_handle h, void *cuda_stream);    /* run on the caller's stream (e.g. torch's current stream) */
+int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *out);
+int32_t pf_mg_begin(pf_handle h, const double *y, double u);
+int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done, const void *gathered_acc, const void *gathered_list,
+                     int64_t list_each);
+/* state[0] = phase (4 done, 3 classify again), [1] = local list entries in use (multiple of 256),
+ * [2] = 1 if this step needs the sample, [3] = classify rounds done.  Synchronises the stream. */
+int32_t pf_mg_state(pf_handle h, int64_t state[4]);
+int32_t pf_mg_tiles(pf_handle h);
+int32_t pf_mg_finish(pf_handle h, const void *gathered_totals);
+/* Exchange plan of the re-partitioning, in particles: send_counts[nranks] by destination,
+ * recv_counts[nranks] by source.  Synchronises the stream. */
+int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global);
+int32_t pf_mg_unpack(pf_handle h, const void *recv_buffer);
 
 /* ---- instrumentation ------------------------------------------------------------------ */
 /* Device milliseconds (CUDA events on the handle's stream) and kernel launches of the last

@@ -16,6 +16,8 @@ struct StepState {
     unsigned int ticket2;
     long long n_picked;     // resampled survivors
     long long n_kept;       // kept survivors
+    long long goff;         // sharded run: global index of this shard's first particle
+    long long n_global;     // sharded run: population over all shards after the step
 };
 
 struct StepLog {            // one record per step, read back after pf_filter
@@ -149,11 +151,69 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
 // -- one exclusive scan of (X, kept), no second dependent scan.  Three launches, no
 // spinning: per-tile sums, one-block prefix over the tiles, apply.
 #define SCAN_THREADS 256
+#define PF_MAX_RANKS 16
 struct TileSum {
     u128 X;
     unsigned int kept;
     unsigned int pad[3];
 };
+
+// Sharded run (particles block-sharded over ranks, global order = rank-major): where this
+// rank's survivors sit in the global survivor order, and how the new population is
+// re-partitioned into equal blocks of q particles (rank r owns global [r q, (r+1) q)).
+struct RankOff {
+    u128 S_off;                    // fixed-point low mass of all lower ranks
+    long long kept_off;            // survivors kept on all lower ranks
+    long long g_first;             // global index of this rank's first survivor
+    long long n_local;             // survivors produced by this rank
+    long long n_mine;              // particles this rank owns after re-partitioning
+    long long n_global, q;
+    long long goff_prev;           // global index of this rank's first PARENT (genealogy)
+    int rank, nranks;
+    long long send_start[PF_MAX_RANKS], send_len[PF_MAX_RANKS], send_off[PF_MAX_RANKS];   // by destination (particles / doubles)
+    long long recv_idx0[PF_MAX_RANKS], recv_len[PF_MAX_RANKS], recv_off[PF_MAX_RANKS];    // by source
+};
+
+// one thread: turn the gathered per-rank totals (mass of the low partition, kept count) into
+// this rank's offsets and the exchange plan.  rows = doubles per migrating particle.
+__global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, int nranks, const SelResult *__restrict__ res,
+                               StepState *st, RankOff *ro, int rows)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const bool comb = res->n > 0 && !isz128(res->T);
+    const u64 n = (u64)res->n;
+    u128 Spre = mk128(0, 0);
+    long long kpre = 0, gpre = 0, tpre = 0;
+    long long g_first[PF_MAX_RANKS], n_loc[PF_MAX_RANKS];
+    long long my_kept = 0, my_picked = 0;
+    for (int r = 0; r < nranks; r++) {
+        u128 Snext = add128(Spre, gathered[r].X);
+        long long tnext = comb ? (long long)teeth_below(mul128_64(Snext, n), res->Uoff, res->T) : 0;
+        long long picked = tnext - tpre;
+        g_first[r] = gpre; n_loc[r] = (long long)gathered[r].kept + picked;
+        if (r == rank) { ro->S_off = Spre; ro->kept_off = kpre; my_kept = gathered[r].kept; my_picked = picked; }
+        Spre = Snext; kpre += gathered[r].kept; tpre = tnext; gpre += n_loc[r];
+    }
+    const long long n_global = gpre;
+    long long q = (n_global + nranks - 1) / nranks;
+    if (q < 1) q = 1;
+    ro->g_first = g_first[rank]; ro->n_local = n_loc[rank]; ro->n_global = n_global; ro->q = q;
+    long long mine = n_global - (long long)rank * q;
+    ro->n_mine = mine < 0 ? 0 : (mine > q ? q : mine);
+    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff;
+    long long soff = 0, roff = 0;
+    for (int d = 0; d < nranks; d++) {
+        long long lo = g_first[rank] > d * q ? g_first[rank] : d * q;
+        long long hi = g_first[rank] + n_loc[rank] < (d + 1) * q ? g_first[rank] + n_loc[rank] : (d + 1) * q;
+        long long len = (d == rank || hi <= lo) ? 0 : hi - lo;
+        ro->send_start[d] = lo; ro->send_len[d] = len; ro->send_off[d] = soff; soff += len * rows;
+        long long lo2 = g_first[d] > rank * q ? g_first[d] : rank * q;
+        long long hi2 = g_first[d] + n_loc[d] < (rank + 1) * q ? g_first[d] + n_loc[d] : (rank + 1) * q;
+        long long len2 = (d == rank || hi2 <= lo2) ? 0 : hi2 - lo2;
+        ro->recv_idx0[d] = lo2 - rank * q; ro->recv_len[d] = len2; ro->recv_off[d] = roff; roff += len2 * rows;
+    }
+    st->n_kept = my_kept; st->n_picked = my_picked; st->n_next = ro->n_mine; st->n_global = n_global;
+}
 
 // mode 0: index-order step (always runs); mode 1: flat sorted list, runs only when the step
 // resamples and emits the PICKED positions only (kept = suffix of the sorted list);
@@ -204,7 +264,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
 
 // exclusive prefix over the tiles (in place) and the step's survivor counts; one block
 __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelResult *__restrict__ res,
-                                                      const long long *__restrict__ n_items_ptr, StepState *st, int mode)
+                                                      const long long *__restrict__ n_items_ptr, StepState *st, int mode,
+                                                      TileSum *local_tot /* sharded run: totals out, counts set later */)
 {
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
@@ -229,9 +290,12 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelR
         runX = add128(runX, x); runK += k;
     }
     if (threadIdx.x == 0) {
-        const bool comb = res->n > 0 && !isz128(res->T);
-        long long picked = comb ? (long long)teeth_below(mul128_64(totX, (u64)res->n), res->Uoff, res->T) : 0;
-        st->n_kept = totK; st->n_picked = picked; st->n_next = (long long)totK + picked;
+        if (local_tot) { local_tot->X = totX; local_tot->kept = totK; }
+        else {
+            const bool comb = res->n > 0 && !isz128(res->T);
+            long long picked = comb ? (long long)teeth_below(mul128_64(totX, (u64)res->n), res->Uoff, res->T) : 0;
+            st->n_kept = totK; st->n_picked = picked; st->n_next = (long long)totK + picked; st->n_global = st->n_next;
+        }
     }
 }
 
@@ -239,7 +303,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                                                              long long cap, const SelResult *__restrict__ res,
                                                              const long long *__restrict__ n_items_ptr,
                                                              const TileSum *__restrict__ tiles, unsigned int *__restrict__ surv_parent,
-                                                             unsigned char *__restrict__ surv_slot, int mode)
+                                                             unsigned char *__restrict__ surv_slot, int mode,
+                                                             const RankOff *__restrict__ ro)
 {
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
@@ -278,6 +343,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
     // by (Tq, Tr) = divmod(T, n) from tooth to tooth.
     u128 S = add128(tiles[blockIdx.x].X, exX);
     long long kcount = (long long)tiles[blockIdx.x].kept + exK;
+    if (ro) { S = add128(S, ro->S_off); kcount += ro->kept_off - ro->g_first; }     // positions relative to this rank's first survivor
     u64 t = 0;
     u128 Q = mk128(0, 0);
     unsigned int R = 0;
@@ -325,25 +391,43 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
                                                      const SelResult *__restrict__ res, const double *__restrict__ V,
                                                      const unsigned int *__restrict__ surv_parent,
                                                      const unsigned char *__restrict__ surv_slot,
-                                                     unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg)
+                                                     unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
+                                                     const RankOff *__restrict__ ro, double *__restrict__ sendbuf, int k_max)
 {
     using L = Layout<D>;
-    const long long n_next = st->n_next;
+    const long long n_out = ro ? ro->n_local : st->n_next;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_next) return;
+    if (t >= n_out) return;
+    // destination of child t: a local index, or a slot of the packed send buffer of another rank
+    double *dstb = S2 + t;
+    long long stride = cap, idx = t;
+    bool remote = false;
+    unsigned int anc_off = 0;
+    if (ro) {
+        const long long g = ro->g_first + t;
+        const long long dest = g / ro->q;
+        anc_off = (unsigned int)ro->goff_prev;
+        if (dest == ro->rank) { idx = g - dest * ro->q; dstb = S2 + idx; }
+        else { remote = true; stride = ro->send_len[dest]; dstb = sendbuf + ro->send_off[dest] + (g - ro->send_start[dest]); }
+    }
     const unsigned int par = surv_parent[t];
     const unsigned char sl = surv_slot[t];
     const int j = sl & 0x7F;
     const bool picked = sl & 0x80;
     const int K = Kc[par];
     const double v = V[(long long)j * cap + par];
-    logw2[t] = picked ? res->lw_resamp : (log(v) - res->log_total);
-    Kc2[t] = K + (j == K ? 1 : 0);
-    if (gen_anc) { gen_anc[t] = par; gen_asg[t] = (unsigned char)j; }
+    const double lw = picked ? res->lw_resamp : (log(v) - res->log_total);
+    const int Knew = K + (j == K ? 1 : 0);
+    if (!remote) {
+        logw2[idx] = lw; Kc2[idx] = Knew;
+        if (gen_anc) { gen_anc[idx] = par + anc_off; gen_asg[idx] = (unsigned char)j; }
+    } else {
+        double *hdr = dstb + (long long)k_max * L::F * stride;
+        hdr[0] = lw; hdr[stride] = (double)Knew; hdr[2 * stride] = (double)(par + anc_off); hdr[3 * stride] = (double)j;
+    }
     // copy the parent's slots (the chosen one is rewritten below)
     {
         const double *src = S + par;
-        double *dst = S2 + t;
         const int nrows = K * L::F;
         int r = 0;
         for (; r + 8 <= nrows; r += 8) {
@@ -351,13 +435,13 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
 #pragma unroll
             for (int k = 0; k < 8; k++) tmp[k] = src[(long long)(r + k) * cap];
 #pragma unroll
-            for (int k = 0; k < 8; k++) dst[(long long)(r + k) * cap] = tmp[k];
+            for (int k = 0; k < 8; k++) dstb[(long long)(r + k) * stride] = tmp[k];
         }
-        for (; r < nrows; r++) dst[(long long)r * cap] = src[(long long)r * cap];
+        for (; r < nrows; r++) dstb[(long long)r * stride] = src[(long long)r * cap];
     }
     if (j < K) {
         const double *src = S + ((long long)j * L::F) * cap + par;
-        double *dst = S2 + ((long long)j * L::F) * cap + t;
+        double *dst = dstb + ((long long)j * L::F) * stride;
         double n = src[(long long)L::F_N * cap];
         double logdet = src[(long long)L::F_LOGDET * cap];
         double m[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1], dx[D], z[D];
@@ -374,22 +458,45 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
         for (int k = 0; k < D; k++) dx[k] *= sr;
         chol_rank1<D>(dinv, off, dx);
         double tw = n + 1.0;
-        dst[(long long)L::F_N * cap] = tw;
-        dst[(long long)L::F_LOGDET * cap] = logdet + log1p(row.r * q);
+        dst[(long long)L::F_N * stride] = tw;
+        dst[(long long)L::F_LOGDET * stride] = logdet + log1p(row.r * q);
 #pragma unroll
         for (int k = 0; k < D; k++) {
             double delta = scp->y[k] - m[k];                       // Welford, src/component.jl:46-47
-            dst[(long long)(L::F_MEAN + k) * cap] = m[k] + delta / tw;
-            dst[(long long)(L::F_DINV + k) * cap] = dinv[k];
+            dst[(long long)(L::F_MEAN + k) * stride] = m[k] + delta / tw;
+            dst[(long long)(L::F_DINV + k) * stride] = dinv[k];
         }
 #pragma unroll
-        for (int k = 0; k < L::NOFF; k++) dst[(long long)(L::F_OFF + k) * cap] = off[k];
-    }
-    if (j == K) {
-        double *dst = S2 + ((long long)K * L::F) * cap + t;
+        for (int k = 0; k < L::NOFF; k++) dst[(long long)(L::F_OFF + k) * stride] = off[k];
+    } else {
+        double *dst = dstb + ((long long)K * L::F) * stride;
 #pragma unroll
-        for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = scp->newslot[f];
+        for (int f = 0; f < L::F; f++) dst[(long long)f * stride] = scp->newslot[f];
     }
+}
+
+// sharded run: particles received from other ranks (packed [row][k] per source segment)
+// are written to their local indices
+__global__ void __launch_bounds__(256) k_unpack(const double *__restrict__ recv, const RankOff *__restrict__ ro,
+                                                double *__restrict__ S2, int *__restrict__ Kc2, double *__restrict__ logw2,
+                                                unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
+                                                long long cap, int store_rows, int F)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int s = 0;
+    const int G = ro->nranks;
+    while (s < G && t >= ro->recv_len[s]) { t -= ro->recv_len[s]; s++; }
+    if (s >= G) return;
+    const long long stride = ro->recv_len[s];
+    const double *src = recv + ro->recv_off[s] + t;
+    const long long idx = ro->recv_idx0[s] + t;
+    const double *hdr = src + (long long)store_rows * stride;
+    const int K = (int)hdr[stride];
+    logw2[idx] = hdr[0]; Kc2[idx] = K;
+    if (gen_anc) { gen_anc[idx] = (unsigned int)hdr[2 * stride]; gen_asg[idx] = (unsigned char)hdr[3 * stride]; }
+    const int nrows = K * F;
+    double *dst = S2 + idx;
+    for (int r = 0; r < nrows; r++) dst[(long long)r * cap] = src[(long long)r * stride];
 }
 
 // ------------------------------------------------------------------ reference-literal order

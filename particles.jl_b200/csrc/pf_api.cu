@@ -56,6 +56,18 @@ struct pf_filter_s {
     u128 *cum = nullptr;
     unsigned char *asg_tmp = nullptr;
     double *cl_part = nullptr;
+    // sharded run
+    int rank = 0, nranks = 1;
+    long long *gscal = nullptr;           // {M, vmax bits} published for the all-reduce
+    TileSum *local_tot = nullptr;
+    RankOff *ro = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr;
+    long long buf_cap = 0;
+    int mig_rows = 0;
+    long long surv_cap = 0;
+    int mg_rounds = 0;
+    bool own_stream = true;
+    double *y1_dev = nullptr;             // y (d) + u (1) of the current sharded step
     // genealogy
     unsigned int *gen_anc = nullptr;
     unsigned char *gen_asg = nullptr;
@@ -199,11 +211,12 @@ extern "C" int32_t pf_destroy(pf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
-                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos};
+                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->gscal, h->local_tot, h->ro, h->sendbuf,
+                    h->recvbuf, h->y1_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return PF_OK;
 }
@@ -226,6 +239,10 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (!cfg->mu0) return set_error(nullptr, PF_ERR_ARG, "pf_create: mu0 is null");
     if (cfg->order != PF_ORDER_INDEX && cfg->order != PF_ORDER_SORTED) return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown order");
     if (cfg->history < 0) return set_error(nullptr, PF_ERR_ARG, "pf_create: history must be >= 0");
+    if (cfg->nranks > 1) {
+        if (cfg->nranks > PF_MAX_RANKS || cfg->rank < 0 || cfg->rank >= cfg->nranks) return set_error(nullptr, PF_ERR_ARG, "pf_create: bad rank / nranks");
+        if (cfg->filter_kind != PF_FEARNHEAD || cfg->order != PF_ORDER_INDEX) return set_error(nullptr, PF_ERR_ARG, "pf_create: sharded runs support the index-order Fearnhead filter");
+    }
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -234,7 +251,10 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
 
     pf_filter_s *h = new pf_filter_s();
     h->cfg = *cfg;
-    h->d = d; h->k_max = cfg->k_max; h->N = cfg->n_particles; h->cap = cfg->n_particles;
+    h->d = d; h->k_max = cfg->k_max; h->N = cfg->n_particles;
+    h->nranks = cfg->nranks > 1 ? cfg->nranks : 1;
+    h->rank = h->nranks > 1 ? cfg->rank : 0;
+    h->cap = (cfg->n_particles + h->nranks - 1) / h->nranks;
     h->F = 2 + d + d * (d + 1) / 2;
     h->mu0.assign(cfg->mu0, cfg->mu0 + d);
     h->lam0.assign(d * d, 0.0);
@@ -266,8 +286,17 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     }
     CT(dmalloc(&h->V, (size_t)(h->k_max + 1) * cap));
     CT(dmalloc(&h->cnt, cap));
-    CT(dmalloc(&h->surv_parent, cap));
-    CT(dmalloc(&h->surv_slot, cap));
+    h->surv_cap = h->nranks > 1 ? 2 * cap + 1024 : cap;
+    CT(dmalloc(&h->surv_parent, h->surv_cap));
+    CT(dmalloc(&h->surv_slot, h->surv_cap));
+    if (h->nranks > 1) {
+        h->mig_rows = h->k_max * h->F + 4;
+        h->buf_cap = (h->surv_cap) * (long long)h->mig_rows;
+        CT(dmalloc(&h->gscal, 2)); CT(dmalloc(&h->local_tot, 1)); CT(dmalloc(&h->ro, 1));
+        CT(dmalloc(&h->sendbuf, (size_t)h->buf_cap)); CT(dmalloc(&h->recvbuf, (size_t)h->buf_cap));
+        CT(dmalloc(&h->y1_dev, (size_t)d + 1));
+        CT(cudaMemsetAsync(h->ro, 0, sizeof(RankOff), h->stream));
+    }
     long long ntiles = (cap + SCAN_THREADS - 1) / SCAN_THREADS;
     if (cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_SORTED) {
         const long long n_pad = cap * (h->k_max + 1);
@@ -318,7 +347,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     StepState st0;
     memset(&st0, 0, sizeof st0);
     if (cfg->filter_kind == PF_FEARNHEAD) {
-        st0.n_live = 1; st0.n_next = 1;              // src/fearnhead.jl:29-30
+        st0.n_live = h->rank == 0 ? 1 : 0; st0.n_next = st0.n_live;     // src/fearnhead.jl:29-30 (the particle lives on rank 0)
         h->n_host = 1; h->ub_live = 1;
     } else {
         st0.n_live = h->N; st0.n_next = h->N;        // src/chenliu.jl:25-26
@@ -349,6 +378,7 @@ static int32_t launch_select(pf_handle h, const double *V, const unsigned char *
     SelArgs a;
     a.V = V; a.cnt = cnt; a.cap = cap; a.n_live = n_live; a.M = M; a.vmax_bits = vmax; a.N = N; a.u = u_dev;
     a.cand = cand; a.cand_cap = cand_cap; a.sc = sc; a.res = res;
+    a.stage = SEL_ST_ALL; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr;
     void *args[] = {&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
     return PF_OK;
@@ -396,28 +426,28 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         LaunchTimer lt(h, KC_SCAN, 7);
         const int gflat = grid_for(n_pad, SCAN_THREADS), gidx = grid_for(ub, SCAN_THREADS);
         k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr);
         k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles,
-                                                             h->pick_pos, h->surv_slot, 1);
+                                                             h->pick_pos, h->surv_slot, 1, nullptr);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
                                                                            h->surv_slot);
         k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 2);
+                                                            h->surv_slot, 2, nullptr);
     } else {
         LaunchTimer lt(h, KC_SCAN, 3);
         const int gidx = grid_for(ub, SCAN_THREADS);
         k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 0);
+                                                            h->surv_slot, 0, nullptr);
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
         k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs);
+                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max);
     }
     {
         LaunchTimer lt(h, KC_STEPLOG);
@@ -568,7 +598,7 @@ extern "C" int32_t pf_last_timing(pf_handle h, double *device_ms, int64_t *kerne
 {
     if (!h) return PF_ERR_ARG;
     if (device_ms) *device_ms = h->last_ms;
-    if (kernel_launches) *kernel_launches = h->last_launches;
+    if (kernel_launches) *kernel_launches = h->nranks > 1 ? h->launches : h->last_launches;
     return PF_OK;
 }
 
@@ -797,8 +827,8 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         rc = launch_select(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res);
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
         k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0);
-        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr);
+        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr);
         ST(cudaGetLastError());
         StepState s1; SelResult r1;
         ST(cudaMemcpyAsync(&s1, st, sizeof s1, cudaMemcpyDeviceToHost, h->stream));
@@ -847,14 +877,186 @@ done:
     return rc;
 }
 
-// ------------------------------------------------------------------ multi-GPU (see comm.cuh)
-extern "C" int32_t pf_comm_unique_id(void *out128)
+// ------------------------------------------------------------------ sharded run (bring your own collective)
+__global__ void k_publish_scalars(const StepState *st, long long *gscal)
 {
-    (void)out128;
-    return set_error(nullptr, PF_ERR_NCCL, "pf_comm_unique_id: multi-GPU sharding is not built yet");
+    if (threadIdx.x || blockIdx.x) return;
+    gscal[0] = st->M; gscal[1] = (long long)st->vmax_bits;
 }
-extern "C" int32_t pf_comm_init(pf_handle h, int32_t rank, int32_t nranks, const void *id)
+
+__global__ void k_steplog_mg(StepState *st, const SelResult *res, const RankOff *ro, StepLog *lg)
 {
-    (void)rank; (void)nranks; (void)id;
-    return set_error(h, PF_ERR_NCCL, "pf_comm_init: multi-GPU sharding is not built yet");
+    if (threadIdx.x || blockIdx.x) return;
+    StepLog r;
+    r.n_in = st->n_live; r.M = st->M; r.n_kept = st->n_kept; r.n_req = res->keep_all ? 0 : res->n;
+    r.n_got = st->n_picked; r.n_out = ro->n_global; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
+    r.log_total = res->log_total; r.lw_resamp = res->lw_resamp; r.thr = res->thr_value; r.cv = 0.0;
+    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds;
+    for (int k = 0; k < 4; k++) r.sel_us[k] = 0.0;
+    *lg = r;
+    st->goff = (long long)ro->rank * ro->q;
+}
+
+#define MG_CHECK(h) do { if (!(h)) return PF_ERR_ARG; if ((h)->nranks < 2) return set_error((h), PF_ERR_STATE, "not a sharded handle (pf_config.nranks < 2)"); } while (0)
+
+extern "C" int32_t pf_set_stream(pf_handle h, void *cuda_stream)
+{
+    if (!h) return PF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream; h->own_stream = false;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *o)
+{
+    MG_CHECK(h);
+    if (!o) return PF_ERR_ARG;
+    o->scalars = h->gscal;
+    o->acc = (char *)h->sc + SEL_ACC_OFFSET; o->acc_bytes = sizeof(SelAcc);
+    o->list = h->cand; o->list_capacity = h->cand_cap;
+    o->local_total = h->local_tot; o->total_bytes = sizeof(TileSum);
+    o->send_buffer = h->sendbuf; o->recv_buffer = h->recvbuf; o->buffer_capacity = h->buf_cap;
+    o->rows_per_particle = h->mig_rows; o->local_capacity = h->cap;
+    return PF_OK;
+}
+
+template <int D>
+static int32_t mg_begin(pf_handle h)
+{
+    if (h->slog_cap < 1) { CUDA_TRY(dmalloc(&h->slog, 16)); h->slog_cap = 16; }
+    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0);
+    k_expand<D><<<grid_for(h->cap, 256), 256, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->k_max, h->tab,
+                                                                h->pc, h->stc, h->st, h->V, h->cnt);
+    k_publish_scalars<<<1, 32, 0, h->stream>>>(h->st, h->gscal);
+    h->launches += 3;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_begin(pf_handle h, const double *y, double u)
+{
+    MG_CHECK(h);
+    if (!y) return PF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int32_t rc = ensure_table(h, h->steps + 3);
+    if (rc != PF_OK) return rc;
+    if (h->hist_cap && h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
+    double buf[PF_MAX_D + 1];
+    for (int k = 0; k < h->d; k++) buf[k] = y[k];
+    buf[h->d] = u;
+    CUDA_TRY(cudaMemcpyAsync(h->y1_dev, buf, sizeof(double) * (h->d + 1), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));       // buf is on the stack
+    h->mg_rounds = 0;
+    DISPATCH_D(h->d, rc = mg_begin<D>(h));
+    CUDA_TRY(cudaGetLastError());
+    return rc;
+}
+
+extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done, const void *gacc, const void *glist, int64_t list_each)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    SelArgs a;
+    a.V = h->V; a.cnt = h->cnt; a.cap = h->cap; a.n_live = &h->st->n_live;
+    a.M = h->gscal; a.vmax_bits = (const u64 *)(h->gscal + 1);
+    a.N = h->N; a.u = h->y1_dev + h->d; a.cand = h->cand; a.cand_cap = h->cand_cap; a.sc = h->sc; a.res = h->res;
+    a.stage = stage; a.round0 = rounds_done; a.nranks = h->nranks; a.gacc = (const SelAcc *)gacc;
+    a.glist = (const double *)glist; a.glist_each = list_each;
+    a.goff = &h->st->goff;
+    void *args[] = {&a};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
+    h->launches++;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_state(pf_handle h, int64_t state[4])
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    SelScratch hdr;
+    CUDA_TRY(cudaMemcpyAsync(&hdr, h->sc, offsetof(SelScratch, B_run), cudaMemcpyDeviceToHost, h->stream));
+    long long gs[2];
+    CUDA_TRY(cudaMemcpyAsync(gs, h->gscal, sizeof gs, cudaMemcpyDeviceToHost, h->stream));
+    SelResult r;
+    CUDA_TRY(cudaMemcpyAsync(&r, h->res, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    state[0] = hdr.phase;
+    state[1] = (int64_t)hdr.cand_chunks * SEL_CHUNK;
+    state[2] = (gs[0] > h->N && gs[1] != 0 && gs[0] > SEL_FINAL_CAP) ? 1 : 0;
+    state[3] = r.rounds;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_tiles(pf_handle h)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int g = grid_for(h->cap, SCAN_THREADS);
+    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0);
+    k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, h->local_tot);
+    h->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+template <int D>
+static int32_t mg_finish(pf_handle h, const TileSum *gathered)
+{
+    const int cur = h->cur, nxt = cur ^ 1;
+    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
+    if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
+    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows);
+    k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
+                                                                                  h->surv_parent, h->surv_slot, 0, h->ro);
+    k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
+                                                                          h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
+                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max);
+    h->launches += 3;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_finish(pf_handle h, const void *gathered_totals)
+{
+    MG_CHECK(h);
+    if (!gathered_totals) return PF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int32_t rc = PF_OK;
+    DISPATCH_D(h->d, rc = mg_finish<D>(h, (const TileSum *)gathered_totals));
+    CUDA_TRY(cudaGetLastError());
+    return rc;
+}
+
+extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    RankOff r;
+    CUDA_TRY(cudaMemcpyAsync(&r, h->ro, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (r.n_local > h->surv_cap) return set_error(h, PF_ERR_OVERFLOW, "shard produced more survivors than its survivor list holds (imbalance)");
+    for (int k = 0; k < h->nranks; k++) { if (send_counts) send_counts[k] = r.send_len[k]; if (recv_counts) recv_counts[k] = r.recv_len[k]; }
+    if (n_local) *n_local = r.n_local;
+    if (n_global) *n_global = r.n_global;
+    h->n_host = r.n_mine;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_unpack(pf_handle h, const void *recv)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int nxt = h->cur ^ 1;
+    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
+    if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
+    k_unpack<<<grid_for(h->cap, 256), 256, 0, h->stream>>>((const double *)recv, h->ro, h->S[nxt], h->Kc[nxt], h->logw[nxt], ga, gs,
+                                                            h->cap, h->k_max * h->F, h->F);
+    k_steplog_mg<<<1, 32, 0, h->stream>>>(h->st, h->res, h->ro, h->slog);
+    h->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(&h->last, h->slog, sizeof(StepLog), cudaMemcpyDeviceToHost, h->stream));
+    h->have_last = true;
+    h->cur = nxt;
+    h->steps++;
+    return PF_OK;
 }

@@ -62,17 +62,17 @@ struct SelScratch {
     int mode;                       // 0 bracket round, 1 keep everything, 2 comb-rescale round (lo = hi = thr)
     long long count_in;             // list items inside [lo, hi)
     long long mult;                 // sample stride while solving the sample, 1 otherwise
-    // accumulators of the classify pass
+    // accumulators of the classify pass (SelAcc: the block a sharded run all-gathers)
     unsigned long long A_hi;        // #items >= hi
     unsigned long long n_cand;      // #items in [lo, hi)
     acc128 B_lo;                    // sum q of items < lo
     acc128 S_cand;                  // sum q of items in [lo, hi)
     acc128 Tot;                     // sum of the items >= hi at scale SEL_TOT_BITS - e(vmax)
+    unsigned long long cand_chunks; // chunks handed out of the candidate / sample list
+    unsigned long long acc_pad;
     // running totals of the descent
     u128 B_run;                     // sum q of list items < lo (after narrowing)
     long long A_run;                // #list items >= hi (after narrowing)
-    // candidate / sample list
-    unsigned long long cand_chunks; // chunks handed out
     // final list
     unsigned int final_n;
     double final_vals[SEL_FINAL_CAP];
@@ -80,6 +80,18 @@ struct SelScratch {
     unsigned int h_cnt[SEL_BINS];
     u64 h_sum[3][SEL_BINS];
 };
+
+// the accumulator block of SelScratch as a stand-alone record (sharded runs gather one per rank)
+struct SelAcc {
+    unsigned long long A_hi, n_cand;
+    acc128 B_lo, S_cand, Tot;
+    unsigned long long cand_chunks, acc_pad;
+};
+#define SEL_ACC_OFFSET offsetof(SelScratch, A_hi)
+
+// stages of k_select: a single-GPU step runs all of them in one launch; a sharded step runs
+// them as separate launches with an all-gather between (see particles_b200/distributed.py)
+enum { SEL_ST_SAMPLE = 1, SEL_ST_BRACKET = 2, SEL_ST_CLASSIFY = 4, SEL_ST_SOLVE = 8, SEL_ST_ALL = 15 };
 
 struct SelArgs {
     const double *V;
@@ -94,7 +106,28 @@ struct SelArgs {
     long long cand_cap;             // in doubles
     SelScratch *sc;
     SelResult *res;
+    int stage;                      // SEL_ST_* bit mask
+    int round0;                     // number of classify rounds already done (sharded re-entry)
+    int nranks;                     // > 1: accumulators / lists come gathered from all ranks
+    const SelAcc *gacc;             // [nranks] gathered accumulator blocks
+    const double *glist;            // gathered sample / candidate list (nranks * glist_each doubles)
+    long long glist_each;           // doubles per rank in glist (padded with the NaN pattern)
+    const long long *goff;          // device: global index of the shard's first particle (phase of the strided sample)
 };
+
+// sharded run: sum the gathered per-rank accumulator blocks into the local scratch
+__device__ inline void sum_gathered(SelScratch *sc, const SelAcc *g, int nranks)
+{
+    unsigned long long A = 0, nc = 0, ch = 0;
+    acc128 b, c, t;
+    for (int k = 0; k < 4; k++) { b.l[k] = 0; c.l[k] = 0; t.l[k] = 0; }
+    for (int r = 0; r < nranks; r++) {
+        A += g[r].A_hi; nc += g[r].n_cand; ch += g[r].cand_chunks;
+        for (int k = 0; k < 4; k++) { b.l[k] += g[r].B_lo.l[k]; c.l[k] += g[r].S_cand.l[k]; t.l[k] += g[r].Tot.l[k]; }
+    }
+    sc->A_hi = A; sc->n_cand = nc; sc->B_lo = b; sc->S_cand = c; sc->Tot = t;
+    (void)ch;
+}
 
 __device__ __forceinline__ unsigned long long gtimer()
 {
@@ -376,8 +409,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
     const int vmax_scale = SEL_ITEM_BITS - e_vmax;
     const bool trivial = (M <= N || vmax == 0);
     const bool sampled = !trivial && M > SEL_FINAL_CAP;
+    const int stage = a.stage;
+    const bool multi = a.nranks > 1;
+    const double *list = multi ? a.glist : a.cand;
 
     // ---------------- phase 0: first bracket
+    if (stage & SEL_ST_SAMPLE) {
     if (blockIdx.x == 0 && tid == 0) {
         reset_round(sc);
         for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
@@ -391,14 +428,19 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         }
     }
     grid.sync();
-    if (sampled) {
-        // strided sample of whole particles, appended to the (still unused) candidate list
-        const long long stride = (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
+    }
+    const long long stride = (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
+    if (!sampled && (stage & SEL_ST_SAMPLE) && !(stage & SEL_ST_BRACKET)) return;    // sharded: nothing to sample
+    if (sampled && (stage & SEL_ST_SAMPLE)) {
+        // strided sample of whole particles (global indices = 0 mod stride), appended to the
+        // (still unused) candidate list
         {
             ChunkWriter cw; cw.init();
             unsigned long long cnt_s = 0;
-            for (long long base = gwarp * 32; base * stride < n_live; base += nwarps * 32) {
-                long long i = (base + lane) * stride;
+            const long long sphase = a.goff ? *a.goff : 0;
+            const long long first = (stride - (sphase % stride)) % stride;
+            for (long long base = gwarp * 32; first + base * stride < n_live; base += nwarps * 32) {
+                long long i = first + (base + lane) * stride;
                 int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
                 int maxc = c;
 #pragma unroll
@@ -414,20 +456,25 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             cw.finish(a.cand, lane);
             cnt_s = warp_sum64(cnt_s);
             if (lane == 0 && cnt_s) atomicAdd(&sc->n_cand, cnt_s);
+            if (!(stage & SEL_ST_BRACKET)) return;          // sharded: the host gathers the samples
+            grid.sync();
         }
-        grid.sync();
+    }
+    if (sampled && (stage & SEL_ST_BRACKET)) {
         if (blockIdx.x == 0 && tid == 0) {
+            if (multi) sum_gathered(sc, a.gacc, a.nranks);
             sc->B_run = mk128(0, 0); sc->A_run = 0; sc->count_in = (long long)sc->n_cand; sc->mult = stride; sc->phase = 2;
+            sc->lo = 1; sc->hi = PF_INF_BITS;
         }
         grid.sync();
-        const long long list_n = (long long)sc->cand_chunks * SEL_CHUNK;
+        const long long list_n = multi ? a.glist_each * a.nranks : (long long)sc->cand_chunks * SEL_CHUNK;
         for (int level = 0; level < 8; level++) {
             const u64 blo = sc->lo, bhi = sc->hi;
             if (sc->count_in == 0 || (bhi - blo) <= 1) break;
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            hist_level(a.cand, list_n, blo, bhi, shift, vmax_scale, sc, smem_raw);
+            hist_level(list, list_n, blo, bhi, shift, vmax_scale, sc, smem_raw);
             grid.sync();
             if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, vmax_scale, 1, smem_raw);
             grid.sync();
@@ -440,19 +487,20 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             sc->lo = lo; sc->hi = hi; sc->mode = 0; sc->mult = 1;
             sc->scale = SEL_ITEM_BITS - exp_of_bits(hi >= PF_INF_BITS ? vmax : hi);
             reset_round(sc);
+            for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
         }
     }
-    if (blockIdx.x == 0 && tid == 0) res->t_ns[1] = gtimer();
+    if (blockIdx.x == 0 && tid == 0 && (stage & SEL_ST_BRACKET)) res->t_ns[1] = gtimer();
     grid.sync();
 
     // ---------------- rounds
-    for (int round = 0; round < 40; round++) {
+    for (int round = a.round0; round < 40; round++) {
         const u64 lo = sc->lo, hi = sc->hi;
         const int scale = sc->scale;
         const int mode = sc->mode;
         const bool keep_all = (mode == 1);
         // ---- classify pass over all items
-        {
+        if (stage & SEL_ST_CLASSIFY) {
             unsigned long long A_hi = 0, n_cand = 0;
             u128 B_lo = mk128(0, 0), S_c = mk128(0, 0), Tot = mk128(0, 0);
             ChunkWriter cw; cw.init();
@@ -495,11 +543,13 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 }
             }
             __syncthreads();
+            if (!(stage & SEL_ST_SOLVE)) return;             // sharded: the host gathers accumulators + candidates
+            grid.sync();
         }
-        grid.sync();
 
         // ---- block 0: verify the bracket, start the descent
         if (blockIdx.x == 0 && tid == 0) {
+            if (multi) sum_gathered(sc, a.gacc, a.nranks);
             res->rounds = round + 1;
             if (round == 0) {
                 res->n_cand_first = (long long)sc->n_cand; res->t_ns[2] = gtimer();
@@ -532,18 +582,18 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             sc->phase = phase;
         }
         grid.sync();
-        if (sc->phase == 3) continue;
+        if (sc->phase == 3) { if (stage & SEL_ST_CLASSIFY) continue; return; }
         if (sc->phase == 4) break;
 
         // ---- radix descent over the candidate list
-        const long long list_n = (long long)sc->cand_chunks * SEL_CHUNK;
+        const long long list_n = multi ? a.glist_each * a.nranks : (long long)sc->cand_chunks * SEL_CHUNK;
         for (int level = 0; level < 8; level++) {
             const u64 blo = sc->lo, bhi = sc->hi;
             const long long count_in = sc->count_in;
             if (count_in <= SEL_FINAL_CAP) {
                 // compact the bracket's items into the final list
                 for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < list_n; t += (long long)gridDim.x * SEL_THREADS) {
-                    u64 bits = (u64)__double_as_longlong(a.cand[t]);
+                    u64 bits = (u64)__double_as_longlong(list[t]);
                     if (bits >= blo && bits < bhi) {
                         unsigned int pos = atomicAdd(&sc->final_n, 1u);
                         if (pos < SEL_FINAL_CAP) sc->final_vals[pos] = __longlong_as_double((long long)bits);
@@ -556,7 +606,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            hist_level(a.cand, list_n, blo, bhi, shift, scale, sc, smem_raw);
+            hist_level(list, list_n, blo, bhi, shift, scale, sc, smem_raw);
             grid.sync();
             if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, scale, 0, smem_raw);
             grid.sync();
@@ -639,6 +689,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         }
         grid.sync();
         if (sc->phase == 4) break;
+        if (!(stage & SEL_ST_CLASSIFY)) return;              // sharded: another classify round is needed (phase 3)
     }
 
     // ---------------- outputs (block 0, thread 0)

@@ -21,7 +21,8 @@ _dp = C.POINTER(C.c_double)
 class pf_config(C.Structure):
     _fields_ = [("filter_kind", C.c_int32), ("prior_kind", C.c_int32), ("d", C.c_int32), ("precision", C.c_int32),
                 ("n_particles", C.c_int64), ("k_max", C.c_int32), ("order", C.c_int32), ("history", C.c_int64),
-                ("device", C.c_int32), ("reserved0", C.c_int32), ("alpha", C.c_double),
+                ("device", C.c_int32), ("reserved0", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("alpha", C.c_double),
                 ("rejuv_threshold", C.c_double), ("kappa0", C.c_double), ("nu0", C.c_double),
                 ("sigma2_0", C.c_double), ("mu0", _dp), ("lambda0", _dp), ("seed", C.c_uint64)]
 
@@ -39,6 +40,15 @@ class pf_step_stats(C.Structure):
         d["select_phase_us"] = list(self.select_phase_us)
         return d
 
+
+class pf_mg_ptrs(C.Structure):
+    _fields_ = [("scalars", C.c_void_p), ("acc", C.c_void_p), ("acc_bytes", C.c_int64), ("list", C.c_void_p),
+                ("list_capacity", C.c_int64), ("local_total", C.c_void_p), ("total_bytes", C.c_int64),
+                ("send_buffer", C.c_void_p), ("recv_buffer", C.c_void_p), ("buffer_capacity", C.c_int64),
+                ("rows_per_particle", C.c_int64), ("local_capacity", C.c_int64)]
+
+
+PF_MG_SAMPLE, PF_MG_BRACKET, PF_MG_CLASSIFY, PF_MG_SOLVE = 1, 2, 4, 8
 
 # every symbol include/particles_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -59,8 +69,16 @@ SYMBOLS = [
     ("pf_get_last_assignments", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     ("pf_select", C.c_int32, [C.c_int32, _dp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.POINTER(C.c_int64),
                               C.POINTER(C.c_uint8), C.POINTER(pf_step_stats)]),
-    ("pf_comm_init", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
-    ("pf_comm_unique_id", C.c_int32, [C.c_void_p]),
+    ("pf_set_stream", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("pf_mg_info", C.c_int32, [C.c_void_p, C.POINTER(pf_mg_ptrs)]),
+    ("pf_mg_begin", C.c_int32, [C.c_void_p, _dp, C.c_double]),
+    ("pf_mg_select", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
+    ("pf_mg_state", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
+    ("pf_mg_tiles", C.c_int32, [C.c_void_p]),
+    ("pf_mg_finish", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("pf_mg_plan", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                               C.POINTER(C.c_int64)]),
+    ("pf_mg_unpack", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_last_timing", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
     ("pf_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
     ("pf_get_kernel_times", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),

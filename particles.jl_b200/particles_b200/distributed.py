@@ -1,0 +1,334 @@
+"""Sharded Fearnhead filter: particles block-sharded over GPUs, one process per GPU.
+
+The library runs the same kernels on every shard and exposes the stage boundaries of one
+observation (include/particles_b200.h, "multi-GPU"); this module supplies the collectives in
+between through a small communicator interface:
+
+  TorchComm   torch.distributed (NCCL over NVLink on the GPU box; gloo in the CPU tests of
+              the host-side logic), one local rank per process;
+  LocalComm   all ranks inside one process on one device, executed in lock step -- used by
+              the single-GPU tests to check "sharded run == unsharded run" bit for bit.
+
+What crosses the ranks per observation: two scalars (all-reduce), the strided sample and the
+bracket's candidates (all-gather, a few MB), one 32-byte record per rank (all-gather) and the
+records of the particles that change owner in the re-partitioning (all-to-all-v)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PF_FEARNHEAD, PF_MG_BRACKET, PF_MG_CLASSIFY, PF_MG_SAMPLE, PF_MG_SOLVE, PF_NIW, PF_NIX2, pf_config, pf_mg_ptrs, \
+    pf_step_stats
+
+_dp = C.POINTER(C.c_double)
+
+
+# ------------------------------------------------------------------ host-side plan (pure)
+def partition_plan(n_local_all, rank):
+    """Re-partitioning of a rank-major population with n_local_all[r] particles produced on
+    rank r into equal blocks of q = ceil(n / G): (send_counts by destination, recv_counts by
+    source, q, n_mine) for `rank`.  Mirrors k_rank_offsets (csrc/fearnhead.cuh)."""
+    n_local_all = [int(x) for x in n_local_all]
+    G = len(n_local_all)
+    first = np.concatenate([[0], np.cumsum(n_local_all)]).astype(np.int64)
+    n = int(first[-1])
+    q = max((n + G - 1) // G, 1)
+    send = np.zeros(G, dtype=np.int64)
+    recv = np.zeros(G, dtype=np.int64)
+    for d in range(G):
+        lo, hi = max(first[rank], d * q), min(first[rank] + n_local_all[rank], (d + 1) * q)
+        send[d] = 0 if d == rank else max(hi - lo, 0)
+        lo, hi = max(first[d], rank * q), min(first[d] + n_local_all[d], (rank + 1) * q)
+        recv[d] = 0 if d == rank else max(hi - lo, 0)
+    n_mine = min(max(n - rank * q, 0), q)
+    return send, recv, q, n_mine
+
+
+# ------------------------------------------------------------------ communicators
+class TorchComm:
+    """torch.distributed default process group; one shard per process."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.size = dist.get_world_size()
+        self.local_ranks = [dist.get_rank()]
+
+    def all_reduce(self, tensors, op):
+        import torch.distributed as dist
+        dist.all_reduce(tensors[0], op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
+
+    def all_gather(self, tensors):
+        import torch
+        t = tensors[0].contiguous().reshape(-1)
+        out = torch.empty(self.size * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t)
+        return [out.reshape((self.size,) + tuple(tensors[0].shape))]
+
+    def max_int(self, values, device):
+        import torch
+        t = torch.tensor([int(values[0])], dtype=torch.int64, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def all_to_all_v(self, sends, send_counts, recvs, recv_counts, rows):
+        ins = [int(c) * rows for c in send_counts[0]]
+        outs = [int(c) * rows for c in recv_counts[0]]
+        self.dist.all_to_all_single(recvs[0][:sum(outs)], sends[0][:sum(ins)], outs, ins)
+
+    def gather_host(self, arrays):
+        out = [None] * self.size
+        self.dist.all_gather_object(out, arrays[0])
+        return out
+
+
+class LocalComm:
+    """All `size` ranks live in this process (on one device) and advance in lock step."""
+
+    def __init__(self, size):
+        self.size = size
+        self.local_ranks = list(range(size))
+
+    def all_reduce(self, tensors, op):
+        import torch
+        st = torch.stack([t.clone() for t in tensors])
+        r = st.sum(0) if op == "sum" else st.max(0).values
+        for t in tensors:
+            t.copy_(r)
+
+    def all_gather(self, tensors):
+        import torch
+        g = torch.stack([t.contiguous() for t in tensors])
+        return [g] * self.size
+
+    def max_int(self, values, device):
+        return max(int(v) for v in values)
+
+    def all_to_all_v(self, sends, send_counts, recvs, recv_counts, rows):
+        G = self.size
+        soff = [np.concatenate([[0], np.cumsum(send_counts[s])]) * rows for s in range(G)]
+        for d in range(G):
+            o = 0
+            for s in range(G):
+                assert int(send_counts[s][d]) == int(recv_counts[d][s]), "inconsistent exchange plan"
+                n = int(send_counts[s][d]) * rows
+                if n:
+                    recvs[d][o:o + n].copy_(sends[s][int(soff[s][d]):int(soff[s][d]) + n])
+                o += n
+
+    def gather_host(self, arrays):
+        return list(arrays)
+
+
+# ------------------------------------------------------------------ device views
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _view(ptr, n, typestr, device):
+    import torch
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+
+
+class _Shard:
+    def __init__(self, L, cfg, device):
+        import torch
+        self.L = L
+        h = C.c_void_p()
+        _lib.check(L.pf_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.device = torch.device("cuda", device)
+        _lib.check(L.pf_set_stream(h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), h)
+        p = pf_mg_ptrs()
+        _lib.check(L.pf_mg_info(h, C.byref(p)), h)
+        self.rows = int(p.rows_per_particle)
+        self.scalars = _view(p.scalars, 2, "<i8", self.device)
+        self.acc = _view(p.acc, p.acc_bytes // 8, "<i8", self.device)
+        self.list = _view(p.list, p.list_capacity, "<i8", self.device)          # bit patterns of the doubles
+        self.total = _view(p.local_total, p.total_bytes // 8, "<i8", self.device)
+        self.send = _view(p.send_buffer, p.buffer_capacity, "<f8", self.device)
+        self.recv = _view(p.recv_buffer, p.buffer_capacity, "<f8", self.device)
+
+    def state(self):
+        st = (C.c_int64 * 4)()
+        _lib.check(self.L.pf_mg_state(self.h, st), self.h)
+        return list(st)
+
+    def select(self, stage, rounds, gacc, glist, each):
+        _lib.check(self.L.pf_mg_select(self.h, stage, rounds,
+                                       C.c_void_p(gacc.data_ptr()) if gacc is not None else None,
+                                       C.c_void_p(glist.data_ptr()) if glist is not None and glist.numel() else None,
+                                       int(each)), self.h)
+
+
+class ShardedFearnheadParticles:
+    """FearnheadParticles (src/fearnhead.jl:13-30) with the population sharded over
+    comm.size ranks.  Same results as the unsharded filter, particle for particle."""
+
+    def __init__(self, n, prior, stateprior, comm, *, k_max=16, history=0, devices=None, seed=0):
+        from . import NormalInverseChisq, NormalInverseWishart
+        import torch
+        self.comm, self.N, self.k_max = comm, int(n), int(k_max)
+        L = _lib.load()
+        self.L = L
+        self.shards = []
+        devices = devices if devices is not None else [torch.cuda.current_device()] * len(comm.local_ranks)
+        for r, dev in zip(comm.local_ranks, devices):
+            cfg = pf_config()
+            cfg.filter_kind, cfg.precision, cfg.n_particles, cfg.k_max = PF_FEARNHEAD, 0, self.N, self.k_max
+            cfg.order, cfg.history, cfg.device, cfg.rank, cfg.nranks = 0, int(history), dev, r, comm.size
+            cfg.alpha, cfg.rejuv_threshold, cfg.seed = stateprior.alpha, 50.0, seed
+            if isinstance(prior, NormalInverseChisq):
+                cfg.prior_kind, cfg.d = PF_NIX2, 1
+                self._mu0, self._lam0 = np.array([prior.mu]), np.zeros((1, 1))
+                cfg.kappa0, cfg.nu0, cfg.sigma2_0 = prior.kappa, prior.nu, prior.sigma2
+            elif isinstance(prior, NormalInverseWishart):
+                cfg.prior_kind, cfg.d = PF_NIW, prior.dim
+                self._mu0, self._lam0 = prior.mu.copy(), np.asfortranarray(prior.Lam)
+                cfg.kappa0, cfg.nu0, cfg.sigma2_0 = prior.kappa, prior.nu, 0.0
+            else:
+                raise ValueError("prior must be NormalInverseChisq or NormalInverseWishart")
+            cfg.mu0 = self._mu0.ctypes.data_as(_dp)
+            cfg.lambda0 = self._lam0.ctypes.data_as(_dp)
+            self.d = cfg.d
+            with torch.cuda.device(dev):
+                self.shards.append(_Shard(L, cfg, dev))
+        self.n_global = 1
+        self.steps = 0
+        self.host_syncs = 0
+        self.bytes_moved = 0
+
+    def close(self):
+        for s in self.shards:
+            if s.h:
+                self.L.pf_destroy(s.h)
+                s.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- one observation
+    def _gather_lists(self):
+        import torch
+        comm, sh = self.comm, self.shards
+        lens = [s.state()[1] for s in sh]
+        self.host_syncs += 1
+        mx = comm.max_int(lens, sh[0].device)
+        for s, ln in zip(sh, lens):
+            if ln < mx:
+                s.list[ln:mx].fill_(-1)                       # all-ones pattern: outside every bracket
+        gl = comm.all_gather([s.list[:mx] for s in sh]) if mx else [None] * len(sh)
+        ga = comm.all_gather([s.acc for s in sh])
+        self.bytes_moved += 8 * mx * comm.size + 8 * sh[0].acc.numel() * comm.size
+        return gl, ga, mx
+
+    def fit_(self, y, u):
+        """fit!(ps, y) (src/fearnhead.jl:130-184) on the sharded population; u = the rand()
+        of src/fearnhead.jl:99."""
+        import torch
+        comm, sh, L = self.comm, self.shards, self.L
+        y, py = (np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64),) * 2
+        py = y.ctypes.data_as(_dp)
+        for s in sh:
+            _lib.check(L.pf_mg_begin(s.h, py, float(u)), s.h)
+        comm.all_reduce([s.scalars[0:1] for s in sh], "sum")
+        comm.all_reduce([s.scalars[1:2] for s in sh], "max")
+        for s in sh:
+            s.select(PF_MG_SAMPLE, 0, None, None, 0)
+        need_sample = sh[0].state()[2]
+        self.host_syncs += 1
+        if need_sample:
+            gl, ga, mx = self._gather_lists()
+            for s, g, a in zip(sh, gl, ga):
+                s.select(PF_MG_BRACKET | PF_MG_CLASSIFY, 0, a, g, mx)
+        else:
+            ga = comm.all_gather([s.acc for s in sh])
+            for s, a in zip(sh, ga):
+                s.select(PF_MG_BRACKET | PF_MG_CLASSIFY, 0, a, None, 0)
+        rounds = 0
+        while True:
+            gl, ga, mx = self._gather_lists()
+            for s, g, a in zip(sh, gl, ga):
+                s.select(PF_MG_SOLVE, rounds, a, g, mx)
+            st = sh[0].state()
+            self.host_syncs += 1
+            if st[0] == 4:
+                break
+            rounds = st[3]
+            if rounds > 40:
+                raise RuntimeError("threshold search did not converge")
+            for s in sh:
+                s.select(PF_MG_CLASSIFY, rounds, None, None, 0)
+        for s in sh:
+            _lib.check(L.pf_mg_tiles(s.h), s.h)
+        gt = comm.all_gather([s.total for s in sh])
+        for s, g in zip(sh, gt):
+            _lib.check(L.pf_mg_finish(s.h, C.c_void_p(g.data_ptr())), s.h)
+        G = comm.size
+        sends, recvs, scs, rcs = [], [], [], []
+        for s in sh:
+            sc, rc = (C.c_int64 * G)(), (C.c_int64 * G)()
+            nl, ng = C.c_int64(), C.c_int64()
+            _lib.check(L.pf_mg_plan(s.h, sc, rc, C.byref(nl), C.byref(ng)), s.h)
+            scs.append(np.array(sc[:], dtype=np.int64))
+            rcs.append(np.array(rc[:], dtype=np.int64))
+            sends.append(s.send)
+            recvs.append(s.recv)
+            self.n_global = ng.value
+        self.host_syncs += 1
+        comm.all_to_all_v(sends, scs, recvs, rcs, sh[0].rows)
+        self.bytes_moved += int(sum(int(x.sum()) for x in scs)) * sh[0].rows * 8
+        for s in sh:
+            _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)
+        self.steps += 1
+        return self
+
+    def filter_(self, ys, uniforms):
+        ys = np.asarray(ys, dtype=np.float64).reshape(len(uniforms), -1)
+        for y, u in zip(ys, uniforms):
+            self.fit_(y, u)
+        return self
+
+    # ---- read-out (concatenated over ranks in global order)
+    def _local(self, fn, dtype, ctype):
+        outs = []
+        for s in self.shards:
+            n = int(self.L.pf_n_particles(s.h))
+            out = np.empty(n, dtype=dtype)
+            _lib.check(fn(s.h, out.ctypes.data_as(C.POINTER(ctype))), s.h)
+            outs.append(out)
+        return outs
+
+    def __len__(self):
+        return int(self.n_global)
+
+    def logweights(self):
+        return np.concatenate(self.comm.gather_host(self._local(self.L.pf_get_logweights, np.float64, C.c_double)))
+
+    def ncomponents(self):
+        return np.concatenate(self.comm.gather_host(self._local(self.L.pf_get_ncomponents, np.int32, C.c_int32)))
+
+    def last_ancestors(self):
+        return np.concatenate(self.comm.gather_host(self._local(self.L.pf_get_last_ancestors, np.int32, C.c_int32)))
+
+    def last_assignments(self):
+        return np.concatenate(self.comm.gather_host(self._local(self.L.pf_get_last_assignments, np.int32, C.c_int32)))
+
+    def last_step(self):
+        s = self.shards[0]
+        st = pf_step_stats()
+        import torch
+        torch.cuda.synchronize(s.device)
+        _lib.check(self.L.pf_get_last_step(s.h, C.byref(st)), s.h)
+        return st.asdict()
+
+    def synchronize(self):
+        import torch
+        for s in self.shards:
+            torch.cuda.synchronize(s.device)
