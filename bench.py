@@ -196,7 +196,8 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0,
-                                                host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K),
+                                                host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K,
+                                                slow_path_steps=ps.slow_steps),
             "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
                     "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le)},
             "gpu_launches": int(l1.value - l0.value) * world,
@@ -252,6 +253,7 @@ def main():
     import particles_b200 as pb
     dist = None
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)              # NCCL prints its version banner to stdout
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)

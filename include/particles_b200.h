@@ -182,12 +182,14 @@ typedef struct {
     int64_t buffer_capacity;   /* doubles in each of send_buffer / recv_buffer */
     int64_t rows_per_particle; /* doubles per migrating particle */
     int64_t local_capacity;    /* particles this shard can hold */
+    int64_t sample_entries;    /* fixed gather size (doubles) of the sample list */
+    int64_t cand_entries;      /* fixed gather size (doubles) of the candidate list */
 } pf_mg_ptrs;
 int32_t pf_set_stream(pf_handle h, void *cuda_stream);    /* run on the caller's stream (e.g. torch's current stream) */
 int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *out);
 int32_t pf_mg_begin(pf_handle h, const double *y, double u);
 int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done, const void *gathered_acc, const void *gathered_list,
-                     int64_t list_each);
+                     int64_t list_each, int64_t pad_to);
 /* state[0] = phase (4 done, 3 classify again), [1] = local list entries in use (multiple of 256),
  * [2] = 1 if this step needs the sample, [3] = classify rounds done.  Synchronises the stream. */
 int32_t pf_mg_state(pf_handle h, int64_t state[4]);
@@ -195,7 +197,8 @@ int32_t pf_mg_tiles(pf_handle h);
 int32_t pf_mg_finish(pf_handle h, const void *gathered_totals);
 /* Exchange plan of the re-partitioning, in particles: send_counts[nranks] by destination,
  * recv_counts[nranks] by source.  Synchronises the stream. */
-int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global);
+int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
+                   int64_t *phase);
 int32_t pf_mg_unpack(pf_handle h, const void *recv_buffer);
 
 /* ---- instrumentation ------------------------------------------------------------------ */

@@ -177,9 +177,10 @@ struct RankOff {
 // one thread: turn the gathered per-rank totals (mass of the low partition, kept count) into
 // this rank's offsets and the exchange plan.  rows = doubles per migrating particle.
 __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, int nranks, const SelResult *__restrict__ res,
-                               StepState *st, RankOff *ro, int rows)
+                               StepState *st, RankOff *ro, int rows, const SelScratch *guard)
 {
     if (threadIdx.x || blockIdx.x) return;
+    if (guard && guard->phase != 4) { ro->n_local = 0; return; }          // the threshold search has not finished (speculative tail)
     const bool comb = res->n > 0 && !isz128(res->T);
     const u64 n = (u64)res->n;
     u128 Spre = mk128(0, 0);
@@ -237,8 +238,9 @@ __device__ __forceinline__ void thread_sums(const double *__restrict__ V, long l
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
                                                             long long cap, const SelResult *__restrict__ res,
                                                             const long long *__restrict__ n_items_ptr, TileSum *__restrict__ tiles,
-                                                            int mode)
+                                                            int mode, const SelScratch *guard)
 {
+    if (guard && guard->phase != 4) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_x[SCAN_THREADS / 32];
     __shared__ unsigned int s_k[SCAN_THREADS / 32];
@@ -265,8 +267,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
 // exclusive prefix over the tiles (in place) and the step's survivor counts; one block
 __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelResult *__restrict__ res,
                                                       const long long *__restrict__ n_items_ptr, StepState *st, int mode,
-                                                      TileSum *local_tot /* sharded run: totals out, counts set later */)
+                                                      TileSum *local_tot /* sharded run: totals out, counts set later */,
+                                                      const SelScratch *guard)
 {
+    if (guard && guard->phase != 4) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
     __shared__ unsigned int s_k[1024];
@@ -304,8 +308,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                                                              const long long *__restrict__ n_items_ptr,
                                                              const TileSum *__restrict__ tiles, unsigned int *__restrict__ surv_parent,
                                                              unsigned char *__restrict__ surv_slot, int mode,
-                                                             const RankOff *__restrict__ ro)
+                                                             const RankOff *__restrict__ ro, const SelScratch *guard)
 {
+    if (guard && guard->phase != 4) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
     __shared__ unsigned int s_wc[33];
@@ -392,9 +397,11 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
                                                      const unsigned int *__restrict__ surv_parent,
                                                      const unsigned char *__restrict__ surv_slot,
                                                      unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
-                                                     const RankOff *__restrict__ ro, double *__restrict__ sendbuf, int k_max)
+                                                     const RankOff *__restrict__ ro, double *__restrict__ sendbuf, int k_max,
+                                                     const SelScratch *guard)
 {
     using L = Layout<D>;
+    if (guard && guard->phase != 4) return;
     const long long n_out = ro ? ro->n_local : st->n_next;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_out) return;

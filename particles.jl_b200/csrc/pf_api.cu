@@ -66,6 +66,7 @@ struct pf_filter_s {
     int mig_rows = 0;
     long long surv_cap = 0;
     int mg_rounds = 0;
+    long long mg_stride = 1, mg_sample_entries = 0, mg_cand_entries = 0;
     bool own_stream = true;
     double *y1_dev = nullptr;             // y (d) + u (1) of the current sharded step
     // genealogy
@@ -292,7 +293,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (h->nranks > 1) {
         h->mig_rows = h->k_max * h->F + 4;
         h->buf_cap = (h->surv_cap) * (long long)h->mig_rows;
-        CT(dmalloc(&h->gscal, 2)); CT(dmalloc(&h->local_tot, 1)); CT(dmalloc(&h->ro, 1));
+        CT(dmalloc(&h->gscal, 4)); CT(dmalloc(&h->local_tot, 1)); CT(dmalloc(&h->ro, 1));
         CT(dmalloc(&h->sendbuf, (size_t)h->buf_cap)); CT(dmalloc(&h->recvbuf, (size_t)h->buf_cap));
         CT(dmalloc(&h->y1_dev, (size_t)d + 1));
         CT(cudaMemsetAsync(h->ro, 0, sizeof(RankOff), h->stream));
@@ -321,6 +322,13 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (occ < 1) { pf_destroy(h); return set_error(nullptr, PF_ERR_CUDA, "pf_create: k_select does not fit on an SM"); }
     h->sel_grid = h->num_sms * (occ > 2 ? 2 : occ);
     h->cand_cap = (long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
+    if (h->nranks > 1) {
+        const long long pad = (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK;
+        h->mg_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
+        h->mg_sample_entries = (2 * SEL_SAMPLE_TARGET + h->nranks - 1) / h->nranks + pad + 1024;
+        h->mg_cand_entries = std::max<long long>(1 << 18, (4ll << 20) / h->nranks) + pad;
+        h->cand_cap = std::max(h->cand_cap, std::max(h->mg_sample_entries, h->mg_cand_entries) + pad);
+    }
     CT(dmalloc(&h->cand, (size_t)h->cand_cap));
     if (cfg->history > 0) {
         h->hist_cap = cfg->history;
@@ -378,7 +386,7 @@ static int32_t launch_select(pf_handle h, const double *V, const unsigned char *
     SelArgs a;
     a.V = V; a.cnt = cnt; a.cap = cap; a.n_live = n_live; a.M = M; a.vmax_bits = vmax; a.N = N; a.u = u_dev;
     a.cand = cand; a.cand_cap = cand_cap; a.sc = sc; a.res = res;
-    a.stage = SEL_ST_ALL; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr;
+    a.stage = SEL_ST_ALL; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr; a.pad_to = -1; a.fixed_stride = 1;
     void *args[] = {&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
     return PF_OK;
@@ -425,29 +433,29 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         // resampling step: comb over the sorted list; exhaustive step: index order
         LaunchTimer lt(h, KC_SCAN, 7);
         const int gflat = grid_for(n_pad, SCAN_THREADS), gidx = grid_for(ub, SCAN_THREADS);
-        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr);
+        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr, nullptr);
         k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles,
-                                                             h->pick_pos, h->surv_slot, 1, nullptr);
+                                                             h->pick_pos, h->surv_slot, 1, nullptr, nullptr);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
                                                                            h->surv_slot);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr);
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 2, nullptr);
+                                                            h->surv_slot, 2, nullptr, nullptr);
     } else {
         LaunchTimer lt(h, KC_SCAN, 3);
         const int gidx = grid_for(ub, SCAN_THREADS);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr);
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 0, nullptr);
+                                                            h->surv_slot, 0, nullptr, nullptr);
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
         k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max);
+                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max, nullptr);
     }
     {
         LaunchTimer lt(h, KC_STEPLOG);
@@ -826,9 +834,9 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         k_vmax<<<h->num_sms * 4, 256, 0, h->stream>>>(Vsel, M, st);
         rc = launch_select(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res);
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
-        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr);
-        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr);
+        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr, nullptr);
+        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr, nullptr);
         ST(cudaGetLastError());
         StepState s1; SelResult r1;
         ST(cudaMemcpyAsync(&s1, st, sizeof s1, cudaMemcpyDeviceToHost, h->stream));
@@ -878,10 +886,10 @@ done:
 }
 
 // ------------------------------------------------------------------ sharded run (bring your own collective)
-__global__ void k_publish_scalars(const StepState *st, long long *gscal)
+__global__ void k_publish_scalars(const StepState *st, SelScratch *sc)
 {
     if (threadIdx.x || blockIdx.x) return;
-    gscal[0] = st->M; gscal[1] = (long long)st->vmax_bits;
+    sc->M_local = (unsigned long long)st->M; sc->vmax_local = st->vmax_bits;
 }
 
 __global__ void k_steplog_mg(StepState *st, const SelResult *res, const RankOff *ro, StepLog *lg)
@@ -919,6 +927,7 @@ extern "C" int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *o)
     o->local_total = h->local_tot; o->total_bytes = sizeof(TileSum);
     o->send_buffer = h->sendbuf; o->recv_buffer = h->recvbuf; o->buffer_capacity = h->buf_cap;
     o->rows_per_particle = h->mig_rows; o->local_capacity = h->cap;
+    o->sample_entries = h->mg_sample_entries; o->cand_entries = h->mg_cand_entries;
     return PF_OK;
 }
 
@@ -929,7 +938,7 @@ static int32_t mg_begin(pf_handle h)
     k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0);
     k_expand<D><<<grid_for(h->cap, 256), 256, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->k_max, h->tab,
                                                                 h->pc, h->stc, h->st, h->V, h->cnt);
-    k_publish_scalars<<<1, 32, 0, h->stream>>>(h->st, h->gscal);
+    k_publish_scalars<<<1, 32, 0, h->stream>>>(h->st, h->sc);
     h->launches += 3;
     return PF_OK;
 }
@@ -953,7 +962,8 @@ extern "C" int32_t pf_mg_begin(pf_handle h, const double *y, double u)
     return rc;
 }
 
-extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done, const void *gacc, const void *glist, int64_t list_each)
+extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done, const void *gacc, const void *glist, int64_t list_each,
+                                int64_t pad_to)
 {
     MG_CHECK(h);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -963,7 +973,8 @@ extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done,
     a.N = h->N; a.u = h->y1_dev + h->d; a.cand = h->cand; a.cand_cap = h->cand_cap; a.sc = h->sc; a.res = h->res;
     a.stage = stage; a.round0 = rounds_done; a.nranks = h->nranks; a.gacc = (const SelAcc *)gacc;
     a.glist = (const double *)glist; a.glist_each = list_each;
-    a.goff = &h->st->goff;
+    a.goff = &h->st->goff; a.pad_to = pad_to; a.fixed_stride = h->mg_stride;
+    if ((stage & SEL_ST_BRACKET) && gacc) { k_mg_globals<<<1, 32, 0, h->stream>>>((const SelAcc *)gacc, h->nranks, h->gscal); h->launches++; }
     void *args[] = {&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
     h->launches++;
@@ -993,8 +1004,8 @@ extern "C" int32_t pf_mg_tiles(pf_handle h)
     MG_CHECK(h);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int g = grid_for(h->cap, SCAN_THREADS);
-    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0);
-    k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, h->local_tot);
+    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, nullptr);
+    k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, h->local_tot, h->sc);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return PF_OK;
@@ -1006,12 +1017,12 @@ static int32_t mg_finish(pf_handle h, const TileSum *gathered)
     const int cur = h->cur, nxt = cur ^ 1;
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows);
+    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc);
     k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
-                                                                                  h->surv_parent, h->surv_slot, 0, h->ro);
+                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc);
     k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max);
+                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max, h->sc);
     h->launches += 3;
     return PF_OK;
 }
@@ -1027,13 +1038,18 @@ extern "C" int32_t pf_mg_finish(pf_handle h, const void *gathered_totals)
     return rc;
 }
 
-extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global)
+extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
+                              int64_t *phase)
 {
     MG_CHECK(h);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     RankOff r;
+    SelScratch hdr;
     CUDA_TRY(cudaMemcpyAsync(&r, h->ro, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(&hdr, h->sc, offsetof(SelScratch, A_hi), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (phase) *phase = hdr.phase;
+    if (hdr.phase != 4) return PF_OK;
     if (r.n_local > h->surv_cap) return set_error(h, PF_ERR_OVERFLOW, "shard produced more survivors than its survivor list holds (imbalance)");
     for (int k = 0; k < h->nranks; k++) { if (send_counts) send_counts[k] = r.send_len[k]; if (recv_counts) recv_counts[k] = r.recv_len[k]; }
     if (n_local) *n_local = r.n_local;

@@ -28,7 +28,7 @@ namespace cg = cooperative_groups;
 #define SEL_WARPS (SEL_THREADS / 32)
 #define SEL_FINAL_CAP 2048
 #define SEL_BINS 1024
-#define SEL_CHUNK 256
+#define SEL_CHUNK 64
 #define SEL_SAMPLE_TARGET (1 << 20)
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax
@@ -69,7 +69,9 @@ struct SelScratch {
     acc128 S_cand;                  // sum q of items in [lo, hi)
     acc128 Tot;                     // sum of the items >= hi at scale SEL_TOT_BITS - e(vmax)
     unsigned long long cand_chunks; // chunks handed out of the candidate / sample list
-    unsigned long long acc_pad;
+    unsigned long long overflow;    // sharded run: the list outgrew the fixed gather size
+    unsigned long long M_local;     // sharded run: this shard's putative count and max weight bits
+    unsigned long long vmax_local;
     // running totals of the descent
     u128 B_run;                     // sum q of list items < lo (after narrowing)
     long long A_run;                // #list items >= hi (after narrowing)
@@ -85,7 +87,7 @@ struct SelScratch {
 struct SelAcc {
     unsigned long long A_hi, n_cand;
     acc128 B_lo, S_cand, Tot;
-    unsigned long long cand_chunks, acc_pad;
+    unsigned long long cand_chunks, overflow, M_local, vmax_local;
 };
 #define SEL_ACC_OFFSET offsetof(SelScratch, A_hi)
 
@@ -113,6 +115,8 @@ struct SelArgs {
     const double *glist;            // gathered sample / candidate list (nranks * glist_each doubles)
     long long glist_each;           // doubles per rank in glist (padded with the NaN pattern)
     const long long *goff;          // device: global index of the shard's first particle (phase of the strided sample)
+    long long pad_to;               // sharded run: pad the local list with the NaN pattern up to this many entries
+    long long fixed_stride;         // sharded run: sample stride chosen by the host (global M is not known yet)
 };
 
 // sharded run: sum the gathered per-rank accumulator blocks into the local scratch
@@ -127,6 +131,25 @@ __device__ inline void sum_gathered(SelScratch *sc, const SelAcc *g, int nranks)
     }
     sc->A_hi = A; sc->n_cand = nc; sc->B_lo = b; sc->S_cand = c; sc->Tot = t;
     (void)ch;
+}
+
+// sharded run: global putative count / max weight from the gathered blocks (one thread)
+__global__ void k_mg_globals(const SelAcc *g, int nranks, long long *gscal)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long M = 0, vm = 0, ov = 0;
+    for (int r = 0; r < nranks; r++) { M += g[r].M_local; vm = g[r].vmax_local > vm ? g[r].vmax_local : vm; ov |= g[r].overflow; }
+    gscal[0] = (long long)M; gscal[1] = (long long)vm; gscal[2] = (long long)ov;
+}
+
+// pad the tail of a chunked list up to `pad_to` entries (grid-wide, after the appends are done)
+__device__ inline void pad_list(double *list, unsigned long long chunks, long long pad_to, SelScratch *sc)
+{
+    const long long used = (long long)chunks * SEL_CHUNK;
+    if (pad_to < 0) return;
+    if (used > pad_to) { if (blockIdx.x == 0 && threadIdx.x == 0) sc->overflow = 1; return; }
+    for (long long t = used + (long long)blockIdx.x * SEL_THREADS + threadIdx.x; t < pad_to; t += (long long)gridDim.x * SEL_THREADS)
+        list[t] = __longlong_as_double(~0ll);
 }
 
 __device__ __forceinline__ unsigned long long gtimer()
@@ -350,7 +373,7 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
 
 __device__ inline void reset_round(SelScratch *sc)
 {
-    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0;
+    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0; sc->overflow = 0;
     for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
 }
 
@@ -421,7 +444,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         res->rounds = 0; res->status = 0; res->n_cand_first = 0;
         res->t_ns[0] = gtimer();
         sc->mult = 1;
-        if (trivial) {             // keep everything (src/fearnhead.jl:135-138); an all-zero step keeps nothing
+        if (multi) {               // sharded: the global M is not known yet; decided at the BRACKET stage
+            sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0;
+        } else if (trivial) {      // keep everything (src/fearnhead.jl:135-138); an all-zero step keeps nothing
             sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1;
         } else {                   // direct solve, or the starting bracket of the sample solve
             sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0;
@@ -429,9 +454,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
     }
     grid.sync();
     }
-    const long long stride = (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
-    if (!sampled && (stage & SEL_ST_SAMPLE) && !(stage & SEL_ST_BRACKET)) return;    // sharded: nothing to sample
-    if (sampled && (stage & SEL_ST_SAMPLE)) {
+    const long long stride = multi ? a.fixed_stride : (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
+    // (a sharded run samples unconditionally: the global M is only known after the gather)
+    if ((sampled || multi) && (stage & SEL_ST_SAMPLE)) {
         // strided sample of whole particles (global indices = 0 mod stride), appended to the
         // (still unused) candidate list
         {
@@ -456,9 +481,21 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             cw.finish(a.cand, lane);
             cnt_s = warp_sum64(cnt_s);
             if (lane == 0 && cnt_s) atomicAdd(&sc->n_cand, cnt_s);
-            if (!(stage & SEL_ST_BRACKET)) return;          // sharded: the host gathers the samples
+            if (!(stage & SEL_ST_BRACKET)) {                 // sharded: the host gathers the samples
+                grid.sync();
+                pad_list(a.cand, sc->cand_chunks, a.pad_to, sc);
+                return;
+            }
             grid.sync();
         }
+    }
+    if (multi && (stage & SEL_ST_BRACKET)) {
+        if (blockIdx.x == 0 && tid == 0) {
+            reset_round(sc);
+            if (trivial) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1; }
+            else { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0; }
+        }
+        grid.sync();
     }
     if (sampled && (stage & SEL_ST_BRACKET)) {
         if (blockIdx.x == 0 && tid == 0) {
@@ -543,13 +580,19 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 }
             }
             __syncthreads();
-            if (!(stage & SEL_ST_SOLVE)) return;             // sharded: the host gathers accumulators + candidates
+            if (!(stage & SEL_ST_SOLVE)) {                   // sharded: the host gathers accumulators + candidates
+                grid.sync();
+                pad_list(a.cand, sc->cand_chunks, a.pad_to, sc);
+                return;
+            }
             grid.sync();
         }
 
         // ---- block 0: verify the bracket, start the descent
         if (blockIdx.x == 0 && tid == 0) {
             if (multi) sum_gathered(sc, a.gacc, a.nranks);
+            bool truncated = false;
+            if (multi) for (int r = 0; r < a.nranks; r++) truncated |= a.gacc[r].overflow != 0;
             res->rounds = round + 1;
             if (round == 0) {
                 res->n_cand_first = (long long)sc->n_cand; res->t_ns[2] = gtimer();
@@ -558,8 +601,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), tot_scale - scale);
                 res->log_total = log(tsum) - (double)tot_scale * 0.693147180559945309417232121458;
             }
-            int phase = 2;       // 2 = descend, 3 = redo classify with a new bracket, 4 = done
-            if (keep_all) phase = 4;
+            int phase = 2;       // 2 = descend, 3 = redo classify with a new bracket, 4 = done, 7 = gathered list truncated
+            if (truncated) phase = 7;
+            else if (keep_all) phase = 4;
             else if (mode == 2) {
                 // comb-rescale round: T at the new scale; lo = hi = thr so A_hi = A again
                 res->T = acc_value(&sc->B_lo); res->scale = scale;
@@ -582,6 +626,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             sc->phase = phase;
         }
         grid.sync();
+        if (sc->phase == 7) return;
         if (sc->phase == 3) { if (stage & SEL_ST_CLASSIFY) continue; return; }
         if (sc->phase == 4) break;
 

@@ -45,7 +45,8 @@ class pf_mg_ptrs(C.Structure):
     _fields_ = [("scalars", C.c_void_p), ("acc", C.c_void_p), ("acc_bytes", C.c_int64), ("list", C.c_void_p),
                 ("list_capacity", C.c_int64), ("local_total", C.c_void_p), ("total_bytes", C.c_int64),
                 ("send_buffer", C.c_void_p), ("recv_buffer", C.c_void_p), ("buffer_capacity", C.c_int64),
-                ("rows_per_particle", C.c_int64), ("local_capacity", C.c_int64)]
+                ("rows_per_particle", C.c_int64), ("local_capacity", C.c_int64), ("sample_entries", C.c_int64),
+                ("cand_entries", C.c_int64)]
 
 
 PF_MG_SAMPLE, PF_MG_BRACKET, PF_MG_CLASSIFY, PF_MG_SOLVE = 1, 2, 4, 8
@@ -72,12 +73,12 @@ SYMBOLS = [
     ("pf_set_stream", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_mg_info", C.c_int32, [C.c_void_p, C.POINTER(pf_mg_ptrs)]),
     ("pf_mg_begin", C.c_int32, [C.c_void_p, _dp, C.c_double]),
-    ("pf_mg_select", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
+    ("pf_mg_select", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     ("pf_mg_state", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("pf_mg_tiles", C.c_int32, [C.c_void_p]),
     ("pf_mg_finish", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_mg_plan", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
-                               C.POINTER(C.c_int64)]),
+                               C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("pf_mg_unpack", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_last_timing", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
     ("pf_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),

@@ -151,17 +151,24 @@ class _Shard:
         self.total = _view(p.local_total, p.total_bytes // 8, "<i8", self.device)
         self.send = _view(p.send_buffer, p.buffer_capacity, "<f8", self.device)
         self.recv = _view(p.recv_buffer, p.buffer_capacity, "<f8", self.device)
+        self.sample_entries, self.cand_entries = int(p.sample_entries), int(p.cand_entries)
 
     def state(self):
         st = (C.c_int64 * 4)()
         _lib.check(self.L.pf_mg_state(self.h, st), self.h)
         return list(st)
 
-    def select(self, stage, rounds, gacc, glist, each):
+    def select(self, stage, rounds, gacc, glist, each, pad_to=-1):
         _lib.check(self.L.pf_mg_select(self.h, stage, rounds,
                                        C.c_void_p(gacc.data_ptr()) if gacc is not None else None,
                                        C.c_void_p(glist.data_ptr()) if glist is not None and glist.numel() else None,
-                                       int(each)), self.h)
+                                       int(each), int(pad_to)), self.h)
+
+    def plan(self, G):
+        sc, rc = (C.c_int64 * G)(), (C.c_int64 * G)()
+        nl, ng, ph = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.L.pf_mg_plan(self.h, sc, rc, C.byref(nl), C.byref(ng), C.byref(ph)), self.h)
+        return np.array(sc[:], dtype=np.int64), np.array(rc[:], dtype=np.int64), nl.value, ng.value, ph.value
 
 
 class ShardedFearnheadParticles:
@@ -200,6 +207,7 @@ class ShardedFearnheadParticles:
         self.steps = 0
         self.host_syncs = 0
         self.bytes_moved = 0
+        self.slow_steps = 0
 
     def close(self):
         for s in self.shards:
@@ -214,8 +222,8 @@ class ShardedFearnheadParticles:
             pass
 
     # ---- one observation
-    def _gather_lists(self):
-        import torch
+    def _gather_exact(self):
+        """Slow path: gather the lists at their exact (host-read) length."""
         comm, sh = self.comm, self.shards
         lens = [s.state()[1] for s in sh]
         self.host_syncs += 1
@@ -228,62 +236,61 @@ class ShardedFearnheadParticles:
         self.bytes_moved += 8 * mx * comm.size + 8 * sh[0].acc.numel() * comm.size
         return gl, ga, mx
 
-    def fit_(self, y, u):
-        """fit!(ps, y) (src/fearnhead.jl:130-184) on the sharded population; u = the rand()
-        of src/fearnhead.jl:99."""
-        import torch
+    def _tail(self):
+        """Survivor scan + instantiate, launched speculatively behind the threshold search;
+        the one host synchronisation of the step reads the search's outcome and the plan."""
         comm, sh, L = self.comm, self.shards, self.L
-        y, py = (np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64),) * 2
-        py = y.ctypes.data_as(_dp)
-        for s in sh:
-            _lib.check(L.pf_mg_begin(s.h, py, float(u)), s.h)
-        comm.all_reduce([s.scalars[0:1] for s in sh], "sum")
-        comm.all_reduce([s.scalars[1:2] for s in sh], "max")
-        for s in sh:
-            s.select(PF_MG_SAMPLE, 0, None, None, 0)
-        need_sample = sh[0].state()[2]
-        self.host_syncs += 1
-        if need_sample:
-            gl, ga, mx = self._gather_lists()
-            for s, g, a in zip(sh, gl, ga):
-                s.select(PF_MG_BRACKET | PF_MG_CLASSIFY, 0, a, g, mx)
-        else:
-            ga = comm.all_gather([s.acc for s in sh])
-            for s, a in zip(sh, ga):
-                s.select(PF_MG_BRACKET | PF_MG_CLASSIFY, 0, a, None, 0)
-        rounds = 0
-        while True:
-            gl, ga, mx = self._gather_lists()
-            for s, g, a in zip(sh, gl, ga):
-                s.select(PF_MG_SOLVE, rounds, a, g, mx)
-            st = sh[0].state()
-            self.host_syncs += 1
-            if st[0] == 4:
-                break
-            rounds = st[3]
-            if rounds > 40:
-                raise RuntimeError("threshold search did not converge")
-            for s in sh:
-                s.select(PF_MG_CLASSIFY, rounds, None, None, 0)
         for s in sh:
             _lib.check(L.pf_mg_tiles(s.h), s.h)
         gt = comm.all_gather([s.total for s in sh])
         for s, g in zip(sh, gt):
             _lib.check(L.pf_mg_finish(s.h, C.c_void_p(g.data_ptr())), s.h)
-        G = comm.size
-        sends, recvs, scs, rcs = [], [], [], []
-        for s in sh:
-            sc, rc = (C.c_int64 * G)(), (C.c_int64 * G)()
-            nl, ng = C.c_int64(), C.c_int64()
-            _lib.check(L.pf_mg_plan(s.h, sc, rc, C.byref(nl), C.byref(ng)), s.h)
-            scs.append(np.array(sc[:], dtype=np.int64))
-            rcs.append(np.array(rc[:], dtype=np.int64))
-            sends.append(s.send)
-            recvs.append(s.recv)
-            self.n_global = ng.value
+        plans = [s.plan(comm.size) for s in sh]
         self.host_syncs += 1
-        comm.all_to_all_v(sends, scs, recvs, rcs, sh[0].rows)
-        self.bytes_moved += int(sum(int(x.sum()) for x in scs)) * sh[0].rows * 8
+        return plans
+
+    def fit_(self, y, u):
+        """fit!(ps, y) (src/fearnhead.jl:130-184) on the sharded population; u = the rand()
+        of src/fearnhead.jl:99."""
+        comm, sh, L = self.comm, self.shards, self.L
+        y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
+        py = y.ctypes.data_as(_dp)
+        Bs, Bc = sh[0].sample_entries, sh[0].cand_entries
+        for s in sh:
+            _lib.check(L.pf_mg_begin(s.h, py, float(u)), s.h)
+            s.select(PF_MG_SAMPLE, 0, None, None, 0, Bs)
+        ga = comm.all_gather([s.acc for s in sh])
+        gl = comm.all_gather([s.list[:Bs] for s in sh])
+        for s, g, a in zip(sh, gl, ga):
+            s.select(PF_MG_BRACKET | PF_MG_CLASSIFY, 0, a, g, Bs, Bc)
+        ga = comm.all_gather([s.acc for s in sh])
+        gl = comm.all_gather([s.list[:Bc] for s in sh])
+        for s, g, a in zip(sh, gl, ga):
+            s.select(PF_MG_SOLVE, 0, a, g, Bc)
+        self.bytes_moved += 8 * (Bs + Bc + 2 * sh[0].acc.numel()) * comm.size
+        plans = self._tail()
+        phase = plans[0][4]
+        if phase != 4:
+            # rare: bracket verification failed, a finer scale is needed, or a list outgrew its
+            # fixed gather size -- finish the search with exact-size gathers, then redo the tail
+            self.slow_steps += 1
+            rounds = sh[0].state()[3]
+            while phase != 4:
+                if phase == 3:
+                    for s in sh:
+                        s.select(PF_MG_CLASSIFY, rounds, None, None, 0, -1)
+                gl, ga, mx = self._gather_exact()
+                for s, g, a in zip(sh, gl, ga):
+                    s.select(PF_MG_SOLVE, rounds, a, g, mx)
+                st = sh[0].state()
+                self.host_syncs += 1
+                phase, rounds = st[0], st[3]
+                if rounds > 40:
+                    raise RuntimeError("threshold search did not converge")
+            plans = self._tail()
+        self.n_global = plans[0][3]
+        comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
+        self.bytes_moved += int(sum(int(p[0].sum()) for p in plans)) * sh[0].rows * 8
         for s in sh:
             _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)
         self.steps += 1

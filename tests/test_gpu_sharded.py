@@ -51,13 +51,8 @@ def test_device_plan_matches_host_plan():
     for t in range(T):
         sh.fit_(ys[t], rng.random())
     # recompute the last plan on the host from the device-reported local counts
-    n_local, plans = [], []
-    for s in sh.shards:
-        sc, rc = (C.c_int64 * G)(), (C.c_int64 * G)()
-        nl, ng = C.c_int64(), C.c_int64()
-        assert sh.L.pf_mg_plan(s.h, sc, rc, C.byref(nl), C.byref(ng)) == 0
-        n_local.append(nl.value)
-        plans.append((list(sc), list(rc)))
+    res = [s.plan(G) for s in sh.shards]
+    n_local = [r[2] for r in res]
     for r in range(G):
         send, recv, q, mine = partition_plan(n_local, r)
-        assert plans[r] == (send.tolist(), recv.tolist())
+        assert res[r][0].tolist() == send.tolist() and res[r][1].tolist() == recv.tolist()
