@@ -142,7 +142,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     from particles_b200.distributed import ShardedFearnheadParticles, TorchComm
     dev = torch.device("cuda", local)
     rng = np.random.default_rng(100)
-    T_all = a.burnin + W + 2 * K
+    T_all = a.burnin + W + 2 * K + 8
     ys = mixture(rng, T_all)
     us = rng.random(T_all)
     ps = ShardedFearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
@@ -187,6 +187,12 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     e2e_s = float(wall.item())
     sampler.stop_flag = True
     kbar = 0.5 * (kbar0 + float(ps.ncomponents().mean()))
+    # (3) stage timeline (device ms, host ms) over a few more steps
+    ps.profile = []
+    for t in range(min(K, 8)):
+        ps.fit_(ys[o % T_all], us[o % T_all]); o += 1
+    stage_ms = ps.profile_summary()
+    ps.profile = None
     if rank != 0:
         return 0
     sampler.join(timeout=2)
@@ -197,7 +203,8 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0,
                                                 host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K,
-                                                slow_path_steps=ps.slow_steps),
+                                                slow_path_steps=ps.slow_steps,
+                                                stage_ms_device_host={k: [round(v[0], 4), round(v[1], 4)] for k, v in stage_ms.items()}),
             "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
                     "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le)},
             "gpu_launches": int(l1.value - l0.value) * world,

@@ -170,6 +170,7 @@ struct RankOff {
     long long n_global, q;
     long long goff_prev;           // global index of this rank's first PARENT (genealogy)
     int rank, nranks;
+    long long overflow;            // survivors that did not fit this rank's survivor list / buffers
     long long send_start[PF_MAX_RANKS], send_len[PF_MAX_RANKS], send_off[PF_MAX_RANKS];   // by destination (particles / doubles)
     long long recv_idx0[PF_MAX_RANKS], recv_len[PF_MAX_RANKS], recv_off[PF_MAX_RANKS];    // by source
 };
@@ -201,7 +202,7 @@ __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, i
     ro->g_first = g_first[rank]; ro->n_local = n_loc[rank]; ro->n_global = n_global; ro->q = q;
     long long mine = n_global - (long long)rank * q;
     ro->n_mine = mine < 0 ? 0 : (mine > q ? q : mine);
-    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff;
+    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0;
     long long soff = 0, roff = 0;
     for (int d = 0; d < nranks; d++) {
         long long lo = g_first[rank] > d * q ? g_first[rank] : d * q;
@@ -308,7 +309,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                                                              const long long *__restrict__ n_items_ptr,
                                                              const TileSum *__restrict__ tiles, unsigned int *__restrict__ surv_parent,
                                                              unsigned char *__restrict__ surv_slot, int mode,
-                                                             const RankOff *__restrict__ ro, const SelScratch *guard)
+                                                             const RankOff *__restrict__ ro, const SelScratch *guard,
+                                                             long long surv_cap)
 {
     if (guard && guard->phase != 4) return;
     if (scan_mode_skips(mode, res)) return;
@@ -363,16 +365,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
         if (bits >= thr) {
             if (mode != 1) {
                 long long pos = kcount + (long long)t;
-                surv_parent[pos] = (unsigned int)i;
-                surv_slot[pos] = (unsigned char)j;
+                if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
             }
             kcount++;
         } else if (comb) {
             S = add128(S, fx70(bits, scale));
             while (lt128(Q, S)) {
                 long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
-                surv_parent[pos] = (unsigned int)i;
-                surv_slot[pos] = (unsigned char)(j | 0x80);
+                if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)(j | 0x80); }
                 t++;
                 Q = add128(Q, Tq);
                 R += Tr;
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
     if (guard && guard->phase != 4) return;
     const long long n_out = ro ? ro->n_local : st->n_next;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_out) return;
+    if (t >= n_out) return;                       // (grid = survivor-list capacity: no thread beyond it)
     // destination of child t: a local index, or a slot of the packed send buffer of another rank
     double *dstb = S2 + t;
     long long stride = cap, idx = t;

@@ -287,12 +287,12 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     }
     CT(dmalloc(&h->V, (size_t)(h->k_max + 1) * cap));
     CT(dmalloc(&h->cnt, cap));
-    h->surv_cap = h->nranks > 1 ? 2 * cap + 1024 : cap;
+    h->surv_cap = h->nranks > 1 ? std::min<long long>(h->N, cap * (h->k_max + 1)) + 1024 : cap;
     CT(dmalloc(&h->surv_parent, h->surv_cap));
     CT(dmalloc(&h->surv_slot, h->surv_cap));
     if (h->nranks > 1) {
         h->mig_rows = h->k_max * h->F + 4;
-        h->buf_cap = (h->surv_cap) * (long long)h->mig_rows;
+        h->buf_cap = (2 * cap + 1024) * (long long)h->mig_rows;
         CT(dmalloc(&h->gscal, 4)); CT(dmalloc(&h->local_tot, 1)); CT(dmalloc(&h->ro, 1));
         CT(dmalloc(&h->sendbuf, (size_t)h->buf_cap)); CT(dmalloc(&h->recvbuf, (size_t)h->buf_cap));
         CT(dmalloc(&h->y1_dev, (size_t)d + 1));
@@ -436,20 +436,20 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr, nullptr);
         k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles,
-                                                             h->pick_pos, h->surv_slot, 1, nullptr, nullptr);
+                                                             h->pick_pos, h->surv_slot, 1, nullptr, nullptr, cap);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
                                                                            h->surv_slot);
         k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 2, nullptr, nullptr);
+                                                            h->surv_slot, 2, nullptr, nullptr, cap);
     } else {
         LaunchTimer lt(h, KC_SCAN, 3);
         const int gidx = grid_for(ub, SCAN_THREADS);
         k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 0, nullptr, nullptr);
+                                                            h->surv_slot, 0, nullptr, nullptr, cap);
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
@@ -836,7 +836,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
         k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr, nullptr);
-        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr, nullptr);
+        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr, nullptr, M);
         ST(cudaGetLastError());
         StepState s1; SelResult r1;
         ST(cudaMemcpyAsync(&s1, st, sizeof s1, cudaMemcpyDeviceToHost, h->stream));
@@ -1019,7 +1019,7 @@ static int32_t mg_finish(pf_handle h, const TileSum *gathered)
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
     k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc);
     k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
-                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc);
+                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
     k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
                                                                           h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max, h->sc);
@@ -1051,10 +1051,32 @@ extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_c
     if (phase) *phase = hdr.phase;
     if (hdr.phase != 4) return PF_OK;
     if (r.n_local > h->surv_cap) return set_error(h, PF_ERR_OVERFLOW, "shard produced more survivors than its survivor list holds (imbalance)");
+    {
+        long long tot_send = 0;
+        for (int k = 0; k < h->nranks; k++) tot_send += r.send_len[k];
+        if (tot_send * h->mig_rows > h->buf_cap) return set_error(h, PF_ERR_OVERFLOW, "shard must send more particles than its send buffer holds (imbalance)");
+    }
     for (int k = 0; k < h->nranks; k++) { if (send_counts) send_counts[k] = r.send_len[k]; if (recv_counts) recv_counts[k] = r.recv_len[k]; }
     if (n_local) *n_local = r.n_local;
     if (n_global) *n_global = r.n_global;
     h->n_host = r.n_mine;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    SelResult r; StepState st; RankOff ro; TileSum lt;
+    memset(&ro, 0, sizeof ro); memset(&lt, 0, sizeof lt);
+    CUDA_TRY(cudaMemcpy(&r, h->res, sizeof r, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&st, h->st, sizeof st, cudaMemcpyDeviceToHost));
+    if (h->ro) CUDA_TRY(cudaMemcpy(&ro, h->ro, sizeof ro, cudaMemcpyDeviceToHost));
+    if (h->local_tot) CUDA_TRY(cudaMemcpy(&lt, h->local_tot, sizeof lt, cudaMemcpyDeviceToHost));
+    int64_t v[24] = {(int64_t)r.thr_bits, r.scale, r.keep_all, (int64_t)r.T.lo, (int64_t)r.T.hi, (int64_t)r.Uoff.lo, (int64_t)r.Uoff.hi,
+                     (int64_t)r.Tq.lo, (int64_t)r.Tq.hi, r.Tr, r.A, r.n, r.rounds, st.n_live, st.M, st.n_next,
+                     (int64_t)lt.X.lo, (int64_t)lt.X.hi, lt.kept, ro.n_local, ro.g_first, ro.kept_off, (int64_t)ro.S_off.lo, ro.n_global};
+    for (int k = 0; k < 24; k++) out[k] = v[k];
     return PF_OK;
 }
 

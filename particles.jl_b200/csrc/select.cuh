@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 res->log_total = log(tsum) - (double)tot_scale * 0.693147180559945309417232121458;
             }
             int phase = 2;       // 2 = descend, 3 = redo classify with a new bracket, 4 = done, 7 = gathered list truncated
-            if (truncated) phase = 7;
+            if (truncated) { reset_round(sc); phase = 7; }      // the host re-classifies and gathers at exact size
             else if (keep_all) phase = 4;
             else if (mode == 2) {
                 // comb-rescale round: T at the new scale; lo = hi = thr so A_hi = A again
@@ -748,7 +748,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             res->thr_value = 0.0;
         } else {
             res->keep_all = 0;
-            const long long n = N - res->A;
+            long long n = N - res->A;
+            if (n < 0) { n = 0; res->status = 1; }          // cannot happen with consistent inputs
             res->n = n;
             const u128 T = res->T;
             // Uoff = floor(mu * T / 2^53), mu = floor(u 2^53): 192-bit product, then >> 53

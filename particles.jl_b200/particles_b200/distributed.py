@@ -175,7 +175,8 @@ class ShardedFearnheadParticles:
     """FearnheadParticles (src/fearnhead.jl:13-30) with the population sharded over
     comm.size ranks.  Same results as the unsharded filter, particle for particle."""
 
-    def __init__(self, n, prior, stateprior, comm, *, k_max=16, history=0, devices=None, seed=0):
+    def __init__(self, n, prior, stateprior, comm, *, k_max=16, history=0, devices=None, seed=0, sample_entries=None,
+                 cand_entries=None):
         from . import NormalInverseChisq, NormalInverseWishart
         import torch
         self.comm, self.N, self.k_max = comm, int(n), int(k_max)
@@ -203,11 +204,17 @@ class ShardedFearnheadParticles:
             self.d = cfg.d
             with torch.cuda.device(dev):
                 self.shards.append(_Shard(L, cfg, dev))
+        for s in self.shards:             # test hooks: force the fixed gather sizes (exercises the slow path)
+            if sample_entries is not None:
+                s.sample_entries = int(sample_entries)
+            if cand_entries is not None:
+                s.cand_entries = int(cand_entries)
         self.n_global = 1
         self.steps = 0
         self.host_syncs = 0
         self.bytes_moved = 0
         self.slow_steps = 0
+        self.profile = None              # set to [] to collect (label, cuda event) marks per step
 
     def close(self):
         for s in self.shards:
@@ -249,26 +256,55 @@ class ShardedFearnheadParticles:
         self.host_syncs += 1
         return plans
 
+    def _mark(self, label):
+        if self.profile is not None:
+            import time
+            import torch
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile.append((label, ev, time.perf_counter()))
+
+    def profile_summary(self):
+        """Mean device and host milliseconds between consecutive marks, by label."""
+        import torch
+        torch.cuda.synchronize()
+        dev, host, cnt = {}, {}, {}
+        for (l0, e0, t0), (l1, e1, t1) in zip(self.profile[:-1], self.profile[1:]):
+            if l1 == "begin":
+                continue
+            dev[l1] = dev.get(l1, 0.0) + e0.elapsed_time(e1)
+            host[l1] = host.get(l1, 0.0) + 1e3 * (t1 - t0)
+            cnt[l1] = cnt.get(l1, 0) + 1
+        return {k: (dev[k] / cnt[k], host[k] / cnt[k]) for k in dev}
+
     def fit_(self, y, u):
         """fit!(ps, y) (src/fearnhead.jl:130-184) on the sharded population; u = the rand()
         of src/fearnhead.jl:99."""
         comm, sh, L = self.comm, self.shards, self.L
+        self._mark("begin")
         y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
         py = y.ctypes.data_as(_dp)
         Bs, Bc = sh[0].sample_entries, sh[0].cand_entries
         for s in sh:
             _lib.check(L.pf_mg_begin(s.h, py, float(u)), s.h)
+            self._mark("expand")
             s.select(PF_MG_SAMPLE, 0, None, None, 0, Bs)
+        self._mark("sample")
         ga = comm.all_gather([s.acc for s in sh])
         gl = comm.all_gather([s.list[:Bs] for s in sh])
+        self._mark("gather_sample")
         for s, g, a in zip(sh, gl, ga):
             s.select(PF_MG_BRACKET | PF_MG_CLASSIFY, 0, a, g, Bs, Bc)
+        self._mark("bracket_classify")
         ga = comm.all_gather([s.acc for s in sh])
         gl = comm.all_gather([s.list[:Bc] for s in sh])
+        self._mark("gather_cand")
         for s, g, a in zip(sh, gl, ga):
             s.select(PF_MG_SOLVE, 0, a, g, Bc)
+        self._mark("solve")
         self.bytes_moved += 8 * (Bs + Bc + 2 * sh[0].acc.numel()) * comm.size
         plans = self._tail()
+        self._mark("tail+sync")
         phase = plans[0][4]
         if phase != 4:
             # rare: bracket verification failed, a finer scale is needed, or a list outgrew its
@@ -276,7 +312,7 @@ class ShardedFearnheadParticles:
             self.slow_steps += 1
             rounds = sh[0].state()[3]
             while phase != 4:
-                if phase == 3:
+                if phase in (3, 7):      # 3: new bracket / scale; 7: a fixed-size gather truncated the list
                     for s in sh:
                         s.select(PF_MG_CLASSIFY, rounds, None, None, 0, -1)
                 gl, ga, mx = self._gather_exact()
@@ -291,8 +327,10 @@ class ShardedFearnheadParticles:
         self.n_global = plans[0][3]
         comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
         self.bytes_moved += int(sum(int(p[0].sum()) for p in plans)) * sh[0].rows * 8
+        self._mark("exchange")
         for s in sh:
             _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)
+        self._mark("unpack")
         self.steps += 1
         return self
 

@@ -56,3 +56,23 @@ def test_device_plan_matches_host_plan():
     for r in range(G):
         send, recv, q, mine = partition_plan(n_local, r)
         assert res[r][0].tolist() == send.tolist() and res[r][1].tolist() == recv.tolist()
+
+
+@pytest.mark.parametrize("kw", [{"cand_entries": 64}, {"sample_entries": 64}, {"sample_entries": 64, "cand_entries": 64}])
+def test_slow_path_truncated_gather_and_rebracketing(kw):
+    """A candidate list that outgrows its fixed gather size (phase 7) and a sample too small to
+    bracket the threshold (verification failure, phase 3) both fall back to exact-size gathers
+    and still reproduce the unsharded run."""
+    rng = np.random.default_rng(11)
+    G, N, T = 4, 20000, 30
+    ys = _mix2d(rng, T)
+    us = rng.random(T)
+    prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
+    crp = pb.ChineseRestaurantProcess(1.0)
+    ref = pb.FearnheadParticles(N, prior, crp, history=T)
+    ref.filter_(ys, uniforms=us)
+    sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T, **kw)
+    sh.filter_(ys, us)
+    assert sh.slow_steps > 0
+    assert np.array_equal(sh.logweights(), ref.logweights())
+    assert np.array_equal(sh.ncomponents(), ref.ncomponents())
