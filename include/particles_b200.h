@@ -198,7 +198,7 @@ int32_t pf_mg_finish(pf_handle h, const void *gathered_totals);
 /* Exchange plan of the re-partitioning, in particles: send_counts[nranks] by destination,
  * recv_counts[nranks] by source.  Synchronises the stream. */
 int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
-                   int64_t *phase);
+                   int64_t *phase, int64_t *exchange);
 int32_t pf_mg_unpack(pf_handle h, const void *recv_buffer);
 /* Raw control-block words of the last threshold search / survivor scan (debugging aid). */
 int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */);

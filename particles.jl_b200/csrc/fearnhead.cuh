@@ -168,9 +168,11 @@ struct RankOff {
     long long n_local;             // survivors produced by this rank
     long long n_mine;              // particles this rank owns after re-partitioning
     long long n_global, q;
+    long long bnd[PF_MAX_RANKS + 1];   // new ownership: rank r owns global [bnd[r], bnd[r+1])
     long long goff_prev;           // global index of this rank's first PARENT (genealogy)
     int rank, nranks;
     long long overflow;            // survivors that did not fit this rank's survivor list / buffers
+    long long exchange;            // 0: every child stays on its parent's rank this step (same decision on all ranks)
     long long send_start[PF_MAX_RANKS], send_len[PF_MAX_RANKS], send_off[PF_MAX_RANKS];   // by destination (particles / doubles)
     long long recv_idx0[PF_MAX_RANKS], recv_len[PF_MAX_RANKS], recv_off[PF_MAX_RANKS];    // by source
 };
@@ -178,7 +180,7 @@ struct RankOff {
 // one thread: turn the gathered per-rank totals (mass of the low partition, kept count) into
 // this rank's offsets and the exchange plan.  rows = doubles per migrating particle.
 __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, int nranks, const SelResult *__restrict__ res,
-                               StepState *st, RankOff *ro, int rows, const SelScratch *guard)
+                               StepState *st, RankOff *ro, int rows, const SelScratch *guard, long long stay_cap)
 {
     if (threadIdx.x || blockIdx.x) return;
     if (guard && guard->phase != 4) { ro->n_local = 0; return; }          // the threshold search has not finished (speculative tail)
@@ -199,20 +201,29 @@ __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, i
     const long long n_global = gpre;
     long long q = (n_global + nranks - 1) / nranks;
     if (q < 1) q = 1;
+    // Ownership after the step.  Children stay on their parent's rank while every rank's
+    // share fits `stay_cap` (no exchange at all); otherwise the population is re-partitioned
+    // into equal blocks of q.  Either way rank r owns a contiguous range of the global order.
+    long long mx = 0, mn = n_global;
+    for (int r = 0; r < nranks; r++) { mx = n_loc[r] > mx ? n_loc[r] : mx; mn = n_loc[r] < mn ? n_loc[r] : mn; }
+    const bool stay = mx <= stay_cap && (mn > 0 || n_global < nranks) && mx - mn <= (q >> 3) + 64;
+    for (int r = 0; r <= nranks; r++) {
+        long long b = stay ? (r < nranks ? g_first[r] : n_global) : (long long)r * q;
+        ro->bnd[r] = b > n_global ? n_global : b;
+    }
     ro->g_first = g_first[rank]; ro->n_local = n_loc[rank]; ro->n_global = n_global; ro->q = q;
-    long long mine = n_global - (long long)rank * q;
-    ro->n_mine = mine < 0 ? 0 : (mine > q ? q : mine);
-    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0;
+    ro->n_mine = ro->bnd[rank + 1] - ro->bnd[rank];
+    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0; ro->exchange = stay ? 0 : 1;
     long long soff = 0, roff = 0;
     for (int d = 0; d < nranks; d++) {
-        long long lo = g_first[rank] > d * q ? g_first[rank] : d * q;
-        long long hi = g_first[rank] + n_loc[rank] < (d + 1) * q ? g_first[rank] + n_loc[rank] : (d + 1) * q;
+        long long lo = g_first[rank] > ro->bnd[d] ? g_first[rank] : ro->bnd[d];
+        long long hi = g_first[rank] + n_loc[rank] < ro->bnd[d + 1] ? g_first[rank] + n_loc[rank] : ro->bnd[d + 1];
         long long len = (d == rank || hi <= lo) ? 0 : hi - lo;
         ro->send_start[d] = lo; ro->send_len[d] = len; ro->send_off[d] = soff; soff += len * rows;
-        long long lo2 = g_first[d] > rank * q ? g_first[d] : rank * q;
-        long long hi2 = g_first[d] + n_loc[d] < (rank + 1) * q ? g_first[d] + n_loc[d] : (rank + 1) * q;
+        long long lo2 = g_first[d] > ro->bnd[rank] ? g_first[d] : ro->bnd[rank];
+        long long hi2 = g_first[d] + n_loc[d] < ro->bnd[rank + 1] ? g_first[d] + n_loc[d] : ro->bnd[rank + 1];
         long long len2 = (d == rank || hi2 <= lo2) ? 0 : hi2 - lo2;
-        ro->recv_idx0[d] = lo2 - rank * q; ro->recv_len[d] = len2; ro->recv_off[d] = roff; roff += len2 * rows;
+        ro->recv_idx0[d] = lo2 - ro->bnd[rank]; ro->recv_len[d] = len2; ro->recv_off[d] = roff; roff += len2 * rows;
     }
     st->n_kept = my_kept; st->n_picked = my_picked; st->n_next = ro->n_mine; st->n_global = n_global;
 }
@@ -412,9 +423,10 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
     unsigned int anc_off = 0;
     if (ro) {
         const long long g = ro->g_first + t;
-        const long long dest = g / ro->q;
+        int dest = 0;
+        while (dest + 1 < ro->nranks && g >= ro->bnd[dest + 1]) dest++;
         anc_off = (unsigned int)ro->goff_prev;
-        if (dest == ro->rank) { idx = g - dest * ro->q; dstb = S2 + idx; }
+        if (dest == ro->rank) { idx = g - ro->bnd[dest]; dstb = S2 + idx; }
         else { remote = true; stride = ro->send_len[dest]; dstb = sendbuf + ro->send_off[dest] + (g - ro->send_start[dest]); }
     }
     const unsigned int par = surv_parent[t];

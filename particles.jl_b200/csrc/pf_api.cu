@@ -69,6 +69,8 @@ struct pf_filter_s {
     long long mg_stride = 1, mg_sample_entries = 0, mg_cand_entries = 0;
     bool own_stream = true;
     double *y1_dev = nullptr;             // y (d) + u (1) of the current sharded step
+    double *y1_pin = nullptr;             // pinned staging ring for (y, u)
+    int y1_slot = 0;
     // genealogy
     unsigned int *gen_anc = nullptr;
     unsigned char *gen_asg = nullptr;
@@ -79,7 +81,7 @@ struct pf_filter_s {
     long long ub_live = 1;                // host upper bound on n_live (grid sizing)
     std::vector<StepLog> logs;            // records of the last call
     StepLog last{};
-    bool have_last = false;
+    bool have_last = false, last_stale = false;
     int sel_grid = 0;
     int num_sms = 0;
     double last_ms = 0.0;
@@ -215,6 +217,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->gscal, h->local_tot, h->ro, h->sendbuf,
                     h->recvbuf, h->y1_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->y1_pin) cudaFreeHost(h->y1_pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -256,6 +259,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     h->nranks = cfg->nranks > 1 ? cfg->nranks : 1;
     h->rank = h->nranks > 1 ? cfg->rank : 0;
     h->cap = (cfg->n_particles + h->nranks - 1) / h->nranks;
+    if (h->nranks > 1) h->cap += h->cap / 8 + 64;          // slack: children stay on their parent's rank while shares fit
     h->F = 2 + d + d * (d + 1) / 2;
     h->mu0.assign(cfg->mu0, cfg->mu0 + d);
     h->lam0.assign(d * d, 0.0);
@@ -324,9 +328,10 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     h->cand_cap = (long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
     if (h->nranks > 1) {
         const long long pad = (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK;
+        const long long spad = (long long)SEL_SAMPLE_WARPS * SEL_CHUNK;
         h->mg_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
-        h->mg_sample_entries = (2 * SEL_SAMPLE_TARGET + h->nranks - 1) / h->nranks + pad + 1024;
-        h->mg_cand_entries = std::max<long long>(1 << 18, (4ll << 20) / h->nranks) + pad;
+        h->mg_sample_entries = (2 * SEL_SAMPLE_TARGET + h->nranks - 1) / h->nranks + spad + 1024;
+        h->mg_cand_entries = std::max<long long>(1 << 17, (2ll << 20) / h->nranks) + pad;
         h->cand_cap = std::max(h->cand_cap, std::max(h->mg_sample_entries, h->mg_cand_entries) + pad);
     }
     CT(dmalloc(&h->cand, (size_t)h->cand_cap));
@@ -713,6 +718,12 @@ extern "C" int32_t pf_get_last_step(pf_handle h, pf_step_stats *o)
 {
     if (!h || !o) return PF_ERR_ARG;
     if (!h->have_last) return set_error(h, PF_ERR_STATE, "pf_get_last_step: no step has run");
+    if (h->last_stale) {
+        CUDA_TRY(cudaSetDevice(h->cfg.device));
+        CUDA_TRY(cudaMemcpyAsync(&h->last, h->slog, sizeof(StepLog), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->last_stale = false;
+    }
     const StepLog &r = h->last;
     memset(o, 0, sizeof *o);
     o->step = h->steps; o->n_in = r.n_in; o->n_putative = r.M; o->n_kept = r.n_kept; o->n_resamp_req = r.n_req;
@@ -902,7 +913,7 @@ __global__ void k_steplog_mg(StepState *st, const SelResult *res, const RankOff 
     r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds;
     for (int k = 0; k < 4; k++) r.sel_us[k] = 0.0;
     *lg = r;
-    st->goff = (long long)ro->rank * ro->q;
+    st->goff = ro->bnd[ro->rank];
 }
 
 #define MG_CHECK(h) do { if (!(h)) return PF_ERR_ARG; if ((h)->nranks < 2) return set_error((h), PF_ERR_STATE, "not a sharded handle (pf_config.nranks < 2)"); } while (0)
@@ -951,11 +962,11 @@ extern "C" int32_t pf_mg_begin(pf_handle h, const double *y, double u)
     int32_t rc = ensure_table(h, h->steps + 3);
     if (rc != PF_OK) return rc;
     if (h->hist_cap && h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
-    double buf[PF_MAX_D + 1];
+    if (!h->y1_pin) CUDA_TRY(cudaMallocHost((void **)&h->y1_pin, sizeof(double) * 64 * (PF_MAX_D + 1)));
+    double *buf = h->y1_pin + (size_t)(h->y1_slot++ & 63) * (PF_MAX_D + 1);   // 64 steps ahead of any reuse: the step's sync bounds the lag
     for (int k = 0; k < h->d; k++) buf[k] = y[k];
     buf[h->d] = u;
     CUDA_TRY(cudaMemcpyAsync(h->y1_dev, buf, sizeof(double) * (h->d + 1), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));       // buf is on the stack
     h->mg_rounds = 0;
     DISPATCH_D(h->d, rc = mg_begin<D>(h));
     CUDA_TRY(cudaGetLastError());
@@ -1017,7 +1028,7 @@ static int32_t mg_finish(pf_handle h, const TileSum *gathered)
     const int cur = h->cur, nxt = cur ^ 1;
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc);
+    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc, h->cap);
     k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
                                                                                   h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
     k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
@@ -1039,7 +1050,7 @@ extern "C" int32_t pf_mg_finish(pf_handle h, const void *gathered_totals)
 }
 
 extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
-                              int64_t *phase)
+                              int64_t *phase, int64_t *exchange)
 {
     MG_CHECK(h);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -1059,6 +1070,7 @@ extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_c
     for (int k = 0; k < h->nranks; k++) { if (send_counts) send_counts[k] = r.send_len[k]; if (recv_counts) recv_counts[k] = r.recv_len[k]; }
     if (n_local) *n_local = r.n_local;
     if (n_global) *n_global = r.n_global;
+    if (exchange) *exchange = r.exchange;
     h->n_host = r.n_mine;
     return PF_OK;
 }
@@ -1092,8 +1104,7 @@ extern "C" int32_t pf_mg_unpack(pf_handle h, const void *recv)
     k_steplog_mg<<<1, 32, 0, h->stream>>>(h->st, h->res, h->ro, h->slog);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(&h->last, h->slog, sizeof(StepLog), cudaMemcpyDeviceToHost, h->stream));
-    h->have_last = true;
+    h->have_last = true; h->last_stale = true;       // the record is fetched when pf_get_last_step asks for it
     h->cur = nxt;
     h->steps++;
     return PF_OK;

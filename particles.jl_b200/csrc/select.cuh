@@ -28,7 +28,8 @@ namespace cg = cooperative_groups;
 #define SEL_WARPS (SEL_THREADS / 32)
 #define SEL_FINAL_CAP 2048
 #define SEL_BINS 1024
-#define SEL_CHUNK 64
+#define SEL_CHUNK 32
+#define SEL_SAMPLE_WARPS 64          // sharded run: warps that gather the sample (bounds the list padding)
 #define SEL_SAMPLE_TARGET (1 << 20)
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax
@@ -464,7 +465,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             unsigned long long cnt_s = 0;
             const long long sphase = a.goff ? *a.goff : 0;
             const long long first = (stride - (sphase % stride)) % stride;
-            for (long long base = gwarp * 32; first + base * stride < n_live; base += nwarps * 32) {
+            const long long swarps = multi ? (nwarps < SEL_SAMPLE_WARPS ? nwarps : SEL_SAMPLE_WARPS) : nwarps;
+            for (long long base = gwarp * 32; gwarp < swarps && first + base * stride < n_live; base += swarps * 32) {
                 long long i = first + (base + lane) * stride;
                 int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
                 int maxc = c;

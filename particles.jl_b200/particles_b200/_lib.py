@@ -78,7 +78,7 @@ SYMBOLS = [
     ("pf_mg_tiles", C.c_int32, [C.c_void_p]),
     ("pf_mg_finish", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_mg_plan", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
-                               C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+                               C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("pf_mg_unpack", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_debug_dump", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("pf_last_timing", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),

@@ -26,24 +26,28 @@ _dp = C.POINTER(C.c_double)
 
 
 # ------------------------------------------------------------------ host-side plan (pure)
-def partition_plan(n_local_all, rank):
-    """Re-partitioning of a rank-major population with n_local_all[r] particles produced on
-    rank r into equal blocks of q = ceil(n / G): (send_counts by destination, recv_counts by
-    source, q, n_mine) for `rank`.  Mirrors k_rank_offsets (csrc/fearnhead.cuh)."""
+def partition_plan(n_local_all, rank, stay_cap=0):
+    """Ownership of a rank-major population with n_local_all[r] particles produced on rank r.
+    Children stay on their parent's rank while every share fits `stay_cap` and the shares are
+    within q/8 + 64 of each other; otherwise equal blocks of q = ceil(n / G).  Returns
+    (send_counts by destination, recv_counts by source, q, n_mine) for `rank`.  Mirrors
+    k_rank_offsets (csrc/fearnhead.cuh)."""
     n_local_all = [int(x) for x in n_local_all]
     G = len(n_local_all)
     first = np.concatenate([[0], np.cumsum(n_local_all)]).astype(np.int64)
     n = int(first[-1])
     q = max((n + G - 1) // G, 1)
+    mx, mn = max(n_local_all), min(n_local_all)
+    stay = mx <= stay_cap and (mn > 0 or n < G) and mx - mn <= (q >> 3) + 64
+    bnd = [min(int(first[r]) if stay else r * q, n) for r in range(G)] + [n if stay else min(G * q, n)]
     send = np.zeros(G, dtype=np.int64)
     recv = np.zeros(G, dtype=np.int64)
     for d in range(G):
-        lo, hi = max(first[rank], d * q), min(first[rank] + n_local_all[rank], (d + 1) * q)
+        lo, hi = max(first[rank], bnd[d]), min(first[rank] + n_local_all[rank], bnd[d + 1])
         send[d] = 0 if d == rank else max(hi - lo, 0)
-        lo, hi = max(first[d], rank * q), min(first[d] + n_local_all[d], (rank + 1) * q)
+        lo, hi = max(first[d], bnd[rank]), min(first[d] + n_local_all[d], bnd[rank + 1])
         recv[d] = 0 if d == rank else max(hi - lo, 0)
-    n_mine = min(max(n - rank * q, 0), q)
-    return send, recv, q, n_mine
+    return send, recv, q, bnd[rank + 1] - bnd[rank]
 
 
 # ------------------------------------------------------------------ communicators
@@ -166,9 +170,9 @@ class _Shard:
 
     def plan(self, G):
         sc, rc = (C.c_int64 * G)(), (C.c_int64 * G)()
-        nl, ng, ph = C.c_int64(), C.c_int64(), C.c_int64()
-        _lib.check(self.L.pf_mg_plan(self.h, sc, rc, C.byref(nl), C.byref(ng), C.byref(ph)), self.h)
-        return np.array(sc[:], dtype=np.int64), np.array(rc[:], dtype=np.int64), nl.value, ng.value, ph.value
+        nl, ng, ph, ex = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.L.pf_mg_plan(self.h, sc, rc, C.byref(nl), C.byref(ng), C.byref(ph), C.byref(ex)), self.h)
+        return np.array(sc[:], dtype=np.int64), np.array(rc[:], dtype=np.int64), nl.value, ng.value, ph.value, ex.value
 
 
 class ShardedFearnheadParticles:
@@ -214,6 +218,7 @@ class ShardedFearnheadParticles:
         self.host_syncs = 0
         self.bytes_moved = 0
         self.slow_steps = 0
+        self.exchanges = 0
         self.profile = None              # set to [] to collect (label, cuda event) marks per step
 
     def close(self):
@@ -325,10 +330,13 @@ class ShardedFearnheadParticles:
                     raise RuntimeError("threshold search did not converge")
             plans = self._tail()
         self.n_global = plans[0][3]
-        comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
-        self.bytes_moved += int(sum(int(p[0].sum()) for p in plans)) * sh[0].rows * 8
+        moving = int(sum(int(p[0].sum()) for p in plans))
+        if plans[0][5]:                    # children stay on their parent's rank while the shares fit: usually nothing moves
+            comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
+            self.exchanges += 1
+        self.bytes_moved += moving * sh[0].rows * 8
         self._mark("exchange")
-        for s in sh:
+        for s in sh:             # (also closes the step when nothing was received)
             _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)
         self._mark("unpack")
         self.steps += 1

@@ -20,6 +20,17 @@ def _brute(n_local_all, rank):
     return send, recv, q, int(np.sum(owner_new == rank))
 
 
+def test_partition_plan_stay_rule():
+    # balanced shares that fit the capacity: nothing moves, ownership follows the parents
+    send, recv, q, mine = partition_plan([100, 103, 98, 99], 1, stay_cap=120)
+    assert send.sum() == 0 and recv.sum() == 0 and mine == 103
+    # a share above the capacity, or too unbalanced: equal blocks
+    for case, cap in (([100, 130, 98, 99], 120), ([10, 200, 200, 200], 1000)):
+        tot = [partition_plan(case, r, stay_cap=cap) for r in range(4)]
+        assert sum(int(t[0].sum()) for t in tot) > 0
+        assert [t[3] for t in tot] == [t[2] for t in tot][:3] + [sum(case) - 3 * tot[0][2]]
+
+
 def test_partition_plan_matches_brute_force():
     rng = np.random.default_rng(0)
     cases = [[1, 0], [0, 0, 0, 0], [52, 0, 0, 0], [100, 103, 98, 99], [5, 0, 17, 1, 0, 0, 3, 9]]
