@@ -149,24 +149,29 @@ int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t N, double 
  * rank runs the same kernels on its shard and the host program supplies the collectives
  * between the stages below ("bring your own communicator": torch.distributed / NCCL in
  * particles_b200/distributed.py, MPI.jl or NCCL.jl under the Julia shim).  What crosses the
- * ranks per observation: two scalars (all-reduce), the strided sample and the bracket's
- * candidates (all-gather of a few MB), one 32-byte total per rank (all-gather) and the
- * records of the particles that change owner when the new population is re-partitioned
- * (all-to-all-v).  All decisions are integer arithmetic on gathered data, so every rank
+ * ranks per observation: the strided sample and the bracket's candidates with their
+ * accumulator blocks (all-gather of a few MB), one 32-byte total per rank (all-gather) and,
+ * only when a share outgrows its shard, the records of the particles that change owner in
+ * the re-partitioning (all-to-all-v).  All decisions are integer arithmetic on gathered data, so every rank
  * reaches the same threshold and an N-rank run reproduces the 1-rank run bit for bit.
  *
  *   pf_mg_begin(y, u)                     expansion of the local shard
- *   all_reduce(scalars[0] SUM, scalars[1] MAX)                       (M, max weight bits)
- *   pf_mg_select(PF_MG_SAMPLE)            local strided sample -> list, acc
- *   all_gather(acc) ; all_gather(list[0 : max chunks * 256])
- *   pf_mg_select(PF_MG_BRACKET | PF_MG_CLASSIFY)   bracket from the gathered sample, classify the shard
- *   all_gather(acc) ; all_gather(list ...)
- *   pf_mg_select(PF_MG_SOLVE)             verify / descend / solve on the gathered candidates;
- *                                         state[0] == 3 -> another PF_MG_CLASSIFY + gather + PF_MG_SOLVE
+ *   pf_mg_select(PF_MG_SAMPLE, pad_to = sample_entries)        local strided sample -> list, acc
+ *   all_gather(acc) ; all_gather(list[0 : sample_entries])
+ *   pf_mg_select(PF_MG_BRACKET | PF_MG_CLASSIFY, gathered acc, gathered list, sample_entries, pad_to = cand_entries)
+ *                                         bracket from the gathered sample, classify the shard
+ *   all_gather(acc) ; all_gather(list[0 : cand_entries])
+ *   pf_mg_select(PF_MG_SOLVE, gathered acc, gathered list, cand_entries)
+ *                                         verify / descend / solve on the gathered candidates
  *   pf_mg_tiles()                         local survivor-scan totals -> local_total
  *   all_gather(local_total)
  *   pf_mg_finish(gathered totals)         offsets, survivor scan, instantiate (local + send buffer)
- *   all_to_all_v(send buffer -> recv buffer, split sizes from pf_mg_plan)
+ *   pf_mg_plan(...)                       THE host synchronisation of the step: search outcome
+ *                                         (phase 4 = done; 3 / 7 = another PF_MG_CLASSIFY + exact-size
+ *                                         gathers + PF_MG_SOLVE, then tiles/finish again) and the
+ *                                         exchange plan; the kernels after PF_MG_SOLVE are no-ops
+ *                                         until the search is done, so they may be queued behind it
+ *   [exchange != 0] all_to_all_v(send buffer -> recv buffer, split sizes = counts * rows)
  *   pf_mg_unpack(recv buffer)             received particles -> local store; step done          */
 enum { PF_MG_SAMPLE = 1, PF_MG_BRACKET = 2, PF_MG_CLASSIFY = 4, PF_MG_SOLVE = 8 };
 typedef struct {

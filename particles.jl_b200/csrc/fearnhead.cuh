@@ -202,11 +202,12 @@ __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, i
     long long q = (n_global + nranks - 1) / nranks;
     if (q < 1) q = 1;
     // Ownership after the step.  Children stay on their parent's rank while every rank's
-    // share fits `stay_cap` (no exchange at all); otherwise the population is re-partitioned
-    // into equal blocks of q.  Either way rank r owns a contiguous range of the global order.
+    // share fits `stay_cap` (the shard capacity, N/G plus 1/8 slack) and no share has fallen
+    // below q/2 (no exchange at all); otherwise the population is re-partitioned into equal
+    // blocks of q.  Either way rank r owns a contiguous range of the global order.
     long long mx = 0, mn = n_global;
     for (int r = 0; r < nranks; r++) { mx = n_loc[r] > mx ? n_loc[r] : mx; mn = n_loc[r] < mn ? n_loc[r] : mn; }
-    const bool stay = mx <= stay_cap && (mn > 0 || n_global < nranks) && mx - mn <= (q >> 3) + 64;
+    const bool stay = mx <= stay_cap && (mn > 0 || n_global < nranks) && mn >= (q >> 1);
     for (int r = 0; r <= nranks; r++) {
         long long b = stay ? (r < nranks ? g_first[r] : n_global) : (long long)r * q;
         ro->bnd[r] = b > n_global ? n_global : b;

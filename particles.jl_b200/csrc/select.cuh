@@ -29,7 +29,7 @@ namespace cg = cooperative_groups;
 #define SEL_FINAL_CAP 2048
 #define SEL_BINS 1024
 #define SEL_CHUNK 32
-#define SEL_SAMPLE_WARPS 64          // sharded run: warps that gather the sample (bounds the list padding)
+#define SEL_SAMPLE_WARPS 1024         // sharded run: warps that gather the sample (bounds the list padding)
 #define SEL_SAMPLE_TARGET (1 << 20)
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax

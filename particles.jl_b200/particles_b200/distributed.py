@@ -28,8 +28,8 @@ _dp = C.POINTER(C.c_double)
 # ------------------------------------------------------------------ host-side plan (pure)
 def partition_plan(n_local_all, rank, stay_cap=0):
     """Ownership of a rank-major population with n_local_all[r] particles produced on rank r.
-    Children stay on their parent's rank while every share fits `stay_cap` and the shares are
-    within q/8 + 64 of each other; otherwise equal blocks of q = ceil(n / G).  Returns
+    Children stay on their parent's rank while every share fits `stay_cap` and none is below
+    q/2; otherwise equal blocks of q = ceil(n / G).  Returns
     (send_counts by destination, recv_counts by source, q, n_mine) for `rank`.  Mirrors
     k_rank_offsets (csrc/fearnhead.cuh)."""
     n_local_all = [int(x) for x in n_local_all]
@@ -38,7 +38,7 @@ def partition_plan(n_local_all, rank, stay_cap=0):
     n = int(first[-1])
     q = max((n + G - 1) // G, 1)
     mx, mn = max(n_local_all), min(n_local_all)
-    stay = mx <= stay_cap and (mn > 0 or n < G) and mx - mn <= (q >> 3) + 64
+    stay = mx <= stay_cap and (mn > 0 or n < G) and mn >= (q >> 1)
     bnd = [min(int(first[r]) if stay else r * q, n) for r in range(G)] + [n if stay else min(G * q, n)]
     send = np.zeros(G, dtype=np.int64)
     recv = np.zeros(G, dtype=np.int64)

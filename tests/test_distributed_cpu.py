@@ -25,7 +25,7 @@ def test_partition_plan_stay_rule():
     send, recv, q, mine = partition_plan([100, 103, 98, 99], 1, stay_cap=120)
     assert send.sum() == 0 and recv.sum() == 0 and mine == 103
     # a share above the capacity, or too unbalanced: equal blocks
-    for case, cap in (([100, 130, 98, 99], 120), ([10, 200, 200, 200], 1000)):
+    for case, cap in (([100, 130, 98, 99], 120), ([10, 200, 200, 200], 1000)):     # above capacity / below q/2
         tot = [partition_plan(case, r, stay_cap=cap) for r in range(4)]
         assert sum(int(t[0].sum()) for t in tot) > 0
         assert [t[3] for t in tot] == [t[2] for t in tot][:3] + [sum(case) - 3 * tot[0][2]]
