@@ -148,8 +148,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     ps = ShardedFearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
                                    pb.ChineseRestaurantProcess(1.0), TorchComm(), k_max=K_MAX, history=0, devices=[local])
     o = 0
-    for t in range(a.burnin + W):
-        ps.fit_(ys[o], us[o]); o += 1
+    ps.filter_(ys[o:o + a.burnin + W], us[o:o + a.burnin + W], lookahead=a.lookahead); o += a.burnin + W
     kbar0 = float(ps.ncomponents().mean())
     n0 = len(ps)
     launches0 = ps.shards[0].L.pf_last_timing  # noqa: F841  (kept for symmetry; launches read below)
@@ -165,8 +164,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize(dev)
     ev0.record()
-    for t in range(K):
-        ps.fit_(ys[o], us[o]); o += 1
+    ps.filter_(ys[o:o + K], us[o:o + K], lookahead=a.lookahead); o += K
     ev1.record()
     torch.cuda.synchronize(dev); dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -178,8 +176,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     # (2) end to end: wall clock around the same public call with host observation buffers
     dist.barrier(); torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for t in range(K):
-        ps.fit_(ys[o], us[o]); o += 1
+    ps.filter_(ys[o:o + K], us[o:o + K], lookahead=a.lookahead); o += K
     le = ps.last_step()["log_total_w"]
     torch.cuda.synchronize(dev); dist.barrier()
     wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -189,8 +186,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     kbar = 0.5 * (kbar0 + float(ps.ncomponents().mean()))
     # (3) stage timeline (device ms, host ms) over a few more steps
     ps.profile = []
-    for t in range(min(K, 8)):
-        ps.fit_(ys[o % T_all], us[o % T_all]); o += 1
+    ps.filter_(ys[o:o + 8], us[o:o + 8], lookahead=a.lookahead); o += 8
     stage_ms = ps.profile_summary()
     ps.profile = None
     if rank != 0:
@@ -203,7 +199,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0,
                                                 host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K,
-                                                slow_path_steps=ps.slow_steps,
+                                                slow_path_steps=ps.slow_steps, exchanges=ps.exchanges, lookahead=a.lookahead,
                                                 stage_ms_device_host={k: [round(v[0], 4), round(v[1], 4)] for k, v in stage_ms.items()}),
             "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
                     "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le)},
@@ -228,6 +224,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--order", default="index", choices=["index", "sorted"])
+    ap.add_argument("--lookahead", type=int, default=10, help="sharded run: observations queued per host synchronisation")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

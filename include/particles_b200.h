@@ -205,6 +205,15 @@ int32_t pf_mg_finish(pf_handle h, const void *gathered_totals);
 int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
                    int64_t *phase, int64_t *exchange);
 int32_t pf_mg_unpack(pf_handle h, const void *recv_buffer);
+/* Look-ahead: pf_mg_close() after pf_mg_finish marks the step as "needs the host" on the device when the search
+ * did not finish or particles must change owner; every kernel of later steps is then a no-op, so a host program
+ * may queue several observations ahead and call pf_mg_drain() (synchronises; out = {halt (1 + step index, or 0),
+ * phase, local population, global population}) only now and then.  After completing a halted step through the
+ * synchronous stages, pf_mg_resume(step) rewinds the host mirrors to `step` and clears the mark. */
+int32_t pf_mg_close(pf_handle h);
+int32_t pf_mg_set_obs(pf_handle h, const double *y, double u);   /* re-upload (y, u) of a halted step before completing it */
+int32_t pf_mg_drain(pf_handle h, int64_t out[4]);
+int32_t pf_mg_resume(pf_handle h, int64_t step);
 /* Raw control-block words of the last threshold search / survivor scan (debugging aid). */
 int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */);
 

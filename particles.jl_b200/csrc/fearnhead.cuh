@@ -32,9 +32,11 @@ struct StepLog {            // one record per step, read back after pf_filter
 // the new-cluster putative (src/particle.jl:108-112 with comp = p.prior) and the slot a
 // new cluster starts with (add(prior, y), src/component.jl:85).
 template <int D>
-__global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, StepConst *sc_out, int first)
+__global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, StepConst *sc_out, int first,
+                          const SelScratch *guard)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (guard && guard->halt) return;
     using L = Layout<D>;
     if (!first) st->n_live = st->n_next;
     st->n_next = 0;
@@ -74,9 +76,11 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
-                                                double *__restrict__ V, unsigned char *__restrict__ cnt)
+                                                double *__restrict__ V, unsigned char *__restrict__ cnt,
+                                                const SelScratch *guard)
 {
     using L = Layout<D>;
+    if (guard && guard->halt) return;
     __shared__ u64 s_max[8];
     __shared__ long long s_M[8], s_ovf[8];
     const long long n_live = st->n_live;
@@ -183,7 +187,7 @@ __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, i
                                StepState *st, RankOff *ro, int rows, const SelScratch *guard, long long stay_cap)
 {
     if (threadIdx.x || blockIdx.x) return;
-    if (guard && guard->phase != 4) { ro->n_local = 0; return; }          // the threshold search has not finished (speculative tail)
+    if (guard && (guard->phase != 4 || guard->halt)) { ro->n_local = 0; return; }          // the threshold search has not finished (speculative tail)
     const bool comb = res->n > 0 && !isz128(res->T);
     const u64 n = (u64)res->n;
     u128 Spre = mk128(0, 0);
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
                                                             const long long *__restrict__ n_items_ptr, TileSum *__restrict__ tiles,
                                                             int mode, const SelScratch *guard)
 {
-    if (guard && guard->phase != 4) return;
+    if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_x[SCAN_THREADS / 32];
     __shared__ unsigned int s_k[SCAN_THREADS / 32];
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelR
                                                       TileSum *local_tot /* sharded run: totals out, counts set later */,
                                                       const SelScratch *guard)
 {
-    if (guard && guard->phase != 4) return;
+    if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
     __shared__ unsigned int s_k[1024];
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                                                              const RankOff *__restrict__ ro, const SelScratch *guard,
                                                              long long surv_cap)
 {
-    if (guard && guard->phase != 4) return;
+    if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
     __shared__ unsigned int s_wc[33];
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
                                                      const SelScratch *guard)
 {
     using L = Layout<D>;
-    if (guard && guard->phase != 4) return;
+    if (guard && (guard->phase != 4 || guard->halt)) return;
     const long long n_out = ro ? ro->n_local : st->n_next;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_out) return;                       // (grid = survivor-list capacity: no thread beyond it)
@@ -500,8 +504,9 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
 __global__ void __launch_bounds__(256) k_unpack(const double *__restrict__ recv, const RankOff *__restrict__ ro,
                                                 double *__restrict__ S2, int *__restrict__ Kc2, double *__restrict__ logw2,
                                                 unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
-                                                long long cap, int store_rows, int F)
+                                                long long cap, int store_rows, int F, const SelScratch *guard)
 {
+    if (guard && guard->halt) return;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int s = 0;
     const int G = ro->nranks;

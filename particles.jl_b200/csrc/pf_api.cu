@@ -413,12 +413,12 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     h->epoch++;
     {
         LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, nullptr);
     }
     {
         LaunchTimer lt(h, KC_EXPAND);
         k_expand<D><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                h->stc, h->st, h->V, h->cnt);
+                                                                h->stc, h->st, h->V, h->cnt, nullptr);
     }
     {
         LaunchTimer lt(h, KC_SELECT);
@@ -485,7 +485,7 @@ static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_de
     const int g256 = grid_for(N, 256);
     {
         LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, nullptr);
     }
     {
         LaunchTimer lt(h, KC_CL_PROP);
@@ -899,13 +899,22 @@ done:
 // ------------------------------------------------------------------ sharded run (bring your own collective)
 __global__ void k_publish_scalars(const StepState *st, SelScratch *sc)
 {
-    if (threadIdx.x || blockIdx.x) return;
+    if (threadIdx.x || blockIdx.x || sc->halt) return;
     sc->M_local = (unsigned long long)st->M; sc->vmax_local = st->vmax_bits;
 }
 
-__global__ void k_steplog_mg(StepState *st, const SelResult *res, const RankOff *ro, StepLog *lg)
+// sharded look-ahead: decide whether this step needs the host (search unfinished, particles must
+// change owner, or a list overflowed); if so every later kernel is a no-op until pf_mg_resume
+__global__ void k_close(SelScratch *sc, const RankOff *ro, long long step, long long surv_cap)
+{
+    if (threadIdx.x || blockIdx.x || sc->halt) return;
+    if (sc->phase != 4 || ro->exchange || ro->n_local > surv_cap) sc->halt = step + 1;
+}
+
+__global__ void k_steplog_mg(StepState *st, const SelResult *res, const RankOff *ro, StepLog *lg, const SelScratch *guard)
 {
     if (threadIdx.x || blockIdx.x) return;
+    if (guard && guard->halt) return;
     StepLog r;
     r.n_in = st->n_live; r.M = st->M; r.n_kept = st->n_kept; r.n_req = res->keep_all ? 0 : res->n;
     r.n_got = st->n_picked; r.n_out = ro->n_global; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
@@ -946,9 +955,9 @@ template <int D>
 static int32_t mg_begin(pf_handle h)
 {
     if (h->slog_cap < 1) { CUDA_TRY(dmalloc(&h->slog, 16)); h->slog_cap = 16; }
-    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0);
+    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc);
     k_expand<D><<<grid_for(h->cap, 256), 256, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->k_max, h->tab,
-                                                                h->pc, h->stc, h->st, h->V, h->cnt);
+                                                                h->pc, h->stc, h->st, h->V, h->cnt, h->sc);
     k_publish_scalars<<<1, 32, 0, h->stream>>>(h->st, h->sc);
     h->launches += 3;
     return PF_OK;
@@ -1075,6 +1084,52 @@ extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_c
     return PF_OK;
 }
 
+extern "C" int32_t pf_mg_set_obs(pf_handle h, const double *y, double u)
+{
+    MG_CHECK(h);
+    if (!y) return PF_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->y1_pin) CUDA_TRY(cudaMallocHost((void **)&h->y1_pin, sizeof(double) * 64 * (PF_MAX_D + 1)));
+    double *buf = h->y1_pin + (size_t)(h->y1_slot++ & 63) * (PF_MAX_D + 1);
+    for (int k = 0; k < h->d; k++) buf[k] = y[k];
+    buf[h->d] = u;
+    CUDA_TRY(cudaMemcpyAsync(h->y1_dev, buf, sizeof(double) * (h->d + 1), cudaMemcpyHostToDevice, h->stream));
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_close(pf_handle h)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    k_close<<<1, 32, 0, h->stream>>>(h->sc, h->ro, h->steps, h->surv_cap);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_drain(pf_handle h, int64_t out[4])
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    SelScratch hdr; StepState st;
+    CUDA_TRY(cudaMemcpyAsync(&hdr, h->sc, offsetof(SelScratch, A_hi), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(&st, h->st, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    out[0] = hdr.halt; out[1] = hdr.phase; out[2] = st.n_next; out[3] = st.n_global;
+    if (!hdr.halt) h->n_host = st.n_next;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_resume(pf_handle h, int64_t step)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (step < 0 || step > h->steps) return set_error(h, PF_ERR_ARG, "pf_mg_resume: bad step");
+    h->steps = step; h->cur = (int)(step & 1);
+    CUDA_TRY(cudaMemsetAsync((char *)h->sc + offsetof(SelScratch, halt), 0, sizeof(long long), h->stream));
+    return PF_OK;
+}
+
 extern "C" int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */)
 {
     if (!h || !out) return PF_ERR_ARG;
@@ -1100,8 +1155,8 @@ extern "C" int32_t pf_mg_unpack(pf_handle h, const void *recv)
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
     k_unpack<<<grid_for(h->cap, 256), 256, 0, h->stream>>>((const double *)recv, h->ro, h->S[nxt], h->Kc[nxt], h->logw[nxt], ga, gs,
-                                                            h->cap, h->k_max * h->F, h->F);
-    k_steplog_mg<<<1, 32, 0, h->stream>>>(h->st, h->res, h->ro, h->slog);
+                                                            h->cap, h->k_max * h->F, h->F, h->sc);
+    k_steplog_mg<<<1, 32, 0, h->stream>>>(h->st, h->res, h->ro, h->slog, h->sc);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
     h->have_last = true; h->last_stale = true;       // the record is fetched when pf_get_last_step asks for it

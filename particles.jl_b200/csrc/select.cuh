@@ -63,6 +63,7 @@ struct SelScratch {
     int mode;                       // 0 bracket round, 1 keep everything, 2 comb-rescale round (lo = hi = thr)
     long long count_in;             // list items inside [lo, hi)
     long long mult;                 // sample stride while solving the sample, 1 otherwise
+    long long halt;                 // sharded run: 1 + index of the step that needs the host (all later kernels are no-ops)
     // accumulators of the classify pass (SelAcc: the block a sharded run all-gathers)
     unsigned long long A_hi;        // #items >= hi
     unsigned long long n_cand;      // #items in [lo, hi)
@@ -411,6 +412,7 @@ __device__ inline bool comb_rescale(SelScratch *sc, const SelResult *res, long l
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
 {
+    if (a.nranks > 1 && a.sc->halt) return;          // sharded look-ahead: an earlier step is waiting for the host
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_u64 = reinterpret_cast<u64 *>(smem_raw);               // SEL_FINAL_CAP u64 for the final sort

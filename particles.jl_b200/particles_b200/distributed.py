@@ -282,9 +282,10 @@ class ShardedFearnheadParticles:
             cnt[l1] = cnt.get(l1, 0) + 1
         return {k: (dev[k] / cnt[k], host[k] / cnt[k]) for k in dev}
 
-    def fit_(self, y, u):
-        """fit!(ps, y) (src/fearnhead.jl:130-184) on the sharded population; u = the rand()
-        of src/fearnhead.jl:99."""
+    def _enqueue(self, y, u):
+        """Queue every kernel and collective of one observation; no host synchronisation.  If
+        the step turns out to need the host (search unfinished / particles change owner), the
+        device marks it (k_close) and everything queued behind it is a no-op."""
         comm, sh, L = self.comm, self.shards, self.L
         self._mark("begin")
         y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
@@ -308,13 +309,41 @@ class ShardedFearnheadParticles:
             s.select(PF_MG_SOLVE, 0, a, g, Bc)
         self._mark("solve")
         self.bytes_moved += 8 * (Bs + Bc + 2 * sh[0].acc.numel()) * comm.size
-        plans = self._tail()
-        self._mark("tail+sync")
-        phase = plans[0][4]
+        for s in sh:
+            _lib.check(L.pf_mg_tiles(s.h), s.h)
+        gt = comm.all_gather([s.total for s in sh])
+        for s, g in zip(sh, gt):
+            _lib.check(L.pf_mg_finish(s.h, C.c_void_p(g.data_ptr())), s.h)
+            _lib.check(L.pf_mg_close(s.h), s.h)
+            _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)     # no-op if the step halted
+        self._mark("tail")
+
+    def _drain(self):
+        """The host synchronisation: (0, ...) if every queued step completed, else (1 + index of
+        the step that needs the host, its search phase)."""
+        outs = []
+        for s in self.shards:
+            o = (C.c_int64 * 4)()
+            _lib.check(self.L.pf_mg_drain(s.h, o), s.h)
+            outs.append(list(o))
+        self.host_syncs += 1
+        self._mark("drain")
+        if not outs[0][0]:
+            self.n_global = outs[0][3]
+        return outs[0][0], outs[0][1]
+
+    def _complete(self, y, u, step, phase):
+        """Finish a halted step through the synchronous stages."""
+        comm, sh, L = self.comm, self.shards, self.L
+        y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
+        for s in sh:
+            _lib.check(L.pf_mg_resume(s.h, int(step)), s.h)
         if phase != 4:
             # rare: bracket verification failed, a finer scale is needed, or a list outgrew its
             # fixed gather size -- finish the search with exact-size gathers, then redo the tail
             self.slow_steps += 1
+            for s in sh:
+                _lib.check(L.pf_mg_set_obs(s.h, y.ctypes.data_as(_dp), float(u)), s.h)
             rounds = sh[0].state()[3]
             while phase != 4:
                 if phase in (3, 7):      # 3: new bracket / scale; 7: a fixed-size gather truncated the list
@@ -329,23 +358,43 @@ class ShardedFearnheadParticles:
                 if rounds > 40:
                     raise RuntimeError("threshold search did not converge")
             plans = self._tail()
+        else:
+            plans = [s.plan(comm.size) for s in sh]
+            self.host_syncs += 1
         self.n_global = plans[0][3]
         moving = int(sum(int(p[0].sum()) for p in plans))
-        if plans[0][5]:                    # children stay on their parent's rank while the shares fit: usually nothing moves
+        if plans[0][5]:                    # some share outgrew its shard: equal re-partition
             comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
             self.exchanges += 1
         self.bytes_moved += moving * sh[0].rows * 8
-        self._mark("exchange")
-        for s in sh:             # (also closes the step when nothing was received)
+        for s in sh:
             _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)
-        self._mark("unpack")
-        self.steps += 1
-        return self
+        self._mark("complete")
 
-    def filter_(self, ys, uniforms):
+    def fit_(self, y, u):
+        """fit!(ps, y) (src/fearnhead.jl:130-184) on the sharded population; u = the rand()
+        of src/fearnhead.jl:99."""
+        return self.filter_([y], [u])
+
+    def filter_(self, ys, uniforms, lookahead=8):
+        """filter!(ps, ys, false) (src/filters.jl:6-13): observations are queued `lookahead` at a
+        time and the host synchronises once per batch; a step that needs the host (re-bracketing,
+        re-partitioning) is completed synchronously and the rest of its batch is queued again."""
         ys = np.asarray(ys, dtype=np.float64).reshape(len(uniforms), -1)
-        for y, u in zip(ys, uniforms):
-            self.fit_(y, u)
+        T, t = len(uniforms), 0
+        base = self.steps
+        while t < T:
+            tend = min(T, t + max(int(lookahead), 1))
+            for k in range(t, tend):
+                self._enqueue(ys[k], uniforms[k])
+            halt, phase = self._drain()
+            if halt:
+                th = halt - 1 - base                     # index of the halted observation
+                self._complete(ys[th], uniforms[th], halt - 1, phase)
+                t = th + 1
+            else:
+                t = tend
+            self.steps = base + t
         return self
 
     # ---- read-out (concatenated over ranks in global order)

@@ -81,3 +81,24 @@ def test_slow_path_truncated_gather_and_rebracketing(kw):
     assert sh.slow_steps > 0
     assert np.array_equal(sh.logweights(), ref.logweights())
     assert np.array_equal(sh.ncomponents(), ref.ncomponents())
+
+
+@pytest.mark.parametrize("lookahead", [1, 4, 16])
+def test_lookahead_batches_equal_stepwise(lookahead):
+    """Queuing several observations ahead of the host (device-side halt mark for the steps that
+    need it) gives the same population as stepping one at a time."""
+    rng = np.random.default_rng(21)
+    G, N, T = 4, 8000, 48
+    ys = _mix2d(rng, T)
+    us = rng.random(T)
+    prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
+    crp = pb.ChineseRestaurantProcess(1.0)
+    ref = pb.FearnheadParticles(N, prior, crp, history=T)
+    ref.filter_(ys, uniforms=us)
+    sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T)
+    sh.filter_(ys, us, lookahead=lookahead)
+    assert len(sh) == len(ref)
+    assert np.array_equal(sh.logweights(), ref.logweights())
+    assert np.array_equal(sh.ncomponents(), ref.ncomponents())
+    assert np.array_equal(sh.last_ancestors(), ref.last_ancestors())
+    assert sh.host_syncs < 2 * T if lookahead > 1 else True
