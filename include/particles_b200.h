@@ -189,6 +189,7 @@ typedef struct {
     int64_t local_capacity;    /* particles this shard can hold */
     int64_t sample_entries;    /* fixed gather size (doubles) of the sample list */
     int64_t cand_entries;      /* fixed gather size (doubles) of the candidate list */
+    int64_t window;            /* neighbour exchange: particles per message slot (send/recv buffers hold 2 slots) */
 } pf_mg_ptrs;
 int32_t pf_set_stream(pf_handle h, void *cuda_stream);    /* run on the caller's stream (e.g. torch's current stream) */
 int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *out);

@@ -184,7 +184,8 @@ struct RankOff {
 // one thread: turn the gathered per-rank totals (mass of the low partition, kept count) into
 // this rank's offsets and the exchange plan.  rows = doubles per migrating particle.
 __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, int nranks, const SelResult *__restrict__ res,
-                               StepState *st, RankOff *ro, int rows, const SelScratch *guard, long long stay_cap)
+                               StepState *st, RankOff *ro, int rows, const SelScratch *guard, long long stay_cap,
+                               long long window)
 {
     if (threadIdx.x || blockIdx.x) return;
     if (guard && (guard->phase != 4 || guard->halt)) { ro->n_local = 0; return; }          // the threshold search has not finished (speculative tail)
@@ -205,30 +206,46 @@ __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, i
     const long long n_global = gpre;
     long long q = (n_global + nranks - 1) / nranks;
     if (q < 1) q = 1;
-    // Ownership after the step.  Children stay on their parent's rank while every rank's
-    // share fits `stay_cap` (the shard capacity, N/G plus 1/8 slack) and no share has fallen
-    // below q/2 (no exchange at all); otherwise the population is re-partitioned into equal
-    // blocks of q.  Either way rank r owns a contiguous range of the global order.
-    long long mx = 0, mn = n_global;
-    for (int r = 0; r < nranks; r++) { mx = n_loc[r] > mx ? n_loc[r] : mx; mn = n_loc[r] < mn ? n_loc[r] : mn; }
-    const bool stay = mx <= stay_cap && (mn > 0 || n_global < nranks) && mn >= (q >> 1);
-    for (int r = 0; r <= nranks; r++) {
-        long long b = stay ? (r < nranks ? g_first[r] : n_global) : (long long)r * q;
-        ro->bnd[r] = b > n_global ? n_global : b;
+    // Ownership after the step.  Children are born on their parent's rank; the boundary between
+    // ranks r-1 and r then moves toward the balanced position r q by at most `window` particles
+    // (and never past a neighbour's range), so only adjacent ranks exchange particles and every
+    // message has a fixed capacity: no host-known sizes, no synchronisation (exchange = 2).  If a
+    // share would still exceed the shard capacity the population is re-partitioned into equal
+    // blocks of q through the host (exchange = 1).
+    ro->bnd[0] = 0; ro->bnd[nranks] = n_global;
+    bool fits = true;
+    for (int r = 1; r < nranks; r++) {
+        long long cur = g_first[r], tgt = (long long)r * q;
+        if (tgt > n_global) tgt = n_global;
+        long long b = tgt < cur - window ? cur - window : (tgt > cur + window ? cur + window : tgt);
+        long long lo = g_first[r - 1], hi = g_first[r] + n_loc[r];          // stay inside the two neighbours' ranges
+        if (b < lo) b = lo;
+        if (b > hi) b = hi;
+        if (b < ro->bnd[r - 1]) b = ro->bnd[r - 1];
+        ro->bnd[r] = b;
     }
+    for (int r = 0; r < nranks; r++) fits = fits && (ro->bnd[r + 1] - ro->bnd[r] <= stay_cap);
+    if (!fits)
+        for (int r = 0; r <= nranks; r++) { long long b = (long long)r * q; ro->bnd[r] = b > n_global ? n_global : b; }
     ro->g_first = g_first[rank]; ro->n_local = n_loc[rank]; ro->n_global = n_global; ro->q = q;
     ro->n_mine = ro->bnd[rank + 1] - ro->bnd[rank];
-    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0; ro->exchange = stay ? 0 : 1;
+    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0; ro->exchange = fits ? 2 : 1;
     long long soff = 0, roff = 0;
     for (int d = 0; d < nranks; d++) {
         long long lo = g_first[rank] > ro->bnd[d] ? g_first[rank] : ro->bnd[d];
         long long hi = g_first[rank] + n_loc[rank] < ro->bnd[d + 1] ? g_first[rank] + n_loc[rank] : ro->bnd[d + 1];
         long long len = (d == rank || hi <= lo) ? 0 : hi - lo;
-        ro->send_start[d] = lo; ro->send_len[d] = len; ro->send_off[d] = soff; soff += len * rows;
         long long lo2 = g_first[d] > ro->bnd[rank] ? g_first[d] : ro->bnd[rank];
         long long hi2 = g_first[d] + n_loc[d] < ro->bnd[rank + 1] ? g_first[d] + n_loc[d] : ro->bnd[rank + 1];
         long long len2 = (d == rank || hi2 <= lo2) ? 0 : hi2 - lo2;
-        ro->recv_idx0[d] = lo2 - ro->bnd[rank]; ro->recv_len[d] = len2; ro->recv_off[d] = roff; roff += len2 * rows;
+        ro->send_start[d] = lo; ro->send_len[d] = len; ro->recv_idx0[d] = lo2 - ro->bnd[rank]; ro->recv_len[d] = len2;
+        if (fits) {      // neighbour mode: fixed slots -- [0, window) left neighbour, [window, 2 window) right neighbour
+            ro->send_off[d] = (d < rank ? 0 : window) * rows;
+            ro->recv_off[d] = (d < rank ? 0 : window) * rows;
+        } else {
+            ro->send_off[d] = soff; soff += len * rows;
+            ro->recv_off[d] = roff; roff += len2 * rows;
+        }
     }
     st->n_kept = my_kept; st->n_picked = my_picked; st->n_next = ro->n_mine; st->n_global = n_global;
 }

@@ -66,7 +66,7 @@ struct pf_filter_s {
     int mig_rows = 0;
     long long surv_cap = 0;
     int mg_rounds = 0;
-    long long mg_stride = 1, mg_sample_entries = 0, mg_cand_entries = 0;
+    long long mg_stride = 1, mg_sample_entries = 0, mg_cand_entries = 0, mg_window = 0;
     bool own_stream = true;
     double *y1_dev = nullptr;             // y (d) + u (1) of the current sharded step
     double *y1_pin = nullptr;             // pinned staging ring for (y, u)
@@ -259,7 +259,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     h->nranks = cfg->nranks > 1 ? cfg->nranks : 1;
     h->rank = h->nranks > 1 ? cfg->rank : 0;
     h->cap = (cfg->n_particles + h->nranks - 1) / h->nranks;
-    if (h->nranks > 1) h->cap += h->cap / 8 + 64;          // slack: children stay on their parent's rank while shares fit
+    if (h->nranks > 1) h->cap += h->cap / 2 + 64;          // slack: children stay on their parent's rank while shares fit
     h->F = 2 + d + d * (d + 1) / 2;
     h->mu0.assign(cfg->mu0, cfg->mu0 + d);
     h->lam0.assign(d * d, 0.0);
@@ -296,6 +296,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->surv_slot, h->surv_cap));
     if (h->nranks > 1) {
         h->mig_rows = h->k_max * h->F + 4;
+        h->mg_window = std::max<long long>(64, ((cfg->n_particles + h->nranks - 1) / h->nranks) / 40);
         h->buf_cap = (2 * cap + 1024) * (long long)h->mig_rows;
         CT(dmalloc(&h->gscal, 4)); CT(dmalloc(&h->local_tot, 1)); CT(dmalloc(&h->ro, 1));
         CT(dmalloc(&h->sendbuf, (size_t)h->buf_cap)); CT(dmalloc(&h->recvbuf, (size_t)h->buf_cap));
@@ -908,7 +909,7 @@ __global__ void k_publish_scalars(const StepState *st, SelScratch *sc)
 __global__ void k_close(SelScratch *sc, const RankOff *ro, long long step, long long surv_cap)
 {
     if (threadIdx.x || blockIdx.x || sc->halt) return;
-    if (sc->phase != 4 || ro->exchange || ro->n_local > surv_cap) sc->halt = step + 1;
+    if (sc->phase != 4 || ro->exchange == 1 || ro->n_local > surv_cap) sc->halt = step + 1;
 }
 
 __global__ void k_steplog_mg(StepState *st, const SelResult *res, const RankOff *ro, StepLog *lg, const SelScratch *guard)
@@ -947,7 +948,7 @@ extern "C" int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *o)
     o->local_total = h->local_tot; o->total_bytes = sizeof(TileSum);
     o->send_buffer = h->sendbuf; o->recv_buffer = h->recvbuf; o->buffer_capacity = h->buf_cap;
     o->rows_per_particle = h->mig_rows; o->local_capacity = h->cap;
-    o->sample_entries = h->mg_sample_entries; o->cand_entries = h->mg_cand_entries;
+    o->sample_entries = h->mg_sample_entries; o->cand_entries = h->mg_cand_entries; o->window = h->mg_window;
     return PF_OK;
 }
 
@@ -1037,7 +1038,7 @@ static int32_t mg_finish(pf_handle h, const TileSum *gathered)
     const int cur = h->cur, nxt = cur ^ 1;
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc, h->cap);
+    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc, h->cap, h->mg_window);
     k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
                                                                                   h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
     k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,

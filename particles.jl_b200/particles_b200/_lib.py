@@ -46,7 +46,7 @@ class pf_mg_ptrs(C.Structure):
                 ("list_capacity", C.c_int64), ("local_total", C.c_void_p), ("total_bytes", C.c_int64),
                 ("send_buffer", C.c_void_p), ("recv_buffer", C.c_void_p), ("buffer_capacity", C.c_int64),
                 ("rows_per_particle", C.c_int64), ("local_capacity", C.c_int64), ("sample_entries", C.c_int64),
-                ("cand_entries", C.c_int64)]
+                ("cand_entries", C.c_int64), ("window", C.c_int64)]
 
 
 PF_MG_SAMPLE, PF_MG_BRACKET, PF_MG_CLASSIFY, PF_MG_SOLVE = 1, 2, 4, 8

@@ -26,28 +26,44 @@ _dp = C.POINTER(C.c_double)
 
 
 # ------------------------------------------------------------------ host-side plan (pure)
-def partition_plan(n_local_all, rank, stay_cap=0):
-    """Ownership of a rank-major population with n_local_all[r] particles produced on rank r.
-    Children stay on their parent's rank while every share fits `stay_cap` and none is below
-    q/2; otherwise equal blocks of q = ceil(n / G).  Returns
-    (send_counts by destination, recv_counts by source, q, n_mine) for `rank`.  Mirrors
-    k_rank_offsets (csrc/fearnhead.cuh)."""
+def ownership(n_local_all, stay_cap=0, window=0):
+    """New ownership boundaries of a rank-major population with n_local_all[r] children born on
+    rank r.  The boundary between ranks r-1 and r moves toward the balanced position r q by at
+    most `window` particles and never past a neighbour's range (only adjacent ranks exchange,
+    fixed-capacity messages: mode 2); if a share would still exceed `stay_cap`, equal blocks of
+    q = ceil(n / G) (mode 1, sizes known to the host only).  Mirrors k_rank_offsets."""
     n_local_all = [int(x) for x in n_local_all]
     G = len(n_local_all)
-    first = np.concatenate([[0], np.cumsum(n_local_all)]).astype(np.int64)
-    n = int(first[-1])
+    first = [0]
+    for x in n_local_all:
+        first.append(first[-1] + x)
+    n = first[-1]
     q = max((n + G - 1) // G, 1)
-    mx, mn = max(n_local_all), min(n_local_all)
-    stay = mx <= stay_cap and (mn > 0 or n < G) and mn >= (q >> 1)
-    bnd = [min(int(first[r]) if stay else r * q, n) for r in range(G)] + [n if stay else min(G * q, n)]
+    bnd = [0] * (G + 1)
+    bnd[G] = n
+    for r in range(1, G):
+        cur, tgt = first[r], min(r * q, n)
+        b = min(max(tgt, cur - window), cur + window)
+        b = min(max(b, first[r - 1]), first[r] + n_local_all[r])
+        bnd[r] = max(b, bnd[r - 1])
+    fits = all(bnd[r + 1] - bnd[r] <= stay_cap for r in range(G))
+    if not fits:
+        bnd = [min(r * q, n) for r in range(G + 1)]
+    return bnd, first, q, (2 if fits else 1)
+
+
+def partition_plan(n_local_all, rank, stay_cap=0, window=0):
+    """(send_counts by destination, recv_counts by source, q, n_mine, mode) for `rank`."""
+    bnd, first, q, mode = ownership(n_local_all, stay_cap, window)
+    G = len(n_local_all)
     send = np.zeros(G, dtype=np.int64)
     recv = np.zeros(G, dtype=np.int64)
     for d in range(G):
-        lo, hi = max(first[rank], bnd[d]), min(first[rank] + n_local_all[rank], bnd[d + 1])
+        lo, hi = max(first[rank], bnd[d]), min(first[rank + 1], bnd[d + 1])
         send[d] = 0 if d == rank else max(hi - lo, 0)
-        lo, hi = max(first[d], bnd[rank]), min(first[d] + n_local_all[d], bnd[rank + 1])
+        lo, hi = max(first[d], bnd[rank]), min(first[d + 1], bnd[rank + 1])
         recv[d] = 0 if d == rank else max(hi - lo, 0)
-    return send, recv, q, bnd[rank + 1] - bnd[rank]
+    return send, recv, q, bnd[rank + 1] - bnd[rank], mode
 
 
 # ------------------------------------------------------------------ communicators
@@ -81,6 +97,17 @@ class TorchComm:
         ins = [int(c) * rows for c in send_counts[0]]
         outs = [int(c) * rows for c in recv_counts[0]]
         self.dist.all_to_all_single(recvs[0][:sum(outs)], sends[0][:sum(ins)], outs, ins)
+
+    def neighbour_exchange(self, sends, recvs, slot):
+        """Fixed-size exchange with the two adjacent ranks: send[0:slot] -> left, send[slot:2 slot]
+        -> right; recv[0:slot] <- left, recv[slot:2 slot] <- right."""
+        dist, r, ops = self.dist, self.local_ranks[0], []
+        if r > 0:
+            ops += [dist.P2POp(dist.isend, sends[0][:slot], r - 1), dist.P2POp(dist.irecv, recvs[0][:slot], r - 1)]
+        if r < self.size - 1:
+            ops += [dist.P2POp(dist.isend, sends[0][slot:2 * slot], r + 1), dist.P2POp(dist.irecv, recvs[0][slot:2 * slot], r + 1)]
+        for req in dist.batch_isend_irecv(ops) if ops else []:
+            req.wait()
 
     def gather_host(self, arrays):
         out = [None] * self.size
@@ -122,6 +149,13 @@ class LocalComm:
                     recvs[d][o:o + n].copy_(sends[s][int(soff[s][d]):int(soff[s][d]) + n])
                 o += n
 
+    def neighbour_exchange(self, sends, recvs, slot):
+        for r in range(self.size):
+            if r > 0:
+                recvs[r][:slot].copy_(sends[r - 1][slot:2 * slot])
+            if r < self.size - 1:
+                recvs[r][slot:2 * slot].copy_(sends[r + 1][:slot])
+
     def gather_host(self, arrays):
         return list(arrays)
 
@@ -156,6 +190,7 @@ class _Shard:
         self.send = _view(p.send_buffer, p.buffer_capacity, "<f8", self.device)
         self.recv = _view(p.recv_buffer, p.buffer_capacity, "<f8", self.device)
         self.sample_entries, self.cand_entries = int(p.sample_entries), int(p.cand_entries)
+        self.window, self.capacity = int(p.window), int(p.local_capacity)
 
     def state(self):
         st = (C.c_int64 * 4)()
@@ -315,8 +350,13 @@ class ShardedFearnheadParticles:
         for s, g in zip(sh, gt):
             _lib.check(L.pf_mg_finish(s.h, C.c_void_p(g.data_ptr())), s.h)
             _lib.check(L.pf_mg_close(s.h), s.h)
-            _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)     # no-op if the step halted
         self._mark("tail")
+        slot = sh[0].window * sh[0].rows
+        comm.neighbour_exchange([s.send for s in sh], [s.recv for s in sh], slot)       # boundaries shift by <= window
+        self.bytes_moved += 2 * slot * 8
+        for s in sh:
+            _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)     # no-op if the step halted
+        self._mark("exchange+unpack")
 
     def _drain(self):
         """The host synchronisation: (0, ...) if every queued step completed, else (1 + index of
@@ -363,10 +403,14 @@ class ShardedFearnheadParticles:
             self.host_syncs += 1
         self.n_global = plans[0][3]
         moving = int(sum(int(p[0].sum()) for p in plans))
-        if plans[0][5]:                    # some share outgrew its shard: equal re-partition
+        if plans[0][5] == 1:               # some share outgrew its shard: equal re-partition, sizes from the plan
             comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
             self.exchanges += 1
-        self.bytes_moved += moving * sh[0].rows * 8
+            self.bytes_moved += moving * sh[0].rows * 8
+        else:
+            slot = sh[0].window * sh[0].rows
+            comm.neighbour_exchange([s.send for s in sh], [s.recv for s in sh], slot)
+            self.bytes_moved += 2 * slot * 8
         for s in sh:
             _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)
         self._mark("complete")

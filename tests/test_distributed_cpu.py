@@ -9,42 +9,52 @@ import pytest
 from particles_b200.distributed import LocalComm, partition_plan
 
 
-def _brute(n_local_all, rank):
+def _brute(n_local_all, rank, bnd):
     G = len(n_local_all)
     n = sum(n_local_all)
-    q = max(-(-n // G), 1)
     owner_old = np.repeat(np.arange(G), n_local_all)
-    owner_new = np.arange(n) // q
+    owner_new = np.searchsorted(np.asarray(bnd[1:]), np.arange(n), side="right")
     send = np.array([np.sum((owner_old == rank) & (owner_new == d)) if d != rank else 0 for d in range(G)])
     recv = np.array([np.sum((owner_old == s) & (owner_new == rank)) if s != rank else 0 for s in range(G)])
-    return send, recv, q, int(np.sum(owner_new == rank))
+    return send, recv, int(np.sum(owner_new == rank))
 
 
-def test_partition_plan_stay_rule():
-    # balanced shares that fit the capacity: nothing moves, ownership follows the parents
-    send, recv, q, mine = partition_plan([100, 103, 98, 99], 1, stay_cap=120)
-    assert send.sum() == 0 and recv.sum() == 0 and mine == 103
-    # a share above the capacity, or too unbalanced: equal blocks
-    for case, cap in (([100, 130, 98, 99], 120), ([10, 200, 200, 200], 1000)):     # above capacity / below q/2
-        tot = [partition_plan(case, r, stay_cap=cap) for r in range(4)]
-        assert sum(int(t[0].sum()) for t in tot) > 0
-        assert [t[3] for t in tot] == [t[2] for t in tot][:3] + [sum(case) - 3 * tot[0][2]]
+def test_ownership_rule():
+    from particles_b200.distributed import ownership
+    # balanced shares: boundaries move to the balanced positions, only neighbours exchange
+    bnd, first, q, mode = ownership([100, 103, 98, 99], stay_cap=150, window=10)
+    assert mode == 2 and bnd == [0, 100, 200, 300, 400]
+    # the window limits the shift per step
+    bnd, first, q, mode = ownership([100, 140, 80, 80], stay_cap=150, window=10)
+    assert mode == 2 and bnd == [0, 100, 230, 310, 400]
+    # a share above the capacity: equal blocks through the host
+    bnd, first, q, mode = ownership([100, 180, 60, 60], stay_cap=150, window=10)
+    assert mode == 1 and bnd == [0, 100, 200, 300, 400]
+    # everything on rank 0 (start of a run): the first boundary gives away one window per step
+    bnd, first, q, mode = ownership([52, 0, 0, 0], stay_cap=60, window=4)
+    assert mode == 2 and bnd[0] == 0 and bnd[1] == 48 and bnd[-1] == 52
 
 
 def test_partition_plan_matches_brute_force():
+    from particles_b200.distributed import ownership
     rng = np.random.default_rng(0)
     cases = [[1, 0], [0, 0, 0, 0], [52, 0, 0, 0], [100, 103, 98, 99], [5, 0, 17, 1, 0, 0, 3, 9]]
     cases += [list(rng.integers(0, 50, int(g))) for g in rng.integers(1, 9, 40)]
     for case in cases:
         G = len(case)
-        tot_send = np.zeros((G, G), dtype=np.int64)
-        for r in range(G):
-            send, recv, q, mine = partition_plan(case, r)
-            bs, br, bq, bm = _brute(case, r)
-            assert np.array_equal(send, bs) and np.array_equal(recv, br) and q == bq and mine == bm
-            tot_send[r] = send
-        for r in range(G):
-            assert np.array_equal(tot_send[:, r], partition_plan(case, r)[1])       # what r receives is what the others send
+        for cap, win in ((10 ** 9, 5), (30, 3), (0, 0)):
+            bnd, first, q, mode = ownership(case, cap, win)
+            assert bnd[0] == 0 and bnd[-1] == sum(case) and all(bnd[r] <= bnd[r + 1] for r in range(G))
+            tot_send = np.zeros((G, G), dtype=np.int64)
+            for r in range(G):
+                send, recv, q2, mine, mode2 = partition_plan(case, r, cap, win)
+                bs, br, bm = _brute(case, r, bnd)
+                assert np.array_equal(send, bs) and np.array_equal(recv, br) and mine == bm and mode2 == mode
+                if mode == 2:        # neighbour mode: adjacent ranks only, at most `window` particles per message
+                    assert all(send[d] == 0 for d in range(G) if abs(d - r) > 1) and send.max(initial=0) <= win
+                tot_send[r] = send
+            for r in range(G):
+                assert np.array_equal(tot_send[:, r], partition_plan(case, r, cap, win)[1])
 
 
 def test_local_comm_all_to_all_matches_plan():
@@ -53,10 +63,10 @@ def test_local_comm_all_to_all_matches_plan():
     G = len(case)
     comm = LocalComm(G)
     first = np.concatenate([[0], np.cumsum(case)])
-    plans = [partition_plan(case, r) for r in range(G)]
+    plans = [partition_plan(case, r) for r in range(G)]        # capacity 0: equal blocks
     sends, recvs = [], []
     for r in range(G):
-        send, recv, q, mine = plans[r]
+        send, recv, q, mine, _ = plans[r]
         buf = []
         for d in range(G):                   # packed [row][k] per destination segment
             lo = max(first[r], d * q)
@@ -66,7 +76,7 @@ def test_local_comm_all_to_all_matches_plan():
         recvs.append(torch.full((rows * 32,), -1.0, dtype=torch.float64))
     comm.all_to_all_v(sends, [p[0] for p in plans], recvs, [p[1] for p in plans], rows)
     for r in range(G):
-        send, recv, q, mine = plans[r]
+        send, recv, q, mine, _ = plans[r]
         o = 0
         for s in range(G):
             n = int(recv[s])
@@ -100,7 +110,7 @@ def _worker(rank, world, port, ok):
         assert comm.max_int([3 + rank], "cpu") == 4
         # exchange plan: rank 0 produced 9 particles, rank 1 produced 1 -> q = 5
         case, rows = [9, 1], 2
-        send, recv, q, mine = partition_plan(case, rank)
+        send, recv, q, mine, _ = partition_plan(case, rank)
         first = [0, 9]
         buf = []
         for d in range(world):
