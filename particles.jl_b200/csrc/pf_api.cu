@@ -296,7 +296,9 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->surv_slot, h->surv_cap));
     if (h->nranks > 1) {
         h->mig_rows = h->k_max * h->F + 4;
-        h->mg_window = std::max<long long>(64, ((cfg->n_particles + h->nranks - 1) / h->nranks) / 40);
+        // neighbour window: 0 = children simply stay on their parent's rank until a share outgrows the shard
+        // (measured on 8xB200: the fixed-capacity neighbour messages cost more than the imbalance they remove)
+        h->mg_window = getenv("PF_MG_WINDOW") ? atoll(getenv("PF_MG_WINDOW")) : 0;
         h->buf_cap = (2 * cap + 1024) * (long long)h->mig_rows;
         CT(dmalloc(&h->gscal, 4)); CT(dmalloc(&h->local_tot, 1)); CT(dmalloc(&h->ro, 1));
         CT(dmalloc(&h->sendbuf, (size_t)h->buf_cap)); CT(dmalloc(&h->recvbuf, (size_t)h->buf_cap));

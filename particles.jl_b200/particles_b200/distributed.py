@@ -352,8 +352,9 @@ class ShardedFearnheadParticles:
             _lib.check(L.pf_mg_close(s.h), s.h)
         self._mark("tail")
         slot = sh[0].window * sh[0].rows
-        comm.neighbour_exchange([s.send for s in sh], [s.recv for s in sh], slot)       # boundaries shift by <= window
-        self.bytes_moved += 2 * slot * 8
+        if slot:                                                                         # boundaries shift by <= window
+            comm.neighbour_exchange([s.send for s in sh], [s.recv for s in sh], slot)
+            self.bytes_moved += 2 * slot * 8
         for s in sh:
             _lib.check(L.pf_mg_unpack(s.h, C.c_void_p(s.recv.data_ptr())), s.h)     # no-op if the step halted
         self._mark("exchange+unpack")
@@ -407,7 +408,7 @@ class ShardedFearnheadParticles:
             comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
             self.exchanges += 1
             self.bytes_moved += moving * sh[0].rows * 8
-        else:
+        elif sh[0].window:
             slot = sh[0].window * sh[0].rows
             comm.neighbour_exchange([s.send for s in sh], [s.recv for s in sh], slot)
             self.bytes_moved += 2 * slot * 8

@@ -83,10 +83,11 @@ def test_slow_path_truncated_gather_and_rebracketing(kw):
     assert np.array_equal(sh.ncomponents(), ref.ncomponents())
 
 
-@pytest.mark.parametrize("lookahead", [1, 4, 16])
-def test_lookahead_batches_equal_stepwise(lookahead):
+@pytest.mark.parametrize("lookahead,window", [(1, 0), (4, 0), (16, 0), (4, 50), (8, 400)])
+def test_lookahead_batches_equal_stepwise(lookahead, window, monkeypatch):
     """Queuing several observations ahead of the host (device-side halt mark for the steps that
     need it) gives the same population as stepping one at a time."""
+    monkeypatch.setenv("PF_MG_WINDOW", str(window))          # > 0: fixed-capacity neighbour exchange every step
     rng = np.random.default_rng(21)
     G, N, T = 4, 8000, 48
     ys = _mix2d(rng, T)
