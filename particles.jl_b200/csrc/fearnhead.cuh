@@ -16,6 +16,9 @@ struct StepState {
     unsigned int ticket2;
     long long n_picked;     // resampled survivors
     long long n_kept;       // kept survivors
+    long long M_pred;       // putatives of this step, known before the expansion (counted by the previous instantiate)
+    long long M_next;       // putatives of the next step (accumulated by k_instantiate)
+    u64 vmax_sample;        // max putative weight of the sample expansion
     long long goff;         // sharded run: global index of this shard's first particle
     long long n_global;     // sharded run: population over all shards after the step
 };
@@ -39,6 +42,8 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
     if (guard && guard->halt) return;
     using L = Layout<D>;
     if (!first) st->n_live = st->n_next;
+    st->M_pred = first ? st->n_live : st->M_next;      // (first step: empty particles, one putative each)
+    st->M_next = 0; st->vmax_sample = 0;
     st->n_next = 0;
     st->M = 0; st->vmax_bits = 0; st->ticket = 0; st->ticket2 = 0; st->n_picked = 0; st->n_kept = 0;
     StepConst c;
@@ -66,27 +71,88 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
     *sc_out = c;
 }
 
+#define SCAN_THREADS 256
+#define PF_MAX_RANKS 16
+struct TileSum {           // survivor-scan record of one tile of SCAN_THREADS particles
+    u128 X;
+    unsigned int kept;
+    unsigned int pad[3];
+};
+
 // ------------------------------------------------------------------ k_expand
 // putatives(p, y) for every particle (src/fearnhead.jl:132, src/particle.jl:100-116):
 // thread i evaluates the K_i + 1 candidate assignments of particle i and writes their
 // LINEAR weights exp(logweight) slot-major into V.  One thread per particle keeps all 32
 // lanes on the FP64 pipe and makes every (slot, field) load a 256-byte coalesced read.
-template <int D>
+//
+// MODE 0  plain expansion.
+// MODE 1  sample expansion: only every `stride`-th particle, nothing is stored except the
+//         putative weights themselves, appended densely to the sample list (the threshold
+//         search brackets the threshold on them BEFORE the full expansion runs).
+// MODE 2  fused expansion: as MODE 0, and every putative is classified on the fly against the
+//         bracket [lo, hi) (exact fixed-point mass below lo, count above hi, candidates in
+//         between appended densely), so the separate classify pass over V disappears; the
+//         block's sums are also the survivor scan's tile record (one block = one tile).
+#define EXP_CAND_CAP 1024          // MODE 2: candidates one block of 256 particles may stage
+#define EXP_SAMPLE_THREADS 32      // MODE 1 runs one warp per block: at most 32 * PF_MAX_SLOTS sample values per block
+struct TileFuse {
+    unsigned int cand_off, cand_cnt;
+};
+
+template <int D, int MODE>
 __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, const double *__restrict__ logw,
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
                                                 double *__restrict__ V, unsigned char *__restrict__ cnt,
-                                                const SelScratch *guard)
+                                                SelScratch *sc, long long stride, double *__restrict__ list,
+                                                TileSum *__restrict__ tiles, TileFuse *__restrict__ tfuse)
 {
     using L = Layout<D>;
-    if (guard && guard->halt) return;
+    if (MODE == 0 && sc && sc->halt) return;
     __shared__ u64 s_max[8];
     __shared__ long long s_M[8], s_ovf[8];
+    constexpr int CAND_CAP = (MODE == 1) ? EXP_SAMPLE_THREADS * PF_MAX_SLOTS : (MODE == 2 ? EXP_CAND_CAP : 1);
+    __shared__ u64 s_cand[CAND_CAP];
+    __shared__ unsigned int s_ncand, s_goff;
+    __shared__ u128 s_tot[8];                    // kept-side total per warp
+    __shared__ u128 s_red[8];
+    __shared__ unsigned int s_redk[8];
     const long long n_live = st->n_live;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (MODE == 1) ? gid * stride : gid;
+    const bool fused = (MODE == 2) && sc->fuse_valid;
+    u64 lo = 0, hi = 0; int scale = 0, tscale = 0;
+    if (fused) { lo = sc->lo; hi = sc->hi; scale = sc->fuse_scale; tscale = sc->fuse_tot_scale; }
+    if (MODE != 0) {
+        if (threadIdx.x == 0) s_ncand = 0;
+        __syncthreads();
+    }
     u64 vmax = 0;
     long long myM = 0, myOvf = 0;
+    u128 B_lo = mk128(0, 0), Tot = mk128(0, 0);
+    unsigned int kept_hi = 0;
+    // what happens to one putative weight
+    auto emit = [&](int j, double v) {
+        const u64 b = (u64)__double_as_longlong(v);
+        vmax = b > vmax ? b : vmax;
+        if (MODE == 1) {
+            if (b != 0) { unsigned int pos = atomicAdd(&s_ncand, 1u); if (pos < CAND_CAP) s_cand[pos] = b; }
+            return;
+        }
+        V[(long long)j * cap + i] = v;
+        if (MODE == 2 && fused) {
+            if (b >= hi) {
+                kept_hi++;
+                Tot = add128(Tot, fx128(b, tscale));              // < 2^99 each by the 28-binade guard of the search
+            } else if (b < lo) {
+                B_lo = add128(B_lo, fx70(b, scale));
+            } else {
+                unsigned int pos = atomicAdd(&s_ncand, 1u);
+                if (pos < CAND_CAP) s_cand[pos] = b;
+            }
+        }
+    };
     if (i < n_live) {
         double y[D], mu0[D];
 #pragma unroll
@@ -109,39 +175,94 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
             double z[D], q;
             const NRow row = tab[(int)fcur[L::F_N]];
             double lw = lw0 + slot_logw<D>(row, fcur[L::F_LOGDET], fcur + L::F_MEAN, fcur + L::F_DINV, fcur + L::F_OFF, y, mu0, z, &q);
-            double v = exp(lw);
-            V[(long long)j * cap + i] = v;
-            u64 b = (u64)__double_as_longlong(v);
-            vmax = b > vmax ? b : vmax;
+            emit(j, exp(lw));
 #pragma unroll
             for (int f = 0; f < L::F; f++) fcur[f] = fnxt[f];
         }
         int c = K;
-        if (K < k_max) {
-            double v = exp(lw0 + scp->lw_new);
-            V[(long long)K * cap + i] = v;
-            u64 b = (u64)__double_as_longlong(v);
-            vmax = b > vmax ? b : vmax;
-            c = K + 1;
-        } else {
-            myOvf = 1;
-        }
-        cnt[i] = (unsigned char)c;
+        if (K < k_max) { emit(K, exp(lw0 + scp->lw_new)); c = K + 1; }
+        else myOvf = 1;
+        if (MODE != 1) cnt[i] = (unsigned char)c;
         myM = c;
     }
+    // ---- block epilogue
     vmax = warp_max64(vmax);
     myM = (long long)warp_sum64((u64)myM);
     myOvf = (long long)warp_sum64((u64)myOvf);
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) { s_max[wid] = vmax; s_M[wid] = myM; s_ovf[wid] = myOvf; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (fused) { B_lo = warp_sum128(B_lo); Tot = warp_sum128(Tot); kept_hi = (unsigned int)warp_sum64(kept_hi); }
+    if (lane == 0) { s_max[wid] = vmax; s_M[wid] = myM; s_ovf[wid] = myOvf; if (fused) { s_red[wid] = B_lo; s_tot[wid] = Tot; s_redk[wid] = kept_hi; } }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int nw = blockDim.x >> 5;
+        const int nw = blockDim.x >> 5;
         for (int w = 1; w < nw; w++) { vmax = s_max[w] > vmax ? s_max[w] : vmax; myM += s_M[w]; myOvf += s_ovf[w]; }
-        if (vmax) atomicMax(&st->vmax_bits, vmax);
-        if (myM) atomicAdd((unsigned long long *)&st->M, (unsigned long long)myM);
-        if (myOvf) atomicAdd((unsigned long long *)&st->overflow, (unsigned long long)myOvf);
+        if (MODE == 1) {
+            if (vmax) atomicMax(&st->vmax_sample, vmax);
+        } else {
+            if (vmax) atomicMax(&st->vmax_bits, vmax);
+            if (myM) atomicAdd((unsigned long long *)&st->M, (unsigned long long)myM);
+            if (myOvf) atomicAdd((unsigned long long *)&st->overflow, (unsigned long long)myOvf);
+        }
+        if (MODE != 0 && (MODE == 1 || fused)) {
+            unsigned int n = s_ncand;
+            if (n > CAND_CAP) { n = CAND_CAP; if (MODE == 2) sc->fuse_overflow = 1; }
+            s_goff = n ? (unsigned int)atomicAdd((unsigned long long *)&sc->list_n, (unsigned long long)n) : 0u;
+            s_ncand = n;
+        }
     }
+    if (MODE != 0 && (MODE == 1 || fused)) {
+        __shared__ u128 s_sc[8];
+        __syncthreads();
+        const unsigned int n = s_ncand, goff = s_goff;
+        u128 Sc = mk128(0, 0);
+        for (unsigned int t = threadIdx.x; t < n; t += blockDim.x) {
+            const u64 b = s_cand[t];
+            list[(long long)goff + t] = __longlong_as_double((long long)b);
+            if (MODE == 2) Sc = add128(Sc, fx70(b, scale));
+        }
+        if (MODE == 2) {
+            Sc = warp_sum128(Sc);
+            if (lane == 0) s_sc[wid] = Sc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                // block totals: the per-warp B_lo / kept_hi were parked in s_red / s_redk above
+                u128 B = s_red[0], C2 = s_sc[0], tot = s_tot[0];
+                unsigned int kh = s_redk[0];
+                for (int w = 1; w < (int)(blockDim.x >> 5); w++) { B = add128(B, s_red[w]); C2 = add128(C2, s_sc[w]); tot = add128(tot, s_tot[w]); kh += s_redk[w]; }
+                tiles[blockIdx.x].X = B; tiles[blockIdx.x].kept = kh;
+                tfuse[blockIdx.x].cand_off = goff; tfuse[blockIdx.x].cand_cnt = n;
+                if (kh) atomicAdd(&sc->A_hi, (unsigned long long)kh);
+                if (n) atomicAdd(&sc->n_cand, (unsigned long long)n);
+                atomic_add_acc(&sc->B_lo, B);
+                atomic_add_acc(&sc->S_cand, C2);
+                atomic_add_acc(&sc->Tot, tot);
+            }
+        }
+    }
+}
+
+// fused path: add each tile's candidates (now that the threshold is known) to its record
+__global__ void __launch_bounds__(256) k_tile_fixup(TileSum *__restrict__ tiles, const TileFuse *__restrict__ tfuse,
+                                                    const double *__restrict__ list, const SelResult *__restrict__ res,
+                                                    const SelScratch *__restrict__ sc, const long long *__restrict__ n_items_ptr)
+{
+    if (!sc->tiles_ok) return;
+    const long long ntiles = (*n_items_ptr + SCAN_THREADS - 1) / SCAN_THREADS;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const bool comb = res->n > 0 && !isz128(res->T);
+    const u64 thr = res->thr_bits;
+    const int scale = res->scale;
+    u128 X = tiles[t].X;
+    unsigned int kept = tiles[t].kept;
+    const unsigned int off = tfuse[t].cand_off, n = tfuse[t].cand_cnt;
+    for (unsigned int k = 0; k < n; k++) {
+        const u64 b = (u64)__double_as_longlong(list[(long long)off + k]);
+        if (b >= thr) kept++;
+        else if (comb) X = add128(X, fx70(b, scale));
+    }
+    if (!comb) X = mk128(0, 0);
+    tiles[t].X = X; tiles[t].kept = kept;
 }
 
 // ------------------------------------------------------------------ survivor scan
@@ -154,13 +275,6 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
 //     (#kept before it) + (#teeth before it)
 // -- one exclusive scan of (X, kept), no second dependent scan.  Three launches, no
 // spinning: per-tile sums, one-block prefix over the tiles, apply.
-#define SCAN_THREADS 256
-#define PF_MAX_RANKS 16
-struct TileSum {
-    u128 X;
-    unsigned int kept;
-    unsigned int pad[3];
-};
 
 // Sharded run (particles block-sharded over ranks, global order = rank-major): where this
 // rank's survivors sit in the global survivor order, and how the new population is
@@ -272,9 +386,10 @@ __device__ __forceinline__ void thread_sums(const double *__restrict__ V, long l
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
                                                             long long cap, const SelResult *__restrict__ res,
                                                             const long long *__restrict__ n_items_ptr, TileSum *__restrict__ tiles,
-                                                            int mode, const SelScratch *guard)
+                                                            int mode, const SelScratch *guard, const SelScratch *fusedsc)
 {
     if (guard && (guard->phase != 4 || guard->halt)) return;
+    if (fusedsc && fusedsc->tiles_ok) return;              // the fused expansion already wrote the tile records
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_x[SCAN_THREADS / 32];
     __shared__ unsigned int s_k[SCAN_THREADS / 32];
@@ -431,7 +546,7 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
                                                      const unsigned char *__restrict__ surv_slot,
                                                      unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
                                                      const RankOff *__restrict__ ro, double *__restrict__ sendbuf, int k_max,
-                                                     const SelScratch *guard)
+                                                     const SelScratch *guard, long long *m_next)
 {
     using L = Layout<D>;
     if (guard && (guard->phase != 4 || guard->halt)) return;
@@ -459,6 +574,11 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
     const double v = V[(long long)j * cap + par];
     const double lw = picked ? res->lw_resamp : (log(v) - res->log_total);
     const int Knew = K + (j == K ? 1 : 0);
+    if (m_next) {        // putatives this child will have at the next observation
+        const unsigned int am = __activemask();
+        const unsigned int c2 = __reduce_add_sync(am, (unsigned int)(Knew + (Knew < k_max ? 1 : 0)));
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(am) - 1)) atomicAdd((unsigned long long *)m_next, (unsigned long long)c2);
+    }
     if (!remote) {
         logw2[idx] = lw; Kc2[idx] = Knew;
         if (gen_anc) { gen_anc[idx] = par + anc_off; gen_asg[idx] = (unsigned char)j; }
@@ -582,7 +702,7 @@ __global__ void k_steplog(const StepState *st, const SelResult *res, StepLog *lg
     r.n_in = st->n_live; r.M = st->M; r.n_kept = st->n_kept; r.n_req = res->keep_all ? 0 : res->n;
     r.n_got = st->n_picked; r.n_out = st->n_next; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
     r.log_total = res->log_total; r.lw_resamp = res->lw_resamp; r.thr = res->thr_value; r.cv = 0.0;
-    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds;
+    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds + 1000 * res->status;
     r.sel_us[0] = (res->t_ns[1] - res->t_ns[0]) * 1e-3; r.sel_us[1] = (res->t_ns[2] - res->t_ns[1]) * 1e-3;
     r.sel_us[2] = (res->t_ns[3] - res->t_ns[2]) * 1e-3; r.sel_us[3] = (res->t_ns[4] - res->t_ns[0]) * 1e-3;
     (void)N;

@@ -33,6 +33,9 @@ struct pf_filter_s {
     unsigned int *surv_parent = nullptr;
     unsigned char *surv_slot = nullptr;
     TileSum *tiles = nullptr;
+    TileFuse *tfuse = nullptr;
+    long long fuse_stride = 1;
+    bool fused = true;                    // single-GPU index-order Fearnhead: classify inside the expansion
     double *cand = nullptr;
     long long cand_cap = 0;
     SelScratch *sc = nullptr;
@@ -213,7 +216,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
-                    h->surv_slot, h->tiles, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
+                    h->surv_slot, h->tiles, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->gscal, h->local_tot, h->ro, h->sendbuf,
                     h->recvbuf, h->y1_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -315,6 +318,9 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         CT(dmalloc(&h->pick_pos, (size_t)cap));
     }
     CT(dmalloc(&h->tiles, ntiles));
+    CT(dmalloc(&h->tfuse, ntiles));
+    h->fuse_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
+    h->fused = getenv("PF_NO_FUSE") == nullptr;
     CT(dmalloc(&h->sc, 1));
     CT(dmalloc(&h->res, 1));
     CT(dmalloc(&h->st, 1));
@@ -332,7 +338,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (h->nranks > 1) {
         const long long pad = (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK;
         const long long spad = (long long)SEL_SAMPLE_WARPS * SEL_CHUNK;
-        h->mg_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
+        h->mg_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));   // = fuse_stride
         h->mg_sample_entries = (2 * SEL_SAMPLE_TARGET + h->nranks - 1) / h->nranks + spad + 1024;
         h->mg_cand_entries = std::max<long long>(1 << 17, (2ll << 20) / h->nranks) + pad;
         h->cand_cap = std::max(h->cand_cap, std::max(h->mg_sample_entries, h->mg_cand_entries) + pad);
@@ -389,12 +395,15 @@ static inline int grid_for(long long n, int bs) { long long g = (n + bs - 1) / b
 
 static int32_t launch_select(pf_handle h, const double *V, const unsigned char *cnt, long long cap, const long long *n_live,
                              const long long *M, const u64 *vmax, long long N, const double *u_dev, double *cand,
-                             long long cand_cap, SelScratch *sc, SelResult *res)
+                             long long cand_cap, SelScratch *sc, SelResult *res, int stage = SEL_ST_ALL, int external_sample = 0,
+                             int preclassified = 0, long long fixed_stride = -1)
 {
     SelArgs a;
     a.V = V; a.cnt = cnt; a.cap = cap; a.n_live = n_live; a.M = M; a.vmax_bits = vmax; a.N = N; a.u = u_dev;
     a.cand = cand; a.cand_cap = cand_cap; a.sc = sc; a.res = res;
-    a.stage = SEL_ST_ALL; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr; a.pad_to = -1; a.fixed_stride = 1;
+    a.stage = stage; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr; a.pad_to = -1;
+    a.fixed_stride = fixed_stride >= 0 ? fixed_stride : h->fuse_stride;       // the same strided sample on every path
+    a.external_sample = external_sample; a.preclassified = preclassified;
     void *args[] = {&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
     return PF_OK;
@@ -418,16 +427,43 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         LaunchTimer lt(h, KC_PRESTEP);
         k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, nullptr);
     }
-    {
-        LaunchTimer lt(h, KC_EXPAND);
-        k_expand<D><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                h->stc, h->st, h->V, h->cnt, nullptr);
-    }
-    {
-        LaunchTimer lt(h, KC_SELECT);
-        int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
-                                   h->cand_cap, h->sc, h->res);
-        if (rc != PF_OK) return rc;
+    const bool fused = h->fused && h->cfg.order == PF_ORDER_INDEX;
+    if (fused) {
+        // bracket the threshold on a sample expansion, then classify inside the full expansion
+        {
+            LaunchTimer lt(h, KC_SELECT, 2);
+            const long long ns = (ub + h->fuse_stride - 1) / h->fuse_stride;
+            CUDA_TRY(cudaMemsetAsync((char *)h->sc + offsetof(SelScratch, list_n), 0, sizeof(long long), h->stream));
+            k_expand<D, 1><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,
+                                                                       nullptr);
+            int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand,
+                                       h->cand_cap, h->sc, h->res, SEL_ST_BRACKET, 1, 0, h->fuse_stride);
+            if (rc != PF_OK) return rc;
+        }
+        {
+            LaunchTimer lt(h, KC_EXPAND);
+            k_expand<D, 2><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse);
+        }
+        {
+            LaunchTimer lt(h, KC_SELECT);
+            int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
+                                       h->cand_cap, h->sc, h->res, SEL_ST_CLASSIFY | SEL_ST_SOLVE, 0, 1, 0);
+            if (rc != PF_OK) return rc;
+        }
+    } else {
+        {
+            LaunchTimer lt(h, KC_EXPAND);
+            k_expand<D, 0><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc, h->st, h->V, h->cnt, nullptr, 1, nullptr, nullptr, nullptr);
+        }
+        {
+            LaunchTimer lt(h, KC_SELECT);
+            int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
+                                       h->cand_cap, h->sc, h->res);
+            if (rc != PF_OK) return rc;
+        }
     }
     if (h->cfg.order == PF_ORDER_SORTED) {
         const int slots = h->k_max + 1;
@@ -441,20 +477,21 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         // resampling step: comb over the sorted list; exhaustive step: index order
         LaunchTimer lt(h, KC_SCAN, 7);
         const int gflat = grid_for(n_pad, SCAN_THREADS), gidx = grid_for(ub, SCAN_THREADS);
-        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, nullptr);
+        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, nullptr, nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr, nullptr);
         k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles,
                                                              h->pick_pos, h->surv_slot, 1, nullptr, nullptr, cap);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
                                                                            h->surv_slot);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, nullptr);
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, nullptr, nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
                                                             h->surv_slot, 2, nullptr, nullptr, cap);
     } else {
-        LaunchTimer lt(h, KC_SCAN, 3);
+        LaunchTimer lt(h, KC_SCAN, 4);
         const int gidx = grid_for(ub, SCAN_THREADS);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, nullptr);
+        if (fused) k_tile_fixup<<<grid_for(gidx, 256), 256, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live);
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, nullptr, fused ? h->sc : nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
                                                             h->surv_slot, 0, nullptr, nullptr, cap);
@@ -463,7 +500,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         LaunchTimer lt(h, KC_INSTANTIATE);
         k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max, nullptr);
+                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max, nullptr, &h->st->M_next);
     }
     {
         LaunchTimer lt(h, KC_STEPLOG);
@@ -820,6 +857,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         int occ = 0;
         ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SMEM_BYTES));
         h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
+        h->fuse_stride = std::max<long long>(1, (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET);
         long long cand_cap = M + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
         long long ntiles = (M + SCAN_THREADS - 1) / SCAN_THREADS;
         ST(dmalloc(&dW, (size_t)M)); ST(dmalloc(&dU, 1)); ST(dmalloc(&cand, (size_t)cand_cap));
@@ -848,7 +886,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         k_vmax<<<h->num_sms * 4, 256, 0, h->stream>>>(Vsel, M, st);
         rc = launch_select(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res);
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
-        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, nullptr);
+        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, nullptr, nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr, nullptr);
         k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr, nullptr, M);
         ST(cudaGetLastError());
@@ -959,8 +997,8 @@ static int32_t mg_begin(pf_handle h)
 {
     if (h->slog_cap < 1) { CUDA_TRY(dmalloc(&h->slog, 16)); h->slog_cap = 16; }
     k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc);
-    k_expand<D><<<grid_for(h->cap, 256), 256, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->k_max, h->tab,
-                                                                h->pc, h->stc, h->st, h->V, h->cnt, h->sc);
+    k_expand<D, 0><<<grid_for(h->cap, 256), 256, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->k_max, h->tab,
+                                                                   h->pc, h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
     k_publish_scalars<<<1, 32, 0, h->stream>>>(h->st, h->sc);
     h->launches += 3;
     return PF_OK;
@@ -996,7 +1034,7 @@ extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done,
     a.N = h->N; a.u = h->y1_dev + h->d; a.cand = h->cand; a.cand_cap = h->cand_cap; a.sc = h->sc; a.res = h->res;
     a.stage = stage; a.round0 = rounds_done; a.nranks = h->nranks; a.gacc = (const SelAcc *)gacc;
     a.glist = (const double *)glist; a.glist_each = list_each;
-    a.goff = &h->st->goff; a.pad_to = pad_to; a.fixed_stride = h->mg_stride;
+    a.goff = &h->st->goff; a.pad_to = pad_to; a.fixed_stride = h->mg_stride; a.external_sample = 0; a.preclassified = 0;
     if ((stage & SEL_ST_BRACKET) && gacc) { k_mg_globals<<<1, 32, 0, h->stream>>>((const SelAcc *)gacc, h->nranks, h->gscal); h->launches++; }
     void *args[] = {&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
@@ -1027,7 +1065,7 @@ extern "C" int32_t pf_mg_tiles(pf_handle h)
     MG_CHECK(h);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int g = grid_for(h->cap, SCAN_THREADS);
-    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, nullptr);
+    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, nullptr);
     k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, h->local_tot, h->sc);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -1045,7 +1083,7 @@ static int32_t mg_finish(pf_handle h, const TileSum *gathered)
                                                                                   h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
     k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max, h->sc);
+                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max, h->sc, nullptr);
     h->launches += 3;
     return PF_OK;
 }

@@ -64,6 +64,18 @@ struct SelScratch {
     long long count_in;             // list items inside [lo, hi)
     long long mult;                 // sample stride while solving the sample, 1 otherwise
     long long halt;                 // sharded run: 1 + index of the step that needs the host (all later kernels are no-ops)
+    // fused path (single GPU): the expansion kernel classifies against a bracket found BEFORE it
+    long long list_n;               // exact number of entries of the sample / candidate list (list_exact)
+    int list_exact;                 // 1: the list is dense (block-reserved ranges), 0: chunked with padding
+    int fuse_valid;                 // 1: k_expand classified against [lo, hi) and filled the accumulators / tile records
+    int fuse_scale;                 // item scale the expansion used (= scale of the bracket)
+    int fuse_tot_scale;             // scale of the kept-side total the expansion used
+    int tot_scale_used;             // scale of the kept-side total of the current classify round
+    int pad2;
+    int fuse_overflow;              // a block had more candidates than its staging buffer
+    int need_tot;                   // the total weight of this step has not been computed yet
+    int tiles_ok;                   // the survivor-scan tile records written by the expansion are usable
+    int pad1;
     // accumulators of the classify pass (SelAcc: the block a sharded run all-gathers)
     unsigned long long A_hi;        // #items >= hi
     unsigned long long n_cand;      // #items in [lo, hi)
@@ -74,6 +86,8 @@ struct SelScratch {
     unsigned long long overflow;    // sharded run: the list outgrew the fixed gather size
     unsigned long long M_local;     // sharded run: this shard's putative count and max weight bits
     unsigned long long vmax_local;
+    unsigned long long vs_bits;     // max weight of the strided sample (its exponent fixes the sample solve's scale)
+    unsigned long long acc_pad2;
     // running totals of the descent
     u128 B_run;                     // sum q of list items < lo (after narrowing)
     long long A_run;                // #list items >= hi (after narrowing)
@@ -89,7 +103,7 @@ struct SelScratch {
 struct SelAcc {
     unsigned long long A_hi, n_cand;
     acc128 B_lo, S_cand, Tot;
-    unsigned long long cand_chunks, overflow, M_local, vmax_local;
+    unsigned long long cand_chunks, overflow, M_local, vmax_local, vs_bits, acc_pad2;
 };
 #define SEL_ACC_OFFSET offsetof(SelScratch, A_hi)
 
@@ -118,7 +132,9 @@ struct SelArgs {
     long long glist_each;           // doubles per rank in glist (padded with the NaN pattern)
     const long long *goff;          // device: global index of the shard's first particle (phase of the strided sample)
     long long pad_to;               // sharded run: pad the local list with the NaN pattern up to this many entries
-    long long fixed_stride;         // sharded run: sample stride chosen by the host (global M is not known yet)
+    long long fixed_stride;         // > 0: sample stride chosen by the host (sharded run; fused path)
+    int external_sample;            // 1: the sample is already in the list (k_expand in sample mode), sc->list_n entries
+    int preclassified;              // 1: round `round0` was classified by the expansion kernel (if sc->fuse_valid)
 };
 
 // sharded run: sum the gathered per-rank accumulator blocks into the local scratch
@@ -139,9 +155,12 @@ __device__ inline void sum_gathered(SelScratch *sc, const SelAcc *g, int nranks)
 __global__ void k_mg_globals(const SelAcc *g, int nranks, long long *gscal)
 {
     if (threadIdx.x || blockIdx.x) return;
-    unsigned long long M = 0, vm = 0, ov = 0;
-    for (int r = 0; r < nranks; r++) { M += g[r].M_local; vm = g[r].vmax_local > vm ? g[r].vmax_local : vm; ov |= g[r].overflow; }
-    gscal[0] = (long long)M; gscal[1] = (long long)vm; gscal[2] = (long long)ov;
+    unsigned long long M = 0, vm = 0, ov = 0, vs = 0;
+    for (int r = 0; r < nranks; r++) {
+        M += g[r].M_local; vm = g[r].vmax_local > vm ? g[r].vmax_local : vm; ov |= g[r].overflow;
+        vs = g[r].vs_bits > vs ? g[r].vs_bits : vs;
+    }
+    gscal[0] = (long long)M; gscal[1] = (long long)vm; gscal[2] = (long long)ov; gscal[3] = (long long)vs;
 }
 
 // pad the tail of a chunked list up to `pad_to` entries (grid-wide, after the appends are done)
@@ -159,6 +178,16 @@ __device__ __forceinline__ unsigned long long gtimer()
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+
+// Scale of the kept-side total (items >= hi).  52 - e(hi) represents every such double exactly
+// (no truncation), so the total weight does not depend on which kernel accumulated it; the
+// sum stays below 2^127 while the maximum is within 46 binades of hi.
+__host__ __device__ __forceinline__ int kept_tot_scale(u64 hi, u64 vmax)
+{
+    const int e_v = exp_of_bits(vmax);
+    if (hi < PF_INF_BITS && e_v - exp_of_bits(hi) <= 46) return 52 - exp_of_bits(hi);
+    return 99 - e_v;
 }
 
 // predicate of cutoff_ascending (src/fearnhead.jl:69): tot <= (N - n_geq) * w
@@ -375,7 +404,7 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
 
 __device__ inline void reset_round(SelScratch *sc)
 {
-    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0; sc->overflow = 0;
+    sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0; sc->overflow = 0; sc->list_n = 0; sc->list_exact = 0;
     for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
 }
 
@@ -446,7 +475,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
         res->rounds = 0; res->status = 0; res->n_cand_first = 0;
         res->t_ns[0] = gtimer();
-        sc->mult = 1;
+        sc->mult = 1; sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0; sc->vs_bits = 0;
         if (multi) {               // sharded: the global M is not known yet; decided at the BRACKET stage
             sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0;
         } else if (trivial) {      // keep everything (src/fearnhead.jl:135-138); an all-zero step keeps nothing
@@ -457,7 +486,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
     }
     grid.sync();
     }
-    const long long stride = multi ? a.fixed_stride : (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
+    const long long stride = (multi || a.fixed_stride > 0) ? a.fixed_stride : (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
     // (a sharded run samples unconditionally: the global M is only known after the gather)
     if ((sampled || multi) && (stage & SEL_ST_SAMPLE)) {
         // strided sample of whole particles (global indices = 0 mod stride), appended to the
@@ -465,6 +494,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         {
             ChunkWriter cw; cw.init();
             unsigned long long cnt_s = 0;
+            u64 vs_max = 0;
             const long long sphase = a.goff ? *a.goff : 0;
             const long long first = (stride - (sphase % stride)) % stride;
             const long long swarps = multi ? (nwarps < SEL_SAMPLE_WARPS ? nwarps : SEL_SAMPLE_WARPS) : nwarps;
@@ -479,12 +509,14 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
                     have = have && bits != 0;             // zeros never decide anything
                     cnt_s += have;
+                    vs_max = bits > vs_max ? bits : vs_max;
                     cw.push(have, bits, a.cand, &sc->cand_chunks, lane);
                 }
             }
             cw.finish(a.cand, lane);
             cnt_s = warp_sum64(cnt_s);
-            if (lane == 0 && cnt_s) atomicAdd(&sc->n_cand, cnt_s);
+            vs_max = warp_max64(vs_max);
+            if (lane == 0 && cnt_s) { atomicAdd(&sc->n_cand, cnt_s); atomicMax(&sc->vs_bits, vs_max); }
             if (!(stage & SEL_ST_BRACKET)) {                 // sharded: the host gathers the samples
                 grid.sync();
                 pad_list(a.cand, sc->cand_chunks, a.pad_to, sc);
@@ -492,6 +524,21 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             }
             grid.sync();
         }
+    }
+    if (a.external_sample && (stage & SEL_ST_BRACKET)) {
+        // fused path: k_expand (sample mode) already filled the list with sc->list_n sample values
+        if (blockIdx.x == 0 && tid == 0) {
+            const long long ns = sc->list_n;
+            reset_round(sc);
+            for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
+            res->rounds = 0; res->status = 0; res->n_cand_first = 0;
+            res->t_ns[0] = gtimer();
+            sc->mult = 1; sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0;
+            sc->n_cand = (unsigned long long)ns; sc->list_n = ns; sc->list_exact = 1; sc->vs_bits = vmax;     // (vmax = the sample's maximum here)
+            if (M <= N) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1; }     // (M is exact here)
+            else { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0; }
+        }
+        grid.sync();
     }
     if (multi && (stage & SEL_ST_BRACKET)) {
         if (blockIdx.x == 0 && tid == 0) {
@@ -506,18 +553,20 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             if (multi) sum_gathered(sc, a.gacc, a.nranks);
             sc->B_run = mk128(0, 0); sc->A_run = 0; sc->count_in = (long long)sc->n_cand; sc->mult = stride; sc->phase = 2;
             sc->lo = 1; sc->hi = PF_INF_BITS;
+            if (multi) sc->vs_bits = (u64)a.M[3];                    // gathered sample maximum (k_mg_globals)
         }
         grid.sync();
-        const long long list_n = multi ? a.glist_each * a.nranks : (long long)sc->cand_chunks * SEL_CHUNK;
+        const int ss = SEL_ITEM_BITS - exp_of_bits(sc->vs_bits);     // the sample solve runs at the sample's own scale
+        const long long list_n = multi ? a.glist_each * a.nranks : (sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK);
         for (int level = 0; level < 8; level++) {
             const u64 blo = sc->lo, bhi = sc->hi;
             if (sc->count_in == 0 || (bhi - blo) <= 1) break;
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            hist_level(list, list_n, blo, bhi, shift, vmax_scale, sc, smem_raw);
+            hist_level(list, list_n, blo, bhi, shift, ss, sc, smem_raw);
             grid.sync();
-            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, vmax_scale, 1, smem_raw);
+            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, ss, 1, smem_raw);
             grid.sync();
             if (sc->phase == 6) break;
         }
@@ -529,19 +578,39 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             sc->scale = SEL_ITEM_BITS - exp_of_bits(hi >= PF_INF_BITS ? vmax : hi);
             reset_round(sc);
             for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
+            if (a.external_sample && hi < PF_INF_BITS) {
+                // the expansion kernel may classify against this bracket: dense candidate list from 0,
+                // kept-side total at the exact scale 52 - e(hi) (valid while the maximum is within 46 binades of hi)
+                sc->fuse_valid = 1; sc->fuse_scale = sc->scale; sc->fuse_tot_scale = 52 - exp_of_bits(hi); sc->list_exact = 1;
+            }
         }
     }
     if (blockIdx.x == 0 && tid == 0 && (stage & SEL_ST_BRACKET)) res->t_ns[1] = gtimer();
+    if (a.external_sample && !(stage & (SEL_ST_CLASSIFY | SEL_ST_SOLVE))) {              // fused path: the expansion runs next
+        if (blockIdx.x == 0 && tid == 0 && !sc->fuse_valid) reset_round(sc);       // the classic rounds start from a clean slate
+        return;
+    }
     grid.sync();
 
     // ---------------- rounds
+    const bool pre = a.preclassified && sc->fuse_valid;      // the expansion kernel classified round `round0`
+    if (pre && blockIdx.x == 0 && tid == 0) res->status |= 1;
+    if (a.preclassified && !pre) {
+        // classic rounds behind a sample expansion: a bracket that is open at the top was scaled by the
+        // SAMPLE's maximum; the true maximum is known now
+        if (blockIdx.x == 0 && tid == 0 && sc->hi >= PF_INF_BITS) sc->scale = vmax_scale;
+        grid.sync();
+    }
     for (int round = a.round0; round < 40; round++) {
         const u64 lo = sc->lo, hi = sc->hi;
         const int scale = sc->scale;
         const int mode = sc->mode;
         const bool keep_all = (mode == 1);
+        const bool pre_round = pre && round == a.round0;
+        const bool need_tot = sc->need_tot != 0;
+        const int ts_round = kept_tot_scale(hi, vmax);
         // ---- classify pass over all items
-        if (stage & SEL_ST_CLASSIFY) {
+        if ((stage & SEL_ST_CLASSIFY) && !pre_round) {
             unsigned long long A_hi = 0, n_cand = 0;
             u128 B_lo = mk128(0, 0), S_c = mk128(0, 0), Tot = mk128(0, 0);
             ChunkWriter cw; cw.init();
@@ -556,7 +625,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
                     bool is_cand = false;
                     if (have) {
-                        if (bits >= hi) { A_hi++; if (round == 0) Tot = add128(Tot, fx128(bits, tot_scale)); }
+                        if (bits >= hi) { A_hi++; if (need_tot) Tot = add128(Tot, fx128(bits, ts_round)); }
                         else if (bits < lo) B_lo = add128(B_lo, fx70(bits, scale));
                         else { is_cand = true; n_cand++; S_c = add128(S_c, fx70(bits, scale)); }
                     }
@@ -580,7 +649,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     if (x1) atomicAdd(&sc->n_cand, x1);
                     atomic_add_acc(&sc->B_lo, y0);
                     atomic_add_acc(&sc->S_cand, y1);
-                    if (round == 0) atomic_add_acc(&sc->Tot, y2);
+                    if (need_tot) atomic_add_acc(&sc->Tot, y2);
                 }
             }
             __syncthreads();
@@ -598,15 +667,21 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             bool truncated = false;
             if (multi) for (int r = 0; r < a.nranks; r++) truncated |= a.gacc[r].overflow != 0;
             res->rounds = round + 1;
-            if (round == 0) {
-                res->n_cand_first = (long long)sc->n_cand; res->t_ns[2] = gtimer();
-                // total weight = kept side (>= hi, scale tot_scale) + low side (< hi, bracket scale)
+            // fused path: the expansion's classification is unusable if a block overflowed its candidate
+            // buffer or the true maximum lies more than 46 binades above hi (kept-side scale not exact)
+            const bool pre_bad = pre_round && (sc->fuse_overflow || kept_tot_scale(hi, vmax) != sc->fuse_tot_scale);
+            if (need_tot && !pre_bad) {
+                if (round == a.round0) { res->n_cand_first = (long long)sc->n_cand; res->t_ns[2] = gtimer(); }
+                // total weight = kept side (>= hi) + low side (< hi, bracket scale)
+                const int ts = pre_round ? sc->fuse_tot_scale : ts_round;
                 u128 low = add128(acc_value(&sc->B_lo), acc_value(&sc->S_cand));
-                double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), tot_scale - scale);
-                res->log_total = log(tsum) - (double)tot_scale * 0.693147180559945309417232121458;
+                double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), ts - scale);
+                res->log_total = log(tsum) - (double)ts * 0.693147180559945309417232121458;
+                sc->need_tot = 0;
             }
             int phase = 2;       // 2 = descend, 3 = redo classify with a new bracket, 4 = done, 7 = gathered list truncated
             if (truncated) { reset_round(sc); phase = 7; }      // the host re-classifies and gathers at exact size
+            else if (pre_bad) { reset_round(sc); for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0; sc->fuse_valid = 0; phase = 3; res->status |= sc->fuse_overflow ? 2 : 4; }
             else if (keep_all) phase = 4;
             else if (mode == 2) {
                 // comb-rescale round: T at the new scale; lo = hi = thr so A_hi = A again
@@ -618,6 +693,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc, fx70(lo, scale));
                 bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(B, Sc), N, Ahi, fx70(hi, scale));
                 if (fail_lo || fail_hi) {
+                    res->status |= fail_lo ? 8 : 16;
                     u64 nlo = fail_lo ? 1ull : lo, nhi = fail_hi ? PF_INF_BITS : hi;
                     sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
                     sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
@@ -635,7 +711,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         if (sc->phase == 4) break;
 
         // ---- radix descent over the candidate list
-        const long long list_n = multi ? a.glist_each * a.nranks : (long long)sc->cand_chunks * SEL_CHUNK;
+        const long long list_n = multi ? a.glist_each * a.nranks : (sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK);
         for (int level = 0; level < 8; level++) {
             const u64 blo = sc->lo, bhi = sc->hi;
             const long long count_in = sc->count_in;
@@ -721,6 +797,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 // precision: the scale must sit within 8 binades of the threshold
                 bool precise = (thr >= PF_INF_BITS) ? (scale == vmax_scale) : ((SEL_ITEM_BITS - scale) - exp_of_bits(thr) <= 8);
                 if (!precise && round < 30) {
+                    res->status |= 32;
                     int e = exp_of_bits(thr);
                     long long elo = e - 1 + 1023, ehi = e + 2 + 1023;
                     u64 nlo = elo <= 0 ? 1ull : ((u64)elo << 52);
@@ -733,6 +810,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 } else {
                     res->thr_bits = thr; res->A = A; res->T = T; res->scale = scale;
                     sc->phase = comb_rescale(sc, res, N) ? 3 : 4;
+                    if (sc->phase == 3) res->status |= 64;
                 }
             }
         }
@@ -772,6 +850,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             res->log_c = log(c);
             res->lw_resamp = res->log_c - res->log_total;
             res->thr_value = __longlong_as_double((long long)res->thr_bits);
+            // the tile records the expansion wrote stay usable if no classic round overwrote the list or the scale
+            sc->tiles_ok = (pre && sc->fuse_valid && res->rounds == a.round0 + 1 && res->scale == sc->fuse_scale) ? 1 : 0;
         }
         res->t_ns[4] = gtimer();
     }

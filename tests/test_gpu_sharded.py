@@ -79,8 +79,12 @@ def test_slow_path_truncated_gather_and_rebracketing(kw):
     sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T, **kw)
     sh.filter_(ys, us)
     assert sh.slow_steps > 0
-    assert np.array_equal(sh.logweights(), ref.logweights())
+    # every decision is identical; the total weight is (exact mass above the bracket) + (fixed-point
+    # mass below it), so with a deliberately different bracket the log-weights agree to rounding
     assert np.array_equal(sh.ncomponents(), ref.ncomponents())
+    assert np.array_equal(sh.last_ancestors(), ref.last_ancestors())
+    assert np.array_equal(sh.last_assignments(), ref.last_assignments())
+    np.testing.assert_allclose(sh.logweights(), ref.logweights(), rtol=0, atol=1e-12)
 
 
 @pytest.mark.parametrize("lookahead,window", [(1, 0), (4, 0), (16, 0), (4, 50), (8, 400)])
