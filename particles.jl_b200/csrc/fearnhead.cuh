@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
     __shared__ unsigned int s_redk[8];
     const long long n_live = st->n_live;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long i = (MODE == 1) ? gid * stride : gid;
+    // MODE 1 samples aligned groups of 4 consecutive particles (one 32-byte sector per field row):
+    // global particle g is in the sample iff (g / 4) % stride == 0
+    const long long i = (MODE == 1) ? (gid >> 2) * (4 * stride) + (gid & 3) : gid;
     const bool fused = (MODE == 2) && sc->fuse_valid;
     u64 lo = 0, hi = 0; int scale = 0, tscale = 0;
     if (fused) { lo = sc->lo; hi = sc->hi; scale = sc->fuse_scale; tscale = sc->fuse_tot_scale; }
@@ -702,7 +704,7 @@ __global__ void k_steplog(const StepState *st, const SelResult *res, StepLog *lg
     r.n_in = st->n_live; r.M = st->M; r.n_kept = st->n_kept; r.n_req = res->keep_all ? 0 : res->n;
     r.n_got = st->n_picked; r.n_out = st->n_next; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
     r.log_total = res->log_total; r.lw_resamp = res->lw_resamp; r.thr = res->thr_value; r.cv = 0.0;
-    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds + 1000 * res->status;
+    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds;
     r.sel_us[0] = (res->t_ns[1] - res->t_ns[0]) * 1e-3; r.sel_us[1] = (res->t_ns[2] - res->t_ns[1]) * 1e-3;
     r.sel_us[2] = (res->t_ns[3] - res->t_ns[2]) * 1e-3; r.sel_us[3] = (res->t_ns[4] - res->t_ns[0]) * 1e-3;
     (void)N;

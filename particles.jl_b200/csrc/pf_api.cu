@@ -432,7 +432,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         // bracket the threshold on a sample expansion, then classify inside the full expansion
         {
             LaunchTimer lt(h, KC_SELECT, 2);
-            const long long ns = (ub + h->fuse_stride - 1) / h->fuse_stride;
+            const long long ns = 4 * ((ub + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride));     // groups of 4 particles
             CUDA_TRY(cudaMemsetAsync((char *)h->sc + offsetof(SelScratch, list_n), 0, sizeof(long long), h->stream));
             k_expand<D, 1><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,

@@ -495,12 +495,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             ChunkWriter cw; cw.init();
             unsigned long long cnt_s = 0;
             u64 vs_max = 0;
-            const long long sphase = a.goff ? *a.goff : 0;
-            const long long first = (stride - (sphase % stride)) % stride;
+            // global particle g is in the sample iff (g / 4) % stride == 0 (aligned groups of 4; the same
+            // rule as the sample expansion, so every path brackets the threshold on the same sample)
+            const long long goff = a.goff ? *a.goff : 0;
+            const long long k0 = goff / (4 * stride);                 // first sampled group that can reach this shard
             const long long swarps = multi ? (nwarps < SEL_SAMPLE_WARPS ? nwarps : SEL_SAMPLE_WARPS) : nwarps;
-            for (long long base = gwarp * 32; gwarp < swarps && first + base * stride < n_live; base += swarps * 32) {
-                long long i = first + (base + lane) * stride;
-                int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
+            for (long long base = gwarp * 32; gwarp < swarps && (k0 + (base >> 2)) * (4 * stride) < goff + n_live; base += swarps * 32) {
+                const long long g = base + lane;
+                const long long i = (k0 + (g >> 2)) * (4 * stride) + (g & 3) - goff;
+                int c = (i >= 0 && i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
                 int maxc = c;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
