@@ -206,6 +206,17 @@ int32_t pf_mg_finish(pf_handle h, const void *gathered_totals);
 int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
                    int64_t *phase, int64_t *exchange);
 int32_t pf_mg_unpack(pf_handle h, const void *recv_buffer);
+/* Direct exchange: when every rank's next-generation arrays are mapped into this process
+ * (pf_mg_ipc_handles on the owner -> pf_mg_set_peer here; or plain pointers from pf_mg_local_arrays when
+ * the ranks live in one process), k_instantiate stores a child that changes owner straight into its
+ * new owner's store over NVLink and the population is re-partitioned into equal blocks at EVERY
+ * step: no send/recv buffers, no all-to-all, no host-known sizes.  The host program must place a
+ * collective (e.g. the next step's first all-gather, or a barrier) between pf_mg_finish and the
+ * next pf_mg_begin so that remote stores are complete before their owner reads them. */
+int32_t pf_mg_local_arrays(pf_handle h, void **out /* [8] */);
+int32_t pf_mg_ipc_handles(pf_handle h, void *out /* 8 x 64 bytes */);
+int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, const void *ipc_handles);
+int32_t pf_mg_enable_direct(pf_handle h);
 /* Look-ahead: pf_mg_close() after pf_mg_finish marks the step as "needs the host" on the device when the search
  * did not finish or particles must change owner; every kernel of later steps is then a no-op, so a host program
  * may queue several observations ahead and call pf_mg_drain() (synchronises; out = {halt (1 + step index, or 0),

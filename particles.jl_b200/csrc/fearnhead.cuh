@@ -297,11 +297,23 @@ struct RankOff {
     long long recv_idx0[PF_MAX_RANKS], recv_len[PF_MAX_RANKS], recv_off[PF_MAX_RANKS];    // by source
 };
 
+// Direct exchange: every rank's next-generation arrays mapped into this process (cudaIpc, or
+// plain pointers when the ranks live in one process), so that k_instantiate stores a child
+// that changes owner straight into its new owner's store over NVLink -- no packing, no
+// send/recv buffers, no host-known sizes.
+struct PeerTable {
+    double *S[PF_MAX_RANKS];
+    int *Kc[PF_MAX_RANKS];
+    double *logw[PF_MAX_RANKS];
+    unsigned int *gen_anc[PF_MAX_RANKS];
+    unsigned char *gen_asg[PF_MAX_RANKS];
+};
+
 // one thread: turn the gathered per-rank totals (mass of the low partition, kept count) into
 // this rank's offsets and the exchange plan.  rows = doubles per migrating particle.
 __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, int nranks, const SelResult *__restrict__ res,
                                StepState *st, RankOff *ro, int rows, const SelScratch *guard, long long stay_cap,
-                               long long window)
+                               long long window, int direct)
 {
     if (threadIdx.x || blockIdx.x) return;
     if (guard && (guard->phase != 4 || guard->halt)) { ro->n_local = 0; return; }          // the threshold search has not finished (speculative tail)
@@ -341,11 +353,12 @@ __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, i
         ro->bnd[r] = b;
     }
     for (int r = 0; r < nranks; r++) fits = fits && (ro->bnd[r + 1] - ro->bnd[r] <= stay_cap);
+    if (direct) fits = false;           // direct exchange: equal blocks every step (children are stored remotely by k_instantiate)
     if (!fits)
         for (int r = 0; r <= nranks; r++) { long long b = (long long)r * q; ro->bnd[r] = b > n_global ? n_global : b; }
     ro->g_first = g_first[rank]; ro->n_local = n_loc[rank]; ro->n_global = n_global; ro->q = q;
     ro->n_mine = ro->bnd[rank + 1] - ro->bnd[rank];
-    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0; ro->exchange = fits ? 2 : 1;
+    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0; ro->exchange = direct ? 3 : (fits ? 2 : 1);
     long long soff = 0, roff = 0;
     for (int d = 0; d < nranks; d++) {
         long long lo = g_first[rank] > ro->bnd[d] ? g_first[rank] : ro->bnd[d];
@@ -354,6 +367,7 @@ __global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, i
         long long lo2 = g_first[d] > ro->bnd[rank] ? g_first[d] : ro->bnd[rank];
         long long hi2 = g_first[d] + n_loc[d] < ro->bnd[rank + 1] ? g_first[d] + n_loc[d] : ro->bnd[rank + 1];
         long long len2 = (d == rank || hi2 <= lo2) ? 0 : hi2 - lo2;
+        if (direct) { len = 0; len2 = 0; }       // nothing goes through the send / recv buffers
         ro->send_start[d] = lo; ro->send_len[d] = len; ro->recv_idx0[d] = lo2 - ro->bnd[rank]; ro->recv_len[d] = len2;
         if (fits) {      // neighbour mode: fixed slots -- [0, window) left neighbour, [window, 2 window) right neighbour
             ro->send_off[d] = (d < rank ? 0 : window) * rows;
@@ -539,16 +553,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
 // genealogy and sets the normalised log-weight (src/fearnhead.jl:172-179).
 template <int D>
 __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ S, const int *__restrict__ Kc,
-                                                     double *__restrict__ S2, int *__restrict__ Kc2,
-                                                     double *__restrict__ logw2, long long cap,
+                                                     double *S2, int *Kc2,
+                                                     double *logw2, long long cap,
                                                      const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                      const StepConst *__restrict__ scp, const StepState *__restrict__ st,
                                                      const SelResult *__restrict__ res, const double *__restrict__ V,
                                                      const unsigned int *__restrict__ surv_parent,
                                                      const unsigned char *__restrict__ surv_slot,
-                                                     unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
+                                                     unsigned int *gen_anc, unsigned char *gen_asg,
                                                      const RankOff *__restrict__ ro, double *__restrict__ sendbuf, int k_max,
-                                                     const SelScratch *guard, long long *m_next)
+                                                     const SelScratch *guard, long long *m_next,
+                                                     const PeerTable *__restrict__ peers, long long gen_off)
 {
     using L = Layout<D>;
     if (guard && (guard->phase != 4 || guard->halt)) return;
@@ -566,6 +581,14 @@ __global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ 
         while (dest + 1 < ro->nranks && g >= ro->bnd[dest + 1]) dest++;
         anc_off = (unsigned int)ro->goff_prev;
         if (dest == ro->rank) { idx = g - ro->bnd[dest]; dstb = S2 + idx; }
+        else if (peers) {
+            // direct exchange: the child is written into its new owner's arrays (peer memory over NVLink)
+            idx = g - ro->bnd[dest];
+            S2 = peers->S[dest]; Kc2 = peers->Kc[dest]; logw2 = peers->logw[dest];
+            gen_anc = peers->gen_anc[dest] ? peers->gen_anc[dest] + gen_off : nullptr;
+            gen_asg = peers->gen_asg[dest] ? peers->gen_asg[dest] + gen_off : nullptr;
+            dstb = S2 + idx;
+        }
         else { remote = true; stride = ro->send_len[dest]; dstb = sendbuf + ro->send_off[dest] + (g - ro->send_start[dest]); }
     }
     const unsigned int par = surv_parent[t];

@@ -71,6 +71,10 @@ struct pf_filter_s {
     int mg_rounds = 0;
     long long mg_stride = 1, mg_sample_entries = 0, mg_cand_entries = 0, mg_window = 0;
     bool own_stream = true;
+    PeerTable *peers[2] = {nullptr, nullptr};   // direct exchange: peer arrays of the buffer written at even / odd steps
+    PeerTable peers_host[2];
+    bool direct = false;
+    std::vector<void *> ipc_opened;
     double *y1_dev = nullptr;             // y (d) + u (1) of the current sharded step
     double *y1_pin = nullptr;             // pinned staging ring for (y, u)
     int y1_slot = 0;
@@ -218,8 +222,9 @@ extern "C" int32_t pf_destroy(pf_handle h)
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->gscal, h->local_tot, h->ro, h->sendbuf,
-                    h->recvbuf, h->y1_dev};
+                    h->recvbuf, h->y1_dev, h->peers[0], h->peers[1]};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->y1_pin) cudaFreeHost(h->y1_pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -500,7 +505,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         LaunchTimer lt(h, KC_INSTANTIATE);
         k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max, nullptr, &h->st->M_next);
+                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max, nullptr, &h->st->M_next, nullptr, 0);
     }
     {
         LaunchTimer lt(h, KC_STEPLOG);
@@ -1078,12 +1083,13 @@ static int32_t mg_finish(pf_handle h, const TileSum *gathered)
     const int cur = h->cur, nxt = cur ^ 1;
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc, h->cap, h->mg_window);
+    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc, h->cap, h->mg_window, h->direct ? 1 : 0);
     k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
                                                                                   h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
     k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max, h->sc, nullptr);
+                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max, h->sc, nullptr, h->direct ? h->peers[nxt] : nullptr,
+                                                                          (long long)h->steps * h->cap);
     h->launches += 3;
     return PF_OK;
 }
@@ -1122,6 +1128,72 @@ extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_c
     if (n_global) *n_global = r.n_global;
     if (exchange) *exchange = r.exchange;
     h->n_host = r.n_mine;
+    return PF_OK;
+}
+
+// ---- direct exchange (peer stores)
+// arrays a peer must be able to write: S[0], S[1], Kc[0], Kc[1], logw[0], logw[1], gen_anc, gen_asg
+#define PF_MG_NPEER_ARRAYS 8
+static void *peer_array(pf_handle h, int k)
+{
+    switch (k) {
+    case 0: return h->S[0]; case 1: return h->S[1]; case 2: return h->Kc[0]; case 3: return h->Kc[1];
+    case 4: return h->logw[0]; case 5: return h->logw[1]; case 6: return h->gen_anc; default: return h->gen_asg;
+    }
+}
+
+extern "C" int32_t pf_mg_local_arrays(pf_handle h, void **out /* [8] */)
+{
+    MG_CHECK(h);
+    for (int k = 0; k < PF_MG_NPEER_ARRAYS; k++) out[k] = peer_array(h, k);
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_ipc_handles(pf_handle h, void *out /* 8 x 64 bytes */)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    memset(out, 0, PF_MG_NPEER_ARRAYS * sizeof(cudaIpcMemHandle_t));
+    for (int k = 0; k < PF_MG_NPEER_ARRAYS; k++)
+        if (peer_array(h, k)) CUDA_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out + k, peer_array(h, k)));
+    return PF_OK;
+}
+
+// arrays of rank `peer`: either pointers valid in this process (ptrs != NULL: ranks emulated in one
+// process) or the 8 IPC handles pf_mg_ipc_handles produced on that rank
+extern "C" int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, const void *ipc_handles)
+{
+    MG_CHECK(h);
+    if (peer < 0 || peer >= h->nranks) return set_error(h, PF_ERR_ARG, "pf_mg_set_peer: bad rank");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    void *a[PF_MG_NPEER_ARRAYS];
+    for (int k = 0; k < PF_MG_NPEER_ARRAYS; k++) {
+        a[k] = nullptr;
+        if (peer == h->rank) a[k] = peer_array(h, k);
+        else if (ptrs) a[k] = ptrs[k];
+        else if (peer_array(h, k)) {      // same configuration on every rank: the peer has the array iff we do
+            CUDA_TRY(cudaIpcOpenMemHandle(&a[k], ((const cudaIpcMemHandle_t *)ipc_handles)[k], cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(a[k]);
+        }
+    }
+    for (int b = 0; b < 2; b++) {
+        h->peers_host[b].S[peer] = (double *)a[b]; h->peers_host[b].Kc[peer] = (int *)a[2 + b];
+        h->peers_host[b].logw[peer] = (double *)a[4 + b];
+        h->peers_host[b].gen_anc[peer] = (unsigned int *)a[6]; h->peers_host[b].gen_asg[peer] = (unsigned char *)a[7];
+    }
+    return PF_OK;
+}
+
+extern "C" int32_t pf_mg_enable_direct(pf_handle h)
+{
+    MG_CHECK(h);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    for (int b = 0; b < 2; b++) {
+        if (!h->peers[b]) CUDA_TRY(dmalloc(&h->peers[b], 1));
+        CUDA_TRY(cudaMemcpyAsync(h->peers[b], &h->peers_host[b], sizeof(PeerTable), cudaMemcpyHostToDevice, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->direct = true;
     return PF_OK;
 }
 

@@ -80,6 +80,10 @@ SYMBOLS = [
     ("pf_mg_plan", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("pf_mg_unpack", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("pf_mg_local_arrays", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("pf_mg_ipc_handles", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("pf_mg_set_peer", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
+    ("pf_mg_enable_direct", C.c_int32, [C.c_void_p]),
     ("pf_mg_close", C.c_int32, [C.c_void_p]),
     ("pf_mg_set_obs", C.c_int32, [C.c_void_p, _dp, C.c_double]),
     ("pf_mg_drain", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),

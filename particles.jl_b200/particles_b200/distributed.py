@@ -98,6 +98,19 @@ class TorchComm:
         outs = [int(c) * rows for c in recv_counts[0]]
         self.dist.all_to_all_single(recvs[0][:sum(outs)], sends[0][:sum(ins)], outs, ins)
 
+    def device_barrier(self, device):
+        """Stream-ordered barrier: a 1-element all-reduce.  Its completion on this rank implies every
+        rank has finished the kernels queued before it (their stores into peer memory included)."""
+        import torch
+        if getattr(self, "_bar", None) is None:
+            self._bar = torch.zeros(1, dtype=torch.int32, device=device)
+        self.dist.all_reduce(self._bar)
+
+    def exchange_handles(self, blob):
+        out = [None] * self.size
+        self.dist.all_gather_object(out, blob)
+        return out
+
     def neighbour_exchange(self, sends, recvs, slot):
         """Fixed-size exchange with the two adjacent ranks: send[0:slot] -> left, send[slot:2 slot]
         -> right; recv[0:slot] <- left, recv[slot:2 slot] <- right."""
@@ -149,6 +162,9 @@ class LocalComm:
                     recvs[d][o:o + n].copy_(sends[s][int(soff[s][d]):int(soff[s][d]) + n])
                 o += n
 
+    def device_barrier(self, device):
+        pass                                  # one process, one stream: already ordered
+
     def neighbour_exchange(self, sends, recvs, slot):
         for r in range(self.size):
             if r > 0:
@@ -175,6 +191,7 @@ class _Shard:
     def __init__(self, L, cfg, device):
         import torch
         self.L = L
+        self.rank = int(cfg.rank)
         h = C.c_void_p()
         _lib.check(L.pf_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -203,6 +220,16 @@ class _Shard:
                                        C.c_void_p(glist.data_ptr()) if glist is not None and glist.numel() else None,
                                        int(each), int(pad_to)), self.h)
 
+    def local_arrays(self):
+        out = (C.c_void_p * 8)()
+        _lib.check(self.L.pf_mg_local_arrays(self.h, out), self.h)
+        return out
+
+    def ipc_handles(self):
+        buf = C.create_string_buffer(8 * 64)
+        _lib.check(self.L.pf_mg_ipc_handles(self.h, buf), self.h)
+        return buf.raw
+
     def plan(self, G):
         sc, rc = (C.c_int64 * G)(), (C.c_int64 * G)()
         nl, ng, ph, ex = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
@@ -215,7 +242,7 @@ class ShardedFearnheadParticles:
     comm.size ranks.  Same results as the unsharded filter, particle for particle."""
 
     def __init__(self, n, prior, stateprior, comm, *, k_max=16, history=0, devices=None, seed=0, sample_entries=None,
-                 cand_entries=None):
+                 cand_entries=None, direct=True):
         from . import NormalInverseChisq, NormalInverseWishart
         import torch
         self.comm, self.N, self.k_max = comm, int(n), int(k_max)
@@ -248,6 +275,24 @@ class ShardedFearnheadParticles:
                 s.sample_entries = int(sample_entries)
             if cand_entries is not None:
                 s.cand_entries = int(cand_entries)
+        # direct exchange: map every rank's arrays into every other rank (same process: plain pointers;
+        # one process per GPU: CUDA IPC), so that children that change owner are stored remotely
+        self.direct = bool(direct) and comm.size > 1
+        if self.direct:
+            if len(self.shards) == comm.size:           # all ranks in this process
+                for s in self.shards:
+                    for p in self.shards:
+                        if p is not s:
+                            _lib.check(L.pf_mg_set_peer(s.h, p.rank, p.local_arrays(), None), s.h)
+            else:
+                s = self.shards[0]
+                blobs = comm.exchange_handles(s.ipc_handles())
+                for r, blob in enumerate(blobs):
+                    if r != s.rank:
+                        _lib.check(L.pf_mg_set_peer(s.h, r, None, blob), s.h)
+            for s in self.shards:
+                _lib.check(L.pf_mg_set_peer(s.h, s.rank, None, None), s.h)
+                _lib.check(L.pf_mg_enable_direct(s.h), s.h)
         self.n_global = 1
         self.steps = 0
         self.host_syncs = 0
@@ -352,7 +397,9 @@ class ShardedFearnheadParticles:
             _lib.check(L.pf_mg_close(s.h), s.h)
         self._mark("tail")
         slot = sh[0].window * sh[0].rows
-        if slot:                                                                         # boundaries shift by <= window
+        if self.direct:
+            comm.device_barrier(sh[0].device)        # remote stores of the re-partitioned children are complete
+        elif slot:                                                                       # boundaries shift by <= window
             comm.neighbour_exchange([s.send for s in sh], [s.recv for s in sh], slot)
             self.bytes_moved += 2 * slot * 8
         for s in sh:
@@ -408,6 +455,8 @@ class ShardedFearnheadParticles:
             comm.all_to_all_v([s.send for s in sh], [p[0] for p in plans], [s.recv for s in sh], [p[1] for p in plans], sh[0].rows)
             self.exchanges += 1
             self.bytes_moved += moving * sh[0].rows * 8
+        elif self.direct:
+            comm.device_barrier(sh[0].device)
         elif sh[0].window:
             slot = sh[0].window * sh[0].rows
             comm.neighbour_exchange([s.send for s in sh], [s.recv for s in sh], slot)

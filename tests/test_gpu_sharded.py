@@ -15,15 +15,16 @@ def _mix2d(rng, T, k=8, radius=6.0):
     return radius * np.stack([np.cos(ang), np.sin(ang)], axis=1) + rng.standard_normal((T, 2))
 
 
-@pytest.mark.parametrize("G,N,T", [(2, 1000, 40), (4, 1000, 40), (2, 1 << 16, 30), (8, 3000, 25)])
-def test_sharded_equals_unsharded(G, N, T):
+@pytest.mark.parametrize("G,N,T,direct", [(2, 1000, 40, True), (4, 1000, 40, True), (2, 1 << 16, 30, True), (8, 3000, 25, True),
+                                          (4, 1000, 40, False), (2, 1 << 16, 30, False)])
+def test_sharded_equals_unsharded(G, N, T, direct):
     rng = np.random.default_rng(5)
     ys = _mix2d(rng, T)
     us = rng.random(T)
     prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
     crp = pb.ChineseRestaurantProcess(1.0)
     ref = pb.FearnheadParticles(N, prior, crp, history=T)
-    sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T)
+    sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T, direct=direct)
     for t in range(T):
         ref.fit_(ys[t], [us[t]])
         sh.fit_(ys[t], us[t])
@@ -39,6 +40,8 @@ def test_sharded_equals_unsharded(G, N, T):
     sizes = [int(sh.L.pf_n_particles(s.h)) for s in sh.shards]
     q = -(-len(sh) // G)
     assert sum(sizes) == len(sh) and max(sizes) <= q + q // 2 + 64 + G
+    if direct:       # equal blocks after every step, nothing through the send / recv buffers
+        assert sizes == [min(max(len(sh) - r * q, 0), q) for r in range(G)] and sh.exchanges == 0
     assert sh.exchanges < T
 
 
@@ -47,7 +50,7 @@ def test_device_plan_matches_host_plan():
     G, N, T = 4, 5000, 20
     ys = _mix2d(rng, T)
     prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
-    sh = ShardedFearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), LocalComm(G), history=T)
+    sh = ShardedFearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), LocalComm(G), history=T, direct=False)
     import ctypes as C
     for t in range(T):
         sh.fit_(ys[t], rng.random())
