@@ -199,7 +199,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0,
                                                 host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K,
-                                                slow_path_steps=ps.slow_steps, exchanges=ps.exchanges, lookahead=a.lookahead,
+                                                slow_path_steps=ps.slow_steps, exchanges=ps.exchanges, lookahead=a.lookahead, halts=ps.halts[-12:],
                                                 stage_ms_device_host={k: [round(v[0], 4), round(v[1], 4)] for k, v in stage_ms.items()}),
             "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
                     "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le)},

@@ -36,7 +36,7 @@ struct StepLog {            // one record per step, read back after pf_filter
 // new cluster starts with (add(prior, y), src/component.jl:85).
 template <int D>
 __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, StepConst *sc_out, int first,
-                          const SelScratch *guard)
+                          const SelScratch *guard, const SelResult *prev)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (guard && guard->halt) return;
@@ -56,6 +56,8 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
     const NRow r0 = pc->row0;
     double l1p = log1p(r0.r * q);
     c.lw_new = r0.C - 0.5 * pc->logdet0 - r0.h * l1p;
+    // exactly what k_expand evaluates for the new-cluster putative of a particle whose log-weight is lw_resamp
+    c.plateau_bits = (prev && !first) ? (unsigned long long)__double_as_longlong(exp(prev->lw_resamp + c.lw_new)) : 0ull;
     // new slot: n = 1, mean = y, L = cholupdate(L0, sqrt(r0) (y - mu0)), logdet = logdet0 + log1p(r0 q)
     double x[D];
     double sr = sqrt(r0.r);
@@ -96,7 +98,7 @@ struct TileSum {           // survivor-scan record of one tile of SCAN_THREADS p
 #define EXP_CAND_CAP 1024          // MODE 2: candidates one block of 256 particles may stage
 #define EXP_SAMPLE_THREADS 32      // MODE 1 runs one warp per block: at most 32 * PF_MAX_SLOTS sample values per block
 struct TileFuse {
-    unsigned int cand_off, cand_cnt;
+    unsigned int cand_off, cand_cnt, n_plateau, pad;
 };
 
 template <int D, int MODE>
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
     __shared__ unsigned int s_ncand, s_goff;
     __shared__ u128 s_tot[8];                    // kept-side total per warp
     __shared__ u128 s_red[8];
-    __shared__ unsigned int s_redk[8];
+    __shared__ unsigned int s_redk[8], s_redp[8];
     const long long n_live = st->n_live;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // MODE 1 samples aligned groups of 4 consecutive particles (one 32-byte sector per field row):
@@ -133,7 +135,8 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
     u64 vmax = 0;
     long long myM = 0, myOvf = 0;
     u128 B_lo = mk128(0, 0), Tot = mk128(0, 0);
-    unsigned int kept_hi = 0;
+    unsigned int kept_hi = 0, n_plat = 0;
+    const u64 plateau = scp->plateau_bits;
     // what happens to one putative weight
     auto emit = [&](int j, double v) {
         const u64 b = (u64)__double_as_longlong(v);
@@ -149,6 +152,8 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
                 Tot = add128(Tot, fx128(b, tscale));              // < 2^99 each by the 28-binade guard of the search
             } else if (b < lo) {
                 B_lo = add128(B_lo, fx70(b, scale));
+            } else if (b == plateau) {
+                n_plat++;                                          // the mass tie: counted, not listed
             } else {
                 unsigned int pos = atomicAdd(&s_ncand, 1u);
                 if (pos < CAND_CAP) s_cand[pos] = b;
@@ -192,8 +197,8 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
     myM = (long long)warp_sum64((u64)myM);
     myOvf = (long long)warp_sum64((u64)myOvf);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (fused) { B_lo = warp_sum128(B_lo); Tot = warp_sum128(Tot); kept_hi = (unsigned int)warp_sum64(kept_hi); }
-    if (lane == 0) { s_max[wid] = vmax; s_M[wid] = myM; s_ovf[wid] = myOvf; if (fused) { s_red[wid] = B_lo; s_tot[wid] = Tot; s_redk[wid] = kept_hi; } }
+    if (fused) { B_lo = warp_sum128(B_lo); Tot = warp_sum128(Tot); kept_hi = (unsigned int)warp_sum64(kept_hi); n_plat = (unsigned int)warp_sum64(n_plat); }
+    if (lane == 0) { s_max[wid] = vmax; s_M[wid] = myM; s_ovf[wid] = myOvf; if (fused) { s_red[wid] = B_lo; s_tot[wid] = Tot; s_redk[wid] = kept_hi; s_redp[wid] = n_plat; } }
     __syncthreads();
     if (threadIdx.x == 0) {
         const int nw = blockDim.x >> 5;
@@ -229,10 +234,11 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
             if (threadIdx.x == 0) {
                 // block totals: the per-warp B_lo / kept_hi were parked in s_red / s_redk above
                 u128 B = s_red[0], C2 = s_sc[0], tot = s_tot[0];
-                unsigned int kh = s_redk[0];
-                for (int w = 1; w < (int)(blockDim.x >> 5); w++) { B = add128(B, s_red[w]); C2 = add128(C2, s_sc[w]); tot = add128(tot, s_tot[w]); kh += s_redk[w]; }
+                unsigned int kh = s_redk[0], np = s_redp[0];
+                for (int w = 1; w < (int)(blockDim.x >> 5); w++) { B = add128(B, s_red[w]); C2 = add128(C2, s_sc[w]); tot = add128(tot, s_tot[w]); kh += s_redk[w]; np += s_redp[w]; }
                 tiles[blockIdx.x].X = B; tiles[blockIdx.x].kept = kh;
-                tfuse[blockIdx.x].cand_off = goff; tfuse[blockIdx.x].cand_cnt = n;
+                tfuse[blockIdx.x].cand_off = goff; tfuse[blockIdx.x].cand_cnt = n; tfuse[blockIdx.x].n_plateau = np;
+                if (np) atomicAdd(&sc->n_plateau, (unsigned long long)np);
                 if (kh) atomicAdd(&sc->A_hi, (unsigned long long)kh);
                 if (n) atomicAdd(&sc->n_cand, (unsigned long long)n);
                 atomic_add_acc(&sc->B_lo, B);
@@ -246,7 +252,8 @@ __global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, co
 // fused path: add each tile's candidates (now that the threshold is known) to its record
 __global__ void __launch_bounds__(256) k_tile_fixup(TileSum *__restrict__ tiles, const TileFuse *__restrict__ tfuse,
                                                     const double *__restrict__ list, const SelResult *__restrict__ res,
-                                                    const SelScratch *__restrict__ sc, const long long *__restrict__ n_items_ptr)
+                                                    const SelScratch *__restrict__ sc, const long long *__restrict__ n_items_ptr,
+                                                    const StepConst *__restrict__ scp)
 {
     if (!sc->tiles_ok) return;
     const long long ntiles = (*n_items_ptr + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -262,6 +269,11 @@ __global__ void __launch_bounds__(256) k_tile_fixup(TileSum *__restrict__ tiles,
         const u64 b = (u64)__double_as_longlong(list[(long long)off + k]);
         if (b >= thr) kept++;
         else if (comb) X = add128(X, fx70(b, scale));
+    }
+    const unsigned int np = tfuse[t].n_plateau;
+    if (np) {
+        if (scp->plateau_bits >= thr) kept += np;
+        else if (comb) X = add128(X, mul128_64(fx70(scp->plateau_bits, scale), (u64)np));
     }
     if (!comb) X = mk128(0, 0);
     tiles[t].X = X; tiles[t].kept = kept;
@@ -720,14 +732,14 @@ __global__ void k_sorted_finalize(const StepState *__restrict__ st, const SelRes
 }
 
 // fill the per-step log record (one thread)
-__global__ void k_steplog(const StepState *st, const SelResult *res, StepLog *lg, long long N)
+__global__ void k_steplog(const StepState *st, const SelResult *res, StepLog *lg, long long N, int dbg_status)
 {
     if (threadIdx.x || blockIdx.x) return;
     StepLog r;
     r.n_in = st->n_live; r.M = st->M; r.n_kept = st->n_kept; r.n_req = res->keep_all ? 0 : res->n;
     r.n_got = st->n_picked; r.n_out = st->n_next; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
     r.log_total = res->log_total; r.lw_resamp = res->lw_resamp; r.thr = res->thr_value; r.cv = 0.0;
-    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds;
+    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds + (dbg_status ? 1000 * res->status : 0);
     r.sel_us[0] = (res->t_ns[1] - res->t_ns[0]) * 1e-3; r.sel_us[1] = (res->t_ns[2] - res->t_ns[1]) * 1e-3;
     r.sel_us[2] = (res->t_ns[3] - res->t_ns[2]) * 1e-3; r.sel_us[3] = (res->t_ns[4] - res->t_ns[0]) * 1e-3;
     (void)N;

@@ -37,6 +37,9 @@ struct Layout {
 struct StepConst {
     double y[PF_MAX_D];
     double lw_new;                         // log alpha + log predictive of y under the prior
+    unsigned long long plateau_bits;       // bit pattern of the new-cluster putative of every RESAMPLED particle: they all
+                                           // carry the same weight c/total (src/fearnhead.jl:173), so these putatives are
+                                           // exactly tied -- the one mass tie of the algorithm, counted instead of listed
     double newslot[2 + PF_MAX_D + PF_MAX_D * (PF_MAX_D + 1) / 2];   // fields of prior (+) y
 };
 

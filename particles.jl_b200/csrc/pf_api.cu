@@ -409,6 +409,7 @@ static int32_t launch_select(pf_handle h, const double *V, const unsigned char *
     a.stage = stage; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr; a.pad_to = -1;
     a.fixed_stride = fixed_stride >= 0 ? fixed_stride : h->fuse_stride;       // the same strided sample on every path
     a.external_sample = external_sample; a.preclassified = preclassified;
+    a.plateau_ptr = (sc == h->sc && h->stc) ? &h->stc->plateau_bits : nullptr;
     void *args[] = {&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
     return PF_OK;
@@ -430,7 +431,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     h->epoch++;
     {
         LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, nullptr);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, nullptr, h->res);
     }
     const bool fused = h->fused && h->cfg.order == PF_ORDER_INDEX;
     if (fused) {
@@ -495,7 +496,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     } else {
         LaunchTimer lt(h, KC_SCAN, 4);
         const int gidx = grid_for(ub, SCAN_THREADS);
-        if (fused) k_tile_fixup<<<grid_for(gidx, 256), 256, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live);
+        if (fused) k_tile_fixup<<<grid_for(gidx, 256), 256, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc);
         k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, nullptr, fused ? h->sc : nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
@@ -509,7 +510,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     }
     {
         LaunchTimer lt(h, KC_STEPLOG);
-        k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->N);
+        k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->N, getenv("PF_DEBUG_STATUS") ? 1 : 0);
     }
     CUDA_TRY(cudaGetLastError());
     h->cur = nxt;
@@ -530,7 +531,7 @@ static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_de
     const int g256 = grid_for(N, 256);
     {
         LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, nullptr);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, nullptr, nullptr);
     }
     {
         LaunchTimer lt(h, KC_CL_PROP);
@@ -1001,7 +1002,7 @@ template <int D>
 static int32_t mg_begin(pf_handle h)
 {
     if (h->slog_cap < 1) { CUDA_TRY(dmalloc(&h->slog, 16)); h->slog_cap = 16; }
-    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc);
+    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc, h->res);
     k_expand<D, 0><<<grid_for(h->cap, 256), 256, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->k_max, h->tab,
                                                                    h->pc, h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
     k_publish_scalars<<<1, 32, 0, h->stream>>>(h->st, h->sc);
@@ -1040,6 +1041,7 @@ extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done,
     a.stage = stage; a.round0 = rounds_done; a.nranks = h->nranks; a.gacc = (const SelAcc *)gacc;
     a.glist = (const double *)glist; a.glist_each = list_each;
     a.goff = &h->st->goff; a.pad_to = pad_to; a.fixed_stride = h->mg_stride; a.external_sample = 0; a.preclassified = 0;
+    a.plateau_ptr = &h->stc->plateau_bits;
     if ((stage & SEL_ST_BRACKET) && gacc) { k_mg_globals<<<1, 32, 0, h->stream>>>((const SelAcc *)gacc, h->nranks, h->gscal); h->launches++; }
     void *args[] = {&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));

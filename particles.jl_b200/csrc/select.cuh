@@ -87,7 +87,10 @@ struct SelScratch {
     unsigned long long M_local;     // sharded run: this shard's putative count and max weight bits
     unsigned long long vmax_local;
     unsigned long long vs_bits;     // max weight of the strided sample (its exponent fixes the sample solve's scale)
-    unsigned long long acc_pad2;
+    unsigned long long n_plateau;   // in-bracket items equal to the plateau value (counted, not listed)
+    // plateau resolution: candidates below the plateau value (count, fixed-point sum)
+    unsigned long long pl_cnt;
+    acc128 pl_sum;
     // running totals of the descent
     u128 B_run;                     // sum q of list items < lo (after narrowing)
     long long A_run;                // #list items >= hi (after narrowing)
@@ -103,7 +106,7 @@ struct SelScratch {
 struct SelAcc {
     unsigned long long A_hi, n_cand;
     acc128 B_lo, S_cand, Tot;
-    unsigned long long cand_chunks, overflow, M_local, vmax_local, vs_bits, acc_pad2;
+    unsigned long long cand_chunks, overflow, M_local, vmax_local, vs_bits, n_plateau;
 };
 #define SEL_ACC_OFFSET offsetof(SelScratch, A_hi)
 
@@ -133,6 +136,7 @@ struct SelArgs {
     const long long *goff;          // device: global index of the shard's first particle (phase of the strided sample)
     long long pad_to;               // sharded run: pad the local list with the NaN pattern up to this many entries
     long long fixed_stride;         // > 0: sample stride chosen by the host (sharded run; fused path)
+    const unsigned long long *plateau_ptr;   // device: value of the step's mass tie (StepConst.plateau_bits); NULL = none
     int external_sample;            // 1: the sample is already in the list (k_expand in sample mode), sc->list_n entries
     int preclassified;              // 1: round `round0` was classified by the expansion kernel (if sc->fuse_valid)
 };
@@ -140,14 +144,14 @@ struct SelArgs {
 // sharded run: sum the gathered per-rank accumulator blocks into the local scratch
 __device__ inline void sum_gathered(SelScratch *sc, const SelAcc *g, int nranks)
 {
-    unsigned long long A = 0, nc = 0, ch = 0;
+    unsigned long long A = 0, nc = 0, ch = 0, npl = 0;
     acc128 b, c, t;
     for (int k = 0; k < 4; k++) { b.l[k] = 0; c.l[k] = 0; t.l[k] = 0; }
     for (int r = 0; r < nranks; r++) {
-        A += g[r].A_hi; nc += g[r].n_cand; ch += g[r].cand_chunks;
+        A += g[r].A_hi; nc += g[r].n_cand; ch += g[r].cand_chunks; npl += g[r].n_plateau;
         for (int k = 0; k < 4; k++) { b.l[k] += g[r].B_lo.l[k]; c.l[k] += g[r].S_cand.l[k]; t.l[k] += g[r].Tot.l[k]; }
     }
-    sc->A_hi = A; sc->n_cand = nc; sc->B_lo = b; sc->S_cand = c; sc->Tot = t;
+    sc->A_hi = A; sc->n_cand = nc; sc->B_lo = b; sc->S_cand = c; sc->Tot = t; sc->n_plateau = npl;
     (void)ch;
 }
 
@@ -405,6 +409,7 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
 __device__ inline void reset_round(SelScratch *sc)
 {
     sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0; sc->overflow = 0; sc->list_n = 0; sc->list_exact = 0;
+    sc->n_plateau = 0; sc->pl_cnt = 0; for (int k = 0; k < 4; k++) sc->pl_sum.l[k] = 0;
     for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
 }
 
@@ -466,6 +471,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
     const bool sampled = !trivial && M > SEL_FINAL_CAP;
     const int stage = a.stage;
     const bool multi = a.nranks > 1;
+    const u64 plateau = a.plateau_ptr ? *a.plateau_ptr : 0ull;
     const double *list = multi ? a.glist : a.cand;
 
     // ---------------- phase 0: first bracket
@@ -614,7 +620,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
         const int ts_round = kept_tot_scale(hi, vmax);
         // ---- classify pass over all items
         if ((stage & SEL_ST_CLASSIFY) && !pre_round) {
-            unsigned long long A_hi = 0, n_cand = 0;
+            unsigned long long A_hi = 0, n_cand = 0, n_plat = 0;
             u128 B_lo = mk128(0, 0), S_c = mk128(0, 0), Tot = mk128(0, 0);
             ChunkWriter cw; cw.init();
             for (long long base = gwarp * 32; base < n_live; base += nwarps * 32) {
@@ -630,6 +636,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     if (have) {
                         if (bits >= hi) { A_hi++; if (need_tot) Tot = add128(Tot, fx128(bits, ts_round)); }
                         else if (bits < lo) B_lo = add128(B_lo, fx70(bits, scale));
+                        else if (bits == plateau) n_plat++;                  // the mass tie: counted, not listed
                         else { is_cand = true; n_cand++; S_c = add128(S_c, fx70(bits, scale)); }
                     }
                     cw.push(is_cand, bits, a.cand, &sc->cand_chunks, lane);
@@ -637,7 +644,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             }
             cw.finish(a.cand, lane);
             // block reduce, then one set of atomics per block
-            A_hi = warp_sum64(A_hi); n_cand = warp_sum64(n_cand);
+            A_hi = warp_sum64(A_hi); n_cand = warp_sum64(n_cand); n_plat = warp_sum64(n_plat);
+            if (lane == 0 && n_plat) atomicAdd(&sc->n_plateau, n_plat);
             B_lo = warp_sum128(B_lo); S_c = warp_sum128(S_c); Tot = warp_sum128(Tot);
             if (lane == 0) { s_redc[0][wid] = A_hi; s_redc[1][wid] = n_cand; s_red[0][wid] = B_lo; s_red[1][wid] = S_c; s_red[2][wid] = Tot; }
             __syncthreads();
@@ -678,6 +686,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 // total weight = kept side (>= hi) + low side (< hi, bracket scale)
                 const int ts = pre_round ? sc->fuse_tot_scale : ts_round;
                 u128 low = add128(acc_value(&sc->B_lo), acc_value(&sc->S_cand));
+                if (sc->n_plateau) low = add128(low, mul128_64(fx70(plateau, scale), (u64)sc->n_plateau));
                 double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), ts - scale);
                 res->log_total = log(tsum) - (double)ts * 0.693147180559945309417232121458;
                 sc->need_tot = 0;
@@ -693,8 +702,10 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             } else {
                 u128 B = acc_value(&sc->B_lo), Sc = acc_value(&sc->S_cand);
                 long long Ahi = (long long)sc->A_hi, nc = (long long)sc->n_cand;
-                bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc, fx70(lo, scale));
-                bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(B, Sc), N, Ahi, fx70(hi, scale));
+                const long long np = (long long)sc->n_plateau;            // in-bracket copies of the plateau value (not in the list)
+                const u128 Pm = np ? mul128_64(fx70(plateau, scale), (u64)np) : mk128(0, 0);
+                bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc + np, fx70(lo, scale));
+                bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(add128(B, Sc), Pm), N, Ahi, fx70(hi, scale));
                 if (fail_lo || fail_hi) {
                     res->status |= fail_lo ? 8 : 16;
                     u64 nlo = fail_lo ? 1ull : lo, nhi = fail_hi ? PF_INF_BITS : hi;
@@ -704,11 +715,42 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     phase = 3;
                 } else {
                     sc->B_run = B; sc->A_run = Ahi; sc->count_in = nc;
+                    if (np) phase = 8;           // first decide on which side of the plateau the threshold lies
                 }
             }
             sc->phase = phase;
         }
         grid.sync();
+        if (sc->phase == 8) {
+            // ---- plateau resolution: mass and count of the candidates below the plateau value P, then the
+            // predicate at P itself; the bracket shrinks to [lo, P) or (P, hi) and never contains the tie
+            const long long ln = multi ? a.glist_each * a.nranks : (sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK);
+            u128 sb = mk128(0, 0);
+            unsigned long long cb = 0;
+            for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < ln; t += (long long)gridDim.x * SEL_THREADS) {
+                u64 bits = (u64)__double_as_longlong(list[t]);
+                if (bits >= lo && bits < plateau) { cb++; sb = add128(sb, fx70(bits, scale)); }
+            }
+            sb = warp_sum128(sb); cb = warp_sum64(cb);
+            if (lane == 0) { s_red[0][wid] = sb; s_redc[0][wid] = cb; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < SEL_WARPS; w++) { sb = add128(sb, s_red[0][w]); cb += s_redc[0][w]; }
+                if (cb) atomicAdd(&sc->pl_cnt, cb);
+                atomic_add_acc(&sc->pl_sum, sb);
+            }
+            grid.sync();
+            if (blockIdx.x == 0 && tid == 0) {
+                const long long np = (long long)sc->n_plateau, cbt = (long long)sc->pl_cnt;
+                const u128 qP = fx70(plateau, scale);
+                const u128 Bp = add128(sc->B_run, acc_value(&sc->pl_sum));
+                const long long A_geqP = sc->A_run + (sc->count_in - cbt) + np;
+                if (pred128(Bp, N, A_geqP, qP)) { sc->hi = plateau; sc->A_run = A_geqP; sc->count_in = cbt; }
+                else { sc->lo = plateau + 1; sc->B_run = add128(Bp, mul128_64(qP, (u64)np)); sc->count_in = sc->count_in - cbt; }
+                sc->phase = 2;
+            }
+            grid.sync();
+        }
         if (sc->phase == 7) return;
         if (sc->phase == 3) { if (stage & SEL_ST_CLASSIFY) continue; return; }
         if (sc->phase == 4) break;

@@ -203,6 +203,7 @@ class _Shard:
         self.scalars = _view(p.scalars, 2, "<i8", self.device)
         self.acc = _view(p.acc, p.acc_bytes // 8, "<i8", self.device)
         self.list = _view(p.list, p.list_capacity, "<i8", self.device)          # bit patterns of the doubles
+        self.list_capacity = int(p.list_capacity)
         self.total = _view(p.local_total, p.total_bytes // 8, "<i8", self.device)
         self.send = _view(p.send_buffer, p.buffer_capacity, "<f8", self.device)
         self.recv = _view(p.recv_buffer, p.buffer_capacity, "<f8", self.device)
@@ -299,6 +300,7 @@ class ShardedFearnheadParticles:
         self.bytes_moved = 0
         self.slow_steps = 0
         self.exchanges = 0
+        self.halts = []                  # (step, search phase) of every step that needed the host
         self.profile = None              # set to [] to collect (label, cuda event) marks per step
 
     def close(self):
@@ -355,8 +357,6 @@ class ShardedFearnheadParticles:
         torch.cuda.synchronize()
         dev, host, cnt = {}, {}, {}
         for (l0, e0, t0), (l1, e1, t1) in zip(self.profile[:-1], self.profile[1:]):
-            if l1 == "begin":
-                continue
             dev[l1] = dev.get(l1, 0.0) + e0.elapsed_time(e1)
             host[l1] = host.get(l1, 0.0) + 1e3 * (t1 - t0)
             cnt[l1] = cnt.get(l1, 0) + 1
@@ -423,6 +423,12 @@ class ShardedFearnheadParticles:
     def _complete(self, y, u, step, phase):
         """Finish a halted step through the synchronous stages."""
         comm, sh, L = self.comm, self.shards, self.L
+        self.halts.append((int(step), int(phase)))
+        if phase == 7:
+            # a candidate list outgrew its fixed gather size (typically a plateau of exactly tied weights:
+            # the new-cluster putatives of all resampled particles): gather more from now on
+            for s in sh:
+                s.cand_entries = min(2 * s.cand_entries, s.list_capacity - 1024)
         y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
         for s in sh:
             _lib.check(L.pf_mg_resume(s.h, int(step)), s.h)
