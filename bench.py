@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--order", default="index", choices=["index", "sorted"])
-    ap.add_argument("--lookahead", type=int, default=4, help="sharded run: observations queued per host synchronisation")
+    ap.add_argument("--lookahead", type=int, default=10, help="sharded run: observations queued per host synchronisation")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -148,6 +148,13 @@ __device__ __forceinline__ u128 shfl_xor128(u128 v, int d)
     r.hi = __shfl_xor_sync(0xffffffffu, v.hi, d);
     return r;
 }
+__device__ __forceinline__ u128 shfl_xor_bcast128(u128 v, int src_lane)
+{
+    u128 r;
+    r.lo = __shfl_sync(0xffffffffu, v.lo, src_lane);
+    r.hi = __shfl_sync(0xffffffffu, v.hi, src_lane);
+    return r;
+}
 __device__ __forceinline__ u128 warp_sum128(u128 v)
 {
 #pragma unroll

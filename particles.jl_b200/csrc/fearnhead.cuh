@@ -441,7 +441,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
     }
 }
 
-// exclusive prefix over the tiles (in place) and the step's survivor counts; one block
+// exclusive prefix over the tiles (in place) and the step's survivor counts; one block of 32
+// warps, warp w owns a contiguous run of tiles and walks it 32 tiles at a time (coalesced
+// 1 KB loads, shuffle scan, carry), then the warps' totals are scanned
 __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelResult *__restrict__ res,
                                                       const long long *__restrict__ n_items_ptr, StepState *st, int mode,
                                                       TileSum *local_tot /* sharded run: totals out, counts set later */,
@@ -449,34 +451,54 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelR
 {
     if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
-    __shared__ u128 s_warp[33];
-    __shared__ unsigned int s_k[1024];
+    __shared__ u128 s_wx[32];
+    __shared__ unsigned int s_wk[32];
     const long long n_items = *n_items_ptr;
     const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
-    const long long per = (ntiles + blockDim.x - 1) / blockDim.x;
-    const long long b = (long long)threadIdx.x * per, e = b + per < ntiles ? b + per : ntiles;
-    u128 lx = mk128(0, 0); unsigned int lk = 0;
-    for (long long t = b; t < e; t++) { lx = add128(lx, tiles[t].X); lk += tiles[t].kept; }
-    u128 totX;
-    u128 runX = block_excl_scan128(lx, s_warp, &totX);
-    s_k[threadIdx.x] = lk;
-    __syncthreads();
-    if (threadIdx.x == 0) { unsigned int run = 0; for (int t = 0; t < (int)blockDim.x; t++) { unsigned int x = s_k[t]; s_k[t] = run; run += x; } s_warp[0].lo = run; }
-    __syncthreads();
-    unsigned int runK = s_k[threadIdx.x];
-    const unsigned int totK = (unsigned int)s_warp[0].lo;
-    for (long long t = b; t < e; t++) {
-        u128 x = tiles[t].X; unsigned int k = tiles[t].kept;
-        tiles[t].X = runX; tiles[t].kept = runK;
-        runX = add128(runX, x); runK += k;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long per = ((ntiles + 31) / 32 + 31) / 32 * 32;          // tiles per warp, multiple of 32
+    const long long b = (long long)wid * per, e = b + per < ntiles ? b + per : ntiles;
+    // pass 1: warp totals
+    u128 wx = mk128(0, 0); unsigned int wk = 0;
+    for (long long t0 = b; t0 < e; t0 += 32) {
+        const long long t = t0 + lane;
+        if (t < e) { wx = add128(wx, tiles[t].X); wk += tiles[t].kept; }
     }
-    if (threadIdx.x == 0) {
-        if (local_tot) { local_tot->X = totX; local_tot->kept = totK; }
-        else {
-            const bool comb = res->n > 0 && !isz128(res->T);
-            long long picked = comb ? (long long)teeth_below(mul128_64(totX, (u64)res->n), res->Uoff, res->T) : 0;
-            st->n_kept = totK; st->n_picked = picked; st->n_next = (long long)totK + picked; st->n_global = st->n_next;
+    wx = warp_sum128(wx); wk = (unsigned int)warp_sum64(wk);
+    if (lane == 0) { s_wx[wid] = wx; s_wk[wid] = wk; }
+    __syncthreads();
+    if (wid == 0) {
+        u128 x = s_wx[lane], ix = x; unsigned int k = s_wk[lane], ik = k;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u128 ox = shfl_up128(ix, d); unsigned int ok = __shfl_up_sync(0xffffffffu, ik, d);
+            if (lane >= d) { ix = add128(ix, ox); ik += ok; }
         }
+        s_wx[lane] = sub128(ix, x); s_wk[lane] = ik - k;                 // exclusive warp offsets
+        if (lane == 31) {
+            if (local_tot) { local_tot->X = ix; local_tot->kept = ik; }
+            else {
+                const bool comb = res->n > 0 && !isz128(res->T);
+                long long picked = comb ? (long long)teeth_below(mul128_64(ix, (u64)res->n), res->Uoff, res->T) : 0;
+                st->n_kept = ik; st->n_picked = picked; st->n_next = (long long)ik + picked; st->n_global = st->n_next;
+            }
+        }
+    }
+    __syncthreads();
+    // pass 2: exclusive prefixes in place
+    u128 runX = s_wx[wid]; unsigned int runK = s_wk[wid];
+    for (long long t0 = b; t0 < e; t0 += 32) {
+        const long long t = t0 + lane;
+        u128 x = mk128(0, 0); unsigned int k = 0;
+        if (t < e) { x = tiles[t].X; k = tiles[t].kept; }
+        u128 ix = x; unsigned int ik = k;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u128 ox = shfl_up128(ix, d); unsigned int ok = __shfl_up_sync(0xffffffffu, ik, d);
+            if (lane >= d) { ix = add128(ix, ox); ik += ok; }
+        }
+        if (t < e) { tiles[t].X = add128(runX, sub128(ix, x)); tiles[t].kept = runK + ik - k; }
+        runX = add128(runX, shfl_xor_bcast128(ix, 31)); runK += __shfl_sync(0xffffffffu, ik, 31);
     }
 }
 

@@ -209,6 +209,7 @@ class _Shard:
         self.recv = _view(p.recv_buffer, p.buffer_capacity, "<f8", self.device)
         self.sample_entries, self.cand_entries = int(p.sample_entries), int(p.cand_entries)
         self.window, self.capacity = int(p.window), int(p.local_capacity)
+        self.cand_entries0 = self.cand_entries
 
     def state(self):
         st = (C.c_int64 * 4)()
@@ -275,7 +276,7 @@ class ShardedFearnheadParticles:
             if sample_entries is not None:
                 s.sample_entries = int(sample_entries)
             if cand_entries is not None:
-                s.cand_entries = int(cand_entries)
+                s.cand_entries = s.cand_entries0 = int(cand_entries)
         # direct exchange: map every rank's arrays into every other rank (same process: plain pointers;
         # one process per GPU: CUDA IPC), so that children that change owner are stored remotely
         self.direct = bool(direct) and comm.size > 1
@@ -429,6 +430,7 @@ class ShardedFearnheadParticles:
             # the new-cluster putatives of all resampled particles): gather more from now on
             for s in sh:
                 s.cand_entries = min(2 * s.cand_entries, s.list_capacity - 1024)
+            self._clean_batches = 0
         y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
         for s in sh:
             _lib.check(L.pf_mg_resume(s.h, int(step)), s.h)
@@ -488,6 +490,13 @@ class ShardedFearnheadParticles:
             for k in range(t, tend):
                 self._enqueue(ys[k], uniforms[k])
             halt, phase = self._drain()
+            if not halt:
+                # the gather size grown by an overflow decays back once the lists are small again
+                self._clean_batches = getattr(self, "_clean_batches", 0) + 1
+                if self._clean_batches >= 2:
+                    for s in self.shards:
+                        s.cand_entries = max(s.cand_entries0, s.cand_entries // 2)
+                    self._clean_batches = 0
             if halt:
                 th = halt - 1 - base                     # index of the halted observation
                 self._complete(ys[th], uniforms[th], halt - 1, phase)
