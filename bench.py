@@ -87,18 +87,20 @@ class ClockSampler(threading.Thread):
             time.sleep(0.1)
 
     def summary(self):
-        sm, reasons, mx = [], set(), None
+        sm, reasons, mx, pw = [], set(), None, []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             try:
                 sm.append(float(s[0]))
                 mx = float(s[1])
+                pw.append(float(s[2]))
                 for nm, v in zip(names, s[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "sm_min_mhz": float(np.min(sm)) if sm else None, "power_w": float(np.median(pw)) if pw else None,
                 "samples": len(sm)}
 
 

@@ -101,8 +101,14 @@ struct TileFuse {
     unsigned int cand_off, cand_cnt, n_plateau, pad;
 };
 
+#ifndef PF_EXPAND_MINBLOCKS
+#define PF_EXPAND_MINBLOCKS 4
+#endif
+#ifndef PF_INST_MINBLOCKS
+#define PF_INST_MINBLOCKS 1
+#endif
 template <int D, int MODE>
-__global__ void __launch_bounds__(256) k_expand(const double *__restrict__ S, const double *__restrict__ logw,
+__global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const double *__restrict__ S, const double *__restrict__ logw,
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
@@ -525,6 +531,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
     const u128 T = res->T, U = res->Uoff;
     const bool comb = n > 0 && !isz128(T);
     const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
+    __shared__ u128 s_S0, s_Q0;
+    __shared__ unsigned int s_R0;
+    __shared__ u64 s_t0;
+    __shared__ long long s_k0;
+    __shared__ double s_inv;
+    if (tid == 0) {
+        u128 S0 = tiles[blockIdx.x].X;
+        long long k0 = (long long)tiles[blockIdx.x].kept;
+        if (ro) { S0 = add128(S0, ro->S_off); k0 += ro->kept_off - ro->g_first; }   // positions relative to this rank's first survivor
+        s_S0 = S0; s_k0 = k0;
+        if (comb) {
+            const u64 t0 = teeth_below(mul128_64(S0, n), U, T);
+            unsigned int R0;
+            s_Q0 = divmod128_32(add128(U, mul128_64(T, t0)), (unsigned int)n, &R0);
+            s_R0 = R0; s_t0 = t0;
+            s_inv = (double)n / to_double128(T);
+        }
+    }
     u128 myX; unsigned int myKept;
     thread_sums(V, cap, i, c, thr, scale, comb, myX, myKept);
     u128 totX;
@@ -541,22 +565,53 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
         s_wc[lane] = wi - w;
     }
     __syncthreads();
-    if (c == 0) return;
     const unsigned int exK = s_wc[wid] + incK - myKept;
     // running low-partition mass S (fixed point) and the next tooth k: tooth k is passed by S
     // <=> Uoff + k T < n S <=> floor((Uoff + k T) / n) < S; (Q, R) = divmod(Uoff + k T, n) steps
-    // by (Tq, Tr) = divmod(T, n) from tooth to tooth.
-    u128 S = add128(tiles[blockIdx.x].X, exX);
-    long long kcount = (long long)tiles[blockIdx.x].kept + exK;
-    if (ro) { S = add128(S, ro->S_off); kcount += ro->kept_off - ro->g_first; }     // positions relative to this rank's first survivor
+    // by (Tq, Tr) = divmod(T, n) from tooth to tooth.  The tile's first tooth (t0, Q0, R0) is
+    // found once per block (the one 128-bit division); a thread reaches its own tooth
+    // t0 + k with Q = Q0 + k Tq + floor((R0 + k Tr) / n), k from an FP estimate corrected exactly.
+    u128 S = add128(s_S0, exX);
+    long long kcount = s_k0 + exK;
     u64 t = 0;
     u128 Q = mk128(0, 0);
     unsigned int R = 0;
     const unsigned int n32 = (unsigned int)n, Tr = res->Tr;
     const u128 Tq = res->Tq;
+    bool tooth_inside = false;
     if (comb) {
-        t = teeth_below(mul128_64(S, n), U, T);
-        Q = divmod128_32(add128(U, mul128_64(T, t)), n32, &R);
+        const u128 Q0 = s_Q0; const unsigned int R0 = s_R0;
+        u64 k = 0; Q = Q0; R = R0;
+        if (lt128(Q0, S)) {
+            k = (u64)(to_double128(sub128(S, Q0)) * s_inv);
+            u64 x = (u64)R0 + k * (u64)Tr;
+            Q = add128(add128(Q0, mul128_64(Tq, k)), mk128(x / n32, 0)); R = (unsigned int)(x % n32);
+            if (lt128(Q, S)) {
+                do { k++; Q = add128(Q, Tq); R += Tr; if (R >= n32) { R -= n32; Q = add128(Q, mk128(1, 0)); } } while (lt128(Q, S));
+            } else {
+                while (k > 0) {
+                    x = (u64)R0 + (k - 1) * (u64)Tr;
+                    u128 Qp = add128(add128(Q0, mul128_64(Tq, k - 1)), mk128(x / n32, 0));
+                    if (lt128(Qp, S)) break;
+                    k--; Q = Qp; R = (unsigned int)(x % n32);
+                }
+            }
+        }
+        t = s_t0 + k;
+        tooth_inside = lt128(Q, add128(S, myX));
+    }
+    if (!__any_sync(0xffffffffu, tooth_inside)) {
+        // no tooth lands in this warp's particles: only kept candidates produce survivors (warp-uniform branch)
+        if (myKept == 0 || mode == 1) return;
+        for (int j = 0; j < c; j++) {
+            u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
+            if (bits >= thr) {
+                long long pos = kcount + (long long)t;
+                if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
+                kcount++;
+            }
+        }
+        return;
     }
     for (int j = 0; j < c; j++) {
         u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
@@ -566,7 +621,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                 if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
             }
             kcount++;
-        } else if (comb) {
+        } else {
             S = add128(S, fx70(bits, scale));
             while (lt128(Q, S)) {
                 long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
@@ -586,7 +641,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
 // Welford mean update + rank-1 Cholesky update, appends (ancestor, assignment) to the
 // genealogy and sets the normalised log-weight (src/fearnhead.jl:172-179).
 template <int D>
-__global__ void __launch_bounds__(256) k_instantiate(const double *__restrict__ S, const int *__restrict__ Kc,
+__global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const double *__restrict__ S, const int *__restrict__ Kc,
                                                      double *S2, int *Kc2,
                                                      double *logw2, long long cap,
                                                      const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,

@@ -36,6 +36,7 @@ struct pf_filter_s {
     TileFuse *tfuse = nullptr;
     long long fuse_stride = 1;
     bool fused = true;                    // single-GPU index-order Fearnhead: classify inside the expansion
+    int sel_margin = 8;                   // half-width of the sample bracket in sigmas (PF_SEL_MARGIN; tests shrink it)
     double *cand = nullptr;
     long long cand_cap = 0;
     SelScratch *sc = nullptr;
@@ -326,6 +327,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->tfuse, ntiles));
     h->fuse_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
     h->fused = getenv("PF_NO_FUSE") == nullptr;
+    h->sel_margin = getenv("PF_SEL_MARGIN") ? std::max(1, atoi(getenv("PF_SEL_MARGIN"))) : 8;
     CT(dmalloc(&h->sc, 1));
     CT(dmalloc(&h->res, 1));
     CT(dmalloc(&h->st, 1));
@@ -406,6 +408,7 @@ static int32_t launch_select(pf_handle h, const double *V, const unsigned char *
     SelArgs a;
     a.V = V; a.cnt = cnt; a.cap = cap; a.n_live = n_live; a.M = M; a.vmax_bits = vmax; a.N = N; a.u = u_dev;
     a.cand = cand; a.cand_cap = cand_cap; a.sc = sc; a.res = res;
+    a.margin = h->sel_margin;
     a.stage = stage; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr; a.pad_to = -1;
     a.fixed_stride = fixed_stride >= 0 ? fixed_stride : h->fuse_stride;       // the same strided sample on every path
     a.external_sample = external_sample; a.preclassified = preclassified;
@@ -1038,6 +1041,7 @@ extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done,
     a.V = h->V; a.cnt = h->cnt; a.cap = h->cap; a.n_live = &h->st->n_live;
     a.M = h->gscal; a.vmax_bits = (const u64 *)(h->gscal + 1);
     a.N = h->N; a.u = h->y1_dev + h->d; a.cand = h->cand; a.cand_cap = h->cand_cap; a.sc = h->sc; a.res = h->res;
+    a.margin = h->sel_margin;
     a.stage = stage; a.round0 = rounds_done; a.nranks = h->nranks; a.gacc = (const SelAcc *)gacc;
     a.glist = (const double *)glist; a.glist_each = list_each;
     a.goff = &h->st->goff; a.pad_to = pad_to; a.fixed_stride = h->mg_stride; a.external_sample = 0; a.preclassified = 0;

@@ -30,7 +30,9 @@ namespace cg = cooperative_groups;
 #define SEL_BINS 1024
 #define SEL_CHUNK 32
 #define SEL_SAMPLE_WARPS 1024         // sharded run: warps that gather the sample (bounds the list padding)
+#ifndef SEL_SAMPLE_TARGET
 #define SEL_SAMPLE_TARGET (1 << 20)
+#endif
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax
 #define SEL_SMEM_BYTES (SEL_BINS * 4 + 3 * SEL_BINS * 8)
@@ -71,7 +73,7 @@ struct SelScratch {
     int fuse_scale;                 // item scale the expansion used (= scale of the bracket)
     int fuse_tot_scale;             // scale of the kept-side total the expansion used
     int tot_scale_used;             // scale of the kept-side total of the current classify round
-    int pad2;
+    int n_fail;                     // bracket verifications that failed in this step (geometric widening, then open)
     int fuse_overflow;              // a block had more candidates than its staging buffer
     int need_tot;                   // the total weight of this step has not been computed yet
     int tiles_ok;                   // the survivor-scan tile records written by the expansion are usable
@@ -128,6 +130,7 @@ struct SelArgs {
     SelScratch *sc;
     SelResult *res;
     int stage;                      // SEL_ST_* bit mask
+    int margin;                     // half-width of the sample bracket in sigmas of the sampling error (8; tests shrink it)
     int round0;                     // number of classify rounds already done (sharded re-entry)
     int nranks;                     // > 1: accumulators / lists come gathered from all ranks
     const SelAcc *gacc;             // [nranks] gathered accumulator blocks
@@ -381,7 +384,7 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
         const long long cnt_found = (long long)pc[found] - (found > 0 ? (long long)pc[found - 1] : 0);
         if (sampling) {
             const long long above = A0 + (count_in - (long long)pc[found]) + cnt_found;
-            const long long delta = (long long)(8.0 * sqrt((double)(above > 1 ? above : 1))) + 32;
+            const long long delta = (long long)((double)sampling * sqrt((double)(above > 1 ? above : 1))) + 4 * sampling;   // `sampling` = margin in sigmas (8)
             if (cnt_found > 2 * delta && shift > 0) {
                 b_lo = found > 0 ? found - 1 : 0;
                 b_hi = found < last_bin ? found + 1 : last_bin;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
     if (blockIdx.x == 0 && tid == 0) {
         reset_round(sc);
         for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
-        res->rounds = 0; res->status = 0; res->n_cand_first = 0;
+        res->rounds = 0; res->status = 0; res->n_cand_first = 0; sc->n_fail = 0;
         res->t_ns[0] = gtimer();
         sc->mult = 1; sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0; sc->vs_bits = 0;
         if (multi) {               // sharded: the global M is not known yet; decided at the BRACKET stage
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             const long long ns = sc->list_n;
             reset_round(sc);
             for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
-            res->rounds = 0; res->status = 0; res->n_cand_first = 0;
+            res->rounds = 0; res->status = 0; res->n_cand_first = 0; sc->n_fail = 0;
             res->t_ns[0] = gtimer();
             sc->mult = 1; sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0;
             sc->n_cand = (unsigned long long)ns; sc->list_n = ns; sc->list_exact = 1; sc->vs_bits = vmax;     // (vmax = the sample's maximum here)
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
             hist_level(list, list_n, blo, bhi, shift, ss, sc, smem_raw);
             grid.sync();
-            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, ss, 1, smem_raw);
+            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, ss, a.margin > 0 ? a.margin : 8, smem_raw);
             grid.sync();
             if (sc->phase == 6) break;
         }
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             u64 lo = sc->lo, hi = sc->hi;
             if (lo < 1) lo = 1;
             if (hi <= lo) hi = lo + 1;
-            sc->lo = lo; sc->hi = hi; sc->mode = 0; sc->mult = 1;
+            sc->lo = lo; sc->hi = hi; sc->mode = 0; sc->mult = 1; sc->n_fail = 0;
             sc->scale = SEL_ITEM_BITS - exp_of_bits(hi >= PF_INF_BITS ? vmax : hi);
             reset_round(sc);
             for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
@@ -708,7 +711,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(add128(B, Sc), Pm), N, Ahi, fx70(hi, scale));
                 if (fail_lo || fail_hi) {
                     res->status |= fail_lo ? 8 : 16;
-                    u64 nlo = fail_lo ? 1ull : lo, nhi = fail_hi ? PF_INF_BITS : hi;
+                    // the sample missed by more than its margin: move the bracket to the failing side and
+                    // make it 8x wider (64x the second time); the third failure opens it completely
+                    const int nf = ++sc->n_fail;
+                    const u64 w = hi - lo;
+                    const bool bounded = nf <= 2 && hi < PF_INF_BITS && lo > 1 && w < (1ull << 56);
+                    const u64 grow = bounded ? w << 3 : 0;
+                    u64 nlo, nhi;
+                    if (fail_hi) { nlo = hi; nhi = (bounded && hi + grow < PF_INF_BITS) ? hi + grow : PF_INF_BITS; }
+                    else { nhi = lo; nlo = (bounded && lo > grow + 1) ? lo - grow : 1ull; }
                     sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
                     sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
                     reset_round(sc);

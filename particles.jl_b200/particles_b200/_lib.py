@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libparticles_b200.so")
+LIB_PATH = os.environ.get("PARTICLES_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libparticles_b200.so")
 
 PF_OK, PF_ERR_ARG, PF_ERR_CUDA, PF_ERR_STATE, PF_ERR_HISTORY, PF_ERR_OVERFLOW, PF_ERR_NCCL = range(7)
 PF_FEARNHEAD, PF_CHENLIU = 0, 1

@@ -10,7 +10,7 @@ mkdir -p $OUT
 # tile_fixup, tile_sums (skipped when the fused records are usable), tile_prefix, scan_apply, instantiate, steplog
 $CMD > $OUT/ncu_plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 539 -c 44 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
-for K in k_expandILi2ELi2 k_instantiate k_scan_apply k_tile_prefix; do
+for K in ${KERNELS:-k_expandILi2ELi2 k_instantiate k_scan_apply k_select}; do
   ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$K -s 50 -c 1 -f -o $OUT/prof_${TAG}_$K $CMD > $OUT/ncu_full_${TAG}_$K.log 2>&1
 done
 ls -la $OUT | grep $TAG

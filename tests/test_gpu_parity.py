@@ -303,3 +303,31 @@ def test_properties_at_2_pow_18():
     ps2.filter_(ys)
     assert np.array_equal(ps2.logweights(), lw)
     assert np.array_equal(ps2.assignments(), A)
+
+
+@pytest.mark.parametrize("margin", [1])
+def test_failed_bracket_is_widened_not_opened(margin, monkeypatch):
+    """A sample bracket that misses the threshold (forced here by shrinking its margin from 8 sigma
+    to 1-2) is moved to the failing side and widened geometrically; decisions are those of the
+    default run, the total weight agrees to rounding (a different bracket splits it differently)."""
+    rng = np.random.default_rng(77)
+    N, T = 1 << 17, 30
+    ys = _mixture_nd(rng, T, 2, 8)
+    us = rng.random(T)
+    prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
+    ref = pb.FearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), history=T)
+    ref.filter_(ys, uniforms=us)
+    monkeypatch.setenv("PF_SEL_MARGIN", str(margin))
+    ps = pb.FearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), history=T)
+    rounds = []
+    for t in range(T):
+        ps.filter_(ys[t:t + 1], uniforms=us[t:t + 1])
+        rounds.append(ps.last_step()["select_rounds"])
+    assert max(rounds) >= 2                      # the verification did fail somewhere
+    assert np.array_equal(ps.ncomponents(), ref.ncomponents())
+    assert np.array_equal(ps.assignments(), ref.assignments())
+    np.testing.assert_allclose(ps.logweights(), ref.logweights(), rtol=0, atol=1e-12)
+    # and the stand-alone selection against the exact oracle
+    w = np.exp(rng.standard_normal(300_000) * 3.0)
+    for order in (pb.PF_ORDER_INDEX, pb.PF_ORDER_SORTED):
+        _check_select(w, 40_000, rng.random(), order)
