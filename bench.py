@@ -104,6 +104,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json; bench.py cannot run ncu)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return float(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        return None, "no committed ncu capture for this kernel"
+
+
 def cpu_leg(n_cpu, burn, timed, seed=100):
     """The reference's CPU path (the literal C restatement in oracle/, 1 thread because
     the reference is single-threaded) on a bounded sample of the same workload."""
@@ -223,7 +234,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=24, help="log2 of the TOTAL particle budget")
     ap.add_argument("--burnin", type=int, default=96)
     ap.add_argument("--cpu-n", type=int, default=16384)
-    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--order", default="index", choices=["index", "sorted"])
     ap.add_argument("--lookahead", type=int, default=10, help="sharded run: observations queued per host synchronisation")
@@ -243,9 +254,9 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        cb = cpu_leg(a.cpu_n, 48, max(K, 1) * 2)
+        cb = cpu_leg(a.cpu_n, 48, max(K, 1) * 15)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": K,
-                "warmup": W, "ms_per_step": 1e3 * cb["seconds"] / (max(K, 1) * 2), "higher_is_better": True,
+                "warmup": W, "ms_per_step": 1e3 * cb["seconds"] / (max(K, 1) * 15), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -317,8 +328,10 @@ def main():
             per_kernel[name] = {"avg_ms": avg, "share": ms / prof_ms, "alg_bytes_per_launch": kb[name] * n_live0,
                                 "achieved_gbs": kb[name] * n_live0 / (avg * 1e-3) / 1e9}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
+    traffic, traffic_src = ncu_traffic("k_" + dom)
     roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": per_kernel[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": per_kernel[dom]["achieved_gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
             "avg_launch_ms": per_kernel[dom]["avg_ms"], "share_of_step": per_kernel[dom]["share"],
             "algorithmic_bytes_per_update": kb[dom], "per_kernel": per_kernel,
             "whole_step": {"algorithmic_bytes_per_update": bytes_per_update(kbar),
