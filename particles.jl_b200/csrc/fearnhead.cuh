@@ -100,6 +100,14 @@ struct TileSum {           // survivor-scan record of one tile of SCAN_THREADS p
 struct TileFuse {
     unsigned int cand_off, cand_cnt, n_plateau, pad;
 };
+// Per-particle record of the fused expansion for the survivor scan (optional): the fixed-point mass of
+// the particle's putatives below the bracket, and a word with the slots that fell INSIDE the bracket
+// (bits 0..23, candidates and plateau copies) and the number of putatives above it (bits 24..31).
+// k_scan_apply then needs V only for the in-bracket slots when it forms the particle's (mass, kept) pair.
+struct ScanRec {
+    ulonglong2 *x;
+    unsigned int *m;
+};
 
 #ifndef PF_EXPAND_MINBLOCKS
 #define PF_EXPAND_MINBLOCKS 4
@@ -114,7 +122,8 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
                                                 const StepConst *__restrict__ scp, StepState *st,
                                                 double *__restrict__ V, unsigned char *__restrict__ cnt,
                                                 SelScratch *sc, long long stride, double *__restrict__ list,
-                                                TileSum *__restrict__ tiles, TileFuse *__restrict__ tfuse)
+                                                TileSum *__restrict__ tiles, TileFuse *__restrict__ tfuse,
+                                                ScanRec rec = ScanRec{nullptr, nullptr})
 {
     using L = Layout<D>;
     if (MODE == 0 && sc && sc->halt) return;
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
     u64 vmax = 0;
     long long myM = 0, myOvf = 0;
     u128 B_lo = mk128(0, 0), Tot = mk128(0, 0);
-    unsigned int kept_hi = 0, n_plat = 0;
+    unsigned int kept_hi = 0, n_plat = 0, in_mask = 0;
     const u64 plateau = scp->plateau_bits;
     // what happens to one putative weight
     auto emit = [&](int j, double v) {
@@ -160,9 +169,11 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
                 B_lo = add128(B_lo, fx70(b, scale));
             } else if (b == plateau) {
                 n_plat++;                                          // the mass tie: counted, not listed
+                in_mask |= 1u << (j & 31);
             } else {
                 unsigned int pos = atomicAdd(&s_ncand, 1u);
                 if (pos < CAND_CAP) s_cand[pos] = b;
+                in_mask |= 1u << (j & 31);
             }
         }
     };
@@ -179,16 +190,19 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
 #pragma unroll
             for (int f = 0; f < L::F; f++) fcur[f] = base[(long long)f * cap];
         }
+        auto eval = [&](const double *fl, int j) {
+            double z[D], q;
+            const NRow row = tab[(int)fl[L::F_N]];
+            double lw = lw0 + slot_logw<D>(row, fl[L::F_LOGDET], fl + L::F_MEAN, fl + L::F_DINV, fl + L::F_OFF, y, mu0, z, &q);
+            emit(j, exp(lw));
+        };
         for (int j = 0; j < K; j++) {
             if (j + 1 < K) {
                 const double *base = S + ((long long)(j + 1) * L::F) * cap + i;
 #pragma unroll
                 for (int f = 0; f < L::F; f++) fnxt[f] = base[(long long)f * cap];
             }
-            double z[D], q;
-            const NRow row = tab[(int)fcur[L::F_N]];
-            double lw = lw0 + slot_logw<D>(row, fcur[L::F_LOGDET], fcur + L::F_MEAN, fcur + L::F_DINV, fcur + L::F_OFF, y, mu0, z, &q);
-            emit(j, exp(lw));
+            eval(fcur, j);
 #pragma unroll
             for (int f = 0; f < L::F; f++) fcur[f] = fnxt[f];
         }
@@ -197,6 +211,10 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
         else myOvf = 1;
         if (MODE != 1) cnt[i] = (unsigned char)c;
         myM = c;
+        if (MODE == 2 && fused && rec.x) {
+            rec.x[i] = make_ulonglong2(B_lo.lo, B_lo.hi);
+            rec.m[i] = in_mask | (kept_hi << 24);
+        }
     }
     // ---- block epilogue
     vmax = warp_max64(vmax);
@@ -514,7 +532,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                                                              const TileSum *__restrict__ tiles, unsigned int *__restrict__ surv_parent,
                                                              unsigned char *__restrict__ surv_slot, int mode,
                                                              const RankOff *__restrict__ ro, const SelScratch *guard,
-                                                             long long surv_cap)
+                                                             long long surv_cap, ScanRec rec = ScanRec{nullptr, nullptr},
+                                                             const SelScratch *recsc = nullptr)
 {
     if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
@@ -550,7 +569,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
         }
     }
     u128 myX; unsigned int myKept;
-    thread_sums(V, cap, i, c, thr, scale, comb, myX, myKept);
+    if (rec.x && recsc->tiles_ok) {
+        // the fused expansion left (mass below the bracket, in-bracket slots, count above the bracket):
+        // only the in-bracket slots (~0.5 % of all putatives) are read again
+        myX = mk128(0, 0); myKept = 0;
+        if (c) {
+            const ulonglong2 x = rec.x[i];
+            unsigned int m = rec.m[i];
+            myKept = m >> 24; m &= 0xFFFFFFu;
+            if (comb) myX = mk128(x.x, x.y);
+            while (m) {
+                const int j = __ffs(m) - 1; m &= m - 1;
+                const u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
+                if (bits >= thr) myKept++;
+                else if (comb) myX = add128(myX, fx70(bits, scale));
+            }
+        }
+    } else {
+        thread_sums(V, cap, i, c, thr, scale, comb, myX, myKept);
+    }
     u128 totX;
     u128 exX = block_excl_scan128(myX, s_warp, &totX);
     unsigned int incK = myKept;

@@ -34,6 +34,7 @@ struct pf_filter_s {
     unsigned char *surv_slot = nullptr;
     TileSum *tiles = nullptr;
     TileFuse *tfuse = nullptr;
+    ScanRec srec = ScanRec{nullptr, nullptr};   // per-particle scan records of the fused expansion (PF_SCAN_REC)
     long long fuse_stride = 1;
     bool fused = true;                    // single-GPU index-order Fearnhead: classify inside the expansion
     int sel_margin = 8;                   // half-width of the sample bracket in sigmas (PF_SEL_MARGIN; tests shrink it)
@@ -223,7 +224,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->gscal, h->local_tot, h->ro, h->sendbuf,
-                    h->recvbuf, h->y1_dev, h->peers[0], h->peers[1]};
+                    h->recvbuf, h->y1_dev, h->peers[0], h->peers[1], h->srec.x, h->srec.m};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->y1_pin) cudaFreeHost(h->y1_pin);
@@ -325,6 +326,11 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     }
     CT(dmalloc(&h->tiles, ntiles));
     CT(dmalloc(&h->tfuse, ntiles));
+    // optional per-particle scan records (a record has 24 slot bits)
+    if (getenv("PF_SCAN_REC") && atoi(getenv("PF_SCAN_REC")) && h->nranks <= 1 && h->k_max + 1 <= 24) {
+        CT(dmalloc(&h->srec.x, (size_t)h->cap));
+        CT(dmalloc(&h->srec.m, (size_t)h->cap));
+    }
     h->fuse_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
     h->fused = getenv("PF_NO_FUSE") == nullptr;
     h->sel_margin = getenv("PF_SEL_MARGIN") ? std::max(1, atoi(getenv("PF_SEL_MARGIN"))) : 8;
@@ -453,7 +459,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         {
             LaunchTimer lt(h, KC_EXPAND);
             k_expand<D, 2><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                       h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse);
+                                                                       h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
         }
         {
             LaunchTimer lt(h, KC_SELECT);
@@ -503,7 +509,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, nullptr, fused ? h->sc : nullptr);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, nullptr);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 0, nullptr, nullptr, cap);
+                                                            h->surv_slot, 0, nullptr, nullptr, cap, fused ? h->srec : ScanRec{nullptr, nullptr}, h->sc);
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);

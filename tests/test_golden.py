@@ -97,7 +97,7 @@ def test_device_reproduces_fearnhead_fixture(name):
     T = len(g["ys"])
     order = pb.PF_ORDER_SORTED if int(g["order"]) == orc.ORDER_SORTED else pb.PF_ORDER_INDEX
     ps = pb.FearnheadParticles(int(g["N"]), _device_prior(pb, g), pb.ChineseRestaurantProcess(float(g["alpha"])),
-                               history=T, order=order)
+                               history=T, order=order, k_max=40)      # (the reference's component vector is unbounded)
     anc, asg, counts = [], [], []
     for y, u in zip(g["ys"], g["uniforms"]):
         ps.fit_(y, [u])
