@@ -202,6 +202,18 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     ps.filter_(ys[o:o + 8], us[o:o + 8], lookahead=a.lookahead); o += 8
     stage_ms = ps.profile_summary()
     ps.profile = None
+    # per-rank view (every rank contributes, rank 0 prints): stage timeline and the survivors this
+    # rank produced in the last step (the producer instantiates, so their spread is the tail's skew)
+    try:
+        mine = {"rank": rank, "n_local_last": int(ps.shards[0].plan(world)[2]),
+                "stage_ms": {k: round(v[0], 4) for k, v in stage_ms.items()}}
+    except Exception as e:                                   # diagnostics must never cost the line
+        mine = {"rank": rank, "error": str(e)[:200]}
+    by_rank = [None] * world
+    try:
+        dist.all_gather_object(by_rank, mine)
+    except Exception as e:
+        by_rank = [{"error": str(e)[:200]}]
     if rank != 0:
         return 0
     sampler.join(timeout=2)
@@ -213,7 +225,8 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
             "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0,
                                                 host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K,
                                                 slow_path_steps=ps.slow_steps, exchanges=ps.exchanges, lookahead=a.lookahead, halts=ps.halts[-12:],
-                                                stage_ms_device_host={k: [round(v[0], 4), round(v[1], 4)] for k, v in stage_ms.items()}),
+                                                stage_ms_device_host={k: [round(v[0], 4), round(v[1], 4)] for k, v in stage_ms.items()},
+                                                by_rank=by_rank),
             "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
                     "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le)},
             "gpu_launches": int(l1.value - l0.value) * world,
