@@ -133,6 +133,55 @@ __host__ __device__ inline u64 teeth_below(u128 X, u128 U, u128 T)
     return q + 1;
 }
 
+// ------------------------------------------------------------------ comb teeth in running-mass space
+// Tooth k of the systematic comb sits at U + k T (in units of 1/n of the fixed-point mass); it is
+// passed by a running mass S iff U + k T < n S iff Q_k < S with (Q_k, R_k) = divmod(U + k T, n).
+// From tooth to tooth (Q, R) steps by (Tq, Tr) = divmod(T, n).
+struct ToothBase {
+    u128 Q0;                 // quotient of the first tooth not passed by the tile's starting mass S0
+    unsigned int R0;         // its remainder
+    u64 t0;                  // its index = number of teeth passed by S0
+    double inv;              // n / T: teeth per unit of running mass (estimate only)
+};
+// once per tile (the one 128-bit division)
+__host__ __device__ inline ToothBase tooth_base(u128 S0, u64 n, u128 U, u128 T)
+{
+    ToothBase b;
+    b.t0 = teeth_below(mul128_64(S0, n), U, T);
+    b.Q0 = divmod128_32(add128(U, mul128_64(T, b.t0)), (unsigned int)n, &b.R0);
+    b.inv = (double)n / to_double128(T);
+    return b;
+}
+__host__ __device__ __forceinline__ void tooth_step(u128 &Q, unsigned int &R, u128 Tq, unsigned int Tr, unsigned int n32)
+{
+    Q = add128(Q, Tq);
+    R += Tr;
+    if (R >= n32) { R -= n32; Q = add128(Q, mk128(1, 0)); }
+}
+// number k of teeth of the tile passed by S >= S0 (so t0 + k teeth are passed in all), with (Q, R) of
+// tooth t0 + k: k from a floating-point estimate, corrected exactly in both directions
+__host__ __device__ __forceinline__ u64 tooth_seek(u128 Q0, unsigned int R0, double inv, u128 S, u128 Tq, unsigned int Tr,
+                                                   unsigned int n32, u128 &Q, unsigned int &R)
+{
+    u64 k = 0; Q = Q0; R = R0;
+    if (lt128(Q0, S)) {
+        k = (u64)(to_double128(sub128(S, Q0)) * inv);
+        u64 x = (u64)R0 + k * (u64)Tr;
+        Q = add128(add128(Q0, mul128_64(Tq, k)), mk128(x / n32, 0)); R = (unsigned int)(x % n32);
+        if (lt128(Q, S)) {
+            do { k++; tooth_step(Q, R, Tq, Tr, n32); } while (lt128(Q, S));
+        } else {
+            while (k > 0) {
+                x = (u64)R0 + (k - 1) * (u64)Tr;
+                u128 Qp = add128(add128(Q0, mul128_64(Tq, k - 1)), mk128(x / n32, 0));
+                if (lt128(Qp, S)) break;
+                k--; Q = Qp; R = (unsigned int)(x % n32);
+            }
+        }
+    }
+    return k;
+}
+
 // ------------------------------------------------------------------ warp / block helpers
 __device__ __forceinline__ u128 shfl_up128(u128 v, int d)
 {

@@ -561,11 +561,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
         if (ro) { S0 = add128(S0, ro->S_off); k0 += ro->kept_off - ro->g_first; }   // positions relative to this rank's first survivor
         s_S0 = S0; s_k0 = k0;
         if (comb) {
-            const u64 t0 = teeth_below(mul128_64(S0, n), U, T);
-            unsigned int R0;
-            s_Q0 = divmod128_32(add128(U, mul128_64(T, t0)), (unsigned int)n, &R0);
-            s_R0 = R0; s_t0 = t0;
-            s_inv = (double)n / to_double128(T);
+            const ToothBase b = tooth_base(S0, n, U, T);
+            s_Q0 = b.Q0; s_R0 = b.R0; s_t0 = b.t0; s_inv = b.inv;
         }
     }
     u128 myX; unsigned int myKept;
@@ -617,24 +614,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
     const u128 Tq = res->Tq;
     bool tooth_inside = false;
     if (comb) {
-        const u128 Q0 = s_Q0; const unsigned int R0 = s_R0;
-        u64 k = 0; Q = Q0; R = R0;
-        if (lt128(Q0, S)) {
-            k = (u64)(to_double128(sub128(S, Q0)) * s_inv);
-            u64 x = (u64)R0 + k * (u64)Tr;
-            Q = add128(add128(Q0, mul128_64(Tq, k)), mk128(x / n32, 0)); R = (unsigned int)(x % n32);
-            if (lt128(Q, S)) {
-                do { k++; Q = add128(Q, Tq); R += Tr; if (R >= n32) { R -= n32; Q = add128(Q, mk128(1, 0)); } } while (lt128(Q, S));
-            } else {
-                while (k > 0) {
-                    x = (u64)R0 + (k - 1) * (u64)Tr;
-                    u128 Qp = add128(add128(Q0, mul128_64(Tq, k - 1)), mk128(x / n32, 0));
-                    if (lt128(Qp, S)) break;
-                    k--; Q = Qp; R = (unsigned int)(x % n32);
-                }
-            }
-        }
-        t = s_t0 + k;
+        t = s_t0 + tooth_seek(s_Q0, s_R0, s_inv, S, Tq, Tr, n32, Q, R);
         tooth_inside = lt128(Q, add128(S, myX));
     }
     if (!__any_sync(0xffffffffu, tooth_inside)) {
@@ -664,9 +644,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                 long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
                 if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)(j | 0x80); }
                 t++;
-                Q = add128(Q, Tq);
-                R += Tr;
-                if (R >= n32) { R -= n32; Q = add128(Q, mk128(1, 0)); }
+                tooth_step(Q, R, Tq, Tr, n32);
             }
         }
     }

@@ -1,0 +1,65 @@
+// Host-side harness for the __host__ __device__ integer arithmetic of csrc/common.cuh: the same
+// source the kernels compile, built for the CPU so that tests/test_host_arith.py can check it
+// against Python's exact integers without a GPU.  Test infrastructure only.
+#include "../../particles.jl_b200/csrc/common.cuh"
+
+extern "C" {
+
+void h_fx128(u64 bits, int s, u64 *out) { u128 r = fx128(bits, s); out[0] = r.lo; out[1] = r.hi; }
+void h_fx70(u64 bits, int s, u64 *out) { u128 r = fx70(bits, s); out[0] = r.lo; out[1] = r.hi; }
+void h_divmod128_32(u64 lo, u64 hi, unsigned int n, u64 *out)
+{
+    unsigned int rem;
+    u128 q = divmod128_32(mk128(lo, hi), n, &rem);
+    out[0] = q.lo; out[1] = q.hi; out[2] = rem;
+}
+u64 h_teeth_below(const u64 *X, const u64 *U, const u64 *T) { return teeth_below(mk128(X[0], X[1]), mk128(U[0], U[1]), mk128(T[0], T[1])); }
+void h_mul128_64(u64 lo, u64 hi, u64 b, u64 *out) { u128 r = mul128_64(mk128(lo, hi), b); out[0] = r.lo; out[1] = r.hi; }
+double h_to_double128(u64 lo, u64 hi) { return to_double128(mk128(lo, hi)); }
+int h_exp_of_bits(u64 bits) { return exp_of_bits(bits); }
+void h_shift128(u64 lo, u64 hi, int s, u64 *out)
+{
+    u128 l = shl128(mk128(lo, hi), s), r = shr128(mk128(lo, hi), s);
+    out[0] = l.lo; out[1] = l.hi; out[2] = r.lo; out[3] = r.hi;
+}
+
+// The survivor scan's comb (k_scan_apply) on the host: `m` items with fixed-point masses q (lo, hi)
+// and a kept flag, traversed in order; tiles of `tile` items, threads of `per` items each.  Every
+// tile starts from its exclusive prefix through tooth_base, every thread through tooth_seek, items
+// step with tooth_step -- the kernel's code path.  Writes for each item the number of comb teeth it
+// receives (0/1 for a valid comb) and the index t of its first tooth; returns the total.
+long long h_comb(const u64 *qlo, const u64 *qhi, const unsigned char *kept, long long m, u64 n, const u64 *Uv, const u64 *Tv,
+                 long long tile, long long per, unsigned char *copies, long long *first_tooth, double inv_scale)
+{
+    const u128 U = mk128(Uv[0], Uv[1]), T = mk128(Tv[0], Tv[1]);
+    unsigned int Tr;
+    const u128 Tq = divmod128_32(T, (unsigned int)n, &Tr);
+    const unsigned int n32 = (unsigned int)n;
+    u128 run = mk128(0, 0);                       // exclusive prefix of the low masses
+    long long total = 0;
+    for (long long t0 = 0; t0 < m; t0 += tile) {
+        ToothBase b = tooth_base(run, n, U, T);
+        b.inv *= inv_scale;            // tests: a wrong estimate must be corrected exactly, in either direction
+        u128 S_thread = run;
+        for (long long a = t0; a < t0 + tile && a < m; a += per) {
+            u128 Q; unsigned int R;
+            u128 S = S_thread;
+            u64 t = b.t0 + tooth_seek(b.Q0, b.R0, b.inv, S, Tq, Tr, n32, Q, R);
+            for (long long i = a; i < a + per && i < t0 + tile && i < m; i++) {
+                copies[i] = 0; first_tooth[i] = -1;
+                if (kept[i]) continue;
+                S = add128(S, mk128(qlo[i], qhi[i]));
+                while (lt128(Q, S)) {
+                    if (!copies[i]) first_tooth[i] = (long long)t;
+                    copies[i]++; total++; t++;
+                    tooth_step(Q, R, Tq, Tr, n32);
+                }
+            }
+            S_thread = S;
+        }
+        run = S_thread;
+    }
+    return total;
+}
+
+}
