@@ -26,6 +26,22 @@ struct __align__(32) NRow {
     double C, r, h, g;
 };
 
+#include <math.h>
+// one table row, computed on the host in long double (the terms that depend on the integer count only)
+static inline NRow make_nrow(double kappa0, double nu0, double alpha, int dim, long long n)
+{
+    const long double LOGPI_L = 1.1447298858494001741434273513530587116473L;
+    long double k0 = kappa0, d = dim;
+    long double kn = k0 + n, nn = (long double)nu0 + n;
+    long double h = (nn + 1.0L) / 2.0L;
+    long double r = kn / (kn + 1.0L);
+    long double lp = n == 0 ? logl((long double)alpha) : logl((long double)n);
+    long double C = lp + lgammal(h) - lgammal(h - d / 2.0L) - d / 2.0L * LOGPI_L + d / 2.0L * logl(r);
+    NRow row;
+    row.C = (double)C; row.r = (double)r; row.h = (double)h; row.g = (double)((long double)n / kn);
+    return row;
+}
+
 template <int D>
 struct Layout {
     static constexpr int F = 2 + D + D * (D + 1) / 2;
@@ -54,7 +70,7 @@ struct PriorConst {
 
 // z = L^{-1} dx (forward substitution), returns |z|^2
 template <int D>
-__device__ __forceinline__ double quad_form(const double *dx, const double *dinv, const double *off, double *z)
+__host__ __device__ __forceinline__ double quad_form(const double *dx, const double *dinv, const double *off, double *z)
 {
     double q = 0.0;
     int o = 0;
@@ -73,7 +89,7 @@ __device__ __forceinline__ double quad_form(const double *dx, const double *dinv
 // Rank-1 update of the lower Cholesky factor: L L' + x x'  (x is overwritten).
 // Works on (1/L_ii, strict lower) storage; returns nothing, logdet handled by the caller.
 template <int D>
-__device__ __forceinline__ void chol_rank1(double *dinv, double *off, double *x)
+__host__ __device__ __forceinline__ void chol_rank1(double *dinv, double *off, double *x)
 {
 #pragma unroll
     for (int k = 0; k < D; k++) {
@@ -98,7 +114,7 @@ __device__ __forceinline__ void chol_rank1(double *dinv, double *off, double *x)
 // (src/component.jl:18-23 in the form of SURVEY 8(a4); equals mll(add(c,y)) - mll(c) of
 // src/particle.jl:104-112 plus log_prior of src/statepriors.jl:65-66).
 template <int D>
-__device__ __forceinline__ double slot_logw(const NRow &row, double logdet, const double *m, const double *dinv,
+__host__ __device__ __forceinline__ double slot_logw(const NRow &row, double logdet, const double *m, const double *dinv,
                                             const double *off, const double *y, const double *mu0, double *z_out,
                                             double *q_out)
 {

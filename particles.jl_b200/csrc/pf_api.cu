@@ -153,19 +153,9 @@ static void collect_profile(pf_handle h)
 }
 
 // ------------------------------------------------------------------ host-side model setup
-static const long double LOGPI_L = 1.1447298858494001741434273513530587116473L;
-
 static NRow make_row(const pf_filter_s *f, long long n)
 {
-    long double k0 = f->cfg.kappa0, nu0 = f->cfg.nu0, d = f->d;
-    long double kn = k0 + n, nn = nu0 + n;
-    long double h = (nn + 1.0L) / 2.0L;
-    long double r = kn / (kn + 1.0L);
-    long double lp = n == 0 ? logl((long double)f->cfg.alpha) : logl((long double)n);
-    long double C = lp + lgammal(h) - lgammal(h - d / 2.0L) - d / 2.0L * LOGPI_L + d / 2.0L * logl(r);
-    NRow row;
-    row.C = (double)C; row.r = (double)r; row.h = (double)h; row.g = (double)((long double)n / kn);
-    return row;
+    return make_nrow(f->cfg.kappa0, f->cfg.nu0, f->cfg.alpha, f->d, n);
 }
 
 static int32_t ensure_table(pf_handle h, long long need)
