@@ -1,7 +1,7 @@
 """Diagnostic: first step at which the device (sorted order) and the oracle disagree on a golden fixture."""
 import os, sys
 import numpy as np
-R = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+R = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, os.path.join(R, "particles.jl_b200")); sys.path.insert(0, R)
 import particles_b200 as pb
 from oracle import oracle as orc

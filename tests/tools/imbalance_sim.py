@@ -3,7 +3,7 @@ population re-partitioned into G equal blocks every step, how many survivors doe
 produce in the next step?  max over ranks / mean is the skew the exchange barrier waits for."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import oracle as orc
 from bench import mixture
 
