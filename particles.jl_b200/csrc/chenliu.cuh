@@ -18,24 +18,6 @@ struct ClState {
     long long n_resampled_steps;
 };
 
-// 128 x 128 -> 256 bit product, little-endian limbs
-__host__ __device__ __forceinline__ void mul128x128(u128 a, u128 b, u64 o[4])
-{
-    u64 p00l = a.lo * b.lo, p00h = mulhi64(a.lo, b.lo);
-    u64 p01l = a.lo * b.hi, p01h = mulhi64(a.lo, b.hi);
-    u64 p10l = a.hi * b.lo, p10h = mulhi64(a.hi, b.lo);
-    u64 p11l = a.hi * b.hi, p11h = mulhi64(a.hi, b.hi);
-    o[0] = p00l;
-    u64 c = 0, s = p00h + p01l; c += s < p00h; u64 s2 = s + p10l; c += s2 < s; o[1] = s2;
-    u64 c2 = 0; s = p01h + p10h; c2 += s < p01h; s2 = s + p11l; c2 += s2 < s; u64 s3 = s2 + c; c2 += s3 < s2; o[2] = s3;
-    o[3] = p11h + c2;
-}
-__host__ __device__ __forceinline__ bool gt256(const u64 a[4], const u64 b[4])
-{
-    for (int k = 3; k >= 0; k--) { if (a[k] != b[k]) return a[k] > b[k]; }
-    return false;
-}
-
 // ------------------------------------------------------------------ k_cl_propagate
 template <int D>
 __global__ void __launch_bounds__(256) k_cl_propagate(double *S0, double *S1, const double *__restrict__ logw0,

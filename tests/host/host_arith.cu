@@ -23,6 +23,15 @@ void h_shift128(u64 lo, u64 hi, int s, u64 *out)
     out[0] = l.lo; out[1] = l.hi; out[2] = r.lo; out[3] = r.hi;
 }
 
+int h_mul_gt256(const u64 *a, const u64 *b, const u64 *c, const u64 *d, u64 *prod)
+{
+    u64 x[4], y[4];
+    mul128x128(mk128(a[0], a[1]), mk128(b[0], b[1]), x);
+    mul128x128(mk128(c[0], c[1]), mk128(d[0], d[1]), y);
+    for (int k = 0; k < 4; k++) prod[k] = x[k];
+    return gt256(x, y) ? 1 : 0;
+}
+
 // The survivor scan's comb (k_scan_apply) on the host: `m` items with fixed-point masses q (lo, hi)
 // and a kept flag, traversed in order; tiles of `tile` items, threads of `per` items each.  Every
 // tile starts from its exclusive prefix through tooth_base, every thread through tooth_seek, items

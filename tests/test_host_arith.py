@@ -89,6 +89,19 @@ def test_shifts_multiply_divide(H):
         assert abs(Fraction(d) - a) <= Fraction(a, 1 << 52)
 
 
+def test_256_bit_product_and_compare(H):
+    # Chen-Liu rejuvenation: cum[mid] * (N 2^53) > (i 2^53 + mu) * Qtot decided in 256 bits
+    import random
+    rnd = random.Random(3)
+    prod = (U64 * 4)()
+    for _ in range(2000):
+        a, b, c, d = (rnd.getrandbits(rnd.choice((20, 64, 100, 128))) for _ in range(4))
+        got = H.h_mul_gt256(_pair(a), _pair(b), _pair(c), _pair(d), prod)
+        assert sum(int(prod[k]) << (64 * k) for k in range(4)) == a * b
+        assert got == (1 if a * b > c * d else 0)
+    assert H.h_mul_gt256(_pair(7), _pair(9), _pair(9), _pair(7), prod) == 0      # equal products are not greater
+
+
 def _teeth_below(X, U, T):
     return 0 if X <= U else (X - U - 1) // T + 1
 
