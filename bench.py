@@ -37,7 +37,14 @@ for p in (ROOT, os.path.join(ROOT, "particles.jl_b200")):
 METRIC = "particle_obs_updates_per_sec"
 UNIT = "updates/s"
 D = 2
-K_MAX = 16
+K_MAX = 24
+T_MAX = 1024         # ONE synthetic stream for every arm (N = 1, N > 1, CPU): observation t is the same everywhere
+SEED = 100           # echoes bench/2d.jl:12
+
+
+def stream():
+    rng = np.random.default_rng(SEED)
+    return mixture(rng, T_MAX), rng.random(T_MAX)
 
 
 def mixture(rng, T, k=8, radius=6.0):
@@ -119,9 +126,8 @@ def cpu_leg(n_cpu, burn, timed, seed=100):
     """The reference's CPU path (the literal C restatement in oracle/, 1 thread because
     the reference is single-threaded) on a bounded sample of the same workload."""
     from oracle import oracle as orc
-    rng = np.random.default_rng(seed)
-    ys = mixture(rng, burn + timed)
-    us = rng.random(burn + timed)
+    ys, us = stream()
+    assert burn + timed <= T_MAX
     f = orc.OracleFilter(orc.FEARNHEAD, n_cpu, orc.Prior.niw(np.zeros(2), 0.1, np.eye(2), 3.0), 1.0,
                          order=orc.ORDER_SORTED, keep_history=False)
     for t in range(burn):
@@ -154,10 +160,8 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     import particles_b200 as pb
     from particles_b200.distributed import ShardedFearnheadParticles, TorchComm
     dev = torch.device("cuda", local)
-    rng = np.random.default_rng(100)
-    T_all = a.burnin + W + 2 * K + 8
-    ys = mixture(rng, T_all)
-    us = rng.random(T_all)
+    ys, us = stream()
+    assert a.burnin + W + 2 * K + 8 <= T_MAX
     ps = ShardedFearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
                                    pb.ChineseRestaurantProcess(1.0), TorchComm(), k_max=K_MAX, history=0, devices=[local])
     o = 0
@@ -250,6 +254,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--order", default="index", choices=["index", "sorted"])
+    ap.add_argument("--k-max", type=int, default=K_MAX, help="cluster slots per particle (the line fails if a candidate was dropped)")
+    ap.add_argument("--allow-overflow", action="store_true")
     ap.add_argument("--lookahead", type=int, default=10, help="sharded run: observations queued per host synchronisation")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
@@ -259,7 +265,7 @@ def main():
     N = 1 << a.log2n
     config = {"workload": f"2-D NIW Fearnhead filter, 2^{a.log2n} particles, 8-cluster synthetic mixture "
                           f"(BASELINE configs[3]); inputs >> L2 (particle store {N * 8 * rec_bytes(D) / 1e9:.1f} GB at K=8)",
-              "n_particles": N, "d": D, "k_max": K_MAX, "prior": "NIW(0, 0.1, I, 3)", "alpha": 1.0,
+              "n_particles": N, "d": D, "k_max": a.k_max, "prior": "NIW(0, 0.1, I, 3)", "alpha": 1.0,
               "burnin_obs": a.burnin, "order": a.order, "sharding": f"particles block-sharded over {a.gpus} GPU(s)",
               "l2_policy": "inputs larger than L2"}
 
@@ -283,7 +289,6 @@ def main():
     import particles_b200 as pb
     dist = None
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)              # NCCL prints its version banner to stdout
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
@@ -292,13 +297,13 @@ def main():
     if world > 1:
         return sharded_arm(a, dist, rank, world, local, N, K, W, config)
 
-    rng = np.random.default_rng(100)
+    ys, us = stream()
     T_all = a.burnin + W + 3 * K
-    ys = mixture(rng, T_all)
-    us = rng.random(T_all)
+    assert T_all <= T_MAX
     order = pb.PF_ORDER_INDEX if a.order == "index" else pb.PF_ORDER_SORTED
     ps = pb.FearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
-                               pb.ChineseRestaurantProcess(1.0), k_max=K_MAX, history=T_all, device=local, order=order)
+                               pb.ChineseRestaurantProcess(1.0), k_max=a.k_max, history=T_all, device=local, order=order,
+                               on_overflow="ignore")
     o = 0
     ps.filter_(ys[o:o + a.burnin], uniforms=us[o:o + a.burnin]); o += a.burnin
     if W:
@@ -338,15 +343,18 @@ def main():
         ms, n = kt[name]
         if n:
             avg = ms / n
-            per_kernel[name] = {"avg_ms": avg, "share": ms / prof_ms, "alg_bytes_per_launch": kb[name] * n_live0,
-                                "achieved_gbs": kb[name] * n_live0 / (avg * 1e-3) / 1e9}
-    dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])
+            # a class may have several launches per step: its algorithmic bytes are per STEP, so the rate
+            # divides by the class's time per step; avg_ms stays the mean duration of one launch
+            per_kernel[name] = {"avg_ms": avg, "launches_per_step": n / K, "ms_per_step": ms / K, "share": ms / prof_ms,
+                                "alg_bytes_per_step": kb[name] * n_live0,
+                                "achieved_gbs": kb[name] * n_live0 / (ms / K * 1e-3) / 1e9}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["avg_ms"])      # (a single-launch class on this path)
     traffic, traffic_src = ncu_traffic("k_" + dom)
     roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
             "frac": per_kernel[dom]["achieved_gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src,
             "avg_launch_ms": per_kernel[dom]["avg_ms"], "share_of_step": per_kernel[dom]["share"],
-            "algorithmic_bytes_per_update": kb[dom], "per_kernel": per_kernel,
+            "algorithmic_bytes_per_update": kb[dom], "alg_bytes_per_launch": kb[dom] * n_live0, "per_kernel": per_kernel,
             "whole_step": {"algorithmic_bytes_per_update": bytes_per_update(kbar),
                            "achieved": bytes_per_update(kbar) * value / 1e9, "frac": bytes_per_update(kbar) * value / 1e9 / peak,
                            "frac_of_nominal_8tbs": bytes_per_update(kbar) * value / 1e9 / 8000.0}}
@@ -354,7 +362,8 @@ def main():
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n_live0,
                                                 select_rounds_last=stats["select_rounds"], candidates_last=stats["n_candidates"],
-                                                select_phase_us_last=stats["select_phase_us"]),
+                                                select_phase_us_last=stats["select_phase_us"], kmax_overflow=int(stats["overflow"]),
+                                                max_clusters_in_a_particle=int(ps.ncomponents().max())),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
                     "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le[-1])},
             "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}
@@ -362,6 +371,10 @@ def main():
         cb = cpu_leg(a.cpu_n, 48, a.cpu_steps)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
+    if stats["overflow"] and not a.allow_overflow:
+        print(f"k_max = {a.k_max} dropped {stats['overflow']} new-cluster candidates: the run no longer computes the reference's "
+              "filter; raise --k-max", file=sys.stderr)
+        return 1
     return 0
 
 

@@ -9,7 +9,7 @@
  * The reference is pure Julia and has no FFI of its own; the boundary it offers is its
  * generic-function surface.  Each entry point below names the reference method it stands
  * behind (file:line in the reference repository).  The Julia shim that binds these with
- * `ccall` is particles.jl_b200/julia/Particles.jl; the Python mirror used by the tests is
+ * `ccall` is particles.jl_b200/julia/particles_b200.jl; the Python mirror used by the tests is
  * particles.jl_b200/particles_b200/.
  *
  * Conventions
@@ -56,7 +56,8 @@ typedef struct {
     int32_t k_max;            /* cluster slots per particle (reference: unbounded, src/particle.jl:142-143);
                                  at K == k_max the new-cluster candidate is dropped and counted */
     int32_t order;            /* PF_ORDER_INDEX | PF_ORDER_SORTED (Fearnhead only) */
-    int64_t history;          /* generations of (ancestor, assignment) kept for assignments(); 0 = none */
+    int64_t history;          /* generations of (ancestor, assignment) kept for assignments(): > 0 fixed capacity, 0 none,
+                                 < 0 grows on demand (the reference's ancestor chain, src/particle.jl:25-32, is unbounded) */
     int32_t device;           /* CUDA device ordinal */
     int32_t reserved0;
     int32_t rank, nranks;     /* sharded run: this handle owns shard `rank` of `nranks` (0, 0 or 0, 1: unsharded) */
@@ -86,6 +87,10 @@ typedef struct {
     int32_t select_rounds;    /* bracket rounds the threshold search needed */
     int64_t n_candidates;     /* putatives inside the first bracket */
     double select_phase_us[4]; /* threshold search: bracket, classify pass(es), descent + solve, total */
+    int64_t n_plateau;        /* in-bracket copies of the step's exactly tied value (counted, not listed) */
+    int32_t select_status;    /* bit set of the threshold search: 1 fused classification used, 2 candidate staging overflowed,
+                                 4 kept-side scale unusable, 8 / 16 bracket failed low / high, 32 rescaled, 64 comb rescaled */
+    int32_t reserved1;
 } pf_step_stats;
 
 /* ---- life cycle ---------------------------------------------------------------------- */
@@ -144,88 +149,46 @@ int32_t pf_get_last_assignments(pf_handle h, int32_t *out);  /* p.assignment - 1
 int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t N, double u, int32_t order,
                   int64_t *survivors, uint8_t *resampled, pf_step_stats *stats);
 
-/* ---- multi-GPU: particles block-sharded, one process (rank) per GPU ------------------
- * The population of a Fearnhead filter is block-sharded in global (rank-major) order; every
- * rank runs the same kernels on its shard and the host program supplies the collectives
- * between the stages below ("bring your own communicator": torch.distributed / NCCL in
- * particles_b200/distributed.py, MPI.jl or NCCL.jl under the Julia shim).  What crosses the
- * ranks per observation: the strided sample and the bracket's candidates with their
- * accumulator blocks (all-gather of a few MB), one 32-byte total per rank (all-gather) and,
- * only when a share outgrows its shard, the records of the particles that change owner in
- * the re-partitioning (all-to-all-v).  All decisions are integer arithmetic on gathered data, so every rank
- * reaches the same threshold and an N-rank run reproduces the 1-rank run bit for bit.
+/* ---- multi-GPU: particles block-sharded over the GPUs of one node ------------------------
+ * The population of a Fearnhead filter is block-sharded in global (rank-major) order, one handle
+ * (shard) per GPU: pf_config.rank / nranks.  Every rank runs the same kernels on its shard; what
+ * crosses the ranks per observation -- the strided sample, the bracket's candidates with their
+ * accumulator blocks (a few MB), one 32-byte survivor-scan total per rank, and the children that
+ * change owner when the new population is re-partitioned into equal blocks -- is written by the
+ * kernels themselves into the peers' device memory over NVLink (CUDA IPC between processes, peer
+ * access inside one process) and synchronised by per-rank sequence flags the kernels spin on:
+ * there is no collective library and no host round trip inside pf_mg_filter.  All decisions are
+ * integer arithmetic on the gathered data, so every rank reaches the same threshold and a G-rank
+ * run reproduces the 1-rank run bit for bit (src/fearnhead.jl:130-184 on the whole population).
  *
- *   pf_mg_begin(y, u)                     expansion of the local shard
- *   pf_mg_select(PF_MG_SAMPLE, pad_to = sample_entries)        local strided sample -> list, acc
- *   all_gather(acc) ; all_gather(list[0 : sample_entries])
- *   pf_mg_select(PF_MG_BRACKET | PF_MG_CLASSIFY, gathered acc, gathered list, sample_entries, pad_to = cand_entries)
- *                                         bracket from the gathered sample, classify the shard
- *   all_gather(acc) ; all_gather(list[0 : cand_entries])
- *   pf_mg_select(PF_MG_SOLVE, gathered acc, gathered list, cand_entries)
- *                                         verify / descend / solve on the gathered candidates
- *   pf_mg_tiles()                         local survivor-scan totals -> local_total
- *   all_gather(local_total)
- *   pf_mg_finish(gathered totals)         offsets, survivor scan, instantiate (local + send buffer)
- *   pf_mg_plan(...)                       THE host synchronisation of the step: search outcome
- *                                         (phase 4 = done; 3 / 7 = another PF_MG_CLASSIFY + exact-size
- *                                         gathers + PF_MG_SOLVE, then tiles/finish again) and the
- *                                         exchange plan; the kernels after PF_MG_SOLVE are no-ops
- *                                         until the search is done, so they may be queued behind it
- *   [exchange != 0] all_to_all_v(send buffer -> recv buffer, split sizes = counts * rows)
- *   pf_mg_unpack(recv buffer)             received particles -> local store; step done          */
-enum { PF_MG_SAMPLE = 1, PF_MG_BRACKET = 2, PF_MG_CLASSIFY = 4, PF_MG_SOLVE = 8 };
-typedef struct {
-    void *scalars;          /* int64[2] device: {M (sum), max weight bit pattern (max)} */
-    void *acc;              /* device: accumulator block of the threshold search, acc_bytes bytes */
-    int64_t acc_bytes;
-    void *list;             /* device: local sample / candidate list (doubles), list_capacity entries */
-    int64_t list_capacity;
-    void *local_total;      /* device: 32-byte survivor-scan total of this shard */
-    int64_t total_bytes;
-    void *send_buffer;      /* device: packed records of emigrating particles (doubles) */
-    void *recv_buffer;      /* device: packed records of immigrating particles (doubles) */
-    int64_t buffer_capacity;   /* doubles in each of send_buffer / recv_buffer */
-    int64_t rows_per_particle; /* doubles per migrating particle */
-    int64_t local_capacity;    /* particles this shard can hold */
-    int64_t sample_entries;    /* fixed gather size (doubles) of the sample list */
-    int64_t cand_entries;      /* fixed gather size (doubles) of the candidate list */
-    int64_t window;            /* neighbour exchange: particles per message slot (send/recv buffers hold 2 slots) */
-} pf_mg_ptrs;
-int32_t pf_set_stream(pf_handle h, void *cuda_stream);    /* run on the caller's stream (e.g. torch's current stream) */
-int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *out);
-int32_t pf_mg_begin(pf_handle h, const double *y, double u);
-int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done, const void *gathered_acc, const void *gathered_list,
-                     int64_t list_each, int64_t pad_to);
-/* state[0] = phase (4 done, 3 classify again), [1] = local list entries in use (multiple of 256),
- * [2] = 1 if this step needs the sample, [3] = classify rounds done.  Synchronises the stream. */
-int32_t pf_mg_state(pf_handle h, int64_t state[4]);
-int32_t pf_mg_tiles(pf_handle h);
-int32_t pf_mg_finish(pf_handle h, const void *gathered_totals);
-/* Exchange plan of the re-partitioning, in particles: send_counts[nranks] by destination,
- * recv_counts[nranks] by source.  Synchronises the stream. */
-int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
-                   int64_t *phase, int64_t *exchange);
-int32_t pf_mg_unpack(pf_handle h, const void *recv_buffer);
-/* Direct exchange: when every rank's next-generation arrays are mapped into this process
- * (pf_mg_ipc_handles on the owner -> pf_mg_set_peer here; or plain pointers from pf_mg_local_arrays when
- * the ranks live in one process), k_instantiate stores a child that changes owner straight into its
- * new owner's store over NVLink and the population is re-partitioned into equal blocks at EVERY
- * step: no send/recv buffers, no all-to-all, no host-known sizes.  The host program must place a
- * collective (e.g. the next step's first all-gather, or a barrier) between pf_mg_finish and the
- * next pf_mg_begin so that remote stores are complete before their owner reads them. */
-int32_t pf_mg_local_arrays(pf_handle h, void **out /* [8] */);
-int32_t pf_mg_ipc_handles(pf_handle h, void *out /* 8 x 64 bytes */);
+ * One process per GPU (e.g. under torchrun / MPI; any side channel can carry the 576-byte blobs):
+ *     pf_create(cfg with rank, nranks)            on every rank
+ *     pf_mg_ipc_handles(h, blob)                  -> all-gather the blobs (host side, once)
+ *     pf_mg_set_peer(h, r, NULL, blob_r)          for every other rank r
+ *     pf_mg_connect(&h, 1)
+ *     pf_mg_filter(&h, 1, ys, T, uniforms, 1, log_evidence)      the same call on every rank
+ * One process driving several GPUs (one Julia / C host thread, no launcher):
+ *     pf_mg_create_local(cfg, devices, n, handles) ;  pf_mg_filter(handles, n, ...)
+ * Read-outs (pf_get_logweights, pf_get_ncomponents, pf_get_last_ancestors, ...) return each shard's
+ * part; concatenated in rank order they are the global arrays (ancestors are global indices).     */
+#define PF_MG_NARRAYS 9         /* S[0], S[1], K[0], K[1], logw[0], logw[1], gen_anc, gen_asg, exchange region */
+#define PF_MG_IPC_BYTES 64      /* sizeof(cudaIpcMemHandle_t) */
+int32_t pf_set_stream(pf_handle h, void *cuda_stream);    /* run on the caller's stream */
+int32_t pf_mg_local_arrays(pf_handle h, void **out /* [PF_MG_NARRAYS] */);
+int32_t pf_mg_ipc_handles(pf_handle h, void *out /* PF_MG_NARRAYS x PF_MG_IPC_BYTES bytes */);
+/* Arrays of rank `peer`: plain device pointers (ptrs, from pf_mg_local_arrays of a handle in this
+ * process) or the IPC blob pf_mg_ipc_handles produced in the peer's process. */
 int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, const void *ipc_handles);
-int32_t pf_mg_enable_direct(pf_handle h);
-/* Look-ahead: pf_mg_close() after pf_mg_finish marks the step as "needs the host" on the device when the search
- * did not finish or particles must change owner; every kernel of later steps is then a no-op, so a host program
- * may queue several observations ahead and call pf_mg_drain() (synchronises; out = {halt (1 + step index, or 0),
- * phase, local population, global population}) only now and then.  After completing a halted step through the
- * synchronous stages, pf_mg_resume(step) rewinds the host mirrors to `step` and clears the mark. */
-int32_t pf_mg_close(pf_handle h);
-int32_t pf_mg_set_obs(pf_handle h, const double *y, double u);   /* re-upload (y, u) of a halted step before completing it */
-int32_t pf_mg_drain(pf_handle h, int64_t out[4]);
-int32_t pf_mg_resume(pf_handle h, int64_t step);
+/* All peers set: upload the peer tables of the n_local handles this process drives. */
+int32_t pf_mg_connect(pf_handle *hs, int32_t n_local);
+/* filter!(ps, ys, false) (src/filters.jl:6-13) on the sharded population; hs = the shards of this
+ * process.  Every process of the group makes the same call.  uniforms[uniforms_per_step x T] (the
+ * first of each column is the step's rand(), src/fearnhead.jl:99) or NULL for the device stream.
+ * PF_ERR_STATE / PF_ERR_OVERFLOW: a step could not be completed on the device (pf_last_error). */
+int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys, int64_t T, const double *uniforms,
+                     int64_t uniforms_per_step, double *log_evidence);
+int64_t pf_mg_n_global(pf_handle h);          /* population over all shards */
+int32_t pf_mg_create_local(const pf_config *cfg, const int32_t *devices, int32_t n, pf_handle *out /* [n] */);
 /* Raw control-block words of the last threshold search / survivor scan (debugging aid). */
 int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */);
 

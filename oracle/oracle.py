@@ -419,3 +419,71 @@ def exact_c_value(T_n):
     if n <= 0:
         return float("nan")
     return float(Fraction(T, n) / (1 << 1074))
+
+
+def select_exact_fast(w, N, u, order=ORDER_INDEX):
+    """select_exact for large M (millions): the same exact-arithmetic specification, evaluated with a
+    numpy sort, C-speed integer prefix sums (itertools.accumulate over Python integers scaled by the
+    smallest exponent present) and a binary search over the distinct weights (the predicate of
+    src/fearnhead.jl:69 is monotone along the ascending weights).  tests/test_oracle_selection.py pins
+    it to select_exact on random and edge cases.  Returns the same tuple, except that the exact c = T/n
+    is returned as (T * 2**-emin_shift, n, emin_shift) folded into (T_scaled_to_2**1074, n)."""
+    from itertools import accumulate
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    M = len(w)
+    bits = w.view(np.uint64)
+    mant, expo = np.frexp(w)
+    m53 = np.ldexp(mant, 53).astype(np.int64)                  # exact: w = m53 * 2**(expo - 53)
+    e = expo.astype(np.int64) - 53
+    nz = m53 != 0
+    emin = int(e[nz].min()) if nz.any() else 0
+    sh = np.where(nz, e - emin, 0)
+    W = [m << s for m, s in zip(m53.tolist(), sh.tolist())]     # w * 2**(-emin), exact integers
+    perm = np.argsort(bits, kind="stable")                     # ascending weight, ties by index
+    sb = bits[perm]
+    Ws = [W[k] for k in perm.tolist()]
+    pre = [0] + list(accumulate(Ws))                           # pre[i] = sum of the i smallest
+    starts = np.flatnonzero(np.concatenate([[True], sb[1:] != sb[:-1]]))   # first position of each distinct value
+    starts = starts[sb[starts] != 0]                           # exact zeros are skipped (src/fearnhead.jl:66)
+
+    def pred(pos):                                             # predicate at the distinct value starting at `pos`
+        return pre[pos] <= (N - (M - pos)) * Ws[pos]
+    lo, hi = 0, len(starts)                                    # first group whose predicate holds
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if pred(int(starts[mid])):
+            hi = mid
+        else:
+            lo = mid + 1
+    kept_start = int(starts[lo]) if lo < len(starts) else M
+    n_kept = M - kept_start
+    n = N - n_kept
+    T = pre[kept_start]
+    lowmask = np.zeros(M, dtype=bool)
+    lowmask[perm[:kept_start]] = True
+    walk = perm[:kept_start] if order == ORDER_SORTED else np.flatnonzero(lowmask)
+    picked = np.zeros(0, dtype=np.int64)
+    if n > 0 and T > 0:
+        fu = Fraction(u)
+        un, ud = fu.numerator, fu.denominator
+        den = ud * T
+        unT = un * T
+        nud = n * ud
+        # teeth strictly below S: 0 if un T >= S n ud, else floor((S n ud - un T - 1) / (ud T)) + 1
+        run = accumulate(W[k] for k in walk.tolist())
+        teeth = [0 if (x := s * nud - unT) <= 0 else (x - 1) // den + 1 for s in run]
+        t = np.asarray(teeth, dtype=np.int64)
+        grow = np.diff(np.concatenate([[0], t])) > 0
+        picked = walk[grow]
+    if order == ORDER_SORTED:
+        surv = np.concatenate([picked, perm[kept_start:]])
+        flag = np.concatenate([np.ones(len(picked), bool), np.zeros(n_kept, bool)])
+    else:
+        take = np.zeros(M, dtype=bool)
+        take[picked] = True
+        keep = ~lowmask
+        surv = np.flatnonzero(keep | take)
+        flag = take[surv]
+    shift = 1074 + emin                                        # W = w * 2**(-emin)  ->  w * 2**1074
+    Tn = (T << shift if shift >= 0 else Fraction(T, 1 << -shift), n)
+    return surv.astype(np.int64), flag, Tn, n_kept

@@ -245,7 +245,7 @@ __global__ void k_cl_steplog(StepState *st, ClState *cl, StepLog *lg, long long 
 {
     if (threadIdx.x || blockIdx.x) return;
     StepLog r;
-    r.n_in = N; r.M = 0; r.n_kept = 0; r.n_req = 0; r.n_got = 0; r.n_out = N; r.overflow = st->overflow; r.n_cand = 0;
+    r.n_in = N; r.M = 0; r.n_kept = 0; r.n_req = 0; r.n_got = 0; r.n_out = N; r.overflow = st->overflow; r.n_cand = 0; r.n_plateau = 0; r.status = 0; r.pad = 0;
     r.log_total = cl->log_total; r.lw_resamp = -log((double)N); r.thr = 0.0; r.cv = cl->cv;
     r.resampled = cl->resample; r.rounds = 0;
     for (int k = 0; k < 4; k++) r.sel_us[k] = 0.0;

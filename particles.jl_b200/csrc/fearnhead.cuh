@@ -24,9 +24,9 @@ struct StepState {
 };
 
 struct StepLog {            // one record per step, read back after pf_filter
-    long long n_in, M, n_kept, n_req, n_got, n_out, overflow, n_cand;
+    long long n_in, M, n_kept, n_req, n_got, n_out, overflow, n_cand, n_plateau;
     double log_total, lw_resamp, thr, cv;
-    int resampled, rounds;
+    int resampled, rounds, status, pad;
     double sel_us[4];
 };
 
@@ -36,13 +36,17 @@ struct StepLog {            // one record per step, read back after pf_filter
 // new cluster starts with (add(prior, y), src/component.jl:85).
 template <int D>
 __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, StepConst *sc_out, int first,
-                          const SelScratch *guard, const SelResult *prev)
+                          SelScratch *guard, const SelResult *prev, const Xch *xch, unsigned long long seq, long long step)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (guard && guard->halt) return;
+    // sharded run: the previous generation is complete on every rank (peers stored children into this shard)
+    if (xch && !xch_wait(xch, XCH_D, seq - 1)) { sel_halt(guard, step, PF_HALT_TIMEOUT); return; }
+    if (guard) guard->list_n = 0;                      // the sample expansion appends from 0
     using L = Layout<D>;
-    if (!first) st->n_live = st->n_next;
-    st->M_pred = first ? st->n_live : st->M_next;      // (first step: empty particles, one putative each)
+    // first: 1 = the filter's first observation, 2 = a halted step is run again (the roll-over already happened)
+    if (first == 0) st->n_live = st->n_next;
+    if (first != 2) st->M_pred = first ? st->n_live : st->M_next;      // (first step: empty particles, one putative each)
     st->M_next = 0; st->vmax_sample = 0;
     st->n_next = 0;
     st->M = 0; st->vmax_bits = 0; st->ticket = 0; st->ticket2 = 0; st->n_picked = 0; st->n_kept = 0;
@@ -57,7 +61,7 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
     double l1p = log1p(r0.r * q);
     c.lw_new = r0.C - 0.5 * pc->logdet0 - r0.h * l1p;
     // exactly what k_expand evaluates for the new-cluster putative of a particle whose log-weight is lw_resamp
-    c.plateau_bits = (prev && !first) ? (unsigned long long)__double_as_longlong(exp(prev->lw_resamp + c.lw_new)) : 0ull;
+    c.plateau_bits = (prev && first != 1) ? (unsigned long long)__double_as_longlong(exp(prev->lw_resamp + c.lw_new)) : 0ull;
     // new slot: n = 1, mean = y, L = cholupdate(L0, sqrt(r0) (y - mu0)), logdet = logdet0 + log1p(r0 q)
     double x[D];
     double sr = sqrt(r0.r);
@@ -74,7 +78,6 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
 }
 
 #define SCAN_THREADS 256
-#define PF_MAX_RANKS 16
 struct TileSum {           // survivor-scan record of one tile of SCAN_THREADS particles
     u128 X;
     unsigned int kept;
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
                                                 ScanRec rec = ScanRec{nullptr, nullptr})
 {
     using L = Layout<D>;
-    if (MODE == 0 && sc && sc->halt) return;
+    if (sc && sc->halt) return;
     __shared__ u64 s_max[8];
     __shared__ long long s_M[8], s_ovf[8];
     constexpr int CAND_CAP = (MODE == 1) ? EXP_SAMPLE_THREADS * PF_MAX_SLOTS : (MODE == 2 ? EXP_CAND_CAP : 1);
@@ -138,8 +141,12 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
     const long long n_live = st->n_live;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // MODE 1 samples aligned groups of 4 consecutive particles (one 32-byte sector per field row):
-    // global particle g is in the sample iff (g / 4) % stride == 0
-    const long long i = (MODE == 1) ? (gid >> 2) * (4 * stride) + (gid & 3) : gid;
+    // GLOBAL particle g is in the sample iff (g / 4) % stride == 0; a shard starts at global index st->goff
+    long long i = gid;
+    if (MODE == 1) {
+        const long long goff = st->goff;
+        i = (goff / (4 * stride) + (gid >> 2)) * (4 * stride) + (gid & 3) - goff;
+    }
     const bool fused = (MODE == 2) && sc->fuse_valid;
     u64 lo = 0, hi = 0; int scale = 0, tscale = 0;
     if (fused) { lo = sc->lo; hi = sc->hi; scale = sc->fuse_scale; tscale = sc->fuse_tot_scale; }
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
             }
         }
     };
-    if (i < n_live) {
+    if (i >= 0 && i < n_live) {
         double y[D], mu0[D];
 #pragma unroll
         for (int k = 0; k < D; k++) { y[k] = scp->y[k]; mu0[k] = pc->mu0[k]; }
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(256) k_tile_fixup(TileSum *__restrict__ tiles,
                                                     const SelScratch *__restrict__ sc, const long long *__restrict__ n_items_ptr,
                                                     const StepConst *__restrict__ scp)
 {
-    if (!sc->tiles_ok) return;
+    if (sc->halt || sc->phase != 4 || !sc->tiles_ok) return;
     const long long ntiles = (*n_items_ptr + SCAN_THREADS - 1) / SCAN_THREADS;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
@@ -315,8 +322,9 @@ __global__ void __launch_bounds__(256) k_tile_fixup(TileSum *__restrict__ tiles,
 // spinning: per-tile sums, one-block prefix over the tiles, apply.
 
 // Sharded run (particles block-sharded over ranks, global order = rank-major): where this
-// rank's survivors sit in the global survivor order, and how the new population is
-// re-partitioned into equal blocks of q particles (rank r owns global [r q, (r+1) q)).
+// rank's survivors sit in the global survivor order.  The new population is re-partitioned into
+// equal blocks of q = ceil(n / G) particles at EVERY step (rank r owns global [r q, (r+1) q)):
+// k_instantiate stores a child that changes owner straight into its new owner's arrays.
 struct RankOff {
     u128 S_off;                    // fixed-point low mass of all lower ranks
     long long kept_off;            // survivors kept on all lower ranks
@@ -324,19 +332,14 @@ struct RankOff {
     long long n_local;             // survivors produced by this rank
     long long n_mine;              // particles this rank owns after re-partitioning
     long long n_global, q;
-    long long bnd[PF_MAX_RANKS + 1];   // new ownership: rank r owns global [bnd[r], bnd[r+1])
     long long goff_prev;           // global index of this rank's first PARENT (genealogy)
+    long long goff_next;           // global index of this rank's first particle after the step
     int rank, nranks;
-    long long overflow;            // survivors that did not fit this rank's survivor list / buffers
-    long long exchange;            // 0: every child stays on its parent's rank this step (same decision on all ranks)
-    long long send_start[PF_MAX_RANKS], send_len[PF_MAX_RANKS], send_off[PF_MAX_RANKS];   // by destination (particles / doubles)
-    long long recv_idx0[PF_MAX_RANKS], recv_len[PF_MAX_RANKS], recv_off[PF_MAX_RANKS];    // by source
 };
 
-// Direct exchange: every rank's next-generation arrays mapped into this process (cudaIpc, or
-// plain pointers when the ranks live in one process), so that k_instantiate stores a child
-// that changes owner straight into its new owner's store over NVLink -- no packing, no
-// send/recv buffers, no host-known sizes.
+// Every rank's next-generation arrays mapped into this process (cudaIpc, or plain pointers when
+// the ranks live in one process): k_instantiate stores a child that changes owner straight into
+// its new owner's store over NVLink -- no packing, no send/recv buffers, no host-known sizes.
 struct PeerTable {
     double *S[PF_MAX_RANKS];
     int *Kc[PF_MAX_RANKS];
@@ -345,75 +348,43 @@ struct PeerTable {
     unsigned char *gen_asg[PF_MAX_RANKS];
 };
 
-// one thread: turn the gathered per-rank totals (mass of the low partition, kept count) into
-// this rank's offsets and the exchange plan.  rows = doubles per migrating particle.
-__global__ void k_rank_offsets(const TileSum *__restrict__ gathered, int rank, int nranks, const SelResult *__restrict__ res,
-                               StepState *st, RankOff *ro, int rows, const SelScratch *guard, long long stay_cap,
-                               long long window, int direct)
+// one thread: wait for every rank's survivor-scan total (exchange kind C), turn the totals (mass of the
+// low partition, kept count) into this rank's offsets and the new ownership
+__global__ void k_rank_offsets(const Xch *x, unsigned long long seq, long long step, const SelResult *__restrict__ res,
+                               StepState *st, RankOff *ro, SelScratch *guard, long long surv_cap)
 {
     if (threadIdx.x || blockIdx.x) return;
-    if (guard && (guard->phase != 4 || guard->halt)) { ro->n_local = 0; return; }          // the threshold search has not finished (speculative tail)
+    if (guard->halt) { ro->n_local = 0; return; }
+    if (guard->phase != 4) { sel_halt(guard, step, PF_HALT_SEARCH); ro->n_local = 0; return; }
+    if (!xch_wait(x, XCH_C, seq)) { sel_halt(guard, step, PF_HALT_TIMEOUT); ro->n_local = 0; return; }
+    const XchTot *gathered = x->reg[x->rank]->c;
+    const int rank = x->rank, nranks = x->nranks;
     const bool comb = res->n > 0 && !isz128(res->T);
     const u64 n = (u64)res->n;
     u128 Spre = mk128(0, 0);
     long long kpre = 0, gpre = 0, tpre = 0;
-    long long g_first[PF_MAX_RANKS], n_loc[PF_MAX_RANKS];
-    long long my_kept = 0, my_picked = 0;
+    long long my_kept = 0, my_picked = 0, my_first = 0, my_n = 0;
     for (int r = 0; r < nranks; r++) {
-        u128 Snext = add128(Spre, gathered[r].X);
+        u128 X;
+        X.lo = ld_peer(reinterpret_cast<const unsigned long long *>(&gathered[r].X.lo));
+        X.hi = ld_peer(reinterpret_cast<const unsigned long long *>(&gathered[r].X.hi));
+        const long long kept = (long long)(unsigned int)ld_peer(reinterpret_cast<const unsigned long long *>(&gathered[r].kept));
+        u128 Snext = add128(Spre, X);
         long long tnext = comb ? (long long)teeth_below(mul128_64(Snext, n), res->Uoff, res->T) : 0;
         long long picked = tnext - tpre;
-        g_first[r] = gpre; n_loc[r] = (long long)gathered[r].kept + picked;
-        if (r == rank) { ro->S_off = Spre; ro->kept_off = kpre; my_kept = gathered[r].kept; my_picked = picked; }
-        Spre = Snext; kpre += gathered[r].kept; tpre = tnext; gpre += n_loc[r];
+        if (r == rank) { ro->S_off = Spre; ro->kept_off = kpre; my_kept = kept; my_picked = picked; my_first = gpre; my_n = kept + picked; }
+        Spre = Snext; kpre += kept; tpre = tnext; gpre += kept + picked;
     }
     const long long n_global = gpre;
     long long q = (n_global + nranks - 1) / nranks;
     if (q < 1) q = 1;
-    // Ownership after the step.  Children are born on their parent's rank; the boundary between
-    // ranks r-1 and r then moves toward the balanced position r q by at most `window` particles
-    // (and never past a neighbour's range), so only adjacent ranks exchange particles and every
-    // message has a fixed capacity: no host-known sizes, no synchronisation (exchange = 2).  If a
-    // share would still exceed the shard capacity the population is re-partitioned into equal
-    // blocks of q through the host (exchange = 1).
-    ro->bnd[0] = 0; ro->bnd[nranks] = n_global;
-    bool fits = true;
-    for (int r = 1; r < nranks; r++) {
-        long long cur = g_first[r], tgt = (long long)r * q;
-        if (tgt > n_global) tgt = n_global;
-        long long b = tgt < cur - window ? cur - window : (tgt > cur + window ? cur + window : tgt);
-        long long lo = g_first[r - 1], hi = g_first[r] + n_loc[r];          // stay inside the two neighbours' ranges
-        if (b < lo) b = lo;
-        if (b > hi) b = hi;
-        if (b < ro->bnd[r - 1]) b = ro->bnd[r - 1];
-        ro->bnd[r] = b;
-    }
-    for (int r = 0; r < nranks; r++) fits = fits && (ro->bnd[r + 1] - ro->bnd[r] <= stay_cap);
-    if (direct) fits = false;           // direct exchange: equal blocks every step (children are stored remotely by k_instantiate)
-    if (!fits)
-        for (int r = 0; r <= nranks; r++) { long long b = (long long)r * q; ro->bnd[r] = b > n_global ? n_global : b; }
-    ro->g_first = g_first[rank]; ro->n_local = n_loc[rank]; ro->n_global = n_global; ro->q = q;
-    ro->n_mine = ro->bnd[rank + 1] - ro->bnd[rank];
-    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff; ro->overflow = 0; ro->exchange = direct ? 3 : (fits ? 2 : 1);
-    long long soff = 0, roff = 0;
-    for (int d = 0; d < nranks; d++) {
-        long long lo = g_first[rank] > ro->bnd[d] ? g_first[rank] : ro->bnd[d];
-        long long hi = g_first[rank] + n_loc[rank] < ro->bnd[d + 1] ? g_first[rank] + n_loc[rank] : ro->bnd[d + 1];
-        long long len = (d == rank || hi <= lo) ? 0 : hi - lo;
-        long long lo2 = g_first[d] > ro->bnd[rank] ? g_first[d] : ro->bnd[rank];
-        long long hi2 = g_first[d] + n_loc[d] < ro->bnd[rank + 1] ? g_first[d] + n_loc[d] : ro->bnd[rank + 1];
-        long long len2 = (d == rank || hi2 <= lo2) ? 0 : hi2 - lo2;
-        if (direct) { len = 0; len2 = 0; }       // nothing goes through the send / recv buffers
-        ro->send_start[d] = lo; ro->send_len[d] = len; ro->recv_idx0[d] = lo2 - ro->bnd[rank]; ro->recv_len[d] = len2;
-        if (fits) {      // neighbour mode: fixed slots -- [0, window) left neighbour, [window, 2 window) right neighbour
-            ro->send_off[d] = (d < rank ? 0 : window) * rows;
-            ro->recv_off[d] = (d < rank ? 0 : window) * rows;
-        } else {
-            ro->send_off[d] = soff; soff += len * rows;
-            ro->recv_off[d] = roff; roff += len2 * rows;
-        }
-    }
+    const long long b0 = (long long)rank * q < n_global ? (long long)rank * q : n_global;
+    const long long b1 = (long long)(rank + 1) * q < n_global ? (long long)(rank + 1) * q : n_global;
+    ro->g_first = my_first; ro->n_local = my_n; ro->n_global = n_global; ro->q = q;
+    ro->n_mine = b1 - b0; ro->goff_next = b0;
+    ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff;
     st->n_kept = my_kept; st->n_picked = my_picked; st->n_next = ro->n_mine; st->n_global = n_global;
+    if (my_n > surv_cap) { sel_halt(guard, step, PF_HALT_SURVIVORS); ro->n_local = 0; }
 }
 
 // mode 0: index-order step (always runs); mode 1: flat sorted list, runs only when the step
@@ -470,8 +441,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
 // 1 KB loads, shuffle scan, carry), then the warps' totals are scanned
 __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelResult *__restrict__ res,
                                                       const long long *__restrict__ n_items_ptr, StepState *st, int mode,
-                                                      TileSum *local_tot /* sharded run: totals out, counts set later */,
-                                                      const SelScratch *guard)
+                                                      const Xch *xch /* sharded run: the total goes to every rank (exchange kind C) */,
+                                                      unsigned long long seq, const SelScratch *guard)
 {
     if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
@@ -500,8 +471,11 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelR
         }
         s_wx[lane] = sub128(ix, x); s_wk[lane] = ik - k;                 // exclusive warp offsets
         if (lane == 31) {
-            if (local_tot) { local_tot->X = ix; local_tot->kept = ik; }
-            else {
+            if (xch) {
+                XchTot tot; tot.X = ix; tot.kept = ik; tot.pad[0] = tot.pad[1] = tot.pad[2] = 0;
+                for (int p = 0; p < xch->nranks; p++) xch->reg[p]->c[xch->rank] = tot;
+                xch_signal(xch, XCH_C, seq);
+            } else {
                 const bool comb = res->n > 0 && !isz128(res->T);
                 long long picked = comb ? (long long)teeth_below(mul128_64(ix, (u64)res->n), res->Uoff, res->T) : 0;
                 st->n_kept = ik; st->n_picked = picked; st->n_next = (long long)ik + picked; st->n_global = st->n_next;
@@ -665,7 +639,7 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
                                                      const unsigned int *__restrict__ surv_parent,
                                                      const unsigned char *__restrict__ surv_slot,
                                                      unsigned int *gen_anc, unsigned char *gen_asg,
-                                                     const RankOff *__restrict__ ro, double *__restrict__ sendbuf, int k_max,
+                                                     const RankOff *__restrict__ ro, int k_max,
                                                      const SelScratch *guard, long long *m_next,
                                                      const PeerTable *__restrict__ peers, long long gen_off)
 {
@@ -674,27 +648,24 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
     const long long n_out = ro ? ro->n_local : st->n_next;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_out) return;                       // (grid = survivor-list capacity: no thread beyond it)
-    // destination of child t: a local index, or a slot of the packed send buffer of another rank
+    // destination of child t: a local index, or (sharded run) an index in the arrays of its new owner
     double *dstb = S2 + t;
-    long long stride = cap, idx = t;
-    bool remote = false;
+    long long idx = t;
     unsigned int anc_off = 0;
     if (ro) {
         const long long g = ro->g_first + t;
-        int dest = 0;
-        while (dest + 1 < ro->nranks && g >= ro->bnd[dest + 1]) dest++;
+        const int dest = (int)(g / ro->q);
         anc_off = (unsigned int)ro->goff_prev;
-        if (dest == ro->rank) { idx = g - ro->bnd[dest]; dstb = S2 + idx; }
-        else if (peers) {
-            // direct exchange: the child is written into its new owner's arrays (peer memory over NVLink)
-            idx = g - ro->bnd[dest];
+        idx = g - (long long)dest * ro->q;
+        if (dest != ro->rank) {
+            // the child is written into its new owner's arrays (peer memory over NVLink)
             S2 = peers->S[dest]; Kc2 = peers->Kc[dest]; logw2 = peers->logw[dest];
             gen_anc = peers->gen_anc[dest] ? peers->gen_anc[dest] + gen_off : nullptr;
             gen_asg = peers->gen_asg[dest] ? peers->gen_asg[dest] + gen_off : nullptr;
-            dstb = S2 + idx;
         }
-        else { remote = true; stride = ro->send_len[dest]; dstb = sendbuf + ro->send_off[dest] + (g - ro->send_start[dest]); }
+        dstb = S2 + idx;
     }
+    const long long stride = cap;
     const unsigned int par = surv_parent[t];
     const unsigned char sl = surv_slot[t];
     const int j = sl & 0x7F;
@@ -708,13 +679,8 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
         const unsigned int c2 = __reduce_add_sync(am, (unsigned int)(Knew + (Knew < k_max ? 1 : 0)));
         if ((threadIdx.x & 31) == (unsigned)(__ffs(am) - 1)) atomicAdd((unsigned long long *)m_next, (unsigned long long)c2);
     }
-    if (!remote) {
-        logw2[idx] = lw; Kc2[idx] = Knew;
-        if (gen_anc) { gen_anc[idx] = par + anc_off; gen_asg[idx] = (unsigned char)j; }
-    } else {
-        double *hdr = dstb + (long long)k_max * L::F * stride;
-        hdr[0] = lw; hdr[stride] = (double)Knew; hdr[2 * stride] = (double)(par + anc_off); hdr[3 * stride] = (double)j;
-    }
+    logw2[idx] = lw; Kc2[idx] = Knew;
+    if (gen_anc) { gen_anc[idx] = par + anc_off; gen_asg[idx] = (unsigned char)j; }
     // copy the parent's slots (the chosen one is rewritten below)
     {
         const double *src = S + par;
@@ -765,31 +731,6 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
     }
 }
 
-// sharded run: particles received from other ranks (packed [row][k] per source segment)
-// are written to their local indices
-__global__ void __launch_bounds__(256) k_unpack(const double *__restrict__ recv, const RankOff *__restrict__ ro,
-                                                double *__restrict__ S2, int *__restrict__ Kc2, double *__restrict__ logw2,
-                                                unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
-                                                long long cap, int store_rows, int F, const SelScratch *guard)
-{
-    if (guard && guard->halt) return;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int s = 0;
-    const int G = ro->nranks;
-    while (s < G && t >= ro->recv_len[s]) { t -= ro->recv_len[s]; s++; }
-    if (s >= G) return;
-    const long long stride = ro->recv_len[s];
-    const double *src = recv + ro->recv_off[s] + t;
-    const long long idx = ro->recv_idx0[s] + t;
-    const double *hdr = src + (long long)store_rows * stride;
-    const int K = (int)hdr[stride];
-    logw2[idx] = hdr[0]; Kc2[idx] = K;
-    if (gen_anc) { gen_anc[idx] = (unsigned int)hdr[2 * stride]; gen_asg[idx] = (unsigned char)hdr[3 * stride]; }
-    const int nrows = K * F;
-    double *dst = S2 + idx;
-    for (int r = 0; r < nrows; r++) dst[(long long)r * cap] = src[(long long)r * stride];
-}
-
 // ------------------------------------------------------------------ reference-literal order
 // flat (particle-major, candidate-minor) key list; dead slots and dead particles get the
 // all-ones pattern so that a stable ascending sort leaves the M live putatives first, ties
@@ -810,8 +751,10 @@ __global__ void k_flat_keys(const double *__restrict__ V, const unsigned char *_
 // [resampled (ascending weight) ; kept (ascending weight)] (src/fearnhead.jl:172-179)
 __global__ void k_sorted_finalize(const StepState *__restrict__ st, const SelResult *__restrict__ res,
                                   const unsigned int *__restrict__ pick_pos, const unsigned int *__restrict__ vals, int slots,
-                                  unsigned int *__restrict__ surv_parent, unsigned char *__restrict__ surv_slot)
+                                  unsigned int *__restrict__ surv_parent, unsigned char *__restrict__ surv_slot,
+                                  const SelScratch *guard)
 {
+    if (guard && (guard->phase != 4 || guard->halt)) return;
     if (res->keep_all) return;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= st->n_next) return;
@@ -823,17 +766,24 @@ __global__ void k_sorted_finalize(const StepState *__restrict__ st, const SelRes
     surv_slot[t] = (unsigned char)((code % (unsigned int)slots) | (picked ? 0x80 : 0));
 }
 
-// fill the per-step log record (one thread)
-__global__ void k_steplog(const StepState *st, const SelResult *res, StepLog *lg, long long N, int dbg_status)
+// fill the per-step log record (one thread) and close the step: a search that did not finish in the
+// queued rounds halts the handle (every later kernel is a no-op, the host reports it); a sharded run
+// moves the shard's global offset and tells every rank that this rank's part of the next generation
+// is complete (exchange kind D)
+__global__ void k_steplog(StepState *st, const SelResult *res, StepLog *lg, SelScratch *sc, long long step, int dbg_status,
+                          const RankOff *ro, const Xch *x, unsigned long long seq)
 {
     if (threadIdx.x || blockIdx.x) return;
+    if (sc->halt) return;
+    if (sc->phase != 4) { sel_halt(sc, step, PF_HALT_SEARCH); return; }
     StepLog r;
     r.n_in = st->n_live; r.M = st->M; r.n_kept = st->n_kept; r.n_req = res->keep_all ? 0 : res->n;
-    r.n_got = st->n_picked; r.n_out = st->n_next; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
+    r.n_got = st->n_picked; r.n_out = ro ? ro->n_global : st->n_next; r.overflow = st->overflow; r.n_cand = res->n_cand_first; r.n_plateau = res->n_plateau_first;
     r.log_total = res->log_total; r.lw_resamp = res->lw_resamp; r.thr = res->thr_value; r.cv = 0.0;
-    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds + (dbg_status ? 1000 * res->status : 0);
+    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds + (dbg_status ? 1000 * res->status : 0); r.status = res->status; r.pad = 0;
     r.sel_us[0] = (res->t_ns[1] - res->t_ns[0]) * 1e-3; r.sel_us[1] = (res->t_ns[2] - res->t_ns[1]) * 1e-3;
     r.sel_us[2] = (res->t_ns[3] - res->t_ns[2]) * 1e-3; r.sel_us[3] = (res->t_ns[4] - res->t_ns[0]) * 1e-3;
-    (void)N;
     *lg = r;
+    if (ro) st->goff = ro->goff_next;
+    if (x) xch_signal(x, XCH_D, seq);
 }

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,7 @@ struct pf_filter_s {
     long long fuse_stride = 1;
     bool fused = true;                    // single-GPU index-order Fearnhead: classify inside the expansion
     int sel_margin = 8;                   // half-width of the sample bracket in sigmas (PF_SEL_MARGIN; tests shrink it)
+    int dbg_status = 0;                   // PF_DEBUG_STATUS (read once at pf_create): selection status bits in the step log
     double *cand = nullptr;
     long long cand_cap = 0;
     SelScratch *sc = nullptr;
@@ -63,27 +65,24 @@ struct pf_filter_s {
     double *cl_part = nullptr;
     // sharded run
     int rank = 0, nranks = 1;
-    long long *gscal = nullptr;           // {M, vmax bits} published for the all-reduce
-    TileSum *local_tot = nullptr;
     RankOff *ro = nullptr;
-    double *sendbuf = nullptr, *recvbuf = nullptr;
-    long long buf_cap = 0;
-    int mig_rows = 0;
     long long surv_cap = 0;
-    int mg_rounds = 0;
-    long long mg_stride = 1, mg_sample_entries = 0, mg_cand_entries = 0, mg_window = 0;
     bool own_stream = true;
-    PeerTable *peers[2] = {nullptr, nullptr};   // direct exchange: peer arrays of the buffer written at even / odd steps
+    std::shared_ptr<void> shared_stream;  // lock-step group: one stream for all shards of a device, destroyed with the last of them
+    XchRegion *xreg = nullptr;            // this rank's exchange region (peers store into it)
+    size_t xreg_bytes = 0;
+    long long capA = 0, capB = 0;
+    Xch xch_host;                         // regions of all ranks as mapped in this process
+    Xch *xch = nullptr;                   // device copy (null until pf_mg_connect)
+    PeerTable *peers[2] = {nullptr, nullptr};   // peer arrays of the store buffer written at even / odd steps
     PeerTable peers_host[2];
-    bool direct = false;
+    bool connected = false, lockstep = false;
     std::vector<void *> ipc_opened;
-    double *y1_dev = nullptr;             // y (d) + u (1) of the current sharded step
-    double *y1_pin = nullptr;             // pinned staging ring for (y, u)
-    int y1_slot = 0;
     // genealogy
     unsigned int *gen_anc = nullptr;
     unsigned char *gen_asg = nullptr;
     long long hist_cap = 0;
+    bool hist_auto = false;               // pf_config.history < 0: the genealogy grows on demand
     // host mirrors
     long long steps = 0;
     long long n_host = 0;                 // population size after the last synchronised step
@@ -92,6 +91,9 @@ struct pf_filter_s {
     StepLog last{};
     bool have_last = false, last_stale = false;
     int sel_grid = 0;
+    int cluster_size = 8;                 // CTAs of the cluster the bracket / solve kernels run on
+    int retries = SEL_RETRIES;            // queued extra search rounds per step
+    int redo = 0;                         // the next step re-runs a halted one
     int num_sms = 0;
     double last_ms = 0.0;
     long long last_launches = 0;
@@ -213,17 +215,18 @@ extern "C" int32_t pf_destroy(pf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
-                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->gscal, h->local_tot, h->ro, h->sendbuf,
-                    h->recvbuf, h->y1_dev, h->peers[0], h->peers[1], h->srec.x, h->srec.m};
+                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
+                    h->peers[0], h->peers[1], h->srec.x, h->srec.m};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-    if (h->y1_pin) cudaFreeHost(h->y1_pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return PF_OK;
 }
+
+static int32_t setup_cluster_kernels(pf_handle h);
 
 extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
 {
@@ -242,7 +245,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (!(cfg->nu0 > d - 1.0)) return set_error(nullptr, PF_ERR_ARG, "pf_create: nu0 must exceed d - 1");
     if (!cfg->mu0) return set_error(nullptr, PF_ERR_ARG, "pf_create: mu0 is null");
     if (cfg->order != PF_ORDER_INDEX && cfg->order != PF_ORDER_SORTED) return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown order");
-    if (cfg->history < 0) return set_error(nullptr, PF_ERR_ARG, "pf_create: history must be >= 0");
+    if (cfg->history < 0 && cfg->nranks > 1) return set_error(nullptr, PF_ERR_ARG, "pf_create: a sharded handle needs a fixed history capacity (>= 0)");
     if (cfg->nranks > 1) {
         if (cfg->nranks > PF_MAX_RANKS || cfg->rank < 0 || cfg->rank >= cfg->nranks) return set_error(nullptr, PF_ERR_ARG, "pf_create: bad rank / nranks");
         if (cfg->filter_kind != PF_FEARNHEAD || cfg->order != PF_ORDER_INDEX) return set_error(nullptr, PF_ERR_ARG, "pf_create: sharded runs support the index-order Fearnhead filter");
@@ -259,7 +262,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     h->nranks = cfg->nranks > 1 ? cfg->nranks : 1;
     h->rank = h->nranks > 1 ? cfg->rank : 0;
     h->cap = (cfg->n_particles + h->nranks - 1) / h->nranks;
-    if (h->nranks > 1) h->cap += h->cap / 2 + 64;          // slack: children stay on their parent's rank while shares fit
+    if (h->nranks > 1) h->cap += 64;                      // equal blocks of ceil(n / G) at every step
     h->F = 2 + d + d * (d + 1) / 2;
     h->mu0.assign(cfg->mu0, cfg->mu0 + d);
     h->lam0.assign(d * d, 0.0);
@@ -295,14 +298,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->surv_parent, h->surv_cap));
     CT(dmalloc(&h->surv_slot, h->surv_cap));
     if (h->nranks > 1) {
-        h->mig_rows = h->k_max * h->F + 4;
-        // neighbour window: 0 = children simply stay on their parent's rank until a share outgrows the shard
-        // (measured on 8xB200: the fixed-capacity neighbour messages cost more than the imbalance they remove)
-        h->mg_window = getenv("PF_MG_WINDOW") ? atoll(getenv("PF_MG_WINDOW")) : 0;
-        h->buf_cap = (2 * cap + 1024) * (long long)h->mig_rows;
-        CT(dmalloc(&h->gscal, 4)); CT(dmalloc(&h->local_tot, 1)); CT(dmalloc(&h->ro, 1));
-        CT(dmalloc(&h->sendbuf, (size_t)h->buf_cap)); CT(dmalloc(&h->recvbuf, (size_t)h->buf_cap));
-        CT(dmalloc(&h->y1_dev, (size_t)d + 1));
+        CT(dmalloc(&h->ro, 1));
         CT(cudaMemsetAsync(h->ro, 0, sizeof(RankOff), h->stream));
     }
     long long ntiles = (cap + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -324,6 +320,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     h->fuse_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
     h->fused = getenv("PF_NO_FUSE") == nullptr;
     h->sel_margin = getenv("PF_SEL_MARGIN") ? std::max(1, atoi(getenv("PF_SEL_MARGIN"))) : 8;
+    h->dbg_status = getenv("PF_DEBUG_STATUS") ? 1 : 0;
     CT(dmalloc(&h->sc, 1));
     CT(dmalloc(&h->res, 1));
     CT(dmalloc(&h->st, 1));
@@ -331,22 +328,33 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->stc, 1));
     CT(cudaMemsetAsync(h->sc, 0, sizeof(SelScratch), h->stream));
     CT(cudaMemsetAsync(h->res, 0, sizeof(SelResult), h->stream));
-    // cooperative grid of the threshold search
-    CT(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SMEM_BYTES));
-    int occ = 0;
-    CT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SMEM_BYTES));
-    if (occ < 1) { pf_destroy(h); return set_error(nullptr, PF_ERR_CUDA, "pf_create: k_select does not fit on an SM"); }
-    h->sel_grid = h->num_sms * (occ > 2 ? 2 : occ);
+    // grid of the classify pass; cluster size of the bracket / solve kernels (16 CTAs if the device can
+    // schedule such a cluster, else the portable 8)
+    {
+        int occ = 0;
+        CT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_classify, SEL_THREADS, 0));
+        h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
+        int32_t rc = setup_cluster_kernels(h);
+        if (rc != PF_OK) { g_create_error = h->err; pf_destroy(h); return rc; }
+    }
     h->cand_cap = (long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
     if (h->nranks > 1) {
-        const long long pad = (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK;
-        const long long spad = (long long)SEL_SAMPLE_WARPS * SEL_CHUNK;
-        h->mg_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));   // = fuse_stride
-        h->mg_sample_entries = (2 * SEL_SAMPLE_TARGET + h->nranks - 1) / h->nranks + spad + 1024;
-        h->mg_cand_entries = std::max<long long>(1 << 17, (2ll << 20) / h->nranks) + pad;
-        h->cand_cap = std::max(h->cand_cap, std::max(h->mg_sample_entries, h->mg_cand_entries) + pad);
+        // exchange region: sample segments (a shard's sample is at most its sampled particles x slots) and
+        // candidate segments (two round buffers; a widened bracket may hold a few per cent of the shard's putatives)
+        h->capA = ((cap + h->fuse_stride - 1) / h->fuse_stride + 8) * (h->k_max + 1) + 1024;
+        h->capB = std::max<long long>(1 << 20, 2 * cap);
+        if (getenv("PF_MG_CAPB")) h->capB = std::max<long long>(64, atoll(getenv("PF_MG_CAPB")));      // tests: force the overflow path
+        h->xreg_bytes = xch_region_bytes(h->nranks, h->capA, h->capB);
+        CT(cudaMalloc((void **)&h->xreg, h->xreg_bytes));
+        CT(cudaMemsetAsync(h->xreg, 0, xch_header_bytes(), h->stream));
+        memset(&h->xch_host, 0, sizeof h->xch_host);
+        h->xch_host.rank = h->rank; h->xch_host.nranks = h->nranks; h->xch_host.capA = h->capA; h->xch_host.capB = h->capB;
+        h->xch_host.timeout_ns = 1000000ull * (unsigned long long)(getenv("PF_MG_TIMEOUT_MS") ? atoll(getenv("PF_MG_TIMEOUT_MS")) : 20000);
+        h->xch_host.reg[h->rank] = h->xreg;
+        memset(h->peers_host, 0, sizeof h->peers_host);
     }
     CT(dmalloc(&h->cand, (size_t)h->cand_cap));
+    h->hist_auto = cfg->history < 0;
     if (cfg->history > 0) {
         h->hist_cap = cfg->history;
         CT(dmalloc(&h->gen_anc, (size_t)h->hist_cap * cap));
@@ -396,21 +404,83 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
 // ------------------------------------------------------------------ the step sequences
 static inline int grid_for(long long n, int bs) { long long g = (n + bs - 1) / bs; return (int)(g < 1 ? 1 : g); }
 
-static int32_t launch_select(pf_handle h, const double *V, const unsigned char *cnt, long long cap, const long long *n_live,
-                             const long long *M, const u64 *vmax, long long N, const double *u_dev, double *cand,
-                             long long cand_cap, SelScratch *sc, SelResult *res, int stage = SEL_ST_ALL, int external_sample = 0,
-                             int preclassified = 0, long long fixed_stride = -1)
+// ---- the threshold search: cluster launches, argument block, launch sequences
+static cudaError_t launch_cluster(void (*kern)(SelArgs), int csize, cudaStream_t stream, const SelArgs &a)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(csize); cfg.blockDim = dim3(SEL_THREADS); cfg.dynamicSmemBytes = SEL_SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+// 16-CTA clusters are a non-portable size: ask the device whether it can co-schedule one, else use 8
+static int32_t setup_cluster_kernels(pf_handle h)
+{
+    void (*kerns[2])(SelArgs) = {k_sel_bracket, k_sel_solve};
+    int best = SEL_MAX_CLUSTER;
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        int ok_size = 8;
+        for (int cs = SEL_MAX_CLUSTER; cs >= 8; cs >>= 1) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(SEL_THREADS); cfg.dynamicSmemBytes = SEL_SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, kerns[k], &cfg) == cudaSuccess && ncl >= 1) { ok_size = cs; break; }
+            cudaGetLastError();
+        }
+        best = std::min(best, ok_size);
+    }
+    if (getenv("PF_SEL_CLUSTER")) { int cs = atoi(getenv("PF_SEL_CLUSTER")); if (cs == 1 || cs == 2 || cs == 4 || cs == 8 || cs == 16) best = std::min(best, cs); }
+    h->cluster_size = best;
+    return PF_OK;
+}
+
+static SelArgs sel_args(pf_handle h, const double *V, const unsigned char *cnt, long long cap, const long long *n_live,
+                        const long long *M, const u64 *vmax, long long N, const double *u_dev, double *cand, long long cand_cap,
+                        SelScratch *sc, SelResult *res)
 {
     SelArgs a;
+    memset(&a, 0, sizeof a);
     a.V = V; a.cnt = cnt; a.cap = cap; a.n_live = n_live; a.M = M; a.vmax_bits = vmax; a.N = N; a.u = u_dev;
     a.cand = cand; a.cand_cap = cand_cap; a.sc = sc; a.res = res;
-    a.margin = h->sel_margin;
-    a.stage = stage; a.round0 = 0; a.nranks = 1; a.gacc = nullptr; a.glist = nullptr; a.glist_each = 0; a.goff = nullptr; a.pad_to = -1;
-    a.fixed_stride = fixed_stride >= 0 ? fixed_stride : h->fuse_stride;       // the same strided sample on every path
-    a.external_sample = external_sample; a.preclassified = preclassified;
+    a.stage = SEL_ST_PUB | SEL_ST_RUN; a.margin = h->sel_margin; a.fixed_stride = h->fuse_stride;
     a.plateau_ptr = (sc == h->sc && h->stc) ? &h->stc->plateau_bits : nullptr;
-    void *args[] = {&a};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
+    a.step = h->steps; a.seq = (unsigned long long)h->steps + 1;
+    return a;
+}
+
+// [classify] + solve of one round (retry = 0: the round behind the expansion; 1: a queued extra round)
+static int32_t launch_round(pf_handle h, SelArgs a, int retry, int solve_stage = SEL_ST_PUB | SEL_ST_RUN)
+{
+    a.retry = retry;
+    k_sel_classify<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
+    a.stage = solve_stage;
+    CUDA_TRY(launch_cluster(k_sel_solve, h->cluster_size, h->stream, a));
+    h->launches += 2;
+    return PF_OK;
+}
+
+// classic search on an existing V: reset, strided sample, bracket, rounds
+static int32_t launch_classic_search(pf_handle h, SelArgs a)
+{
+    a.external_sample = 0; a.preclassified = 0;
+    k_sel_reset<<<1, 32, 0, h->stream>>>(a);
+    k_sel_sample<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
+    CUDA_TRY(launch_cluster(k_sel_bracket, h->cluster_size, h->stream, a));
+    h->launches += 3;
+    for (int r = 0; r <= h->retries; r++) {
+        int32_t rc = launch_round(h, a, r > 0);
+        if (rc != PF_OK) return rc;
+    }
     return PF_OK;
 }
 
@@ -430,7 +500,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     h->epoch++;
     {
         LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, nullptr, h->res);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->redo ? 2 : (h->steps == 0 ? 1 : 0), h->sc, h->res, nullptr, 0, h->steps);
     }
     const bool fused = h->fused && h->cfg.order == PF_ORDER_INDEX;
     if (fused) {
@@ -438,13 +508,12 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         {
             LaunchTimer lt(h, KC_SELECT, 2);
             const long long ns = 4 * ((ub + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride));     // groups of 4 particles
-            CUDA_TRY(cudaMemsetAsync((char *)h->sc + offsetof(SelScratch, list_n), 0, sizeof(long long), h->stream));
             k_expand<D, 1><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,
                                                                        nullptr);
-            int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand,
-                                       h->cand_cap, h->sc, h->res, SEL_ST_BRACKET, 1, 0, h->fuse_stride);
-            if (rc != PF_OK) return rc;
+            SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
+            a.external_sample = 1;
+            CUDA_TRY(launch_cluster(k_sel_bracket, h->cluster_size, h->stream, a));
         }
         {
             LaunchTimer lt(h, KC_EXPAND);
@@ -452,22 +521,29 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
                                                                        h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
         }
         {
-            LaunchTimer lt(h, KC_SELECT);
-            int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
-                                       h->cand_cap, h->sc, h->res, SEL_ST_CLASSIFY | SEL_ST_SOLVE, 0, 1, 0);
-            if (rc != PF_OK) return rc;
+            LaunchTimer lt(h, KC_SELECT, 2 * (h->retries + 1));
+            SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
+            a.external_sample = 1; a.preclassified = 1;
+            const long long l0 = h->launches;
+            for (int r = 0; r <= h->retries; r++) {
+                int32_t rc = launch_round(h, a, r > 0);
+                if (rc != PF_OK) return rc;
+            }
+            h->launches = l0;                   // (counted by the LaunchTimer)
         }
     } else {
         {
             LaunchTimer lt(h, KC_EXPAND);
             k_expand<D, 0><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                       h->stc, h->st, h->V, h->cnt, nullptr, 1, nullptr, nullptr, nullptr);
+                                                                       h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
         }
         {
-            LaunchTimer lt(h, KC_SELECT);
-            int32_t rc = launch_select(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand,
-                                       h->cand_cap, h->sc, h->res);
+            LaunchTimer lt(h, KC_SELECT, 3 + 2 * (h->retries + 1));
+            SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
+            const long long l0 = h->launches;
+            int32_t rc = launch_classic_search(h, a);
             if (rc != PF_OK) return rc;
+            h->launches = l0;
         }
     }
     if (h->cfg.order == PF_ORDER_SORTED) {
@@ -482,34 +558,34 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         // resampling step: comb over the sorted list; exhaustive step: index order
         LaunchTimer lt(h, KC_SCAN, 7);
         const int gflat = grid_for(n_pad, SCAN_THREADS), gidx = grid_for(ub, SCAN_THREADS);
-        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, nullptr, nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr, nullptr);
+        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, h->sc, nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr, 0, h->sc);
         k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles,
-                                                             h->pick_pos, h->surv_slot, 1, nullptr, nullptr, cap);
+                                                             h->pick_pos, h->surv_slot, 1, nullptr, h->sc, cap);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
-                                                                           h->surv_slot);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, nullptr, nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr, nullptr);
+                                                                           h->surv_slot, h->sc);
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, h->sc, nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr, 0, h->sc);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 2, nullptr, nullptr, cap);
+                                                            h->surv_slot, 2, nullptr, h->sc, cap);
     } else {
         LaunchTimer lt(h, KC_SCAN, 4);
         const int gidx = grid_for(ub, SCAN_THREADS);
         if (fused) k_tile_fixup<<<grid_for(gidx, 256), 256, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, nullptr, fused ? h->sc : nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, nullptr);
+        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, fused ? h->sc : nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, 0, h->sc);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
-                                                            h->surv_slot, 0, nullptr, nullptr, cap, fused ? h->srec : ScanRec{nullptr, nullptr}, h->sc);
+                                                            h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr}, h->sc);
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
         k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, nullptr, nullptr, h->k_max, nullptr, &h->st->M_next, nullptr, 0);
+                                                                          h->surv_slot, ga, gs, nullptr, h->k_max, h->sc, &h->st->M_next, nullptr, 0);
     }
     {
         LaunchTimer lt(h, KC_STEPLOG);
-        k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->N, getenv("PF_DEBUG_STATUS") ? 1 : 0);
+        k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->sc, h->steps, h->dbg_status, nullptr, nullptr, 0);
     }
     CUDA_TRY(cudaGetLastError());
     h->cur = nxt;
@@ -530,7 +606,7 @@ static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_de
     const int g256 = grid_for(N, 256);
     {
         LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, nullptr, nullptr);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, nullptr, nullptr, nullptr, 0, h->steps);
     }
     {
         LaunchTimer lt(h, KC_CL_PROP);
@@ -561,6 +637,30 @@ static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_de
     return PF_OK;
 }
 
+// history < 0: make room for `need` generations (doubling; the old generations are copied over)
+static int32_t ensure_history(pf_handle h, long long need)
+{
+    if (!h->hist_auto || need <= h->hist_cap) return PF_OK;
+    long long ncap = std::max<long long>(std::max<long long>(need, 2 * h->hist_cap), 16);
+    unsigned int *na = nullptr; unsigned char *ns = nullptr;
+    cudaError_t e = dmalloc(&na, (size_t)ncap * h->cap);
+    if (e == cudaSuccess) e = dmalloc(&ns, (size_t)ncap * h->cap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (na) cudaFree(na);
+        return set_error(h, PF_ERR_HISTORY, "the genealogy no longer fits in device memory: create the filter with history = 0 (none) or a fixed capacity");
+    }
+    if (h->steps > 0 && h->gen_anc) {
+        CUDA_TRY(cudaMemcpyAsync(na, h->gen_anc, sizeof(unsigned int) * (size_t)h->steps * h->cap, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(ns, h->gen_asg, (size_t)h->steps * h->cap, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (h->gen_anc) cudaFree(h->gen_anc);
+    if (h->gen_asg) cudaFree(h->gen_asg);
+    h->gen_anc = na; h->gen_asg = ns; h->hist_cap = ncap;
+    return PF_OK;
+}
+
 static int32_t run_steps(pf_handle h, const double *ys, long long T, const double *uniforms, long long ups, double *log_evidence)
 {
     if (!h) return PF_ERR_ARG;
@@ -573,6 +673,8 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
     }
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     int32_t rc = ensure_table(h, h->steps + T + 2);
+    if (rc != PF_OK) return rc;
+    rc = ensure_history(h, h->steps + T);
     if (rc != PF_OK) return rc;
     const int d = h->d;
     if (T * d > h->ys_cap) {
@@ -603,18 +705,45 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
         CUDA_TRY(cudaStreamSynchronize(h->stream));      // ubuf goes out of scope
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     }
-    for (long long t = 0; t < T; t++) {
-        if (fh) {
-            DISPATCH_D(d, rc = fearnhead_step<D>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t));
-        } else {
-            const double *ud = nullptr;
-            if (uniforms) {
-                CUDA_TRY(cudaMemcpyAsync(h->u_dev, uniforms + t * ups, sizeof(double) * 2 * h->N, cudaMemcpyHostToDevice, h->stream));
-                ud = h->u_dev;
+    // Every step of the call is queued without a host round trip.  A Fearnhead step whose threshold search
+    // needed more rounds than were queued halts the handle on the device (later kernels are no-ops); the
+    // host then runs that step again with more rounds queued and resumes behind it.
+    const long long steps0 = h->steps;
+    const int cur0 = h->cur;
+    std::vector<long long> ub_hist(T + 1, h->ub_live);
+    long long t_begin = 0;
+    for (int attempt = 0; ; attempt++) {
+        for (long long t = t_begin; t < T; t++) {
+            ub_hist[t] = h->ub_live;
+            if (fh) {
+                DISPATCH_D(d, rc = fearnhead_step<D>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t));
+                h->redo = 0; h->retries = SEL_RETRIES;
+            } else {
+                const double *ud = nullptr;
+                if (uniforms) {
+                    CUDA_TRY(cudaMemcpyAsync(h->u_dev, uniforms + t * ups, sizeof(double) * 2 * h->N, cudaMemcpyHostToDevice, h->stream));
+                    ud = h->u_dev;
+                }
+                DISPATCH_D(d, rc = chenliu_step<D>(h, h->ys_dev + t * d, ud, h->slog + t));
             }
-            DISPATCH_D(d, rc = chenliu_step<D>(h, h->ys_dev + t * d, ud, h->slog + t));
+            if (rc != PF_OK) { cudaStreamSynchronize(h->stream); return rc; }
         }
-        if (rc != PF_OK) { cudaStreamSynchronize(h->stream); return rc; }
+        long long halt[2] = {0, 0};
+        if (fh) CUDA_TRY(cudaMemcpyAsync(halt, &h->sc->halt, sizeof halt, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (!halt[0]) break;
+        const long long th = halt[0] - 1 - steps0;          // index of the halted step within this call
+        const int reason = (int)(halt[1] & 0xffffffffll);
+        if (th < 0 || th >= T || reason != PF_HALT_SEARCH || attempt >= 3) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "step %lld could not be completed on the device (reason %d, attempt %d)", halt[0] - 1, reason, attempt);
+            return set_error(h, PF_ERR_STATE, buf);
+        }
+        // rewind the host mirrors to the halted step and run it again with more rounds queued
+        h->steps = steps0 + th; h->cur = cur0 ^ (int)(th & 1); h->ub_live = ub_hist[th];
+        h->redo = 1; h->retries = 12;
+        CUDA_TRY(cudaMemsetAsync(&h->sc->halt, 0, 2 * sizeof(long long), h->stream));
+        t_begin = th;
     }
     h->logs.resize(T);
     CUDA_TRY(cudaMemcpyAsync(h->logs.data(), h->slog, sizeof(StepLog) * T, cudaMemcpyDeviceToHost, h->stream));
@@ -631,7 +760,6 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
         CUDA_TRY(cudaMemcpy(&cs, h->cl, sizeof cs, cudaMemcpyDeviceToHost));
         h->cur = cs.cur;
     }
-    if (fh && h->n_host < h->ub_live && h->n_host >= 1) { /* keep the conservative bound */ }
     if (log_evidence) for (long long t = 0; t < T; t++) log_evidence[t] = h->logs[t].log_total;
     return PF_OK;
 }
@@ -743,6 +871,7 @@ extern "C" int32_t pf_get_assignments(pf_handle h, int32_t *out)
 {
     if (!h || !out) return PF_ERR_ARG;
     if (!h->hist_cap) return set_error(h, PF_ERR_HISTORY, "pf_get_assignments: history is disabled (pf_config.history = 0)");
+    if (h->nranks > 1) return set_error(h, PF_ERR_STATE, "pf_get_assignments: a sharded handle holds global parent indices; use pf_mg_get_assignments");
     const long long T = h->steps, n = h->n_host;
     if (T == 0 || n == 0) return PF_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -774,7 +903,7 @@ extern "C" int32_t pf_get_last_step(pf_handle h, pf_step_stats *o)
     o->step = h->steps; o->n_in = r.n_in; o->n_putative = r.M; o->n_kept = r.n_kept; o->n_resamp_req = r.n_req;
     o->n_resamp_got = r.n_got; o->n_out = r.n_out; o->overflow = r.overflow; o->log_total_w = r.log_total;
     o->log_w_resamp = r.lw_resamp; o->threshold = r.thr; o->cv = r.cv; o->resampled = r.resampled;
-    o->select_rounds = r.rounds; o->n_candidates = r.n_cand;
+    o->select_rounds = r.rounds; o->n_candidates = r.n_cand; o->n_plateau = r.n_plateau; o->select_status = r.status;
     for (int k = 0; k < 4; k++) o->select_phase_us[k] = r.sel_us[k];
     return PF_OK;
 }
@@ -840,6 +969,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
     pf_filter_s tmp;             // only for error text / stream bookkeeping
     pf_handle h = &tmp;
     if (!w || M < 1 || N < 1 || !survivors || M > (1ll << 28)) return set_error(nullptr, PF_ERR_ARG, "pf_select: bad argument");
+    h->stc = nullptr;
     if (!(u >= 0.0 && u < 1.0)) return set_error(nullptr, PF_ERR_ARG, "pf_select: u must be in [0, 1)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(nullptr, PF_ERR_CUDA, "pf_select: no CUDA device (no CPU fallback)"); }
@@ -858,10 +988,14 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         ST(cudaGetDeviceProperties(&prop, device));
         h->num_sms = prop.multiProcessorCount;
         ST(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        ST(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SMEM_BYTES));
-        int occ = 0;
-        ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select, SEL_THREADS, SEL_SMEM_BYTES));
-        h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
+        {
+            int occ = 0;
+            ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_classify, SEL_THREADS, 0));
+            h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
+            rc = setup_cluster_kernels(h);
+            if (rc != PF_OK) { g_create_error = h->err; goto done; }
+            h->sel_margin = getenv("PF_SEL_MARGIN") ? std::max(1, atoi(getenv("PF_SEL_MARGIN"))) : 8;
+        }
         h->fuse_stride = std::max<long long>(1, (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET);
         long long cand_cap = M + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
         long long ntiles = (M + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -889,16 +1023,28 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
             Vsel = (const double *)keys;           // sorted weights (bit patterns are the doubles)
         }
         k_vmax<<<h->num_sms * 4, 256, 0, h->stream>>>(Vsel, M, st);
-        rc = launch_select(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res);
+        h->retries = 12;                  // stand-alone call: queue enough rounds for any input
+        rc = launch_classic_search(h, sel_args(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res));
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
-        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, nullptr, nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr, nullptr);
-        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr, nullptr, M);
+        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, sc, nullptr);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr, 0, sc);
+        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr, sc, M);
         ST(cudaGetLastError());
         StepState s1; SelResult r1;
+        int phase_end = 0;
         ST(cudaMemcpyAsync(&s1, st, sizeof s1, cudaMemcpyDeviceToHost, h->stream));
         ST(cudaMemcpyAsync(&r1, res, sizeof r1, cudaMemcpyDeviceToHost, h->stream));
+        ST(cudaMemcpyAsync(&phase_end, &sc->phase, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         ST(cudaStreamSynchronize(h->stream));
+        if (phase_end != 4) {
+            SelScratch hs;
+            cudaMemcpy(&hs, sc, offsetof(SelScratch, final_vals), cudaMemcpyDeviceToHost);
+            char buf[400];
+            snprintf(buf, sizeof buf, "pf_select: the threshold search did not converge (phase %d mode %d rounds %d status %d lo %llx hi %llx scale %d "
+                     "count_in %lld n_fail %d n_cand %llu A_hi %llu final_n %u chunks %llu)", hs.phase, hs.mode, r1.rounds, r1.status,
+                     (unsigned long long)hs.lo, (unsigned long long)hs.hi, hs.scale, hs.count_in, hs.n_fail, hs.n_cand, hs.A_hi, hs.final_n, hs.cand_chunks);
+            rc = set_error(nullptr, PF_ERR_STATE, buf); goto done;
+        }
         long long n_out = s1.n_next;
         std::vector<unsigned int> p(n_out > 0 ? n_out : 1);
         std::vector<unsigned char> sl(n_out > 0 ? n_out : 1);
@@ -942,35 +1088,11 @@ done:
     return rc;
 }
 
-// ------------------------------------------------------------------ sharded run (bring your own collective)
-__global__ void k_publish_scalars(const StepState *st, SelScratch *sc)
-{
-    if (threadIdx.x || blockIdx.x || sc->halt) return;
-    sc->M_local = (unsigned long long)st->M; sc->vmax_local = st->vmax_bits;
-}
-
-// sharded look-ahead: decide whether this step needs the host (search unfinished, particles must
-// change owner, or a list overflowed); if so every later kernel is a no-op until pf_mg_resume
-__global__ void k_close(SelScratch *sc, const RankOff *ro, long long step, long long surv_cap)
-{
-    if (threadIdx.x || blockIdx.x || sc->halt) return;
-    if (sc->phase != 4 || ro->exchange == 1 || ro->n_local > surv_cap) sc->halt = step + 1;
-}
-
-__global__ void k_steplog_mg(StepState *st, const SelResult *res, const RankOff *ro, StepLog *lg, const SelScratch *guard)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    if (guard && guard->halt) return;
-    StepLog r;
-    r.n_in = st->n_live; r.M = st->M; r.n_kept = st->n_kept; r.n_req = res->keep_all ? 0 : res->n;
-    r.n_got = st->n_picked; r.n_out = ro->n_global; r.overflow = st->overflow; r.n_cand = res->n_cand_first;
-    r.log_total = res->log_total; r.lw_resamp = res->lw_resamp; r.thr = res->thr_value; r.cv = 0.0;
-    r.resampled = res->keep_all ? 0 : 1; r.rounds = res->rounds;
-    for (int k = 0; k < 4; k++) r.sel_us[k] = 0.0;
-    *lg = r;
-    st->goff = ro->bnd[ro->rank];
-}
-
+// ------------------------------------------------------------------ sharded run
+// Particles block-sharded over ranks (one handle per GPU; one process per GPU, or several handles in
+// one process).  Every exchange of a step is done by the kernels themselves through peer memory
+// (select.cuh, "peer exchange"); the host only queues launches: no collective library, no host round
+// trip inside pf_mg_filter.
 #define MG_CHECK(h) do { if (!(h)) return PF_ERR_ARG; if ((h)->nranks < 2) return set_error((h), PF_ERR_STATE, "not a sharded handle (pf_config.nranks < 2)"); } while (0)
 
 extern "C" int32_t pf_set_stream(pf_handle h, void *cuda_stream)
@@ -983,193 +1105,44 @@ extern "C" int32_t pf_set_stream(pf_handle h, void *cuda_stream)
     return PF_OK;
 }
 
-extern "C" int32_t pf_mg_info(pf_handle h, pf_mg_ptrs *o)
-{
-    MG_CHECK(h);
-    if (!o) return PF_ERR_ARG;
-    o->scalars = h->gscal;
-    o->acc = (char *)h->sc + SEL_ACC_OFFSET; o->acc_bytes = sizeof(SelAcc);
-    o->list = h->cand; o->list_capacity = h->cand_cap;
-    o->local_total = h->local_tot; o->total_bytes = sizeof(TileSum);
-    o->send_buffer = h->sendbuf; o->recv_buffer = h->recvbuf; o->buffer_capacity = h->buf_cap;
-    o->rows_per_particle = h->mig_rows; o->local_capacity = h->cap;
-    o->sample_entries = h->mg_sample_entries; o->cand_entries = h->mg_cand_entries; o->window = h->mg_window;
-    return PF_OK;
-}
-
-template <int D>
-static int32_t mg_begin(pf_handle h)
-{
-    if (h->slog_cap < 1) { CUDA_TRY(dmalloc(&h->slog, 16)); h->slog_cap = 16; }
-    k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, h->y1_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc, h->res);
-    k_expand<D, 0><<<grid_for(h->cap, 256), 256, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->k_max, h->tab,
-                                                                   h->pc, h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
-    k_publish_scalars<<<1, 32, 0, h->stream>>>(h->st, h->sc);
-    h->launches += 3;
-    return PF_OK;
-}
-
-extern "C" int32_t pf_mg_begin(pf_handle h, const double *y, double u)
-{
-    MG_CHECK(h);
-    if (!y) return PF_ERR_ARG;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    int32_t rc = ensure_table(h, h->steps + 3);
-    if (rc != PF_OK) return rc;
-    if (h->hist_cap && h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
-    if (!h->y1_pin) CUDA_TRY(cudaMallocHost((void **)&h->y1_pin, sizeof(double) * 64 * (PF_MAX_D + 1)));
-    double *buf = h->y1_pin + (size_t)(h->y1_slot++ & 63) * (PF_MAX_D + 1);   // 64 steps ahead of any reuse: the step's sync bounds the lag
-    for (int k = 0; k < h->d; k++) buf[k] = y[k];
-    buf[h->d] = u;
-    CUDA_TRY(cudaMemcpyAsync(h->y1_dev, buf, sizeof(double) * (h->d + 1), cudaMemcpyHostToDevice, h->stream));
-    h->mg_rounds = 0;
-    DISPATCH_D(h->d, rc = mg_begin<D>(h));
-    CUDA_TRY(cudaGetLastError());
-    return rc;
-}
-
-extern "C" int32_t pf_mg_select(pf_handle h, int32_t stage, int32_t rounds_done, const void *gacc, const void *glist, int64_t list_each,
-                                int64_t pad_to)
-{
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    SelArgs a;
-    a.V = h->V; a.cnt = h->cnt; a.cap = h->cap; a.n_live = &h->st->n_live;
-    a.M = h->gscal; a.vmax_bits = (const u64 *)(h->gscal + 1);
-    a.N = h->N; a.u = h->y1_dev + h->d; a.cand = h->cand; a.cand_cap = h->cand_cap; a.sc = h->sc; a.res = h->res;
-    a.margin = h->sel_margin;
-    a.stage = stage; a.round0 = rounds_done; a.nranks = h->nranks; a.gacc = (const SelAcc *)gacc;
-    a.glist = (const double *)glist; a.glist_each = list_each;
-    a.goff = &h->st->goff; a.pad_to = pad_to; a.fixed_stride = h->mg_stride; a.external_sample = 0; a.preclassified = 0;
-    a.plateau_ptr = &h->stc->plateau_bits;
-    if ((stage & SEL_ST_BRACKET) && gacc) { k_mg_globals<<<1, 32, 0, h->stream>>>((const SelAcc *)gacc, h->nranks, h->gscal); h->launches++; }
-    void *args[] = {&a};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_select, dim3(h->sel_grid), dim3(SEL_THREADS), args, SEL_SMEM_BYTES, h->stream));
-    h->launches++;
-    return PF_OK;
-}
-
-extern "C" int32_t pf_mg_state(pf_handle h, int64_t state[4])
-{
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    SelScratch hdr;
-    CUDA_TRY(cudaMemcpyAsync(&hdr, h->sc, offsetof(SelScratch, B_run), cudaMemcpyDeviceToHost, h->stream));
-    long long gs[2];
-    CUDA_TRY(cudaMemcpyAsync(gs, h->gscal, sizeof gs, cudaMemcpyDeviceToHost, h->stream));
-    SelResult r;
-    CUDA_TRY(cudaMemcpyAsync(&r, h->res, sizeof r, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    state[0] = hdr.phase;
-    state[1] = (int64_t)hdr.cand_chunks * SEL_CHUNK;
-    state[2] = (gs[0] > h->N && gs[1] != 0 && gs[0] > SEL_FINAL_CAP) ? 1 : 0;
-    state[3] = r.rounds;
-    return PF_OK;
-}
-
-extern "C" int32_t pf_mg_tiles(pf_handle h)
-{
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const int g = grid_for(h->cap, SCAN_THREADS);
-    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, nullptr);
-    k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, h->local_tot, h->sc);
-    h->launches += 2;
-    CUDA_TRY(cudaGetLastError());
-    return PF_OK;
-}
-
-template <int D>
-static int32_t mg_finish(pf_handle h, const TileSum *gathered)
-{
-    const int cur = h->cur, nxt = cur ^ 1;
-    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
-    if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    k_rank_offsets<<<1, 32, 0, h->stream>>>(gathered, h->rank, h->nranks, h->res, h->st, h->ro, h->mig_rows, h->sc, h->cap, h->mg_window, h->direct ? 1 : 0);
-    k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
-                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
-    k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
-                                                                          h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, h->ro, h->sendbuf, h->k_max, h->sc, nullptr, h->direct ? h->peers[nxt] : nullptr,
-                                                                          (long long)h->steps * h->cap);
-    h->launches += 3;
-    return PF_OK;
-}
-
-extern "C" int32_t pf_mg_finish(pf_handle h, const void *gathered_totals)
-{
-    MG_CHECK(h);
-    if (!gathered_totals) return PF_ERR_ARG;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    int32_t rc = PF_OK;
-    DISPATCH_D(h->d, rc = mg_finish<D>(h, (const TileSum *)gathered_totals));
-    CUDA_TRY(cudaGetLastError());
-    return rc;
-}
-
-extern "C" int32_t pf_mg_plan(pf_handle h, int64_t *send_counts, int64_t *recv_counts, int64_t *n_local, int64_t *n_global,
-                              int64_t *phase, int64_t *exchange)
-{
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    RankOff r;
-    SelScratch hdr;
-    CUDA_TRY(cudaMemcpyAsync(&r, h->ro, sizeof r, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(&hdr, h->sc, offsetof(SelScratch, A_hi), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (phase) *phase = hdr.phase;
-    if (hdr.phase != 4) return PF_OK;
-    if (r.n_local > h->surv_cap) return set_error(h, PF_ERR_OVERFLOW, "shard produced more survivors than its survivor list holds (imbalance)");
-    {
-        long long tot_send = 0;
-        for (int k = 0; k < h->nranks; k++) tot_send += r.send_len[k];
-        if (tot_send * h->mig_rows > h->buf_cap) return set_error(h, PF_ERR_OVERFLOW, "shard must send more particles than its send buffer holds (imbalance)");
-    }
-    for (int k = 0; k < h->nranks; k++) { if (send_counts) send_counts[k] = r.send_len[k]; if (recv_counts) recv_counts[k] = r.recv_len[k]; }
-    if (n_local) *n_local = r.n_local;
-    if (n_global) *n_global = r.n_global;
-    if (exchange) *exchange = r.exchange;
-    h->n_host = r.n_mine;
-    return PF_OK;
-}
-
-// ---- direct exchange (peer stores)
-// arrays a peer must be able to write: S[0], S[1], Kc[0], Kc[1], logw[0], logw[1], gen_anc, gen_asg
-#define PF_MG_NPEER_ARRAYS 8
+// arrays a peer must be able to write: S[0], S[1], Kc[0], Kc[1], logw[0], logw[1], gen_anc, gen_asg, exchange region
 static void *peer_array(pf_handle h, int k)
 {
     switch (k) {
     case 0: return h->S[0]; case 1: return h->S[1]; case 2: return h->Kc[0]; case 3: return h->Kc[1];
-    case 4: return h->logw[0]; case 5: return h->logw[1]; case 6: return h->gen_anc; default: return h->gen_asg;
+    case 4: return h->logw[0]; case 5: return h->logw[1]; case 6: return h->gen_anc; case 7: return h->gen_asg;
+    default: return h->xreg;
     }
 }
 
-extern "C" int32_t pf_mg_local_arrays(pf_handle h, void **out /* [8] */)
+extern "C" int32_t pf_mg_local_arrays(pf_handle h, void **out /* [PF_MG_NARRAYS] */)
 {
     MG_CHECK(h);
-    for (int k = 0; k < PF_MG_NPEER_ARRAYS; k++) out[k] = peer_array(h, k);
+    for (int k = 0; k < PF_MG_NARRAYS; k++) out[k] = peer_array(h, k);
     return PF_OK;
 }
 
-extern "C" int32_t pf_mg_ipc_handles(pf_handle h, void *out /* 8 x 64 bytes */)
+extern "C" int32_t pf_mg_ipc_handles(pf_handle h, void *out /* PF_MG_NARRAYS x 64 bytes */)
 {
     MG_CHECK(h);
+    static_assert(sizeof(cudaIpcMemHandle_t) == PF_MG_IPC_BYTES, "IPC handle size");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    memset(out, 0, PF_MG_NPEER_ARRAYS * sizeof(cudaIpcMemHandle_t));
-    for (int k = 0; k < PF_MG_NPEER_ARRAYS; k++)
+    memset(out, 0, PF_MG_NARRAYS * sizeof(cudaIpcMemHandle_t));
+    for (int k = 0; k < PF_MG_NARRAYS; k++)
         if (peer_array(h, k)) CUDA_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out + k, peer_array(h, k)));
     return PF_OK;
 }
 
-// arrays of rank `peer`: either pointers valid in this process (ptrs != NULL: ranks emulated in one
-// process) or the 8 IPC handles pf_mg_ipc_handles produced on that rank
+// arrays of rank `peer`: either pointers valid in this process (ptrs != NULL: the peer's handle lives in
+// this process) or the IPC handles pf_mg_ipc_handles produced in the peer's process
 extern "C" int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, const void *ipc_handles)
 {
     MG_CHECK(h);
     if (peer < 0 || peer >= h->nranks) return set_error(h, PF_ERR_ARG, "pf_mg_set_peer: bad rank");
+    if (peer != h->rank && !ptrs && !ipc_handles) return set_error(h, PF_ERR_ARG, "pf_mg_set_peer: no pointers and no IPC handles");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    void *a[PF_MG_NPEER_ARRAYS];
-    for (int k = 0; k < PF_MG_NPEER_ARRAYS; k++) {
+    void *a[PF_MG_NARRAYS];
+    for (int k = 0; k < PF_MG_NARRAYS; k++) {
         a[k] = nullptr;
         if (peer == h->rank) a[k] = peer_array(h, k);
         else if (ptrs) a[k] = ptrs[k];
@@ -1183,99 +1156,275 @@ extern "C" int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, 
         h->peers_host[b].logw[peer] = (double *)a[4 + b];
         h->peers_host[b].gen_anc[peer] = (unsigned int *)a[6]; h->peers_host[b].gen_asg[peer] = (unsigned char *)a[7];
     }
+    h->xch_host.reg[peer] = (XchRegion *)a[8];
     return PF_OK;
 }
 
-extern "C" int32_t pf_mg_enable_direct(pf_handle h)
+// All peers are set: upload the peer tables.  hs[0..n_local) are the handles of THIS process; if several of
+// them share a device they are driven in lock step on one stream (publish and consume as separate launches:
+// a kernel that waits for a peer on the same device could not be overtaken by the kernel it waits for).
+extern "C" int32_t pf_mg_connect(pf_handle *hs, int32_t n_local)
 {
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    for (int b = 0; b < 2; b++) {
-        if (!h->peers[b]) CUDA_TRY(dmalloc(&h->peers[b], 1));
-        CUDA_TRY(cudaMemcpyAsync(h->peers[b], &h->peers_host[b], sizeof(PeerTable), cudaMemcpyHostToDevice, h->stream));
+    if (!hs || n_local < 1) return PF_ERR_ARG;
+    bool same_device = false;
+    for (int i = 0; i < n_local; i++) {
+        MG_CHECK(hs[i]);
+        for (int j = 0; j < i; j++) same_device = same_device || hs[i]->cfg.device == hs[j]->cfg.device;
     }
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->direct = true;
+    for (int i = 0; i < n_local; i++) {
+        pf_handle h = hs[i];
+        CUDA_TRY(cudaSetDevice(h->cfg.device));
+        for (int r = 0; r < h->nranks; r++)
+            if (!h->xch_host.reg[r]) return set_error(h, PF_ERR_STATE, "pf_mg_connect: a peer has not been set (pf_mg_set_peer)");
+        // handles of this process on other devices: plain pointers need peer access
+        for (int j = 0; j < n_local; j++)
+            if (hs[j]->cfg.device != h->cfg.device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->cfg.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_cuda_error(h, e, "cudaDeviceEnablePeerAccess", __LINE__);
+                cudaGetLastError();
+            }
+        for (int b = 0; b < 2; b++) {
+            if (!h->peers[b]) CUDA_TRY(dmalloc(&h->peers[b], 1));
+            CUDA_TRY(cudaMemcpyAsync(h->peers[b], &h->peers_host[b], sizeof(PeerTable), cudaMemcpyHostToDevice, h->stream));
+        }
+        if (!h->xch) CUDA_TRY(dmalloc(&h->xch, 1));
+        CUDA_TRY(cudaMemcpyAsync(h->xch, &h->xch_host, sizeof(Xch), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->lockstep = same_device;
+        if (same_device) {                               // one stream for the whole group
+            if (i == 0) {
+                if (h->own_stream) { h->shared_stream = std::shared_ptr<void>((void *)h->stream, [](void *s) { cudaStreamDestroy((cudaStream_t)s); }); h->own_stream = false; }
+            } else {
+                if (h->own_stream) cudaStreamDestroy(h->stream);
+                h->stream = hs[0]->stream; h->own_stream = false; h->shared_stream = hs[0]->shared_stream;
+            }
+        }
+        h->connected = true;
+    }
     return PF_OK;
 }
 
-extern "C" int32_t pf_mg_set_obs(pf_handle h, const double *y, double u)
+// ---- the stages of one sharded observation (each queues launches on the handle's stream)
+// A: roll the control block over (waits for every rank's previous generation), sample expansion, bracket
+template <int D>
+static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev, int cluster_stage)
 {
-    MG_CHECK(h);
-    if (!y) return PF_ERR_ARG;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    if (!h->y1_pin) CUDA_TRY(cudaMallocHost((void **)&h->y1_pin, sizeof(double) * 64 * (PF_MAX_D + 1)));
-    double *buf = h->y1_pin + (size_t)(h->y1_slot++ & 63) * (PF_MAX_D + 1);
-    for (int k = 0; k < h->d; k++) buf[k] = y[k];
-    buf[h->d] = u;
-    CUDA_TRY(cudaMemcpyAsync(h->y1_dev, buf, sizeof(double) * (h->d + 1), cudaMemcpyHostToDevice, h->stream));
-    return PF_OK;
-}
-
-extern "C" int32_t pf_mg_close(pf_handle h)
-{
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    k_close<<<1, 32, 0, h->stream>>>(h->sc, h->ro, h->steps, h->surv_cap);
+    const long long cap = h->cap;
+    const int cur = h->cur;
+    const unsigned long long seq = (unsigned long long)h->steps + 1;
+    if (cluster_stage & SEL_ST_PUB) {
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc, h->res, h->xch, seq, h->steps);
+        const long long ns = 4 * ((cap + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride) + 1);      // groups of 4 particles (+1: the shard's phase)
+        k_expand<D, 1><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                   h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr, nullptr);
+        h->launches += 2;
+    }
+    SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
+    a.external_sample = 1; a.x = h->xch; a.stage = cluster_stage;
+    CUDA_TRY(launch_cluster(k_sel_bracket, h->cluster_size, h->stream, a));
     h->launches++;
+    return PF_OK;
+}
+
+// B: fused expansion (round 0) / classify pass (retry rounds), then the solve on the gathered candidates
+template <int D>
+static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int cluster_stage)
+{
+    const long long cap = h->cap;
+    const int cur = h->cur;
+    SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
+    a.external_sample = 1; a.preclassified = 1; a.x = h->xch; a.retry = retry;
+    if (cluster_stage & SEL_ST_PUB) {
+        if (!retry) {
+            k_expand<D, 2><<<grid_for(cap, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                        h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
+            h->launches++;
+        }
+        k_sel_classify<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
+        h->launches++;
+    }
+    a.stage = cluster_stage;
+    CUDA_TRY(launch_cluster(k_sel_solve, h->cluster_size, h->stream, a));
+    h->launches++;
+    return PF_OK;
+}
+
+// C: survivor-scan tile records and their prefix; the shard's total goes to every rank
+static int32_t mg_stage_c(pf_handle h)
+{
+    const int g = grid_for(h->cap, SCAN_THREADS);
+    const unsigned long long seq = (unsigned long long)h->steps + 1;
+    k_tile_fixup<<<grid_for(g, 256), 256, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc);
+    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, h->sc);
+    k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, h->xch, seq, h->sc);
+    h->launches += 3;
+    return PF_OK;
+}
+
+// D: global offsets from every rank's total, survivor scan, instantiate (children that change owner are
+// stored into their new owner's arrays), step record + "generation complete" signal
+template <int D>
+static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
+{
+    const int cur = h->cur, nxt = cur ^ 1;
+    const unsigned long long seq = (unsigned long long)h->steps + 1;
+    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
+    if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
+    k_rank_offsets<<<1, 32, 0, h->stream>>>(h->xch, seq, h->steps, h->res, h->st, h->ro, h->sc, h->surv_cap);
+    k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
+                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
+    k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
+                                                                          h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
+                                                                          h->surv_slot, ga, gs, h->ro, h->k_max, h->sc, &h->st->M_next, h->peers[nxt],
+                                                                          (long long)h->steps * h->cap);
+    k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->sc, h->steps, h->dbg_status, h->ro, h->xch, seq);
+    h->launches += 4;
     CUDA_TRY(cudaGetLastError());
+    h->cur = nxt;
+    h->steps++;
     return PF_OK;
 }
 
-extern "C" int32_t pf_mg_drain(pf_handle h, int64_t out[4])
+static const char *halt_text(int reason)
 {
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    SelScratch hdr; StepState st;
-    CUDA_TRY(cudaMemcpyAsync(&hdr, h->sc, offsetof(SelScratch, A_hi), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(&st, h->st, sizeof st, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    out[0] = hdr.halt; out[1] = hdr.phase; out[2] = st.n_next; out[3] = st.n_global;
-    if (!hdr.halt) h->n_host = st.n_next;
+    switch (reason) {
+    case PF_HALT_SEARCH: return "the threshold search needed more rounds than were queued";
+    case PF_HALT_TIMEOUT: return "a peer's exchange flag did not arrive in time (PF_MG_TIMEOUT_MS)";
+    case PF_HALT_XCH_OVERFLOW: return "a sample / candidate list outgrew its exchange segment";
+    case PF_HALT_SURVIVORS: return "a shard produced more survivors than its survivor list holds";
+    default: return "unknown";
+    }
+}
+
+// filter!(ps, ys, false) (src/filters.jl:6-13) on a sharded population: hs[0..n_local) are the shards this
+// process drives; every process of the group calls this with the same observations and uniforms.
+extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys, int64_t T, const double *uniforms,
+                                int64_t uniforms_per_step, double *log_evidence)
+{
+    if (!hs || n_local < 1) return PF_ERR_ARG;
+    for (int i = 0; i < n_local; i++) {
+        MG_CHECK(hs[i]);
+        if (!hs[i]->connected) return set_error(hs[i], PF_ERR_STATE, "pf_mg_filter: pf_mg_connect has not been called");
+    }
+    if (T < 0 || (!ys && T > 0)) return set_error(hs[0], PF_ERR_ARG, "pf_mg_filter: bad ys/T");
+    if (uniforms && uniforms_per_step < 1) return set_error(hs[0], PF_ERR_ARG, "pf_mg_filter: Fearnhead needs 1 uniform per step");
+    if (T == 0) return PF_OK;
+    const int d = hs[0]->d;
+    const bool lockstep = hs[0]->lockstep;
+    int32_t rc = PF_OK;
+    for (int i = 0; i < n_local; i++) {
+        pf_handle h = hs[i];
+        CUDA_TRY(cudaSetDevice(h->cfg.device));
+        rc = ensure_table(h, h->steps + T + 2);
+        if (rc != PF_OK) return rc;
+        if (h->hist_cap && h->steps + T > h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
+        if (T * d > h->ys_cap) { if (h->ys_dev) cudaFree(h->ys_dev); h->ys_cap = T * d; CUDA_TRY(dmalloc(&h->ys_dev, (size_t)h->ys_cap)); }
+        if (T > h->slog_cap) { if (h->slog) cudaFree(h->slog); h->slog_cap = T; CUDA_TRY(dmalloc(&h->slog, (size_t)T)); }
+        if (T > h->u_cap) { if (h->u_dev) cudaFree(h->u_dev); h->u_cap = T; CUDA_TRY(dmalloc(&h->u_dev, (size_t)T)); }
+        std::vector<double> ubuf(T);
+        for (long long t = 0; t < T; t++)
+            ubuf[t] = uniforms ? uniforms[t * uniforms_per_step] : pf_uniform(h->cfg.seed, (uint64_t)(h->steps + t), 0, 0);
+        h->launches = 0;
+        CUDA_TRY(cudaMemcpyAsync(h->ys_dev, ys, sizeof(double) * T * d, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->u_dev, ubuf.data(), sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));      // ubuf goes out of scope
+        CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    }
+#define FOR_SHARDS(CALL) for (int i_ = 0; i_ < n_local && rc == PF_OK; i_++) { pf_handle h = hs[i_]; cudaSetDevice(h->cfg.device); DISPATCH_D(d, rc = CALL); }
+    const int both = SEL_ST_PUB | SEL_ST_RUN;
+    for (long long t = 0; t < T && rc == PF_OK; t++) {
+        if (lockstep) {
+            FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_PUB)));
+            FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_RUN)));
+            for (int r = 0; r <= SEL_RETRIES; r++) {
+                FOR_SHARDS((mg_stage_b<D>(h, h->u_dev + t, r > 0, SEL_ST_PUB)));
+                FOR_SHARDS((mg_stage_b<D>(h, h->u_dev + t, r > 0, SEL_ST_RUN)));
+            }
+        } else {
+            FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, both)));
+            for (int r = 0; r <= SEL_RETRIES; r++) FOR_SHARDS((mg_stage_b<D>(h, h->u_dev + t, r > 0, both)));
+        }
+        for (int i = 0; i < n_local && rc == PF_OK; i++) { cudaSetDevice(hs[i]->cfg.device); rc = mg_stage_c(hs[i]); }
+        FOR_SHARDS((mg_stage_d<D>(h, h->slog + t)));
+    }
+#undef FOR_SHARDS
+    // drain: every shard's records; a halted shard reports why
+    int32_t first_err = rc;
+    for (int i = 0; i < n_local; i++) {
+        pf_handle h = hs[i];
+        cudaSetDevice(h->cfg.device);
+        h->logs.resize(T);
+        long long halt[2] = {0, 0};
+        StepState st;
+        cudaError_t e = cudaMemcpyAsync(h->logs.data(), h->slog, sizeof(StepLog) * T, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(halt, &h->sc->halt, sizeof halt, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&st, h->st, sizeof st, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev1, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { if (first_err == PF_OK) first_err = set_cuda_error(h, e, "pf_mg_filter drain", __LINE__); continue; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->last_ms = ms; h->last_launches = h->launches;
+        if (halt[0]) {
+            char buf[200];
+            const int reason = (int)(halt[1] & 0xffffffffll);
+            snprintf(buf, sizeof buf, "sharded step %lld halted on rank %d: %s", halt[0] - 1, h->rank, halt_text(reason));
+            const int32_t code = (reason == PF_HALT_XCH_OVERFLOW || reason == PF_HALT_SURVIVORS) ? PF_ERR_OVERFLOW : PF_ERR_STATE;
+            set_error(h, code, buf);
+            if (first_err == PF_OK) { first_err = code; if (h != hs[0]) hs[0]->err = buf; }
+            continue;
+        }
+        h->last = h->logs.back(); h->have_last = true; h->last_stale = false;
+        h->n_host = st.n_next;
+    }
+    if (first_err != PF_OK) return first_err;
+    if (log_evidence) for (long long t = 0; t < T; t++) log_evidence[t] = hs[0]->logs[t].log_total;
     return PF_OK;
 }
 
-extern "C" int32_t pf_mg_resume(pf_handle h, int64_t step)
+// population over all shards after the last step
+extern "C" int64_t pf_mg_n_global(pf_handle h) { return (h && h->have_last) ? h->last.n_out : (h ? 1 : -1); }
+
+// Convenience for a single process that drives several GPUs (one host thread): creates one shard per entry
+// of `devices`, maps them into each other (peer access) and connects them.  cfg->rank / nranks / device are
+// ignored.  The same device may be listed several times (lock-step emulation, used by the tests).
+extern "C" int32_t pf_mg_create_local(const pf_config *cfg, const int32_t *devices, int32_t n, pf_handle *out)
 {
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    if (step < 0 || step > h->steps) return set_error(h, PF_ERR_ARG, "pf_mg_resume: bad step");
-    h->steps = step; h->cur = (int)(step & 1);
-    CUDA_TRY(cudaMemsetAsync((char *)h->sc + offsetof(SelScratch, halt), 0, sizeof(long long), h->stream));
-    return PF_OK;
+    if (!cfg || !devices || !out || n < 2 || n > PF_MAX_RANKS) return set_error(nullptr, PF_ERR_ARG, "pf_mg_create_local: bad argument");
+    for (int i = 0; i < n; i++) out[i] = nullptr;
+    int32_t rc = PF_OK;
+    for (int i = 0; i < n && rc == PF_OK; i++) {
+        pf_config c = *cfg;
+        c.rank = i; c.nranks = n; c.device = devices[i];
+        rc = pf_create(&c, &out[i]);
+    }
+    for (int i = 0; i < n && rc == PF_OK; i++)
+        for (int j = 0; j < n && rc == PF_OK; j++) {
+            void *arr[PF_MG_NARRAYS];
+            pf_mg_local_arrays(out[j], arr);
+            rc = pf_mg_set_peer(out[i], j, arr, nullptr);
+            if (rc != PF_OK) g_create_error = out[i]->err;
+        }
+    if (rc == PF_OK) { rc = pf_mg_connect(out, n); if (rc != PF_OK) for (int i = 0; i < n; i++) if (!out[i]->err.empty()) g_create_error = out[i]->err; }
+    if (rc != PF_OK) { for (int i = 0; i < n; i++) { if (out[i]) pf_destroy(out[i]); out[i] = nullptr; } }
+    return rc;
 }
 
 extern "C" int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */)
 {
     if (!h || !out) return PF_ERR_ARG;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    SelResult r; StepState st; RankOff ro; TileSum lt;
-    memset(&ro, 0, sizeof ro); memset(&lt, 0, sizeof lt);
+    SelResult r; StepState st; RankOff ro; SelScratch *scp = h->sc;
+    long long hdr[8];
+    memset(&ro, 0, sizeof ro);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(&r, h->res, sizeof r, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&st, h->st, sizeof st, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hdr, scp, sizeof hdr, cudaMemcpyDeviceToHost));
     if (h->ro) CUDA_TRY(cudaMemcpy(&ro, h->ro, sizeof ro, cudaMemcpyDeviceToHost));
-    if (h->local_tot) CUDA_TRY(cudaMemcpy(&lt, h->local_tot, sizeof lt, cudaMemcpyDeviceToHost));
     int64_t v[24] = {(int64_t)r.thr_bits, r.scale, r.keep_all, (int64_t)r.T.lo, (int64_t)r.T.hi, (int64_t)r.Uoff.lo, (int64_t)r.Uoff.hi,
                      (int64_t)r.Tq.lo, (int64_t)r.Tq.hi, r.Tr, r.A, r.n, r.rounds, st.n_live, st.M, st.n_next,
-                     (int64_t)lt.X.lo, (int64_t)lt.X.hi, lt.kept, ro.n_local, ro.g_first, ro.kept_off, (int64_t)ro.S_off.lo, ro.n_global};
+                     r.status, hdr[2] /* scale | phase */, hdr[5] /* halt */, ro.n_local, ro.g_first, ro.kept_off, (int64_t)ro.S_off.lo, ro.n_global};
     for (int k = 0; k < 24; k++) out[k] = v[k];
-    return PF_OK;
-}
-
-extern "C" int32_t pf_mg_unpack(pf_handle h, const void *recv)
-{
-    MG_CHECK(h);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const int nxt = h->cur ^ 1;
-    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
-    if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    k_unpack<<<grid_for(h->cap, 256), 256, 0, h->stream>>>((const double *)recv, h->ro, h->S[nxt], h->Kc[nxt], h->logw[nxt], ga, gs,
-                                                            h->cap, h->k_max * h->F, h->F, h->sc);
-    k_steplog_mg<<<1, 32, 0, h->stream>>>(h->st, h->res, h->ro, h->slog, h->sc);
-    h->launches += 2;
-    CUDA_TRY(cudaGetLastError());
-    h->have_last = true; h->last_stale = true;       // the record is fetched when pf_get_last_step asks for it
-    h->cur = nxt;
-    h->steps++;
     return PF_OK;
 }

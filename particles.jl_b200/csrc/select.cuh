@@ -1,17 +1,30 @@
-// select.cuh -- Fearnhead-Clifford threshold search (cutoff_ascending, src/fearnhead.jl:59-77)
-// as ONE cooperative persistent kernel:
+// select.cuh -- Fearnhead-Clifford threshold search (cutoff_ascending, src/fearnhead.jl:59-77).
 //
-//   phase 0  bracket   a strided sample of the putative weights (about 2^20 of them) is
-//                      solved approximately by the same radix descent that solves the real
-//                      problem, and widened by a sampling-error margin into [lo, hi);
-//   round r  classify  one pass over all putatives: exact fixed-point mass below lo, count
-//                      above hi, the few in between become the candidate list;
-//            verify    predicate false at lo and true at hi (else widen and redo);
-//            descend   1024-bin radix histogram levels over the candidate list until the
-//                      bracket holds <= 2048 values;
-//            solve     sort them, evaluate the predicate of src/fearnhead.jl:69 exactly;
-//            rescale   if the comb needs a finer scale than the threshold did, one more
-//                      classify pass at that scale.
+//   bracket   a strided sample of the putative weights (about 2^20 of them) is solved
+//             approximately by the same radix descent that solves the real problem, and widened
+//             by a sampling-error margin into [lo, hi);                     k_sel_bracket
+//   classify  one pass over all putatives: exact fixed-point mass below lo, count above hi, the
+//             few in between become the candidate list (the fused expansion kernel does this on
+//             the fly for the first round);                                  k_sel_classify
+//   solve     verify the bracket (predicate false at lo and true at hi, else move / widen it
+//             and ask for another classify round), resolve the plateau tie, 1024-bin radix
+//             histogram levels over the candidate list until <= 2048 values remain, sort them
+//             and evaluate the predicate of src/fearnhead.jl:69 exactly; if the comb needs a
+//             finer scale than the threshold did, ask for one more classify round.  k_sel_solve
+//
+// k_sel_bracket and k_sel_solve work on short lists (~10^6 values) and are latency-bound: each
+// runs on ONE thread-block cluster (16 CTAs where the device schedules it, else 8): the radix
+// histograms live in every CTA's shared memory and are reduced across the cluster through
+// distributed shared memory, and the ~10 barriers per launch are cluster barriers instead of
+// grid-wide ones.  k_sel_classify streams the whole V and is a plain full-grid kernel.  A round
+// that asks for another one (phase 3) is followed by queued retry launches of k_sel_classify /
+// k_sel_solve, which are no-ops otherwise: no host round trip inside a step.
+//
+// Sharded runs (particles block-sharded over GPUs): k_sel_bracket / k_sel_solve begin by
+// writing the local sample / candidate list and accumulator block into EVERY peer's exchange
+// region (stores into peer memory over NVLink) and wait on per-rank sequence flags, so the
+// all-gather is part of the kernel; every rank then solves the same gathered problem in
+// integer arithmetic and reaches the same threshold, bit-identical to the single-GPU result.
 //
 // All sums that feed a decision are 128-bit fixed-point integers (order-free, hence
 // deterministic and shard-independent).  Items are addressed as (particle i, slot j):
@@ -29,13 +42,15 @@ namespace cg = cooperative_groups;
 #define SEL_FINAL_CAP 2048
 #define SEL_BINS 1024
 #define SEL_CHUNK 32
-#define SEL_SAMPLE_WARPS 1024         // sharded run: warps that gather the sample (bounds the list padding)
 #ifndef SEL_SAMPLE_TARGET
 #define SEL_SAMPLE_TARGET (1 << 20)
 #endif
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax
 #define SEL_SMEM_BYTES (SEL_BINS * 4 + 3 * SEL_BINS * 8)
+#define SEL_MAX_CLUSTER 16
+#define SEL_RETRIES 2               // queued extra rounds per step (no-ops unless the previous round asked for one)
+#define PF_MAX_RANKS 16
 
 struct SelResult {
     u64 thr_bits;                   // kept = {bits(v) >= thr_bits}; 0 = keep everything
@@ -53,20 +68,23 @@ struct SelResult {
     double thr_value;
     int rounds;
     long long n_cand_first;
-    int status;                     // 0 ok
+    long long n_plateau_first;      // in-bracket copies of the plateau value in the first round (counted, not listed)
+    int status;                     // bit set, see pf_step_stats.select_status
     unsigned long long t_ns[5];     // globaltimer at: start, bracket ready, first classify done, solve done, end
 };
 
 struct SelScratch {
-    // bracket state (written by block 0, read by all after grid.sync)
+    // bracket state (written by CTA 0 of the cluster kernels, read by all after a barrier)
     u64 lo, hi;
     int scale;
-    int phase;                      // control word for the next loop iteration
+    int phase;                      // 2 descend, 3 another classify round is needed, 4 done, 6 sample solve finished, 8 plateau
     int mode;                       // 0 bracket round, 1 keep everything, 2 comb-rescale round (lo = hi = thr)
     long long count_in;             // list items inside [lo, hi)
     long long mult;                 // sample stride while solving the sample, 1 otherwise
-    long long halt;                 // sharded run: 1 + index of the step that needs the host (all later kernels are no-ops)
-    // fused path (single GPU): the expansion kernel classifies against a bracket found BEFORE it
+    long long halt;                 // 1 + index of the step that could not be completed (all later kernels are no-ops)
+    int halt_reason;                // PF_HALT_*
+    int pad0;
+    // fused path: the expansion kernel classifies against a bracket found BEFORE it
     long long list_n;               // exact number of entries of the sample / candidate list (list_exact)
     int list_exact;                 // 1: the list is dense (block-reserved ranges), 0: chunked with padding
     int fuse_valid;                 // 1: k_expand classified against [lo, hi) and filled the accumulators / tile records
@@ -77,107 +95,92 @@ struct SelScratch {
     int fuse_overflow;              // a block had more candidates than its staging buffer
     int need_tot;                   // the total weight of this step has not been computed yet
     int tiles_ok;                   // the survivor-scan tile records written by the expansion are usable
-    int pad1;
-    // accumulators of the classify pass (SelAcc: the block a sharded run all-gathers)
+    int low_max_valid;              // the round was classified by k_sel_classify (which tracks low_max)
+    // accumulators of the classify pass (SelAcc: the block a sharded run exchanges)
     unsigned long long A_hi;        // #items >= hi
     unsigned long long n_cand;      // #items in [lo, hi)
     acc128 B_lo;                    // sum q of items < lo
     acc128 S_cand;                  // sum q of items in [lo, hi)
-    acc128 Tot;                     // sum of the items >= hi at scale SEL_TOT_BITS - e(vmax)
+    acc128 Tot;                     // sum of the items >= hi at scale kept_tot_scale(hi, vmax)
     unsigned long long cand_chunks; // chunks handed out of the candidate / sample list
-    unsigned long long overflow;    // sharded run: the list outgrew the fixed gather size
+    unsigned long long overflow;    // sharded run: the list outgrew its exchange segment
     unsigned long long M_local;     // sharded run: this shard's putative count and max weight bits
     unsigned long long vmax_local;
     unsigned long long vs_bits;     // max weight of the strided sample (its exponent fixes the sample solve's scale)
     unsigned long long n_plateau;   // in-bracket items equal to the plateau value (counted, not listed)
+    unsigned long long low_max;     // largest item below lo seen by k_sel_classify (bit pattern; valid if low_max_valid)
     // plateau resolution: candidates below the plateau value (count, fixed-point sum)
     unsigned long long pl_cnt;
     acc128 pl_sum;
     // running totals of the descent
     u128 B_run;                     // sum q of list items < lo (after narrowing)
     long long A_run;                // #list items >= hi (after narrowing)
+    // the global problem of the current launch (sharded: summed over the ranks)
+    long long gM;
+    u64 gvmax;
     // final list
     unsigned int final_n;
     double final_vals[SEL_FINAL_CAP];
-    // histogram of one descent level
+    // histogram of one descent level (cluster-reduced)
     unsigned int h_cnt[SEL_BINS];
     u64 h_sum[3][SEL_BINS];
 };
+enum { PF_HALT_SEARCH = 1,          // the threshold search needed more rounds than were queued
+       PF_HALT_TIMEOUT = 2,         // a peer's flag did not arrive (sharded run)
+       PF_HALT_XCH_OVERFLOW = 3,    // a sample / candidate list outgrew its exchange segment (sharded run)
+       PF_HALT_SURVIVORS = 4 };     // a shard produced more survivors than its survivor list holds
 
-// the accumulator block of SelScratch as a stand-alone record (sharded runs gather one per rank)
+// the accumulator block of SelScratch as a stand-alone record (sharded runs exchange one per rank)
 struct SelAcc {
     unsigned long long A_hi, n_cand;
     acc128 B_lo, S_cand, Tot;
-    unsigned long long cand_chunks, overflow, M_local, vmax_local, vs_bits, n_plateau;
+    unsigned long long cand_chunks, overflow, M_local, vmax_local, vs_bits, n_plateau, low_max;
 };
 #define SEL_ACC_OFFSET offsetof(SelScratch, A_hi)
 
-// stages of k_select: a single-GPU step runs all of them in one launch; a sharded step runs
-// them as separate launches with an all-gather between (see particles_b200/distributed.py)
-enum { SEL_ST_SAMPLE = 1, SEL_ST_BRACKET = 2, SEL_ST_CLASSIFY = 4, SEL_ST_SOLVE = 8, SEL_ST_ALL = 15 };
-
-struct SelArgs {
-    const double *V;
-    const unsigned char *cnt;
-    long long cap;
-    const long long *n_live;        // device
-    const long long *M;             // device: total number of items
-    const u64 *vmax_bits;           // device
-    long long N;
-    const double *u;                // device: the uniform of this step
-    double *cand;                   // candidate list, chunked
-    long long cand_cap;             // in doubles
-    SelScratch *sc;
-    SelResult *res;
-    int stage;                      // SEL_ST_* bit mask
-    int margin;                     // half-width of the sample bracket in sigmas of the sampling error (8; tests shrink it)
-    int round0;                     // number of classify rounds already done (sharded re-entry)
-    int nranks;                     // > 1: accumulators / lists come gathered from all ranks
-    const SelAcc *gacc;             // [nranks] gathered accumulator blocks
-    const double *glist;            // gathered sample / candidate list (nranks * glist_each doubles)
-    long long glist_each;           // doubles per rank in glist (padded with the NaN pattern)
-    const long long *goff;          // device: global index of the shard's first particle (phase of the strided sample)
-    long long pad_to;               // sharded run: pad the local list with the NaN pattern up to this many entries
-    long long fixed_stride;         // > 0: sample stride chosen by the host (sharded run; fused path)
-    const unsigned long long *plateau_ptr;   // device: value of the step's mass tie (StepConst.plateau_bits); NULL = none
-    int external_sample;            // 1: the sample is already in the list (k_expand in sample mode), sc->list_n entries
-    int preclassified;              // 1: round `round0` was classified by the expansion kernel (if sc->fuse_valid)
+// ------------------------------------------------------------------ peer exchange (sharded runs)
+// Every rank owns one exchange region in device memory, mapped into every other rank (CUDA IPC between
+// processes, plain pointers inside one process).  Rank r PUSHES its contribution into slot r of every
+// region (stores into peer memory over NVLink), makes the stores visible (__threadfence_system) and
+// raises flag[kind][r] to a sequence number; a consumer spins on the G flags of its OWN region, so all
+// reads are local.  Sequence numbers only grow, nothing is ever reset.
+//   kind A  strided sample            (header XchHdrA + list)        seq = step + 1
+//   kind B  candidates of a round     (header SelAcc  + list)        seq = (step + 1) * 64 + round, two buffers by round parity
+//   kind C  survivor-scan total       (XchTot)                       seq = step + 1
+//   kind D  next generation complete  (flag only)                    seq = step + 1
+// A rank publishes step t + 1 only after it has seen every peer's D flag of step t, which a peer raises
+// after its last kernel of step t: one buffer per kind is enough across steps; within a step the rounds
+// of kind B alternate between two buffers because a fast rank may publish round k + 1 while a slow one
+// still reads round k.
+enum { XCH_A = 0, XCH_B = 1, XCH_C = 2, XCH_D = 3, XCH_KINDS = 4 };
+struct XchHdrA { unsigned long long n, vmax, M_pred, overflow; };
+struct XchTot { u128 X; unsigned int kept; unsigned int pad[3]; };         // = TileSum (fearnhead.cuh)
+struct XchRegion {
+    unsigned long long flag[XCH_KINDS][PF_MAX_RANKS];
+    XchHdrA a[PF_MAX_RANKS];
+    SelAcc b[2][PF_MAX_RANKS];
+    XchTot c[PF_MAX_RANKS];
+    // followed (256-byte aligned) by listA[nranks][capA] and listB[2][nranks][capB] (doubles)
 };
-
-// sharded run: sum the gathered per-rank accumulator blocks into the local scratch
-__device__ inline void sum_gathered(SelScratch *sc, const SelAcc *g, int nranks)
+struct Xch {
+    int rank, nranks;
+    long long capA, capB;
+    unsigned long long timeout_ns;
+    XchRegion *reg[PF_MAX_RANKS];   // region of every rank as mapped in this process (reg[rank]: own)
+};
+__host__ __device__ __forceinline__ size_t xch_header_bytes() { return (sizeof(XchRegion) + 255) / 256 * 256; }
+__host__ __device__ __forceinline__ double *xch_listA(XchRegion *reg, long long capA, int src)
 {
-    unsigned long long A = 0, nc = 0, ch = 0, npl = 0;
-    acc128 b, c, t;
-    for (int k = 0; k < 4; k++) { b.l[k] = 0; c.l[k] = 0; t.l[k] = 0; }
-    for (int r = 0; r < nranks; r++) {
-        A += g[r].A_hi; nc += g[r].n_cand; ch += g[r].cand_chunks; npl += g[r].n_plateau;
-        for (int k = 0; k < 4; k++) { b.l[k] += g[r].B_lo.l[k]; c.l[k] += g[r].S_cand.l[k]; t.l[k] += g[r].Tot.l[k]; }
-    }
-    sc->A_hi = A; sc->n_cand = nc; sc->B_lo = b; sc->S_cand = c; sc->Tot = t; sc->n_plateau = npl;
-    (void)ch;
+    return reinterpret_cast<double *>(reinterpret_cast<char *>(reg) + xch_header_bytes()) + (long long)src * capA;
 }
-
-// sharded run: global putative count / max weight from the gathered blocks (one thread)
-__global__ void k_mg_globals(const SelAcc *g, int nranks, long long *gscal)
+__host__ __device__ __forceinline__ double *xch_listB(XchRegion *reg, int nranks, long long capA, long long capB, int parity, int src)
 {
-    if (threadIdx.x || blockIdx.x) return;
-    unsigned long long M = 0, vm = 0, ov = 0, vs = 0;
-    for (int r = 0; r < nranks; r++) {
-        M += g[r].M_local; vm = g[r].vmax_local > vm ? g[r].vmax_local : vm; ov |= g[r].overflow;
-        vs = g[r].vs_bits > vs ? g[r].vs_bits : vs;
-    }
-    gscal[0] = (long long)M; gscal[1] = (long long)vm; gscal[2] = (long long)ov; gscal[3] = (long long)vs;
+    return reinterpret_cast<double *>(reinterpret_cast<char *>(reg) + xch_header_bytes()) + (long long)nranks * capA +
+           ((long long)parity * nranks + src) * capB;
 }
-
-// pad the tail of a chunked list up to `pad_to` entries (grid-wide, after the appends are done)
-__device__ inline void pad_list(double *list, unsigned long long chunks, long long pad_to, SelScratch *sc)
+__host__ __device__ __forceinline__ size_t xch_region_bytes(int nranks, long long capA, long long capB)
 {
-    const long long used = (long long)chunks * SEL_CHUNK;
-    if (pad_to < 0) return;
-    if (used > pad_to) { if (blockIdx.x == 0 && threadIdx.x == 0) sc->overflow = 1; return; }
-    for (long long t = used + (long long)blockIdx.x * SEL_THREADS + threadIdx.x; t < pad_to; t += (long long)gridDim.x * SEL_THREADS)
-        list[t] = __longlong_as_double(~0ll);
+    return xch_header_bytes() + sizeof(double) * ((size_t)nranks * capA + 2 * (size_t)nranks * capB);
 }
 
 __device__ __forceinline__ unsigned long long gtimer()
@@ -185,6 +188,81 @@ __device__ __forceinline__ unsigned long long gtimer()
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// one thread: wait until every rank's flag of `kind` in the OWN region reached `seq`; false on time-out
+__device__ inline bool xch_wait(const Xch *x, int kind, unsigned long long seq)
+{
+    const unsigned long long *f = x->reg[x->rank]->flag[kind];
+    const unsigned long long t0 = gtimer();
+    for (int r = 0; r < x->nranks; r++) {
+        unsigned int spins = 0;
+        while (ld_acquire_sys(f + r) < seq) {
+            if ((++spins & 1023u) == 0 && gtimer() - t0 > x->timeout_ns) return false;
+            __nanosleep(40);
+        }
+    }
+    return true;
+}
+// one thread: raise this rank's flag of `kind` to `seq` in every region (own included)
+__device__ inline void xch_signal(const Xch *x, int kind, unsigned long long seq)
+{
+    __threadfence_system();
+    for (int p = 0; p < x->nranks; p++) st_release_sys(&x->reg[p]->flag[kind][x->rank], seq);
+}
+// a u64 that a peer wrote into local memory: read it from L2 (never from a stale L1 line)
+__device__ __forceinline__ unsigned long long ld_peer(const unsigned long long *p) { return __ldcg(p); }
+
+// stages of the cluster kernels
+enum { SEL_ST_PUB = 1,        // sharded: write the local list / header into the peers' regions and raise the flag
+       SEL_ST_RUN = 2 };      // do the stage's work (sharded: after waiting for every rank's flag)
+
+struct SelArgs {
+    const double *V;
+    const unsigned char *cnt;
+    long long cap;
+    const long long *n_live;        // device
+    const long long *M;             // device: number of items (sharded: of this shard)
+    const u64 *vmax_bits;           // device: maximum item (sharded: of this shard)
+    long long N;
+    const double *u;                // device: the uniform of this step
+    double *cand;                   // local sample / candidate list
+    long long cand_cap;             // in doubles
+    SelScratch *sc;
+    SelResult *res;
+    int stage;                      // SEL_ST_* bit mask
+    int margin;                     // half-width of the sample bracket in sigmas of the sampling error (8; tests shrink it)
+    int retry;                      // 1: a queued extra round -- runs only if the previous round asked for it (phase 3)
+    int external_sample;            // 1: the sample came from k_expand (sample mode): M is the predicted count, vmax the sample's
+    int preclassified;              // 1: round 0 was classified by the expansion kernel (if sc->fuse_valid)
+    int pad0;
+    long long fixed_stride;         // sample stride (the same strided sample on every path)
+    const unsigned long long *plateau_ptr;   // device: value of the step's mass tie (StepConst.plateau_bits); NULL = none
+    const Xch *x;                   // sharded run: exchange descriptor (device); NULL = single GPU
+    unsigned long long seq;         // sharded run: step + 1
+    long long step;                 // index of this step (halt mark)
+};
+
+// the list a cluster kernel works on: one segment (single GPU) or one per rank (own exchange region)
+struct ListView {
+    const double *seg[PF_MAX_RANKS];
+    long long off[PF_MAX_RANKS + 1];    // exclusive prefix of the segment lengths
+    int nseg;
+};
+__device__ __forceinline__ u64 lv_load(const ListView &lv, long long t)
+{
+    int s = 0;
+    while (s + 1 < lv.nseg && t >= lv.off[s + 1]) s++;
+    return (u64)__double_as_longlong(__ldcg(lv.seg[s] + (t - lv.off[s])));      // L2: peers may have written this memory
 }
 
 // Scale of the kept-side total (items >= hi).  52 - e(hi) represents every such double exactly
@@ -281,19 +359,23 @@ struct ChunkWriter {
     }
 };
 
-// one radix level: histogram (count, fixed-point sum) of the list items inside [blo, bhi)
-// into sc->h_* (which block 0 left zeroed), 1024 bins of width 2^shift bit patterns.
-__device__ inline void hist_level(const double *list, long long list_n, u64 blo, u64 bhi, int shift, int scale, SelScratch *sc,
-                                  unsigned char *smem_raw)
+// One radix level on a cluster: every CTA histograms (count, fixed-point sum) its share of the list items
+// inside [blo, bhi) into ITS shared memory (1024 bins of width 2^shift bit patterns); after a cluster
+// barrier CTA c sums bins [c B/C, (c+1) B/C) over all CTAs through distributed shared memory and writes the
+// totals to sc->h_* (which select_bin reads).
+__device__ inline void hist_level(cg::cluster_group &cluster, const ListView &lv, u64 blo, u64 bhi, int shift, int scale,
+                                  SelScratch *sc, unsigned char *smem_raw)
 {
     unsigned int *h_cnt = reinterpret_cast<unsigned int *>(smem_raw);
     u64 *h_s0 = reinterpret_cast<u64 *>(smem_raw + SEL_BINS * 4);
     u64 *h_s1 = h_s0 + SEL_BINS, *h_s2 = h_s1 + SEL_BINS;
     const int tid = threadIdx.x;
+    const unsigned int nctas = cluster.num_blocks(), crank = cluster.block_rank();
     for (int t = tid; t < SEL_BINS; t += SEL_THREADS) { h_cnt[t] = 0; h_s0[t] = 0; h_s1[t] = 0; h_s2[t] = 0; }
     __syncthreads();
-    for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < list_n; t += (long long)gridDim.x * SEL_THREADS) {
-        u64 bits = (u64)__double_as_longlong(list[t]);
+    const long long list_n = lv.off[lv.nseg];
+    for (long long t = (long long)crank * SEL_THREADS + tid; t < list_n; t += (long long)nctas * SEL_THREADS) {
+        u64 bits = lv_load(lv, t);
         if (bits >= blo && bits < bhi) {
             int b = (int)((bits - blo) >> shift);
             u128 q = fx70(bits, scale);
@@ -303,23 +385,23 @@ __device__ inline void hist_level(const double *list, long long list_n, u64 blo,
             atomicAdd(&h_s2[b], q.hi);
         }
     }
-    __syncthreads();
-    for (int t = tid; t < SEL_BINS; t += SEL_THREADS)
-        if (h_cnt[t]) {
-            atomicAdd(&sc->h_cnt[t], h_cnt[t]);
-            atomicAdd(&sc->h_sum[0][t], h_s0[t]);
-            atomicAdd(&sc->h_sum[1][t], h_s1[t]);
-            atomicAdd(&sc->h_sum[2][t], h_s2[t]);
+    cluster.sync();
+    const int per = SEL_BINS / (int)nctas;
+    for (int k = tid; k < per; k += SEL_THREADS) {
+        const int b = (int)crank * per + k;
+        unsigned int c = 0; u64 s0 = 0, s1 = 0, s2 = 0;
+        for (unsigned int r = 0; r < nctas; r++) {
+            const unsigned int *rc = cluster.map_shared_rank(h_cnt, r);
+            const u64 *r0 = cluster.map_shared_rank(h_s0, r);
+            c += rc[b]; s0 += r0[b]; s1 += r0[SEL_BINS + b]; s2 += r0[2 * SEL_BINS + b];
         }
-    __syncthreads();
+        sc->h_cnt[b] = c; sc->h_sum[0][b] = s0; sc->h_sum[1][b] = s1; sc->h_sum[2][b] = s2;
+    }
+    __threadfence();
+    cluster.sync();          // remote reads done before anyone reuses its shared memory; totals visible to CTA 0
 }
 
-__device__ __forceinline__ u128 hist_bin_sum(const SelScratch *sc, int b)
-{
-    return add128(add128(mk128(sc->h_sum[0][b], 0), shl128(mk128(sc->h_sum[1][b], 0), 32)), mk128(0, sc->h_sum[2][b]));
-}
-
-// Block 0 (all threads), after a histogram level: find the first bin whose UPPER boundary
+// CTA 0 (all threads), after a histogram level: find the first bin whose UPPER boundary
 // satisfies the predicate and narrow the bracket to it.  With sampling != 0 the list is a
 // strided sample (sums and counts are multiplied by sc->mult): the level either narrows to
 // the bin and its two neighbours, or -- once the bin is finer than the sampling error --
@@ -333,9 +415,8 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
     __shared__ int s_found;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int b = tid; b < SEL_BINS; b += SEL_THREADS) {
-        pc[b] = sc->h_cnt[b];
-        ps[b] = add128(add128(mk128(sc->h_sum[0][b], 0), shl128(mk128(sc->h_sum[1][b], 0), 32)), mk128(0, sc->h_sum[2][b]));
-        sc->h_cnt[b] = 0; sc->h_sum[0][b] = 0; sc->h_sum[1][b] = 0; sc->h_sum[2][b] = 0;      // ready for the next level
+        pc[b] = __ldcg(&sc->h_cnt[b]);
+        ps[b] = add128(add128(mk128(__ldcg(&sc->h_sum[0][b]), 0), shl128(mk128(__ldcg(&sc->h_sum[1][b]), 0), 32)), mk128(0, __ldcg(&sc->h_sum[2][b])));
     }
     __syncthreads();
     const int per = SEL_BINS / 32;
@@ -405,6 +486,7 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
         sc->A_run = A0 + (count_in - cbefore - cin);
         sc->lo = nlo; sc->hi = nhi; sc->count_in = cin;
         sc->phase = next_phase;
+        __threadfence();
     }
     __syncthreads();
 }
@@ -413,6 +495,7 @@ __device__ inline void reset_round(SelScratch *sc)
 {
     sc->A_hi = 0; sc->n_cand = 0; sc->cand_chunks = 0; sc->final_n = 0; sc->overflow = 0; sc->list_n = 0; sc->list_exact = 0;
     sc->n_plateau = 0; sc->pl_cnt = 0; for (int k = 0; k < 4; k++) sc->pl_sum.l[k] = 0;
+    sc->low_max = 0; sc->low_max_valid = 0;
     for (int k = 0; k < 4; k++) { sc->B_lo.l[k] = 0; sc->S_cand.l[k] = 0; }
 }
 
@@ -431,7 +514,12 @@ __device__ inline bool comb_rescale(SelScratch *sc, const SelResult *res, long l
     int nscale;
     if (isz128(T)) {
         if (scale >= max_scale) return false;               // the low partition really is all zero
-        nscale = scale + 64;
+        if (sc->low_max_valid) {
+            // the classify pass saw the largest low item: go straight to the scale that resolves it
+            if (sc->low_max == 0) return false;             // nothing but exact zeros below the threshold
+            nscale = SEL_ITEM_BITS - 3 - exp_of_bits(sc->low_max);
+            if (nscale <= scale) nscale = scale + 64;
+        } else nscale = scale + 64;                         // (fused round: the next, classic, round will know)
     } else {
         if (!lt128(T, shl128(mk128((u64)n, 0), 52))) return false;
         int blT = T.hi ? 128 - __clzll((long long)T.hi) : 64 - __clzll((long long)T.lo);
@@ -446,143 +534,181 @@ __device__ inline bool comb_rescale(SelScratch *sc, const SelResult *res, long l
     return true;
 }
 
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
+// mark the step as not completable: every later kernel of the handle is a no-op
+__device__ __forceinline__ void sel_halt(SelScratch *sc, long long step, int reason)
 {
-    if (a.nranks > 1 && a.sc->halt) return;          // sharded look-ahead: an earlier step is waiting for the host
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s_u64 = reinterpret_cast<u64 *>(smem_raw);               // SEL_FINAL_CAP u64 for the final sort
-    __shared__ u128 s_warp[33];
-    __shared__ long long s_ll[4];
-    __shared__ u128 s_red[3][SEL_WARPS];
-    __shared__ unsigned long long s_redc[2][SEL_WARPS];
+    if (!sc->halt) { sc->halt = step + 1; sc->halt_reason = reason; }
+}
 
+// sharded: all threads of the cluster copy `n` doubles of the local list into segment `rank` of every region
+__device__ inline void xch_copy_list(cg::cluster_group &cluster, const Xch *x, const double *src, long long n, int kind, int parity)
+{
+    const long long nth = (long long)cluster.num_blocks() * SEL_THREADS;
+    const long long t0 = (long long)cluster.block_rank() * SEL_THREADS + threadIdx.x;
+    for (int p = 0; p < x->nranks; p++) {
+        double *dst = kind == XCH_A ? xch_listA(x->reg[p], x->capA, x->rank)
+                                    : xch_listB(x->reg[p], x->nranks, x->capA, x->capB, parity, x->rank);
+        for (long long t = t0; t < n; t += nth) dst[t] = src[t];
+    }
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------ classic path: reset + strided sample
+// (pf_select, the sorted traversal order and PF_NO_FUSE; the fused path samples inside k_expand)
+__global__ void k_sel_reset(SelArgs a)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    SelScratch *sc = a.sc; SelResult *res = a.res;
+    if (sc->halt) return;
+    reset_round(sc);
+    for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
+    res->rounds = 0; res->status = 0; res->n_cand_first = 0; res->n_plateau_first = 0; sc->n_fail = 0;
+    res->t_ns[0] = gtimer();
+    sc->mult = 1; sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0; sc->vs_bits = 0; sc->phase = 0;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_sample(SelArgs a)
+{
+    SelScratch *sc = a.sc;
+    if (sc->halt) return;
+    const long long n_live = *a.n_live, M = *a.M;
+    const u64 vmax = *a.vmax_bits;
+    if (M <= a.N || vmax == 0 || M <= SEL_FINAL_CAP) return;           // solved directly
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long gwarp = (long long)blockIdx.x * SEL_WARPS + wid, nwarps = (long long)gridDim.x * SEL_WARPS;
+    const long long stride = a.fixed_stride;
+    ChunkWriter cw; cw.init();
+    unsigned long long cnt_s = 0;
+    u64 vs_max = 0;
+    // particle g is in the sample iff (g / 4) % stride == 0 (aligned groups of 4; the same
+    // rule as the sample expansion, so every path brackets the threshold on the same sample)
+    for (long long base = gwarp * 32; (base >> 2) * (4 * stride) < n_live; base += nwarps * 32) {
+        const long long g = base + lane;
+        const long long i = (g >> 2) * (4 * stride) + (g & 3);
+        int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
+        int maxc = c;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+        for (int j = 0; j < maxc; j++) {
+            bool have = j < c;
+            u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
+            have = have && bits != 0;             // zeros never decide anything
+            cnt_s += have;
+            vs_max = bits > vs_max ? bits : vs_max;
+            cw.push(have, bits, a.cand, &sc->cand_chunks, lane);
+        }
+    }
+    cw.finish(a.cand, lane);
+    cnt_s = warp_sum64(cnt_s);
+    vs_max = warp_max64(vs_max);
+    if (lane == 0 && cnt_s) { atomicAdd(&sc->n_cand, cnt_s); atomicMax(&sc->vs_bits, vs_max); }
+}
+
+// ------------------------------------------------------------------ k_sel_bracket (one cluster)
+__global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ ListView s_lv;
     SelScratch *sc = a.sc;
     SelResult *res = a.res;
-    const long long n_live = *a.n_live;
-    const long long M = *a.M;
-    const u64 vmax = *a.vmax_bits;
+    const Xch *x = a.x;
+    if (sc->halt) return;
+    const int tid = threadIdx.x;
+    const bool lead = cluster.block_rank() == 0 && tid == 0;
     const long long N = a.N;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long gwarp = (long long)blockIdx.x * SEL_WARPS + wid;
-    const long long nwarps = (long long)gridDim.x * SEL_WARPS;
-    const int e_vmax = exp_of_bits(vmax);
-    const int tot_scale = SEL_TOT_BITS - e_vmax;
-    const int vmax_scale = SEL_ITEM_BITS - e_vmax;
-    const bool trivial = (M <= N || vmax == 0);
-    const bool sampled = !trivial && M > SEL_FINAL_CAP;
-    const int stage = a.stage;
-    const bool multi = a.nranks > 1;
-    const u64 plateau = a.plateau_ptr ? *a.plateau_ptr : 0ull;
-    const double *list = multi ? a.glist : a.cand;
 
-    // ---------------- phase 0: first bracket
-    if (stage & SEL_ST_SAMPLE) {
-    if (blockIdx.x == 0 && tid == 0) {
-        reset_round(sc);
-        for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
-        res->rounds = 0; res->status = 0; res->n_cand_first = 0; sc->n_fail = 0;
-        res->t_ns[0] = gtimer();
-        sc->mult = 1; sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0; sc->vs_bits = 0;
-        if (multi) {               // sharded: the global M is not known yet; decided at the BRACKET stage
-            sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0;
-        } else if (trivial) {      // keep everything (src/fearnhead.jl:135-138); an all-zero step keeps nothing
-            sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1;
-        } else {                   // direct solve, or the starting bracket of the sample solve
-            sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0;
+    // ---- the sample: local list, or (sharded) every rank's list gathered through the exchange regions
+    if (x) {
+        if (a.stage & SEL_ST_PUB) {
+            const long long ns = sc->list_n;
+            const long long n_pub = ns <= x->capA ? ns : x->capA;
+            xch_copy_list(cluster, x, a.cand, n_pub, XCH_A, 0);
+            cluster.sync();
+            if (lead) {
+                XchHdrA hd; hd.n = (unsigned long long)n_pub; hd.vmax = *a.vmax_bits; hd.M_pred = (unsigned long long)*a.M;
+                hd.overflow = ns > x->capA ? 1ull : 0ull;
+                for (int p = 0; p < x->nranks; p++) x->reg[p]->a[x->rank] = hd;
+                xch_signal(x, XCH_A, a.seq);
+            }
         }
-    }
-    grid.sync();
-    }
-    const long long stride = (multi || a.fixed_stride > 0) ? a.fixed_stride : (M + SEL_SAMPLE_TARGET - 1) / SEL_SAMPLE_TARGET;
-    // (a sharded run samples unconditionally: the global M is only known after the gather)
-    if ((sampled || multi) && (stage & SEL_ST_SAMPLE)) {
-        // strided sample of whole particles (global indices = 0 mod stride), appended to the
-        // (still unused) candidate list
-        {
-            ChunkWriter cw; cw.init();
-            unsigned long long cnt_s = 0;
-            u64 vs_max = 0;
-            // global particle g is in the sample iff (g / 4) % stride == 0 (aligned groups of 4; the same
-            // rule as the sample expansion, so every path brackets the threshold on the same sample)
-            const long long goff = a.goff ? *a.goff : 0;
-            const long long k0 = goff / (4 * stride);                 // first sampled group that can reach this shard
-            const long long swarps = multi ? (nwarps < SEL_SAMPLE_WARPS ? nwarps : SEL_SAMPLE_WARPS) : nwarps;
-            for (long long base = gwarp * 32; gwarp < swarps && (k0 + (base >> 2)) * (4 * stride) < goff + n_live; base += swarps * 32) {
-                const long long g = base + lane;
-                const long long i = (k0 + (g >> 2)) * (4 * stride) + (g & 3) - goff;
-                int c = (i >= 0 && i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
-                int maxc = c;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
-                for (int j = 0; j < maxc; j++) {
-                    bool have = j < c;
-                    u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
-                    have = have && bits != 0;             // zeros never decide anything
-                    cnt_s += have;
-                    vs_max = bits > vs_max ? bits : vs_max;
-                    cw.push(have, bits, a.cand, &sc->cand_chunks, lane);
+        if (!(a.stage & SEL_ST_RUN)) return;
+        if (lead) {
+            const bool ok = xch_wait(x, XCH_A, a.seq);
+            unsigned long long ovf = 0;
+            long long gM = 0; u64 gv = 0;
+            if (ok) {
+                const XchHdrA *ha = x->reg[x->rank]->a;
+                for (int r = 0; r < x->nranks; r++) {
+                    gM += (long long)ld_peer(&ha[r].M_pred);
+                    const u64 v = ld_peer(&ha[r].vmax); gv = v > gv ? v : gv;
+                    ovf |= ld_peer(&ha[r].overflow);
                 }
             }
-            cw.finish(a.cand, lane);
-            cnt_s = warp_sum64(cnt_s);
-            vs_max = warp_max64(vs_max);
-            if (lane == 0 && cnt_s) { atomicAdd(&sc->n_cand, cnt_s); atomicMax(&sc->vs_bits, vs_max); }
-            if (!(stage & SEL_ST_BRACKET)) {                 // sharded: the host gathers the samples
-                grid.sync();
-                pad_list(a.cand, sc->cand_chunks, a.pad_to, sc);
-                return;
+            if (!ok) sel_halt(sc, a.step, PF_HALT_TIMEOUT); else if (ovf) sel_halt(sc, a.step, PF_HALT_XCH_OVERFLOW);
+            sc->gM = gM; sc->gvmax = gv;
+            __threadfence();
+        }
+        cluster.sync();
+        if (sc->halt) return;
+        if (tid == 0) {
+            const XchHdrA *ha = x->reg[x->rank]->a;
+            s_lv.nseg = x->nranks; s_lv.off[0] = 0;
+            for (int r = 0; r < x->nranks; r++) {
+                s_lv.seg[r] = xch_listA(x->reg[x->rank], x->capA, r);
+                s_lv.off[r + 1] = s_lv.off[r] + (long long)ld_peer(&ha[r].n);
             }
-            grid.sync();
+        }
+    } else {
+        if (lead) { sc->gM = *a.M; sc->gvmax = *a.vmax_bits; __threadfence(); }
+        cluster.sync();
+        if (tid == 0) {
+            s_lv.nseg = 1; s_lv.seg[0] = a.cand; s_lv.off[0] = 0;
+            s_lv.off[1] = a.external_sample ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
         }
     }
-    if (a.external_sample && (stage & SEL_ST_BRACKET)) {
-        // fused path: k_expand (sample mode) already filled the list with sc->list_n sample values
-        if (blockIdx.x == 0 && tid == 0) {
-            const long long ns = sc->list_n;
+    __syncthreads();
+    const long long M = sc->gM;
+    const u64 vmax = sc->gvmax;                         // (external sample: the sample's maximum)
+    const int vmax_scale = SEL_ITEM_BITS - exp_of_bits(vmax);
+    const bool trivial = a.external_sample ? (M <= N) : (M <= N || vmax == 0);
+    const bool sampled = a.external_sample ? !trivial : (!trivial && M > SEL_FINAL_CAP);
+    const long long stride = a.fixed_stride;
+    const long long ns_total = s_lv.off[s_lv.nseg];
+    cluster.sync();                                     // every CTA has read the sample's size before the lead resets the counters
+
+    if (lead) {
+        if (a.external_sample) {
+            // fused path: k_expand (sample mode) filled the list; this is also the step's reset
             reset_round(sc);
             for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0;
-            res->rounds = 0; res->status = 0; res->n_cand_first = 0; sc->n_fail = 0;
+            res->rounds = 0; res->status = 0; res->n_cand_first = 0; res->n_plateau_first = 0; sc->n_fail = 0;
             res->t_ns[0] = gtimer();
-            sc->mult = 1; sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0;
-            sc->n_cand = (unsigned long long)ns; sc->list_n = ns; sc->list_exact = 1; sc->vs_bits = vmax;     // (vmax = the sample's maximum here)
-            if (M <= N) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1; }     // (M is exact here)
-            else { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0; }
+            sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0;
+            sc->n_cand = (unsigned long long)ns_total; sc->vs_bits = vmax;
         }
-        grid.sync();
+        sc->mult = 1;
+        if (trivial) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1; }     // keep everything (src/fearnhead.jl:135-138)
+        else { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0; }                     // direct solve, or the sample solve's start
+        if (sampled) { sc->B_run = mk128(0, 0); sc->A_run = 0; sc->count_in = (long long)sc->n_cand; sc->mult = stride; sc->phase = 2; }
+        __threadfence();
     }
-    if (multi && (stage & SEL_ST_BRACKET)) {
-        if (blockIdx.x == 0 && tid == 0) {
-            reset_round(sc);
-            if (trivial) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1; }
-            else { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0; }
-        }
-        grid.sync();
-    }
-    if (sampled && (stage & SEL_ST_BRACKET)) {
-        if (blockIdx.x == 0 && tid == 0) {
-            if (multi) sum_gathered(sc, a.gacc, a.nranks);
-            sc->B_run = mk128(0, 0); sc->A_run = 0; sc->count_in = (long long)sc->n_cand; sc->mult = stride; sc->phase = 2;
-            sc->lo = 1; sc->hi = PF_INF_BITS;
-            if (multi) sc->vs_bits = (u64)a.M[3];                    // gathered sample maximum (k_mg_globals)
-        }
-        grid.sync();
+    cluster.sync();
+    if (sampled) {
         const int ss = SEL_ITEM_BITS - exp_of_bits(sc->vs_bits);     // the sample solve runs at the sample's own scale
-        const long long list_n = multi ? a.glist_each * a.nranks : (sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK);
         for (int level = 0; level < 8; level++) {
             const u64 blo = sc->lo, bhi = sc->hi;
             if (sc->count_in == 0 || (bhi - blo) <= 1) break;
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            hist_level(list, list_n, blo, bhi, shift, ss, sc, smem_raw);
-            grid.sync();
-            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, ss, a.margin > 0 ? a.margin : 8, smem_raw);
-            grid.sync();
+            hist_level(cluster, s_lv, blo, bhi, shift, ss, sc, smem_raw);
+            if (cluster.block_rank() == 0) select_bin(sc, N, blo, bhi, shift, ss, a.margin > 0 ? a.margin : 8, smem_raw);
+            cluster.sync();
             if (sc->phase == 6) break;
         }
-        if (blockIdx.x == 0 && tid == 0) {
+        cluster.sync();                                 // everyone has left the loop before the lead rewrites the bracket
+        if (lead) {
             u64 lo = sc->lo, hi = sc->hi;
             if (lo < 1) lo = 1;
             if (hi <= lo) hi = lo + 1;
@@ -596,205 +722,304 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                 sc->fuse_valid = 1; sc->fuse_scale = sc->scale; sc->fuse_tot_scale = 52 - exp_of_bits(hi); sc->list_exact = 1;
             }
         }
+    } else if (lead && a.external_sample) {
+        reset_round(sc);                                 // the classic rounds start from a clean slate
     }
-    if (blockIdx.x == 0 && tid == 0 && (stage & SEL_ST_BRACKET)) res->t_ns[1] = gtimer();
-    if (a.external_sample && !(stage & (SEL_ST_CLASSIFY | SEL_ST_SOLVE))) {              // fused path: the expansion runs next
-        if (blockIdx.x == 0 && tid == 0 && !sc->fuse_valid) reset_round(sc);       // the classic rounds start from a clean slate
-        return;
-    }
-    grid.sync();
+    if (lead) { sc->phase = 0; res->t_ns[1] = gtimer(); }
+}
 
-    // ---------------- rounds
-    const bool pre = a.preclassified && sc->fuse_valid;      // the expansion kernel classified round `round0`
-    if (pre && blockIdx.x == 0 && tid == 0) res->status |= 1;
-    if (a.preclassified && !pre) {
-        // classic rounds behind a sample expansion: a bracket that is open at the top was scaled by the
-        // SAMPLE's maximum; the true maximum is known now
-        if (blockIdx.x == 0 && tid == 0 && sc->hi >= PF_INF_BITS) sc->scale = vmax_scale;
-        grid.sync();
-    }
-    for (int round = a.round0; round < 40; round++) {
-        const u64 lo = sc->lo, hi = sc->hi;
-        const int scale = sc->scale;
-        const int mode = sc->mode;
-        const bool keep_all = (mode == 1);
-        const bool pre_round = pre && round == a.round0;
-        const bool need_tot = sc->need_tot != 0;
-        const int ts_round = kept_tot_scale(hi, vmax);
-        // ---- classify pass over all items
-        if ((stage & SEL_ST_CLASSIFY) && !pre_round) {
-            unsigned long long A_hi = 0, n_cand = 0, n_plat = 0;
-            u128 B_lo = mk128(0, 0), S_c = mk128(0, 0), Tot = mk128(0, 0);
-            ChunkWriter cw; cw.init();
-            for (long long base = gwarp * 32; base < n_live; base += nwarps * 32) {
-                long long i = base + lane;
-                int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
-                int maxc = c;
+// ------------------------------------------------------------------ k_sel_classify (full grid)
+// One pass over all putatives against the current bracket.  Round 0 of a fused step was classified by the
+// expansion kernel (no-op here); a queued retry round runs only if the previous solve asked for it.
+__global__ void __launch_bounds__(SEL_THREADS, 2) k_sel_classify(SelArgs a)
+{
+    SelScratch *sc = a.sc;
+    if (sc->halt) return;
+    if (a.retry ? sc->phase != 3 : (a.preclassified && sc->fuse_valid)) return;
+    __shared__ u128 s_red[3][SEL_WARPS];
+    __shared__ unsigned long long s_redc[2][SEL_WARPS];
+    const long long n_live = *a.n_live;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long gwarp = (long long)blockIdx.x * SEL_WARPS + wid;
+    const long long nwarps = (long long)gridDim.x * SEL_WARPS;
+    const u64 lo = sc->lo, hi = sc->hi;
+    const int scale = sc->scale;
+    const bool need_tot = sc->need_tot != 0;
+    // kept-side scale from the maximum known here: the exact one on a single GPU; in a sharded run the global
+    // one of the previous exchange (round 0: the SAMPLE's maximum -- the solve checks the choice against the
+    // true maximum and redoes the round if it was not the exact scale)
+    const int ts_round = kept_tot_scale(hi, a.x ? sc->gvmax : *a.vmax_bits);
+    const u64 plateau = a.plateau_ptr ? *a.plateau_ptr : 0ull;
+    if (blockIdx.x == 0 && tid == 0) { sc->tot_scale_used = ts_round; sc->low_max_valid = 1; }
+    unsigned long long A_hi = 0, n_cand = 0, n_plat = 0;
+    u64 low_max = 0;
+    u128 B_lo = mk128(0, 0), S_c = mk128(0, 0), Tot = mk128(0, 0);
+    ChunkWriter cw; cw.init();
+    for (long long base = gwarp * 32; base < n_live; base += nwarps * 32) {
+        long long i = base + lane;
+        int c = (i < n_live) ? (a.cnt ? a.cnt[i] : 1) : 0;
+        int maxc = c;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
-                for (int j = 0; j < maxc; j++) {
-                    bool have = j < c;
-                    u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
-                    bool is_cand = false;
-                    if (have) {
-                        if (bits >= hi) { A_hi++; if (need_tot) Tot = add128(Tot, fx128(bits, ts_round)); }
-                        else if (bits < lo) B_lo = add128(B_lo, fx70(bits, scale));
-                        else if (bits == plateau) n_plat++;                  // the mass tie: counted, not listed
-                        else { is_cand = true; n_cand++; S_c = add128(S_c, fx70(bits, scale)); }
-                    }
-                    cw.push(is_cand, bits, a.cand, &sc->cand_chunks, lane);
-                }
+        for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+        for (int j = 0; j < maxc; j++) {
+            bool have = j < c;
+            u64 bits = have ? (u64)__double_as_longlong(a.V[(long long)j * a.cap + i]) : 0ull;
+            bool is_cand = false;
+            if (have) {
+                if (bits >= hi) { A_hi++; if (need_tot) Tot = add128(Tot, fx128(bits, ts_round)); }
+                else if (bits < lo) { B_lo = add128(B_lo, fx70(bits, scale)); low_max = bits > low_max ? bits : low_max; }
+                else if (bits == plateau) n_plat++;                  // the mass tie: counted, not listed
+                else { is_cand = true; n_cand++; S_c = add128(S_c, fx70(bits, scale)); }
             }
-            cw.finish(a.cand, lane);
-            // block reduce, then one set of atomics per block
-            A_hi = warp_sum64(A_hi); n_cand = warp_sum64(n_cand); n_plat = warp_sum64(n_plat);
-            if (lane == 0 && n_plat) atomicAdd(&sc->n_plateau, n_plat);
-            B_lo = warp_sum128(B_lo); S_c = warp_sum128(S_c); Tot = warp_sum128(Tot);
-            if (lane == 0) { s_redc[0][wid] = A_hi; s_redc[1][wid] = n_cand; s_red[0][wid] = B_lo; s_red[1][wid] = S_c; s_red[2][wid] = Tot; }
-            __syncthreads();
-            if (wid == 0) {
-                unsigned long long x0 = lane < SEL_WARPS ? s_redc[0][lane] : 0, x1 = lane < SEL_WARPS ? s_redc[1][lane] : 0;
-                u128 y0 = lane < SEL_WARPS ? s_red[0][lane] : mk128(0, 0), y1 = lane < SEL_WARPS ? s_red[1][lane] : mk128(0, 0),
-                     y2 = lane < SEL_WARPS ? s_red[2][lane] : mk128(0, 0);
-                x0 = warp_sum64(x0); x1 = warp_sum64(x1);
-                y0 = warp_sum128(y0); y1 = warp_sum128(y1); y2 = warp_sum128(y2);
-                if (lane == 0) {
-                    if (x0) atomicAdd(&sc->A_hi, x0);
-                    if (x1) atomicAdd(&sc->n_cand, x1);
-                    atomic_add_acc(&sc->B_lo, y0);
-                    atomic_add_acc(&sc->S_cand, y1);
-                    if (need_tot) atomic_add_acc(&sc->Tot, y2);
-                }
-            }
-            __syncthreads();
-            if (!(stage & SEL_ST_SOLVE)) {                   // sharded: the host gathers accumulators + candidates
-                grid.sync();
-                pad_list(a.cand, sc->cand_chunks, a.pad_to, sc);
-                return;
-            }
-            grid.sync();
+            cw.push(is_cand, bits, a.cand, &sc->cand_chunks, lane);
         }
+    }
+    cw.finish(a.cand, lane);
+    // block reduce, then one set of atomics per block
+    A_hi = warp_sum64(A_hi); n_cand = warp_sum64(n_cand); n_plat = warp_sum64(n_plat); low_max = warp_max64(low_max);
+    if (lane == 0 && n_plat) atomicAdd(&sc->n_plateau, n_plat);
+    if (lane == 0 && low_max) atomicMax(&sc->low_max, low_max);
+    B_lo = warp_sum128(B_lo); S_c = warp_sum128(S_c); Tot = warp_sum128(Tot);
+    if (lane == 0) { s_redc[0][wid] = A_hi; s_redc[1][wid] = n_cand; s_red[0][wid] = B_lo; s_red[1][wid] = S_c; s_red[2][wid] = Tot; }
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long x0 = lane < SEL_WARPS ? s_redc[0][lane] : 0, x1 = lane < SEL_WARPS ? s_redc[1][lane] : 0;
+        u128 y0 = lane < SEL_WARPS ? s_red[0][lane] : mk128(0, 0), y1 = lane < SEL_WARPS ? s_red[1][lane] : mk128(0, 0),
+             y2 = lane < SEL_WARPS ? s_red[2][lane] : mk128(0, 0);
+        x0 = warp_sum64(x0); x1 = warp_sum64(x1);
+        y0 = warp_sum128(y0); y1 = warp_sum128(y1); y2 = warp_sum128(y2);
+        if (lane == 0) {
+            if (x0) atomicAdd(&sc->A_hi, x0);
+            if (x1) atomicAdd(&sc->n_cand, x1);
+            atomic_add_acc(&sc->B_lo, y0);
+            atomic_add_acc(&sc->S_cand, y1);
+            if (need_tot) atomic_add_acc(&sc->Tot, y2);
+        }
+    }
+}
 
-        // ---- block 0: verify the bracket, start the descent
-        if (blockIdx.x == 0 && tid == 0) {
-            if (multi) sum_gathered(sc, a.gacc, a.nranks);
-            bool truncated = false;
-            if (multi) for (int r = 0; r < a.nranks; r++) truncated |= a.gacc[r].overflow != 0;
-            res->rounds = round + 1;
-            // fused path: the expansion's classification is unusable if a block overflowed its candidate
-            // buffer or the true maximum lies more than 46 binades above hi (kept-side scale not exact)
-            const bool pre_bad = pre_round && (sc->fuse_overflow || kept_tot_scale(hi, vmax) != sc->fuse_tot_scale);
-            if (need_tot && !pre_bad) {
-                if (round == a.round0) { res->n_cand_first = (long long)sc->n_cand; res->t_ns[2] = gtimer(); }
-                // total weight = kept side (>= hi) + low side (< hi, bracket scale)
-                const int ts = pre_round ? sc->fuse_tot_scale : ts_round;
-                u128 low = add128(acc_value(&sc->B_lo), acc_value(&sc->S_cand));
-                if (sc->n_plateau) low = add128(low, mul128_64(fx70(plateau, scale), (u64)sc->n_plateau));
-                double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), ts - scale);
-                res->log_total = log(tsum) - (double)ts * 0.693147180559945309417232121458;
-                sc->need_tot = 0;
+// ------------------------------------------------------------------ k_sel_solve (one cluster)
+__global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s_u64 = reinterpret_cast<u64 *>(smem_raw);               // SEL_FINAL_CAP u64 for the final sort
+    __shared__ ListView s_lv;
+    __shared__ u128 s_warp[33];
+    __shared__ long long s_ll[4];
+    __shared__ u128 s_red[SEL_WARPS];
+    __shared__ unsigned long long s_redc[SEL_WARPS];
+
+    SelScratch *sc = a.sc;
+    SelResult *res = a.res;
+    const Xch *x = a.x;
+    if (sc->halt) return;
+    if (a.retry && sc->phase != 3) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned int nctas = cluster.num_blocks(), crank = cluster.block_rank();
+    const bool lead = crank == 0 && tid == 0;
+    const long long N = a.N;
+    const int round = a.retry ? res->rounds : 0;
+    const bool pre_round = !a.retry && a.preclassified && sc->fuse_valid;      // the expansion kernel classified this round
+    const u64 plateau = a.plateau_ptr ? *a.plateau_ptr : 0ull;
+
+    // ---- the candidate list and the accumulators: local, or (sharded) gathered through the exchange regions
+    if (x) {
+        const int parity = round & 1;
+        const unsigned long long seq = a.seq * 64 + (unsigned long long)round;
+        if (a.stage & SEL_ST_PUB) {
+            const long long nl = sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
+            const long long n_pub = nl <= x->capB ? nl : x->capB;
+            xch_copy_list(cluster, x, a.cand, n_pub, XCH_B, parity);
+            cluster.sync();
+            if (lead) {
+                SelAcc hd = *reinterpret_cast<const SelAcc *>(reinterpret_cast<const char *>(sc) + SEL_ACC_OFFSET);
+                hd.cand_chunks = (unsigned long long)n_pub;            // entries of this rank's segment
+                hd.overflow = nl > x->capB ? 1ull : 0ull;
+                hd.M_local = (unsigned long long)*a.M; hd.vmax_local = *a.vmax_bits;
+                for (int p = 0; p < x->nranks; p++) x->reg[p]->b[parity][x->rank] = hd;
+                xch_signal(x, XCH_B, seq);
             }
-            int phase = 2;       // 2 = descend, 3 = redo classify with a new bracket, 4 = done, 7 = gathered list truncated
-            if (truncated) { reset_round(sc); phase = 7; }      // the host re-classifies and gathers at exact size
-            else if (pre_bad) { reset_round(sc); for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0; sc->fuse_valid = 0; phase = 3; res->status |= sc->fuse_overflow ? 2 : 4; }
-            else if (keep_all) phase = 4;
-            else if (mode == 2) {
-                // comb-rescale round: T at the new scale; lo = hi = thr so A_hi = A again
-                res->T = acc_value(&sc->B_lo); res->scale = scale;
-                phase = comb_rescale(sc, res, N) ? 3 : 4;
+        }
+        if (!(a.stage & SEL_ST_RUN)) return;
+        if (lead) {
+            const bool ok = xch_wait(x, XCH_B, seq);
+            if (ok) {
+                const SelAcc *g = x->reg[x->rank]->b[parity];
+                unsigned long long A = 0, nc = 0, npl = 0, ovf = 0, Mg = 0, vm = 0, lm = 0;
+                acc128 b, c, t;
+                for (int k = 0; k < 4; k++) { b.l[k] = 0; c.l[k] = 0; t.l[k] = 0; }
+                for (int r = 0; r < x->nranks; r++) {
+                    A += ld_peer(&g[r].A_hi); nc += ld_peer(&g[r].n_cand); npl += ld_peer(&g[r].n_plateau); ovf |= ld_peer(&g[r].overflow);
+                    Mg += ld_peer(&g[r].M_local);
+                    const u64 v = ld_peer(&g[r].vmax_local); vm = v > vm ? v : vm;
+                    const u64 l = ld_peer(&g[r].low_max); lm = l > lm ? l : lm;
+                    for (int k = 0; k < 4; k++) { b.l[k] += ld_peer(&g[r].B_lo.l[k]); c.l[k] += ld_peer(&g[r].S_cand.l[k]); t.l[k] += ld_peer(&g[r].Tot.l[k]); }
+                }
+                sc->A_hi = A; sc->n_cand = nc; sc->B_lo = b; sc->S_cand = c; sc->Tot = t; sc->n_plateau = npl; sc->low_max = lm;
+                sc->gM = (long long)Mg; sc->gvmax = vm;
+                if (ovf) sel_halt(sc, a.step, PF_HALT_XCH_OVERFLOW);
+            } else sel_halt(sc, a.step, PF_HALT_TIMEOUT);
+            __threadfence();
+        }
+        cluster.sync();
+        if (sc->halt) return;
+        if (tid == 0) {
+            const SelAcc *g = x->reg[x->rank]->b[parity];
+            s_lv.nseg = x->nranks; s_lv.off[0] = 0;
+            for (int r = 0; r < x->nranks; r++) {
+                s_lv.seg[r] = xch_listB(x->reg[x->rank], x->nranks, x->capA, x->capB, parity, r);
+                s_lv.off[r + 1] = s_lv.off[r] + (long long)ld_peer(&g[r].cand_chunks);
+            }
+        }
+    } else {
+        if (lead) { sc->gM = *a.M; sc->gvmax = *a.vmax_bits; __threadfence(); }
+        cluster.sync();
+        if (tid == 0) {
+            s_lv.nseg = 1; s_lv.seg[0] = a.cand; s_lv.off[0] = 0;
+            s_lv.off[1] = sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
+        }
+    }
+    __syncthreads();
+    const long long M = sc->gM;
+    const u64 vmax = sc->gvmax;
+    const int vmax_scale = SEL_ITEM_BITS - exp_of_bits(vmax);
+    const bool trivial = (M <= N || vmax == 0);
+    const long long list_n = s_lv.off[s_lv.nseg];
+
+    const u64 lo = sc->lo, hi = sc->hi;
+    const int scale = sc->scale;
+    const int mode = sc->mode;
+    const bool keep_all = (mode == 1);
+    const bool need_tot = sc->need_tot != 0;
+    cluster.sync();                          // everyone has read the round's bracket before CTA 0 may change it
+
+    // ---- CTA 0: verify the bracket, start the descent
+    if (lead) {
+        res->rounds = round + 1;
+        // fused path: the expansion's classification is unusable if a block overflowed its candidate
+        // buffer or the true maximum lies more than 46 binades above hi (kept-side scale not exact)
+        const bool pre_bad = pre_round && (sc->fuse_overflow || kept_tot_scale(hi, vmax) != sc->fuse_tot_scale);
+        // sharded classic round: k_sel_classify chose the kept-side scale from the maximum it knew; redo the
+        // round (the true maximum is known from now on) if that was not the scale the true maximum asks for
+        bool ts_bad = !pre_round && x && need_tot && kept_tot_scale(hi, vmax) != sc->tot_scale_used;
+        // a bracket that is open at the top was scaled by the maximum known when it was set (the SAMPLE's maximum
+        // behind a sample expansion); the true maximum is known now: redo the round at its scale if they differ
+        if (!pre_round && !keep_all && mode == 0 && hi >= PF_INF_BITS && scale != vmax_scale && vmax != 0) { ts_bad = true; sc->scale = vmax_scale; }
+        if (need_tot && !pre_bad && !ts_bad) {
+            if (round == 0) { res->n_cand_first = (long long)sc->n_cand; res->n_plateau_first = (long long)sc->n_plateau; res->t_ns[2] = gtimer(); }
+            // total weight = kept side (>= hi) + low side (< hi, bracket scale)
+            const int ts = pre_round ? sc->fuse_tot_scale : sc->tot_scale_used;
+            u128 low = add128(acc_value(&sc->B_lo), acc_value(&sc->S_cand));
+            if (sc->n_plateau) low = add128(low, mul128_64(fx70(plateau, scale), (u64)sc->n_plateau));
+            double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), ts - scale);
+            res->log_total = log(tsum) - (double)ts * 0.693147180559945309417232121458;
+            sc->need_tot = 0;
+        }
+        int phase = 2;       // 2 = descend, 3 = another classify round with a new bracket / scale, 4 = done
+        if (pre_bad || ts_bad) {
+            reset_round(sc); for (int k = 0; k < 4; k++) sc->Tot.l[k] = 0; sc->fuse_valid = 0; phase = 3;
+            res->status |= (pre_round && sc->fuse_overflow) ? 2 : 4;
+        }
+        else if (keep_all) phase = 4;
+        else if (mode == 2) {
+            // comb-rescale round: T at the new scale; lo = hi = thr so A_hi = A again
+            res->T = acc_value(&sc->B_lo); res->scale = scale;
+            phase = comb_rescale(sc, res, N) ? 3 : 4;
+        } else {
+            if (pre_round) res->status |= 1;
+            u128 B = acc_value(&sc->B_lo), Sc = acc_value(&sc->S_cand);
+            long long Ahi = (long long)sc->A_hi, nc = (long long)sc->n_cand;
+            const long long np = (long long)sc->n_plateau;            // in-bracket copies of the plateau value (not in the list)
+            const u128 Pm = np ? mul128_64(fx70(plateau, scale), (u64)np) : mk128(0, 0);
+            bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc + np, fx70(lo, scale));
+            bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(add128(B, Sc), Pm), N, Ahi, fx70(hi, scale));
+            if (fail_lo || fail_hi) {
+                res->status |= fail_lo ? 8 : 16;
+                // the sample missed by more than its margin: move the bracket to the failing side and
+                // make it 8x wider (64x the second time); the third failure opens it completely
+                const int nf = ++sc->n_fail;
+                const u64 w = hi - lo;
+                const bool bounded = nf <= 2 && hi < PF_INF_BITS && lo > 1 && w < (1ull << 56);
+                const u64 grow = bounded ? w << 3 : 0;
+                u64 nlo, nhi;
+                if (fail_hi) { nlo = hi; nhi = (bounded && hi + grow < PF_INF_BITS) ? hi + grow : PF_INF_BITS; }
+                else { nhi = lo; nlo = (bounded && lo > grow + 1) ? lo - grow : 1ull; }
+                sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
+                sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
+                reset_round(sc);
+                phase = 3;
             } else {
-                u128 B = acc_value(&sc->B_lo), Sc = acc_value(&sc->S_cand);
-                long long Ahi = (long long)sc->A_hi, nc = (long long)sc->n_cand;
-                const long long np = (long long)sc->n_plateau;            // in-bracket copies of the plateau value (not in the list)
-                const u128 Pm = np ? mul128_64(fx70(plateau, scale), (u64)np) : mk128(0, 0);
-                bool fail_lo = (lo > 1) && pred128(B, N, Ahi + nc + np, fx70(lo, scale));
-                bool fail_hi = (hi < PF_INF_BITS) && !pred128(add128(add128(B, Sc), Pm), N, Ahi, fx70(hi, scale));
-                if (fail_lo || fail_hi) {
-                    res->status |= fail_lo ? 8 : 16;
-                    // the sample missed by more than its margin: move the bracket to the failing side and
-                    // make it 8x wider (64x the second time); the third failure opens it completely
-                    const int nf = ++sc->n_fail;
-                    const u64 w = hi - lo;
-                    const bool bounded = nf <= 2 && hi < PF_INF_BITS && lo > 1 && w < (1ull << 56);
-                    const u64 grow = bounded ? w << 3 : 0;
-                    u64 nlo, nhi;
-                    if (fail_hi) { nlo = hi; nhi = (bounded && hi + grow < PF_INF_BITS) ? hi + grow : PF_INF_BITS; }
-                    else { nhi = lo; nlo = (bounded && lo > grow + 1) ? lo - grow : 1ull; }
-                    sc->lo = nlo; sc->hi = nhi; sc->mode = 0;
-                    sc->scale = SEL_ITEM_BITS - exp_of_bits(nhi >= PF_INF_BITS ? vmax : nhi);
-                    reset_round(sc);
-                    phase = 3;
-                } else {
-                    sc->B_run = B; sc->A_run = Ahi; sc->count_in = nc;
-                    if (np) phase = 8;           // first decide on which side of the plateau the threshold lies
-                }
+                sc->B_run = B; sc->A_run = Ahi; sc->count_in = nc;
+                if (np) phase = 8;           // first decide on which side of the plateau the threshold lies
             }
-            sc->phase = phase;
         }
-        grid.sync();
-        if (sc->phase == 8) {
-            // ---- plateau resolution: mass and count of the candidates below the plateau value P, then the
-            // predicate at P itself; the bracket shrinks to [lo, P) or (P, hi) and never contains the tie
-            const long long ln = multi ? a.glist_each * a.nranks : (sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK);
-            u128 sb = mk128(0, 0);
-            unsigned long long cb = 0;
-            for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < ln; t += (long long)gridDim.x * SEL_THREADS) {
-                u64 bits = (u64)__double_as_longlong(list[t]);
-                if (bits >= lo && bits < plateau) { cb++; sb = add128(sb, fx70(bits, scale)); }
-            }
-            sb = warp_sum128(sb); cb = warp_sum64(cb);
-            if (lane == 0) { s_red[0][wid] = sb; s_redc[0][wid] = cb; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int w = 1; w < SEL_WARPS; w++) { sb = add128(sb, s_red[0][w]); cb += s_redc[0][w]; }
-                if (cb) atomicAdd(&sc->pl_cnt, cb);
-                atomic_add_acc(&sc->pl_sum, sb);
-            }
-            grid.sync();
-            if (blockIdx.x == 0 && tid == 0) {
-                const long long np = (long long)sc->n_plateau, cbt = (long long)sc->pl_cnt;
-                const u128 qP = fx70(plateau, scale);
-                const u128 Bp = add128(sc->B_run, acc_value(&sc->pl_sum));
-                const long long A_geqP = sc->A_run + (sc->count_in - cbt) + np;
-                if (pred128(Bp, N, A_geqP, qP)) { sc->hi = plateau; sc->A_run = A_geqP; sc->count_in = cbt; }
-                else { sc->lo = plateau + 1; sc->B_run = add128(Bp, mul128_64(qP, (u64)np)); sc->count_in = sc->count_in - cbt; }
-                sc->phase = 2;
-            }
-            grid.sync();
+        sc->phase = phase;
+        __threadfence();
+    }
+    cluster.sync();
+    if (sc->phase == 8) {
+        // ---- plateau resolution: mass and count of the candidates below the plateau value P, then the
+        // predicate at P itself; the bracket shrinks to [lo, P) or (P, hi) and never contains the tie
+        u128 sb = mk128(0, 0);
+        unsigned long long cb = 0;
+        for (long long t = (long long)crank * SEL_THREADS + tid; t < list_n; t += (long long)nctas * SEL_THREADS) {
+            u64 bits = lv_load(s_lv, t);
+            if (bits >= lo && bits < plateau) { cb++; sb = add128(sb, fx70(bits, scale)); }
         }
-        if (sc->phase == 7) return;
-        if (sc->phase == 3) { if (stage & SEL_ST_CLASSIFY) continue; return; }
-        if (sc->phase == 4) break;
+        sb = warp_sum128(sb); cb = warp_sum64(cb);
+        if (lane == 0) { s_red[wid] = sb; s_redc[wid] = cb; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < SEL_WARPS; w++) { sb = add128(sb, s_red[w]); cb += s_redc[w]; }
+            if (cb) atomicAdd(&sc->pl_cnt, cb);
+            atomic_add_acc(&sc->pl_sum, sb);
+            __threadfence();
+        }
+        cluster.sync();
+        if (lead) {
+            const long long np = (long long)sc->n_plateau, cbt = (long long)sc->pl_cnt;
+            const u128 qP = fx70(plateau, scale);
+            const u128 Bp = add128(sc->B_run, acc_value(&sc->pl_sum));
+            const long long A_geqP = sc->A_run + (sc->count_in - cbt) + np;
+            if (pred128(Bp, N, A_geqP, qP)) { sc->hi = plateau; sc->A_run = A_geqP; sc->count_in = cbt; }
+            else { sc->lo = plateau + 1; sc->B_run = add128(Bp, mul128_64(qP, (u64)np)); sc->count_in = sc->count_in - cbt; }
+            sc->phase = 2;
+            __threadfence();
+        }
+        cluster.sync();
+    }
+    if (sc->phase == 3) return;              // a queued retry round (k_sel_classify + k_sel_solve) takes over
 
+    if (sc->phase == 2) {
         // ---- radix descent over the candidate list
-        const long long list_n = multi ? a.glist_each * a.nranks : (sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK);
         for (int level = 0; level < 8; level++) {
             const u64 blo = sc->lo, bhi = sc->hi;
             const long long count_in = sc->count_in;
             if (count_in <= SEL_FINAL_CAP) {
                 // compact the bracket's items into the final list
-                for (long long t = (long long)blockIdx.x * SEL_THREADS + tid; t < list_n; t += (long long)gridDim.x * SEL_THREADS) {
-                    u64 bits = (u64)__double_as_longlong(list[t]);
+                for (long long t = (long long)crank * SEL_THREADS + tid; t < list_n; t += (long long)nctas * SEL_THREADS) {
+                    u64 bits = lv_load(s_lv, t);
                     if (bits >= blo && bits < bhi) {
                         unsigned int pos = atomicAdd(&sc->final_n, 1u);
                         if (pos < SEL_FINAL_CAP) sc->final_vals[pos] = __longlong_as_double((long long)bits);
                     }
                 }
-                grid.sync();
+                __threadfence();
                 break;
             }
             if ((bhi - blo) == 1) break;       // one value with > SEL_FINAL_CAP ties: closed form below
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            hist_level(list, list_n, blo, bhi, shift, scale, sc, smem_raw);
-            grid.sync();
-            if (blockIdx.x == 0) select_bin(sc, N, blo, bhi, shift, scale, 0, smem_raw);
-            grid.sync();
+            hist_level(cluster, s_lv, blo, bhi, shift, scale, sc, smem_raw);
+            if (crank == 0) select_bin(sc, N, blo, bhi, shift, scale, 0, smem_raw);
+            cluster.sync();
         }
+        cluster.sync();
 
-        // ---- block 0: exact solve on the final list
-        if (blockIdx.x == 0) {
+        // ---- CTA 0: exact solve on the final list
+        if (crank == 0) {
             const u64 blo = sc->lo, bhi = sc->hi;
             const long long count_in = sc->count_in;
             const u128 B0 = sc->B_run;
@@ -812,7 +1037,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             } else {
                 int nf = (int)count_in;
                 int np2 = 2; while (np2 < nf) np2 <<= 1;
-                for (int t = tid; t < np2; t += SEL_THREADS) s_u64[t] = t < nf ? (u64)__double_as_longlong(sc->final_vals[t]) : ~0ull;
+                for (int t = tid; t < np2; t += SEL_THREADS) s_u64[t] = t < nf ? (u64)__double_as_longlong(__ldcg(&sc->final_vals[t])) : ~0ull;
                 __syncthreads();
                 bitonic_sort_smem(s_u64, np2);
                 const int per = SEL_FINAL_CAP / SEL_THREADS;
@@ -868,15 +1093,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
                     sc->phase = comb_rescale(sc, res, N) ? 3 : 4;
                     if (sc->phase == 3) res->status |= 64;
                 }
+                __threadfence();
             }
         }
-        grid.sync();
-        if (sc->phase == 4) break;
-        if (!(stage & SEL_ST_CLASSIFY)) return;              // sharded: another classify round is needed (phase 3)
+        cluster.sync();
+        if (sc->phase != 4) return;
     }
 
-    // ---------------- outputs (block 0, thread 0)
-    if (blockIdx.x == 0 && tid == 0) {
+    // ---------------- outputs (CTA 0, thread 0)
+    if (lead) {
         res->t_ns[3] = gtimer();
         if (trivial) {
             const bool none = (vmax == 0 && M > N);
@@ -884,10 +1109,11 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             res->T = mk128(0, 0); res->Uoff = mk128(0, 0); res->Tq = mk128(0, 0); res->Tr = 0; res->scale = sc->scale;
             res->lw_resamp = __longlong_as_double(0xFFF0000000000000ll); res->log_c = res->lw_resamp;
             res->thr_value = 0.0;
+            sc->tiles_ok = 0;
         } else {
             res->keep_all = 0;
             long long n = N - res->A;
-            if (n < 0) { n = 0; res->status = 1; }          // cannot happen with consistent inputs
+            if (n < 0) { n = 0; res->status |= 128; }          // cannot happen with consistent inputs
             res->n = n;
             const u128 T = res->T;
             // Uoff = floor(mu * T / 2^53), mu = floor(u 2^53): 192-bit product, then >> 53
@@ -907,7 +1133,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_select(SelArgs a)
             res->lw_resamp = res->log_c - res->log_total;
             res->thr_value = __longlong_as_double((long long)res->thr_bits);
             // the tile records the expansion wrote stay usable if no classic round overwrote the list or the scale
-            sc->tiles_ok = (pre && sc->fuse_valid && res->rounds == a.round0 + 1 && res->scale == sc->fuse_scale) ? 1 : 0;
+            sc->tiles_ok = (a.preclassified && sc->fuse_valid && res->rounds == 1 && res->scale == sc->fuse_scale) ? 1 : 0;
         }
         res->t_ns[4] = gtimer();
     }

@@ -9,11 +9,19 @@ libparticles_b200.so on the GPU; nothing in this module computes the filter on t
     ps = FearnheadParticles(100, NormalInverseChisq(0., 1., 0.1, 1.0), ChineseRestaurantProcess(1.))
     filter_(ps, ys)
     assignments(ps)          # T x n matrix of 1-based component labels
+
+Two things the reference does not have, both stated in include/particles_b200.h:
+`k_max` (cluster slots per particle; the reference's component vector is unbounded,
+src/particle.jl:141-146) -- a step that had to drop a new-cluster candidate because K == k_max is
+reported (`on_overflow="warn"` by default, "raise" to make it an error); and `history`
+(generations of genealogy kept for `assignments`; the default -1 grows on demand like the
+reference's ancestor chain, 0 disables it, n > 0 is a fixed capacity).
 """
 from __future__ import annotations
 
 import ctypes as C
 import math
+import warnings
 
 import numpy as np
 
@@ -122,8 +130,8 @@ class ParticleFilter:
 
     _kind = None
 
-    def __init__(self, n, prior, stateprior, *, k_max=16, order=PF_ORDER_INDEX, history=0, device=0, seed=0,
-                 rejuv=50.0):
+    def __init__(self, n, prior, stateprior, *, k_max=32, order=PF_ORDER_INDEX, history=-1, device=0, seed=0,
+                 rejuv=50.0, on_overflow="warn"):
         if isinstance(prior, tuple):
             prior = NormalInverseChisq(*prior)                      # Component(params::NTuple), src/component.jl:8
         if not isinstance(stateprior, ChineseRestaurantProcess):
@@ -131,6 +139,9 @@ class ParticleFilter:
         self.N, self.prior, self.stateprior = int(n), prior, stateprior
         self.k_max, self.order, self.history = int(k_max), order, int(history)
         self.rejuvination_threshold = float(rejuv)
+        if on_overflow not in ("warn", "raise", "ignore"):
+            raise ValueError("on_overflow must be 'warn', 'raise' or 'ignore'")
+        self.on_overflow, self._overflow_seen = on_overflow, 0
         L = _lib.load()
         cfg = pf_config()
         cfg.filter_kind = self._kind
@@ -185,7 +196,25 @@ class ParticleFilter:
         else:
             u, pu = _d(np.atleast_1d(uniforms))
             _lib.check(self._L.pf_step(self._h, py, pu, len(u)), self._h)
+        self._check_overflow()
         return self
+
+    def _check_overflow(self):
+        """The reference always proposes a new component (src/particle.jl:141-146); the store has k_max
+        slots, and a particle at K == k_max loses that candidate.  Say so when it happens."""
+        if self.on_overflow == "ignore":
+            return
+        s = pf_step_stats()
+        if self._L.pf_get_last_step(self._h, C.byref(s)) != 0:
+            return
+        if s.overflow > self._overflow_seen:
+            msg = (f"{s.overflow - self._overflow_seen} new-cluster candidates were dropped because a particle already "
+                   f"had k_max = {self.k_max} components (the reference's component vector is unbounded): "
+                   "results differ from the reference from this step on; construct the filter with a larger k_max")
+            self._overflow_seen = s.overflow
+            if self.on_overflow == "raise":
+                raise PFError(_lib.PF_ERR_OVERFLOW, msg)
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
     def filter_(self, ys, progress=False, cb=None, uniforms=None):
         """filter!(ps, ys, progress; cb) (src/filters.jl:6-13).  Without a callback the whole
@@ -211,6 +240,7 @@ class ParticleFilter:
             _lib.check(self._L.pf_filter(self._h, pys, T, uniforms.ctypes.data_as(_dp), uniforms.shape[1],
                                          le.ctypes.data_as(_dp)), self._h)
         self.log_evidence = le
+        self._check_overflow()
         return self
 
     # --- read-out

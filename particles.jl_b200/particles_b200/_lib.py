@@ -33,7 +33,8 @@ class pf_step_stats(C.Structure):
                 ("overflow", C.c_int64), ("log_total_w", C.c_double), ("log_w_resamp", C.c_double),
                 ("threshold", C.c_double), ("cv", C.c_double), ("resampled", C.c_int32),
                 ("select_rounds", C.c_int32), ("n_candidates", C.c_int64),
-                ("select_phase_us", C.c_double * 4)]
+                ("select_phase_us", C.c_double * 4), ("n_plateau", C.c_int64), ("select_status", C.c_int32),
+                ("reserved1", C.c_int32)]
 
     def asdict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -41,15 +42,7 @@ class pf_step_stats(C.Structure):
         return d
 
 
-class pf_mg_ptrs(C.Structure):
-    _fields_ = [("scalars", C.c_void_p), ("acc", C.c_void_p), ("acc_bytes", C.c_int64), ("list", C.c_void_p),
-                ("list_capacity", C.c_int64), ("local_total", C.c_void_p), ("total_bytes", C.c_int64),
-                ("send_buffer", C.c_void_p), ("recv_buffer", C.c_void_p), ("buffer_capacity", C.c_int64),
-                ("rows_per_particle", C.c_int64), ("local_capacity", C.c_int64), ("sample_entries", C.c_int64),
-                ("cand_entries", C.c_int64), ("window", C.c_int64)]
-
-
-PF_MG_SAMPLE, PF_MG_BRACKET, PF_MG_CLASSIFY, PF_MG_SOLVE = 1, 2, 4, 8
+PF_MG_NARRAYS, PF_MG_IPC_BYTES = 9, 64
 
 # every symbol include/particles_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -71,23 +64,13 @@ SYMBOLS = [
     ("pf_select", C.c_int32, [C.c_int32, _dp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.POINTER(C.c_int64),
                               C.POINTER(C.c_uint8), C.POINTER(pf_step_stats)]),
     ("pf_set_stream", C.c_int32, [C.c_void_p, C.c_void_p]),
-    ("pf_mg_info", C.c_int32, [C.c_void_p, C.POINTER(pf_mg_ptrs)]),
-    ("pf_mg_begin", C.c_int32, [C.c_void_p, _dp, C.c_double]),
-    ("pf_mg_select", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
-    ("pf_mg_state", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
-    ("pf_mg_tiles", C.c_int32, [C.c_void_p]),
-    ("pf_mg_finish", C.c_int32, [C.c_void_p, C.c_void_p]),
-    ("pf_mg_plan", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
-                               C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    ("pf_mg_unpack", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_mg_local_arrays", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pf_mg_ipc_handles", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("pf_mg_set_peer", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
-    ("pf_mg_enable_direct", C.c_int32, [C.c_void_p]),
-    ("pf_mg_close", C.c_int32, [C.c_void_p]),
-    ("pf_mg_set_obs", C.c_int32, [C.c_void_p, _dp, C.c_double]),
-    ("pf_mg_drain", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
-    ("pf_mg_resume", C.c_int32, [C.c_void_p, C.c_int64]),
+    ("pf_mg_connect", C.c_int32, [C.POINTER(C.c_void_p), C.c_int32]),
+    ("pf_mg_filter", C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, _dp, C.c_int64, _dp, C.c_int64, _dp]),
+    ("pf_mg_n_global", C.c_int64, [C.c_void_p]),
+    ("pf_mg_create_local", C.c_int32, [C.POINTER(pf_config), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
     ("pf_debug_dump", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("pf_last_timing", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
     ("pf_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),

@@ -315,10 +315,10 @@ def test_failed_bracket_is_widened_not_opened(margin, monkeypatch):
     ys = _mixture_nd(rng, T, 2, 8)
     us = rng.random(T)
     prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
-    ref = pb.FearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), history=T)
+    ref = pb.FearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), history=T, k_max=16)
     ref.filter_(ys, uniforms=us)
     monkeypatch.setenv("PF_SEL_MARGIN", str(margin))
-    ps = pb.FearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), history=T)
+    ps = pb.FearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), history=T, k_max=16)
     rounds = []
     for t in range(T):
         ps.filter_(ys[t:t + 1], uniforms=us[t:t + 1])

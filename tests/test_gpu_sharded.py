@@ -1,11 +1,12 @@
 """Sharded run == unsharded run, bit for bit, with all ranks emulated inside one
-process on one GPU (LocalComm): same kernels, same stage boundaries, the collectives replaced
-by local concatenation."""
+process on one GPU (LocalGroup, lock step): the same kernels and the same peer-memory exchanges
+(sample / candidates / survivor totals / children that change owner) as the one-process-per-GPU run,
+with "publish" and "consume" queued as separate launches on one stream."""
 import numpy as np
 import pytest
 
 import particles_b200 as pb
-from particles_b200.distributed import LocalComm, ShardedFearnheadParticles, partition_plan
+from particles_b200.distributed import LocalGroup, ShardedFearnheadParticles, equal_blocks
 
 pytestmark = pytest.mark.gpu
 
@@ -15,98 +16,100 @@ def _mix2d(rng, T, k=8, radius=6.0):
     return radius * np.stack([np.cos(ang), np.sin(ang)], axis=1) + rng.standard_normal((T, 2))
 
 
-@pytest.mark.parametrize("G,N,T,direct", [(2, 1000, 40, True), (4, 1000, 40, True), (2, 1 << 16, 30, True), (8, 3000, 25, True),
-                                          (4, 1000, 40, False), (2, 1 << 16, 30, False)])
-def test_sharded_equals_unsharded(G, N, T, direct):
+def _same_population(sh, ref, what):
+    assert len(sh) == len(ref), f"population differs {what}"
+    assert np.array_equal(sh.ncomponents(), ref.ncomponents()), f"K differs {what}"
+    assert np.array_equal(sh.last_ancestors(), ref.last_ancestors()), f"ancestors differ {what}"
+    assert np.array_equal(sh.last_assignments(), ref.last_assignments()), f"assignments differ {what}"
+    assert np.array_equal(sh.logweights(), ref.logweights()), f"log-weights differ {what}"
+    a, b = sh.last_step(), ref.last_step()
+    for key in ("n_out", "log_total_w", "log_w_resamp", "threshold", "resampled", "n_resamp_req"):
+        assert a[key] == b[key] or (np.isnan(a[key]) and np.isnan(b[key])), (key, what)
+
+
+@pytest.mark.parametrize("G,N,T", [(2, 1000, 40), (4, 1000, 40), (2, 1 << 16, 30), (8, 3000, 25), (3, 5000, 30), (16, 700, 20)])
+def test_sharded_equals_unsharded_stepwise(G, N, T):
     rng = np.random.default_rng(5)
     ys = _mix2d(rng, T)
     us = rng.random(T)
     prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
     crp = pb.ChineseRestaurantProcess(1.0)
-    ref = pb.FearnheadParticles(N, prior, crp, history=T)
-    sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T, direct=direct)
+    ref = pb.FearnheadParticles(N, prior, crp, history=T, k_max=24)
+    sh = ShardedFearnheadParticles(N, prior, crp, LocalGroup(G), history=T, k_max=24)
     for t in range(T):
         ref.fit_(ys[t], [us[t]])
         sh.fit_(ys[t], us[t])
-        assert len(sh) == len(ref), f"population differs at step {t}"
-        assert np.array_equal(sh.ncomponents(), ref.ncomponents()), f"K differs at step {t}"
-        assert np.array_equal(sh.last_ancestors(), ref.last_ancestors()), f"ancestors differ at step {t}"
-        assert np.array_equal(sh.last_assignments(), ref.last_assignments()), f"assignments differ at step {t}"
-        assert np.array_equal(sh.logweights(), ref.logweights()), f"log-weights differ at step {t}"
-        a, b = sh.last_step(), ref.last_step()
-        for key in ("n_out", "log_total_w", "log_w_resamp", "threshold", "resampled"):
-            assert a[key] == b[key] or (np.isnan(a[key]) and np.isnan(b[key])), (key, t)
-    # shards stay balanced (children stay with their parents only while shares are within q/8 + 64)
-    sizes = [int(sh.L.pf_n_particles(s.h)) for s in sh.shards]
-    q = -(-len(sh) // G)
-    assert sum(sizes) == len(sh) and max(sizes) <= q + q // 2 + 64 + G
-    if direct:       # equal blocks after every step, nothing through the send / recv buffers
-        assert sizes == [min(max(len(sh) - r * q, 0), q) for r in range(G)] and sh.exchanges == 0
-    assert sh.exchanges < T
+        _same_population(sh, ref, f"at step {t}")
+        # equal blocks after every step
+        assert sh.local_sizes() == np.diff(equal_blocks(len(sh), G)).tolist()
 
 
-def test_device_plan_matches_host_plan():
-    rng = np.random.default_rng(6)
-    G, N, T = 4, 5000, 20
+@pytest.mark.parametrize("G,N,T,alpha", [(4, 1 << 17, 40, 1.0), (8, 1 << 18, 30, 3.0), (2, 1 << 18, 30, 0.3)])
+def test_sharded_equals_unsharded_one_call(G, N, T, alpha):
+    """The whole stream in ONE pf_mg_filter call (no host round trip between observations), at sizes where the
+    sample stride is > 1 and the candidate lists hold 10^4..10^5 values per rank."""
+    rng = np.random.default_rng(50 + G)
     ys = _mix2d(rng, T)
+    us = rng.random(T)
     prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
-    sh = ShardedFearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), LocalComm(G), history=T, direct=False)
-    import ctypes as C
-    for t in range(T):
-        sh.fit_(ys[t], rng.random())
-    # recompute the last plan on the host from the device-reported local counts
-    from particles_b200._lib import pf_mg_ptrs
-    info = pf_mg_ptrs()
-    sh.L.pf_mg_info(sh.shards[0].h, C.byref(info))
-    res = [s.plan(G) for s in sh.shards]
-    n_local = [r[2] for r in res]
-    for r in range(G):
-        send, recv, q, mine, mode = partition_plan(n_local, r, stay_cap=info.local_capacity, window=info.window)
-        assert res[r][0].tolist() == send.tolist() and res[r][1].tolist() == recv.tolist() and mode == res[r][5]
-        assert mine == int(sh.L.pf_n_particles(sh.shards[r].h))
+    crp = pb.ChineseRestaurantProcess(alpha)
+    ref = pb.FearnheadParticles(N, prior, crp, history=T, k_max=24)
+    ref.filter_(ys, uniforms=us)
+    sh = ShardedFearnheadParticles(N, prior, crp, LocalGroup(G), history=T, k_max=24)
+    sh.filter_(ys, us)
+    _same_population(sh, ref, "after the stream")
+    assert np.array_equal(sh.log_evidence, ref.log_evidence)
 
 
-@pytest.mark.parametrize("kw", [{"cand_entries": 64}, {"sample_entries": 64}, {"sample_entries": 64, "cand_entries": 64}])
-def test_slow_path_truncated_gather_and_rebracketing(kw):
-    """A candidate list that outgrows its fixed gather size (phase 7) and a sample too small to
-    bracket the threshold (verification failure, phase 3) both fall back to exact-size gathers
-    and still reproduce the unsharded run."""
-    rng = np.random.default_rng(11)
-    G, N, T = 4, 20000, 30
+def test_sharded_1d_nix2():
+    rng = np.random.default_rng(9)
+    T, N, G = 60, 20000, 4
+    ys = np.array([-6.0, -2.0, 2.0, 6.0])[rng.integers(0, 4, T)] + rng.standard_normal(T)
+    us = rng.random(T)
+    prior = pb.NormalInverseChisq(0.0, 1.0, 0.1, 1.0)
+    crp = pb.ChineseRestaurantProcess(1.0)
+    ref = pb.FearnheadParticles(N, prior, crp, history=T, k_max=24)
+    ref.filter_(ys, uniforms=us)
+    sh = ShardedFearnheadParticles(N, prior, crp, LocalGroup(G), history=T, k_max=24)
+    sh.filter_(ys.reshape(-1, 1), us)
+    _same_population(sh, ref, "after the stream")
+
+
+def test_failed_bracket_retries_on_the_device(monkeypatch):
+    """A sample bracket that misses the threshold (forced by shrinking its margin from 8 sigma to 1) is moved /
+    widened and the round is repeated by the queued retry launches, including the second exchange of the
+    candidates; decisions equal the default run, the total weight agrees to rounding (a different bracket splits
+    it differently)."""
+    rng = np.random.default_rng(77)
+    G, N, T = 4, 1 << 17, 30
     ys = _mix2d(rng, T)
     us = rng.random(T)
     prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
     crp = pb.ChineseRestaurantProcess(1.0)
-    ref = pb.FearnheadParticles(N, prior, crp, history=T)
+    ref = pb.FearnheadParticles(N, prior, crp, history=T, k_max=16)
     ref.filter_(ys, uniforms=us)
-    sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T, **kw)
-    sh.filter_(ys, us)
-    assert sh.slow_steps > 0
-    # every decision is identical; the total weight is (exact mass above the bracket) + (fixed-point
-    # mass below it), so with a deliberately different bracket the log-weights agree to rounding
+    monkeypatch.setenv("PF_SEL_MARGIN", "1")
+    sh = ShardedFearnheadParticles(N, prior, crp, LocalGroup(G), history=T, k_max=16)
+    rounds = []
+    for t in range(T):
+        sh.fit_(ys[t], us[t])
+        rounds.append(sh.last_step()["select_rounds"])
+    assert max(rounds) >= 2
     assert np.array_equal(sh.ncomponents(), ref.ncomponents())
     assert np.array_equal(sh.last_ancestors(), ref.last_ancestors())
     assert np.array_equal(sh.last_assignments(), ref.last_assignments())
     np.testing.assert_allclose(sh.logweights(), ref.logweights(), rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("lookahead,window", [(1, 0), (4, 0), (16, 0), (4, 50), (8, 400)])
-def test_lookahead_batches_equal_stepwise(lookahead, window, monkeypatch):
-    """Queuing several observations ahead of the host (device-side halt mark for the steps that
-    need it) gives the same population as stepping one at a time."""
-    monkeypatch.setenv("PF_MG_WINDOW", str(window))          # > 0: fixed-capacity neighbour exchange every step
-    rng = np.random.default_rng(21)
-    G, N, T = 4, 8000, 48
+def test_exchange_overflow_is_reported_not_silent(monkeypatch):
+    """A candidate list that outgrows its exchange segment halts the step on the device and comes back as
+    PF_ERR_OVERFLOW (never a truncated gather)."""
+    monkeypatch.setenv("PF_MG_CAPB", "64")
+    rng = np.random.default_rng(3)
+    G, N, T = 2, 1 << 15, 24
     ys = _mix2d(rng, T)
-    us = rng.random(T)
     prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
-    crp = pb.ChineseRestaurantProcess(1.0)
-    ref = pb.FearnheadParticles(N, prior, crp, history=T)
-    ref.filter_(ys, uniforms=us)
-    sh = ShardedFearnheadParticles(N, prior, crp, LocalComm(G), history=T)
-    sh.filter_(ys, us, lookahead=lookahead)
-    assert len(sh) == len(ref)
-    assert np.array_equal(sh.logweights(), ref.logweights())
-    assert np.array_equal(sh.ncomponents(), ref.ncomponents())
-    assert np.array_equal(sh.last_ancestors(), ref.last_ancestors())
-    assert sh.host_syncs < 2 * T if lookahead > 1 else True
+    sh = ShardedFearnheadParticles(N, prior, pb.ChineseRestaurantProcess(1.0), LocalGroup(G), k_max=16)
+    with pytest.raises(pb.PFError) as e:
+        sh.filter_(ys, rng.random(T))
+    assert e.value.code == 5 and "exchange segment" in str(e.value)

@@ -144,3 +144,33 @@ def test_fearnhead_population_growth_and_orders():
     assert sizes[:5] == [1, 2, 5, 15, 52]
     # the first resampling step sees identical inputs in both orders: same kept set size
     assert max(sizes) <= 100
+
+
+def test_select_exact_fast_equals_select_exact():
+    """The large-M evaluation of the exact specification (numpy sort + C-speed integer prefix sums +
+    binary search over distinct values) is the same function as the straightforward one."""
+    rng = np.random.default_rng(4242)
+    cases = []
+    for trial in range(60):
+        M = int(rng.integers(5, 1500))
+        N = int(rng.integers(1, M))
+        w = np.exp(rng.standard_normal(M) * rng.choice([0.5, 3.0, 12.0]))
+        if trial % 4 == 0:
+            w[rng.integers(0, M, M // 3)] = 0.0
+        if trial % 5 == 0:
+            w = np.round(w, 1)
+        if trial % 7 == 0:
+            w[rng.integers(0, M)] = 1e12
+        cases.append((w, N, rng.random()))
+    cases.append((np.ones(20), 10, 0.3))
+    cases.append((np.array([1.0] * 10 + [0.0] * 10), 10, 0.3))
+    cases.append((np.array([.05, .05, .1, .1, .2, .5]), 4, 0.5))
+    cases.append((np.array([1e-300, 1e-310, 5e-324, 1.0, 2.0, 3.0]), 4, 0.7))
+    cases.append((np.full(300, 3.0), 7, 0.9))
+    for w, N, u in cases:
+        for order in (orc.ORDER_INDEX, orc.ORDER_SORTED):
+            a = orc.select_exact(w, N, u, order)
+            b = orc.select_exact_fast(w, N, u, order)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[3] == b[3]
+            if a[2][1] > 0 and a[2][0] > 0:
+                assert orc.exact_c_value(a[2]) == orc.exact_c_value(b[2])
