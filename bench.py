@@ -153,71 +153,97 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def evidence_check(le, first_obs):
+    """Fingerprint of the log-evidence increments of the device-timed steps: identical on every arm
+    (N = 1 and N > 1 filter the same stream and must agree bit for bit)."""
+    import zlib
+    le = np.ascontiguousarray(le, dtype=np.float64)
+    return {"first_obs": int(first_obs), "n": int(len(le)), "sum": float(le.sum()), "crc32": int(zlib.crc32(le.tobytes()))}
+
+
 def sharded_arm(a, dist, rank, world, local, N, K, W, config):
-    """N > 1: particles block-sharded over the ranks (one process per GPU), collectives through
-    torch.distributed / NCCL between the library's stages (particles_b200/distributed.py)."""
+    """N > 1: particles block-sharded over the ranks, one process per GPU.  Every exchange of a step is done by
+    the library's kernels through peer memory over NVLink (CUDA IPC); torch.distributed (NCCL) only carries the
+    IPC handles at start-up and the barriers / max-over-ranks of the timing."""
     import torch
     import particles_b200 as pb
-    from particles_b200.distributed import ShardedFearnheadParticles, TorchComm
+    from particles_b200.distributed import ShardedFearnheadParticles, TorchGroup
     dev = torch.device("cuda", local)
     ys, us = stream()
-    assert a.burnin + W + 2 * K + 8 <= T_MAX
-    ps = ShardedFearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
-                                   pb.ChineseRestaurantProcess(1.0), TorchComm(), k_max=K_MAX, history=0, devices=[local])
+    T_all = a.burnin + W + 3 * K
+    assert T_all <= T_MAX
+    prior, crp = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0), pb.ChineseRestaurantProcess(1.0)
+    ps = ShardedFearnheadParticles(N, prior, crp, TorchGroup(), k_max=a.k_max, history=0, device=local, on_overflow="ignore")
+
+    def mean_k():
+        K_loc = ps._local(ps.L.pf_get_ncomponents, np.int32, __import__("ctypes").c_int32)[0]
+        t = torch.tensor([float(K_loc.sum()), float(len(K_loc)), float(K_loc.max(initial=0))], dtype=torch.float64, device=dev)
+        mx = t[2:3].clone()
+        dist.all_reduce(t[:2]); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        return float(t[0] / t[1]), int(mx.item())
+
+    les = []
     o = 0
-    ps.filter_(ys[o:o + a.burnin + W], us[o:o + a.burnin + W], lookahead=a.lookahead); o += a.burnin + W
-    kbar0 = float(ps.ncomponents().mean())
+    ps.filter_(ys[o:o + a.burnin + W], us[o:o + a.burnin + W]); o += a.burnin + W
+    les.append(ps.log_evidence.copy())
+    kbar0, _ = mean_k()
     n0 = len(ps)
-    launches0 = ps.shards[0].L.pf_last_timing  # noqa: F841  (kept for symmetry; launches read below)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ps.host_syncs = 0
-    ps.bytes_moved = 0
-    import ctypes as C
-    ms0, l0 = C.c_double(), C.c_int64()
-    ps.L.pf_last_timing(ps.shards[0].h, C.byref(ms0), C.byref(l0))
-    # (1) device-timed K steps: CUDA events on the stream every kernel and collective runs on
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # (1) device-timed K steps: CUDA events on the library's stream around ONE pf_mg_filter call, max over ranks
     dist.barrier(); torch.cuda.synchronize(dev)
-    ev0.record()
-    ps.filter_(ys[o:o + K], us[o:o + K], lookahead=a.lookahead); o += K
-    ev1.record()
+    ps.filter_(ys[o:o + K], us[o:o + K]); o += K
     torch.cuda.synchronize(dev); dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    les.append(ps.log_evidence.copy())
+    dev_ms_local, launches = ps.timing()
+    ms = torch.tensor([dev_ms_local], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dev_ms = float(ms.item())
-    ms1, l1 = C.c_double(), C.c_int64()
-    ps.L.pf_last_timing(ps.shards[0].h, C.byref(ms1), C.byref(l1))
-    syncs, moved = ps.host_syncs, ps.bytes_moved
     # (2) end to end: wall clock around the same public call with host observation buffers
     dist.barrier(); torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    ps.filter_(ys[o:o + K], us[o:o + K], lookahead=a.lookahead); o += K
-    le = ps.last_step()["log_total_w"]
+    ps.filter_(ys[o:o + K], us[o:o + K]); o += K
+    le_e2e = ps.log_evidence.copy()
     torch.cuda.synchronize(dev); dist.barrier()
     wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(wall, op=dist.ReduceOp.MAX)
     e2e_s = float(wall.item())
+    les.append(le_e2e)
     sampler.stop_flag = True
-    kbar = 0.5 * (kbar0 + float(ps.ncomponents().mean()))
-    # (3) stage timeline (device ms, host ms) over a few more steps
-    ps.profile = []
-    ps.filter_(ys[o:o + 8], us[o:o + 8], lookahead=a.lookahead); o += 8
-    stage_ms = ps.profile_summary()
-    ps.profile = None
-    # per-rank view (every rank contributes, rank 0 prints): stage timeline and the survivors this
-    # rank produced in the last step (the producer instantiates, so their spread is the tail's skew)
-    try:
-        mine = {"rank": rank, "n_local_last": int(ps.shards[0].plan(world)[2]),
-                "stage_ms": {k: round(v[0], 4) for k, v in stage_ms.items()}}
-    except Exception as e:                                   # diagnostics must never cost the line
-        mine = {"rank": rank, "error": str(e)[:200]}
+    kbar1, kmax_seen = mean_k()
+    kbar = 0.5 * (kbar0 + kbar1)
+    # (3) per-kernel-class device times over K more steps (the bracket / solve / offset kernels include the wait for
+    # the peers' data: "select" and "scan" are where the replicated search and the exchanges show up)
+    ps.set_profiling(True)
+    ps.filter_(ys[o:o + K], us[o:o + K]); o += K
+    les.append(ps.log_evidence.copy())
+    prof_ms, _ = ps.timing()
+    kt = ps.kernel_times()
+    ps.set_profiling(False)
+    stats = ps.last_step()
+    ov = torch.tensor([float(stats["overflow"])], dtype=torch.float64, device=dev)
+    dist.all_reduce(ov)
+    overflow = int(ov.item())
     by_rank = [None] * world
     try:
-        dist.all_gather_object(by_rank, mine)
-    except Exception as e:
+        dist.all_gather_object(by_rank, {"rank": rank, "dev_ms_timed": round(dev_ms_local, 4), "n_local": ps.local_sizes()[0],
+                                         "class_ms_per_step": {k: round(v[0] / K, 4) for k, v in kt.items() if v[1]}})
+    except Exception as e:                                   # diagnostics must never cost the line
         by_rank = [{"error": str(e)[:200]}]
+    # (4) correctness of the timed run: rank 0 filters the same observations unsharded; the log-evidence
+    # increments of EVERY observation must be bit-identical
+    verify = None
+    if not a.no_verify:
+        if rank == 0:
+            ref = pb.FearnheadParticles(N, prior, crp, k_max=a.k_max, history=0, device=local, on_overflow="ignore")
+            ref.filter_(ys[:o], uniforms=us[:o])
+            le_all = np.concatenate(les)
+            same = bool(np.array_equal(le_all, ref.log_evidence))
+            verify = {"unsharded_run_on_rank0": True, "observations": int(o), "log_evidence_bitwise_equal": same,
+                      "max_abs_diff": float(np.max(np.abs(le_all - ref.log_evidence)))}
+            ref.close()
+        dist.barrier()
     if rank != 0:
         return 0
     sampler.join(timeout=2)
@@ -226,19 +252,27 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     bpu = bytes_per_update(kbar)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0,
-                                                host_syncs_per_step=syncs / K, collective_bytes_per_step=moved / K,
-                                                slow_path_steps=ps.slow_steps, exchanges=ps.exchanges, lookahead=a.lookahead, halts=ps.halts[-12:],
-                                                stage_ms_device_host={k: [round(v[0], 4), round(v[1], 4)] for k, v in stage_ms.items()},
-                                                by_rank=by_rank),
-            "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
-                    "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le)},
-            "gpu_launches": int(l1.value - l0.value) * world,
+            "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n0, kmax_overflow=overflow,
+                                                max_clusters_in_a_particle=kmax_seen, host_syncs_per_step=0,
+                                                exchange="peer stores + sequence flags inside the kernels (CUDA IPC over NVLink); "
+                                                         "no collective call on the data path",
+                                                select_rounds_last=stats["select_rounds"], by_rank=by_rank, verify=verify,
+                                                evidence_check=evidence_check(les[1], a.burnin + W)),
+            "e2e": {"value": n0 * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": (8 * D + 8) * world, "d2h_bytes_per_step": 136 * world,
+                    "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le_e2e[-1])},
+            "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "kernel": "whole step (per GPU)", "achieved": bpu * value / 1e9 / world, "peak": peak,
                          "unit": "GB/s", "frac": bpu * value / 1e9 / world / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_update": bpu},
+                         "algorithmic_bytes_per_update": bpu,
+                         "class_ms_per_step": {k: round(v[0] / K, 4) for k, v in kt.items() if v[1]}},
             "clocks": sampler.summary()}
     print(json.dumps(line))
+    if overflow and not a.allow_overflow:
+        print(f"k_max = {a.k_max} dropped {overflow} new-cluster candidates; raise --k-max", file=sys.stderr)
+        return 1
+    if verify is not None and not verify["log_evidence_bitwise_equal"]:
+        print("the sharded run does not reproduce the unsharded run", file=sys.stderr)
+        return 1
     return 0
 
 
@@ -256,7 +290,7 @@ def main():
     ap.add_argument("--order", default="index", choices=["index", "sorted"])
     ap.add_argument("--k-max", type=int, default=K_MAX, help="cluster slots per particle (the line fails if a candidate was dropped)")
     ap.add_argument("--allow-overflow", action="store_true")
-    ap.add_argument("--lookahead", type=int, default=10, help="sharded run: observations queued per host synchronisation")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the unsharded re-run on rank 0 (outside the timed region)")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -315,6 +349,7 @@ def main():
     sampler.start()
     # (1) device-timed K steps
     ps.filter_(ys[o:o + K], uniforms=us[o:o + K]); o += K
+    le_timed = ps.log_evidence.copy()
     dev_ms, launches = ps.timing()
     # (2) end to end through the public API with host buffers
     t0 = time.perf_counter()
@@ -363,6 +398,7 @@ def main():
             "data": "synthetic", "config": dict(config, mean_clusters_per_particle=kbar, population=n_live0,
                                                 select_rounds_last=stats["select_rounds"], candidates_last=stats["n_candidates"],
                                                 select_phase_us_last=stats["select_phase_us"], kmax_overflow=int(stats["overflow"]),
+                                                evidence_check=evidence_check(le_timed, a.burnin + W),
                                                 max_clusters_in_a_particle=int(ps.ncomponents().max())),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * D + 8, "d2h_bytes_per_step": 136,
                     "ms_per_step": 1e3 * e2e_s / K, "log_evidence_last": float(le[-1])},

@@ -280,36 +280,11 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
     }
 }
 
-// fused path: add each tile's candidates (now that the threshold is known) to its record
-__global__ void __launch_bounds__(256) k_tile_fixup(TileSum *__restrict__ tiles, const TileFuse *__restrict__ tfuse,
-                                                    const double *__restrict__ list, const SelResult *__restrict__ res,
-                                                    const SelScratch *__restrict__ sc, const long long *__restrict__ n_items_ptr,
-                                                    const StepConst *__restrict__ scp)
-{
-    if (sc->halt || sc->phase != 4 || !sc->tiles_ok) return;
-    const long long ntiles = (*n_items_ptr + SCAN_THREADS - 1) / SCAN_THREADS;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    const bool comb = res->n > 0 && !isz128(res->T);
-    const u64 thr = res->thr_bits;
-    const int scale = res->scale;
-    u128 X = tiles[t].X;
-    unsigned int kept = tiles[t].kept;
-    const unsigned int off = tfuse[t].cand_off, n = tfuse[t].cand_cnt;
-    for (unsigned int k = 0; k < n; k++) {
-        const u64 b = (u64)__double_as_longlong(list[(long long)off + k]);
-        if (b >= thr) kept++;
-        else if (comb) X = add128(X, fx70(b, scale));
-    }
-    const unsigned int np = tfuse[t].n_plateau;
-    if (np) {
-        if (scp->plateau_bits >= thr) kept += np;
-        else if (comb) X = add128(X, mul128_64(fx70(scp->plateau_bits, scale), (u64)np));
-    }
-    if (!comb) X = mk128(0, 0);
-    tiles[t].X = X; tiles[t].kept = kept;
-}
-
+// Survivor scan, level 1: one block owns a "supertile" of SUPER_TILES consecutive tile records.  On the fused
+// path each record first receives its tile's in-bracket candidates (their side is known now that the
+// threshold is); then the block turns its records into exclusive prefixes WITHIN the supertile and
+// leaves the supertile's total in supers[] (level 2, k_tile_prefix on supers[], scans those).
+#define SUPER_TILES 256
 // ------------------------------------------------------------------ survivor scan
 // The systematic comb (sample_stratified!, src/fearnhead.jl:97-114) over the putatives in
 // (particle, slot) order, in exact integer arithmetic.  With X = n * (running fixed-point
@@ -406,6 +381,62 @@ __device__ __forceinline__ void thread_sums(const double *__restrict__ V, long l
     }
 }
 
+__global__ void __launch_bounds__(SUPER_TILES) k_tile_scan1(TileSum *__restrict__ tiles, const TileFuse *__restrict__ tfuse,
+                                                           const double *__restrict__ list, const SelResult *__restrict__ res,
+                                                           const SelScratch *__restrict__ sc, const long long *__restrict__ n_items_ptr,
+                                                           const StepConst *__restrict__ scp, TileSum *__restrict__ supers, int mode,
+                                                           const SelScratch *guard)
+{
+    if (guard && (guard->phase != 4 || guard->halt)) return;
+    if (scan_mode_skips(mode, res)) return;
+    __shared__ u128 s_warp[33];
+    __shared__ unsigned int s_wc[33];
+    const long long ntiles = (*n_items_ptr + SCAN_THREADS - 1) / SCAN_THREADS;
+    if ((long long)blockIdx.x * SUPER_TILES >= ntiles) return;
+    const long long t = (long long)blockIdx.x * SUPER_TILES + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool comb = res->n > 0 && !isz128(res->T);
+    u128 X = mk128(0, 0);
+    unsigned int kept = 0;
+    if (t < ntiles) {
+        X = tiles[t].X; kept = tiles[t].kept;
+        if (tfuse && sc && sc->tiles_ok) {
+            // the fused expansion's record holds the tile's putatives outside the bracket: add its candidates
+            const u64 thr = res->thr_bits;
+            const int scale = res->scale;
+            const unsigned int off = tfuse[t].cand_off, n = tfuse[t].cand_cnt;
+            for (unsigned int k = 0; k < n; k++) {
+                const u64 b = (u64)__double_as_longlong(list[(long long)off + k]);
+                if (b >= thr) kept++;
+                else if (comb) X = add128(X, fx70(b, scale));
+            }
+            const unsigned int np = tfuse[t].n_plateau;
+            if (np) {
+                if (scp->plateau_bits >= thr) kept += np;
+                else if (comb) X = add128(X, mul128_64(fx70(scp->plateau_bits, scale), (u64)np));
+            }
+            if (!comb) X = mk128(0, 0);
+        }
+    }
+    u128 totX;
+    const u128 exX = block_excl_scan128(X, s_warp, &totX);
+    unsigned int incK = kept;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, incK, d); if (lane >= d) incK += o; }
+    if (lane == 31) s_wc[wid] = incK;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = lane < (SUPER_TILES / 32) ? s_wc[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
+        s_wc[lane] = wi - w;
+        if (lane == 31) s_wc[32] = wi;
+    }
+    __syncthreads();
+    if (t < ntiles) { tiles[t].X = exX; tiles[t].kept = s_wc[wid] + incK - kept; }
+    if (threadIdx.x == 0) { supers[blockIdx.x].X = totX; supers[blockIdx.x].kept = s_wc[32]; }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
                                                             long long cap, const SelResult *__restrict__ res,
                                                             const long long *__restrict__ n_items_ptr, TileSum *__restrict__ tiles,
@@ -418,21 +449,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
     __shared__ unsigned int s_k[SCAN_THREADS / 32];
     const long long n_items = *n_items_ptr;
     const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
-    if (blockIdx.x >= ntiles) return;
-    const long long i = (long long)blockIdx.x * SCAN_THREADS + threadIdx.x;
     const u64 n = (u64)res->n;
     const bool comb = n > 0 && !isz128(res->T);
-    const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
-    u128 X; unsigned int kept;
-    thread_sums(V, cap, i, c, res->thr_bits, res->scale, comb, X, kept);
-    X = warp_sum128(X);
-    kept = (unsigned int)warp_sum64(kept);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) { s_x[wid] = X; s_k[wid] = kept; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < SCAN_THREADS / 32; w++) { X = add128(X, s_x[w]); kept += s_k[w]; }
-        tiles[blockIdx.x].X = X; tiles[blockIdx.x].kept = kept;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {         // (a small grid: the kernel is a no-op on the fused path)
+        const long long i = tile * SCAN_THREADS + threadIdx.x;
+        const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
+        u128 X; unsigned int kept;
+        thread_sums(V, cap, i, c, res->thr_bits, res->scale, comb, X, kept);
+        X = warp_sum128(X);
+        kept = (unsigned int)warp_sum64(kept);
+        if (lane == 0) { s_x[wid] = X; s_k[wid] = kept; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SCAN_THREADS / 32; w++) { X = add128(X, s_x[w]); kept += s_k[w]; }
+            tiles[tile].X = X; tiles[tile].kept = kept;
+        }
+        __syncthreads();
     }
 }
 
@@ -442,14 +475,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
 __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelResult *__restrict__ res,
                                                       const long long *__restrict__ n_items_ptr, StepState *st, int mode,
                                                       const Xch *xch /* sharded run: the total goes to every rank (exchange kind C) */,
-                                                      unsigned long long seq, const SelScratch *guard)
+                                                      unsigned long long seq, const SelScratch *guard, int super_level)
 {
     if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_wx[32];
     __shared__ unsigned int s_wk[32];
     const long long n_items = *n_items_ptr;
-    const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
+    long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
+    if (super_level) ntiles = (ntiles + SUPER_TILES - 1) / SUPER_TILES;           // `tiles` holds supertile totals
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long per = ((ntiles + 31) / 32 + 31) / 32 * 32;          // tiles per warp, multiple of 32
     const long long b = (long long)wid * per, e = b + per < ntiles ? b + per : ntiles;
@@ -503,7 +537,8 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelR
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
                                                              long long cap, const SelResult *__restrict__ res,
                                                              const long long *__restrict__ n_items_ptr,
-                                                             const TileSum *__restrict__ tiles, unsigned int *__restrict__ surv_parent,
+                                                             const TileSum *__restrict__ tiles, const TileSum *__restrict__ supers,
+                                                             unsigned int *__restrict__ surv_parent,
                                                              unsigned char *__restrict__ surv_slot, int mode,
                                                              const RankOff *__restrict__ ro, const SelScratch *guard,
                                                              long long surv_cap, ScanRec rec = ScanRec{nullptr, nullptr},
@@ -530,8 +565,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
     __shared__ long long s_k0;
     __shared__ double s_inv;
     if (tid == 0) {
-        u128 S0 = tiles[blockIdx.x].X;
-        long long k0 = (long long)tiles[blockIdx.x].kept;
+        u128 S0 = add128(tiles[blockIdx.x].X, supers[blockIdx.x / SUPER_TILES].X);      // prefix within the supertile + prefix of the supertiles
+        long long k0 = (long long)tiles[blockIdx.x].kept + (long long)supers[blockIdx.x / SUPER_TILES].kept;
         if (ro) { S0 = add128(S0, ro->S_off); k0 += ro->kept_off - ro->g_first; }   // positions relative to this rank's first survivor
         s_S0 = S0; s_k0 = k0;
         if (comb) {

@@ -34,6 +34,7 @@ struct pf_filter_s {
     unsigned int *surv_parent = nullptr;
     unsigned char *surv_slot = nullptr;
     TileSum *tiles = nullptr;
+    TileSum *supers = nullptr;            // totals of SUPER_TILES consecutive tile records (level 2 of the survivor scan)
     TileFuse *tfuse = nullptr;
     ScanRec srec = ScanRec{nullptr, nullptr};   // per-particle scan records of the fused expansion (PF_SCAN_REC)
     long long fuse_stride = 1;
@@ -214,7 +215,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
-                    h->surv_slot, h->tiles, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
+                    h->surv_slot, h->tiles, h->supers, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
                     h->peers[0], h->peers[1], h->srec.x, h->srec.m};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -311,6 +312,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         CT(dmalloc(&h->pick_pos, (size_t)cap));
     }
     CT(dmalloc(&h->tiles, ntiles));
+    CT(dmalloc(&h->supers, ntiles / SUPER_TILES + 2));
     CT(dmalloc(&h->tfuse, ntiles));
     // optional per-particle scan records (a record has 24 slot bits)
     if (getenv("PF_SCAN_REC") && atoi(getenv("PF_SCAN_REC")) && h->nranks <= 1 && h->k_max + 1 <= 24) {
@@ -337,13 +339,13 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         int32_t rc = setup_cluster_kernels(h);
         if (rc != PF_OK) { g_create_error = h->err; pf_destroy(h); return rc; }
     }
-    h->cand_cap = (long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK;
+    h->cand_cap = ((long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK + 2) & ~1ll;
     if (h->nranks > 1) {
         // exchange region: sample segments (a shard's sample is at most its sampled particles x slots) and
         // candidate segments (two round buffers; a widened bracket may hold a few per cent of the shard's putatives)
-        h->capA = ((cap + h->fuse_stride - 1) / h->fuse_stride + 8) * (h->k_max + 1) + 1024;
-        h->capB = std::max<long long>(1 << 20, 2 * cap);
-        if (getenv("PF_MG_CAPB")) h->capB = std::max<long long>(64, atoll(getenv("PF_MG_CAPB")));      // tests: force the overflow path
+        h->capA = (((cap + h->fuse_stride - 1) / h->fuse_stride + 8) * (h->k_max + 1) + 1024 + 1) & ~1ll;       // even: segments stay 16-byte aligned
+        h->capB = std::max<long long>(1 << 20, 2 * cap) & ~1ll;
+        if (getenv("PF_MG_CAPB")) h->capB = std::max<long long>(64, atoll(getenv("PF_MG_CAPB"))) & ~1ll;      // tests: force the overflow path
         h->xreg_bytes = xch_region_bytes(h->nranks, h->capA, h->capB);
         CT(cudaMalloc((void **)&h->xreg, h->xreg_bytes));
         CT(cudaMemsetAsync(h->xreg, 0, xch_header_bytes(), h->stream));
@@ -409,7 +411,7 @@ static cudaError_t launch_cluster(void (*kern)(SelArgs), int csize, cudaStream_t
 {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(csize); cfg.blockDim = dim3(SEL_THREADS); cfg.dynamicSmemBytes = SEL_SMEM_BYTES; cfg.stream = stream;
+    cfg.gridDim = dim3(csize); cfg.blockDim = dim3(SELC_THREADS); cfg.dynamicSmemBytes = SELC_SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -424,11 +426,12 @@ static int32_t setup_cluster_kernels(pf_handle h)
     int best = SEL_MAX_CLUSTER;
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CUDA_TRY(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, SELC_SMEM_BYTES));
         int ok_size = 8;
         for (int cs = SEL_MAX_CLUSTER; cs >= 8; cs >>= 1) {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
-            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(SEL_THREADS); cfg.dynamicSmemBytes = SEL_SMEM_BYTES;
+            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(SELC_THREADS); cfg.dynamicSmemBytes = SELC_SMEM_BYTES;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -556,25 +559,28 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
                 return set_error(h, PF_ERR_CUDA, "radix sort launch failed");
         }
         // resampling step: comb over the sorted list; exhaustive step: index order
-        LaunchTimer lt(h, KC_SCAN, 7);
+        LaunchTimer lt(h, KC_SCAN, 9);
         const int gflat = grid_for(n_pad, SCAN_THREADS), gidx = grid_for(ub, SCAN_THREADS);
-        k_tile_sums<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, h->sc, nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->M, h->st, 1, nullptr, 0, h->sc);
-        k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles,
+        k_tile_sums<<<std::min(gflat, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, h->sc, nullptr);
+        k_tile_scan1<<<grid_for(gflat, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, nullptr, nullptr, h->res, nullptr, &h->st->M, h->stc, h->supers, 1, h->sc);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->M, h->st, 1, nullptr, 0, h->sc, 1);
+        k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, h->supers,
                                                              h->pick_pos, h->surv_slot, 1, nullptr, h->sc, cap);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
                                                                            h->surv_slot, h->sc);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, h->sc, nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 2, nullptr, 0, h->sc);
-        k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
+        k_tile_sums<<<std::min(gidx, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, h->sc, nullptr);
+        k_tile_scan1<<<grid_for(gidx, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, nullptr, nullptr, h->res, nullptr, &h->st->n_live, h->stc, h->supers, 2, h->sc);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 2, nullptr, 0, h->sc, 1);
+        k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
                                                             h->surv_slot, 2, nullptr, h->sc, cap);
     } else {
         LaunchTimer lt(h, KC_SCAN, 4);
         const int gidx = grid_for(ub, SCAN_THREADS);
-        if (fused) k_tile_fixup<<<grid_for(gidx, 256), 256, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc);
-        k_tile_sums<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, fused ? h->sc : nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, nullptr, 0, h->sc);
-        k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->surv_parent,
+        k_tile_sums<<<std::min(gidx, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, fused ? h->sc : nullptr);
+        k_tile_scan1<<<grid_for(gidx, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, fused ? h->tfuse : nullptr, h->cand, h->res, h->sc, &h->st->n_live, h->stc,
+                                                                                     h->supers, 0, h->sc);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, nullptr, 0, h->sc, 1);
+        k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
                                                             h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr}, h->sc);
     }
     {
@@ -977,6 +983,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
     double *dW = nullptr, *dU = nullptr, *cand = nullptr;
     StepState *st = nullptr; SelScratch *sc = nullptr; SelResult *res = nullptr;
     TileSum *tiles = nullptr;
+    TileSum *supers = nullptr;            // totals of SUPER_TILES consecutive tile records (level 2 of the survivor scan)
     unsigned int *sp = nullptr; unsigned char *ss = nullptr;
     u64 *keys = nullptr, *keys2 = nullptr; unsigned int *vals = nullptr, *vals2 = nullptr;
     unsigned int *hist = nullptr;
@@ -1002,6 +1009,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         ST(dmalloc(&dW, (size_t)M)); ST(dmalloc(&dU, 1)); ST(dmalloc(&cand, (size_t)cand_cap));
         ST(dmalloc(&st, 1)); ST(dmalloc(&sc, 1)); ST(dmalloc(&res, 1));
         ST(dmalloc(&tiles, (size_t)ntiles));
+        ST(dmalloc(&supers, (size_t)ntiles / SUPER_TILES + 2));
         ST(dmalloc(&sp, (size_t)M)); ST(dmalloc(&ss, (size_t)M));
         ST(cudaMemsetAsync(sc, 0, sizeof(SelScratch), h->stream));
         ST(cudaMemsetAsync(res, 0, sizeof(SelResult), h->stream));
@@ -1026,9 +1034,10 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         h->retries = 12;                  // stand-alone call: queue enough rounds for any input
         rc = launch_classic_search(h, sel_args(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res));
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
-        k_tile_sums<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, sc, nullptr);
-        k_tile_prefix<<<1, 1024, 0, h->stream>>>(tiles, res, &st->n_live, st, 0, nullptr, 0, sc);
-        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, sp, ss, 0, nullptr, sc, M);
+        k_tile_sums<<<std::min(grid_for(M, SCAN_THREADS), h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, sc, nullptr);
+        k_tile_scan1<<<grid_for(ntiles, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(tiles, nullptr, nullptr, res, nullptr, &st->n_live, nullptr, supers, 0, sc);
+        k_tile_prefix<<<1, 1024, 0, h->stream>>>(supers, res, &st->n_live, st, 0, nullptr, 0, sc, 1);
+        k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, supers, sp, ss, 0, nullptr, sc, M);
         ST(cudaGetLastError());
         StepState s1; SelResult r1;
         int phase_end = 0;
@@ -1080,7 +1089,7 @@ done:
 #undef ST
     if (h->stream) { cudaStreamSynchronize(h->stream); }
     {
-        void *ptrs[] = {dW, dU, cand, st, sc, res, tiles, sp, ss, keys, keys2, vals, vals2, hist};
+        void *ptrs[] = {dW, dU, cand, st, sc, res, tiles, supers, sp, ss, keys, keys2, vals, vals2, hist};
         for (void *p : ptrs) if (p) cudaFree(p);
     }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1213,16 +1222,19 @@ static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev,
     const int cur = h->cur;
     const unsigned long long seq = (unsigned long long)h->steps + 1;
     if (cluster_stage & SEL_ST_PUB) {
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc, h->res, h->xch, seq, h->steps);
+        {
+            LaunchTimer lt(h, KC_PRESTEP);            // (includes the wait for every rank's previous generation)
+            k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc, h->res, h->xch, seq, h->steps);
+        }
+        LaunchTimer lt(h, KC_SELECT);
         const long long ns = 4 * ((cap + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride) + 1);      // groups of 4 particles (+1: the shard's phase)
         k_expand<D, 1><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                    h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr, nullptr);
-        h->launches += 2;
     }
     SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
     a.external_sample = 1; a.x = h->xch; a.stage = cluster_stage;
+    LaunchTimer lt(h, KC_SELECT);
     CUDA_TRY(launch_cluster(k_sel_bracket, h->cluster_size, h->stream, a));
-    h->launches++;
     return PF_OK;
 }
 
@@ -1236,16 +1248,16 @@ static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int clust
     a.external_sample = 1; a.preclassified = 1; a.x = h->xch; a.retry = retry;
     if (cluster_stage & SEL_ST_PUB) {
         if (!retry) {
+            LaunchTimer lt(h, KC_EXPAND);
             k_expand<D, 2><<<grid_for(cap, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                         h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
-            h->launches++;
         }
+        LaunchTimer lt(h, KC_SELECT);
         k_sel_classify<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
-        h->launches++;
     }
     a.stage = cluster_stage;
+    LaunchTimer lt(h, KC_SELECT);
     CUDA_TRY(launch_cluster(k_sel_solve, h->cluster_size, h->stream, a));
-    h->launches++;
     return PF_OK;
 }
 
@@ -1254,10 +1266,10 @@ static int32_t mg_stage_c(pf_handle h)
 {
     const int g = grid_for(h->cap, SCAN_THREADS);
     const unsigned long long seq = (unsigned long long)h->steps + 1;
-    k_tile_fixup<<<grid_for(g, 256), 256, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc);
-    k_tile_sums<<<g, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, h->sc);
-    k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->tiles, h->res, &h->st->n_live, h->st, 0, h->xch, seq, h->sc);
-    h->launches += 3;
+    LaunchTimer lt(h, KC_SCAN, 3);
+    k_tile_sums<<<std::min(g, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, h->sc);
+    k_tile_scan1<<<grid_for(g, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc, h->supers, 0, h->sc);
+    k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, h->xch, seq, h->sc, 1);
     return PF_OK;
 }
 
@@ -1270,15 +1282,23 @@ static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
     const unsigned long long seq = (unsigned long long)h->steps + 1;
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    k_rank_offsets<<<1, 32, 0, h->stream>>>(h->xch, seq, h->steps, h->res, h->st, h->ro, h->sc, h->surv_cap);
-    k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles,
-                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
-    k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
-                                                                          h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, h->ro, h->k_max, h->sc, &h->st->M_next, h->peers[nxt],
-                                                                          (long long)h->steps * h->cap);
-    k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->sc, h->steps, h->dbg_status, h->ro, h->xch, seq);
-    h->launches += 4;
+    {
+        LaunchTimer lt(h, KC_SCAN, 2);            // (k_rank_offsets includes the wait for every rank's total)
+        k_rank_offsets<<<1, 32, 0, h->stream>>>(h->xch, seq, h->steps, h->res, h->st, h->ro, h->sc, h->surv_cap);
+        k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, h->supers,
+                                                                                      h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
+    }
+    {
+        LaunchTimer lt(h, KC_INSTANTIATE);
+        k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
+                                                                              h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
+                                                                              h->surv_slot, ga, gs, h->ro, h->k_max, h->sc, &h->st->M_next, h->peers[nxt],
+                                                                              (long long)h->steps * h->cap);
+    }
+    {
+        LaunchTimer lt(h, KC_STEPLOG);
+        k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->sc, h->steps, h->dbg_status, h->ro, h->xch, seq);
+    }
     CUDA_TRY(cudaGetLastError());
     h->cur = nxt;
     h->steps++;
@@ -1365,6 +1385,7 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
         h->last_ms = ms; h->last_launches = h->launches;
+        collect_profile(h);
         if (halt[0]) {
             char buf[200];
             const int reason = (int)(halt[1] & 0xffffffffll);
@@ -1426,5 +1447,14 @@ extern "C" int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */)
                      (int64_t)r.Tq.lo, (int64_t)r.Tq.hi, r.Tr, r.A, r.n, r.rounds, st.n_live, st.M, st.n_next,
                      r.status, hdr[2] /* scale | phase */, hdr[5] /* halt */, ro.n_local, ro.g_first, ro.kept_off, (int64_t)ro.S_off.lo, ro.n_global};
     for (int k = 0; k < 24; k++) out[k] = v[k];
+    if (getenv("PF_DEBUG_STAMPS")) {
+        unsigned long long t[32];
+        CUDA_TRY(cudaMemcpy(t, scp->dbg_t, sizeof t, cudaMemcpyDeviceToHost));
+        for (int g = 0; g < 2; g++) {
+            fprintf(stderr, "%s stamps (us):", g ? "solve" : "bracket");
+            for (int k = 1; k < 16 && t[16 * g + k] >= t[16 * g + k - 1] && t[16 * g + k]; k++) fprintf(stderr, " %.1f", (t[16 * g + k] - t[16 * g + k - 1]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+    }
     return PF_OK;
 }

@@ -47,7 +47,15 @@ namespace cg = cooperative_groups;
 #endif
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax
-#define SEL_SMEM_BYTES (SEL_BINS * 4 + 3 * SEL_BINS * 8)
+// cluster kernels (k_sel_bracket, k_sel_solve): 8 warps per CTA, each with a PRIVATE 1024-bin histogram in shared
+// memory (no atomics), the list streamed through a shared-memory ring by 1-D bulk copies (TMA)
+#define SELC_THREADS 256
+#define SELC_WARPS (SELC_THREADS / 32)
+#define SEL_CH 2048                 // doubles per bulk copy (16 KB)
+#define SEL_STAGES 3                // ring depth
+#define SELC_HIST_BYTES (SELC_WARPS * SEL_BINS * 20)
+#define SELC_RING_BYTES (SEL_STAGES * SEL_CH * 8)
+#define SELC_SMEM_BYTES (SELC_HIST_BYTES + SELC_RING_BYTES + 64)
 #define SEL_MAX_CLUSTER 16
 #define SEL_RETRIES 2               // queued extra rounds per step (no-ops unless the previous round asked for one)
 #define PF_MAX_RANKS 16
@@ -123,7 +131,8 @@ struct SelScratch {
     double final_vals[SEL_FINAL_CAP];
     // histogram of one descent level (cluster-reduced)
     unsigned int h_cnt[SEL_BINS];
-    u64 h_sum[3][SEL_BINS];
+    u64 h_sum[2][SEL_BINS];         // bin sum = h_sum[0] + h_sum[1] 2^32
+    unsigned long long dbg_t[32];   // globaltimer stamps of the last bracket (0..15) and solve (16..31) launch (debugging aid)
 };
 enum { PF_HALT_SEARCH = 1,          // the threshold search needed more rounds than were queued
        PF_HALT_TIMEOUT = 2,         // a peer's flag did not arrive (sharded run)
@@ -254,15 +263,114 @@ struct SelArgs {
 
 // the list a cluster kernel works on: one segment (single GPU) or one per rank (own exchange region)
 struct ListView {
-    const double *seg[PF_MAX_RANKS];
+    const double *seg[PF_MAX_RANKS];    // 16-byte aligned
     long long off[PF_MAX_RANKS + 1];    // exclusive prefix of the segment lengths
+    long long choff[PF_MAX_RANKS + 1];  // exclusive prefix of the segments' chunk counts (SEL_CH doubles per chunk)
     int nseg;
 };
+__device__ __forceinline__ void lv_finish(ListView &lv)
+{
+    lv.choff[0] = 0;
+    for (int r = 0; r < lv.nseg; r++) lv.choff[r + 1] = lv.choff[r] + (lv.off[r + 1] - lv.off[r] + SEL_CH - 1) / SEL_CH;
+}
 __device__ __forceinline__ u64 lv_load(const ListView &lv, long long t)
 {
     int s = 0;
     while (s + 1 < lv.nseg && t >= lv.off[s + 1]) s++;
     return (u64)__double_as_longlong(__ldcg(lv.seg[s] + (t - lv.off[s])));      // L2: peers may have written this memory
+}
+
+// Every thread of the cluster visits its share of the list, U independent loads in flight per thread (the
+// cluster kernels run on 16 SMs: without the batching every item would cost a full memory latency).
+// Padding entries (all-ones pattern) are skipped.
+#define SEL_BATCH 8
+template <class F>
+__device__ __forceinline__ void lv_for_each(const ListView &lv, long long start, long long step, F f)
+{
+    const long long n = lv.off[lv.nseg];
+    for (long long t0 = start; t0 < n; t0 += step * SEL_BATCH) {
+        u64 b[SEL_BATCH];
+#pragma unroll
+        for (int k = 0; k < SEL_BATCH; k++) { const long long t = t0 + k * step; b[k] = t < n ? lv_load(lv, t) : ~0ull; }
+#pragma unroll
+        for (int k = 0; k < SEL_BATCH; k++) if (b[k] != ~0ull) f(b[k]);
+    }
+}
+
+// ---- streaming a list through shared memory: 1-D bulk copies (cp.async.bulk, the TMA unit) complete on an
+// mbarrier per ring stage; thread 0 keeps SEL_STAGES copies in flight, all threads consume.  16 SMs pull a
+// few MB this way at close to their share of the L2 bandwidth; per-thread loads would leave them latency-bound.
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity)
+{
+    unsigned int ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+// once per kernel, before the first pass
+__device__ __forceinline__ void stream_init(unsigned char *smem_raw)
+{
+    if (threadIdx.x == 0) {
+        const unsigned int bar0 = smem_u32(smem_raw + SELC_HIST_BYTES + SELC_RING_BYTES);
+        for (int s = 0; s < SEL_STAGES; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+// One pass over the list: CTA c of the cluster takes chunks c, c + C, c + 2C, ...; f(chunk, len) is called by
+// ALL threads of the CTA with the chunk in shared memory (len valid entries).  `ph` carries the stages' phase
+// bits from pass to pass.
+template <class F>
+__device__ __forceinline__ void stream_pass(cg::cluster_group &cluster, const ListView &lv, unsigned char *smem_raw, unsigned int &ph, F f)
+{
+    double *ring = reinterpret_cast<double *>(smem_raw + SELC_HIST_BYTES);
+    const unsigned int bar0 = smem_u32(smem_raw + SELC_HIST_BYTES + SELC_RING_BYTES);
+    const long long nctas = cluster.num_blocks(), crank = cluster.block_rank();
+    const long long total = lv.choff[lv.nseg];
+    const long long mine = total > crank ? (total - crank + nctas - 1) / nctas : 0;
+    auto locate = [&](long long i, int &sg, long long &c, long long &len) {
+        const long long g = crank + i * nctas;
+        sg = 0;
+        while (sg + 1 < lv.nseg && g >= lv.choff[sg + 1]) sg++;
+        c = g - lv.choff[sg];
+        const long long n_s = lv.off[sg + 1] - lv.off[sg];
+        len = n_s - c * SEL_CH < SEL_CH ? n_s - c * SEL_CH : SEL_CH;
+    };
+    auto issue = [&](long long i) {
+        int sg; long long c, len;
+        locate(i, sg, c, len);
+        const unsigned int bytes = (unsigned int)((len * 8 + 15) & ~15ll);       // (lists have an even capacity: the pad stays inside)
+        const int st = (int)(i % SEL_STAGES);
+        mbar_expect_tx(bar0 + 8 * st, bytes);
+        bulk_g2s(smem_u32(ring + (long long)st * SEL_CH), lv.seg[sg] + c * SEL_CH, bytes, bar0 + 8 * st);
+    };
+    if (threadIdx.x == 0)
+        for (long long i = 0; i < mine && i < SEL_STAGES; i++) issue(i);
+    for (long long i = 0; i < mine; i++) {
+        int sg; long long c, len;
+        locate(i, sg, c, len);
+        const int st = (int)(i % SEL_STAGES);
+        mbar_wait(bar0 + 8 * st, (ph >> st) & 1u);
+        ph ^= 1u << st;
+        f(reinterpret_cast<const u64 *>(ring + (long long)st * SEL_CH), (int)len);
+        __syncthreads();                                   // everyone is done with the stage before it is refilled
+        if (threadIdx.x == 0 && i + SEL_STAGES < mine) issue(i + SEL_STAGES);
+    }
 }
 
 // Scale of the kept-side total (items >= hi).  52 - e(hi) represents every such double exactly
@@ -273,6 +381,57 @@ __host__ __device__ __forceinline__ int kept_tot_scale(u64 hi, u64 vmax)
     const int e_v = exp_of_bits(vmax);
     if (hi < PF_INF_BITS && e_v - exp_of_bits(hi) <= 46) return 52 - exp_of_bits(hi);
     return 99 - e_v;
+}
+
+// log of the step's total weight = (kept side: integer Tot at scale ts) + (low side: integer low at scale `scale`).
+// Where the scales are close (the usual case: scale - ts = 17) the two integers are added EXACTLY (192 bits)
+// and rounded to a double ONCE, so the result depends on the sum only, not on where the bracket split it --
+// runs whose brackets differ (another sample stride, a retried round, another sharding) agree bit for bit.
+__host__ __device__ inline double log_total_exact(u128 Tot, int ts, u128 low, int scale)
+{
+    const double LN2 = 0.693147180559945309417232121458;
+    const int d = scale - ts;                           // the low side's scale minus the kept side's
+    if (!isz128(Tot) && !isz128(low) && (d > 60 || d < -60)) {
+        // scales far apart (kept side far above the bracket: its sum was truncated anyway): plain floating point
+        const double tsum = to_double128(Tot) + ldexp(to_double128(low), ts - scale);
+        return log(tsum) - (double)ts * LN2;
+    }
+    // total = A * 2^sh + B at scale sc (the finer of the two scales)
+    u128 A = mk128(0, 0), B = low;
+    int sh = 0, sc = scale;
+    if (isz128(Tot)) { }
+    else if (isz128(low)) { B = Tot; sc = ts; }
+    else if (d >= 0) { A = Tot; sh = d; }
+    else { A = low; B = Tot; sh = -d; sc = ts; }
+    // w = A * 2^sh + B, little-endian 64-bit limbs
+    u64 w[3];
+    w[0] = A.lo << sh; w[1] = (A.hi << sh) | (sh ? A.lo >> (64 - sh) : 0ull); w[2] = sh ? A.hi >> (64 - sh) : 0ull;
+    u64 c = 0;
+    w[0] += B.lo; c = w[0] < B.lo ? 1ull : 0ull;
+    u64 t1 = w[1] + B.hi; u64 c1 = t1 < B.hi ? 1ull : 0ull;
+    w[1] = t1 + c; c1 += w[1] < t1 ? 1ull : 0ull;
+    w[2] += c1;
+    // top 64 significant bits + sticky, converted with one round-to-nearest-even
+    int top = w[2] ? 2 : (w[1] ? 1 : 0);
+    u64 hi64 = w[top];
+#ifdef __CUDA_ARCH__
+    const int lz = hi64 ? __clzll((long long)hi64) : 64;
+#else
+    const int lz = hi64 ? __builtin_clzll(hi64) : 64;
+#endif
+    if (lz == 64) return log(0.0);
+    u64 m = hi64 << lz;
+    bool sticky = false;
+    if (top > 0) {
+        const u64 nxt = w[top - 1];
+        if (lz) { m |= nxt >> (64 - lz); sticky = (nxt << lz) != 0; } else sticky = nxt != 0;
+        if (top > 1) sticky = sticky || w[top - 2] != 0;
+    }
+    if (sticky) m |= 1ull;
+    const double v = (double)m;                         // w = m * 2^(64 top - lz) up to the one rounding of this conversion
+    const int e = 64 * top - lz - sc;
+    if (e > -1000 && e < 900) return log(ldexp(v, e));  // the total as ONE correctly rounded double, then its log
+    return log(v) + (double)e * LN2;
 }
 
 // predicate of cutoff_ascending (src/fearnhead.jl:69): tot <= (N - n_geq) * w
@@ -359,43 +518,73 @@ struct ChunkWriter {
     }
 };
 
-// One radix level on a cluster: every CTA histograms (count, fixed-point sum) its share of the list items
-// inside [blo, bhi) into ITS shared memory (1024 bins of width 2^shift bit patterns); after a cluster
-// barrier CTA c sums bins [c B/C, (c+1) B/C) over all CTAs through distributed shared memory and writes the
-// totals to sc->h_* (which select_bin reads).
+// One radix level on a cluster: every WARP histograms (count, fixed-point sum as two 64-bit words) the list items of
+// its CTA's chunks inside [blo, bhi) into its PRIVATE 1024-bin histogram in shared memory (bins of width 2^shift bit
+// patterns).  Lanes that hit the same bin are grouped (match.any), their items summed with three 32-bit warp
+// reductions (24-bit limbs) and the group's first lane updates the bin with plain loads and stores: no atomics
+// (64-bit shared-memory atomics are compare-and-swap loops and the first level's bins -- whole binades -- are hot).
+// Then the CTA folds its 8 copies, and CTA c of the cluster sums bins [c B/C, (c+1) B/C) over all CTAs through
+// distributed shared memory and writes the totals to sc->h_* (which select_bin reads).
 __device__ inline void hist_level(cg::cluster_group &cluster, const ListView &lv, u64 blo, u64 bhi, int shift, int scale,
-                                  SelScratch *sc, unsigned char *smem_raw)
+                                  SelScratch *sc, unsigned char *smem_raw, unsigned int &ph)
 {
-    unsigned int *h_cnt = reinterpret_cast<unsigned int *>(smem_raw);
-    u64 *h_s0 = reinterpret_cast<u64 *>(smem_raw + SEL_BINS * 4);
-    u64 *h_s1 = h_s0 + SEL_BINS, *h_s2 = h_s1 + SEL_BINS;
-    const int tid = threadIdx.x;
+    unsigned int *h_cnt = reinterpret_cast<unsigned int *>(smem_raw);                          // [warp][bin]
+    u64 *h_s0 = reinterpret_cast<u64 *>(smem_raw + SELC_WARPS * SEL_BINS * 4);                  // [warp][bin]: sum of q mod 2^32
+    u64 *h_s1 = h_s0 + SELC_WARPS * SEL_BINS;                                                  // [warp][bin]: sum of q >> 32
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned int nctas = cluster.num_blocks(), crank = cluster.block_rank();
-    for (int t = tid; t < SEL_BINS; t += SEL_THREADS) { h_cnt[t] = 0; h_s0[t] = 0; h_s1[t] = 0; h_s2[t] = 0; }
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+        for (int t = tid; t < SELC_HIST_BYTES / 16; t += SELC_THREADS) z[t] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
-    const long long list_n = lv.off[lv.nseg];
-    for (long long t = (long long)crank * SEL_THREADS + tid; t < list_n; t += (long long)nctas * SEL_THREADS) {
-        u64 bits = lv_load(lv, t);
-        if (bits >= blo && bits < bhi) {
-            int b = (int)((bits - blo) >> shift);
-            u128 q = fx70(bits, scale);
-            atomicAdd(&h_cnt[b], 1u);
-            atomicAdd(&h_s0[b], q.lo & 0xffffffffull);
-            atomicAdd(&h_s1[b], q.lo >> 32);
-            atomicAdd(&h_s2[b], q.hi);
+    unsigned int *wc = h_cnt + wid * SEL_BINS;
+    u64 *w0 = h_s0 + wid * SEL_BINS, *w1 = h_s1 + wid * SEL_BINS;
+    stream_pass(cluster, lv, smem_raw, ph, [&](const u64 *chunk, int len) {
+        for (int base = wid * 32; base < len; base += SELC_THREADS) {                          // (warp-uniform trip count)
+            const int idx = base + lane;
+            const u64 bits = idx < len ? chunk[idx] : ~0ull;
+            const bool in = bits >= blo && bits < bhi;
+            if (!__any_sync(0xffffffffu, in)) continue;
+            const int b = in ? (int)((bits - blo) >> shift) : -1 - lane;
+            const unsigned int peers = __match_any_sync(0xffffffffu, b);
+            if (in) {
+                const u128 q = fx70(bits, scale);                                              // < 2^71
+                const int np = __popc(peers);
+                if (np == 1) {
+                    wc[b] += 1u; w0[b] += q.lo & 0xffffffffull; w1[b] += (q.lo >> 32) | (q.hi << 32);
+                } else {
+                    const unsigned int s0 = __reduce_add_sync(peers, (unsigned int)(q.lo & 0xffffffu));
+                    const unsigned int s1 = __reduce_add_sync(peers, (unsigned int)((q.lo >> 24) & 0xffffffu));
+                    const unsigned int s2 = __reduce_add_sync(peers, (unsigned int)((q.lo >> 48) | (q.hi << 16)));
+                    if (lane == __ffs(peers) - 1) {
+                        const u128 tot = add128(add128(mk128(s0, 0), mk128((u64)s1 << 24, 0)), shl128(mk128(s2, 0), 48));
+                        wc[b] += (unsigned int)np; w0[b] += tot.lo & 0xffffffffull; w1[b] += (tot.lo >> 32) | (tot.hi << 32);
+                    }
+                }
+            }
+            __syncwarp();                                                                      // the next step may touch the same bin from another lane
         }
+    });
+    __syncthreads();
+    for (int b = tid; b < SEL_BINS; b += SELC_THREADS) {                                        // fold the CTA's copies into copy 0
+        unsigned int c = 0; u64 s0 = 0, s1 = 0;
+#pragma unroll
+        for (int w = 0; w < SELC_WARPS; w++) { c += h_cnt[w * SEL_BINS + b]; s0 += h_s0[w * SEL_BINS + b]; s1 += h_s1[w * SEL_BINS + b]; }
+        h_cnt[b] = c; h_s0[b] = s0; h_s1[b] = s1;
     }
     cluster.sync();
     const int per = SEL_BINS / (int)nctas;
-    for (int k = tid; k < per; k += SEL_THREADS) {
+    for (int k = tid; k < per; k += SELC_THREADS) {
         const int b = (int)crank * per + k;
-        unsigned int c = 0; u64 s0 = 0, s1 = 0, s2 = 0;
+        unsigned int c = 0; u64 s0 = 0, s1 = 0;
+#pragma unroll 4
         for (unsigned int r = 0; r < nctas; r++) {
-            const unsigned int *rc = cluster.map_shared_rank(h_cnt, r);
-            const u64 *r0 = cluster.map_shared_rank(h_s0, r);
-            c += rc[b]; s0 += r0[b]; s1 += r0[SEL_BINS + b]; s2 += r0[2 * SEL_BINS + b];
+            c += cluster.map_shared_rank(h_cnt, r)[b];
+            s0 += cluster.map_shared_rank(h_s0, r)[b];
+            s1 += cluster.map_shared_rank(h_s1, r)[b];
         }
-        sc->h_cnt[b] = c; sc->h_sum[0][b] = s0; sc->h_sum[1][b] = s1; sc->h_sum[2][b] = s2;
+        sc->h_cnt[b] = c; sc->h_sum[0][b] = s0; sc->h_sum[1][b] = s1;          // bin sum = s0 + s1 2^32
     }
     __threadfence();
     cluster.sync();          // remote reads done before anyone reuses its shared memory; totals visible to CTA 0
@@ -414,9 +603,9 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
     u128 *ps = reinterpret_cast<u128 *>(smem_raw + SEL_BINS * 4);            // inclusive sum prefix
     __shared__ int s_found;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int b = tid; b < SEL_BINS; b += SEL_THREADS) {
+    for (int b = tid; b < SEL_BINS; b += (int)blockDim.x) {
         pc[b] = __ldcg(&sc->h_cnt[b]);
-        ps[b] = add128(add128(mk128(__ldcg(&sc->h_sum[0][b]), 0), shl128(mk128(__ldcg(&sc->h_sum[1][b]), 0), 32)), mk128(0, __ldcg(&sc->h_sum[2][b])));
+        ps[b] = add128(mk128(__ldcg(&sc->h_sum[0][b]), 0), shl128(mk128(__ldcg(&sc->h_sum[1][b]), 0), 32));
     }
     __syncthreads();
     const int per = SEL_BINS / 32;
@@ -543,12 +732,18 @@ __device__ __forceinline__ void sel_halt(SelScratch *sc, long long step, int rea
 // sharded: all threads of the cluster copy `n` doubles of the local list into segment `rank` of every region
 __device__ inline void xch_copy_list(cg::cluster_group &cluster, const Xch *x, const double *src, long long n, int kind, int parity)
 {
-    const long long nth = (long long)cluster.num_blocks() * SEL_THREADS;
-    const long long t0 = (long long)cluster.block_rank() * SEL_THREADS + threadIdx.x;
+    const long long nth = (long long)cluster.num_blocks() * SELC_THREADS;
+    const long long t0 = (long long)cluster.block_rank() * SELC_THREADS + threadIdx.x;
     for (int p = 0; p < x->nranks; p++) {
         double *dst = kind == XCH_A ? xch_listA(x->reg[p], x->capA, x->rank)
                                     : xch_listB(x->reg[p], x->nranks, x->capA, x->capB, parity, x->rank);
-        for (long long t = t0; t < n; t += nth) dst[t] = src[t];
+        for (long long t = t0; t < n; t += nth * SEL_BATCH) {
+            double v[SEL_BATCH];
+#pragma unroll
+            for (int k = 0; k < SEL_BATCH; k++) v[k] = t + k * nth < n ? src[t + k * nth] : 0.0;
+#pragma unroll
+            for (int k = 0; k < SEL_BATCH; k++) if (t + k * nth < n) dst[t + k * nth] = v[k];
+        }
     }
     __threadfence_system();
 }
@@ -605,7 +800,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_sample(SelArgs a)
 }
 
 // ------------------------------------------------------------------ k_sel_bracket (one cluster)
-__global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
+__global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_bracket(SelArgs a)
 {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -618,6 +813,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
     const bool lead = cluster.block_rank() == 0 && tid == 0;
     const long long N = a.N;
 
+    int dbg_k = 0;
+#define DBG_STAMP(base) do { if (lead && dbg_k < 16) sc->dbg_t[(base) + dbg_k++] = gtimer(); } while (0)
+    DBG_STAMP(0);
     // ---- the sample: local list, or (sharded) every rank's list gathered through the exchange regions
     if (x) {
         if (a.stage & SEL_ST_PUB) {
@@ -667,7 +865,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
             s_lv.off[1] = a.external_sample ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
         }
     }
-    __syncthreads();
+    if (tid == 0) lv_finish(s_lv);
+    stream_init(smem_raw);
+    unsigned int ph = 0;
     const long long M = sc->gM;
     const u64 vmax = sc->gvmax;                         // (external sample: the sample's maximum)
     const int vmax_scale = SEL_ITEM_BITS - exp_of_bits(vmax);
@@ -676,6 +876,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
     const long long stride = a.fixed_stride;
     const long long ns_total = s_lv.off[s_lv.nseg];
     cluster.sync();                                     // every CTA has read the sample's size before the lead resets the counters
+    DBG_STAMP(0);
 
     if (lead) {
         if (a.external_sample) {
@@ -688,7 +889,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
             sc->n_cand = (unsigned long long)ns_total; sc->vs_bits = vmax;
         }
         sc->mult = 1;
-        if (trivial) { sc->lo = PF_INF_BITS; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 1; }     // keep everything (src/fearnhead.jl:135-138)
+        // keep everything (src/fearnhead.jl:135-138): lo = hi = 0 puts every putative on the kept side, whose sum is the
+        // (practically) exact one -- the step's total weight does not depend on a bracket scale
+        if (trivial) { sc->lo = 0; sc->hi = 0; sc->scale = vmax_scale; sc->mode = 1; }
         else { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0; }                     // direct solve, or the sample solve's start
         if (sampled) { sc->B_run = mk128(0, 0); sc->A_run = 0; sc->count_in = (long long)sc->n_cand; sc->mult = stride; sc->phase = 2; }
         __threadfence();
@@ -702,9 +905,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            hist_level(cluster, s_lv, blo, bhi, shift, ss, sc, smem_raw);
+            DBG_STAMP(0);
+            hist_level(cluster, s_lv, blo, bhi, shift, ss, sc, smem_raw, ph);
+            DBG_STAMP(0);
             if (cluster.block_rank() == 0) select_bin(sc, N, blo, bhi, shift, ss, a.margin > 0 ? a.margin : 8, smem_raw);
             cluster.sync();
+            DBG_STAMP(0);
             if (sc->phase == 6) break;
         }
         cluster.sync();                                 // everyone has left the loop before the lead rewrites the bracket
@@ -726,6 +932,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
         reset_round(sc);                                 // the classic rounds start from a clean slate
     }
     if (lead) { sc->phase = 0; res->t_ns[1] = gtimer(); }
+    DBG_STAMP(0);
 }
 
 // ------------------------------------------------------------------ k_sel_classify (full grid)
@@ -799,7 +1006,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_sel_classify(SelArgs a)
 }
 
 // ------------------------------------------------------------------ k_sel_solve (one cluster)
-__global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
+__global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
 {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -807,8 +1014,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
     __shared__ ListView s_lv;
     __shared__ u128 s_warp[33];
     __shared__ long long s_ll[4];
-    __shared__ u128 s_red[SEL_WARPS];
-    __shared__ unsigned long long s_redc[SEL_WARPS];
+    __shared__ u128 s_red[SELC_WARPS];
+    __shared__ unsigned long long s_redc[SELC_WARPS];
 
     SelScratch *sc = a.sc;
     SelResult *res = a.res;
@@ -823,6 +1030,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
     const bool pre_round = !a.retry && a.preclassified && sc->fuse_valid;      // the expansion kernel classified this round
     const u64 plateau = a.plateau_ptr ? *a.plateau_ptr : 0ull;
 
+    int dbg_k = 0;
+    DBG_STAMP(16);
     // ---- the candidate list and the accumulators: local, or (sharded) gathered through the exchange regions
     if (x) {
         const int parity = round & 1;
@@ -880,7 +1089,9 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
             s_lv.off[1] = sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
         }
     }
-    __syncthreads();
+    if (tid == 0) lv_finish(s_lv);
+    stream_init(smem_raw);
+    unsigned int ph = 0;
     const long long M = sc->gM;
     const u64 vmax = sc->gvmax;
     const int vmax_scale = SEL_ITEM_BITS - exp_of_bits(vmax);
@@ -893,6 +1104,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
     const bool keep_all = (mode == 1);
     const bool need_tot = sc->need_tot != 0;
     cluster.sync();                          // everyone has read the round's bracket before CTA 0 may change it
+    DBG_STAMP(16);
 
     // ---- CTA 0: verify the bracket, start the descent
     if (lead) {
@@ -912,8 +1124,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
             const int ts = pre_round ? sc->fuse_tot_scale : sc->tot_scale_used;
             u128 low = add128(acc_value(&sc->B_lo), acc_value(&sc->S_cand));
             if (sc->n_plateau) low = add128(low, mul128_64(fx70(plateau, scale), (u64)sc->n_plateau));
-            double tsum = to_double128(acc_value(&sc->Tot)) + ldexp(to_double128(low), ts - scale);
-            res->log_total = log(tsum) - (double)ts * 0.693147180559945309417232121458;
+            res->log_total = log_total_exact(acc_value(&sc->Tot), ts, low, scale);
             sc->need_tot = 0;
         }
         int phase = 2;       // 2 = descend, 3 = another classify round with a new bracket / scale, 4 = done
@@ -963,15 +1174,17 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
         // predicate at P itself; the bracket shrinks to [lo, P) or (P, hi) and never contains the tie
         u128 sb = mk128(0, 0);
         unsigned long long cb = 0;
-        for (long long t = (long long)crank * SEL_THREADS + tid; t < list_n; t += (long long)nctas * SEL_THREADS) {
-            u64 bits = lv_load(s_lv, t);
-            if (bits >= lo && bits < plateau) { cb++; sb = add128(sb, fx70(bits, scale)); }
-        }
+        stream_pass(cluster, s_lv, smem_raw, ph, [&](const u64 *chunk, int len) {
+            for (int idx = tid; idx < len; idx += SELC_THREADS) {
+                const u64 bits = chunk[idx];
+                if (bits >= lo && bits < plateau) { cb++; sb = add128(sb, fx70(bits, scale)); }
+            }
+        });
         sb = warp_sum128(sb); cb = warp_sum64(cb);
         if (lane == 0) { s_red[wid] = sb; s_redc[wid] = cb; }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < SEL_WARPS; w++) { sb = add128(sb, s_red[w]); cb += s_redc[w]; }
+            for (int w = 1; w < SELC_WARPS; w++) { sb = add128(sb, s_red[w]); cb += s_redc[w]; }
             if (cb) atomicAdd(&sc->pl_cnt, cb);
             atomic_add_acc(&sc->pl_sum, sb);
             __threadfence();
@@ -989,6 +1202,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
         }
         cluster.sync();
     }
+    DBG_STAMP(16);
     if (sc->phase == 3) return;              // a queued retry round (k_sel_classify + k_sel_solve) takes over
 
     if (sc->phase == 2) {
@@ -998,13 +1212,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
             const long long count_in = sc->count_in;
             if (count_in <= SEL_FINAL_CAP) {
                 // compact the bracket's items into the final list
-                for (long long t = (long long)crank * SEL_THREADS + tid; t < list_n; t += (long long)nctas * SEL_THREADS) {
-                    u64 bits = lv_load(s_lv, t);
-                    if (bits >= blo && bits < bhi) {
-                        unsigned int pos = atomicAdd(&sc->final_n, 1u);
-                        if (pos < SEL_FINAL_CAP) sc->final_vals[pos] = __longlong_as_double((long long)bits);
+                stream_pass(cluster, s_lv, smem_raw, ph, [&](const u64 *chunk, int len) {
+                    for (int idx = tid; idx < len; idx += SELC_THREADS) {
+                        const u64 bits = chunk[idx];
+                        if (bits >= blo && bits < bhi) {
+                            unsigned int pos = atomicAdd(&sc->final_n, 1u);
+                            if (pos < SEL_FINAL_CAP) sc->final_vals[pos] = __longlong_as_double((long long)bits);
+                        }
                     }
-                }
+                });
                 __threadfence();
                 break;
             }
@@ -1012,11 +1228,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            hist_level(cluster, s_lv, blo, bhi, shift, scale, sc, smem_raw);
+            DBG_STAMP(16);
+            hist_level(cluster, s_lv, blo, bhi, shift, scale, sc, smem_raw, ph);
+            DBG_STAMP(16);
             if (crank == 0) select_bin(sc, N, blo, bhi, shift, scale, 0, smem_raw);
             cluster.sync();
+            DBG_STAMP(16);
         }
         cluster.sync();
+        DBG_STAMP(16);
 
         // ---- CTA 0: exact solve on the final list
         if (crank == 0) {
@@ -1037,10 +1257,10 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
             } else {
                 int nf = (int)count_in;
                 int np2 = 2; while (np2 < nf) np2 <<= 1;
-                for (int t = tid; t < np2; t += SEL_THREADS) s_u64[t] = t < nf ? (u64)__double_as_longlong(__ldcg(&sc->final_vals[t])) : ~0ull;
+                for (int t = tid; t < np2; t += SELC_THREADS) s_u64[t] = t < nf ? (u64)__double_as_longlong(__ldcg(&sc->final_vals[t])) : ~0ull;
                 __syncthreads();
                 bitonic_sort_smem(s_u64, np2);
-                const int per = SEL_FINAL_CAP / SEL_THREADS;
+                const int per = SEL_FINAL_CAP / SELC_THREADS;
                 u128 loc = mk128(0, 0);
                 for (int k = 0; k < per; k++) { int t = tid * per + k; if (t < nf) loc = add128(loc, fx70(s_u64[t], scale)); }
                 u128 tot;
@@ -1097,6 +1317,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
             }
         }
         cluster.sync();
+        DBG_STAMP(16);
         if (sc->phase != 4) return;
     }
 

@@ -223,6 +223,18 @@ class ShardedFearnheadParticles:
         _lib.check(self.L.pf_get_last_step(self.handles[0], C.byref(st)), self.handles[0])
         return st.asdict()
 
+    def set_profiling(self, on=True):
+        for h in self.handles:
+            _lib.check(self.L.pf_set_profiling(h, int(on)), h)
+
+    def kernel_times(self):
+        """{class name: (device ms, launches)} of this process's first shard since set_profiling."""
+        ms = np.zeros(10)
+        n = np.zeros(10, dtype=np.int64)
+        _lib.check(self.L.pf_get_kernel_times(self.handles[0], ms.ctypes.data_as(_dp), n.ctypes.data_as(C.POINTER(C.c_int64))),
+                   self.handles[0])
+        return {self.L.pf_kernel_class_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(10)}
+
     def timing(self):
         """(device ms of the last filter_ call on this process's first shard, its kernel launches)."""
         ms, n = C.c_double(), C.c_int64()
