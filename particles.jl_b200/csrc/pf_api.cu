@@ -92,7 +92,7 @@ struct pf_filter_s {
     StepLog last{};
     bool have_last = false, last_stale = false;
     int sel_grid = 0;
-    int cluster_size = 8;                 // CTAs of the cluster the bracket / solve kernels run on
+    int coop_grid = 0;                    // CTAs of the cooperative bracket / solve kernels (one per SM)
     int retries = SEL_RETRIES;            // queued extra search rounds per step
     int redo = 0;                         // the next step re-runs a halted one
     int num_sms = 0;
@@ -227,7 +227,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     return PF_OK;
 }
 
-static int32_t setup_cluster_kernels(pf_handle h);
+static int32_t setup_search_kernels(pf_handle h);
 
 extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
 {
@@ -330,13 +330,12 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->stc, 1));
     CT(cudaMemsetAsync(h->sc, 0, sizeof(SelScratch), h->stream));
     CT(cudaMemsetAsync(h->res, 0, sizeof(SelResult), h->stream));
-    // grid of the classify pass; cluster size of the bracket / solve kernels (16 CTAs if the device can
-    // schedule such a cluster, else the portable 8)
+    // grids of the classify pass and of the cooperative bracket / solve kernels
     {
         int occ = 0;
         CT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_classify, SEL_THREADS, 0));
         h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
-        int32_t rc = setup_cluster_kernels(h);
+        int32_t rc = setup_search_kernels(h);
         if (rc != PF_OK) { g_create_error = h->err; pf_destroy(h); return rc; }
     }
     h->cand_cap = ((long long)(h->k_max + 1) * cap + (long long)h->sel_grid * (SEL_THREADS / 32) * SEL_CHUNK * 2 + SEL_CHUNK + 2) & ~1ll;
@@ -406,44 +405,23 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
 // ------------------------------------------------------------------ the step sequences
 static inline int grid_for(long long n, int bs) { long long g = (n + bs - 1) / bs; return (int)(g < 1 ? 1 : g); }
 
-// ---- the threshold search: cluster launches, argument block, launch sequences
-static cudaError_t launch_cluster(void (*kern)(SelArgs), int csize, cudaStream_t stream, const SelArgs &a)
+// ---- the threshold search: cooperative launches, argument block, launch sequences
+static cudaError_t launch_coop(void (*kern)(SelArgs), int grid, cudaStream_t stream, SelArgs &a)
 {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(csize); cfg.blockDim = dim3(SELC_THREADS); cfg.dynamicSmemBytes = SELC_SMEM_BYTES; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, a);
+    void *args[] = {&a};
+    return cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(SEL_THREADS), args, 0, stream);
 }
 
-// 16-CTA clusters are a non-portable size: ask the device whether it can co-schedule one, else use 8
-static int32_t setup_cluster_kernels(pf_handle h)
+// the bracket / solve kernels synchronise grid-wide: one resident CTA per SM
+static int32_t setup_search_kernels(pf_handle h)
 {
     void (*kerns[2])(SelArgs) = {k_sel_bracket, k_sel_solve};
-    int best = SEL_MAX_CLUSTER;
     for (int k = 0; k < 2; k++) {
-        CUDA_TRY(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CUDA_TRY(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, SELC_SMEM_BYTES));
-        int ok_size = 8;
-        for (int cs = SEL_MAX_CLUSTER; cs >= 8; cs >>= 1) {
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof cfg);
-            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(SELC_THREADS); cfg.dynamicSmemBytes = SELC_SMEM_BYTES;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, kerns[k], &cfg) == cudaSuccess && ncl >= 1) { ok_size = cs; break; }
-            cudaGetLastError();
-        }
-        best = std::min(best, ok_size);
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kerns[k], SEL_THREADS, 0));
+        if (occ < 1) return set_error(h, PF_ERR_CUDA, "a threshold-search kernel does not fit on an SM");
     }
-    if (getenv("PF_SEL_CLUSTER")) { int cs = atoi(getenv("PF_SEL_CLUSTER")); if (cs == 1 || cs == 2 || cs == 4 || cs == 8 || cs == 16) best = std::min(best, cs); }
-    h->cluster_size = best;
+    h->coop_grid = h->num_sms;
     return PF_OK;
 }
 
@@ -467,7 +445,7 @@ static int32_t launch_round(pf_handle h, SelArgs a, int retry, int solve_stage =
     a.retry = retry;
     k_sel_classify<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
     a.stage = solve_stage;
-    CUDA_TRY(launch_cluster(k_sel_solve, h->cluster_size, h->stream, a));
+    CUDA_TRY(launch_coop(k_sel_solve, h->coop_grid, h->stream, a));
     h->launches += 2;
     return PF_OK;
 }
@@ -478,7 +456,7 @@ static int32_t launch_classic_search(pf_handle h, SelArgs a)
     a.external_sample = 0; a.preclassified = 0;
     k_sel_reset<<<1, 32, 0, h->stream>>>(a);
     k_sel_sample<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
-    CUDA_TRY(launch_cluster(k_sel_bracket, h->cluster_size, h->stream, a));
+    CUDA_TRY(launch_coop(k_sel_bracket, h->coop_grid, h->stream, a));
     h->launches += 3;
     for (int r = 0; r <= h->retries; r++) {
         int32_t rc = launch_round(h, a, r > 0);
@@ -516,7 +494,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
                                                                        nullptr);
             SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
             a.external_sample = 1;
-            CUDA_TRY(launch_cluster(k_sel_bracket, h->cluster_size, h->stream, a));
+            CUDA_TRY(launch_coop(k_sel_bracket, h->coop_grid, h->stream, a));
         }
         {
             LaunchTimer lt(h, KC_EXPAND);
@@ -999,7 +977,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
             int occ = 0;
             ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_classify, SEL_THREADS, 0));
             h->sel_grid = h->num_sms * (occ > 2 ? 2 : (occ < 1 ? 1 : occ));
-            rc = setup_cluster_kernels(h);
+            rc = setup_search_kernels(h);
             if (rc != PF_OK) { g_create_error = h->err; goto done; }
             h->sel_margin = getenv("PF_SEL_MARGIN") ? std::max(1, atoi(getenv("PF_SEL_MARGIN"))) : 8;
         }
@@ -1216,12 +1194,12 @@ extern "C" int32_t pf_mg_connect(pf_handle *hs, int32_t n_local)
 // ---- the stages of one sharded observation (each queues launches on the handle's stream)
 // A: roll the control block over (waits for every rank's previous generation), sample expansion, bracket
 template <int D>
-static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev, int cluster_stage)
+static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev, int search_stage)
 {
     const long long cap = h->cap;
     const int cur = h->cur;
     const unsigned long long seq = (unsigned long long)h->steps + 1;
-    if (cluster_stage & SEL_ST_PUB) {
+    if (search_stage & SEL_ST_PUB) {
         {
             LaunchTimer lt(h, KC_PRESTEP);            // (includes the wait for every rank's previous generation)
             k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->steps == 0 ? 1 : 0, h->sc, h->res, h->xch, seq, h->steps);
@@ -1232,21 +1210,21 @@ static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev,
                                                                    h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr, nullptr);
     }
     SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
-    a.external_sample = 1; a.x = h->xch; a.stage = cluster_stage;
+    a.external_sample = 1; a.x = h->xch; a.stage = search_stage;
     LaunchTimer lt(h, KC_SELECT);
-    CUDA_TRY(launch_cluster(k_sel_bracket, h->cluster_size, h->stream, a));
+    CUDA_TRY(launch_coop(k_sel_bracket, h->coop_grid, h->stream, a));
     return PF_OK;
 }
 
 // B: fused expansion (round 0) / classify pass (retry rounds), then the solve on the gathered candidates
 template <int D>
-static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int cluster_stage)
+static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int search_stage)
 {
     const long long cap = h->cap;
     const int cur = h->cur;
     SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
     a.external_sample = 1; a.preclassified = 1; a.x = h->xch; a.retry = retry;
-    if (cluster_stage & SEL_ST_PUB) {
+    if (search_stage & SEL_ST_PUB) {
         if (!retry) {
             LaunchTimer lt(h, KC_EXPAND);
             k_expand<D, 2><<<grid_for(cap, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
@@ -1255,9 +1233,9 @@ static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int clust
         LaunchTimer lt(h, KC_SELECT);
         k_sel_classify<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
     }
-    a.stage = cluster_stage;
+    a.stage = search_stage;
     LaunchTimer lt(h, KC_SELECT);
-    CUDA_TRY(launch_cluster(k_sel_solve, h->cluster_size, h->stream, a));
+    CUDA_TRY(launch_coop(k_sel_solve, h->coop_grid, h->stream, a));
     return PF_OK;
 }
 
@@ -1447,14 +1425,5 @@ extern "C" int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */)
                      (int64_t)r.Tq.lo, (int64_t)r.Tq.hi, r.Tr, r.A, r.n, r.rounds, st.n_live, st.M, st.n_next,
                      r.status, hdr[2] /* scale | phase */, hdr[5] /* halt */, ro.n_local, ro.g_first, ro.kept_off, (int64_t)ro.S_off.lo, ro.n_global};
     for (int k = 0; k < 24; k++) out[k] = v[k];
-    if (getenv("PF_DEBUG_STAMPS")) {
-        unsigned long long t[32];
-        CUDA_TRY(cudaMemcpy(t, scp->dbg_t, sizeof t, cudaMemcpyDeviceToHost));
-        for (int g = 0; g < 2; g++) {
-            fprintf(stderr, "%s stamps (us):", g ? "solve" : "bracket");
-            for (int k = 1; k < 16 && t[16 * g + k] >= t[16 * g + k - 1] && t[16 * g + k]; k++) fprintf(stderr, " %.1f", (t[16 * g + k] - t[16 * g + k - 1]) * 1e-3);
-            fprintf(stderr, "\n");
-        }
-    }
     return PF_OK;
 }

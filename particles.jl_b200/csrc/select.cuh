@@ -12,13 +12,13 @@
 //             and evaluate the predicate of src/fearnhead.jl:69 exactly; if the comb needs a
 //             finer scale than the threshold did, ask for one more classify round.  k_sel_solve
 //
-// k_sel_bracket and k_sel_solve work on short lists (~10^6 values) and are latency-bound: each
-// runs on ONE thread-block cluster (16 CTAs where the device schedules it, else 8): the radix
-// histograms live in every CTA's shared memory and are reduced across the cluster through
-// distributed shared memory, and the ~10 barriers per launch are cluster barriers instead of
-// grid-wide ones.  k_sel_classify streams the whole V and is a plain full-grid kernel.  A round
-// that asks for another one (phase 3) is followed by queued retry launches of k_sel_classify /
-// k_sel_solve, which are no-ops otherwise: no host round trip inside a step.
+// k_sel_bracket and k_sel_solve work on short lists (~10^6 values); they are cooperative full-grid
+// kernels: a 16-CTA cluster with DSMEM histograms was built and measured 2-4x slower (the list passes
+// are instruction-bound on 16 SMs, profiles/r2/cluster_search_experiment.md).  Every CTA keeps the
+// same search state and selects the next bin redundantly from the level's global histogram, so a
+// radix level costs ONE grid barrier.  k_sel_classify streams the whole V and is a plain full-grid
+// kernel.  A round that asks for another one (phase 3) is followed by queued retry launches of
+// k_sel_classify / k_sel_solve, which are no-ops otherwise: no host round trip inside a step.
 //
 // Sharded runs (particles block-sharded over GPUs): k_sel_bracket / k_sel_solve begin by
 // writing the local sample / candidate list and accumulator block into EVERY peer's exchange
@@ -47,16 +47,7 @@ namespace cg = cooperative_groups;
 #endif
 #define SEL_ITEM_BITS 69            // items q = floor(v 2^scale) < 2^(SEL_ITEM_BITS+1)
 #define SEL_TOT_BITS 89             // total-weight accumulator scale relative to vmax
-// cluster kernels (k_sel_bracket, k_sel_solve): 8 warps per CTA, each with a PRIVATE 1024-bin histogram in shared
-// memory (no atomics), the list streamed through a shared-memory ring by 1-D bulk copies (TMA)
-#define SELC_THREADS 256
-#define SELC_WARPS (SELC_THREADS / 32)
-#define SEL_CH 2048                 // doubles per bulk copy (16 KB)
-#define SEL_STAGES 3                // ring depth
-#define SELC_HIST_BYTES (SELC_WARPS * SEL_BINS * 20)
-#define SELC_RING_BYTES (SEL_STAGES * SEL_CH * 8)
-#define SELC_SMEM_BYTES (SELC_HIST_BYTES + SELC_RING_BYTES + 64)
-#define SEL_MAX_CLUSTER 16
+#define SEL_SMEM_BYTES (SEL_BINS * 4 + 2 * SEL_BINS * 8)   // one CTA's level histogram; also the scratch of select_bin / the final sort
 #define SEL_RETRIES 2               // queued extra rounds per step (no-ops unless the previous round asked for one)
 #define PF_MAX_RANKS 16
 
@@ -82,7 +73,7 @@ struct SelResult {
 };
 
 struct SelScratch {
-    // bracket state (written by CTA 0 of the cluster kernels, read by all after a barrier)
+    // bracket state (written by CTA 0 of the search kernels, read by all after a barrier)
     u64 lo, hi;
     int scale;
     int phase;                      // 2 descend, 3 another classify round is needed, 4 done, 6 sample solve finished, 8 plateau
@@ -129,10 +120,9 @@ struct SelScratch {
     // final list
     unsigned int final_n;
     double final_vals[SEL_FINAL_CAP];
-    // histogram of one descent level (cluster-reduced)
-    unsigned int h_cnt[SEL_BINS];
-    u64 h_sum[2][SEL_BINS];         // bin sum = h_sum[0] + h_sum[1] 2^32
-    unsigned long long dbg_t[32];   // globaltimer stamps of the last bracket (0..15) and solve (16..31) launch (debugging aid)
+    // histograms of the descent levels: three rotating buffers, all zero between launches
+    unsigned int h_cnt[3][SEL_BINS];
+    u64 h_sum[3][2][SEL_BINS];      // bin sum = h_sum[.][0] + h_sum[.][1] 2^32
 };
 enum { PF_HALT_SEARCH = 1,          // the threshold search needed more rounds than were queued
        PF_HALT_TIMEOUT = 2,         // a peer's flag did not arrive (sharded run)
@@ -231,7 +221,7 @@ __device__ inline void xch_signal(const Xch *x, int kind, unsigned long long seq
 // a u64 that a peer wrote into local memory: read it from L2 (never from a stale L1 line)
 __device__ __forceinline__ unsigned long long ld_peer(const unsigned long long *p) { return __ldcg(p); }
 
-// stages of the cluster kernels
+// stages of the search kernels (k_sel_bracket, k_sel_solve)
 enum { SEL_ST_PUB = 1,        // sharded: write the local list / header into the peers' regions and raise the flag
        SEL_ST_RUN = 2 };      // do the stage's work (sharded: after waiting for every rank's flag)
 
@@ -261,18 +251,12 @@ struct SelArgs {
     long long step;                 // index of this step (halt mark)
 };
 
-// the list a cluster kernel works on: one segment (single GPU) or one per rank (own exchange region)
+// the list a search kernel works on: one segment (single GPU) or one per rank (own exchange region)
 struct ListView {
-    const double *seg[PF_MAX_RANKS];    // 16-byte aligned
+    const double *seg[PF_MAX_RANKS];
     long long off[PF_MAX_RANKS + 1];    // exclusive prefix of the segment lengths
-    long long choff[PF_MAX_RANKS + 1];  // exclusive prefix of the segments' chunk counts (SEL_CH doubles per chunk)
     int nseg;
 };
-__device__ __forceinline__ void lv_finish(ListView &lv)
-{
-    lv.choff[0] = 0;
-    for (int r = 0; r < lv.nseg; r++) lv.choff[r + 1] = lv.choff[r] + (lv.off[r + 1] - lv.off[r] + SEL_CH - 1) / SEL_CH;
-}
 __device__ __forceinline__ u64 lv_load(const ListView &lv, long long t)
 {
     int s = 0;
@@ -280,10 +264,9 @@ __device__ __forceinline__ u64 lv_load(const ListView &lv, long long t)
     return (u64)__double_as_longlong(__ldcg(lv.seg[s] + (t - lv.off[s])));      // L2: peers may have written this memory
 }
 
-// Every thread of the cluster visits its share of the list, U independent loads in flight per thread (the
-// cluster kernels run on 16 SMs: without the batching every item would cost a full memory latency).
+// Every thread of the grid visits its share of the list, SEL_BATCH independent loads in flight per thread.
 // Padding entries (all-ones pattern) are skipped.
-#define SEL_BATCH 8
+#define SEL_BATCH 4
 template <class F>
 __device__ __forceinline__ void lv_for_each(const ListView &lv, long long start, long long step, F f)
 {
@@ -294,82 +277,6 @@ __device__ __forceinline__ void lv_for_each(const ListView &lv, long long start,
         for (int k = 0; k < SEL_BATCH; k++) { const long long t = t0 + k * step; b[k] = t < n ? lv_load(lv, t) : ~0ull; }
 #pragma unroll
         for (int k = 0; k < SEL_BATCH; k++) if (b[k] != ~0ull) f(b[k]);
-    }
-}
-
-// ---- streaming a list through shared memory: 1-D bulk copies (cp.async.bulk, the TMA unit) complete on an
-// mbarrier per ring stage; thread 0 keeps SEL_STAGES copies in flight, all threads consume.  16 SMs pull a
-// few MB this way at close to their share of the L2 bandwidth; per-thread loads would leave them latency-bound.
-__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity)
-{
-    unsigned int ok = 0;
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    }
-}
-// once per kernel, before the first pass
-__device__ __forceinline__ void stream_init(unsigned char *smem_raw)
-{
-    if (threadIdx.x == 0) {
-        const unsigned int bar0 = smem_u32(smem_raw + SELC_HIST_BYTES + SELC_RING_BYTES);
-        for (int s = 0; s < SEL_STAGES; s++) mbar_init(bar0 + 8 * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-}
-// One pass over the list: CTA c of the cluster takes chunks c, c + C, c + 2C, ...; f(chunk, len) is called by
-// ALL threads of the CTA with the chunk in shared memory (len valid entries).  `ph` carries the stages' phase
-// bits from pass to pass.
-template <class F>
-__device__ __forceinline__ void stream_pass(cg::cluster_group &cluster, const ListView &lv, unsigned char *smem_raw, unsigned int &ph, F f)
-{
-    double *ring = reinterpret_cast<double *>(smem_raw + SELC_HIST_BYTES);
-    const unsigned int bar0 = smem_u32(smem_raw + SELC_HIST_BYTES + SELC_RING_BYTES);
-    const long long nctas = cluster.num_blocks(), crank = cluster.block_rank();
-    const long long total = lv.choff[lv.nseg];
-    const long long mine = total > crank ? (total - crank + nctas - 1) / nctas : 0;
-    auto locate = [&](long long i, int &sg, long long &c, long long &len) {
-        const long long g = crank + i * nctas;
-        sg = 0;
-        while (sg + 1 < lv.nseg && g >= lv.choff[sg + 1]) sg++;
-        c = g - lv.choff[sg];
-        const long long n_s = lv.off[sg + 1] - lv.off[sg];
-        len = n_s - c * SEL_CH < SEL_CH ? n_s - c * SEL_CH : SEL_CH;
-    };
-    auto issue = [&](long long i) {
-        int sg; long long c, len;
-        locate(i, sg, c, len);
-        const unsigned int bytes = (unsigned int)((len * 8 + 15) & ~15ll);       // (lists have an even capacity: the pad stays inside)
-        const int st = (int)(i % SEL_STAGES);
-        mbar_expect_tx(bar0 + 8 * st, bytes);
-        bulk_g2s(smem_u32(ring + (long long)st * SEL_CH), lv.seg[sg] + c * SEL_CH, bytes, bar0 + 8 * st);
-    };
-    if (threadIdx.x == 0)
-        for (long long i = 0; i < mine && i < SEL_STAGES; i++) issue(i);
-    for (long long i = 0; i < mine; i++) {
-        int sg; long long c, len;
-        locate(i, sg, c, len);
-        const int st = (int)(i % SEL_STAGES);
-        mbar_wait(bar0 + 8 * st, (ph >> st) & 1u);
-        ph ^= 1u << st;
-        f(reinterpret_cast<const u64 *>(ring + (long long)st * SEL_CH), (int)len);
-        __syncthreads();                                   // everyone is done with the stage before it is refilled
-        if (threadIdx.x == 0 && i + SEL_STAGES < mine) issue(i + SEL_STAGES);
     }
 }
 
@@ -518,32 +425,44 @@ struct ChunkWriter {
     }
 };
 
-// One radix level on a cluster: every WARP histograms (count, fixed-point sum as two 64-bit words) the list items of
-// its CTA's chunks inside [blo, bhi) into its PRIVATE 1024-bin histogram in shared memory (bins of width 2^shift bit
-// patterns).  Lanes that hit the same bin are grouped (match.any), their items summed with three 32-bit warp
-// reductions (24-bit limbs) and the group's first lane updates the bin with plain loads and stores: no atomics
-// (64-bit shared-memory atomics are compare-and-swap loops and the first level's bins -- whole binades -- are hot).
-// Then the CTA folds its 8 copies, and CTA c of the cluster sums bins [c B/C, (c+1) B/C) over all CTAs through
-// distributed shared memory and writes the totals to sc->h_* (which select_bin reads).
-__device__ inline void hist_level(cg::cluster_group &cluster, const ListView &lv, u64 blo, u64 bhi, int shift, int scale,
-                                  SelScratch *sc, unsigned char *smem_raw, unsigned int &ph)
+// search state of the radix descent: identical in every CTA (each computes it from the same global histogram),
+// so a level needs only ONE grid barrier (after the histogram is complete); CTA 0 mirrors it to SelScratch
+struct SrchSt {
+    u64 lo, hi;
+    long long count_in, A_run, mult;
+    u128 B_run;
+    int phase;
+};
+
+// One radix level: every CTA histograms (count, fixed-point sum as two 64-bit words) its share of the list items
+// inside [blo, bhi) in shared memory (1024 bins of width 2^shift bit patterns) and adds its non-empty bins to the
+// level's global buffer `buf`.  Lanes of a warp that hit the same bin are grouped (match.any), their items summed
+// with three 32-bit warp reductions (24-bit limbs) and the group's first lane does the shared-memory atomics:
+// the first level's bins are whole binades, a handful of them hold most items, and 64-bit shared-memory atomics
+// are compare-and-swap loops.  CTA 0 also clears the buffer the NEXT level will use (three buffers rotate: the
+// one being cleared was last read two levels ago, before the previous barrier).
+__device__ inline void hist_level(const ListView &lv, u64 blo, u64 bhi, int shift, int scale, SelScratch *sc, int buf,
+                                  unsigned char *smem_raw)
 {
-    unsigned int *h_cnt = reinterpret_cast<unsigned int *>(smem_raw);                          // [warp][bin]
-    u64 *h_s0 = reinterpret_cast<u64 *>(smem_raw + SELC_WARPS * SEL_BINS * 4);                  // [warp][bin]: sum of q mod 2^32
-    u64 *h_s1 = h_s0 + SELC_WARPS * SEL_BINS;                                                  // [warp][bin]: sum of q >> 32
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned int nctas = cluster.num_blocks(), crank = cluster.block_rank();
-    {
-        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
-        for (int t = tid; t < SELC_HIST_BYTES / 16; t += SELC_THREADS) z[t] = make_uint4(0, 0, 0, 0);
+    unsigned int *h_cnt = reinterpret_cast<unsigned int *>(smem_raw);
+    u64 *h_s0 = reinterpret_cast<u64 *>(smem_raw + SEL_BINS * 4);
+    u64 *h_s1 = h_s0 + SEL_BINS;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int t = tid; t < SEL_BINS; t += SEL_THREADS) { h_cnt[t] = 0; h_s0[t] = 0; h_s1[t] = 0; }
+    if (blockIdx.x == 0) {
+        const int nb = (buf + 1) % 3;
+        for (int t = tid; t < SEL_BINS; t += SEL_THREADS) { sc->h_cnt[nb][t] = 0; sc->h_sum[nb][0][t] = 0; sc->h_sum[nb][1][t] = 0; }
     }
     __syncthreads();
-    unsigned int *wc = h_cnt + wid * SEL_BINS;
-    u64 *w0 = h_s0 + wid * SEL_BINS, *w1 = h_s1 + wid * SEL_BINS;
-    stream_pass(cluster, lv, smem_raw, ph, [&](const u64 *chunk, int len) {
-        for (int base = wid * 32; base < len; base += SELC_THREADS) {                          // (warp-uniform trip count)
-            const int idx = base + lane;
-            const u64 bits = idx < len ? chunk[idx] : ~0ull;
+    const long long n = lv.off[lv.nseg];
+    const long long step = (long long)gridDim.x * SEL_THREADS;
+    for (long long t0 = (long long)blockIdx.x * SEL_THREADS + (tid & ~31); t0 < n; t0 += step * SEL_BATCH) {      // (warp-uniform trip count)
+        u64 bb[SEL_BATCH];
+#pragma unroll
+        for (int k = 0; k < SEL_BATCH; k++) { const long long t = t0 + lane + k * step; bb[k] = t < n ? lv_load(lv, t) : ~0ull; }
+#pragma unroll
+        for (int k = 0; k < SEL_BATCH; k++) {
+            const u64 bits = bb[k];
             const bool in = bits >= blo && bits < bhi;
             if (!__any_sync(0xffffffffu, in)) continue;
             const int b = in ? (int)((bits - blo) >> shift) : -1 - lane;
@@ -552,116 +471,117 @@ __device__ inline void hist_level(cg::cluster_group &cluster, const ListView &lv
                 const u128 q = fx70(bits, scale);                                              // < 2^71
                 const int np = __popc(peers);
                 if (np == 1) {
-                    wc[b] += 1u; w0[b] += q.lo & 0xffffffffull; w1[b] += (q.lo >> 32) | (q.hi << 32);
+                    atomicAdd(&h_cnt[b], 1u);
+                    atomicAdd(&h_s0[b], q.lo & 0xffffffffull);
+                    atomicAdd(&h_s1[b], (q.lo >> 32) | (q.hi << 32));
                 } else {
                     const unsigned int s0 = __reduce_add_sync(peers, (unsigned int)(q.lo & 0xffffffu));
                     const unsigned int s1 = __reduce_add_sync(peers, (unsigned int)((q.lo >> 24) & 0xffffffu));
                     const unsigned int s2 = __reduce_add_sync(peers, (unsigned int)((q.lo >> 48) | (q.hi << 16)));
                     if (lane == __ffs(peers) - 1) {
                         const u128 tot = add128(add128(mk128(s0, 0), mk128((u64)s1 << 24, 0)), shl128(mk128(s2, 0), 48));
-                        wc[b] += (unsigned int)np; w0[b] += tot.lo & 0xffffffffull; w1[b] += (tot.lo >> 32) | (tot.hi << 32);
+                        atomicAdd(&h_cnt[b], (unsigned int)np);
+                        atomicAdd(&h_s0[b], tot.lo & 0xffffffffull);
+                        atomicAdd(&h_s1[b], (tot.lo >> 32) | (tot.hi << 32));
                     }
                 }
             }
-            __syncwarp();                                                                      // the next step may touch the same bin from another lane
         }
-    });
+    }
     __syncthreads();
-    for (int b = tid; b < SEL_BINS; b += SELC_THREADS) {                                        // fold the CTA's copies into copy 0
-        unsigned int c = 0; u64 s0 = 0, s1 = 0;
-#pragma unroll
-        for (int w = 0; w < SELC_WARPS; w++) { c += h_cnt[w * SEL_BINS + b]; s0 += h_s0[w * SEL_BINS + b]; s1 += h_s1[w * SEL_BINS + b]; }
-        h_cnt[b] = c; h_s0[b] = s0; h_s1[b] = s1;
-    }
-    cluster.sync();
-    const int per = SEL_BINS / (int)nctas;
-    for (int k = tid; k < per; k += SELC_THREADS) {
-        const int b = (int)crank * per + k;
-        unsigned int c = 0; u64 s0 = 0, s1 = 0;
-#pragma unroll 4
-        for (unsigned int r = 0; r < nctas; r++) {
-            c += cluster.map_shared_rank(h_cnt, r)[b];
-            s0 += cluster.map_shared_rank(h_s0, r)[b];
-            s1 += cluster.map_shared_rank(h_s1, r)[b];
+    for (int t = tid; t < SEL_BINS; t += SEL_THREADS)
+        if (h_cnt[t]) {
+            atomicAdd(&sc->h_cnt[buf][t], h_cnt[t]);
+            atomicAdd(&sc->h_sum[buf][0][t], h_s0[t]);
+            atomicAdd(&sc->h_sum[buf][1][t], h_s1[t]);           // bin sum = h_sum[0] + h_sum[1] 2^32
         }
-        sc->h_cnt[b] = c; sc->h_sum[0][b] = s0; sc->h_sum[1][b] = s1;          // bin sum = s0 + s1 2^32
-    }
     __threadfence();
-    cluster.sync();          // remote reads done before anyone reuses its shared memory; totals visible to CTA 0
 }
 
-// CTA 0 (all threads), after a histogram level: find the first bin whose UPPER boundary
-// satisfies the predicate and narrow the bracket to it.  With sampling != 0 the list is a
-// strided sample (sums and counts are multiplied by sc->mult): the level either narrows to
-// the bin and its two neighbours, or -- once the bin is finer than the sampling error --
-// ends the sample solve by widening the bin to `delta` sample items on each side
-// (sc->phase = 6).  Works on a shared-memory copy of the level's histogram.
-__device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi, int shift, int scale, int sampling,
-                                  unsigned char *smem_raw)
+__device__ __forceinline__ unsigned int block_excl_scan_u32(unsigned int v, unsigned int *smem_warp /* >= 33 */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) smem_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = lane < nw ? smem_warp[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
+        smem_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned int r = smem_warp[wid] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// After a histogram level (and the grid barrier behind it), in EVERY CTA, all threads: find the first bin whose
+// UPPER boundary satisfies the predicate and narrow the bracket to it.  With sampling != 0 the list is a strided
+// sample (sums and counts are multiplied by st->mult): the level either narrows to the bin and its two neighbours,
+// or -- once the bin is finer than the sampling error -- ends the sample solve by widening the bin to `delta`
+// sample items on each side (st->phase = 6).  Two bins per thread, block-wide prefix sums.
+__device__ inline void select_bin(SrchSt *st, const SelScratch *sc, int buf, long long N, u64 blo, u64 bhi, int shift, int scale,
+                                  int sampling, unsigned char *smem_raw, u128 *s_warp, unsigned int *s_wc)
 {
     unsigned int *pc = reinterpret_cast<unsigned int *>(smem_raw);            // inclusive count prefix
     u128 *ps = reinterpret_cast<u128 *>(smem_raw + SEL_BINS * 4);            // inclusive sum prefix
     __shared__ int s_found;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int b = tid; b < SEL_BINS; b += (int)blockDim.x) {
-        pc[b] = __ldcg(&sc->h_cnt[b]);
-        ps[b] = add128(mk128(__ldcg(&sc->h_sum[0][b]), 0), shl128(mk128(__ldcg(&sc->h_sum[1][b]), 0), 32));
+    const int tid = threadIdx.x;
+    constexpr int PER = SEL_BINS / SEL_THREADS;
+    u128 v[PER]; unsigned int c[PER];
+    u128 loc = mk128(0, 0); unsigned int lc = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int b = tid * PER + k;
+        c[k] = __ldcg(&sc->h_cnt[buf][b]);
+        v[k] = add128(mk128(__ldcg(&sc->h_sum[buf][0][b]), 0), shl128(mk128(__ldcg(&sc->h_sum[buf][1][b]), 0), 32));
+        loc = add128(loc, v[k]); lc += c[k];
     }
-    __syncthreads();
-    const int per = SEL_BINS / 32;
+    if (tid == 0) s_found = SEL_BINS;
+    u128 tot;
+    u128 pre = block_excl_scan128(loc, s_warp, &tot);
+    unsigned int prec = block_excl_scan_u32(lc, s_wc);
     const u64 width = bhi - blo;
-    const long long count_in = sc->count_in;
-    const long long mult = sc->mult;
-    const u128 B0 = sc->B_run; const long long A0 = sc->A_run;
+    const long long count_in = st->count_in;
+    const long long mult = st->mult;
+    const u128 B0 = st->B_run; const long long A0 = st->A_run;
     const int last_bin = (int)((width - 1) >> shift);
-    if (wid == 0) {
-        u128 ls = mk128(0, 0);
-        unsigned int lc = 0;
-        for (int k = 0; k < per; k++) { int b = lane * per + k; ls = add128(ls, ps[b]); lc += pc[b]; }
-        u128 inc = ls; unsigned int incc = lc;
+    int found = SEL_BINS;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u128 o = shfl_up128(inc, d);
-            unsigned int oc = __shfl_up_sync(0xffffffffu, incc, d);
-            if (lane >= d) { inc = add128(inc, o); incc += oc; }
+    for (int k = 0; k < PER; k++) {
+        const int b = tid * PER + k;
+        pre = add128(pre, v[k]); prec += c[k];
+        ps[b] = pre; pc[b] = prec;
+        if (b <= last_bin) {
+            u64 off = ((u64)(b + 1)) << shift;
+            u64 x = (off >= width) ? bhi : blo + off;
+            bool ok = (x >= PF_INF_BITS) ? true
+                                         : pred128(mul128_64(add128(B0, pre), (u64)mult), N, (A0 + (count_in - (long long)prec)) * mult,
+                                                   fx70(x, scale));
+            if (ok && found == SEL_BINS) found = b;
         }
-        u128 pre = sub128(inc, ls);
-        unsigned int prec = incc - lc;
-        int found = SEL_BINS;
-        for (int k = 0; k < per; k++) {
-            int b = lane * per + k;
-            pre = add128(pre, ps[b]); prec += pc[b];
-            ps[b] = pre; pc[b] = prec;
-            if (b <= last_bin) {
-                u64 off = ((u64)(b + 1)) << shift;
-                u64 x = (off >= width) ? bhi : blo + off;
-                bool ok = (x >= PF_INF_BITS) ? true
-                                             : pred128(mul128_64(add128(B0, pre), (u64)mult), N, (A0 + (count_in - (long long)prec)) * mult,
-                                                       fx70(x, scale));
-                if (ok && found == SEL_BINS) found = b;
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, d));
-        if (found > last_bin) found = last_bin;
-        if (lane == 0) s_found = found;
     }
+    if (found < SEL_BINS) atomicMin(&s_found, found);
     __syncthreads();
     if (tid == 0) {
-        const int found = s_found;
-        int b_lo = found, b_hi = found;
+        int f = s_found;
+        if (f > last_bin) f = last_bin;
+        int b_lo = f, b_hi = f;
         int next_phase = 2;
-        const long long cnt_found = (long long)pc[found] - (found > 0 ? (long long)pc[found - 1] : 0);
+        const long long cnt_found = (long long)pc[f] - (f > 0 ? (long long)pc[f - 1] : 0);
         if (sampling) {
-            const long long above = A0 + (count_in - (long long)pc[found]) + cnt_found;
+            const long long above = A0 + (count_in - (long long)pc[f]) + cnt_found;
             const long long delta = (long long)((double)sampling * sqrt((double)(above > 1 ? above : 1))) + 4 * sampling;   // `sampling` = margin in sigmas (8)
             if (cnt_found > 2 * delta && shift > 0) {
-                b_lo = found > 0 ? found - 1 : 0;
-                b_hi = found < last_bin ? found + 1 : last_bin;
+                b_lo = f > 0 ? f - 1 : 0;
+                b_hi = f < last_bin ? f + 1 : last_bin;
             } else {
-                const long long below_found = found > 0 ? (long long)pc[found - 1] : 0;
+                const long long below_found = f > 0 ? (long long)pc[f - 1] : 0;
                 while (b_lo > 0 && below_found - (b_lo > 0 ? (long long)pc[b_lo - 1] : 0) < delta) b_lo--;
-                while (b_hi < last_bin && (long long)pc[b_hi] - (long long)pc[found] < delta) b_hi++;
+                while (b_hi < last_bin && (long long)pc[b_hi] - (long long)pc[f] < delta) b_hi++;
                 next_phase = 6;
             }
         }
@@ -671,13 +591,21 @@ __device__ inline void select_bin(SelScratch *sc, long long N, u64 blo, u64 bhi,
         const u64 nlo = blo + (((u64)b_lo) << shift);
         const u64 off = ((u64)(b_hi + 1)) << shift;
         const u64 nhi = (off >= width) ? bhi : blo + off;
-        sc->B_run = add128(B0, before);
-        sc->A_run = A0 + (count_in - cbefore - cin);
-        sc->lo = nlo; sc->hi = nhi; sc->count_in = cin;
-        sc->phase = next_phase;
-        __threadfence();
+        st->B_run = add128(B0, before);
+        st->A_run = A0 + (count_in - cbefore - cin);
+        st->lo = nlo; st->hi = nhi; st->count_in = cin;
+        st->phase = next_phase;
     }
     __syncthreads();
+}
+
+// all CTAs: clear the three histogram buffers (after a grid barrier that follows the last bin selection)
+__device__ __forceinline__ void hist_clear(SelScratch *sc)
+{
+    unsigned int *c = &sc->h_cnt[0][0];
+    u64 *s = &sc->h_sum[0][0][0];
+    for (long long t = (long long)blockIdx.x * SEL_THREADS + threadIdx.x; t < 3 * SEL_BINS; t += (long long)gridDim.x * SEL_THREADS) c[t] = 0;
+    for (long long t = (long long)blockIdx.x * SEL_THREADS + threadIdx.x; t < 6 * SEL_BINS; t += (long long)gridDim.x * SEL_THREADS) s[t] = 0;
 }
 
 __device__ inline void reset_round(SelScratch *sc)
@@ -729,21 +657,15 @@ __device__ __forceinline__ void sel_halt(SelScratch *sc, long long step, int rea
     if (!sc->halt) { sc->halt = step + 1; sc->halt_reason = reason; }
 }
 
-// sharded: all threads of the cluster copy `n` doubles of the local list into segment `rank` of every region
-__device__ inline void xch_copy_list(cg::cluster_group &cluster, const Xch *x, const double *src, long long n, int kind, int parity)
+// sharded: all threads of the grid copy `n` doubles of the local list into segment `rank` of every region
+__device__ inline void xch_copy_list(const Xch *x, const double *src, long long n, int kind, int parity)
 {
-    const long long nth = (long long)cluster.num_blocks() * SELC_THREADS;
-    const long long t0 = (long long)cluster.block_rank() * SELC_THREADS + threadIdx.x;
+    const long long nth = (long long)gridDim.x * SEL_THREADS;
+    const long long t0 = (long long)blockIdx.x * SEL_THREADS + threadIdx.x;
     for (int p = 0; p < x->nranks; p++) {
         double *dst = kind == XCH_A ? xch_listA(x->reg[p], x->capA, x->rank)
                                     : xch_listB(x->reg[p], x->nranks, x->capA, x->capB, parity, x->rank);
-        for (long long t = t0; t < n; t += nth * SEL_BATCH) {
-            double v[SEL_BATCH];
-#pragma unroll
-            for (int k = 0; k < SEL_BATCH; k++) v[k] = t + k * nth < n ? src[t + k * nth] : 0.0;
-#pragma unroll
-            for (int k = 0; k < SEL_BATCH; k++) if (t + k * nth < n) dst[t + k * nth] = v[k];
-        }
+        for (long long t = t0; t < n; t += nth) dst[t] = src[t];
     }
     __threadfence_system();
 }
@@ -799,30 +721,30 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_sample(SelArgs a)
     if (lane == 0 && cnt_s) { atomicAdd(&sc->n_cand, cnt_s); atomicMax(&sc->vs_bits, vs_max); }
 }
 
-// ------------------------------------------------------------------ k_sel_bracket (one cluster)
-__global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_bracket(SelArgs a)
+// ------------------------------------------------------------------ k_sel_bracket (cooperative grid)
+__global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_bracket(SelArgs a)
 {
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) unsigned char smem_raw[SEL_SMEM_BYTES];
     __shared__ ListView s_lv;
+    __shared__ SrchSt s_st;
+    __shared__ u128 s_warp[33];
+    __shared__ unsigned int s_wc[33];
     SelScratch *sc = a.sc;
     SelResult *res = a.res;
     const Xch *x = a.x;
     if (sc->halt) return;
     const int tid = threadIdx.x;
-    const bool lead = cluster.block_rank() == 0 && tid == 0;
+    const bool lead = blockIdx.x == 0 && tid == 0;
     const long long N = a.N;
 
-    int dbg_k = 0;
-#define DBG_STAMP(base) do { if (lead && dbg_k < 16) sc->dbg_t[(base) + dbg_k++] = gtimer(); } while (0)
-    DBG_STAMP(0);
     // ---- the sample: local list, or (sharded) every rank's list gathered through the exchange regions
     if (x) {
         if (a.stage & SEL_ST_PUB) {
             const long long ns = sc->list_n;
             const long long n_pub = ns <= x->capA ? ns : x->capA;
-            xch_copy_list(cluster, x, a.cand, n_pub, XCH_A, 0);
-            cluster.sync();
+            xch_copy_list(x, a.cand, n_pub, XCH_A, 0);
+            grid.sync();
             if (lead) {
                 XchHdrA hd; hd.n = (unsigned long long)n_pub; hd.vmax = *a.vmax_bits; hd.M_pred = (unsigned long long)*a.M;
                 hd.overflow = ns > x->capA ? 1ull : 0ull;
@@ -847,7 +769,7 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_bracket(SelArgs a)
             sc->gM = gM; sc->gvmax = gv;
             __threadfence();
         }
-        cluster.sync();
+        grid.sync();
         if (sc->halt) return;
         if (tid == 0) {
             const XchHdrA *ha = x->reg[x->rank]->a;
@@ -858,25 +780,21 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_bracket(SelArgs a)
             }
         }
     } else {
-        if (lead) { sc->gM = *a.M; sc->gvmax = *a.vmax_bits; __threadfence(); }
-        cluster.sync();
         if (tid == 0) {
             s_lv.nseg = 1; s_lv.seg[0] = a.cand; s_lv.off[0] = 0;
             s_lv.off[1] = a.external_sample ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
         }
     }
-    if (tid == 0) lv_finish(s_lv);
-    stream_init(smem_raw);
-    unsigned int ph = 0;
-    const long long M = sc->gM;
-    const u64 vmax = sc->gvmax;                         // (external sample: the sample's maximum)
+    __syncthreads();
+    const long long M = x ? sc->gM : *a.M;
+    const u64 vmax = x ? sc->gvmax : *a.vmax_bits;      // (external sample: the sample's maximum)
     const int vmax_scale = SEL_ITEM_BITS - exp_of_bits(vmax);
     const bool trivial = a.external_sample ? (M <= N) : (M <= N || vmax == 0);
     const bool sampled = a.external_sample ? !trivial : (!trivial && M > SEL_FINAL_CAP);
-    const long long stride = a.fixed_stride;
     const long long ns_total = s_lv.off[s_lv.nseg];
-    cluster.sync();                                     // every CTA has read the sample's size before the lead resets the counters
-    DBG_STAMP(0);
+    const unsigned long long n_cand0 = a.external_sample ? (unsigned long long)ns_total : sc->n_cand;   // sample items (classic: counted by k_sel_sample)
+    const u64 vs_bits = a.external_sample ? vmax : sc->vs_bits;
+    grid.sync();                                        // every CTA has read the sample's size / counters before the lead resets them
 
     if (lead) {
         if (a.external_sample) {
@@ -886,36 +804,36 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_bracket(SelArgs a)
             res->rounds = 0; res->status = 0; res->n_cand_first = 0; res->n_plateau_first = 0; sc->n_fail = 0;
             res->t_ns[0] = gtimer();
             sc->need_tot = 1; sc->fuse_valid = 0; sc->fuse_overflow = 0; sc->tiles_ok = 0;
-            sc->n_cand = (unsigned long long)ns_total; sc->vs_bits = vmax;
+            sc->vs_bits = vmax;
         }
+        if (!x) { sc->gM = M; sc->gvmax = vmax; }
         sc->mult = 1;
         // keep everything (src/fearnhead.jl:135-138): lo = hi = 0 puts every putative on the kept side, whose sum is the
         // (practically) exact one -- the step's total weight does not depend on a bracket scale
         if (trivial) { sc->lo = 0; sc->hi = 0; sc->scale = vmax_scale; sc->mode = 1; }
         else { sc->lo = 1; sc->hi = PF_INF_BITS; sc->scale = vmax_scale; sc->mode = 0; }                     // direct solve, or the sample solve's start
-        if (sampled) { sc->B_run = mk128(0, 0); sc->A_run = 0; sc->count_in = (long long)sc->n_cand; sc->mult = stride; sc->phase = 2; }
-        __threadfence();
     }
-    cluster.sync();
     if (sampled) {
-        const int ss = SEL_ITEM_BITS - exp_of_bits(sc->vs_bits);     // the sample solve runs at the sample's own scale
+        // the sample solve: every CTA keeps the same search state; one grid barrier per level
+        if (tid == 0) { s_st.lo = 1; s_st.hi = PF_INF_BITS; s_st.count_in = (long long)n_cand0; s_st.A_run = 0; s_st.mult = a.fixed_stride; s_st.B_run = mk128(0, 0); s_st.phase = 2; }
+        __syncthreads();
+        const int ss = SEL_ITEM_BITS - exp_of_bits(vs_bits);         // the sample solve runs at the sample's own scale
         for (int level = 0; level < 8; level++) {
-            const u64 blo = sc->lo, bhi = sc->hi;
-            if (sc->count_in == 0 || (bhi - blo) <= 1) break;
+            const u64 blo = s_st.lo, bhi = s_st.hi;
+            if (s_st.count_in == 0 || (bhi - blo) <= 1) break;
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            DBG_STAMP(0);
-            hist_level(cluster, s_lv, blo, bhi, shift, ss, sc, smem_raw, ph);
-            DBG_STAMP(0);
-            if (cluster.block_rank() == 0) select_bin(sc, N, blo, bhi, shift, ss, a.margin > 0 ? a.margin : 8, smem_raw);
-            cluster.sync();
-            DBG_STAMP(0);
-            if (sc->phase == 6) break;
+            __syncthreads();
+            hist_level(s_lv, blo, bhi, shift, ss, sc, level % 3, smem_raw);
+            grid.sync();
+            select_bin(&s_st, sc, level % 3, N, blo, bhi, shift, ss, a.margin > 0 ? a.margin : 8, smem_raw, s_warp, s_wc);
+            if (s_st.phase == 6) break;
         }
-        cluster.sync();                                 // everyone has left the loop before the lead rewrites the bracket
+        grid.sync();                                    // every CTA is done with the histogram buffers
+        hist_clear(sc);
         if (lead) {
-            u64 lo = sc->lo, hi = sc->hi;
+            u64 lo = s_st.lo, hi = s_st.hi;
             if (lo < 1) lo = 1;
             if (hi <= lo) hi = lo + 1;
             sc->lo = lo; sc->hi = hi; sc->mode = 0; sc->mult = 1; sc->n_fail = 0;
@@ -932,7 +850,6 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_bracket(SelArgs a)
         reset_round(sc);                                 // the classic rounds start from a clean slate
     }
     if (lead) { sc->phase = 0; res->t_ns[1] = gtimer(); }
-    DBG_STAMP(0);
 }
 
 // ------------------------------------------------------------------ k_sel_classify (full grid)
@@ -1005,17 +922,19 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) k_sel_classify(SelArgs a)
     }
 }
 
-// ------------------------------------------------------------------ k_sel_solve (one cluster)
-__global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
+// ------------------------------------------------------------------ k_sel_solve (cooperative grid)
+__global__ void __launch_bounds__(SEL_THREADS, 1) k_sel_solve(SelArgs a)
 {
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) unsigned char smem_raw[SEL_SMEM_BYTES];
     u64 *s_u64 = reinterpret_cast<u64 *>(smem_raw);               // SEL_FINAL_CAP u64 for the final sort
     __shared__ ListView s_lv;
+    __shared__ SrchSt s_st;
     __shared__ u128 s_warp[33];
+    __shared__ unsigned int s_wc[33];
     __shared__ long long s_ll[4];
-    __shared__ u128 s_red[SELC_WARPS];
-    __shared__ unsigned long long s_redc[SELC_WARPS];
+    __shared__ u128 s_red[SEL_WARPS];
+    __shared__ unsigned long long s_redc[SEL_WARPS];
 
     SelScratch *sc = a.sc;
     SelResult *res = a.res;
@@ -1023,15 +942,12 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
     if (sc->halt) return;
     if (a.retry && sc->phase != 3) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned int nctas = cluster.num_blocks(), crank = cluster.block_rank();
-    const bool lead = crank == 0 && tid == 0;
+    const bool lead = blockIdx.x == 0 && tid == 0;
     const long long N = a.N;
     const int round = a.retry ? res->rounds : 0;
     const bool pre_round = !a.retry && a.preclassified && sc->fuse_valid;      // the expansion kernel classified this round
     const u64 plateau = a.plateau_ptr ? *a.plateau_ptr : 0ull;
 
-    int dbg_k = 0;
-    DBG_STAMP(16);
     // ---- the candidate list and the accumulators: local, or (sharded) gathered through the exchange regions
     if (x) {
         const int parity = round & 1;
@@ -1039,8 +955,8 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
         if (a.stage & SEL_ST_PUB) {
             const long long nl = sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
             const long long n_pub = nl <= x->capB ? nl : x->capB;
-            xch_copy_list(cluster, x, a.cand, n_pub, XCH_B, parity);
-            cluster.sync();
+            xch_copy_list(x, a.cand, n_pub, XCH_B, parity);
+            grid.sync();
             if (lead) {
                 SelAcc hd = *reinterpret_cast<const SelAcc *>(reinterpret_cast<const char *>(sc) + SEL_ACC_OFFSET);
                 hd.cand_chunks = (unsigned long long)n_pub;            // entries of this rank's segment
@@ -1071,7 +987,7 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
             } else sel_halt(sc, a.step, PF_HALT_TIMEOUT);
             __threadfence();
         }
-        cluster.sync();
+        grid.sync();
         if (sc->halt) return;
         if (tid == 0) {
             const SelAcc *g = x->reg[x->rank]->b[parity];
@@ -1082,32 +998,27 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
             }
         }
     } else {
-        if (lead) { sc->gM = *a.M; sc->gvmax = *a.vmax_bits; __threadfence(); }
-        cluster.sync();
         if (tid == 0) {
             s_lv.nseg = 1; s_lv.seg[0] = a.cand; s_lv.off[0] = 0;
             s_lv.off[1] = sc->list_exact ? sc->list_n : (long long)sc->cand_chunks * SEL_CHUNK;
         }
     }
-    if (tid == 0) lv_finish(s_lv);
-    stream_init(smem_raw);
-    unsigned int ph = 0;
-    const long long M = sc->gM;
-    const u64 vmax = sc->gvmax;
+    __syncthreads();
+    const long long M = x ? sc->gM : *a.M;
+    const u64 vmax = x ? sc->gvmax : *a.vmax_bits;
     const int vmax_scale = SEL_ITEM_BITS - exp_of_bits(vmax);
     const bool trivial = (M <= N || vmax == 0);
-    const long long list_n = s_lv.off[s_lv.nseg];
 
     const u64 lo = sc->lo, hi = sc->hi;
     const int scale = sc->scale;
     const int mode = sc->mode;
     const bool keep_all = (mode == 1);
     const bool need_tot = sc->need_tot != 0;
-    cluster.sync();                          // everyone has read the round's bracket before CTA 0 may change it
-    DBG_STAMP(16);
+    grid.sync();                             // everyone has read the round's bracket before CTA 0 may change it
 
     // ---- CTA 0: verify the bracket, start the descent
     if (lead) {
+        if (!x) { sc->gM = M; sc->gvmax = vmax; }
         res->rounds = round + 1;
         // fused path: the expansion's classification is unusable if a block overflowed its candidate
         // buffer or the true maximum lies more than 46 binades above hi (kept-side scale not exact)
@@ -1168,28 +1079,25 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
         sc->phase = phase;
         __threadfence();
     }
-    cluster.sync();
+    grid.sync();
     if (sc->phase == 8) {
         // ---- plateau resolution: mass and count of the candidates below the plateau value P, then the
         // predicate at P itself; the bracket shrinks to [lo, P) or (P, hi) and never contains the tie
         u128 sb = mk128(0, 0);
         unsigned long long cb = 0;
-        stream_pass(cluster, s_lv, smem_raw, ph, [&](const u64 *chunk, int len) {
-            for (int idx = tid; idx < len; idx += SELC_THREADS) {
-                const u64 bits = chunk[idx];
-                if (bits >= lo && bits < plateau) { cb++; sb = add128(sb, fx70(bits, scale)); }
-            }
+        lv_for_each(s_lv, (long long)blockIdx.x * SEL_THREADS + tid, (long long)gridDim.x * SEL_THREADS, [&](u64 bits) {
+            if (bits >= lo && bits < plateau) { cb++; sb = add128(sb, fx70(bits, scale)); }
         });
         sb = warp_sum128(sb); cb = warp_sum64(cb);
         if (lane == 0) { s_red[wid] = sb; s_redc[wid] = cb; }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < SELC_WARPS; w++) { sb = add128(sb, s_red[w]); cb += s_redc[w]; }
+            for (int w = 1; w < SEL_WARPS; w++) { sb = add128(sb, s_red[w]); cb += s_redc[w]; }
             if (cb) atomicAdd(&sc->pl_cnt, cb);
             atomic_add_acc(&sc->pl_sum, sb);
             __threadfence();
         }
-        cluster.sync();
+        grid.sync();
         if (lead) {
             const long long np = (long long)sc->n_plateau, cbt = (long long)sc->pl_cnt;
             const u128 qP = fx70(plateau, scale);
@@ -1200,25 +1108,23 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
             sc->phase = 2;
             __threadfence();
         }
-        cluster.sync();
+        grid.sync();
     }
-    DBG_STAMP(16);
     if (sc->phase == 3) return;              // a queued retry round (k_sel_classify + k_sel_solve) takes over
 
     if (sc->phase == 2) {
-        // ---- radix descent over the candidate list
+        // ---- radix descent over the candidate list: every CTA keeps the same search state, one grid barrier per level
+        if (tid == 0) { s_st.lo = sc->lo; s_st.hi = sc->hi; s_st.count_in = sc->count_in; s_st.A_run = sc->A_run; s_st.mult = 1; s_st.B_run = sc->B_run; s_st.phase = 2; }
+        __syncthreads();
+        int levels = 0;
         for (int level = 0; level < 8; level++) {
-            const u64 blo = sc->lo, bhi = sc->hi;
-            const long long count_in = sc->count_in;
-            if (count_in <= SEL_FINAL_CAP) {
+            const u64 blo = s_st.lo, bhi = s_st.hi;
+            if (s_st.count_in <= SEL_FINAL_CAP) {
                 // compact the bracket's items into the final list
-                stream_pass(cluster, s_lv, smem_raw, ph, [&](const u64 *chunk, int len) {
-                    for (int idx = tid; idx < len; idx += SELC_THREADS) {
-                        const u64 bits = chunk[idx];
-                        if (bits >= blo && bits < bhi) {
-                            unsigned int pos = atomicAdd(&sc->final_n, 1u);
-                            if (pos < SEL_FINAL_CAP) sc->final_vals[pos] = __longlong_as_double((long long)bits);
-                        }
+                lv_for_each(s_lv, (long long)blockIdx.x * SEL_THREADS + tid, (long long)gridDim.x * SEL_THREADS, [&](u64 bits) {
+                    if (bits >= blo && bits < bhi) {
+                        unsigned int pos = atomicAdd(&sc->final_n, 1u);
+                        if (pos < SEL_FINAL_CAP) sc->final_vals[pos] = __longlong_as_double((long long)bits);
                     }
                 });
                 __threadfence();
@@ -1228,22 +1134,21 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
             const u64 width = bhi - blo;
             int shift = 0;
             while (((width - 1) >> shift) >= SEL_BINS) shift++;
-            DBG_STAMP(16);
-            hist_level(cluster, s_lv, blo, bhi, shift, scale, sc, smem_raw, ph);
-            DBG_STAMP(16);
-            if (crank == 0) select_bin(sc, N, blo, bhi, shift, scale, 0, smem_raw);
-            cluster.sync();
-            DBG_STAMP(16);
+            __syncthreads();
+            hist_level(s_lv, blo, bhi, shift, scale, sc, level % 3, smem_raw);
+            grid.sync();
+            select_bin(&s_st, sc, level % 3, N, blo, bhi, shift, scale, 0, smem_raw, s_warp, s_wc);
+            levels++;
         }
-        cluster.sync();
-        DBG_STAMP(16);
+        grid.sync();                          // final list complete; every CTA is done with the histogram buffers
+        if (levels) hist_clear(sc);
 
         // ---- CTA 0: exact solve on the final list
-        if (crank == 0) {
-            const u64 blo = sc->lo, bhi = sc->hi;
-            const long long count_in = sc->count_in;
-            const u128 B0 = sc->B_run;
-            const long long A0 = sc->A_run;
+        if (blockIdx.x == 0) {
+            const u64 blo = s_st.lo, bhi = s_st.hi;
+            const long long count_in = s_st.count_in;
+            const u128 B0 = s_st.B_run;
+            const long long A0 = s_st.A_run;
             if (count_in > SEL_FINAL_CAP) {
                 // (bhi - blo) == 1: count_in copies of the single value blo
                 if (tid == 0) {
@@ -1257,10 +1162,10 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
             } else {
                 int nf = (int)count_in;
                 int np2 = 2; while (np2 < nf) np2 <<= 1;
-                for (int t = tid; t < np2; t += SELC_THREADS) s_u64[t] = t < nf ? (u64)__double_as_longlong(__ldcg(&sc->final_vals[t])) : ~0ull;
+                for (int t = tid; t < np2; t += SEL_THREADS) s_u64[t] = t < nf ? (u64)__double_as_longlong(__ldcg(&sc->final_vals[t])) : ~0ull;
                 __syncthreads();
                 bitonic_sort_smem(s_u64, np2);
-                const int per = SEL_FINAL_CAP / SELC_THREADS;
+                const int per = SEL_FINAL_CAP / SEL_THREADS;
                 u128 loc = mk128(0, 0);
                 for (int k = 0; k < per; k++) { int t = tid * per + k; if (t < nf) loc = add128(loc, fx70(s_u64[t], scale)); }
                 u128 tot;
@@ -1295,6 +1200,7 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
                 const u64 thr = (u64)s_ll[1];
                 const long long A = s_ll[2];
                 const u128 T = s_warp[0];
+                sc->lo = blo; sc->hi = bhi; sc->count_in = count_in; sc->B_run = B0; sc->A_run = A0;      // (mirror of the search state)
                 // precision: the scale must sit within 8 binades of the threshold
                 bool precise = (thr >= PF_INF_BITS) ? (scale == vmax_scale) : ((SEL_ITEM_BITS - scale) - exp_of_bits(thr) <= 8);
                 if (!precise && round < 30) {
@@ -1316,8 +1222,7 @@ __global__ void __launch_bounds__(SELC_THREADS, 1) k_sel_solve(SelArgs a)
                 __threadfence();
             }
         }
-        cluster.sync();
-        DBG_STAMP(16);
+        grid.sync();
         if (sc->phase != 4) return;
     }
 
