@@ -178,6 +178,17 @@ __host__ __device__ __forceinline__ void tooth_step(u128 &Q, unsigned int &R, u1
 }
 // number k of teeth of the tile passed by S >= S0 (so t0 + k teeth are passed in all), with (Q, R) of
 // tooth t0 + k: k from a floating-point estimate, corrected exactly in both directions
+// x / n and x % n for x < 2^63 and a 32-bit n > 0 whose quotient is small (< 2^20): a double-precision
+// estimate corrected by one step either way (two 64-bit divisions are ~200 instructions on the GPU)
+__host__ __device__ __forceinline__ u64 divmod_small(u64 x, unsigned int n32, unsigned int *rem)
+{
+    u64 q = (u64)((double)x / (double)n32);
+    long long r = (long long)(x - q * (u64)n32);
+    if (r < 0) { q--; r += n32; }
+    else if (r >= (long long)n32) { q++; r -= n32; }
+    *rem = (unsigned int)r;
+    return q;
+}
 __host__ __device__ __forceinline__ u64 tooth_seek(u128 Q0, unsigned int R0, double inv, u128 S, u128 Tq, unsigned int Tr,
                                                    unsigned int n32, u128 &Q, unsigned int &R)
 {
@@ -185,15 +196,18 @@ __host__ __device__ __forceinline__ u64 tooth_seek(u128 Q0, unsigned int R0, dou
     if (lt128(Q0, S)) {
         k = (u64)(to_double128(sub128(S, Q0)) * inv);
         u64 x = (u64)R0 + k * (u64)Tr;
-        Q = add128(add128(Q0, mul128_64(Tq, k)), mk128(x / n32, 0)); R = (unsigned int)(x % n32);
+        if (k < (1ull << 20)) { unsigned int rr; const u64 qq = divmod_small(x, n32, &rr); Q = add128(add128(Q0, mul128_64(Tq, k)), mk128(qq, 0)); R = rr; }
+        else { Q = add128(add128(Q0, mul128_64(Tq, k)), mk128(x / n32, 0)); R = (unsigned int)(x % n32); }
         if (lt128(Q, S)) {
             do { k++; tooth_step(Q, R, Tq, Tr, n32); } while (lt128(Q, S));
         } else {
             while (k > 0) {
                 x = (u64)R0 + (k - 1) * (u64)Tr;
-                u128 Qp = add128(add128(Q0, mul128_64(Tq, k - 1)), mk128(x / n32, 0));
+                unsigned int rp;
+                const u64 qp = (k - 1 < (1ull << 20)) ? divmod_small(x, n32, &rp) : (rp = (unsigned int)(x % n32), x / n32);
+                u128 Qp = add128(add128(Q0, mul128_64(Tq, k - 1)), mk128(qp, 0));
                 if (lt128(Qp, S)) break;
-                k--; Q = Qp; R = (unsigned int)(x % n32);
+                k--; Q = Qp; R = rp;
             }
         }
     }

@@ -103,13 +103,14 @@ struct TileSum {           // survivor-scan record of one tile of SCAN_THREADS p
 struct TileFuse {
     unsigned int cand_off, cand_cnt, n_plateau, pad;
 };
-// Per-particle record of the fused expansion for the survivor scan (optional): the fixed-point mass of
-// the particle's putatives below the bracket, and a word with the slots that fell INSIDE the bracket
-// (bits 0..23, candidates and plateau copies) and the number of putatives above it (bits 24..31).
-// k_scan_apply then needs V only for the in-bracket slots when it forms the particle's (mass, kept) pair.
+// Per-particle record of the fused expansion for the survivor scan: the fixed-point mass of the particle's
+// putatives below the bracket (< 2^77: 120 bits are plenty) with the number of putatives above the bracket
+// in the top byte, and a 64-bit mask of the slots that fell INSIDE the bracket (candidates and plateau
+// copies).  k_scan_apply then needs V only for the in-bracket slots (~0.5 % of the putatives) when it
+// forms the particle's exact (mass, kept) pair.
 struct ScanRec {
     ulonglong2 *x;
-    unsigned int *m;
+    unsigned long long *m;
 };
 
 #ifndef PF_EXPAND_MINBLOCKS
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
     u64 vmax = 0;
     long long myM = 0, myOvf = 0;
     u128 B_lo = mk128(0, 0), Tot = mk128(0, 0);
-    unsigned int kept_hi = 0, n_plat = 0, in_mask = 0;
+    unsigned int kept_hi = 0, n_plat = 0;
+    unsigned long long in_mask = 0;
     const u64 plateau = scp->plateau_bits;
     // what happens to one putative weight
     auto emit = [&](int j, double v) {
@@ -176,11 +178,11 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
                 B_lo = add128(B_lo, fx70(b, scale));
             } else if (b == plateau) {
                 n_plat++;                                          // the mass tie: counted, not listed
-                in_mask |= 1u << (j & 31);
+                in_mask |= 1ull << j;
             } else {
                 unsigned int pos = atomicAdd(&s_ncand, 1u);
                 if (pos < CAND_CAP) s_cand[pos] = b;
-                in_mask |= 1u << (j & 31);
+                in_mask |= 1ull << j;
             }
         }
     };
@@ -219,8 +221,8 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
         if (MODE != 1) cnt[i] = (unsigned char)c;
         myM = c;
         if (MODE == 2 && fused && rec.x) {
-            rec.x[i] = make_ulonglong2(B_lo.lo, B_lo.hi);
-            rec.m[i] = in_mask | (kept_hi << 24);
+            rec.x[i] = make_ulonglong2(B_lo.lo, B_lo.hi | ((u64)kept_hi << 56));
+            rec.m[i] = in_mask;
         }
     }
     // ---- block epilogue
@@ -581,11 +583,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
         myX = mk128(0, 0); myKept = 0;
         if (c) {
             const ulonglong2 x = rec.x[i];
-            unsigned int m = rec.m[i];
-            myKept = m >> 24; m &= 0xFFFFFFu;
-            if (comb) myX = mk128(x.x, x.y);
+            unsigned long long m = rec.m[i];
+            myKept = (unsigned int)(x.y >> 56);
+            if (comb) myX = mk128(x.x, x.y & 0x00FFFFFFFFFFFFFFull);
             while (m) {
-                const int j = __ffs(m) - 1; m &= m - 1;
+                const int j = __ffsll((long long)m) - 1; m &= m - 1;
                 const u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
                 if (bits >= thr) myKept++;
                 else if (comb) myX = add128(myX, fx70(bits, scale));
@@ -626,34 +628,82 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
         t = s_t0 + tooth_seek(s_Q0, s_R0, s_inv, S, Tq, Tr, n32, Q, R);
         tooth_inside = lt128(Q, add128(S, myX));
     }
-    if (!__any_sync(0xffffffffu, tooth_inside)) {
-        // no tooth lands in this warp's particles: only kept candidates produce survivors (warp-uniform branch)
-        if (myKept == 0 || mode == 1) return;
+    if (!__any_sync(0xffffffffu, tooth_inside) && (mode == 1 || !__any_sync(0xffffffffu, myKept != 0))) return;      // nothing to list in this warp
+    // The walk over the particle's putatives: kept ones are listed; for the low ones the question "has the running
+    // mass passed the next tooth?" is Q - S_particle < (sum of the q_j so far).  It is asked in double precision
+    // first -- the items' values scaled by 2^scale, summed with DADD, against D = (double)(Q - S_particle) -- and the
+    // answer is taken only when it clears the rounding error by a wide margin (the integer q_j = floor(v_j 2^scale)
+    // differ from the scaled doubles by < 1 each, the doubles by 2^-53 relative); a lane that comes closer than
+    // that (or meets a subnormal weight) redoes its particle in exact 128-bit arithmetic.  Decisions are those of
+    // the exact walk; the common case costs one DADD per putative instead of a 128-bit conversion, add and compare.
+    // The putatives are fetched eight at a time (independent loads in flight: the pass streams V from HBM once).
+    const long long kcount0 = kcount;
+    const u64 t_first = t;
+    const u128 Q_first = Q; const unsigned int R_first = R;
+    bool amb = false;
+    {
+        double cum = 0.0;
+        double Dd = tooth_inside ? to_double128(sub128(Q, S)) : 0.0;
+        const long long sadd = (long long)scale << 52;
+        int cmax = c;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
+        for (int j0 = 0; j0 < cmax; j0 += 8) {
+            u64 vb[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) vb[k] = (j0 + k < c) ? (u64)__double_as_longlong(V[(long long)(j0 + k) * cap + i]) : 0ull;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int j = j0 + k;
+                const u64 bits = vb[k];
+                if (j >= c || amb) continue;
+                if (bits >= thr) {
+                    if (mode != 1) {
+                        long long pos = kcount + (long long)t;
+                        if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
+                    }
+                    kcount++;
+                } else if (tooth_inside && bits != 0) {
+                    const long long eb = (long long)(bits >> 52) + scale;           // exponent field of v 2^scale
+                    if ((bits >> 52) == 0 || eb <= 0 || eb >= 2046) { amb = true; continue; }
+                    cum += __longlong_as_double((long long)bits + sadd);              // v_j 2^scale, exact
+                    for (;;) {
+                        const double diff = cum - Dd;
+                        const double tol = 64.0 + (cum + Dd) * 2.8421709430404007e-14;   // 2^-45 relative + the floors
+                        if (diff > tol) {
+                            long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
+                            if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)(j | 0x80); }
+                            t++;
+                            tooth_step(Q, R, Tq, Tr, n32);
+                            Dd = to_double128(sub128(Q, S));
+                            continue;
+                        }
+                        if (diff >= -tol) amb = true;
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    if (amb) {
+        // exact walk of this particle from its start (rewrites the survivors the fast walk listed)
+        kcount = kcount0; t = t_first; Q = Q_first; R = R_first;
         for (int j = 0; j < c; j++) {
             u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
             if (bits >= thr) {
-                long long pos = kcount + (long long)t;
-                if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
+                if (mode != 1) {
+                    long long pos = kcount + (long long)t;
+                    if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
+                }
                 kcount++;
-            }
-        }
-        return;
-    }
-    for (int j = 0; j < c; j++) {
-        u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
-        if (bits >= thr) {
-            if (mode != 1) {
-                long long pos = kcount + (long long)t;
-                if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
-            }
-            kcount++;
-        } else {
-            S = add128(S, fx70(bits, scale));
-            while (lt128(Q, S)) {
-                long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
-                if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)(j | 0x80); }
-                t++;
-                tooth_step(Q, R, Tq, Tr, n32);
+            } else {
+                S = add128(S, fx70(bits, scale));
+                while (lt128(Q, S)) {
+                    long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
+                    if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)(j | 0x80); }
+                    t++;
+                    tooth_step(Q, R, Tq, Tr, n32);
+                }
             }
         }
     }

@@ -314,8 +314,8 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->tiles, ntiles));
     CT(dmalloc(&h->supers, ntiles / SUPER_TILES + 2));
     CT(dmalloc(&h->tfuse, ntiles));
-    // optional per-particle scan records (a record has 24 slot bits)
-    if (getenv("PF_SCAN_REC") && atoi(getenv("PF_SCAN_REC")) && h->nranks <= 1 && h->k_max + 1 <= 24) {
+    // per-particle scan records of the fused expansion (24 bytes per particle; PF_NO_SCAN_REC=1 disables them)
+    if (cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_INDEX && !getenv("PF_NO_SCAN_REC")) {
         CT(dmalloc(&h->srec.x, (size_t)h->cap));
         CT(dmalloc(&h->srec.m, (size_t)h->cap));
     }
@@ -1264,7 +1264,7 @@ static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
         LaunchTimer lt(h, KC_SCAN, 2);            // (k_rank_offsets includes the wait for every rank's total)
         k_rank_offsets<<<1, 32, 0, h->stream>>>(h->xch, seq, h->steps, h->res, h->st, h->ro, h->sc, h->surv_cap);
         k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, h->supers,
-                                                                                      h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap);
+                                                                                      h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap, h->srec, h->sc);
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
