@@ -46,6 +46,10 @@ enum { PF_F64 = 0, PF_F32 = 1 };
  * PF_ORDER_INDEX is the sort-free variant the reference's TODO proposes
  * (src/fearnhead.jl:140-145): same kept set, same sampler, putative-index order. */
 enum { PF_ORDER_INDEX = 0, PF_ORDER_SORTED = 1 };
+/* State priors, src/statepriors.jl: ChineseRestaurantProcess(alpha) :47-69; StickyCRP(alpha, rho) :93-145;
+ * ChangePoint(p) :162-190; NStatePrior(counts) :203-221.  Priors other than the CRP run the Fearnhead filter on a
+ * single GPU (the classic expansion -> search sequence). */
+enum { PF_SP_CRP = 0, PF_SP_STICKY = 1, PF_SP_CHANGEPOINT = 2, PF_SP_NSTATE = 3 };
 
 typedef struct {
     int32_t filter_kind;      /* PF_FEARNHEAD | PF_CHENLIU */
@@ -59,7 +63,7 @@ typedef struct {
     int64_t history;          /* generations of (ancestor, assignment) kept for assignments(): > 0 fixed capacity, 0 none,
                                  < 0 grows on demand (the reference's ancestor chain, src/particle.jl:25-32, is unbounded) */
     int32_t device;           /* CUDA device ordinal */
-    int32_t reserved0;
+    int32_t stateprior_kind;  /* PF_SP_* */
     int32_t rank, nranks;     /* sharded run: this handle owns shard `rank` of `nranks` (0, 0 or 0, 1: unsharded) */
     double alpha;             /* ChineseRestaurantProcess(alpha), src/statepriors.jl:47-52 */
     double rejuv_threshold;   /* ChenLiuParticles rejuvination_threshold (percent CV), src/chenliu.jl:25 */
@@ -68,6 +72,10 @@ typedef struct {
     const double *mu0;        /* [d] */
     const double *lambda0;    /* NIW only: [d*d] column-major, symmetric positive definite */
     uint64_t seed;            /* device uniform stream, used when a step is given uniforms == NULL */
+    double sp_param;          /* StickyCRP: rho ; ChangePoint: probability of a change */
+    const double *sp_counts;  /* NStatePrior: counts[sp_n] (the particles start with sp_n empty components) */
+    int32_t sp_n;
+    int32_t reserved2;
 } pf_config;
 
 typedef struct {
@@ -114,6 +122,12 @@ int32_t pf_step(pf_handle h, const double *y, const double *uniforms, int64_t n_
  * synchronises before returning. */
 int32_t pf_filter(pf_handle h, const double *ys, int64_t T, const double *uniforms,
                   int64_t uniforms_per_step, double *log_evidence);
+/* filter!(ps, Labeled.(ys, labels)): src/labeled.jl:1-11.  labels[T]: 0-based component of observation t, or -1
+ * (missing: the ordinary step).  A labeled observation gives every particle the single putative fit(p, y, label)
+ * (src/particle.jl:154); a label beyond K (K + 1 under NStatePrior ... any invalid state) is the ArgumentError of
+ * src/particle.jl:137-139: PF_ERR_ARG.  Fearnhead filter, single GPU. */
+int32_t pf_filter_labeled(pf_handle h, const double *ys, const int32_t *labels, int64_t T, const double *uniforms,
+                          int64_t uniforms_per_step, double *log_evidence);
 
 /* ---- read-out (each synchronises) ---------------------------------------------------- */
 int64_t pf_n_particles(pf_handle h);          /* length(particles(ps)), src/filters.jl:15 */
@@ -127,6 +141,9 @@ int32_t pf_get_ncomponents(pf_handle h, int32_t *out);    /* ncomponents(p), src
  * Buffers sized for k_max components. */
 int32_t pf_get_particle(pf_handle h, int64_t i, int32_t *K, double *counts, double *means,
                         double *chol, double *logdet);
+/* p.stateprior of particle i: StickyCRP N[K], Nsame[K], last (0-based) (src/statepriors.jl:95-100); the other
+ * priors' counts follow from pf_get_particle (CRP N = NStatePrior counts - initial counts = nobs per component). */
+int32_t pf_get_stateprior(pf_handle h, int64_t i, double *N, double *Nsame, int32_t *last);
 /* assignments(ps), src/filters.jl:26-34: out[T x n] column-major (column = particle),
  * 0-based component labels.  Needs history >= steps. */
 int32_t pf_get_assignments(pf_handle h, int32_t *out);

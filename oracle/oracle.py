@@ -27,6 +27,7 @@ _SO = os.path.join(_HERE, "_build", "libparticles_oracle.so")
 NIX2, NIW = 0, 1
 FEARNHEAD, CHENLIU = 0, 1
 ORDER_SORTED, ORDER_INDEX = 0, 1
+SP_CRP, SP_STICKY, SP_CHANGEPOINT, SP_NSTATE = 0, 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -58,6 +59,16 @@ def lib():
         L.orc_fh_expand.argtypes = [C.c_void_p, _dp]
         L.orc_fh_expand.restype = C.c_int
         L.orc_fh_commit.argtypes = [C.c_void_p, _ip, _dp, C.c_int]
+        L.orc_fh_step_labeled.argtypes = [C.c_void_p, _dp, C.c_double, C.c_int]
+        L.orc_fh_step_labeled.restype = C.c_int
+        L.orc_set_stateprior.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp, C.c_int]
+        L.orc_set_stateprior.restype = C.c_int
+        L.orc_get_sticky.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.orc_get_sticky.restype = C.c_int
+        L.orc_sp_log_prior.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_sp_log_prior.restype = C.c_double
+        L.orc_sp_candidates.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.orc_sp_candidates.restype = C.c_int
         L.orc_cl_step.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.orc_cl_step.restype = C.c_int
         for name in ("orc_n_particles", "orc_n_steps", "orc_n_putatives", "orc_resampled",
@@ -181,7 +192,9 @@ class OracleFilter:
     """FearnheadParticles / ChenLiuParticles restated (see particles_oracle.c)."""
 
     def __init__(self, filter_kind, N, prior: Prior, alpha, rejuv=50.0, order=ORDER_SORTED,
-                 keep_history=True):
+                 keep_history=True, stateprior=None):
+        """stateprior: None = ChineseRestaurantProcess(alpha); ("sticky", alpha, rho) = StickyCRP;
+        ("changepoint", p) = ChangePoint(p); ("nstate", counts) = NStatePrior(counts) (src/statepriors.jl)."""
         self.prior, self.N, self.kind = prior, N, filter_kind
         lam_f = np.asfortranarray(prior.Lam0)
         self.h = lib().orc_create(filter_kind, N, prior.kind, prior.d,
@@ -190,6 +203,19 @@ class OracleFilter:
                                   float(rejuv), order, int(keep_history))
         if not self.h:
             raise ValueError("orc_create failed")
+        if stateprior is not None:
+            kind = stateprior[0]
+            if kind == "sticky":
+                rc = lib().orc_set_stateprior(self.h, SP_STICKY, float(stateprior[1]), float(stateprior[2]), None, 0)
+            elif kind == "changepoint":
+                rc = lib().orc_set_stateprior(self.h, SP_CHANGEPOINT, 0.0, float(stateprior[1]), None, 0)
+            elif kind == "nstate":
+                c, pc = _d(stateprior[1])
+                rc = lib().orc_set_stateprior(self.h, SP_NSTATE, 0.0, 0.0, pc, len(c))
+            else:
+                raise ValueError(f"unknown state prior {kind}")
+            if rc != 0:
+                raise ValueError("invalid state prior")          # ArgumentError, src/statepriors.jl:169
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -200,6 +226,25 @@ class OracleFilter:
     def fh_step(self, y, u):
         y, py = _d(np.atleast_1d(y))
         return lib().orc_fh_step(self.h, py, float(u))
+
+    def fh_step_labeled(self, y, u, label):
+        """fit!(ps, Labeled(y, label)) (src/labeled.jl:10-11); label None / 0 = missing."""
+        y, py = _d(np.atleast_1d(y))
+        return lib().orc_fh_step_labeled(self.h, py, float(u), int(label or 0))
+
+    def sp_log_prior(self, i, x):
+        return lib().orc_sp_log_prior(self.h, i, int(x))
+
+    def sp_candidates(self, i):
+        first = C.c_int()
+        n = lib().orc_sp_candidates(self.h, i, C.byref(first))
+        return list(range(first.value, first.value + n))
+
+    def sticky(self, i):
+        K = int(self.ncomponents()[i])
+        ns = np.zeros(max(K, 1))
+        last = lib().orc_get_sticky(self.h, i, ns.ctypes.data_as(_dp))
+        return ns[:K], last
 
     def fh_expand(self, y):
         y, py = _d(np.atleast_1d(y))

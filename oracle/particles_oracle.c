@@ -46,6 +46,7 @@
 enum { ORC_NIX2 = 0, ORC_NIW = 1 };
 enum { ORC_FEARNHEAD = 0, ORC_CHENLIU = 1 };
 enum { ORC_ORDER_SORTED = 0, ORC_ORDER_INDEX = 1 };
+enum { ORC_SP_CRP = 0, ORC_SP_STICKY = 1, ORC_SP_CHANGEPOINT = 2, ORC_SP_NSTATE = 3 };
 
 typedef struct {
     int kind, d;
@@ -246,7 +247,12 @@ double orc_logpred(const orc_prior *p, const double *ss, const double *y)
 typedef struct {
     int K;
     double *st;      /* K * ss_len doubles */
-    double *crpN;    /* K doubles: ChineseRestaurantProcess.N, src/statepriors.jl:47-50 */
+    double *crpN;    /* K doubles: ChineseRestaurantProcess.N (src/statepriors.jl:47-50), StickyCRP.N (:95-100),
+                        NStatePrior.counts (:203-207) */
+    double *Nsame;   /* K doubles: StickyCRP.Nsame (src/statepriors.jl:99) */
+    int last;        /* StickyCRP.last (:97), 1-based */
+    double total;    /* NStatePrior.total_count (:205) */
+    int cp_n;        /* ChangePoint.n (:162-166); ChangePoint.k == K */
     double weight;   /* linear space, src/particle.jl:42 */
     int ancestor;    /* index into the previous generation, -1 for the root */
     int assignment;  /* 1-based component index, 0 for the root (src/particle.jl:62) */
@@ -265,16 +271,20 @@ typedef struct {
     int filter, N, order;
     orc_prior prior;
     double alpha, rejuv;
+    int sp_kind;                 /* ORC_SP_* */
+    double sp_rho, sp_logp;      /* StickyCRP.rho ; ChangePoint.logp */
+    int sp_n;                    /* NStatePrior.n */
     particle *pop; int n;
     putative *put; int M, put_cap; double *upd_pool; long upd_pool_cap;
     generation *gens; int T, gens_cap;
     int keep_history;
+    int forced_label;            /* > 0: the observation being filtered is Labeled(y, label), src/labeled.jl:1-11 */
     /* last-step diagnostics */
     double total_w, w_resamp, cv;
     int n_kept, n_resamp_req, n_resamp_got, kept_i, resampled;
 } orc_filter;
 
-static void particle_free(particle *p) { free(p->st); free(p->crpN); }
+static void particle_free(particle *p) { free(p->st); free(p->crpN); free(p->Nsame); }
 
 static void pop_free(particle *pop, int n)
 {
@@ -317,10 +327,49 @@ void orc_destroy(orc_filter *f)
     free(f);
 }
 
-/* log_prior(crp, x), src/statepriors.jl:65-66 */
-static double crp_log_prior(const particle *p, int x, double alpha)
+/* StatsFuns.log1mexp(x) = x < -log(2) ? log1p(-exp(x)) : log(-expm1(x)) */
+static double log1mexp(double x) { return x < -0.6931471805599453 ? log1p(-exp(x)) : log(-expm1(x)); }
+
+/* candidates(stateprior): CRP 1:K+1 (src/statepriors.jl:54); StickyCRP 1:1 if empty else 0:K+1 (:105);
+ * ChangePoint max(k,1):k+1 (:177-178); NStatePrior 1:n (:219).  Returns the count, *first = first candidate. */
+static int sp_candidates(const orc_filter *f, const particle *p, int *first)
 {
-    return x == p->K + 1 ? log(alpha) : log(p->crpN[x - 1]);
+    switch (f->sp_kind) {
+    case ORC_SP_STICKY: if (p->K == 0) { *first = 1; return 1; } *first = 0; return p->K + 2;
+    case ORC_SP_CHANGEPOINT: *first = p->K > 1 ? p->K : 1; return p->K + 1 - *first + 1;
+    case ORC_SP_NSTATE: *first = 1; return f->sp_n;
+    default: *first = 1; return p->K + 1;
+    }
+}
+
+/* state_to_index(stateprior, state): identity (src/statepriors.jl:22) except StickyCRP 0 -> last (:103) */
+static int sp_state_to_index(const orc_filter *f, const particle *p, int x)
+{
+    return (f->sp_kind == ORC_SP_STICKY && x == 0) ? p->last : x;
+}
+
+/* log_prior(stateprior, x): CRP src/statepriors.jl:65-66; StickyCRP :131-145; ChangePoint :181-183;
+ * NStatePrior :220.  NAN = ArgumentError (:141). */
+static double sp_log_prior(const orc_filter *f, const particle *p, int x)
+{
+    switch (f->sp_kind) {
+    case ORC_SP_STICKY: {
+        if (x == 0) {
+            double sumN = 0.0;
+            for (int k = 0; k < p->K; k++) sumN += p->crpN[k];
+            return log(f->sp_rho / (1.0 - f->sp_rho)) + log(sumN + f->alpha);       /* logit(rho) + log(sum(N) + alpha) */
+        }
+        if (x >= 1 && x <= p->K) return log(p->crpN[x - 1]);
+        if (x == p->K + 1) return log(f->alpha);
+        return NAN;
+    }
+    case ORC_SP_CHANGEPOINT:
+        return p->K == 0 ? 0.0 : (x == p->K ? log1mexp(f->sp_logp) : f->sp_logp);
+    case ORC_SP_NSTATE:
+        return log(p->crpN[x - 1]) - log(p->total);
+    default:
+        return x == p->K + 1 ? log(f->alpha) : log(p->crpN[x - 1]);
+    }
 }
 
 /* PutativeParticle(p, obs, state), src/particle.jl:100-116.  upd receives add(comp, obs). */
@@ -329,11 +378,12 @@ static double putative_weight(const orc_filter *f, const particle *p, const doub
 {
     int L = ss_len(f->prior.d);
     double logweight = log(p->weight);
-    logweight += crp_log_prior(p, state, f->alpha);
+    logweight += sp_log_prior(f, p, state);
+    int comp_i = sp_state_to_index(f, p, state);
     double empty[1 + 2 * ORC_DMAX + ORC_DMAX * ORC_DMAX];
     const double *comp;
-    if (state <= p->K) {
-        comp = p->st + (size_t)(state - 1) * L;
+    if (comp_i <= p->K) {
+        comp = p->st + (size_t)(comp_i - 1) * L;
         logweight -= orc_mll(&f->prior, comp);
     } else {
         orc_empty_stats(f->prior.d, empty);
@@ -346,23 +396,68 @@ static double putative_weight(const orc_filter *f, const particle *p, const doub
     return exp(logweight);
 }
 
-/* instantiate(putative, weight), src/particle.jl:134-149 (+ CRP add, src/statepriors.jl:55-63) */
+/* instantiate(putative, weight), src/particle.jl:134-149, with add(stateprior, state):
+ * CRP src/statepriors.jl:55-63; StickyCRP :106-128; ChangePoint :171-175; NStatePrior :211-217 */
 static void instantiate(const orc_filter *f, const putative *q, double weight, particle *out)
 {
     const particle *p = &f->pop[q->parent];
     int L = ss_len(f->prior.d);
-    int comp_i = q->state;
+    int comp_i = sp_state_to_index(f, p, q->state);
     int K = p->K + (comp_i > p->K);
     out->K = K;
-    out->st = malloc(sizeof(double) * (size_t)K * L);
-    out->crpN = malloc(sizeof(double) * K);
+    out->st = malloc(sizeof(double) * (size_t)(K > 0 ? K : 1) * L);
+    out->crpN = malloc(sizeof(double) * (K > 0 ? K : 1));
+    out->Nsame = malloc(sizeof(double) * (K > 0 ? K : 1));
     memcpy(out->st, p->st, sizeof(double) * (size_t)p->K * L);
     memcpy(out->crpN, p->crpN, sizeof(double) * p->K);
+    if (p->Nsame) memcpy(out->Nsame, p->Nsame, sizeof(double) * p->K); else memset(out->Nsame, 0, sizeof(double) * p->K);
     memcpy(out->st + (size_t)(comp_i - 1) * L, q->upd, sizeof(double) * L);
-    if (comp_i > p->K) out->crpN[comp_i - 1] = 1.0; else out->crpN[comp_i - 1] += 1.0;
+    out->last = p->last; out->total = p->total; out->cp_n = p->cp_n;
+    switch (f->sp_kind) {
+    case ORC_SP_STICKY: {
+        const int sticky = q->state == 0;
+        if (comp_i > p->K) { out->crpN[comp_i - 1] = 0.0; out->Nsame[comp_i - 1] = 0.0; }
+        if (comp_i == p->last) out->Nsame[comp_i - 1] += 1.0;
+        if (!sticky) out->crpN[comp_i - 1] += 1.0;
+        out->last = comp_i;
+        break;
+    }
+    case ORC_SP_CHANGEPOINT: out->cp_n = p->cp_n + 1; break;
+    case ORC_SP_NSTATE: out->crpN[comp_i - 1] += 1.0; out->total = p->total + 1.0; break;
+    default:
+        if (comp_i > p->K) out->crpN[comp_i - 1] = 1.0; else out->crpN[comp_i - 1] += 1.0;
+    }
     out->weight = weight;
     out->ancestor = q->parent;
     out->assignment = comp_i;
+}
+
+/* Replace the state prior of a filter that has not seen data yet (StatePrior of the initial particles,
+ * src/particle.jl:59-63).  kind = ORC_SP_*: p1 = alpha (CRP, StickyCRP); p2 = rho (StickyCRP, :102) or the
+ * change probability (ChangePoint(p), :168-171); counts[n] = NStatePrior(counts) (:209): the particles start
+ * with n empty components, as test/labeled.jl:13-18 builds them. */
+int orc_set_stateprior(orc_filter *f, int kind, double p1, double p2, const double *counts, int n)
+{
+    if (f->T != 0) return -1;
+    f->sp_kind = kind;
+    if (kind == ORC_SP_CRP || kind == ORC_SP_STICKY) f->alpha = p1;
+    if (kind == ORC_SP_STICKY) f->sp_rho = p2;
+    if (kind == ORC_SP_CHANGEPOINT) { if (!(p2 >= 0.0 && p2 <= 1.0)) return -2; f->sp_logp = log(p2); }
+    int L = ss_len(f->prior.d);
+    for (int i = 0; i < f->n; i++) {
+        particle *p = &f->pop[i];
+        particle_free(p);
+        p->st = NULL; p->crpN = NULL; p->Nsame = NULL; p->K = 0; p->last = 1; p->total = 0.0; p->cp_n = 0;
+        if (kind == ORC_SP_NSTATE) {
+            f->sp_n = n;
+            p->K = n;
+            p->st = calloc((size_t)n * L, sizeof(double));
+            p->crpN = malloc(sizeof(double) * n);
+            p->Nsame = calloc(n, sizeof(double));
+            for (int k = 0; k < n; k++) { p->crpN[k] = counts[k]; p->total += counts[k]; }
+        }
+    }
+    return 0;
 }
 
 static void record_generation(orc_filter *f)
@@ -455,7 +550,8 @@ int orc_fh_expand(orc_filter *f, const double *y)
 {
     int L = ss_len(f->prior.d);
     long M = 0;
-    for (int i = 0; i < f->n; i++) M += f->pop[i].K + 1;
+    int first;
+    for (int i = 0; i < f->n; i++) M += f->forced_label > 0 ? 1 : sp_candidates(f, &f->pop[i], &first);
     if (M > f->put_cap) {
         f->put_cap = (int)M;
         f->put = realloc(f->put, sizeof(putative) * M);
@@ -466,12 +562,16 @@ int orc_fh_expand(orc_filter *f, const double *y)
         f->upd_pool = malloc(sizeof(double) * M * L);
     }
     long k = 0;
-    for (int i = 0; i < f->n; i++)
-        for (int j = 1; j <= f->pop[i].K + 1; j++, k++) {
+    for (int i = 0; i < f->n; i++) {
+        /* putatives(p, y), src/particle.jl:68-69; a labeled observation has ONE putative, src/labeled.jl:10-11 */
+        int nc = sp_candidates(f, &f->pop[i], &first);
+        if (f->forced_label > 0) { first = f->forced_label; nc = 1; }
+        for (int j = first; j < first + nc; j++, k++) {
             putative *q = &f->put[k];
             q->parent = i; q->state = j; q->upd = f->upd_pool + k * L;
             q->weight = putative_weight(f, &f->pop[i], y, j, q->upd);
         }
+    }
     f->M = (int)M;
     double total = 0.0;                 /* sum(weight(p) for p in putative): left fold, :133 */
     for (long q = 0; q < M; q++) total += f->put[q].weight;
@@ -548,6 +648,16 @@ int orc_fh_step(orc_filter *f, const double *y, double u)
     return n_out;
 }
 
+/* fit!(ps, Labeled(y, label)), src/labeled.jl:10-11 through src/fearnhead.jl:130-184: every particle has the single
+ * putative fit(p, y, label); label <= 0 = missing (the ordinary step). */
+int orc_fh_step_labeled(orc_filter *f, const double *y, double u, int label)
+{
+    f->forced_label = label > 0 ? label : 0;
+    int n = orc_fh_step(f, y, u);
+    f->forced_label = 0;
+    return n;
+}
+
 /* ------------------------------------------------------------------ chenliu.jl */
 
 /* StatsBase.sample(rng, wv::AbstractWeights) (inverse CDF), rand() := u; 0-based result */
@@ -588,12 +698,13 @@ int orc_cl_step(orc_filter *f, const double *y, const double *u_prop, const doub
     double upd[(1 + 2 * ORC_DMAX + ORC_DMAX * ORC_DMAX)];
     for (int i = 0; i < N; i++) {
         particle *p = &f->pop[i];
-        int C = p->K + 1;
+        int first;
+        int C = sp_candidates(f, p, &first);
         double *v = malloc(sizeof(double) * C);
         double *u = malloc(sizeof(double) * (size_t)C * L);
-        for (int j = 1; j <= C; j++) v[j - 1] = putative_weight(f, p, y, j, u + (size_t)(j - 1) * L);
+        for (int j = 0; j < C; j++) v[j] = putative_weight(f, p, y, first + j, u + (size_t)j * L);
         int pick = wsample1(v, C, u_prop[i]);                      /* :35 */
-        putative q = { i, pick + 1, v[pick], u + (size_t)pick * L };
+        putative q = { i, first + pick, v[pick], u + (size_t)pick * L };
         instantiate(f, &q, sum_pairwise(v, C), &np[i]);            /* :35,:41 */
         ws[i] = np[i].weight;
         free(v); free(u);
@@ -613,9 +724,12 @@ int orc_cl_step(orc_filter *f, const double *y, const double *u_prop, const doub
             particle *src = &np[k];
             out[i].K = src->K;
             out[i].st = malloc(sizeof(double) * (size_t)src->K * L);
-            out[i].crpN = malloc(sizeof(double) * src->K);
+            out[i].crpN = malloc(sizeof(double) * (src->K > 0 ? src->K : 1));
+            out[i].Nsame = malloc(sizeof(double) * (src->K > 0 ? src->K : 1));
             memcpy(out[i].st, src->st, sizeof(double) * (size_t)src->K * L);
             memcpy(out[i].crpN, src->crpN, sizeof(double) * src->K);
+            memcpy(out[i].Nsame, src->Nsame, sizeof(double) * src->K);
+            out[i].last = src->last; out[i].total = src->total; out[i].cp_n = src->cp_n;
             out[i].weight = 1.0 / (double)N;
             out[i].ancestor = src->ancestor; out[i].assignment = src->assignment;
         }
@@ -663,6 +777,17 @@ int orc_get_particle(const orc_filter *f, int i, double *st, double *crpN)
     memcpy(crpN, p->crpN, sizeof(double) * p->K);
     return p->K;
 }
+
+/* StickyCRP book-keeping of one particle (src/statepriors.jl:95-100): Nsame[K]; returns `last` (1-based) */
+int orc_get_sticky(const orc_filter *f, int i, double *Nsame)
+{
+    const particle *p = &f->pop[i];
+    for (int k = 0; k < p->K; k++) Nsame[k] = p->Nsame ? p->Nsame[k] : 0.0;
+    return p->last;
+}
+/* log_prior(p.stateprior, x) of particle i (NAN = ArgumentError) and the candidate range */
+double orc_sp_log_prior(const orc_filter *f, int i, int x) { return sp_log_prior(f, &f->pop[i], x); }
+int orc_sp_candidates(const orc_filter *f, int i, int *first) { return sp_candidates(f, &f->pop[i], first); }
 
 /* assignments(ps), src/filters.jl:26-34 via assignments(p), src/particle.jl:25-32:
  * out is T x n column-major (column i = particle i), 1-based component labels. */

@@ -36,7 +36,7 @@ struct StepLog {            // one record per step, read back after pf_filter
 // new cluster starts with (add(prior, y), src/component.jl:85).
 template <int D>
 __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, StepConst *sc_out, int first,
-                          SelScratch *guard, const SelResult *prev, const Xch *xch, unsigned long long seq, long long step)
+                          SelScratch *guard, const SelResult *prev, const Xch *xch, unsigned long long seq, long long step, int forced = -1)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (guard && guard->halt) return;
@@ -51,6 +51,7 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
     st->n_next = 0;
     st->M = 0; st->vmax_bits = 0; st->ticket = 0; st->ticket2 = 0; st->n_picked = 0; st->n_kept = 0;
     StepConst c;
+    c.forced = forced; c.pad = 0;
     double dx[D], z[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1];
 #pragma unroll
     for (int i = 0; i < D; i++) { c.y[i] = y[i]; dx[i] = y[i] - pc->mu0[i]; dinv[i] = pc->L0_dinv[i]; }
@@ -279,6 +280,120 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
                 atomic_add_acc(&sc->Tot, tot);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------ k_expand_sp
+// putatives(p, y) under the other state priors (src/statepriors.jl:93-221) and for Labeled observations
+// (src/labeled.jl:10-11): the same predictive arithmetic as k_expand, the candidates and their log-priors per
+// prior.  Putative index jj of a particle with K components (row jj of V):
+//   ChineseRestaurantProcess   jj = slot (jj = K: new)                                  candidates 1:K+1
+//   StickyCRP                  K = 0: jj = 0 new; else jj = 0 "stick" (slot last), 1 + slot, K + 1 new   0:K+1
+//   ChangePoint                K = 0: jj = 0 new; else jj = 0 stay (slot K-1), jj = 1 change (slot K)    max(k,1):k+1
+//   NStatePrior                jj = slot                                                 1:n
+//   labeled                    jj = 0 only: the labelled slot
+template <int D>
+__global__ void __launch_bounds__(256) k_expand_sp(const double *__restrict__ S, const double *__restrict__ logw,
+                                                   const int *__restrict__ Kc, long long cap, int k_max,
+                                                   const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
+                                                   const StepConst *__restrict__ scp, StepState *st, double *__restrict__ V,
+                                                   unsigned char *__restrict__ cnt, SelScratch *sc, SpArrays sp, long long step)
+{
+    using L = Layout<D>;
+    if (sc->halt) return;
+    __shared__ u64 s_max[8];
+    __shared__ long long s_M[8], s_ovf[8];
+    const long long n_live = st->n_live;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 vmax = 0;
+    long long myM = 0, myOvf = 0;
+    bool bad_label = false;
+    if (i < n_live) {
+        double y[D], mu0[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) { y[k] = scp->y[k]; mu0[k] = pc->mu0[k]; }
+        const int K = Kc[i];
+        const double lw0 = logw[i];
+        const int kind = pc->sp_kind, forced = scp->forced;
+        const double lp_newc = kind == SPK_STICKY ? pc->sp_log_alpha : 0.0;      // (CRP: log alpha is inside lw_new)
+        double n_of = 0.0;
+        auto pred = [&](int j) {       // log predictive of y under slot j (+ log N_j under the CRP: folded into the table)
+            const double *base = S + ((long long)j * L::F) * cap + i;
+            double fl[L::F], z[D], q;
+#pragma unroll
+            for (int f = 0; f < L::F; f++) fl[f] = base[(long long)f * cap];
+            n_of = fl[L::F_N];
+            const NRow row = tab[(int)fl[L::F_N]];
+            return slot_logw<D>(row, fl[L::F_LOGDET], fl + L::F_MEAN, fl + L::F_DINV, fl + L::F_OFF, y, mu0, z, &q);
+        };
+        auto put = [&](int jj, double lw) {
+            const double v = exp(lw);
+            const u64 b = (u64)__double_as_longlong(v);
+            vmax = b > vmax ? b : vmax;
+            V[(long long)jj * cap + i] = v;
+        };
+        auto lp_slot = [&](int j, double nj) {     // log-prior of the non-sticky candidate "existing slot j"
+            if (kind == SPK_STICKY) return log(sp.N[(long long)j * cap + i]);
+            if (kind == SPK_CHANGEPOINT) return pc->sp_lp_stay;
+            if (kind == SPK_NSTATE) return log(pc->sp_counts0[j] + nj) - log(pc->sp_total0 + (double)step);
+            return 0.0;                              // CRP: in the table
+        };
+        int c = 0;
+        if (forced >= 0) {
+            // fit(p, y, label): one putative.  Valid states: CRP / StickyCRP 1..K+1, ChangePoint k or k+1, NStatePrior 1..n
+            const int j = forced;
+            bool ok = kind == SPK_NSTATE ? j < pc->sp_n : (kind == SPK_CHANGEPOINT ? (K == 0 ? j == 0 : (j == K - 1 || j == K)) : j <= K);
+            if (j >= k_max) ok = false;
+            if (!ok) { bad_label = true; put(0, -INFINITY); }
+            else if (j < K) { const double p = pred(j); put(0, lw0 + lp_slot(j, n_of) + p); }
+            else put(0, lw0 + (kind == SPK_CHANGEPOINT ? (K == 0 ? 0.0 : pc->sp_lp_change) : lp_newc) + scp->lw_new);
+            c = 1;
+        } else if (kind == SPK_CHANGEPOINT) {
+            if (K == 0) { put(0, lw0 + scp->lw_new); c = 1; }
+            else {
+                const double p = pred(K - 1);
+                put(0, lw0 + pc->sp_lp_stay + p); c = 1;
+                if (K < k_max) { put(1, lw0 + pc->sp_lp_change + scp->lw_new); c = 2; } else myOvf = 1;
+            }
+        } else if (kind == SPK_NSTATE) {
+            for (int j = 0; j < K; j++) { const double p = pred(j); put(j, lw0 + lp_slot(j, n_of) + p); }
+            c = K;
+        } else if (kind == SPK_STICKY) {
+            if (K == 0) { put(0, lw0 + lp_newc + scp->lw_new); c = 1; }
+            else {
+                const int last = sp.last[i];
+                double sumN = 0.0, p_last = 0.0;
+                for (int j = 0; j < K; j++) {
+                    const double Nj = sp.N[(long long)j * cap + i];
+                    sumN += Nj;
+                    const double p = pred(j);
+                    if (j == last) p_last = p;
+                    put(1 + j, lw0 + log(Nj) + p);
+                }
+                put(0, lw0 + pc->sp_logit_rho + log(sumN + pc->alpha) + p_last);
+                c = K + 1;
+                if (K < k_max) { put(K + 1, lw0 + lp_newc + scp->lw_new); c = K + 2; } else myOvf = 1;
+            }
+        } else {                                      // CRP (labeled streams with missing labels)
+            for (int j = 0; j < K; j++) { const double p = pred(j); put(j, lw0 + p); }
+            c = K;
+            if (K < k_max) { put(K, lw0 + scp->lw_new); c = K + 1; } else myOvf = 1;
+        }
+        cnt[i] = (unsigned char)c;
+        myM = c;
+    }
+    if (bad_label) sel_halt(sc, step, PF_HALT_LABEL);
+    vmax = warp_max64(vmax);
+    myM = (long long)warp_sum64((u64)myM);
+    myOvf = (long long)warp_sum64((u64)myOvf);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_max[wid] = vmax; s_M[wid] = myM; s_ovf[wid] = myOvf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) { vmax = s_max[w] > vmax ? s_max[w] : vmax; myM += s_M[w]; myOvf += s_ovf[w]; }
+        if (vmax) atomicMax(&st->vmax_bits, vmax);
+        if (myM) atomicAdd((unsigned long long *)&st->M, (unsigned long long)myM);
+        if (myOvf) atomicAdd((unsigned long long *)&st->overflow, (unsigned long long)myOvf);
     }
 }
 
@@ -715,7 +830,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
 // Welford mean update + rank-1 Cholesky update, appends (ancestor, assignment) to the
 // genealogy and sets the normalised log-weight (src/fearnhead.jl:172-179).
 template <int D>
-__global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const double *__restrict__ S, const int *__restrict__ Kc,
+__device__ __forceinline__ void instantiate_one(const long long t, const double *__restrict__ S, const int *__restrict__ Kc,
                                                      double *S2, int *Kc2,
                                                      double *logw2, long long cap,
                                                      const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
@@ -726,13 +841,9 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
                                                      unsigned int *gen_anc, unsigned char *gen_asg,
                                                      const RankOff *__restrict__ ro, int k_max,
                                                      const SelScratch *guard, long long *m_next,
-                                                     const PeerTable *__restrict__ peers, long long gen_off)
+                                                     const PeerTable *__restrict__ peers, long long gen_off, SpArrays sp_cur, SpArrays sp_nxt)
 {
     using L = Layout<D>;
-    if (guard && (guard->phase != 4 || guard->halt)) return;
-    const long long n_out = ro ? ro->n_local : st->n_next;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_out) return;                       // (grid = survivor-list capacity: no thread beyond it)
     // destination of child t: a local index, or (sharded run) an index in the arrays of its new owner
     double *dstb = S2 + t;
     long long idx = t;
@@ -753,10 +864,17 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
     const long long stride = cap;
     const unsigned int par = surv_parent[t];
     const unsigned char sl = surv_slot[t];
-    const int j = sl & 0x7F;
+    const int jj = sl & 0x7F;                    // putative index = row of V
     const bool picked = sl & 0x80;
     const int K = Kc[par];
-    const double v = V[(long long)j * cap + par];
+    // the component the putative assigns y to (state_to_index, src/statepriors.jl:22,103; k_expand_sp's table)
+    int j = jj;
+    bool sticky = false;
+    const int sp_kind = pc->sp_kind;
+    if (scp->forced >= 0) j = scp->forced;
+    else if (sp_kind == SPK_CHANGEPOINT) j = K == 0 ? 0 : K - 1 + jj;
+    else if (sp_kind == SPK_STICKY && K > 0) { if (jj == 0) { j = sp_cur.last[par]; sticky = true; } else j = jj - 1; }
+    const double v = V[(long long)jj * cap + par];
     const double lw = picked ? res->lw_resamp : (log(v) - res->log_total);
     const int Knew = K + (j == K ? 1 : 0);
     if (m_next) {        // putatives this child will have at the next observation
@@ -766,6 +884,19 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
     }
     logw2[idx] = lw; Kc2[idx] = Knew;
     if (gen_anc) { gen_anc[idx] = par + anc_off; gen_asg[idx] = (unsigned char)j; }
+    if (sp_kind == SPK_STICKY) {
+        // add(crp::StickyCRP, x, sticky), src/statepriors.jl:106-128
+        const int last = sp_cur.last[par];
+        for (int k = 0; k < K; k++) {
+            sp_nxt.N[(long long)k * cap + idx] = sp_cur.N[(long long)k * cap + par];
+            sp_nxt.Nsame[(long long)k * cap + idx] = sp_cur.Nsame[(long long)k * cap + par];
+        }
+        double Nj = j < K ? sp_cur.N[(long long)j * cap + par] : 0.0, Sj = j < K ? sp_cur.Nsame[(long long)j * cap + par] : 0.0;
+        if (j == last) Sj += 1.0;
+        if (!sticky) Nj += 1.0;
+        sp_nxt.N[(long long)j * cap + idx] = Nj; sp_nxt.Nsame[(long long)j * cap + idx] = Sj;
+        sp_nxt.last[idx] = j;
+    }
     // copy the parent's slots (the chosen one is rewritten below)
     {
         const double *src = S + par;
@@ -814,6 +945,28 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
 #pragma unroll
         for (int f = 0; f < L::F; f++) dst[(long long)f * stride] = scp->newslot[f];
     }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const double *__restrict__ S, const int *__restrict__ Kc,
+                                                     double *S2, int *Kc2,
+                                                     double *logw2, long long cap,
+                                                     const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
+                                                     const StepConst *__restrict__ scp, const StepState *__restrict__ st,
+                                                     const SelResult *__restrict__ res, const double *__restrict__ V,
+                                                     const unsigned int *__restrict__ surv_parent,
+                                                     const unsigned char *__restrict__ surv_slot,
+                                                     unsigned int *gen_anc, unsigned char *gen_asg,
+                                                     const RankOff *__restrict__ ro, int k_max,
+                                                     const SelScratch *guard, long long *m_next,
+                                                     const PeerTable *__restrict__ peers, long long gen_off,
+                                                     SpArrays sp_cur = SpArrays{nullptr, nullptr, nullptr}, SpArrays sp_nxt = SpArrays{nullptr, nullptr, nullptr})
+{
+    if (guard && (guard->phase != 4 || guard->halt)) return;
+    const long long n_out = ro ? ro->n_local : st->n_next;
+    // (grid-stride: a sharded rank sizes its grid for a balanced share and loops when it produced more)
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_out; t += (long long)gridDim.x * blockDim.x)
+        instantiate_one<D>(t, S, Kc, S2, Kc2, logw2, cap, tab, pc, scp, st, res, V, surv_parent, surv_slot, gen_anc, gen_asg, ro, k_max, guard, m_next, peers, gen_off, sp_cur, sp_nxt);
 }
 
 // ------------------------------------------------------------------ reference-literal order

@@ -28,14 +28,15 @@ struct __align__(32) NRow {
 
 #include <math.h>
 // one table row, computed on the host in long double (the terms that depend on the integer count only)
-static inline NRow make_nrow(double kappa0, double nu0, double alpha, int dim, long long n)
+// with_lp = false leaves the state prior's term out of C (state priors other than the CRP add theirs per candidate)
+static inline NRow make_nrow(double kappa0, double nu0, double alpha, int dim, long long n, bool with_lp = true)
 {
     const long double LOGPI_L = 1.1447298858494001741434273513530587116473L;
     long double k0 = kappa0, d = dim;
     long double kn = k0 + n, nn = (long double)nu0 + n;
     long double h = (nn + 1.0L) / 2.0L;
     long double r = kn / (kn + 1.0L);
-    long double lp = n == 0 ? logl((long double)alpha) : logl((long double)n);
+    long double lp = !with_lp ? 0.0L : (n == 0 ? logl((long double)alpha) : logl((long double)n));
     long double C = lp + lgammal(h) - lgammal(h - d / 2.0L) - d / 2.0L * LOGPI_L + d / 2.0L * logl(r);
     NRow row;
     row.C = (double)C; row.r = (double)r; row.h = (double)h; row.g = (double)((long double)n / kn);
@@ -57,6 +58,9 @@ struct StepConst {
                                            // carry the same weight c/total (src/fearnhead.jl:173), so these putatives are
                                            // exactly tied -- the one mass tie of the algorithm, counted instead of listed
     double newslot[2 + PF_MAX_D + PF_MAX_D * (PF_MAX_D + 1) / 2];   // fields of prior (+) y
+    int forced;                            // >= 0: Labeled(y, label) -- every particle has the single putative "slot forced"
+                                           // (src/labeled.jl:10-11); -1: label missing
+    int pad;
 };
 
 struct PriorConst {
@@ -65,7 +69,24 @@ struct PriorConst {
     double L0_dinv[PF_MAX_D];
     double L0_off[PF_MAX_D * (PF_MAX_D - 1) / 2];
     double logdet0;
-    NRow row0;                             // n = 0 row (C uses log alpha)
+    NRow row0;                             // n = 0 row (C uses log alpha under the CRP)
+    // state prior (src/statepriors.jl): PF_SP_CRP N_j-or-alpha is folded into the table rows; the others add their
+    // log-prior per candidate
+    int sp_kind, sp_n;                     // PF_SP_* ; NStatePrior: number of states
+    double sp_log_alpha;                   // StickyCRP: log alpha
+    double sp_logit_rho;                   // StickyCRP: logit(rho), src/statepriors.jl:135
+    double sp_lp_stay, sp_lp_change;       // ChangePoint: log1mexp(logp), logp, src/statepriors.jl:181-183
+    double sp_counts0[PF_MAX_SLOTS];       // NStatePrior: initial counts (src/statepriors.jl:203-209)
+    double sp_total0;
+};
+
+enum { SPK_CRP = 0, SPK_STICKY = 1, SPK_CHANGEPOINT = 2, SPK_NSTATE = 3 };      // = PF_SP_* of the C header
+
+// StickyCRP book-keeping of a population (src/statepriors.jl:95-100), slot-major like the store
+struct SpArrays {
+    double *N;                             // [slot * cap + i]: non-sticky occupations
+    double *Nsame;                         // [slot * cap + i]: transitions to the same state
+    int *last;                             // [i]: component of the previous observation (0-based)
 };
 
 // z = L^{-1} dx (forward substitution), returns |z|^2

@@ -55,6 +55,11 @@ struct pf_filter_s {
     long long slog_cap = 0;
     double *ys_dev = nullptr, *u_dev = nullptr;
     long long ys_cap = 0, u_cap = 0;
+    // state prior (src/statepriors.jl) and labeled observations (src/labeled.jl)
+    int sp_kind = PF_SP_CRP;
+    std::vector<double> sp_counts;
+    SpArrays sp[2] = {SpArrays{nullptr, nullptr, nullptr}, SpArrays{nullptr, nullptr, nullptr}};
+    int cur_label = -1;                   // label of the observation being queued (-1: missing)
     // reference-literal order scratch
     u64 *keys = nullptr, *keys2 = nullptr;
     unsigned int *vals = nullptr, *vals2 = nullptr, *hist = nullptr, *pick_pos = nullptr;
@@ -158,7 +163,7 @@ static void collect_profile(pf_handle h)
 // ------------------------------------------------------------------ host-side model setup
 static NRow make_row(const pf_filter_s *f, long long n)
 {
-    return make_nrow(f->cfg.kappa0, f->cfg.nu0, f->cfg.alpha, f->d, n);
+    return make_nrow(f->cfg.kappa0, f->cfg.nu0, f->cfg.alpha, f->d, n, f->sp_kind == PF_SP_CRP);
 }
 
 static int32_t ensure_table(pf_handle h, long long need)
@@ -217,7 +222,8 @@ extern "C" int32_t pf_destroy(pf_handle h)
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->supers, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
-                    h->peers[0], h->peers[1], h->srec.x, h->srec.m};
+                    h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
+                    h->sp[1].Nsame, h->sp[1].last};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -247,6 +253,15 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (!cfg->mu0) return set_error(nullptr, PF_ERR_ARG, "pf_create: mu0 is null");
     if (cfg->order != PF_ORDER_INDEX && cfg->order != PF_ORDER_SORTED) return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown order");
     if (cfg->history < 0 && cfg->nranks > 1) return set_error(nullptr, PF_ERR_ARG, "pf_create: a sharded handle needs a fixed history capacity (>= 0)");
+    const int spk = cfg->stateprior_kind;
+    if (spk < PF_SP_CRP || spk > PF_SP_NSTATE) return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown stateprior_kind");
+    if (spk != PF_SP_CRP && (cfg->filter_kind != PF_FEARNHEAD || cfg->nranks > 1))
+        return set_error(nullptr, PF_ERR_ARG, "pf_create: state priors other than the CRP run the single-GPU Fearnhead filter");
+    if (spk == PF_SP_STICKY && !(cfg->sp_param >= 0.0 && cfg->sp_param < 1.0)) return set_error(nullptr, PF_ERR_ARG, "pf_create: StickyCRP rho must be in [0, 1)");
+    if (spk == PF_SP_STICKY && cfg->k_max + 2 > PF_MAX_SLOTS) return set_error(nullptr, PF_ERR_ARG, "pf_create: StickyCRP needs k_max <= 62");
+    if (spk == PF_SP_CHANGEPOINT && !(cfg->sp_param >= 0.0 && cfg->sp_param <= 1.0))
+        return set_error(nullptr, PF_ERR_ARG, "pf_create: ChangePoint probability p must be between 0 and 1");      // src/statepriors.jl:169
+    if (spk == PF_SP_NSTATE && (!cfg->sp_counts || cfg->sp_n < 1 || cfg->sp_n > cfg->k_max)) return set_error(nullptr, PF_ERR_ARG, "pf_create: NStatePrior needs 1 <= sp_n <= k_max counts");
     if (cfg->nranks > 1) {
         if (cfg->nranks > PF_MAX_RANKS || cfg->rank < 0 || cfg->rank >= cfg->nranks) return set_error(nullptr, PF_ERR_ARG, "pf_create: bad rank / nranks");
         if (cfg->filter_kind != PF_FEARNHEAD || cfg->order != PF_ORDER_INDEX) return set_error(nullptr, PF_ERR_ARG, "pf_create: sharded runs support the index-order Fearnhead filter");
@@ -265,6 +280,8 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     h->cap = (cfg->n_particles + h->nranks - 1) / h->nranks;
     if (h->nranks > 1) h->cap += 64;                      // equal blocks of ceil(n / G) at every step
     h->F = 2 + d + d * (d + 1) / 2;
+    h->sp_kind = spk;
+    if (spk == PF_SP_NSTATE) h->sp_counts.assign(cfg->sp_counts, cfg->sp_counts + cfg->sp_n);
     h->mu0.assign(cfg->mu0, cfg->mu0 + d);
     h->lam0.assign(d * d, 0.0);
     if (cfg->prior_kind == PF_NIX2) {
@@ -274,7 +291,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         if (!cfg->lambda0) { delete h; return set_error(nullptr, PF_ERR_ARG, "pf_create: lambda0 is null"); }
         h->lam0.assign(cfg->lambda0, cfg->lambda0 + d * d);
     }
-    h->cfg.mu0 = nullptr; h->cfg.lambda0 = nullptr;
+    h->cfg.mu0 = nullptr; h->cfg.lambda0 = nullptr; h->cfg.sp_counts = nullptr;
     std::vector<double> L0(d * d);
     if (!chol_lower(d, h->lam0.data(), L0.data())) { delete h; return set_error(nullptr, PF_ERR_ARG, "pf_create: lambda0 is not positive definite"); }
 
@@ -293,7 +310,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         CT(dmalloc(&h->logw[b], cap));
         CT(dmalloc(&h->Kc[b], cap));
     }
-    CT(dmalloc(&h->V, (size_t)(h->k_max + 1) * cap));
+    CT(dmalloc(&h->V, (size_t)(h->k_max + 2) * cap));
     CT(dmalloc(&h->cnt, cap));
     h->surv_cap = h->nranks > 1 ? std::min<long long>(h->N, cap * (h->k_max + 1)) + 1024 : cap;
     CT(dmalloc(&h->surv_parent, h->surv_cap));
@@ -372,7 +389,21 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     pc.logdet0 = 2.0 * ld;
     h->row0 = make_row(h, 0);
     pc.row0 = h->row0;
+    pc.sp_kind = spk; pc.sp_n = spk == PF_SP_NSTATE ? cfg->sp_n : 0;
+    pc.sp_log_alpha = std::log(cfg->alpha);
+    if (spk == PF_SP_STICKY) pc.sp_logit_rho = std::log(cfg->sp_param / (1.0 - cfg->sp_param));
+    if (spk == PF_SP_CHANGEPOINT) {
+        const double logp = std::log(cfg->sp_param);
+        pc.sp_lp_change = logp;
+        pc.sp_lp_stay = logp < -0.6931471805599453 ? std::log1p(-std::exp(logp)) : std::log(-std::expm1(logp));     // StatsFuns.log1mexp
+    }
+    if (spk == PF_SP_NSTATE) for (int k = 0; k < cfg->sp_n; k++) { pc.sp_counts0[k] = h->sp_counts[k]; pc.sp_total0 += h->sp_counts[k]; }
     CT(cudaMemcpyAsync(h->pc, &pc, sizeof pc, cudaMemcpyHostToDevice, h->stream));
+    if (spk == PF_SP_STICKY)
+        for (int b = 0; b < 2; b++) {
+            CT(dmalloc(&h->sp[b].N, (size_t)h->k_max * cap)); CT(dmalloc(&h->sp[b].Nsame, (size_t)h->k_max * cap)); CT(dmalloc(&h->sp[b].last, (size_t)cap));
+            CT(cudaMemsetAsync(h->sp[b].last, 0, sizeof(int) * cap, h->stream));        // StickyCRP(alpha, rho): last = 1 (src/statepriors.jl:102)
+        }
     {
         int32_t rc = ensure_table(h, 4096);
         if (rc != PF_OK) { g_create_error = h->err; pf_destroy(h); return rc; }
@@ -396,6 +427,19 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(cudaMemcpyAsync(h->st, &st0, sizeof st0, cudaMemcpyHostToDevice, h->stream));
     CT(cudaMemsetAsync(h->logw[0], 0, sizeof(double) * cap, h->stream));   // weight 1.0, src/particle.jl:62
     CT(cudaMemsetAsync(h->Kc[0], 0, sizeof(int) * cap, h->stream));
+    if (spk == PF_SP_NSTATE) {
+        // the particle starts with sp_n EMPTY components (test/labeled.jl:13-18): n = 0, Lambda_n = Lambda_0
+        std::vector<double> slot(h->F, 0.0);
+        slot[1] = pc.logdet0;
+        for (int k = 0; k < d; k++) slot[2 + d + k] = pc.L0_dinv[k];
+        for (int k = 0; k < d * (d - 1) / 2; k++) slot[2 + 2 * d + k] = pc.L0_off[k];
+        for (int j = 0; j < cfg->sp_n; j++)
+            for (int f = 0; f < h->F; f++)
+                CT(cudaMemcpyAsync(h->S[0] + ((size_t)j * h->F + f) * cap, &slot[f], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CT(cudaStreamSynchronize(h->stream));
+        const int Kn = cfg->sp_n;
+        CT(cudaMemcpyAsync(h->Kc[0], &Kn, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
     CT(cudaStreamSynchronize(h->stream));
 #undef CT
     *out = h;
@@ -471,7 +515,8 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     const long long cap = h->cap;
     const int cur = h->cur, nxt = cur ^ 1;
     const long long ub = h->ub_live;                                     // n_live <= ub
-    long long ub_next = ub * (long long)(std::min<long long>(h->k_max, h->steps + 1) + 1);
+    long long ub_next = ub * (long long)(std::max<long long>(std::min<long long>(h->k_max, h->steps + 1), h->sp_kind == PF_SP_NSTATE ? h->cfg.sp_n : 0) +
+                                         (h->sp_kind == PF_SP_STICKY ? 2 : 1));
     if (ub_next > h->N || ub_next < 0) ub_next = h->N;
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) {
@@ -479,11 +524,14 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap;
     }
     h->epoch++;
+    const int forced = h->cur_label;
+    // other state priors and labeled observations: their own expansion kernel, then the classic search
+    const bool sp_path = h->sp_kind != PF_SP_CRP || forced >= 0;
     {
         LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->redo ? 2 : (h->steps == 0 ? 1 : 0), h->sc, h->res, nullptr, 0, h->steps);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->redo ? 2 : (h->steps == 0 ? 1 : 0), h->sc, h->res, nullptr, 0, h->steps, forced);
     }
-    const bool fused = h->fused && h->cfg.order == PF_ORDER_INDEX;
+    const bool fused = h->fused && h->cfg.order == PF_ORDER_INDEX && !sp_path;
     if (fused) {
         // bracket the threshold on a sample expansion, then classify inside the full expansion
         {
@@ -515,8 +563,12 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     } else {
         {
             LaunchTimer lt(h, KC_EXPAND);
-            k_expand<D, 0><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                       h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
+            if (sp_path)
+                k_expand_sp<D><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc, h->stc,
+                                                                          h->st, h->V, h->cnt, h->sc, h->sp[cur], h->steps);
+            else
+                k_expand<D, 0><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                           h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
         }
         {
             LaunchTimer lt(h, KC_SELECT, 3 + 2 * (h->retries + 1));
@@ -565,7 +617,8 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         LaunchTimer lt(h, KC_INSTANTIATE);
         k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
-                                                                          h->surv_slot, ga, gs, nullptr, h->k_max, h->sc, &h->st->M_next, nullptr, 0);
+                                                                          h->surv_slot, ga, gs, nullptr, h->k_max, h->sc, &h->st->M_next, nullptr, 0,
+                                                                          h->sp[cur], h->sp[nxt]);
     }
     {
         LaunchTimer lt(h, KC_STEPLOG);
@@ -645,12 +698,18 @@ static int32_t ensure_history(pf_handle h, long long need)
     return PF_OK;
 }
 
-static int32_t run_steps(pf_handle h, const double *ys, long long T, const double *uniforms, long long ups, double *log_evidence)
+static int32_t run_steps(pf_handle h, const double *ys, long long T, const double *uniforms, long long ups, double *log_evidence,
+                         const int32_t *labels = nullptr)
 {
     if (!h) return PF_ERR_ARG;
     if (T < 0 || (!ys && T > 0)) return set_error(h, PF_ERR_ARG, "pf_filter: bad ys/T");
     if (T == 0) return PF_OK;
     const bool fh = h->cfg.filter_kind == PF_FEARNHEAD;
+    if (labels) {
+        if (!fh || h->nranks > 1) return set_error(h, PF_ERR_ARG, "labeled observations run the single-GPU Fearnhead filter");
+        for (long long t = 0; t < T; t++)
+            if (labels[t] < -1 || labels[t] >= h->k_max) return set_error(h, PF_ERR_ARG, "label out of range (0-based component, or -1 for missing)");
+    }
     if (uniforms) {
         long long need = fh ? 1 : 2 * h->N;
         if (ups < need) return set_error(h, PF_ERR_ARG, fh ? "pf_filter: Fearnhead needs 1 uniform per step" : "pf_filter: Chen-Liu needs 2*N uniforms per step");
@@ -700,8 +759,9 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
         for (long long t = t_begin; t < T; t++) {
             ub_hist[t] = h->ub_live;
             if (fh) {
+                h->cur_label = labels ? labels[t] : -1;
                 DISPATCH_D(d, rc = fearnhead_step<D>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t));
-                h->redo = 0; h->retries = SEL_RETRIES;
+                h->redo = 0; h->retries = SEL_RETRIES; h->cur_label = -1;
             } else {
                 const double *ud = nullptr;
                 if (uniforms) {
@@ -718,6 +778,12 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
         if (!halt[0]) break;
         const long long th = halt[0] - 1 - steps0;          // index of the halted step within this call
         const int reason = (int)(halt[1] & 0xffffffffll);
+        if (reason == PF_HALT_LABEL) {
+            // (the handle stays halted at that observation: like the reference's ArgumentError, the filter is not usable further)
+            char buf[160];
+            snprintf(buf, sizeof buf, "can't fit the labelled component of observation %lld: it is not a candidate state of every particle", halt[0] - 1);
+            return set_error(h, PF_ERR_ARG, buf);           // ArgumentError, src/particle.jl:137-139
+        }
         if (th < 0 || th >= T || reason != PF_HALT_SEARCH || attempt >= 3) {
             char buf[160];
             snprintf(buf, sizeof buf, "step %lld could not be completed on the device (reason %d, attempt %d)", halt[0] - 1, reason, attempt);
@@ -757,6 +823,31 @@ extern "C" int32_t pf_filter(pf_handle h, const double *ys, int64_t T, const dou
                              double *log_evidence)
 {
     return run_steps(h, ys, T, uniforms, uniforms_per_step, log_evidence);
+}
+
+extern "C" int32_t pf_filter_labeled(pf_handle h, const double *ys, const int32_t *labels, int64_t T, const double *uniforms,
+                                     int64_t uniforms_per_step, double *log_evidence)
+{
+    return run_steps(h, ys, T, uniforms, uniforms_per_step, log_evidence, labels);
+}
+
+extern "C" int32_t pf_get_stateprior(pf_handle h, int64_t i, double *N, double *Nsame, int32_t *last)
+{
+    if (!h) return PF_ERR_ARG;
+    if (h->sp_kind != PF_SP_STICKY) return set_error(h, PF_ERR_STATE, "pf_get_stateprior: only the StickyCRP keeps counts of its own");
+    if (i < 0 || i >= h->n_host) return set_error(h, PF_ERR_ARG, "pf_get_stateprior: index out of range");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    int K = 0, l = 0;
+    CUDA_TRY(cudaMemcpyAsync(&K, h->Kc[h->cur] + i, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(&l, h->sp[h->cur].last + i, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (K > 0) {
+        if (N) CUDA_TRY(cudaMemcpy2DAsync(N, sizeof(double), h->sp[h->cur].N + i, sizeof(double) * h->cap, sizeof(double), (size_t)K, cudaMemcpyDeviceToHost, h->stream));
+        if (Nsame) CUDA_TRY(cudaMemcpy2DAsync(Nsame, sizeof(double), h->sp[h->cur].Nsame + i, sizeof(double) * h->cap, sizeof(double), (size_t)K, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (last) *last = l;
+    return PF_OK;
 }
 
 // ------------------------------------------------------------------ read-out
@@ -897,7 +988,7 @@ extern "C" int32_t pf_get_putative_weights(pf_handle h, double *out, int64_t cap
     if (!h || !M_out) return PF_ERR_ARG;
     if (!h->have_last || h->cfg.filter_kind != PF_FEARNHEAD) return set_error(h, PF_ERR_STATE, "pf_get_putative_weights: needs a Fearnhead step");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const long long n_in = h->last.n_in, slots = h->k_max + 1;
+    const long long n_in = h->last.n_in, slots = h->k_max + 2;
     std::vector<unsigned char> c(n_in);
     CUDA_TRY(cudaMemcpyAsync(c.data(), h->cnt, n_in, cudaMemcpyDeviceToHost, h->stream));
     std::vector<double> v((size_t)slots * n_in);
@@ -1268,7 +1359,7 @@ static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
-        k_instantiate<D><<<grid_for(h->surv_cap, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
+        k_instantiate<D><<<grid_for(std::min<long long>(h->surv_cap, h->cap + h->cap / 4), 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
                                                                               h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
                                                                               h->surv_slot, ga, gs, h->ro, h->k_max, h->sc, &h->st->M_next, h->peers[nxt],
                                                                               (long long)h->steps * h->cap);

@@ -127,7 +127,8 @@ struct SelScratch {
 enum { PF_HALT_SEARCH = 1,          // the threshold search needed more rounds than were queued
        PF_HALT_TIMEOUT = 2,         // a peer's flag did not arrive (sharded run)
        PF_HALT_XCH_OVERFLOW = 3,    // a sample / candidate list outgrew its exchange segment (sharded run)
-       PF_HALT_SURVIVORS = 4 };     // a shard produced more survivors than its survivor list holds
+       PF_HALT_SURVIVORS = 4,       // a shard produced more survivors than its survivor list holds
+       PF_HALT_LABEL = 5 };         // a labeled observation named a state that is not a candidate (ArgumentError, src/particle.jl:137-139)
 
 // the accumulator block of SelScratch as a stand-alone record (sharded runs exchange one per rank)
 struct SelAcc {

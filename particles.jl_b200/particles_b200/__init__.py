@@ -29,7 +29,8 @@ from . import _lib
 from ._lib import (PF_CHENLIU, PF_FEARNHEAD, PF_NIW, PF_NIX2, PF_ORDER_INDEX, PF_ORDER_SORTED, PFError, pf_config,
                    pf_step_stats)
 
-__all__ = ["NormalInverseChisq", "NormalInverseWishart", "ChineseRestaurantProcess", "Component",
+__all__ = ["NormalInverseChisq", "NormalInverseWishart", "ChineseRestaurantProcess", "StickyCRP", "ChangePoint", "NStatePrior",
+           "Labeled", "Component",
            "InfiniteParticle", "ParticleFilter", "FearnheadParticles", "ChenLiuParticles", "fit_", "filter_",
            "particles", "weight", "nobs", "ncomponents", "components", "assignments", "ncomponents_dist",
            "assignment_similarity", "randindex", "select", "PF_ORDER_INDEX", "PF_ORDER_SORTED", "PFError"]
@@ -70,6 +71,42 @@ class ChineseRestaurantProcess:
     def __init__(self, alpha, N=None):
         self.alpha = float(alpha)
         self.N = np.zeros(0) if N is None else np.asarray(N, dtype=np.float64)
+
+
+class StickyCRP:
+    """StickyCRP(alpha, rho) (src/statepriors.jl:93-145): with probability rho the state repeats the previous one,
+    otherwise it is drawn from a CRP.  N counts the non-sticky occupations, Nsame the transitions to the same
+    state, `last` is the previous component (1-based here, as in the reference)."""
+
+    def __init__(self, alpha, rho, last=1, N=None, Nsame=None):
+        self.alpha, self.rho, self.last = float(alpha), float(rho), int(last)
+        self.N = np.zeros(0) if N is None else np.asarray(N, dtype=np.float64)
+        self.Nsame = np.zeros(0) if Nsame is None else np.asarray(Nsame, dtype=np.float64)
+
+
+class ChangePoint:
+    """ChangePoint(p) (src/statepriors.jl:162-190): the state either stays (log(1-p)) or moves to a new one (log p)."""
+
+    def __init__(self, p, k=0, n=0):
+        if not 0.0 <= float(p) <= 1.0:
+            raise ValueError(f"ChangePoint probability p must be between 0 and 1 (got p={p})")        # ArgumentError, :169
+        self.p, self.logp, self.k, self.n = float(p), (math.log(p) if p > 0 else -math.inf), int(k), int(n)
+
+
+class NStatePrior:
+    """NStatePrior(counts) (src/statepriors.jl:203-221): a fixed number of states; the particles start with one empty
+    component per state (test/labeled.jl:13-18)."""
+
+    def __init__(self, counts):
+        self.counts = np.asarray(counts, dtype=np.float64).copy()
+        self.total_count, self.n = float(self.counts.sum()), len(self.counts)
+
+
+class Labeled:
+    """Labeled(obs, label) (src/labeled.jl:1-8): label = 1-based component, or None for missing."""
+
+    def __init__(self, obs, label=None):
+        self.obs, self.label = obs, (None if label is None else int(label))
 
 
 class Component:
@@ -121,7 +158,15 @@ class InfiniteParticle:
 
     @property
     def stateprior(self):
-        return ChineseRestaurantProcess(self._ps.stateprior.alpha, [c.n for c in self.components])
+        sp = self._ps.stateprior
+        if isinstance(sp, StickyCRP):
+            N, Nsame, last = self._ps._read_stateprior(self._i, self.K)
+            return StickyCRP(sp.alpha, sp.rho, last + 1, N, Nsame)
+        if isinstance(sp, ChangePoint):
+            return ChangePoint(sp.p, self.K, self._ps.n_steps)
+        if isinstance(sp, NStatePrior):
+            return NStatePrior(sp.counts + np.array([c.n for c in self.components], dtype=np.float64))
+        return ChineseRestaurantProcess(sp.alpha, [c.n for c in self.components])
 
 
 # ------------------------------------------------------------------ filters
@@ -134,8 +179,8 @@ class ParticleFilter:
                  rejuv=50.0, on_overflow="warn"):
         if isinstance(prior, tuple):
             prior = NormalInverseChisq(*prior)                      # Component(params::NTuple), src/component.jl:8
-        if not isinstance(stateprior, ChineseRestaurantProcess):
-            raise ValueError("only ChineseRestaurantProcess state priors are on the accelerated path")
+        if not isinstance(stateprior, (ChineseRestaurantProcess, StickyCRP, ChangePoint, NStatePrior)):
+            raise ValueError("stateprior must be a ChineseRestaurantProcess, StickyCRP, ChangePoint or NStatePrior")
         self.N, self.prior, self.stateprior = int(n), prior, stateprior
         self.k_max, self.order, self.history = int(k_max), order, int(history)
         self.rejuvination_threshold = float(rejuv)
@@ -151,7 +196,14 @@ class ParticleFilter:
         cfg.order = order
         cfg.history = self.history
         cfg.device = device
-        cfg.alpha = stateprior.alpha
+        cfg.alpha = getattr(stateprior, "alpha", 1.0)
+        if isinstance(stateprior, StickyCRP):
+            cfg.stateprior_kind, cfg.sp_param = _lib.PF_SP_STICKY, stateprior.rho
+        elif isinstance(stateprior, ChangePoint):
+            cfg.stateprior_kind, cfg.sp_param = _lib.PF_SP_CHANGEPOINT, stateprior.p
+        elif isinstance(stateprior, NStatePrior):
+            self._spc = stateprior.counts.copy()
+            cfg.stateprior_kind, cfg.sp_n, cfg.sp_counts = _lib.PF_SP_NSTATE, stateprior.n, self._spc.ctypes.data_as(_dp)
         cfg.rejuv_threshold = self.rejuvination_threshold
         cfg.seed = seed
         if isinstance(prior, NormalInverseChisq):
@@ -187,7 +239,9 @@ class ParticleFilter:
 
     # --- stepping
     def fit_(self, y, uniforms=None):
-        """fit!(ps, y) (src/fearnhead.jl:130, src/chenliu.jl:54)."""
+        """fit!(ps, y) (src/fearnhead.jl:130, src/chenliu.jl:54); y may be Labeled(obs, label) (src/labeled.jl)."""
+        if isinstance(y, Labeled):
+            return self.filter_([y], uniforms=None if uniforms is None else np.atleast_2d(uniforms))
         y, py = _d(np.atleast_1d(y))
         if len(y) != self.d:
             raise ValueError(f"observation has {len(y)} entries, the prior has dimension {self.d}")
@@ -219,6 +273,11 @@ class ParticleFilter:
     def filter_(self, ys, progress=False, cb=None, uniforms=None):
         """filter!(ps, ys, progress; cb) (src/filters.jl:6-13).  Without a callback the whole
         stream is one library call; with one, the callback sees the filter after every y."""
+        labels = None
+        if len(ys) and isinstance(ys[0], Labeled):
+            # Labeled.(ys, labels): 1-based labels, None = missing  ->  0-based / -1 across the ABI
+            labels = np.array([-1 if y.label is None else y.label - 1 for y in ys], dtype=np.int32)
+            ys = [y.obs for y in ys]
         ys = np.asarray(ys, dtype=np.float64)
         if ys.ndim == 1 and self.d == 1:
             ys = ys.reshape(-1, 1)
@@ -229,12 +288,17 @@ class ParticleFilter:
             uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(T, -1)
         if cb is not None:
             for t in range(T):
-                self.fit_(ys[t], None if uniforms is None else uniforms[t])
+                yt = ys[t] if labels is None else Labeled(ys[t], None if labels[t] < 0 else int(labels[t]) + 1)
+                self.fit_(yt, None if uniforms is None else uniforms[t])
                 cb(self, ys[t])
             return self
         ysc, pys = _d(ys)                    # row t = observation t == column-major d x T
         le = np.empty(T)
-        if uniforms is None:
+        if labels is not None:
+            pu, ups = (None, 0) if uniforms is None else (uniforms.ctypes.data_as(_dp), uniforms.shape[1])
+            _lib.check(self._L.pf_filter_labeled(self._h, pys, labels.ctypes.data_as(C.POINTER(C.c_int32)), T, pu, ups,
+                                                 le.ctypes.data_as(_dp)), self._h)
+        elif uniforms is None:
             _lib.check(self._L.pf_filter(self._h, pys, T, None, 0, le.ctypes.data_as(_dp)), self._h)
         else:
             _lib.check(self._L.pf_filter(self._h, pys, T, uniforms.ctypes.data_as(_dp), uniforms.shape[1],
@@ -275,6 +339,12 @@ class ParticleFilter:
         return [Component(self.prior, counts[j], means[j].copy(), chol[j].T.copy(), logdet[j])
                 for j in range(K.value)]
 
+    def _read_stateprior(self, i, K):
+        N, Nsame = np.zeros(max(K, 1)), np.zeros(max(K, 1))
+        last = C.c_int32()
+        _lib.check(self._L.pf_get_stateprior(self._h, i, N.ctypes.data_as(_dp), Nsame.ctypes.data_as(_dp), C.byref(last)), self._h)
+        return N[:K].copy(), Nsame[:K].copy(), last.value
+
     def particles(self):
         """particles(ps) (src/filters.jl:15)."""
         lw, K = self.logweights(), self.ncomponents()
@@ -294,7 +364,7 @@ class ParticleFilter:
 
     def putative_weights(self):
         M = C.c_int64()
-        cap = len(self) * (self.k_max + 1) + self.N * (self.k_max + 1)
+        cap = len(self) * (self.k_max + 2) + self.N * (self.k_max + 2)
         out = np.empty(cap)
         _lib.check(self._L.pf_get_putative_weights(self._h, out.ctypes.data_as(_dp), cap, C.byref(M)), self._h)
         return out[:M.value].copy()

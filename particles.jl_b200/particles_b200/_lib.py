@@ -14,6 +14,7 @@ PF_FEARNHEAD, PF_CHENLIU = 0, 1
 PF_NIX2, PF_NIW = 0, 1
 PF_F64, PF_F32 = 0, 1
 PF_ORDER_INDEX, PF_ORDER_SORTED = 0, 1
+PF_SP_CRP, PF_SP_STICKY, PF_SP_CHANGEPOINT, PF_SP_NSTATE = 0, 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
 
@@ -21,10 +22,11 @@ _dp = C.POINTER(C.c_double)
 class pf_config(C.Structure):
     _fields_ = [("filter_kind", C.c_int32), ("prior_kind", C.c_int32), ("d", C.c_int32), ("precision", C.c_int32),
                 ("n_particles", C.c_int64), ("k_max", C.c_int32), ("order", C.c_int32), ("history", C.c_int64),
-                ("device", C.c_int32), ("reserved0", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("device", C.c_int32), ("stateprior_kind", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("alpha", C.c_double),
                 ("rejuv_threshold", C.c_double), ("kappa0", C.c_double), ("nu0", C.c_double),
-                ("sigma2_0", C.c_double), ("mu0", _dp), ("lambda0", _dp), ("seed", C.c_uint64)]
+                ("sigma2_0", C.c_double), ("mu0", _dp), ("lambda0", _dp), ("seed", C.c_uint64),
+                ("sp_param", C.c_double), ("sp_counts", _dp), ("sp_n", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class pf_step_stats(C.Structure):
@@ -51,6 +53,8 @@ SYMBOLS = [
     ("pf_last_error", C.c_char_p, [C.c_void_p]),
     ("pf_step", C.c_int32, [C.c_void_p, _dp, _dp, C.c_int64]),
     ("pf_filter", C.c_int32, [C.c_void_p, _dp, C.c_int64, _dp, C.c_int64, _dp]),
+    ("pf_filter_labeled", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int32), C.c_int64, _dp, C.c_int64, _dp]),
+    ("pf_get_stateprior", C.c_int32, [C.c_void_p, C.c_int64, _dp, _dp, C.POINTER(C.c_int32)]),
     ("pf_n_particles", C.c_int64, [C.c_void_p]),
     ("pf_n_steps", C.c_int64, [C.c_void_p]),
     ("pf_get_logweights", C.c_int32, [C.c_void_p, _dp]),

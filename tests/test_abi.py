@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.pf_config) == 120
+    assert C.sizeof(_lib.pf_config) == 144
     assert C.sizeof(_lib.pf_step_stats) == 8 * 8 + 4 * 8 + 2 * 4 + 8 + 4 * 8 + 8 + 2 * 4
 
 

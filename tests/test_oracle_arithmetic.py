@@ -226,3 +226,96 @@ def test_crp_counts():
     f.fh_commit([1], [1.0])            # new table -> N = [2., 1.]
     assert f.particle(0)[1].tolist() == [2.0, 1.0]
     assert f.fh_expand(0.4) == 3       # candidates 1:3
+
+
+# ------------------------------------------------------------------ other state priors (src/statepriors.jl:93-221)
+def _nix2():
+    return orc.Prior.nix2(0.0, 1.0, 2.0, 3.0)
+
+
+def test_sticky_crp_with_rho_0_is_the_crp():
+    """test/statepriors.jl:36-51: with rho = 0 the sticky CRP's non-sticky candidates carry the CRP's log-priors
+    (the sticky candidate has log-prior -inf) and the filters agree."""
+    rng = np.random.default_rng(3)
+    ys = np.where(rng.random(40) < 0.5, -2.0, 2.0) + rng.standard_normal(40)
+    us = rng.random(40)
+    a = orc.OracleFilter(orc.FEARNHEAD, 30, _nix2(), 0.5, order=orc.ORDER_INDEX)
+    b = orc.OracleFilter(orc.FEARNHEAD, 30, _nix2(), 0.5, order=orc.ORDER_INDEX, stateprior=("sticky", 0.5, 0.0))
+    for t, (y, u) in enumerate(zip(ys, us)):
+        if t:
+            i0 = int(np.argmax(b.weights() > 0))          # first live particle of the sticky filter = particle 0 of the CRP one
+            assert b.sp_candidates(i0) == [0] + a.sp_candidates(0)
+            assert b.sp_log_prior(i0, 0) == -np.inf
+            assert [b.sp_log_prior(i0, x) for x in a.sp_candidates(0)] == [a.sp_log_prior(0, x) for x in a.sp_candidates(0)]
+        else:
+            assert b.sp_candidates(0) == [1] == a.sp_candidates(0)            # isempty: 1:1, src/statepriors.jl:105
+        a.fh_step(y, u)
+        b.fh_step(y, u)
+        live = b.weights() > 0                # (the sticky putatives have weight exp(-inf) = 0; they are kept while M <= N)
+        assert np.array_equal(a.ncomponents(), b.ncomponents()[live])
+        np.testing.assert_allclose(a.weights(), b.weights()[live], rtol=1e-12)
+        if t > 8:
+            break
+
+
+def test_sticky_crp_bookkeeping():
+    """test/statepriors.jl:53-62 and the rules of src/statepriors.jl:106-128: a sticky visit leaves N alone, any
+    repeat of the previous state counts in Nsame, `last` follows the assignment; log-prior of the sticky candidate
+    is logit(rho) + log(sum(N) + alpha) (:133-135); an invalid state is an ArgumentError (:141)."""
+    f = orc.OracleFilter(orc.FEARNHEAD, 1000, _nix2(), 0.5, order=orc.ORDER_INDEX, stateprior=("sticky", 0.5, 0.9))
+    f.fh_step(0.3, 0.5)                      # first observation: one candidate, a new component, not sticky
+    st, N = f.particle(0)
+    assert N.tolist() == [1.0] and f.sticky(0)[1] == 1 and f.sticky(0)[0].tolist() == [1.0]      # x == last (initially 1): Nsame counts it, :119-121
+    f.fh_step(0.1, 0.5)                      # candidates 0 (stick to 1), 1, 2
+    assert f.n == 3
+    (_, N0), (_, N1), (_, N2) = f.particle(0), f.particle(1), f.particle(2)
+    assert N0.tolist() == [1.0] and N1.tolist() == [2.0] and N2.tolist() == [1.0, 1.0]      # sticky: N unchanged
+    assert f.sticky(0)[0].tolist() == [2.0] and f.sticky(1)[0].tolist() == [2.0] and f.sticky(2)[0].tolist() == [1.0, 0.0]
+    assert [f.sticky(i)[1] for i in range(3)] == [1, 1, 2]
+    assert [int(a) for a in f.last_assignments()] == [1, 1, 2]
+    assert f.sp_log_prior(1, 0) == pytest.approx(math.log(0.9 / 0.1) + math.log(2.0 + 0.5))
+    assert f.sp_log_prior(1, 1) == pytest.approx(math.log(2.0)) and f.sp_log_prior(1, 2) == pytest.approx(math.log(0.5))
+    assert math.isnan(f.sp_log_prior(1, 3))
+
+
+def test_changepoint_prior():
+    """src/statepriors.jl:162-190: candidates max(k,1):k+1, log-prior 0 for the first point, then log(1-p) to stay
+    and log(p) to change; p outside [0, 1] is an ArgumentError (:169)."""
+    f = orc.OracleFilter(orc.FEARNHEAD, 100, _nix2(), 1.0, order=orc.ORDER_INDEX, stateprior=("changepoint", 0.2))
+    assert f.sp_candidates(0) == [1] and f.sp_log_prior(0, 1) == 0.0
+    f.fh_step(0.0, 0.5)
+    assert f.sp_candidates(0) == [1, 2]
+    assert f.sp_log_prior(0, 1) == pytest.approx(math.log(0.8)) and f.sp_log_prior(0, 2) == pytest.approx(math.log(0.2))
+    for y in (0.1, 5.0, 5.2):
+        f.fh_step(y, 0.5)
+    assert f.n == 8                           # 2^(T-1) segmentations
+    A = f.assignments()
+    assert np.all(np.diff(A, axis=0) >= 0) and np.all(np.diff(A, axis=0) <= 1) and np.all(A[0] == 1)
+    # the change between the 2nd and 3rd observation is the most probable segmentation
+    assert A[:, int(np.argmax(f.weights()))].tolist() == [1, 1, 2, 2]
+    with pytest.raises(ValueError):
+        orc.OracleFilter(orc.FEARNHEAD, 10, _nix2(), 1.0, stateprior=("changepoint", 1.5))
+
+
+def test_nstate_prior_and_labeled_observations():
+    """test/labeled.jl:21-64: NStatePrior([1, 1]) particles with two empty components; a labeled observation has the
+    single putative fit(p, y, label) (src/labeled.jl:10-11); missing labels filter like plain observations."""
+    rng = np.random.default_rng(11)
+    ys = np.where(rng.random(20) < 0.5, -2.0, 2.0) + rng.standard_normal(20)
+    labels = np.where(ys > 0, 1, 2)
+    us = rng.random(20)
+    mk = lambda: orc.OracleFilter(orc.FEARNHEAD, 10, _nix2(), 1.0, order=orc.ORDER_SORTED, stateprior=("nstate", [1.0, 1.0]))
+    f1, f2, f3 = mk(), mk(), mk()
+    assert f1.sp_candidates(0) == [1, 2]
+    assert f1.sp_log_prior(0, 1) == pytest.approx(math.log(0.5))
+    for y, u, lab in zip(ys, us, labels):
+        f1.fh_step(y, u)
+        f2.fh_step_labeled(y, u, None)        # "filter equivalence with missing"
+        f3.fh_step_labeled(y, u, int(lab))    # "filtering with labels"
+    np.testing.assert_array_equal(f1.weights(), f2.weights())
+    assert np.array_equal(f1.assignments(), f2.assignments())
+    assert f3.n == 1                          # only one particle
+    st, counts = f3.particle(0)
+    assert [int(r[0]) for r in st] == [int((labels == 1).sum()), int((labels == 2).sum())]     # nobs.(pp.components)
+    assert counts.tolist() == [1.0 + (labels == 1).sum(), 1.0 + (labels == 2).sum()]
+    assert f3.assignments()[:, 0].tolist() == labels.tolist()
