@@ -149,6 +149,33 @@ int32_t pf_get_stateprior(pf_handle h, int64_t i, double *N, double *Nsame, int3
 int32_t pf_get_assignments(pf_handle h, int32_t *out);
 int32_t pf_get_last_step(pf_handle h, pf_step_stats *out);
 
+/* ---- filter-level summaries, evaluated on the device-resident population ------------------ */
+/* posterior_predictive(ps), src/filters.jl:22-24 with src/particle.jl:156-172 and src/component.jl:12-23: the density
+ * of the next observation, sum_i w_i sum_j pi_ij t_ij(x), at the Q query points xs[d x Q] (column-major).  out[Q].
+ * ChineseRestaurantProcess state prior. */
+int32_t pf_posterior_predictive(pf_handle h, const double *xs, int64_t Q, double *out);
+/* mean(f, ps), src/filters.jl:17-18, for the two per-particle functions the reference ships:
+ * ncomponents (src/particle.jl:157-158) and state_entropy (src/particle.jl:162, src/filters.jl:20). */
+enum { PF_MEAN_NCOMPONENTS = 0, PF_MEAN_STATE_ENTROPY = 1 };
+int32_t pf_weighted_mean(pf_handle h, int32_t what, double *out);
+/* ncomponents_dist(ps), src/filters.jl:36-37: out[k] = weighted share of the particles with k components, k = 0..k_max. */
+int32_t pf_ncomponents_dist(pf_handle h, double *out /* [k_max + 1] */);
+/* assignment_similarity(ps), src/filters.jl:39-42: out[T x T] = 1 - Hamming(assignments of s, of t) / n.  Needs history. */
+int32_t pf_assignment_similarity(pf_handle h, double *out);
+/* randindex(ps, truth, type), src/filters.jl:53-80: truth[T] labels; adjusted != 0 -> :adjusted.  T != observations
+ * filtered is the DimensionMismatch of :57-58: PF_ERR_ARG. */
+int32_t pf_randindex(pf_handle h, const int32_t *truth, int64_t T, int32_t adjusted, double *out);
+
+/* ---- checkpoint / restore -------------------------------------------------- */
+/* The whole state of a single-GPU handle (population, control blocks, genealogy, step counter) in one file;
+ * a loaded handle continues bit for bit where the saved one stopped. */
+int32_t pf_save(pf_handle h, const char *path);
+int32_t pf_load(const char *path, int32_t device, pf_handle *out);
+/* The configuration a handle was created (or loaded) with; the array members of *out are NULL, pf_get_prior copies
+ * them: mu0[d], lambda0[d x d] (NIX2: nu0 sigma2_0), sp_counts[sp_n]. */
+int32_t pf_get_config(pf_handle h, pf_config *out);
+int32_t pf_get_prior(pf_handle h, double *mu0, double *lambda0, double *sp_counts);
+
 /* ---- debugging taps used by the parity tests ------------------------------------------ */
 /* Putative weights exp(logweight) of the LAST step (src/particle.jl:114) in
  * particle-major / candidate-minor order (src/fearnhead.jl:132); *M receives their count. */
@@ -205,6 +232,10 @@ int32_t pf_mg_connect(pf_handle *hs, int32_t n_local);
 int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys, int64_t T, const double *uniforms,
                      int64_t uniforms_per_step, double *log_evidence);
 int64_t pf_mg_n_global(pf_handle h);          /* population over all shards */
+/* assignments(ps) (src/filters.jl:26-34) of this shard's particles: out[T x pf_n_particles(h)] column-major, 0-based.
+ * A particle's ancestor chain is followed through the genealogy arrays of whichever rank owned each ancestor (peer
+ * memory); the shards' blocks concatenated in rank order are the unsharded filter's matrix.  Needs history. */
+int32_t pf_mg_get_assignments(pf_handle h, int32_t *out);
 int32_t pf_mg_create_local(const pf_config *cfg, const int32_t *devices, int32_t n, pf_handle *out /* [n] */);
 /* Raw control-block words of the last threshold search / survivor scan (debugging aid). */
 int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */);

@@ -328,6 +328,82 @@ class OracleFilter:
         return lib().orc_marginal_log_posterior(self.h, i)
 
 
+    # ---- filter-level summaries (src/filters.jl:17-42, 53-80), restated on the oracle's population
+    def sp_weights(self, i):
+        """weights(p) = exp.(log_prior(p.stateprior)) (src/particle.jl:160, src/statepriors.jl:24-29): the normalised
+        prior over the candidate states of particle i."""
+        lp = np.array([self.sp_log_prior(i, x) for x in self.sp_candidates(i)])
+        m = lp.max()
+        return np.exp(lp - (m + np.log(np.exp(lp - m).sum())))             # StatsFuns.logsumexp
+
+    def state_entropy(self):
+        """state_entropy(ps) = mean(state_entropy, ps) (src/filters.jl:17-20); state_entropy(p) = entropy of weights(p)
+        (src/particle.jl:162, src/statepriors.jl:36; StatsBase.entropy = -sum(p log p), 0 log 0 = 0)."""
+        w = self.weights()
+        H = np.empty(self.n)
+        for i in range(self.n):
+            p = self.sp_weights(i)
+            p = p[p > 0]
+            H[i] = -(p * np.log(p)).sum()
+        return float((H * w).sum() / w.sum())
+
+    def mean_ncomponents(self):
+        """mean(ncomponents, ps) (src/filters.jl:17-18)."""
+        w = self.weights()
+        return float((self.ncomponents() * w).sum() / w.sum())
+
+    def ncomponents_dist(self):
+        """ncomponents_dist(ps) = fit(Categorical, ncomponents, weights) (src/filters.jl:36-37): p[k-1] = weighted share
+        of the particles with k components, k = 1..max."""
+        K, w = self.ncomponents(), self.weights()
+        return np.bincount(K, weights=w, minlength=1)[1:] / w.sum()
+
+    def posterior_predictive(self, xs):
+        """pdf(posterior_predictive(ps), x) (src/filters.jl:22-24): mixture over particles (normalised weights) of
+        MixtureModel(posterior_predictive.(components(p)), weights(p)) (src/particle.jl:156-172), components(p) =
+        [p.components..., p.prior]; the component's predictive is src/component.jl:12-23 (orc_logpred)."""
+        xs = np.atleast_2d(np.asarray(xs, dtype=np.float64))
+        if self.prior.d == 1 and xs.shape[0] == 1 and xs.shape[1] != 1:
+            xs = xs.T
+        w = self.weights()
+        w = w / w.sum()
+        out = np.zeros(len(xs))
+        empty = self.prior.empty()
+        for i in range(self.n):
+            st, _ = self.particle(i)
+            pi = self.sp_weights(i)
+            assert len(pi) == len(st) + 1
+            for q, x in enumerate(xs):
+                dens = sum(pi[j] * np.exp(self.prior.logpred(st[j], x)) for j in range(len(st)))
+                dens += pi[-1] * np.exp(self.prior.logpred(empty, x))
+                out[q] += w[i] * dens
+        return out
+
+    def assignment_similarity(self):
+        """assignment_similarity(ps) (src/filters.jl:39-42): 1 .- pairwise(Hamming(), as, dims=1) ./ size(as, 2)."""
+        a = self.assignments()
+        T, n = a.shape
+        ham = np.array([[(a[s] != a[t]).sum() for t in range(T)] for s in range(T)], dtype=np.float64)
+        return 1.0 - ham / n
+
+    def randindex(self, truth, kind="adjusted"):
+        """randindex(ps, truth, type) (src/filters.jl:53-80)."""
+        truth = np.asarray(truth)
+        ps_sim = self.assignment_similarity()
+        truth_sim = (truth[:, None] == truth[None, :]).astype(np.float64)
+        if truth_sim.shape != ps_sim.shape:
+            raise ValueError("Ground truth and particles have different number of obs!")        # DimensionMismatch, :57-58
+        N = ps_sim.size
+        nis, njs = ps_sim.sum(), truth_sim.sum()
+        both_same = (ps_sim * truth_sim).sum()
+        both_diff = N - nis - njs + both_same
+        if kind == "adjusted":
+            n = len(truth)
+            nc = (n * (n ** 2 + 1) - (n + 1) * nis - (n + 1) * njs + 2 * (nis * njs) / n) / (2 * (n - 1))
+            return (both_same + both_diff - nc) / (N - nc)
+        return (both_same + both_diff) / N
+
+
 # ---------------------------------------------------------------------------------------
 # stand-alone literal helpers
 

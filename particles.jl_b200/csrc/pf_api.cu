@@ -13,6 +13,7 @@
 #include "fearnhead.cuh"
 #include "chenliu.cuh"
 #include "sort.cuh"
+#include "summaries.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -89,6 +90,7 @@ struct pf_filter_s {
     unsigned char *gen_asg = nullptr;
     long long hist_cap = 0;
     bool hist_auto = false;               // pf_config.history < 0: the genealogy grows on demand
+    std::vector<long long> gen_q;         // sharded run: block length q = ceil(n / G) of the population after each step
     // host mirrors
     long long steps = 0;
     long long n_host = 0;                 // population size after the last synchronised step
@@ -930,16 +932,14 @@ extern "C" int32_t pf_get_particle(pf_handle h, int64_t i, int32_t *K_out, doubl
     return PF_OK;
 }
 
-__global__ void k_backtrack(const unsigned int *__restrict__ gen_anc, const unsigned char *__restrict__ gen_asg, long long cap,
-                            long long T, long long n, int *__restrict__ out /* [T][n] */)
+// assignments(ps), src/filters.jl:26-34: the genealogy is walked on the device into a byte-wide time-major block for
+// a slice of the particles at a time (k_backtrack8), the slices are widened / transposed on the host
+static long long assign_chunk(long long T, long long n)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    long long k = i;
-    for (long long t = T - 1; t >= 0; t--) {          // assignments(p), src/particle.jl:25-32
-        out[t * n + i] = gen_asg[t * cap + k];
-        k = gen_anc[t * cap + k];
-    }
+    long long nc = (1ll << 30) / std::max<long long>(T, 1);          // <= 1 GiB of labels per slice
+    if (getenv("PF_ASSIGN_CHUNK")) return std::max<long long>(1, std::min<long long>(atoll(getenv("PF_ASSIGN_CHUNK")), n));      // tests: force several slices
+    nc = std::max<long long>(nc & ~255ll, 4096);
+    return std::min(nc, (n + 15) & ~15ll);
 }
 
 extern "C" int32_t pf_get_assignments(pf_handle h, int32_t *out)
@@ -950,16 +950,20 @@ extern "C" int32_t pf_get_assignments(pf_handle h, int32_t *out)
     const long long T = h->steps, n = h->n_host;
     if (T == 0 || n == 0) return PF_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    int *tmp = nullptr;
-    CUDA_TRY(dmalloc(&tmp, (size_t)T * n));
-    k_backtrack<<<grid_for(n, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, n, tmp);
-    std::vector<int> host((size_t)T * n);
-    cudaError_t e = cudaMemcpyAsync(host.data(), tmp, sizeof(int) * T * n, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    const long long nc_max = assign_chunk(T, n);
+    unsigned char *tmp = nullptr;
+    CUDA_TRY(dmalloc(&tmp, (size_t)T * nc_max));
+    std::vector<unsigned char> host((size_t)T * nc_max);
+    for (long long i0 = 0; i0 < n; i0 += nc_max) {
+        const long long nc = std::min(nc_max, n - i0);
+        k_backtrack8<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i0, nc, tmp);
+        cudaError_t e = cudaMemcpyAsync(host.data(), tmp, (size_t)T * nc, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { cudaFree(tmp); return set_cuda_error(h, e, "pf_get_assignments", __LINE__); }
+        for (long long c = 0; c < nc; c++)                  // -> column-major T x n
+            for (long long t = 0; t < T; t++) out[(i0 + c) * T + t] = host[(size_t)t * nc + c];
+    }
     cudaFree(tmp);
-    if (e != cudaSuccess) return set_cuda_error(h, e, "pf_get_assignments", __LINE__);
-    for (long long i = 0; i < n; i++)                  // -> column-major T x n
-        for (long long t = 0; t < T; t++) out[i * T + t] = host[t * n + i];
     return PF_OK;
 }
 
@@ -1023,6 +1027,327 @@ extern "C" int32_t pf_get_last_assignments(pf_handle h, int32_t *out)
     CUDA_TRY(cudaMemcpyAsync(a.data(), h->gen_asg + (size_t)(h->steps - 1) * h->cap, h->n_host, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (long long i = 0; i < h->n_host; i++) out[i] = a[i];
+    return PF_OK;
+}
+
+// ------------------------------------------------------------------ filter-level summaries on the device
+// (src/filters.jl:17-42, 53-80; kernels in summaries.cuh)
+struct DevBuf {                  // scoped device allocation
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+static int32_t summary_ready(pf_handle h, const char *who)
+{
+    if (h->nranks > 1) return set_error(h, PF_ERR_STATE, std::string(who) + ": sharded handles are summarised per shard by pf_mg_* read-outs");
+    if (h->n_host < 1) return set_error(h, PF_ERR_STATE, std::string(who) + ": the population is empty");
+    return PF_OK;
+}
+
+template <int D>
+static void launch_predictive(pf_handle h, int nb, const double *xs_dev, int nq, double *part)
+{
+    k_predictive<D><<<nb, SUM_THREADS, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->n_host, h->tab, h->pc, xs_dev, nq, part);
+}
+template <int D>
+static void launch_pop_summary(pf_handle h, int nb, int slots, double *part)
+{
+    k_pop_summary<D><<<nb, SUM_THREADS, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->n_host, slots, h->pc, h->sp[h->cur],
+                                                         (double)h->steps, part);
+}
+
+extern "C" int32_t pf_posterior_predictive(pf_handle h, const double *xs, int64_t Q, double *out)
+{
+    if (!h || (Q > 0 && (!xs || !out)) || Q < 0) return PF_ERR_ARG;
+    int32_t rc = summary_ready(h, "pf_posterior_predictive");
+    if (rc != PF_OK) return rc;
+    if (h->sp_kind != PF_SP_CRP)      // components(p) has K + 1 entries, weights(p) one per candidate state: only the CRP lines them up
+        return set_error(h, PF_ERR_STATE, "pf_posterior_predictive: defined for the ChineseRestaurantProcess state prior (src/particle.jl:156-172)");
+    if (Q == 0) return PF_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int d = h->d;
+    const long long n = h->n_host;
+    const int QB = 64;                                    // query points per pass over the store
+    const long long nb = grid_for(n, SUM_THREADS);
+    DevBuf dx, dpart, dout;
+    CUDA_TRY(dx.alloc(sizeof(double) * Q * d));
+    CUDA_TRY(dpart.alloc(sizeof(double) * nb * (QB + 1)));
+    CUDA_TRY(dout.alloc(sizeof(double) * (QB + 1)));
+    CUDA_TRY(cudaMemcpyAsync(dx.p, xs, sizeof(double) * Q * d, cudaMemcpyHostToDevice, h->stream));
+    const double norm = (double)h->steps + h->cfg.alpha;  // sum_j N_j + alpha, the same for every particle under the CRP
+    for (long long q0 = 0; q0 < Q; q0 += QB) {
+        const int nq = (int)std::min<long long>(QB, Q - q0);
+        DISPATCH_D(d, launch_predictive<D>(h, (int)nb, dx.as<double>() + q0 * d, nq, dpart.as<double>()));
+        k_sum_partials<<<nq + 1, SUM_THREADS, 0, h->stream>>>(dpart.as<double>(), nb, nq + 1, dout.as<double>());
+        double res[QB + 1];
+        CUDA_TRY(cudaMemcpyAsync(res, dout.p, sizeof(double) * (nq + 1), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int q = 0; q < nq; q++) out[q0 + q] = res[q] / res[nq] / norm;
+    }
+    return PF_OK;
+}
+
+// [0] sum w, [1] sum w K, [2] sum w H, [3 + k] weight of the particles with K = k
+static int32_t pop_summary(pf_handle h, std::vector<double> &rec)
+{
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const long long n = h->n_host;
+    const int slots = h->k_max + 1, ncol = 3 + slots;
+    const long long nb = grid_for(n, SUM_THREADS);
+    DevBuf dpart, dout;
+    CUDA_TRY(dpart.alloc(sizeof(double) * nb * ncol));
+    CUDA_TRY(dout.alloc(sizeof(double) * ncol));
+    DISPATCH_D(h->d, launch_pop_summary<D>(h, (int)nb, slots, dpart.as<double>()));
+    k_sum_partials<<<ncol, SUM_THREADS, 0, h->stream>>>(dpart.as<double>(), nb, ncol, dout.as<double>());
+    rec.resize(ncol);
+    CUDA_TRY(cudaMemcpyAsync(rec.data(), dout.p, sizeof(double) * ncol, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PF_OK;
+}
+
+extern "C" int32_t pf_weighted_mean(pf_handle h, int32_t what, double *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    if (what != PF_MEAN_NCOMPONENTS && what != PF_MEAN_STATE_ENTROPY) return set_error(h, PF_ERR_ARG, "pf_weighted_mean: unknown quantity");
+    int32_t rc = summary_ready(h, "pf_weighted_mean");
+    if (rc != PF_OK) return rc;
+    std::vector<double> rec;
+    rc = pop_summary(h, rec);
+    if (rc != PF_OK) return rc;
+    *out = rec[what == PF_MEAN_NCOMPONENTS ? 1 : 2] / rec[0];
+    return PF_OK;
+}
+
+extern "C" int32_t pf_ncomponents_dist(pf_handle h, double *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    int32_t rc = summary_ready(h, "pf_ncomponents_dist");
+    if (rc != PF_OK) return rc;
+    std::vector<double> rec;
+    rc = pop_summary(h, rec);
+    if (rc != PF_OK) return rc;
+    for (int k = 0; k <= h->k_max; k++) out[k] = rec[3 + k] / rec[0];
+    return PF_OK;
+}
+
+// number of particles that give observations s and t the same label, for all pairs (counts[T x T])
+static int32_t similarity_counts(pf_handle h, std::vector<unsigned long long> &counts)
+{
+    if (!h->hist_cap) return set_error(h, PF_ERR_HISTORY, "assignment_similarity: history is disabled (pf_config.history = 0)");
+    const long long T = h->steps, n = h->n_host;
+    counts.assign((size_t)T * T, 0ull);
+    if (T == 0) return PF_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const long long nc_max = assign_chunk(T, n);
+    DevBuf dA, dC;
+    CUDA_TRY(dA.alloc((size_t)T * nc_max));
+    CUDA_TRY(dC.alloc(sizeof(unsigned long long) * T * T));
+    CUDA_TRY(cudaMemsetAsync(dC.p, 0, sizeof(unsigned long long) * T * T, h->stream));
+    const long long ntile = (T + SIM_TILE - 1) / SIM_TILE, npair = ntile * (ntile + 1) / 2;
+    if (npair > 0x7fffffffll) return set_error(h, PF_ERR_ARG, "assignment_similarity: too many observations");
+    for (long long i0 = 0; i0 < n; i0 += nc_max) {
+        const long long nc = std::min(nc_max, n - i0);
+        k_backtrack8<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i0, nc, dA.as<unsigned char>());
+        long long gy = std::max<long long>(1, std::min<long long>((nc / 16 + SUM_THREADS * 4 - 1) / (SUM_THREADS * 4), 4096));
+        if (npair * gy < 2 * h->num_sms) gy = std::min<long long>((2 * h->num_sms + npair - 1) / npair, std::max<long long>(1, (nc + SUM_THREADS - 1) / SUM_THREADS));
+        k_similarity<<<dim3((unsigned)npair, (unsigned)gy), SUM_THREADS, 0, h->stream>>>(dA.as<unsigned char>(), T, nc, dC.as<unsigned long long>());
+    }
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), dC.p, sizeof(unsigned long long) * T * T, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PF_OK;
+}
+
+extern "C" int32_t pf_assignment_similarity(pf_handle h, double *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    int32_t rc = summary_ready(h, "pf_assignment_similarity");
+    if (rc != PF_OK) return rc;
+    std::vector<unsigned long long> c;
+    rc = similarity_counts(h, c);
+    if (rc != PF_OK) return rc;
+    const long long T = h->steps;
+    const double n = (double)h->n_host;
+    for (long long k = 0; k < T * T; k++) out[k] = 1.0 - ((double)(h->n_host - (long long)c[k])) / n;     // 1 - Hamming / n
+    return PF_OK;
+}
+
+extern "C" int32_t pf_randindex(pf_handle h, const int32_t *truth, int64_t T, int32_t adjusted, double *out)
+{
+    if (!h || !truth || !out) return PF_ERR_ARG;
+    int32_t rc = summary_ready(h, "pf_randindex");
+    if (rc != PF_OK) return rc;
+    if (T != h->steps) return set_error(h, PF_ERR_ARG, "Ground truth and particles have different number of obs!");   // DimensionMismatch, src/filters.jl:57-58
+    std::vector<unsigned long long> c;
+    rc = similarity_counts(h, c);
+    if (rc != PF_OK) return rc;
+    // src/filters.jl:60-79 on ps_sim = 1 - Hamming / n and truth_sim = truth .== truth'
+    const double n_part = (double)h->n_host;
+    const double Np = (double)T * (double)T;
+    double nis = 0.0, njs = 0.0, both_same = 0.0;
+    for (long long s = 0; s < T; s++)
+        for (long long t = 0; t < T; t++) {
+            const double sim = 1.0 - ((double)(h->n_host - (long long)c[s * T + t])) / n_part;
+            nis += sim;
+            if (truth[s] == truth[t]) { njs += 1.0; both_same += sim; }
+        }
+    const double both_diff = Np - nis - njs + both_same;
+    if (adjusted) {
+        const double n = (double)T;
+        const double nc = (n * (n * n + 1.0) - (n + 1.0) * nis - (n + 1.0) * njs + 2.0 * (nis * njs) / n) / (2.0 * (n - 1.0));
+        *out = (both_same + both_diff - nc) / (Np - nc);
+    } else {
+        *out = (both_same + both_diff) / Np;
+    }
+    return PF_OK;
+}
+
+// ------------------------------------------------------------------ checkpoint / restore
+// The population (live slots only), the control blocks, the genealogy and the host mirrors of a single-GPU handle
+// go to one file; pf_load builds a handle that continues bit for bit (same seed and step counter => same device
+// uniforms).  Layout: header, pf_config + prior arrays, mirrors, device control blocks, arrays.
+static const char CKPT_MAGIC[8] = {'P', 'F', 'B', '2', '0', '0', 'C', '2'};
+struct CkptHeader {
+    char magic[8];
+    uint32_t sz_cfg, sz_st, sz_res, sz_sc, sz_cl, sz_log;
+    int32_t d, F, k_max, cur, sp_kind, have_last, max_k, has_hist;
+    int64_t N, cap, steps, n_host, ub_live, hist_rows, epoch;
+};
+
+static bool dump_dev(FILE *f, const void *dptr, size_t bytes, std::vector<char> &stage)
+{
+    const char *p = static_cast<const char *>(dptr);
+    while (bytes) {
+        const size_t c = std::min(bytes, stage.size());
+        if (cudaMemcpy(stage.data(), p, c, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        if (fwrite(stage.data(), 1, c, f) != c) return false;
+        p += c; bytes -= c;
+    }
+    return true;
+}
+static bool load_dev(FILE *f, void *dptr, size_t bytes, std::vector<char> &stage)
+{
+    char *p = static_cast<char *>(dptr);
+    while (bytes) {
+        const size_t c = std::min(bytes, stage.size());
+        if (fread(stage.data(), 1, c, f) != c) return false;
+        if (cudaMemcpy(p, stage.data(), c, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        p += c; bytes -= c;
+    }
+    return true;
+}
+
+extern "C" int32_t pf_save(pf_handle h, const char *path)
+{
+    if (!h || !path) return PF_ERR_ARG;
+    if (h->nranks > 1) return set_error(h, PF_ERR_STATE, "pf_save: sharded handles are not checkpointed");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const long long n = h->n_host, cap = h->cap;
+    const int cur = h->cur;
+    std::vector<int> K(n);
+    CUDA_TRY(cudaMemcpy(K.data(), h->Kc[cur], sizeof(int) * n, cudaMemcpyDeviceToHost));
+    int max_k = 0;
+    for (long long i = 0; i < n; i++) max_k = std::max(max_k, K[i]);
+    FILE *f = fopen(path, "wb");
+    if (!f) return set_error(h, PF_ERR_ARG, std::string("pf_save: cannot open ") + path);
+    CkptHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, CKPT_MAGIC, 8);
+    hd.sz_cfg = sizeof(pf_config); hd.sz_st = sizeof(StepState); hd.sz_res = sizeof(SelResult); hd.sz_sc = sizeof(SelScratch);
+    hd.sz_cl = sizeof(ClState); hd.sz_log = sizeof(StepLog);
+    hd.d = h->d; hd.F = h->F; hd.k_max = h->k_max; hd.cur = cur; hd.sp_kind = h->sp_kind; hd.have_last = h->have_last; hd.max_k = max_k;
+    hd.has_hist = h->hist_cap > 0; hd.N = h->N; hd.cap = cap; hd.steps = h->steps; hd.n_host = n; hd.ub_live = h->ub_live;
+    hd.hist_rows = h->hist_cap > 0 ? h->steps : 0; hd.epoch = h->epoch;
+    std::vector<char> stage((size_t)64 << 20);
+    bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(&h->cfg, sizeof h->cfg, 1, f) == 1 &&
+              fwrite(h->mu0.data(), sizeof(double), h->d, f) == (size_t)h->d &&
+              fwrite(h->lam0.data(), sizeof(double), (size_t)h->d * h->d, f) == (size_t)h->d * h->d;
+    const int64_t nsp = (int64_t)h->sp_counts.size();
+    ok = ok && fwrite(&nsp, sizeof nsp, 1, f) == 1 && (nsp == 0 || fwrite(h->sp_counts.data(), sizeof(double), nsp, f) == (size_t)nsp);
+    ok = ok && fwrite(&h->last, sizeof(StepLog), 1, f) == 1;
+    ok = ok && dump_dev(f, h->st, sizeof(StepState), stage) && dump_dev(f, h->res, sizeof(SelResult), stage) && dump_dev(f, h->sc, sizeof(SelScratch), stage);
+    if (h->cl) ok = ok && dump_dev(f, h->cl, sizeof(ClState), stage);
+    ok = ok && dump_dev(f, h->Kc[cur], sizeof(int) * n, stage) && dump_dev(f, h->logw[cur], sizeof(double) * n, stage);
+    for (long long r = 0; ok && r < (long long)max_k * h->F; r++) ok = dump_dev(f, h->S[cur] + r * cap, sizeof(double) * n, stage);
+    if (h->sp_kind == PF_SP_STICKY) {
+        for (long long r = 0; ok && r < max_k; r++) ok = dump_dev(f, h->sp[cur].N + r * cap, sizeof(double) * n, stage) && dump_dev(f, h->sp[cur].Nsame + r * cap, sizeof(double) * n, stage);
+        ok = ok && dump_dev(f, h->sp[cur].last, sizeof(int) * n, stage);
+    }
+    for (long long t = 0; ok && t < hd.hist_rows; t++)
+        ok = dump_dev(f, h->gen_anc + t * cap, sizeof(unsigned int) * cap, stage) && dump_dev(f, h->gen_asg + t * cap, (size_t)cap, stage);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { cudaGetLastError(); return set_error(h, PF_ERR_STATE, std::string("pf_save: write to ") + path + " failed"); }
+    return PF_OK;
+}
+
+extern "C" int32_t pf_load(const char *path, int32_t device, pf_handle *out)
+{
+    if (!path || !out) return set_error(nullptr, PF_ERR_ARG, "pf_load: null argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return set_error(nullptr, PF_ERR_ARG, std::string("pf_load: cannot open ") + path);
+    CkptHeader hd;
+    pf_config cfg;
+    bool ok = fread(&hd, sizeof hd, 1, f) == 1 && memcmp(hd.magic, CKPT_MAGIC, 8) == 0 && hd.sz_cfg == sizeof(pf_config) &&
+              hd.sz_st == sizeof(StepState) && hd.sz_res == sizeof(SelResult) && hd.sz_sc == sizeof(SelScratch) &&
+              hd.sz_cl == sizeof(ClState) && hd.sz_log == sizeof(StepLog) && fread(&cfg, sizeof cfg, 1, f) == 1;
+    if (!ok || hd.d < 1 || hd.d > PF_MAX_D) { fclose(f); return set_error(nullptr, PF_ERR_ARG, "pf_load: not a checkpoint of this library version"); }
+    std::vector<double> mu0(hd.d), lam0((size_t)hd.d * hd.d), spc;
+    int64_t nsp = 0;
+    ok = fread(mu0.data(), sizeof(double), hd.d, f) == (size_t)hd.d && fread(lam0.data(), sizeof(double), lam0.size(), f) == lam0.size() &&
+         fread(&nsp, sizeof nsp, 1, f) == 1 && nsp >= 0 && nsp <= PF_MAX_SLOTS;
+    if (ok && nsp) { spc.resize(nsp); ok = fread(spc.data(), sizeof(double), nsp, f) == (size_t)nsp; }
+    StepLog last;
+    ok = ok && fread(&last, sizeof last, 1, f) == 1;
+    if (!ok) { fclose(f); return set_error(nullptr, PF_ERR_ARG, "pf_load: truncated checkpoint"); }
+    cfg.mu0 = mu0.data(); cfg.lambda0 = lam0.data(); cfg.sp_counts = nsp ? spc.data() : nullptr;
+    cfg.device = device;
+    if (cfg.prior_kind == PF_NIX2) cfg.lambda0 = nullptr;
+    if (cfg.history > 0 && cfg.history < hd.steps) cfg.history = hd.steps;
+    pf_handle h = nullptr;
+    int32_t rc = pf_create(&cfg, &h);
+    if (rc != PF_OK) { fclose(f); return rc; }
+    auto fail = [&](const char *msg) { fclose(f); cudaGetLastError(); g_create_error = msg; pf_destroy(h); return (int32_t)PF_ERR_STATE; };
+    if (h->cap != hd.cap || h->F != hd.F) return fail("pf_load: layout mismatch");
+    h->steps = hd.steps; h->n_host = hd.n_host; h->ub_live = hd.ub_live; h->cur = hd.cur; h->epoch = (unsigned int)hd.epoch;
+    h->last = last; h->have_last = hd.have_last != 0;
+    if (ensure_table(h, h->steps + 4096) != PF_OK) return fail("pf_load: table allocation failed");
+    if (hd.has_hist && ensure_history(h, hd.steps) != PF_OK) return fail("pf_load: the genealogy does not fit in device memory");
+    std::vector<char> stage((size_t)64 << 20);
+    const long long n = hd.n_host, cap = hd.cap;
+    const int cur = hd.cur;
+    ok = load_dev(f, h->st, sizeof(StepState), stage) && load_dev(f, h->res, sizeof(SelResult), stage) && load_dev(f, h->sc, sizeof(SelScratch), stage);
+    if (h->cl) ok = ok && load_dev(f, h->cl, sizeof(ClState), stage);
+    ok = ok && load_dev(f, h->Kc[cur], sizeof(int) * n, stage) && load_dev(f, h->logw[cur], sizeof(double) * n, stage);
+    for (long long r = 0; ok && r < (long long)hd.max_k * h->F; r++) ok = load_dev(f, h->S[cur] + r * cap, sizeof(double) * n, stage);
+    if (h->sp_kind == PF_SP_STICKY) {
+        for (long long r = 0; ok && r < hd.max_k; r++) ok = load_dev(f, h->sp[cur].N + r * cap, sizeof(double) * n, stage) && load_dev(f, h->sp[cur].Nsame + r * cap, sizeof(double) * n, stage);
+        ok = ok && load_dev(f, h->sp[cur].last, sizeof(int) * n, stage);
+    }
+    if (hd.has_hist && h->hist_cap < hd.hist_rows) ok = false;
+    for (long long t = 0; ok && hd.has_hist && t < hd.hist_rows; t++)
+        ok = load_dev(f, h->gen_anc + t * cap, sizeof(unsigned int) * cap, stage) && load_dev(f, h->gen_asg + t * cap, (size_t)cap, stage);
+    if (!ok) return fail("pf_load: truncated checkpoint or device copy failed");
+    fclose(f);
+    *out = h;
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_config(pf_handle h, pf_config *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    *out = h->cfg;                                     // (the array pointers are null: pf_get_prior returns the arrays)
+    return PF_OK;
+}
+
+extern "C" int32_t pf_get_prior(pf_handle h, double *mu0, double *lambda0, double *sp_counts)
+{
+    if (!h) return PF_ERR_ARG;
+    if (mu0) std::copy(h->mu0.begin(), h->mu0.end(), mu0);
+    if (lambda0) std::copy(h->lam0.begin(), h->lam0.end(), lambda0);
+    if (sp_counts) std::copy(h->sp_counts.begin(), h->sp_counts.end(), sp_counts);
     return PF_OK;
 }
 
@@ -1466,9 +1791,67 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
         }
         h->last = h->logs.back(); h->have_last = true; h->last_stale = false;
         h->n_host = st.n_next;
+        for (long long t = 0; t < T; t++) h->gen_q.push_back(std::max<long long>(1, (h->logs[t].n_out + h->nranks - 1) / h->nranks));
     }
     if (first_err != PF_OK) return first_err;
     if (log_evidence) for (long long t = 0; t < T; t++) log_evidence[t] = hs[0]->logs[t].log_total;
+    return PF_OK;
+}
+
+// assignments(ps) (src/filters.jl:26-34, src/particle.jl:25-32) of THIS shard's particles: the ancestor chain of a
+// particle runs through the genealogy arrays of whichever rank owned each ancestor (peer memory); generation t's
+// parent index is global in the population after step t - 1, whose owner blocks have length q[t - 1]
+__global__ void k_mg_wait_generation(const Xch *x, unsigned long long seq, int *ok)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    *ok = xch_wait(x, XCH_D, seq) ? 1 : 0;
+}
+__global__ void k_backtrack8_mg(const PeerTable *__restrict__ peers, long long cap, long long T, const long long *__restrict__ q,
+                                int rank, long long i0, long long nc, unsigned char *__restrict__ out8)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    int r = rank;
+    long long k = i0 + c;
+    for (long long t = T - 1; t >= 0; t--) {
+        out8[t * nc + c] = peers->gen_asg[r][t * cap + k];
+        const long long g = peers->gen_anc[r][t * cap + k];
+        if (t > 0) { const long long qq = q[t - 1]; r = (int)(g / qq); k = g - (long long)r * qq; }
+    }
+}
+
+extern "C" int32_t pf_mg_get_assignments(pf_handle h, int32_t *out)
+{
+    MG_CHECK(h);
+    if (!out) return PF_ERR_ARG;
+    if (!h->connected) return set_error(h, PF_ERR_STATE, "pf_mg_get_assignments: pf_mg_connect has not been called");
+    if (!h->hist_cap) return set_error(h, PF_ERR_HISTORY, "pf_mg_get_assignments: history is disabled (pf_config.history = 0)");
+    const long long T = h->steps, n = h->n_host;
+    if ((long long)h->gen_q.size() != T) return set_error(h, PF_ERR_STATE, "pf_mg_get_assignments: the last sharded call did not complete");
+    if (T == 0 || n == 0) return PF_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const long long nc_max = assign_chunk(T, n);
+    DevBuf dq, dtmp, dok;
+    CUDA_TRY(dq.alloc(sizeof(long long) * T));
+    CUDA_TRY(dtmp.alloc((size_t)T * nc_max));
+    CUDA_TRY(dok.alloc(sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(dq.p, h->gen_q.data(), sizeof(long long) * T, cudaMemcpyHostToDevice, h->stream));
+    // every rank has finished its last generation (peers stored children and genealogy entries into this shard, and
+    // this shard reads theirs)
+    k_mg_wait_generation<<<1, 32, 0, h->stream>>>(h->xch, (unsigned long long)T, dok.as<int>());
+    int ok = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ok, dok.p, sizeof ok, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!ok) return set_error(h, PF_ERR_STATE, "pf_mg_get_assignments: a peer has not finished its last generation");
+    std::vector<unsigned char> host((size_t)T * nc_max);
+    for (long long i0 = 0; i0 < n; i0 += nc_max) {
+        const long long nc = std::min(nc_max, n - i0);
+        k_backtrack8_mg<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->peers[0], h->cap, T, dq.as<long long>(), h->rank, i0, nc, dtmp.as<unsigned char>());
+        CUDA_TRY(cudaMemcpyAsync(host.data(), dtmp.p, (size_t)T * nc, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (long long c = 0; c < nc; c++)
+            for (long long t = 0; t < T; t++) out[(i0 + c) * T + t] = host[(size_t)t * nc + c];
+    }
     return PF_OK;
 }
 

@@ -33,7 +33,7 @@ __all__ = ["NormalInverseChisq", "NormalInverseWishart", "ChineseRestaurantProce
            "Labeled", "Component",
            "InfiniteParticle", "ParticleFilter", "FearnheadParticles", "ChenLiuParticles", "fit_", "filter_",
            "particles", "weight", "nobs", "ncomponents", "components", "assignments", "ncomponents_dist",
-           "assignment_similarity", "randindex", "select", "PF_ORDER_INDEX", "PF_ORDER_SORTED", "PFError"]
+           "assignment_similarity", "randindex", "state_entropy", "mean", "posterior_predictive", "save", "load", "select", "PF_ORDER_INDEX", "PF_ORDER_SORTED", "PFError"]
 
 _dp = C.POINTER(C.c_double)
 
@@ -357,6 +357,74 @@ class ParticleFilter:
         _lib.check(self._L.pf_get_assignments(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
         return out.T.astype(np.int64) + 1
 
+    # --- filter-level summaries, reduced on the device (src/filters.jl:17-42, 53-80)
+    def mean(self, f):
+        """mean(f, ps) (src/filters.jl:17-18).  ncomponents and state_entropy are reduced on the device; any other f
+        is a host function of InfiniteParticle views, as in the reference."""
+        what = {ncomponents: _lib.PF_MEAN_NCOMPONENTS, state_entropy: _lib.PF_MEAN_STATE_ENTROPY}.get(f)
+        if what is None:
+            ps, w = self.particles(), self.weights()
+            return float(np.dot([f(p) for p in ps], w) / w.sum())
+        out = C.c_double()
+        _lib.check(self._L.pf_weighted_mean(self._h, what, C.byref(out)), self._h)
+        return out.value
+
+    def ncomponents_dist(self):
+        out = np.zeros(self.k_max + 1)
+        _lib.check(self._L.pf_ncomponents_dist(self._h, out.ctypes.data_as(_dp)), self._h)
+        kmax = int(np.nonzero(out)[0].max()) if out.any() else 0
+        return out[1:kmax + 1].copy()
+
+    def posterior_predictive(self, xs):
+        xs = np.asarray(xs, dtype=np.float64)
+        xs = xs.reshape(-1, 1) if (xs.ndim == 1 and self.d == 1) else np.atleast_2d(xs)
+        if xs.shape[1] != self.d:
+            raise ValueError(f"query points must be Q x {self.d}")
+        xs, px = _d(xs)
+        out = np.empty(len(xs))
+        _lib.check(self._L.pf_posterior_predictive(self._h, px, len(xs), out.ctypes.data_as(_dp)), self._h)
+        return out
+
+    def assignment_similarity(self):
+        T = self.n_steps
+        out = np.empty((T, T))
+        _lib.check(self._L.pf_assignment_similarity(self._h, out.ctypes.data_as(_dp)), self._h)
+        return out
+
+    def randindex(self, truth, kind="adjusted"):
+        t = np.ascontiguousarray(truth, dtype=np.int32)
+        out = C.c_double()
+        rc = self._L.pf_randindex(self._h, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t), int(kind == "adjusted"), C.byref(out))
+        _lib.check(rc, self._h)                           # a length mismatch is the reference's DimensionMismatch
+        return out.value
+
+    # --- checkpoint / restore
+    def save(self, path):
+        _lib.check(self._L.pf_save(self._h, str(path).encode()), self._h)
+
+    @classmethod
+    def load(cls, path, device=0):
+        """Rebuild a filter from pf_save's file; it continues bit for bit where the saved one stopped."""
+        L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(L.pf_load(str(path).encode(), device, C.byref(h)))
+        cfg = pf_config()
+        _lib.check(L.pf_get_config(h, C.byref(cfg)), h)
+        self = object.__new__(FearnheadParticles if cfg.filter_kind == PF_FEARNHEAD else ChenLiuParticles)
+        self._h, self._L = h, L
+        self.N, self.k_max, self.order, self.history, self.d = cfg.n_particles, cfg.k_max, cfg.order, cfg.history, cfg.d if cfg.prior_kind == PF_NIW else 1
+        self.rejuvination_threshold = cfg.rejuv_threshold
+        self.on_overflow, self._overflow_seen = "warn", 0
+        mu0, lam0, spc = np.empty(self.d), np.empty((self.d, self.d)), np.zeros(64)
+        _lib.check(L.pf_get_prior(h, mu0.ctypes.data_as(_dp), lam0.ctypes.data_as(_dp), spc.ctypes.data_as(_dp)), h)
+        self.prior = (NormalInverseChisq(mu0[0], cfg.sigma2_0, cfg.kappa0, cfg.nu0) if cfg.prior_kind == PF_NIX2
+                      else NormalInverseWishart(mu0, cfg.kappa0, lam0.T, cfg.nu0))
+        k = cfg.stateprior_kind
+        self.stateprior = (StickyCRP(cfg.alpha, cfg.sp_param) if k == _lib.PF_SP_STICKY else
+                           ChangePoint(cfg.sp_param) if k == _lib.PF_SP_CHANGEPOINT else
+                           NStatePrior(spc[:cfg.sp_n]) if k == _lib.PF_SP_NSTATE else ChineseRestaurantProcess(cfg.alpha))
+        return self
+
     def last_step(self):
         s = pf_step_stats()
         _lib.check(self._L.pf_get_last_step(self._h, C.byref(s)), self._h)
@@ -439,38 +507,57 @@ def assignments(ps):
 
 
 def ncomponents_dist(ps):
-    """ncomponents_dist(ps) (src/filters.jl:36-37): weighted distribution of K."""
-    K, w = ps.ncomponents(), ps.weights()
-    p = np.bincount(K, weights=w / w.sum())
-    return p
+    """ncomponents_dist(ps) (src/filters.jl:36-37): weighted distribution of K; entry k-1 = P(K = k), k = 1..max K
+    (fit(Categorical, ...) has max(K) categories).  Reduced on the device."""
+    return ps.ncomponents_dist()
+
+
+def state_entropy(x):
+    """state_entropy(ps) = mean(state_entropy, ps) (src/filters.jl:20) on the device; state_entropy(p) for one particle
+    (src/particle.jl:162) from its state prior."""
+    if isinstance(x, ParticleFilter):
+        return x.mean(state_entropy)
+    sp = x.stateprior
+    if isinstance(sp, ChangePoint):
+        lp = np.zeros(1) if sp.k == 0 else np.array([math.log1p(-sp.p) if sp.p < 1 else -math.inf, sp.logp])
+    elif isinstance(sp, NStatePrior):
+        lp = np.log(sp.counts) - math.log(sp.total_count)
+    elif isinstance(sp, StickyCRP):
+        lp = (np.zeros(1) if len(sp.N) == 0 else
+              np.concatenate([[math.log(sp.rho / (1 - sp.rho)) + math.log(sp.N.sum() + sp.alpha)], np.log(sp.N), [math.log(sp.alpha)]]))
+    else:
+        lp = np.concatenate([np.log(sp.N), [math.log(sp.alpha)]])
+    p = np.exp(lp - np.logaddexp.reduce(lp))
+    p = p[p > 0]
+    return float(-(p * np.log(p)).sum())
+
+
+def mean(f, ps):
+    """mean(f, ps) (src/filters.jl:17-18)."""
+    return ps.mean(f)
+
+
+def posterior_predictive(ps, xs):
+    """pdf.(posterior_predictive(ps), xs) (src/filters.jl:22-24), evaluated on the device."""
+    return ps.posterior_predictive(xs)
 
 
 def assignment_similarity(ps):
-    """assignment_similarity(ps) (src/filters.jl:39-42): 1 - Hamming distance between rows."""
-    a = ps.assignments()
-    T = a.shape[0]
-    out = np.empty((T, T))
-    for t in range(T):
-        out[t] = (a == a[t]).mean(axis=1)
-    return out
+    """assignment_similarity(ps) (src/filters.jl:39-42): 1 - Hamming distance between rows (device)."""
+    return ps.assignment_similarity()
 
 
 def randindex(ps, truth, kind="adjusted"):
-    """randindex(ps, truth, type) (src/filters.jl:53-80)."""
-    truth = np.asarray(truth)
-    ps_sim = assignment_similarity(ps)
-    truth_sim = (truth[:, None] == truth[None, :]).astype(np.float64)
-    if truth_sim.shape != ps_sim.shape:
-        raise ValueError("Ground truth and particles have different number of obs!")   # DimensionMismatch
-    Np = ps_sim.size
-    nis, njs = ps_sim.sum(), truth_sim.sum()
-    both_same = (ps_sim * truth_sim).sum()
-    both_diff = Np - nis - njs + both_same
-    if kind == "adjusted":
-        n = len(truth)
-        nc = (n * (n ** 2 + 1) - (n + 1) * nis - (n + 1) * njs + 2 * (nis * njs) / n) / (2 * (n - 1))
-        return (both_same + both_diff - nc) / (Np - nc)
-    return (both_same + both_diff) / Np
+    """randindex(ps, truth, type) (src/filters.jl:53-80) on the device-computed similarity counts."""
+    return ps.randindex(truth, kind)
+
+
+def save(ps, path):
+    return ps.save(path)
+
+
+def load(path, device=0):
+    return ParticleFilter.load(path, device)
 
 
 def select(w, N, u, order=PF_ORDER_INDEX, device=0):

@@ -15,6 +15,7 @@ PF_NIX2, PF_NIW = 0, 1
 PF_F64, PF_F32 = 0, 1
 PF_ORDER_INDEX, PF_ORDER_SORTED = 0, 1
 PF_SP_CRP, PF_SP_STICKY, PF_SP_CHANGEPOINT, PF_SP_NSTATE = 0, 1, 2, 3
+PF_MEAN_NCOMPONENTS, PF_MEAN_STATE_ENTROPY = 0, 1
 
 _dp = C.POINTER(C.c_double)
 
@@ -62,6 +63,15 @@ SYMBOLS = [
     ("pf_get_particle", C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), _dp, _dp, _dp, _dp]),
     ("pf_get_assignments", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     ("pf_get_last_step", C.c_int32, [C.c_void_p, C.POINTER(pf_step_stats)]),
+    ("pf_posterior_predictive", C.c_int32, [C.c_void_p, _dp, C.c_int64, _dp]),
+    ("pf_weighted_mean", C.c_int32, [C.c_void_p, C.c_int32, _dp]),
+    ("pf_ncomponents_dist", C.c_int32, [C.c_void_p, _dp]),
+    ("pf_assignment_similarity", C.c_int32, [C.c_void_p, _dp]),
+    ("pf_randindex", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.c_int64, C.c_int32, _dp]),
+    ("pf_save", C.c_int32, [C.c_void_p, C.c_char_p]),
+    ("pf_load", C.c_int32, [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    ("pf_get_config", C.c_int32, [C.c_void_p, C.POINTER(pf_config)]),
+    ("pf_get_prior", C.c_int32, [C.c_void_p, _dp, _dp, _dp]),
     ("pf_get_putative_weights", C.c_int32, [C.c_void_p, _dp, C.c_int64, C.POINTER(C.c_int64)]),
     ("pf_get_last_ancestors", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     ("pf_get_last_assignments", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
@@ -74,6 +84,7 @@ SYMBOLS = [
     ("pf_mg_connect", C.c_int32, [C.POINTER(C.c_void_p), C.c_int32]),
     ("pf_mg_filter", C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, _dp, C.c_int64, _dp, C.c_int64, _dp]),
     ("pf_mg_n_global", C.c_int64, [C.c_void_p]),
+    ("pf_mg_get_assignments", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     ("pf_mg_create_local", C.c_int32, [C.POINTER(pf_config), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
     ("pf_debug_dump", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("pf_last_timing", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),

@@ -218,6 +218,19 @@ class ShardedFearnheadParticles:
     def last_assignments(self):
         return np.concatenate(self.group.gather_host(self._local(self.L.pf_get_last_assignments, np.int32, C.c_int32)))
 
+    def assignments(self):
+        """assignments(ps) (src/filters.jl:26-34): T x n matrix of 1-based labels, columns in global particle order.
+        Each shard follows its particles' ancestor chains through the peers' genealogy arrays on the device."""
+        T = self.n_steps
+        outs = []
+        for h in self.handles:
+            out = np.empty((int(self.L.pf_n_particles(h)), T), dtype=np.int32)
+            _lib.check(self.L.pf_mg_get_assignments(h, out.ctypes.data_as(C.POINTER(C.c_int32))), h)
+            outs.append(out)
+        if len(outs) > 1:
+            outs = [np.concatenate(outs, axis=0)]
+        return np.concatenate(self.group.gather_host(outs), axis=0).T.astype(np.int64) + 1
+
     def last_step(self):
         st = pf_step_stats()
         _lib.check(self.L.pf_get_last_step(self.handles[0], C.byref(st)), self.handles[0])

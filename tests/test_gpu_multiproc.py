@@ -62,6 +62,8 @@ def _worker(rank, world, port, N, T, margin, ok):
         assert np.array_equal(K, ref.ncomponents())
         assert np.array_equal(anc, ref.last_ancestors())
         assert np.array_equal(asg, ref.last_assignments())
+        if N <= (1 << 17):                               # T x N labels through the peers' genealogy arrays (CUDA IPC)
+            assert np.array_equal(sh.assignments(), ref.assignments())
         if margin:
             np.testing.assert_allclose(lw, ref.logweights(), rtol=0, atol=1e-12)
             np.testing.assert_allclose(le, ref.log_evidence, rtol=1e-13)
@@ -112,3 +114,4 @@ def test_one_process_driving_all_gpus():
     assert np.array_equal(sh.ncomponents(), ref.ncomponents())
     assert np.array_equal(sh.last_ancestors(), ref.last_ancestors())
     assert np.array_equal(sh.log_evidence, ref.log_evidence)
+    assert np.array_equal(sh.assignments(), ref.assignments())

@@ -42,6 +42,7 @@ def test_sharded_equals_unsharded_stepwise(G, N, T):
         _same_population(sh, ref, f"at step {t}")
         # equal blocks after every step
         assert sh.local_sizes() == np.diff(equal_blocks(len(sh), G)).tolist()
+    assert np.array_equal(sh.assignments(), ref.assignments())
 
 
 @pytest.mark.parametrize("G,N,T,alpha", [(4, 1 << 17, 40, 1.0), (8, 1 << 18, 30, 3.0), (2, 1 << 18, 30, 0.3)])
@@ -59,6 +60,8 @@ def test_sharded_equals_unsharded_one_call(G, N, T, alpha):
     sh.filter_(ys, us)
     _same_population(sh, ref, "after the stream")
     assert np.array_equal(sh.log_evidence, ref.log_evidence)
+    # the ancestor chains cross the shards: every shard walks them through the peers' genealogy arrays
+    assert np.array_equal(sh.assignments(), ref.assignments())
 
 
 def test_sharded_1d_nix2():
