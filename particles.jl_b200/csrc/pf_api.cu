@@ -69,7 +69,10 @@ struct pf_filter_s {
     double *W = nullptr;
     u128 *cum = nullptr;
     unsigned char *asg_tmp = nullptr;
-    double *cl_part = nullptr;
+    u128 *cl_tiles = nullptr;             // tile totals / prefixes of the rejuvenation scan
+    ClPeers *clp = nullptr;               // every rank's store / prefix arrays (single GPU: entry 0 = the local arrays)
+    ClPeers clp_host;
+    ClShard shard{0, 0, 0, 0};            // this shard's block of the Chen-Liu population
     // sharded run
     int rank = 0, nranks = 1;
     RankOff *ro = nullptr;
@@ -223,7 +226,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->supers, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
-                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_part, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
+                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_tiles, h->clp, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
                     h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
                     h->sp[1].Nsame, h->sp[1].last};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -266,7 +269,8 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (spk == PF_SP_NSTATE && (!cfg->sp_counts || cfg->sp_n < 1 || cfg->sp_n > cfg->k_max)) return set_error(nullptr, PF_ERR_ARG, "pf_create: NStatePrior needs 1 <= sp_n <= k_max counts");
     if (cfg->nranks > 1) {
         if (cfg->nranks > PF_MAX_RANKS || cfg->rank < 0 || cfg->rank >= cfg->nranks) return set_error(nullptr, PF_ERR_ARG, "pf_create: bad rank / nranks");
-        if (cfg->filter_kind != PF_FEARNHEAD || cfg->order != PF_ORDER_INDEX) return set_error(nullptr, PF_ERR_ARG, "pf_create: sharded runs support the index-order Fearnhead filter");
+        if (cfg->filter_kind == PF_FEARNHEAD && cfg->order != PF_ORDER_INDEX) return set_error(nullptr, PF_ERR_ARG, "pf_create: sharded Fearnhead runs use the index order");
+        if (cfg->filter_kind == PF_CHENLIU && cfg->n_particles < cfg->nranks) return set_error(nullptr, PF_ERR_ARG, "pf_create: fewer particles than ranks");
     }
 
     int ndev = 0;
@@ -364,6 +368,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         h->capA = (((cap + h->fuse_stride - 1) / h->fuse_stride + 8) * (h->k_max + 1) + 1024 + 1) & ~1ll;       // even: segments stay 16-byte aligned
         h->capB = std::max<long long>(1 << 20, 2 * cap) & ~1ll;
         if (getenv("PF_MG_CAPB")) h->capB = std::max<long long>(64, atoll(getenv("PF_MG_CAPB"))) & ~1ll;      // tests: force the overflow path
+        if (cfg->filter_kind == PF_CHENLIU) h->capA = h->capB = 2;          // Chen-Liu exchanges scalars only
         h->xreg_bytes = xch_region_bytes(h->nranks, h->capA, h->capB);
         CT(cudaMalloc((void **)&h->xreg, h->xreg_bytes));
         CT(cudaMemsetAsync(h->xreg, 0, xch_header_bytes(), h->stream));
@@ -417,14 +422,24 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         st0.n_live = h->rank == 0 ? 1 : 0; st0.n_next = st0.n_live;     // src/fearnhead.jl:29-30 (the particle lives on rank 0)
         h->n_host = 1; h->ub_live = 1;
     } else {
-        st0.n_live = h->N; st0.n_next = h->N;        // src/chenliu.jl:25-26
-        h->n_host = h->N; h->ub_live = h->N;
+        // src/chenliu.jl:25-26: N empty particles; rank r owns the global particles [r q, (r + 1) q)
+        h->shard.N = h->N; h->shard.q = (h->N + h->nranks - 1) / h->nranks; h->shard.goff = (long long)h->rank * h->shard.q;
+        h->shard.n_loc = std::max<long long>(0, std::min<long long>(h->N, h->shard.goff + h->shard.q) - h->shard.goff);
+        st0.n_live = h->shard.n_loc; st0.n_next = h->shard.n_loc;
+        h->n_host = h->shard.n_loc; h->ub_live = h->shard.n_loc;
         CT(dmalloc(&h->cl, 1));
         CT(cudaMemsetAsync(h->cl, 0, sizeof(ClState), h->stream));
         CT(dmalloc(&h->W, cap));
         CT(dmalloc(&h->cum, cap));
         CT(dmalloc(&h->asg_tmp, cap));
-        CT(dmalloc(&h->cl_part, 4096));
+        CT(dmalloc(&h->cl_tiles, (size_t)(cap + CL_TILE - 1) / CL_TILE + 1));
+        CT(dmalloc(&h->clp, 1));
+        memset(&h->clp_host, 0, sizeof h->clp_host);
+        if (h->nranks == 1) {
+            for (int b = 0; b < 2; b++) { h->clp_host.S[b][0] = h->S[b]; h->clp_host.Kc[b][0] = h->Kc[b]; }
+            h->clp_host.cum[0] = h->cum; h->clp_host.asg_tmp[0] = h->asg_tmp;
+            CT(cudaMemcpyAsync(h->clp, &h->clp_host, sizeof(ClPeers), cudaMemcpyHostToDevice, h->stream));
+        }
     }
     CT(cudaMemcpyAsync(h->st, &st0, sizeof st0, cudaMemcpyHostToDevice, h->stream));
     CT(cudaMemsetAsync(h->logw[0], 0, sizeof(double) * cap, h->stream));   // weight 1.0, src/particle.jl:62
@@ -633,46 +648,90 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     return PF_OK;
 }
 
+// One Chen-Liu observation as six stages; the exchange kernel that closes stage s publishes this shard's scalar and
+// (unless the shards of this process run in lock step on one stream) also waits for the peers'; in lock step the wait
+// is the first launch of stage s + 1, queued after every shard has published.  Single GPU: stages 0..5 back to back.
+template <int D>
+static int32_t chenliu_stage(pf_handle h, int s, const double *y_dev, const double *u_dev /* [2 n_loc] or null */, StepLog *log_dev)
+{
+    const long long cap = h->cap, N = h->N, n_loc = h->shard.n_loc;
+    const Xch *x = h->nranks > 1 ? h->xch : nullptr;
+    const unsigned long long seq = (unsigned long long)h->steps + 1;
+    const bool split = h->lockstep;
+    const int pub = split ? SEL_ST_PUB : (SEL_ST_PUB | SEL_ST_RUN);
+    const int g256 = grid_for(n_loc, 256), gtile = grid_for(n_loc, CL_TILE);
+    int gstat = h->num_sms * 2;
+    if (gstat > 1024) gstat = 1024;
+    switch (s) {
+    case 0: {
+        if (h->hist_cap && h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
+        {
+            LaunchTimer lt(h, KC_PRESTEP);            // (sharded: waits until no peer reads this shard's store any more)
+            k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, h->sc, nullptr, x, seq, h->steps);
+        }
+        LaunchTimer lt(h, KC_CL_PROP);
+        k_cl_propagate<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], cap, h->shard, h->k_max,
+                                                         h->tab, h->pc, h->stc, h->st, h->cl, u_dev, h->cfg.seed, (u64)h->steps, h->W,
+                                                         h->asg_tmp, h->V, h->sc);
+        if (x) { k_cl_x_wmax<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, pub, h->sc); h->launches++; }
+        break;
+    }
+    case 1: {
+        LaunchTimer lt(h, KC_CL_STATS, 2);
+        if (x && split) { k_cl_x_wmax<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, SEL_ST_RUN, h->sc); h->launches++; }
+        k_cl_sum<<<gstat, 256, 0, h->stream>>>(h->W, n_loc, h->cl, h->sc);
+        k_cl_x_sum<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, pub, N, h->sc);
+        break;
+    }
+    case 2: {
+        LaunchTimer lt(h, KC_CL_STATS, 2);
+        if (x && split) { k_cl_x_sum<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, SEL_ST_RUN, N, h->sc); h->launches++; }
+        k_cl_var<<<gstat, 256, 0, h->stream>>>(h->W, n_loc, h->cl, h->sc);
+        k_cl_decide<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, pub, N, h->cfg.rejuv_threshold, h->sc);
+        break;
+    }
+    case 3: {
+        LaunchTimer lt(h, KC_CL_STATS, 2);
+        if (x && split) { k_cl_decide<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, SEL_ST_RUN, N, h->cfg.rejuv_threshold, h->sc); h->launches++; }
+        k_cl_tile_sums<<<gtile, 256, 0, h->stream>>>(h->W, n_loc, h->cl, h->cl_tiles, h->sc);
+        k_cl_tile_prefix<<<1, 1024, 0, h->stream>>>(h->cl_tiles, gtile, h->cl, x, seq, h->steps, pub, h->sc);
+        break;
+    }
+    case 4: {
+        LaunchTimer lt(h, KC_CL_STATS, 1);
+        if (x && split) { k_cl_tile_prefix<<<1, 1024, 0, h->stream>>>(h->cl_tiles, gtile, h->cl, x, seq, h->steps, SEL_ST_RUN, h->sc); h->launches++; }
+        k_cl_tile_apply<<<gtile, 256, 0, h->stream>>>(h->W, n_loc, h->cl, h->cl_tiles, h->cum, h->sc);
+        if (x) { k_cl_x_ready<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, pub, h->sc); h->launches++; }
+        break;
+    }
+    default: {
+        unsigned int *ga = nullptr; unsigned char *gs = nullptr;
+        if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap; }
+        {
+            LaunchTimer lt(h, KC_CL_FINISH);
+            if (x && split) { k_cl_x_ready<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, SEL_ST_RUN, h->sc); h->launches++; }
+            k_cl_finish<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->Kc[0], h->Kc[1], h->logw[0], h->logw[1], cap, h->shard, h->nranks, h->cl,
+                                                          h->W, h->clp, u_dev ? u_dev + n_loc : nullptr, h->cfg.seed, (u64)h->steps, h->asg_tmp, ga, gs, h->sc);
+        }
+        {
+            LaunchTimer lt(h, KC_STEPLOG);
+            k_cl_steplog<<<1, 32, 0, h->stream>>>(h->st, h->cl, log_dev, N, n_loc, x, seq, h->sc);
+        }
+        CUDA_TRY(cudaGetLastError());
+        h->steps++;
+        break;
+    }
+    }
+    return PF_OK;
+}
+
 template <int D>
 static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_dev /* 2N or null */, StepLog *log_dev)
 {
-    const long long cap = h->cap, N = h->N;
-    unsigned int *ga = nullptr; unsigned char *gs = nullptr;
-    if (h->hist_cap) {
-        if (h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
-        ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap;
+    for (int s = 0; s < 6; s++) {
+        int32_t rc = chenliu_stage<D>(h, s, y_dev, u_dev, log_dev);
+        if (rc != PF_OK) return rc;
     }
-    const int g256 = grid_for(N, 256);
-    {
-        LaunchTimer lt(h, KC_PRESTEP);
-        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, nullptr, nullptr, nullptr, 0, h->steps);
-    }
-    {
-        LaunchTimer lt(h, KC_CL_PROP);
-        k_cl_propagate<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], cap, N, h->k_max,
-                                                         h->tab, h->pc, h->stc, h->st, h->cl, u_dev, h->cfg.seed, (u64)h->steps, h->W,
-                                                         h->asg_tmp);
-    }
-    int gstat = h->num_sms * 2;
-    if (gstat > 1024) gstat = 1024;
-    {
-        LaunchTimer lt(h, KC_CL_STATS, 4);
-        k_cl_sum<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl);
-        k_cl_var<<<gstat, 256, 0, h->stream>>>(h->W, N, h->cl, h->cl_part);
-        k_cl_decide<<<1, 32, 0, h->stream>>>(h->cl, h->cl_part, gstat, N, h->cfg.rejuv_threshold);
-        k_cl_scan<<<1, 1024, 0, h->stream>>>(h->W, N, h->cl, h->cum);
-    }
-    {
-        LaunchTimer lt(h, KC_CL_FINISH);
-        k_cl_finish<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->Kc[0], h->Kc[1], h->logw[0], h->logw[1], cap, N, h->cl, h->W,
-                                                      h->cum, u_dev ? u_dev + N : nullptr, h->cfg.seed, (u64)h->steps, h->asg_tmp, ga, gs);
-    }
-    {
-        LaunchTimer lt(h, KC_STEPLOG);
-        k_cl_steplog<<<1, 32, 0, h->stream>>>(h->st, h->cl, log_dev, N);
-    }
-    CUDA_TRY(cudaGetLastError());
-    h->steps++;
     return PF_OK;
 }
 
@@ -1508,13 +1567,15 @@ extern "C" int32_t pf_set_stream(pf_handle h, void *cuda_stream)
     return PF_OK;
 }
 
-// arrays a peer must be able to write: S[0], S[1], Kc[0], Kc[1], logw[0], logw[1], gen_anc, gen_asg, exchange region
+// arrays a peer must be able to write or read: S[0], S[1], Kc[0], Kc[1], logw[0], logw[1], gen_anc, gen_asg, exchange
+// region, and (Chen-Liu) the prefix array and the step's assignments
 static void *peer_array(pf_handle h, int k)
 {
     switch (k) {
     case 0: return h->S[0]; case 1: return h->S[1]; case 2: return h->Kc[0]; case 3: return h->Kc[1];
     case 4: return h->logw[0]; case 5: return h->logw[1]; case 6: return h->gen_anc; case 7: return h->gen_asg;
-    default: return h->xreg;
+    case 8: return h->xreg; case 9: return h->cum;
+    default: return h->asg_tmp;
     }
 }
 
@@ -1560,6 +1621,8 @@ extern "C" int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, 
         h->peers_host[b].gen_anc[peer] = (unsigned int *)a[6]; h->peers_host[b].gen_asg[peer] = (unsigned char *)a[7];
     }
     h->xch_host.reg[peer] = (XchRegion *)a[8];
+    for (int b = 0; b < 2; b++) { h->clp_host.S[b][peer] = (const double *)a[b]; h->clp_host.Kc[b][peer] = (const int *)a[2 + b]; }
+    h->clp_host.cum[peer] = (const u128 *)a[9]; h->clp_host.asg_tmp[peer] = (const unsigned char *)a[10];
     return PF_OK;
 }
 
@@ -1592,6 +1655,7 @@ extern "C" int32_t pf_mg_connect(pf_handle *hs, int32_t n_local)
         }
         if (!h->xch) CUDA_TRY(dmalloc(&h->xch, 1));
         CUDA_TRY(cudaMemcpyAsync(h->xch, &h->xch_host, sizeof(Xch), cudaMemcpyHostToDevice, h->stream));
+        if (h->clp) CUDA_TRY(cudaMemcpyAsync(h->clp, &h->clp_host, sizeof(ClPeers), cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->lockstep = same_device;
         if (same_device) {                               // one stream for the whole group
@@ -1721,7 +1785,9 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
         if (!hs[i]->connected) return set_error(hs[i], PF_ERR_STATE, "pf_mg_filter: pf_mg_connect has not been called");
     }
     if (T < 0 || (!ys && T > 0)) return set_error(hs[0], PF_ERR_ARG, "pf_mg_filter: bad ys/T");
-    if (uniforms && uniforms_per_step < 1) return set_error(hs[0], PF_ERR_ARG, "pf_mg_filter: Fearnhead needs 1 uniform per step");
+    const bool cl = hs[0]->cfg.filter_kind == PF_CHENLIU;
+    if (uniforms && uniforms_per_step < (cl ? 2 * hs[0]->N : 1))
+        return set_error(hs[0], PF_ERR_ARG, cl ? "pf_mg_filter: Chen-Liu needs 2*N uniforms per step" : "pf_mg_filter: Fearnhead needs 1 uniform per step");
     if (T == 0) return PF_OK;
     const int d = hs[0]->d;
     const bool lockstep = hs[0]->lockstep;
@@ -1734,7 +1800,8 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
         if (h->hist_cap && h->steps + T > h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
         if (T * d > h->ys_cap) { if (h->ys_dev) cudaFree(h->ys_dev); h->ys_cap = T * d; CUDA_TRY(dmalloc(&h->ys_dev, (size_t)h->ys_cap)); }
         if (T > h->slog_cap) { if (h->slog) cudaFree(h->slog); h->slog_cap = T; CUDA_TRY(dmalloc(&h->slog, (size_t)T)); }
-        if (T > h->u_cap) { if (h->u_dev) cudaFree(h->u_dev); h->u_cap = T; CUDA_TRY(dmalloc(&h->u_dev, (size_t)T)); }
+        const long long un = cl ? std::max<long long>(T, 2 * h->shard.n_loc) : T;
+        if (un > h->u_cap) { if (h->u_dev) cudaFree(h->u_dev); h->u_cap = un; CUDA_TRY(dmalloc(&h->u_dev, (size_t)un)); }
         std::vector<double> ubuf(T);
         for (long long t = 0; t < T; t++)
             ubuf[t] = uniforms ? uniforms[t * uniforms_per_step] : pf_uniform(h->cfg.seed, (uint64_t)(h->steps + t), 0, 0);
@@ -1747,6 +1814,19 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
 #define FOR_SHARDS(CALL) for (int i_ = 0; i_ < n_local && rc == PF_OK; i_++) { pf_handle h = hs[i_]; cudaSetDevice(h->cfg.device); DISPATCH_D(d, rc = CALL); }
     const int both = SEL_ST_PUB | SEL_ST_RUN;
     for (long long t = 0; t < T && rc == PF_OK; t++) {
+        if (cl) {
+            // (uniforms[2N] of the step: [0, N) categorical draws, [N, 2N) rejuvenation; every shard takes its block)
+            if (uniforms)
+                for (int i = 0; i < n_local; i++) {
+                    pf_handle h = hs[i];
+                    cudaSetDevice(h->cfg.device);
+                    const double *ut = uniforms + t * uniforms_per_step;
+                    cudaMemcpyAsync(h->u_dev, ut + h->shard.goff, sizeof(double) * h->shard.n_loc, cudaMemcpyHostToDevice, h->stream);
+                    cudaMemcpyAsync(h->u_dev + h->shard.n_loc, ut + h->N + h->shard.goff, sizeof(double) * h->shard.n_loc, cudaMemcpyHostToDevice, h->stream);
+                }
+            for (int st = 0; st < 6; st++) FOR_SHARDS((chenliu_stage<D>(h, st, h->ys_dev + t * d, uniforms ? h->u_dev : nullptr, h->slog + t)));
+            continue;
+        }
         if (lockstep) {
             FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_PUB)));
             FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_RUN)));
@@ -1791,6 +1871,7 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
         }
         h->last = h->logs.back(); h->have_last = true; h->last_stale = false;
         h->n_host = st.n_next;
+        if (cl) { ClState cs; if (cudaMemcpy(&cs, h->cl, sizeof cs, cudaMemcpyDeviceToHost) == cudaSuccess) h->cur = cs.cur; }
         for (long long t = 0; t < T; t++) h->gen_q.push_back(std::max<long long>(1, (h->logs[t].n_out + h->nranks - 1) / h->nranks));
     }
     if (first_err != PF_OK) return first_err;

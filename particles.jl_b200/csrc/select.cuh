@@ -152,7 +152,9 @@ struct SelAcc {
 // after its last kernel of step t: one buffer per kind is enough across steps; within a step the rounds
 // of kind B alternate between two buffers because a fast rank may publish round k + 1 while a slow one
 // still reads round k.
-enum { XCH_A = 0, XCH_B = 1, XCH_C = 2, XCH_D = 3, XCH_KINDS = 4 };
+// Chen-Liu (chenliu.cuh): kinds CL_W max weight, CL_S sum of weights, CL_Q sum of squared deviations, CL_T mass of the
+// shard (rejuvenation), CL_R prefix array ready -- one scalar per rank each, seq = step + 1
+enum { XCH_A = 0, XCH_B = 1, XCH_C = 2, XCH_D = 3, XCH_CL_W = 4, XCH_CL_S = 5, XCH_CL_Q = 6, XCH_CL_T = 7, XCH_CL_R = 8, XCH_KINDS = 9 };
 struct XchHdrA { unsigned long long n, vmax, M_pred, overflow; };
 struct XchTot { u128 X; unsigned int kept; unsigned int pad[3]; };         // = TileSum (fearnhead.cuh)
 struct XchRegion {
@@ -160,6 +162,9 @@ struct XchRegion {
     XchHdrA a[PF_MAX_RANKS];
     SelAcc b[2][PF_MAX_RANKS];
     XchTot c[PF_MAX_RANKS];
+    unsigned long long clw[PF_MAX_RANKS];
+    acc128 clsum[PF_MAX_RANKS], clsq[PF_MAX_RANKS];
+    u128 clq[PF_MAX_RANKS];
     // followed (256-byte aligned) by listA[nranks][capA] and listB[2][nranks][capB] (doubles)
 };
 struct Xch {

@@ -45,7 +45,7 @@ class pf_step_stats(C.Structure):
         return d
 
 
-PF_MG_NARRAYS, PF_MG_IPC_BYTES = 9, 64
+PF_MG_NARRAYS, PF_MG_IPC_BYTES = 11, 64
 
 # every symbol include/particles_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [

@@ -1,11 +1,11 @@
-"""Sharded Fearnhead filter: particles block-sharded over the GPUs of one node.
+"""Sharded Fearnhead and Chen-Liu filters: particles block-sharded over the GPUs of one node.
 
 All device work, including every exchange between the shards, happens inside
 libparticles_b200.so: the kernels write what other ranks need straight into the peers' device
 memory over NVLink and synchronise through sequence flags (include/particles_b200.h,
 "multi-GPU").  This module only does the one-time plumbing a host program owes the library:
 
-  * one process per GPU (torchrun / mpirun ...): all-gather the 576-byte CUDA-IPC blobs of
+  * one process per GPU (torchrun / mpirun ...): all-gather the 704-byte CUDA-IPC blobs of
     `pf_mg_ipc_handles` once (any side channel; `TorchGroup` uses torch.distributed, which is
     also what the tests use over gloo for the host-side logic), `pf_mg_set_peer`, `pf_mg_connect`;
   * one process driving several GPUs (`LocalGroup`): `pf_mg_create_local` does all of it.
@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PF_FEARNHEAD, PF_MG_IPC_BYTES, PF_MG_NARRAYS, PF_NIW, PF_NIX2, pf_config, pf_step_stats
+from ._lib import PF_CHENLIU, PF_FEARNHEAD, PF_MG_IPC_BYTES, PF_MG_NARRAYS, PF_NIW, PF_NIX2, pf_config, pf_step_stats
 
 _dp = C.POINTER(C.c_double)
 
@@ -81,12 +81,12 @@ class LocalGroup:
 LocalComm = LocalGroup          # (name used by earlier tests)
 
 
-def _config(n, prior, stateprior, k_max, history, seed, keep):
+def _config(n, prior, stateprior, k_max, history, seed, keep, kind=PF_FEARNHEAD, rejuv=50.0):
     from . import NormalInverseChisq, NormalInverseWishart
     cfg = pf_config()
-    cfg.filter_kind, cfg.precision, cfg.n_particles, cfg.k_max = PF_FEARNHEAD, 0, int(n), int(k_max)
+    cfg.filter_kind, cfg.precision, cfg.n_particles, cfg.k_max = kind, 0, int(n), int(k_max)
     cfg.order, cfg.history = 0, int(history)
-    cfg.alpha, cfg.rejuv_threshold, cfg.seed = stateprior.alpha, 50.0, seed
+    cfg.alpha, cfg.rejuv_threshold, cfg.seed = stateprior.alpha, float(rejuv), seed
     if isinstance(prior, NormalInverseChisq):
         cfg.prior_kind, cfg.d = PF_NIX2, 1
         mu0, lam0 = np.array([prior.mu]), np.zeros((1, 1))
@@ -107,13 +107,15 @@ class ShardedFearnheadParticles:
     """FearnheadParticles (src/fearnhead.jl:13-30) with the population sharded over group.size GPUs.
     Same results as the unsharded filter, particle for particle (global order = rank-major)."""
 
-    def __init__(self, n, prior, stateprior, group, *, k_max=32, history=0, device=None, seed=0, on_overflow="warn"):
+    _kind = PF_FEARNHEAD
+
+    def __init__(self, n, prior, stateprior, group, *, k_max=32, history=0, device=None, seed=0, on_overflow="warn", rejuv=50.0):
         self.group, self.N, self.k_max = group, int(n), int(k_max)
         self.on_overflow, self._overflow_seen = on_overflow, 0
         L = _lib.load()
         self.L = L
         self._keep = []
-        cfg = _config(n, prior, stateprior, k_max, history, seed, self._keep)
+        cfg = _config(n, prior, stateprior, k_max, history, seed, self._keep, self._kind, rejuv)
         self.d = int(cfg.d)
         G = group.size
         if isinstance(group, LocalGroup):
@@ -253,3 +255,18 @@ class ShardedFearnheadParticles:
         ms, n = C.c_double(), C.c_int64()
         _lib.check(self.L.pf_last_timing(self.handles[0], C.byref(ms), C.byref(n)), self.handles[0])
         return ms.value, n.value
+
+
+class ShardedChenLiuParticles(ShardedFearnheadParticles):
+    """ChenLiuParticles (src/chenliu.jl:7-26) with the N particles block-sharded over group.size GPUs (rank r owns the
+    global particles [r q, (r + 1) q), q = ceil(N / G)).  The coefficient of variation is formed from exact integer
+    sums exchanged through peer memory, so every rank takes the 1-GPU run's rejuvenation decisions; a rejuvenating
+    child pulls its ancestor's record from whichever rank owns it.  uniforms: T x 2N (the categorical draws, then the
+    stratified rejuvenation uniforms), or None for the device stream."""
+    _kind = PF_CHENLIU
+
+    def fit_(self, y, u=None):
+        return self.filter_(np.atleast_2d(np.asarray(y, dtype=np.float64).reshape(1, -1)), None if u is None else np.atleast_2d(u))
+
+    def __len__(self):
+        return self.N

@@ -115,3 +115,51 @@ def test_one_process_driving_all_gpus():
     assert np.array_equal(sh.last_ancestors(), ref.last_ancestors())
     assert np.array_equal(sh.log_evidence, ref.log_evidence)
     assert np.array_equal(sh.assignments(), ref.assignments())
+
+
+def _worker_chenliu(rank, world, port, N, T, d, ok):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["PF_MG_TIMEOUT_MS"] = "30000"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import particles_b200 as pb
+        from particles_b200.distributed import ShardedChenLiuParticles, TorchGroup
+        rng = np.random.default_rng(4321)
+        if d == 2:
+            ys = _mix2d(rng, T)
+        else:
+            ys = 6.0 * np.sign(rng.standard_normal((32, d)))[rng.integers(0, 32, T)] + rng.standard_normal((T, d))
+        prior = pb.NormalInverseWishart(np.zeros(d), 0.1, np.eye(d), d + 1.0)
+        crp = pb.ChineseRestaurantProcess(1.0)
+        sh = ShardedChenLiuParticles(N, prior, crp, TorchGroup(), history=T, k_max=40, device=rank, seed=7)
+        half = T // 2
+        sh.filter_(ys[:half])                            # device uniforms, two calls
+        le0 = sh.log_evidence.copy()
+        sh.filter_(ys[half:])
+        le = np.concatenate([le0, sh.log_evidence])
+        ref = pb.ChenLiuParticles(N, prior, crp, history=T, k_max=40, device=rank, seed=7)
+        ref.filter_(ys)
+        assert np.array_equal(sh.ncomponents(), ref.ncomponents())
+        assert np.array_equal(sh.last_ancestors(), ref.last_ancestors())
+        assert np.array_equal(sh.logweights(), ref.logweights())
+        assert np.array_equal(le, ref.log_evidence)
+        assert np.array_equal(sh.assignments(), ref.assignments())
+        dist.barrier()
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ndev() < 2, reason="needs >= 2 CUDA devices")
+@pytest.mark.parametrize("N,T,d", [(1 << 17, 40, 2), (1 << 14, 40, 8)])
+def test_chenliu_one_process_per_gpu_equals_unsharded(N, T, d):
+    """Sharded Chen-Liu over CUDA IPC: scalar exchanges through peer memory, ancestors pulled from the peers' stores on
+    rejuvenation steps; bitwise equal to the one-GPU run."""
+    import torch.multiprocessing as mp
+    world = min(4, _ndev())
+    ok = mp.get_context("spawn").Array("i", [0] * world)
+    mp.spawn(_worker_chenliu, args=(world, _free_port(), N, T, d, ok), nprocs=world, join=True)
+    assert list(ok) == [1] * world

@@ -116,3 +116,57 @@ def test_exchange_overflow_is_reported_not_silent(monkeypatch):
     with pytest.raises(pb.PFError) as e:
         sh.filter_(ys, rng.random(T))
     assert e.value.code == 5 and "exchange segment" in str(e.value)
+
+
+# ------------------------------------------------------------------ Chen-Liu (src/chenliu.jl:54-69), sharded
+def _same_chenliu(sh, ref, what):
+    assert np.array_equal(sh.ncomponents(), ref.ncomponents()), f"K differs {what}"
+    assert np.array_equal(sh.last_ancestors(), ref.last_ancestors()), f"ancestors differ {what}"
+    assert np.array_equal(sh.last_assignments(), ref.last_assignments()), f"assignments differ {what}"
+    assert np.array_equal(sh.logweights(), ref.logweights()), f"log-weights differ {what}"
+    a, b = sh.last_step(), ref.last_step()
+    for key in ("n_out", "log_total_w", "cv", "resampled"):
+        assert a[key] == b[key], (key, what)
+
+
+@pytest.mark.parametrize("G,N,T,d", [(2, 1000, 60, 1), (4, 1003, 60, 2), (8, 4096, 40, 2), (3, 600, 30, 8), (16, 5000, 30, 1)])
+def test_sharded_chenliu_equals_unsharded_stepwise(G, N, T, d):
+    """All decisions (categorical draws, CV trigger, stratified rejuvenation across shards) and the weights are those
+    of the one-GPU run, bit for bit; N not divisible by G leaves the last shard shorter."""
+    from particles_b200.distributed import ShardedChenLiuParticles
+    rng = np.random.default_rng(40 + G)
+    if d == 1:
+        ys = (np.array([-6.0, -2.0, 2.0, 6.0])[rng.integers(0, 4, T)] + rng.standard_normal(T)).reshape(-1, 1)
+        prior = pb.NormalInverseChisq(0.0, 1.0, 0.1, 1.0)
+    else:
+        ys = _mix2d(rng, T) if d == 2 else 6.0 * np.sign(rng.standard_normal((8, d)))[rng.integers(0, 8, T)] + rng.standard_normal((T, d))
+        prior = pb.NormalInverseWishart(np.zeros(d), 0.1, np.eye(d), d + 1.0)
+    U = rng.random((T, 2 * N))
+    crp = pb.ChineseRestaurantProcess(1.0)
+    ref = pb.ChenLiuParticles(N, prior, crp, history=T, k_max=40)
+    sh = ShardedChenLiuParticles(N, prior, crp, LocalGroup(G), history=T, k_max=40)
+    n_rejuv = 0
+    for t in range(T):
+        ref.fit_(ys[t], U[t])
+        sh.fit_(ys[t], U[t])
+        _same_chenliu(sh, ref, f"at step {t}")
+        n_rejuv += ref.last_step()["resampled"]
+    assert n_rejuv >= (2 if d < 8 else 0)
+    assert np.array_equal(sh.assignments(), ref.assignments())
+
+
+@pytest.mark.parametrize("G,N,T", [(4, 1 << 17, 40), (8, 1 << 18, 30)])
+def test_sharded_chenliu_one_call_device_uniforms(G, N, T):
+    """The whole stream in one pf_mg_filter call, uniforms drawn on the device from the global particle index."""
+    from particles_b200.distributed import ShardedChenLiuParticles
+    rng = np.random.default_rng(60 + G)
+    ys = _mix2d(rng, T)
+    prior = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0)
+    crp = pb.ChineseRestaurantProcess(1.0)
+    ref = pb.ChenLiuParticles(N, prior, crp, history=T, k_max=32, seed=11)
+    ref.filter_(ys)
+    sh = ShardedChenLiuParticles(N, prior, crp, LocalGroup(G), history=T, k_max=32, seed=11)
+    sh.filter_(ys)
+    _same_chenliu(sh, ref, "after the stream")
+    assert np.array_equal(sh.log_evidence, ref.log_evidence)
+    assert np.array_equal(sh.assignments(), ref.assignments())
