@@ -247,8 +247,9 @@ int32_t pf_last_timing(pf_handle h, double *device_ms, int64_t *kernel_launches)
 /* Per-kernel-class device times: when profiling is on, every launch of the step sequence is
  * bracketed by CUDA events on the handle's stream; times accumulate until the next
  * pf_set_profiling call.  Classes: 0 prestep, 1 expand, 2 select, 3 scan, 4 instantiate,
- * 5 steplog, 6 sort, 7 cl_propagate, 8 cl_stats, 9 cl_finish. */
-#define PF_KERNEL_CLASSES 10
+ * 5 steplog, 6 sort, 7 cl_propagate, 8 cl_stats, 9 cl_finish, 10 inst_expand (instantiate fused with the next
+ * observation's expansion: the pipelined steps of pf_filter). */
+#define PF_KERNEL_CLASSES 11
 int32_t pf_set_profiling(pf_handle h, int32_t on);
 int32_t pf_get_kernel_times(pf_handle h, double *ms /* [PF_KERNEL_CLASSES] */, int64_t *launches /* [PF_KERNEL_CLASSES] */);
 const char *pf_kernel_class_name(int32_t k);

@@ -44,14 +44,18 @@ __global__ void k_prestep(StepState *st, const PriorConst *pc, const double *y, 
     if (xch && !xch_wait(xch, XCH_D, seq - 1)) { sel_halt(guard, step, PF_HALT_TIMEOUT); return; }
     if (guard) guard->list_n = 0;                      // the sample expansion appends from 0
     using L = Layout<D>;
-    // first: 1 = the filter's first observation, 2 = a halted step is run again (the roll-over already happened)
-    if (first == 0) st->n_live = st->n_next;
-    if (first != 2) st->M_pred = first ? st->n_live : st->M_next;      // (first step: empty particles, one putative each)
+    // first: 1 = the filter's first observation, 2 = a halted step is run again (the roll-over already happened),
+    // 3 = pipelined step: the previous step's children are instantiated WHILE they are expanded for this observation,
+    // so the putative count is not known yet (k_count_next accumulates it)
+    if (first == 0 || first == 3) st->n_live = st->n_next;
+    if (first == 3) st->M_pred = 0;
+    else if (first != 2) st->M_pred = first ? st->n_live : st->M_next;      // (first step: empty particles, one putative each)
     st->M_next = 0; st->vmax_sample = 0;
     st->n_next = 0;
     st->M = 0; st->vmax_bits = 0; st->ticket = 0; st->ticket2 = 0; st->n_picked = 0; st->n_kept = 0;
     StepConst c;
     c.forced = forced; c.pad = 0;
+    c.prev_lw_resamp = prev ? prev->lw_resamp : 0.0; c.prev_log_total = prev ? prev->log_total : 0.0;
     double dx[D], z[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1];
 #pragma unroll
     for (int i = 0; i < D; i++) { c.y[i] = y[i]; dx[i] = y[i] - pc->mu0[i]; dinv[i] = pc->L0_dinv[i]; }
@@ -120,15 +124,30 @@ struct ScanRec {
 #ifndef PF_INST_MINBLOCKS
 #define PF_INST_MINBLOCKS 1
 #endif
-template <int D, int MODE>
-__global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const double *__restrict__ S, const double *__restrict__ logw,
+// INST (pipelined step): particle i is child i of the PREVIOUS step's survivor list.  Its record does not exist yet:
+// the thread gathers the parent's slots, applies add(comp, y_prev) to the chosen one in registers
+// (instantiate, src/particle.jl:131-149), stores the child (MODE 2) and evaluates the child's putatives for THIS
+// observation from the registers -- the separate read of the new population by the expansion disappears.
+struct InstArgs {
+    const unsigned int *surv_parent;       // survivor list of the previous step
+    const unsigned char *surv_slot;
+    const double *V_prev;                  // the previous step's putative weights
+    const StepConst *scp_prev;             // ... observation and new-cluster slot
+    double *S2; int *Kc2; double *logw2;   // the children's store (MODE 2)
+    unsigned int *gen_anc; unsigned char *gen_asg;
+};
+#ifndef PF_INSTEXP_MINBLOCKS
+#define PF_INSTEXP_MINBLOCKS 3
+#endif
+template <int D, int MODE, bool INST = false>
+__global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_MINBLOCKS) k_expand(const double *__restrict__ S, const double *__restrict__ logw,
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
                                                 double *__restrict__ V, unsigned char *__restrict__ cnt,
                                                 SelScratch *sc, long long stride, double *__restrict__ list,
                                                 TileSum *__restrict__ tiles, TileFuse *__restrict__ tfuse,
-                                                ScanRec rec = ScanRec{nullptr, nullptr})
+                                                ScanRec rec = ScanRec{nullptr, nullptr}, InstArgs ia = InstArgs{})
 {
     using L = Layout<D>;
     if (sc && sc->halt) return;
@@ -191,12 +210,28 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
         double y[D], mu0[D];
 #pragma unroll
         for (int k = 0; k < D; k++) { y[k] = scp->y[k]; mu0[k] = pc->mu0[k]; }
-        const int K = Kc[i];
-        const double lw0 = logw[i];
+        long long src = i;                   // the particle whose slots are read
+        int jsel = -1;                       // INST: the slot that receives the previous observation
+        int K; double lw0;
+        if (INST) {
+            const unsigned int par = ia.surv_parent[i];
+            const unsigned char sl = ia.surv_slot[i];
+            jsel = sl & 0x7F;
+            K = Kc[par];
+            const double v = ia.V_prev[(long long)jsel * cap + par];
+            lw0 = (sl & 0x80) ? scp->prev_lw_resamp : (log(v) - scp->prev_log_total);      // src/fearnhead.jl:172-179
+            src = par;
+            if (MODE == 2) {
+                ia.logw2[i] = lw0; ia.Kc2[i] = K + (jsel == K ? 1 : 0);
+                if (ia.gen_anc) { ia.gen_anc[i] = par; ia.gen_asg[i] = (unsigned char)jsel; }
+            }
+        } else {
+            K = Kc[i]; lw0 = logw[i];
+        }
         // software pipeline: the fields of slot j+1 are in flight while slot j is evaluated
         double fcur[L::F], fnxt[L::F];
         if (K > 0) {
-            const double *base = S + i;
+            const double *base = S + src;
 #pragma unroll
             for (int f = 0; f < L::F; f++) fcur[f] = base[(long long)f * cap];
         }
@@ -206,18 +241,40 @@ __global__ void __launch_bounds__(256, PF_EXPAND_MINBLOCKS) k_expand(const doubl
             double lw = lw0 + slot_logw<D>(row, fl[L::F_LOGDET], fl + L::F_MEAN, fl + L::F_DINV, fl + L::F_OFF, y, mu0, z, &q);
             emit(j, exp(lw));
         };
+        auto store_child = [&](const double *fl, int j) {
+            double *dst = ia.S2 + ((long long)j * L::F) * cap + i;
+#pragma unroll
+            for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = fl[f];
+        };
         for (int j = 0; j < K; j++) {
             if (j + 1 < K) {
-                const double *base = S + ((long long)(j + 1) * L::F) * cap + i;
+                const double *base = S + ((long long)(j + 1) * L::F) * cap + src;
 #pragma unroll
                 for (int f = 0; f < L::F; f++) fnxt[f] = base[(long long)f * cap];
+            }
+            if (INST) {
+                if (j == jsel) {
+                    double yp[D];
+#pragma unroll
+                    for (int k = 0; k < D; k++) yp[k] = ia.scp_prev->y[k];
+                    slot_add<D>(fcur, tab[(int)fcur[L::F_N]], yp, mu0);
+                }
+                if (MODE == 2) store_child(fcur, j);
             }
             eval(fcur, j);
 #pragma unroll
             for (int f = 0; f < L::F; f++) fcur[f] = fnxt[f];
         }
-        int c = K;
-        if (K < k_max) { emit(K, exp(lw0 + scp->lw_new)); c = K + 1; }
+        int Kn = K;
+        if (INST && jsel == K) {             // the previous observation opened a new cluster (src/particle.jl:141-146)
+#pragma unroll
+            for (int f = 0; f < L::F; f++) fcur[f] = ia.scp_prev->newslot[f];
+            if (MODE == 2) store_child(fcur, K);
+            eval(fcur, K);
+            Kn = K + 1;
+        }
+        int c = Kn;
+        if (Kn < k_max) { emit(Kn, exp(lw0 + scp->lw_new)); c = Kn + 1; }
         else myOvf = 1;
         if (MODE != 1) cnt[i] = (unsigned char)c;
         myM = c;
@@ -914,32 +971,14 @@ __device__ __forceinline__ void instantiate_one(const long long t, const double 
     if (j < K) {
         const double *src = S + ((long long)j * L::F) * cap + par;
         double *dst = dstb + ((long long)j * L::F) * stride;
-        double n = src[(long long)L::F_N * cap];
-        double logdet = src[(long long)L::F_LOGDET * cap];
-        double m[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1], dx[D], z[D];
+        double fl[L::F], y[D], mu0[D];
 #pragma unroll
-        for (int k = 0; k < D; k++) { m[k] = src[(long long)(L::F_MEAN + k) * cap]; dinv[k] = src[(long long)(L::F_DINV + k) * cap]; }
+        for (int f = 0; f < L::F; f++) fl[f] = src[(long long)f * cap];
 #pragma unroll
-        for (int k = 0; k < L::NOFF; k++) off[k] = src[(long long)(L::F_OFF + k) * cap];
-        const NRow row = tab[(int)n];
+        for (int k = 0; k < D; k++) { y[k] = scp->y[k]; mu0[k] = pc->mu0[k]; }
+        slot_add<D>(fl, tab[(int)fl[L::F_N]], y, mu0);
 #pragma unroll
-        for (int k = 0; k < D; k++) dx[k] = scp->y[k] - (pc->mu0[k] + row.g * (m[k] - pc->mu0[k]));
-        double q = quad_form<D>(dx, dinv, off, z);
-        double sr = sqrt(row.r);
-#pragma unroll
-        for (int k = 0; k < D; k++) dx[k] *= sr;
-        chol_rank1<D>(dinv, off, dx);
-        double tw = n + 1.0;
-        dst[(long long)L::F_N * stride] = tw;
-        dst[(long long)L::F_LOGDET * stride] = logdet + log1p(row.r * q);
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            double delta = scp->y[k] - m[k];                       // Welford, src/component.jl:46-47
-            dst[(long long)(L::F_MEAN + k) * stride] = m[k] + delta / tw;
-            dst[(long long)(L::F_DINV + k) * stride] = dinv[k];
-        }
-#pragma unroll
-        for (int k = 0; k < L::NOFF; k++) dst[(long long)(L::F_OFF + k) * stride] = off[k];
+        for (int f = 0; f < L::F; f++) dst[(long long)f * stride] = fl[f];
     } else {
         double *dst = dstb + ((long long)K * L::F) * stride;
 #pragma unroll
@@ -967,6 +1006,31 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
     // (grid-stride: a sharded rank sizes its grid for a balanced share and loops when it produced more)
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_out; t += (long long)gridDim.x * blockDim.x)
         instantiate_one<D>(t, S, Kc, S2, Kc2, logw2, cap, tab, pc, scp, st, res, V, surv_parent, surv_slot, gen_anc, gen_asg, ro, k_max, guard, m_next, peers, gen_off, sp_cur, sp_nxt);
+}
+
+// pipelined step: the number of putatives the children will have (M of the next observation, exact: it decides
+// "keep everything" and scales the sample bracket), from the survivor list alone
+__global__ void __launch_bounds__(256) k_count_next(const StepState *__restrict__ st, const int *__restrict__ Kc,
+                                                    const unsigned int *__restrict__ surv_parent, const unsigned char *__restrict__ surv_slot,
+                                                    int k_max, long long *m_pred, const SelScratch *guard)
+{
+    if (guard->halt) return;
+    const long long n = st->n_live;
+    unsigned int c = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int K = Kc[surv_parent[t]];
+        const int Kn = K + (((int)(surv_slot[t] & 0x7F) == K) ? 1 : 0);
+        c += (unsigned int)(Kn + (Kn < k_max ? 1 : 0));
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ unsigned int s_c[8];
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < 8; w++) tot += s_c[w];
+        if (tot) atomicAdd((unsigned long long *)m_pred, tot);
+    }
 }
 
 // ------------------------------------------------------------------ reference-literal order

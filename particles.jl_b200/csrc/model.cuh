@@ -61,6 +61,8 @@ struct StepConst {
     int forced;                            // >= 0: Labeled(y, label) -- every particle has the single putative "slot forced"
                                            // (src/labeled.jl:10-11); -1: label missing
     int pad;
+    double prev_lw_resamp, prev_log_total; // the previous step's log(c / total) and log(total) (src/fearnhead.jl:172-179): the
+                                           // pipelined step builds a child's log-weight while it expands it for this observation
 };
 
 struct PriorConst {
@@ -126,6 +128,31 @@ __host__ __device__ __forceinline__ void chol_rank1(double *dinv, double *off, d
             x[i] = c * x[i] - s * Lik;
             off[idx] = Lik;
         }
+    }
+}
+
+// add(comp, y) (src/component.jl:44-50, 64-70, 85) on one slot's fields in registers: Welford mean update and rank-1
+// update of the carried Cholesky factor of Lambda_n
+template <int D>
+__host__ __device__ __forceinline__ void slot_add(double *fl, const NRow &row, const double *y, const double *mu0)
+{
+    using L = Layout<D>;
+    double dx[D], z[D];
+    double *m = fl + L::F_MEAN, *dinv = fl + L::F_DINV, *off = fl + L::F_OFF;
+#pragma unroll
+    for (int k = 0; k < D; k++) dx[k] = y[k] - (mu0[k] + row.g * (m[k] - mu0[k]));
+    const double q = quad_form<D>(dx, dinv, off, z);
+    const double sr = sqrt(row.r);
+#pragma unroll
+    for (int k = 0; k < D; k++) dx[k] *= sr;
+    chol_rank1<D>(dinv, off, dx);
+    const double tw = fl[L::F_N] + 1.0;
+    fl[L::F_N] = tw;
+    fl[L::F_LOGDET] = fl[L::F_LOGDET] + log1p(row.r * q);
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const double delta = y[k] - m[k];                          // Welford, src/component.jl:46-47
+        m[k] = m[k] + delta / tw;
     }
 }
 

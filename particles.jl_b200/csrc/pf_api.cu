@@ -30,7 +30,11 @@ struct pf_filter_s {
     int *Kc[2] = {nullptr, nullptr};
     int cur = 0;
     // step scratch
-    double *V = nullptr;
+    double *V = nullptr;                  // putative weights of the current step
+    double *V_alt = nullptr;              // pipelined steps: the buffer the NEXT step's putatives are written to (swapped with V)
+    StepConst *stc_alt = nullptr;         // ... and its per-observation constants (swapped with stc)
+    bool pipeline = false;                // instantiate of step t fused with the expansion of step t + 1 inside pf_filter
+    bool pre_expanded = false;            // the step about to run was expanded by the previous step's pipelined tail
     unsigned char *cnt = nullptr;
     unsigned int *surv_parent = nullptr;
     unsigned char *surv_slot = nullptr;
@@ -135,8 +139,8 @@ static int32_t set_cuda_error(pf_handle h, cudaError_t e, const char *what, int 
 
 // ------------------------------------------------------------------ per-kernel timing
 static const char *k_class_names[PF_KERNEL_CLASSES] = {"prestep", "expand", "select", "scan", "instantiate", "steplog",
-                                                        "sort", "cl_propagate", "cl_stats", "cl_finish"};
-enum { KC_PRESTEP = 0, KC_EXPAND, KC_SELECT, KC_SCAN, KC_INSTANTIATE, KC_STEPLOG, KC_SORT, KC_CL_PROP, KC_CL_STATS, KC_CL_FINISH };
+                                                        "sort", "cl_propagate", "cl_stats", "cl_finish", "inst_expand"};
+enum { KC_PRESTEP = 0, KC_EXPAND, KC_SELECT, KC_SCAN, KC_INSTANTIATE, KC_STEPLOG, KC_SORT, KC_CL_PROP, KC_CL_STATS, KC_CL_FINISH, KC_INST_EXPAND };
 
 struct LaunchTimer {            // records an event pair around one launch (or launch group) when profiling
     pf_handle h; int cls; size_t slot = 0; bool on;
@@ -224,7 +228,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     if (!h) return PF_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->cnt, h->surv_parent,
+    void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->V_alt, h->stc_alt, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->supers, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_tiles, h->clp, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
                     h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
@@ -317,6 +321,10 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         CT(dmalloc(&h->Kc[b], cap));
     }
     CT(dmalloc(&h->V, (size_t)(h->k_max + 2) * cap));
+    // single-GPU index-order CRP Fearnhead filter: instantiate of one observation is fused with the expansion of the next
+    h->pipeline = cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_INDEX && h->nranks == 1 && spk == PF_SP_CRP &&
+                  !getenv("PF_NO_PIPELINE") && !getenv("PF_NO_FUSE");
+    if (h->pipeline) { CT(dmalloc(&h->V_alt, (size_t)(h->k_max + 2) * cap)); CT(dmalloc(&h->stc_alt, 1)); }
     CT(dmalloc(&h->cnt, cap));
     h->surv_cap = h->nranks > 1 ? std::min<long long>(h->N, cap * (h->k_max + 1)) + 1024 : cap;
     CT(dmalloc(&h->surv_parent, h->surv_cap));
@@ -526,8 +534,11 @@ static int32_t launch_classic_search(pf_handle h, SelArgs a)
     return PF_OK;
 }
 
+// y_next / u_next: the next observation of the same call when the step may run its tail pipelined (instantiate fused
+// with the next expansion), else null
 template <int D>
-static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_dev, StepLog *log_dev)
+static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_dev, StepLog *log_dev,
+                              const double *y_next = nullptr, const double *u_next = nullptr)
 {
     const long long cap = h->cap;
     const int cur = h->cur, nxt = cur ^ 1;
@@ -544,12 +555,24 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     const int forced = h->cur_label;
     // other state priors and labeled observations: their own expansion kernel, then the classic search
     const bool sp_path = h->sp_kind != PF_SP_CRP || forced >= 0;
-    {
+    const bool pre = h->pre_expanded;          // prestep, sample, bracket and expansion ran in the previous step's tail
+    h->pre_expanded = false;
+    if (!pre) {
         LaunchTimer lt(h, KC_PRESTEP);
         k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, h->redo ? 2 : (h->steps == 0 ? 1 : 0), h->sc, h->res, nullptr, 0, h->steps, forced);
     }
     const bool fused = h->fused && h->cfg.order == PF_ORDER_INDEX && !sp_path;
-    if (fused) {
+    if (fused && pre) {
+        LaunchTimer lt(h, KC_SELECT, 2 * (h->retries + 1));
+        SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
+        a.external_sample = 1; a.preclassified = 1;
+        const long long l0 = h->launches;
+        for (int r = 0; r <= h->retries; r++) {
+            int32_t rc = launch_round(h, a, r > 0);
+            if (rc != PF_OK) return rc;
+        }
+        h->launches = l0;
+    } else if (fused) {
         // bracket the threshold on a sample expansion, then classify inside the full expansion
         {
             LaunchTimer lt(h, KC_SELECT, 2);
@@ -629,6 +652,48 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, nullptr, 0, h->sc, 1);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
                                                             h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr}, h->sc);
+    }
+    if (fused && y_next && h->pipeline) {
+        // pipelined tail: close this step's record, then build the children WHILE expanding them for the next observation
+        {
+            LaunchTimer lt(h, KC_STEPLOG);
+            k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->sc, h->steps, h->dbg_status, nullptr, nullptr, 0);
+        }
+        h->steps++;                                   // the host mirrors now describe the next step
+        h->ub_live = ub_next;
+        h->epoch++;
+        {
+            LaunchTimer lt(h, KC_PRESTEP, 2);
+            k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_next, h->stc_alt, 3, h->sc, h->res, nullptr, 0, h->steps, -1);
+            k_count_next<<<std::min(grid_for(ub_next, 256), h->num_sms * 8), 256, 0, h->stream>>>(h->st, h->Kc[cur], h->surv_parent, h->surv_slot, h->k_max,
+                                                                                                 &h->st->M_pred, h->sc);
+        }
+        InstArgs ia;
+        ia.surv_parent = h->surv_parent; ia.surv_slot = h->surv_slot; ia.V_prev = h->V; ia.scp_prev = h->stc;
+        ia.S2 = h->S[nxt]; ia.Kc2 = h->Kc[nxt]; ia.logw2 = h->logw[nxt]; ia.gen_anc = ga; ia.gen_asg = gs;
+        {
+            LaunchTimer lt(h, KC_SELECT, 2);
+            const long long ns = 4 * ((ub_next + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride));
+            k_expand<D, 1, true><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,
+                                                                       nullptr, ScanRec{nullptr, nullptr}, ia);
+            std::swap(h->stc, h->stc_alt);            // (sel_args points the search at the next step's plateau value)
+            SelArgs a = sel_args(h, h->V_alt, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_next, h->cand, h->cand_cap, h->sc, h->res);
+            std::swap(h->stc, h->stc_alt);
+            a.external_sample = 1;
+            CUDA_TRY(launch_coop(k_sel_bracket, h->coop_grid, h->stream, a));
+        }
+        {
+            LaunchTimer lt(h, KC_INST_EXPAND);
+            k_expand<D, 2, true><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec, ia);
+        }
+        CUDA_TRY(cudaGetLastError());
+        std::swap(h->V, h->V_alt);
+        std::swap(h->stc, h->stc_alt);
+        h->cur = nxt;
+        h->pre_expanded = true;
+        return PF_OK;
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
@@ -821,7 +886,12 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
             ub_hist[t] = h->ub_live;
             if (fh) {
                 h->cur_label = labels ? labels[t] : -1;
-                DISPATCH_D(d, rc = fearnhead_step<D>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t));
+                // the tail of step t may be fused with the expansion of step t + 1 (both ordinary CRP steps of this call,
+                // genealogy row available)
+                const bool next_ok = h->pipeline && t + 1 < T && !(labels && (labels[t] >= 0 || labels[t + 1] >= 0)) &&
+                                     (!h->hist_cap || h->steps + 1 < h->hist_cap);
+                DISPATCH_D(d, rc = fearnhead_step<D>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t,
+                                                     next_ok ? h->ys_dev + (t + 1) * d : nullptr, next_ok ? h->u_dev + t + 1 : nullptr));
                 h->redo = 0; h->retries = SEL_RETRIES; h->cur_label = -1;
             } else {
                 const double *ud = nullptr;
@@ -852,7 +922,7 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
         }
         // rewind the host mirrors to the halted step and run it again with more rounds queued
         h->steps = steps0 + th; h->cur = cur0 ^ (int)(th & 1); h->ub_live = ub_hist[th];
-        h->redo = 1; h->retries = 12;
+        h->redo = 1; h->retries = 12; h->pre_expanded = false;       // the halted step is expanded again from the store
         CUDA_TRY(cudaMemsetAsync(&h->sc->halt, 0, 2 * sizeof(long long), h->stream));
         t_begin = th;
     }

@@ -452,10 +452,10 @@ class ParticleFilter:
 
     def kernel_times(self):
         """{class name: (device ms, launches)} accumulated since set_profiling."""
-        ms = np.zeros(10)
-        n = np.zeros(10, dtype=np.int64)
+        ms = np.zeros(_lib.PF_KERNEL_CLASSES)
+        n = np.zeros(_lib.PF_KERNEL_CLASSES, dtype=np.int64)
         _lib.check(self._L.pf_get_kernel_times(self._h, ms.ctypes.data_as(_dp), n.ctypes.data_as(C.POINTER(C.c_int64))), self._h)
-        return {self._L.pf_kernel_class_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(10)}
+        return {self._L.pf_kernel_class_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(_lib.PF_KERNEL_CLASSES)}
 
     def timing(self):
         ms, n = C.c_double(), C.c_int64()

@@ -244,11 +244,11 @@ class ShardedFearnheadParticles:
 
     def kernel_times(self):
         """{class name: (device ms, launches)} of this process's first shard since set_profiling."""
-        ms = np.zeros(10)
-        n = np.zeros(10, dtype=np.int64)
+        ms = np.zeros(_lib.PF_KERNEL_CLASSES)
+        n = np.zeros(_lib.PF_KERNEL_CLASSES, dtype=np.int64)
         _lib.check(self.L.pf_get_kernel_times(self.handles[0], ms.ctypes.data_as(_dp), n.ctypes.data_as(C.POINTER(C.c_int64))),
                    self.handles[0])
-        return {self.L.pf_kernel_class_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(10)}
+        return {self.L.pf_kernel_class_name(k).decode(): (float(ms[k]), int(n[k])) for k in range(_lib.PF_KERNEL_CLASSES)}
 
     def timing(self):
         """(device ms of the last filter_ call on this process's first shard, its kernel launches)."""

@@ -331,3 +331,53 @@ def test_failed_bracket_is_widened_not_opened(margin, monkeypatch):
     w = np.exp(rng.standard_normal(300_000) * 3.0)
     for order in (pb.PF_ORDER_INDEX, pb.PF_ORDER_SORTED):
         _check_select(w, 40_000, rng.random(), order)
+
+
+# ------------------------------------------------------------------ pipelined steps of pf_filter
+@pytest.mark.parametrize("d,N,T", [(1, 300, 80), (2, 5000, 60), (2, 1 << 17, 40), (4, 2000, 40), (8, 600, 30)])
+def test_pipelined_filter_equals_stepwise(d, N, T, monkeypatch):
+    """Inside one pf_filter call the tail of every observation (instantiate) is fused with the expansion of the next
+    one; observation-by-observation calls run the separate kernels.  Same arithmetic, same decisions: weights,
+    genealogy, evidence and store are bitwise equal -- also with the pipelining switched off, and when the stream is
+    cut into several calls."""
+    rng = np.random.default_rng(300 + d)
+    ys = _mixture_1d(rng, T).reshape(-1, 1) if d == 1 else _mixture_nd(rng, T, d, 4)
+    us = rng.random(T)
+    pprior, _ = _priors("nix2" if d == 1 else "niw", d)
+    crp = pb.ChineseRestaurantProcess(1.0)
+
+    def run(mode):
+        ps = pb.FearnheadParticles(N, pprior, crp, history=T, k_max=40, on_overflow="raise")
+        if mode == "one_call":
+            ps.filter_(ys, uniforms=us)
+            le = ps.log_evidence
+        elif mode == "three_calls":
+            cuts, le = [0, T // 3, T // 3 + 1, T], []
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                ps.filter_(ys[a:b], uniforms=us[a:b])
+                le.append(ps.log_evidence)
+            le = np.concatenate(le)
+        else:
+            le = []
+            for t in range(T):
+                ps.fit_(ys[t], [us[t]])
+                le.append(ps.last_step()["log_total_w"])
+            le = np.array(le)
+        return ps, le
+
+    ref, le_ref = run("stepwise")
+    for mode in ("one_call", "three_calls"):
+        ps, le = run(mode)
+        assert len(ps) == len(ref), mode
+        assert np.array_equal(le, le_ref), mode
+        assert np.array_equal(ps.logweights(), ref.logweights()), mode
+        assert np.array_equal(ps.ncomponents(), ref.ncomponents()), mode
+        assert np.array_equal(ps.assignments(), ref.assignments()), mode
+        assert np.array_equal(ps.putative_weights(), ref.putative_weights()), mode
+        for i in (0, len(ps) // 2, len(ps) - 1):
+            for c0, c1 in zip(ps.particles()[i].components, ref.particles()[i].components):
+                assert c0.n == c1.n and np.array_equal(c0.mean, c1.mean) and np.array_equal(c0.chol, c1.chol) and c0.logdet == c1.logdet
+        assert ps.last_step()["n_putative"] == ref.last_step()["n_putative"]
+    monkeypatch.setenv("PF_NO_PIPELINE", "1")
+    ps, le = run("one_call")
+    assert np.array_equal(le, le_ref) and np.array_equal(ps.assignments(), ref.assignments())
