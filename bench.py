@@ -52,8 +52,11 @@ def mixture(rng, T, k=8, radius=6.0):
     return radius * np.stack([np.cos(ang), np.sin(ang)], axis=1) + rng.standard_normal((T, 2))
 
 
+STORE_BYTES = 8      # bytes per cluster field in the particle store (4 under --precision f32)
+
+
 def rec_bytes(d):
-    return 8 * (2 + d + d * (d + 1) // 2)
+    return STORE_BYTES * (2 + d + d * (d + 1) // 2)
 
 
 def bytes_per_update(kbar, d=D):
@@ -176,7 +179,8 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     T_all = a.burnin + W + 3 * K
     assert T_all <= T_MAX
     prior, crp = pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0), pb.ChineseRestaurantProcess(1.0)
-    ps = ShardedFearnheadParticles(N, prior, crp, TorchGroup(), k_max=a.k_max, history=0, device=local, on_overflow="ignore")
+    ps = ShardedFearnheadParticles(N, prior, crp, TorchGroup(), k_max=a.k_max, history=0, device=local, on_overflow="ignore",
+                                   precision=a.precision)
 
     def mean_k():
         K_loc = ps._local(ps.L.pf_get_ncomponents, np.int32, __import__("ctypes").c_int32)[0]
@@ -239,7 +243,7 @@ def sharded_arm(a, dist, rank, world, local, N, K, W, config):
     verify = None
     if not a.no_verify:
         if rank == 0:
-            ref = pb.FearnheadParticles(N, prior, crp, k_max=a.k_max, history=0, device=local, on_overflow="ignore")
+            ref = pb.FearnheadParticles(N, prior, crp, k_max=a.k_max, history=0, device=local, on_overflow="ignore", precision=a.precision)
             ref.filter_(ys[:o], uniforms=us[:o])
             le_all = np.concatenate(les)
             same = bool(np.array_equal(le_all, ref.log_evidence))
@@ -293,8 +297,12 @@ def main():
     ap.add_argument("--order", default="index", choices=["index", "sorted"])
     ap.add_argument("--k-max", type=int, default=K_MAX, help="cluster slots per particle (the line fails if a candidate was dropped)")
     ap.add_argument("--allow-overflow", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="storage type of the particle store (f32: PF_F32, floats in the store, FP64 arithmetic and selection)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the unsharded re-run on rank 0 (outside the timed region)")
     a = ap.parse_args()
+    global STORE_BYTES
+    STORE_BYTES = 4 if a.precision == "f32" else 8
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,7 +311,7 @@ def main():
     config = {"workload": f"2-D NIW Fearnhead filter, 2^{a.log2n} particles, 8-cluster synthetic mixture "
                           f"(BASELINE configs[3]); inputs >> L2 (particle store {N * 8 * rec_bytes(D) / 1e9:.1f} GB at K=8)",
               "n_particles": N, "d": D, "k_max": a.k_max, "prior": "NIW(0, 0.1, I, 3)", "alpha": 1.0,
-              "burnin_obs": a.burnin, "order": a.order, "sharding": f"particles block-sharded over {a.gpus} GPU(s)",
+              "burnin_obs": a.burnin, "order": a.order, "store_precision": a.precision, "sharding": f"particles block-sharded over {a.gpus} GPU(s)",
               "l2_policy": "inputs larger than L2"}
 
     # ---------------------------------------------------------------- reference arm
@@ -340,7 +348,7 @@ def main():
     order = pb.PF_ORDER_INDEX if a.order == "index" else pb.PF_ORDER_SORTED
     ps = pb.FearnheadParticles(N, pb.NormalInverseWishart(np.zeros(2), 0.1, np.eye(2), 3.0),
                                pb.ChineseRestaurantProcess(1.0), k_max=a.k_max, history=T_all, device=local, order=order,
-                               on_overflow="ignore")
+                               on_overflow="ignore", precision=a.precision)
     o = 0
     ps.filter_(ys[o:o + a.burnin], uniforms=us[o:o + a.burnin]); o += a.burnin
     if W:

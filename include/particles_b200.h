@@ -55,7 +55,9 @@ typedef struct {
     int32_t filter_kind;      /* PF_FEARNHEAD | PF_CHENLIU */
     int32_t prior_kind;       /* PF_NIX2 | PF_NIW */
     int32_t d;                /* observation dimension (NIX2: 1) */
-    int32_t precision;        /* PF_F64 (PF_F32: reserved) */
+    int32_t precision;        /* storage type of the particle store: PF_F64, or PF_F32 (every cluster field is kept as a
+                                 float: half the store traffic; the predictive arithmetic, the putative weights and the
+                                 selection stay as in PF_F64.  Log-weights agree with the FP64 filter to ~1e-6 relative) */
     int64_t n_particles;      /* N: particle budget (src/fearnhead.jl:15, src/chenliu.jl:9) */
     int32_t k_max;            /* cluster slots per particle (reference: unbounded, src/particle.jl:142-143);
                                  at K == k_max the new-cluster candidate is dropped and counted */

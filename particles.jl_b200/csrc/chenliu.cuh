@@ -44,8 +44,8 @@ struct ClShard {
 // ------------------------------------------------------------------ k_cl_propagate
 // Pass 1 evaluates the K + 1 putative weights (src/particle.jl:100-116) into the scratch rows of V and sums them;
 // pass 2 walks them for the inverse-CDF draw; the chosen slot is updated in place.
-template <int D>
-__global__ void __launch_bounds__(256) k_cl_propagate(double *S0, double *S1, const double *__restrict__ logw0,
+template <int D, typename R = double>
+__global__ void __launch_bounds__(256) k_cl_propagate(R *S0, R *S1, const double *__restrict__ logw0,
                                                       const double *__restrict__ logw1, int *Kc0, int *Kc1, long long cap,
                                                       ClShard sh, int k_max, const NRow *__restrict__ tab,
                                                       const PriorConst *__restrict__ pc, const StepConst *__restrict__ scp,
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) k_cl_propagate(double *S0, double *S1, co
     __shared__ u64 s_max[8];
     __shared__ long long s_ovf[8];
     const int cur = cl->cur;
-    double *S = cur ? S1 : S0;
+    R *S = cur ? S1 : S0;
     const double *logw = cur ? logw1 : logw0;
     int *Kc = cur ? Kc1 : Kc0;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,10 +72,10 @@ __global__ void __launch_bounds__(256) k_cl_propagate(double *S0, double *S1, co
         const double lw0 = logw[i];
         double sum = 0.0;
         for (int j = 0; j < K; j++) {
-            const double *base = S + ((long long)j * L::F) * cap + i;
+            const R *base = S + ((long long)j * L::F) * cap + i;
             double fl[L::F], z[D], q;
 #pragma unroll
-            for (int f = 0; f < L::F; f++) fl[f] = base[(long long)f * cap];
+            for (int f = 0; f < L::F; f++) fl[f] = (double)base[(long long)f * cap];
             const NRow row = tab[(int)fl[L::F_N]];
             const double v = exp(lw0 + slot_logw<D>(row, fl[L::F_LOGDET], fl + L::F_MEAN, fl + L::F_DINV, fl + L::F_OFF, y, mu0, z, &q));
             V[(long long)j * cap + i] = v;
@@ -95,38 +95,18 @@ __global__ void __launch_bounds__(256) k_cl_propagate(double *S0, double *S1, co
         double cw = V[i];
         while (cw < t && pick < C - 1) { pick++; cw += V[(long long)pick * cap + i]; }
         // instantiate in place (src/particle.jl:134-149)
-        double *dst = S + ((long long)pick * L::F) * cap + i;
+        R *dst = S + ((long long)pick * L::F) * cap + i;
         if (pick == K) {
 #pragma unroll
-            for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = scp->newslot[f];
+            for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = (R)scp->newslot[f];
             Kc[i] = K + 1;
         } else {
-            double n = dst[(long long)L::F_N * cap];
-            double logdet = dst[(long long)L::F_LOGDET * cap];
-            double m[D], dinv[D], off[L::NOFF > 0 ? L::NOFF : 1], dx[D], z[D];
+            double fl[L::F];
 #pragma unroll
-            for (int k = 0; k < D; k++) { m[k] = dst[(long long)(L::F_MEAN + k) * cap]; dinv[k] = dst[(long long)(L::F_DINV + k) * cap]; }
+            for (int f = 0; f < L::F; f++) fl[f] = (double)dst[(long long)f * cap];
+            slot_add<D>(fl, tab[(int)fl[L::F_N]], y, mu0);
 #pragma unroll
-            for (int k = 0; k < L::NOFF; k++) off[k] = dst[(long long)(L::F_OFF + k) * cap];
-            const NRow row = tab[(int)n];
-#pragma unroll
-            for (int k = 0; k < D; k++) dx[k] = y[k] - (mu0[k] + row.g * (m[k] - mu0[k]));
-            double q = quad_form<D>(dx, dinv, off, z);
-            double sr = sqrt(row.r);
-#pragma unroll
-            for (int k = 0; k < D; k++) dx[k] *= sr;
-            chol_rank1<D>(dinv, off, dx);
-            double tw = n + 1.0;
-            dst[(long long)L::F_N * cap] = tw;
-            dst[(long long)L::F_LOGDET * cap] = logdet + log1p(row.r * q);
-#pragma unroll
-            for (int k = 0; k < D; k++) {
-                double delta = y[k] - m[k];
-                dst[(long long)(L::F_MEAN + k) * cap] = m[k] + delta / tw;
-                dst[(long long)(L::F_DINV + k) * cap] = dinv[k];
-            }
-#pragma unroll
-            for (int k = 0; k < L::NOFF; k++) dst[(long long)(L::F_OFF + k) * cap] = off[k];
+            for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = (R)fl[f];
         }
         W[i] = sum;
         asg_tmp[i] = (unsigned char)pick;
@@ -356,7 +336,7 @@ __global__ void k_cl_x_ready(const ClState *cl, const Xch *x, unsigned long long
 
 // arrays of every rank a rejuvenating child reads its ancestor from (single GPU: entry 0 = the local arrays)
 struct ClPeers {
-    const double *S[2][PF_MAX_RANKS];
+    const void *S[2][PF_MAX_RANKS];          // (elements of the handle's storage type)
     const int *Kc[2][PF_MAX_RANKS];
     const u128 *cum[PF_MAX_RANKS];
     const unsigned char *asg_tmp[PF_MAX_RANKS];
@@ -365,8 +345,8 @@ struct ClPeers {
 // normalise (src/chenliu.jl:65-66) or rejuvenate (src/chenliu.jl:61, stratified variant): child gi takes the ancestor
 //   a = min{k : cum_k N 2^53 > (gi 2^53 + floor(u 2^53)) Qtot} = min{k : cum_k > floor((gi 2^53 + mu) Qtot / (N 2^53))}
 // found by a search over the ranks' totals and a binary search in the owner's prefix array
-template <int D>
-__global__ void __launch_bounds__(256) k_cl_finish(double *S0, double *S1, int *Kc0, int *Kc1, double *logw0, double *logw1,
+template <int D, typename R = double>
+__global__ void __launch_bounds__(256) k_cl_finish(R *S0, R *S1, int *Kc0, int *Kc1, double *logw0, double *logw1,
                                                    long long cap, ClShard sh, int nranks, const ClState *__restrict__ cl,
                                                    const double *__restrict__ W, const ClPeers *__restrict__ peers,
                                                    const double *__restrict__ u_dev, u64 seed, u64 step,
@@ -385,14 +365,14 @@ __global__ void __launch_bounds__(256) k_cl_finish(double *S0, double *S1, int *
         if (gen_anc) { gen_anc[i] = (unsigned int)gi; gen_asg[i] = asg_tmp[i]; }
         return;
     }
-    double *S2 = cur ? S0 : S1;
+    R *S2 = cur ? S0 : S1;
     int *Kc2 = cur ? Kc0 : Kc1;
     double *logw2 = cur ? logw0 : logw1;
     const double u = u_dev ? u_dev[i] : pf_uniform(seed, step, 2, (u64)gi);
     const u64 mu = (u64)(u * 9007199254740992.0);
-    const u128 R = add128(shl128(mk128((u64)gi, 0), 53), mk128(mu, 0));           // gi 2^53 + mu  (< 2^81)
+    const u128 Rpos = add128(shl128(mk128((u64)gi, 0), 53), mk128(mu, 0));        // gi 2^53 + mu  (< 2^81)
     u64 X[4];
-    mul128x128(R, cl->Qtot, X);                                                     // < 2^168
+    mul128x128(Rpos, cl->Qtot, X);                                                     // < 2^168
     const u128 Xs = mk128((X[0] >> 53) | (X[1] << 11), (X[1] >> 53) | (X[2] << 11));   // X >> 53  (< 2^115)
     unsigned int rem;
     const u128 thr = divmod128_32(Xs, (unsigned int)sh.N, &rem);
@@ -409,17 +389,17 @@ __global__ void __launch_bounds__(256) k_cl_finish(double *S0, double *S1, int *
         if (lt128(thr, c)) hi = mid; else lo = mid + 1;
     }
     const long long a = lo;
-    const double *S = peers->S[cur][r];
+    const R *S = static_cast<const R *>(peers->S[cur][r]);
     const int K = __ldcg(peers->Kc[cur][r] + a);
     Kc2[i] = K;
     logw2[i] = -log((double)sh.N);                     // weights reset to 1/N
     if (gen_anc) { gen_anc[i] = (unsigned int)((long long)r * sh.q + a); gen_asg[i] = __ldcg(peers->asg_tmp[r] + a); }
-    const double *src = S + a;
-    double *dst = S2 + i;
+    const R *src = S + a;
+    R *dst = S2 + i;
     const int nrows = K * L::F;
     int row = 0;
     for (; row + 8 <= nrows; row += 8) {
-        double tmp[8];
+        R tmp[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) tmp[k] = __ldcg(src + (long long)(row + k) * cap);
 #pragma unroll

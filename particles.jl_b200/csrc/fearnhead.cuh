@@ -133,14 +133,16 @@ struct InstArgs {
     const unsigned char *surv_slot;
     const double *V_prev;                  // the previous step's putative weights
     const StepConst *scp_prev;             // ... observation and new-cluster slot
-    double *S2; int *Kc2; double *logw2;   // the children's store (MODE 2)
+    void *S2; int *Kc2; double *logw2;     // the children's store (MODE 2; elements of the kernel's storage type)
     unsigned int *gen_anc; unsigned char *gen_asg;
 };
 #ifndef PF_INSTEXP_MINBLOCKS
 #define PF_INSTEXP_MINBLOCKS 3
 #endif
-template <int D, int MODE, bool INST = false>
-__global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_MINBLOCKS) k_expand(const double *__restrict__ S, const double *__restrict__ logw,
+// R: storage type of the particle store (double, or float under PF_F32: the arithmetic stays in double, every field
+// is rounded to R when it is stored, so the store traffic halves)
+template <int D, int MODE, bool INST = false, typename R = double>
+__global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_MINBLOCKS) k_expand(const R *__restrict__ S, const double *__restrict__ logw,
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
@@ -231,9 +233,9 @@ __global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_M
         // software pipeline: the fields of slot j+1 are in flight while slot j is evaluated
         double fcur[L::F], fnxt[L::F];
         if (K > 0) {
-            const double *base = S + src;
+            const R *base = S + src;
 #pragma unroll
-            for (int f = 0; f < L::F; f++) fcur[f] = base[(long long)f * cap];
+            for (int f = 0; f < L::F; f++) fcur[f] = (double)base[(long long)f * cap];
         }
         auto eval = [&](const double *fl, int j) {
             double z[D], q;
@@ -242,15 +244,15 @@ __global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_M
             emit(j, exp(lw));
         };
         auto store_child = [&](const double *fl, int j) {
-            double *dst = ia.S2 + ((long long)j * L::F) * cap + i;
+            R *dst = static_cast<R *>(ia.S2) + ((long long)j * L::F) * cap + i;
 #pragma unroll
-            for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = fl[f];
+            for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = (R)fl[f];
         };
         for (int j = 0; j < K; j++) {
             if (j + 1 < K) {
-                const double *base = S + ((long long)(j + 1) * L::F) * cap + src;
+                const R *base = S + ((long long)(j + 1) * L::F) * cap + src;
 #pragma unroll
-                for (int f = 0; f < L::F; f++) fnxt[f] = base[(long long)f * cap];
+                for (int f = 0; f < L::F; f++) fnxt[f] = (double)base[(long long)f * cap];
             }
             if (INST) {
                 if (j == jsel) {
@@ -258,6 +260,8 @@ __global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_M
 #pragma unroll
                     for (int k = 0; k < D; k++) yp[k] = ia.scp_prev->y[k];
                     slot_add<D>(fcur, tab[(int)fcur[L::F_N]], yp, mu0);
+#pragma unroll
+                    for (int f = 0; f < L::F; f++) fcur[f] = (double)(R)fcur[f];      // what the stored child holds (no-op for R = double)
                 }
                 if (MODE == 2) store_child(fcur, j);
             }
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_M
         int Kn = K;
         if (INST && jsel == K) {             // the previous observation opened a new cluster (src/particle.jl:141-146)
 #pragma unroll
-            for (int f = 0; f < L::F; f++) fcur[f] = ia.scp_prev->newslot[f];
+            for (int f = 0; f < L::F; f++) fcur[f] = (double)(R)ia.scp_prev->newslot[f];
             if (MODE == 2) store_child(fcur, K);
             eval(fcur, K);
             Kn = K + 1;
@@ -349,8 +353,8 @@ __global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_M
 //   ChangePoint                K = 0: jj = 0 new; else jj = 0 stay (slot K-1), jj = 1 change (slot K)    max(k,1):k+1
 //   NStatePrior                jj = slot                                                 1:n
 //   labeled                    jj = 0 only: the labelled slot
-template <int D>
-__global__ void __launch_bounds__(256) k_expand_sp(const double *__restrict__ S, const double *__restrict__ logw,
+template <int D, typename R = double>
+__global__ void __launch_bounds__(256) k_expand_sp(const R *__restrict__ S, const double *__restrict__ logw,
                                                    const int *__restrict__ Kc, long long cap, int k_max,
                                                    const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                    const StepConst *__restrict__ scp, StepState *st, double *__restrict__ V,
@@ -375,10 +379,10 @@ __global__ void __launch_bounds__(256) k_expand_sp(const double *__restrict__ S,
         const double lp_newc = kind == SPK_STICKY ? pc->sp_log_alpha : 0.0;      // (CRP: log alpha is inside lw_new)
         double n_of = 0.0;
         auto pred = [&](int j) {       // log predictive of y under slot j (+ log N_j under the CRP: folded into the table)
-            const double *base = S + ((long long)j * L::F) * cap + i;
+            const R *base = S + ((long long)j * L::F) * cap + i;
             double fl[L::F], z[D], q;
 #pragma unroll
-            for (int f = 0; f < L::F; f++) fl[f] = base[(long long)f * cap];
+            for (int f = 0; f < L::F; f++) fl[f] = (double)base[(long long)f * cap];
             n_of = fl[L::F_N];
             const NRow row = tab[(int)fl[L::F_N]];
             return slot_logw<D>(row, fl[L::F_LOGDET], fl + L::F_MEAN, fl + L::F_DINV, fl + L::F_OFF, y, mu0, z, &q);
@@ -490,7 +494,7 @@ struct RankOff {
 // the ranks live in one process): k_instantiate stores a child that changes owner straight into
 // its new owner's store over NVLink -- no packing, no send/recv buffers, no host-known sizes.
 struct PeerTable {
-    double *S[PF_MAX_RANKS];
+    void *S[PF_MAX_RANKS];                 // (elements of the handle's storage type)
     int *Kc[PF_MAX_RANKS];
     double *logw[PF_MAX_RANKS];
     unsigned int *gen_anc[PF_MAX_RANKS];
@@ -886,9 +890,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
 // population from its parent's slots (copy), applies add(comp, y) to the chosen slot as a
 // Welford mean update + rank-1 Cholesky update, appends (ancestor, assignment) to the
 // genealogy and sets the normalised log-weight (src/fearnhead.jl:172-179).
-template <int D>
-__device__ __forceinline__ void instantiate_one(const long long t, const double *__restrict__ S, const int *__restrict__ Kc,
-                                                     double *S2, int *Kc2,
+template <int D, typename R>
+__device__ __forceinline__ void instantiate_one(const long long t, const R *__restrict__ S, const int *__restrict__ Kc,
+                                                     R *S2, int *Kc2,
                                                      double *logw2, long long cap,
                                                      const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                      const StepConst *__restrict__ scp, const StepState *__restrict__ st,
@@ -902,7 +906,7 @@ __device__ __forceinline__ void instantiate_one(const long long t, const double 
 {
     using L = Layout<D>;
     // destination of child t: a local index, or (sharded run) an index in the arrays of its new owner
-    double *dstb = S2 + t;
+    R *dstb = S2 + t;
     long long idx = t;
     unsigned int anc_off = 0;
     if (ro) {
@@ -912,7 +916,7 @@ __device__ __forceinline__ void instantiate_one(const long long t, const double 
         idx = g - (long long)dest * ro->q;
         if (dest != ro->rank) {
             // the child is written into its new owner's arrays (peer memory over NVLink)
-            S2 = peers->S[dest]; Kc2 = peers->Kc[dest]; logw2 = peers->logw[dest];
+            S2 = static_cast<R *>(peers->S[dest]); Kc2 = peers->Kc[dest]; logw2 = peers->logw[dest];
             gen_anc = peers->gen_anc[dest] ? peers->gen_anc[dest] + gen_off : nullptr;
             gen_asg = peers->gen_asg[dest] ? peers->gen_asg[dest] + gen_off : nullptr;
         }
@@ -956,11 +960,11 @@ __device__ __forceinline__ void instantiate_one(const long long t, const double 
     }
     // copy the parent's slots (the chosen one is rewritten below)
     {
-        const double *src = S + par;
+        const R *src = S + par;
         const int nrows = K * L::F;
         int r = 0;
         for (; r + 8 <= nrows; r += 8) {
-            double tmp[8];
+            R tmp[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) tmp[k] = src[(long long)(r + k) * cap];
 #pragma unroll
@@ -969,26 +973,26 @@ __device__ __forceinline__ void instantiate_one(const long long t, const double 
         for (; r < nrows; r++) dstb[(long long)r * stride] = src[(long long)r * cap];
     }
     if (j < K) {
-        const double *src = S + ((long long)j * L::F) * cap + par;
-        double *dst = dstb + ((long long)j * L::F) * stride;
+        const R *src = S + ((long long)j * L::F) * cap + par;
+        R *dst = dstb + ((long long)j * L::F) * stride;
         double fl[L::F], y[D], mu0[D];
 #pragma unroll
-        for (int f = 0; f < L::F; f++) fl[f] = src[(long long)f * cap];
+        for (int f = 0; f < L::F; f++) fl[f] = (double)src[(long long)f * cap];
 #pragma unroll
         for (int k = 0; k < D; k++) { y[k] = scp->y[k]; mu0[k] = pc->mu0[k]; }
         slot_add<D>(fl, tab[(int)fl[L::F_N]], y, mu0);
 #pragma unroll
-        for (int f = 0; f < L::F; f++) dst[(long long)f * stride] = fl[f];
+        for (int f = 0; f < L::F; f++) dst[(long long)f * stride] = (R)fl[f];
     } else {
-        double *dst = dstb + ((long long)K * L::F) * stride;
+        R *dst = dstb + ((long long)K * L::F) * stride;
 #pragma unroll
-        for (int f = 0; f < L::F; f++) dst[(long long)f * stride] = scp->newslot[f];
+        for (int f = 0; f < L::F; f++) dst[(long long)f * stride] = (R)scp->newslot[f];
     }
 }
 
-template <int D>
-__global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const double *__restrict__ S, const int *__restrict__ Kc,
-                                                     double *S2, int *Kc2,
+template <int D, typename R = double>
+__global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const R *__restrict__ S, const int *__restrict__ Kc,
+                                                     R *S2, int *Kc2,
                                                      double *logw2, long long cap,
                                                      const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                      const StepConst *__restrict__ scp, const StepState *__restrict__ st,
@@ -1005,7 +1009,7 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const do
     const long long n_out = ro ? ro->n_local : st->n_next;
     // (grid-stride: a sharded rank sizes its grid for a balanced share and loops when it produced more)
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_out; t += (long long)gridDim.x * blockDim.x)
-        instantiate_one<D>(t, S, Kc, S2, Kc2, logw2, cap, tab, pc, scp, st, res, V, surv_parent, surv_slot, gen_anc, gen_asg, ro, k_max, guard, m_next, peers, gen_off, sp_cur, sp_nxt);
+        instantiate_one<D, R>(t, S, Kc, S2, Kc2, logw2, cap, tab, pc, scp, st, res, V, surv_parent, surv_slot, gen_anc, gen_asg, ro, k_max, guard, m_next, peers, gen_off, sp_cur, sp_nxt);
 }
 
 // pipelined step: the number of putatives the children will have (M of the next observation, exact: it decides

@@ -25,7 +25,9 @@ struct pf_filter_s {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // particle store (ping-pong)
-    double *S[2] = {nullptr, nullptr};
+    void *S[2] = {nullptr, nullptr};      // elements of the storage type: double, or float under PF_F32
+    bool f32 = false;
+    size_t esz = sizeof(double);          // bytes per store element
     double *logw[2] = {nullptr, nullptr};
     int *Kc[2] = {nullptr, nullptr};
     int cur = 0;
@@ -207,13 +209,15 @@ static bool chol_lower(int d, const double *A /*col-major*/, double *Lo /*col-ma
 template <typename T>
 static cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
-#define DISPATCH_D(dd, CALL)                                         \
+// CALL sees `D` (observation dimension) and `R` (storage type of the particle store of handle `h`)
+#define DISPATCH_P(...) do { if (h->f32) { using R = float; __VA_ARGS__; } else { using R = double; __VA_ARGS__; } } while (0)
+#define DISPATCH_D(dd, ...)                                          \
     switch (dd) {                                                    \
-    case 1: { constexpr int D = 1; CALL; } break;                    \
-    case 2: { constexpr int D = 2; CALL; } break;                    \
-    case 3: { constexpr int D = 3; CALL; } break;                    \
-    case 4: { constexpr int D = 4; CALL; } break;                    \
-    case 8: { constexpr int D = 8; CALL; } break;                    \
+    case 1: { constexpr int D = 1; DISPATCH_P(__VA_ARGS__); } break;        \
+    case 2: { constexpr int D = 2; DISPATCH_P(__VA_ARGS__); } break;        \
+    case 3: { constexpr int D = 3; DISPATCH_P(__VA_ARGS__); } break;        \
+    case 4: { constexpr int D = 4; DISPATCH_P(__VA_ARGS__); } break;        \
+    case 8: { constexpr int D = 8; DISPATCH_P(__VA_ARGS__); } break;        \
     default: break;                                                  \
     }
 
@@ -254,7 +258,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown prior_kind");
     int d = cfg->prior_kind == PF_NIX2 ? 1 : cfg->d;
     if (!supported_d(d)) return set_error(nullptr, PF_ERR_ARG, "pf_create: d must be one of 1, 2, 3, 4, 8");
-    if (cfg->precision != PF_F64) return set_error(nullptr, PF_ERR_ARG, "pf_create: only PF_F64 is implemented");
+    if (cfg->precision != PF_F64 && cfg->precision != PF_F32) return set_error(nullptr, PF_ERR_ARG, "pf_create: unknown precision");
     if (cfg->n_particles < 1 || cfg->n_particles > (1ll << 27)) return set_error(nullptr, PF_ERR_ARG, "pf_create: n_particles out of range [1, 2^27]");
     if (cfg->k_max < 1 || cfg->k_max + 1 > PF_MAX_SLOTS) return set_error(nullptr, PF_ERR_ARG, "pf_create: k_max out of range [1, 63]");
     if (!(cfg->alpha > 0.0) || !(cfg->kappa0 > 0.0)) return set_error(nullptr, PF_ERR_ARG, "pf_create: alpha and kappa0 must be positive");
@@ -290,6 +294,8 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     h->cap = (cfg->n_particles + h->nranks - 1) / h->nranks;
     if (h->nranks > 1) h->cap += 64;                      // equal blocks of ceil(n / G) at every step
     h->F = 2 + d + d * (d + 1) / 2;
+    h->f32 = cfg->precision == PF_F32;
+    h->esz = h->f32 ? sizeof(float) : sizeof(double);
     h->sp_kind = spk;
     if (spk == PF_SP_NSTATE) h->sp_counts.assign(cfg->sp_counts, cfg->sp_counts + cfg->sp_n);
     h->mu0.assign(cfg->mu0, cfg->mu0 + d);
@@ -316,7 +322,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     const long long cap = h->cap;
     const size_t store = (size_t)h->k_max * h->F * cap;
     for (int b = 0; b < 2; b++) {
-        CT(dmalloc(&h->S[b], store));
+        CT(cudaMalloc(&h->S[b], store * h->esz));
         CT(dmalloc(&h->logw[b], cap));
         CT(dmalloc(&h->Kc[b], cap));
     }
@@ -460,7 +466,12 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         for (int k = 0; k < d * (d - 1) / 2; k++) slot[2 + 2 * d + k] = pc.L0_off[k];
         for (int j = 0; j < cfg->sp_n; j++)
             for (int f = 0; f < h->F; f++)
-                CT(cudaMemcpyAsync(h->S[0] + ((size_t)j * h->F + f) * cap, &slot[f], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                {
+                    const float sf = (float)slot[f];
+                    CT(cudaMemcpyAsync((char *)h->S[0] + ((size_t)j * h->F + f) * cap * h->esz, h->f32 ? (const void *)&sf : (const void *)&slot[f], h->esz,
+                                       cudaMemcpyHostToDevice, h->stream));
+                    CT(cudaStreamSynchronize(h->stream));
+                }
         CT(cudaStreamSynchronize(h->stream));
         const int Kn = cfg->sp_n;
         CT(cudaMemcpyAsync(h->Kc[0], &Kn, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -536,7 +547,7 @@ static int32_t launch_classic_search(pf_handle h, SelArgs a)
 
 // y_next / u_next: the next observation of the same call when the step may run its tail pipelined (instantiate fused
 // with the next expansion), else null
-template <int D>
+template <int D, typename R>
 static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_dev, StepLog *log_dev,
                               const double *y_next = nullptr, const double *u_next = nullptr)
 {
@@ -577,7 +588,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         {
             LaunchTimer lt(h, KC_SELECT, 2);
             const long long ns = 4 * ((ub + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride));     // groups of 4 particles
-            k_expand<D, 1><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+            k_expand<D, 1, false, R><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,
                                                                        nullptr);
             SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
@@ -586,7 +597,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         }
         {
             LaunchTimer lt(h, KC_EXPAND);
-            k_expand<D, 2><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+            k_expand<D, 2, false, R><<<grid_for(ub, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
         }
         {
@@ -604,10 +615,10 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         {
             LaunchTimer lt(h, KC_EXPAND);
             if (sp_path)
-                k_expand_sp<D><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc, h->stc,
+                k_expand_sp<D, R><<<grid_for(ub, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc, h->stc,
                                                                           h->st, h->V, h->cnt, h->sc, h->sp[cur], h->steps);
             else
-                k_expand<D, 0><<<grid_for(ub, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                k_expand<D, 0, false, R><<<grid_for(ub, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                            h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
         }
         {
@@ -674,7 +685,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         {
             LaunchTimer lt(h, KC_SELECT, 2);
             const long long ns = 4 * ((ub_next + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride));
-            k_expand<D, 1, true><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+            k_expand<D, 1, true, R><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,
                                                                        nullptr, ScanRec{nullptr, nullptr}, ia);
             std::swap(h->stc, h->stc_alt);            // (sel_args points the search at the next step's plateau value)
@@ -685,7 +696,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         }
         {
             LaunchTimer lt(h, KC_INST_EXPAND);
-            k_expand<D, 2, true><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+            k_expand<D, 2, true, R><<<grid_for(ub_next, 256), 256, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec, ia);
         }
         CUDA_TRY(cudaGetLastError());
@@ -697,7 +708,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
-        k_instantiate<D><<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
+        k_instantiate<D, R><<<grid_for(ub_next, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->Kc[cur], (R *)h->S[nxt], h->Kc[nxt], h->logw[nxt], cap,
                                                                           h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
                                                                           h->surv_slot, ga, gs, nullptr, h->k_max, h->sc, &h->st->M_next, nullptr, 0,
                                                                           h->sp[cur], h->sp[nxt]);
@@ -716,7 +727,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
 // One Chen-Liu observation as six stages; the exchange kernel that closes stage s publishes this shard's scalar and
 // (unless the shards of this process run in lock step on one stream) also waits for the peers'; in lock step the wait
 // is the first launch of stage s + 1, queued after every shard has published.  Single GPU: stages 0..5 back to back.
-template <int D>
+template <int D, typename R>
 static int32_t chenliu_stage(pf_handle h, int s, const double *y_dev, const double *u_dev /* [2 n_loc] or null */, StepLog *log_dev)
 {
     const long long cap = h->cap, N = h->N, n_loc = h->shard.n_loc;
@@ -735,7 +746,7 @@ static int32_t chenliu_stage(pf_handle h, int s, const double *y_dev, const doub
             k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_dev, h->stc, 1, h->sc, nullptr, x, seq, h->steps);
         }
         LaunchTimer lt(h, KC_CL_PROP);
-        k_cl_propagate<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], cap, h->shard, h->k_max,
+        k_cl_propagate<D, R><<<g256, 256, 0, h->stream>>>((R *)h->S[0], (R *)h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], cap, h->shard, h->k_max,
                                                          h->tab, h->pc, h->stc, h->st, h->cl, u_dev, h->cfg.seed, (u64)h->steps, h->W,
                                                          h->asg_tmp, h->V, h->sc);
         if (x) { k_cl_x_wmax<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, pub, h->sc); h->launches++; }
@@ -775,7 +786,7 @@ static int32_t chenliu_stage(pf_handle h, int s, const double *y_dev, const doub
         {
             LaunchTimer lt(h, KC_CL_FINISH);
             if (x && split) { k_cl_x_ready<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, SEL_ST_RUN, h->sc); h->launches++; }
-            k_cl_finish<D><<<g256, 256, 0, h->stream>>>(h->S[0], h->S[1], h->Kc[0], h->Kc[1], h->logw[0], h->logw[1], cap, h->shard, h->nranks, h->cl,
+            k_cl_finish<D, R><<<g256, 256, 0, h->stream>>>((R *)h->S[0], (R *)h->S[1], h->Kc[0], h->Kc[1], h->logw[0], h->logw[1], cap, h->shard, h->nranks, h->cl,
                                                           h->W, h->clp, u_dev ? u_dev + n_loc : nullptr, h->cfg.seed, (u64)h->steps, h->asg_tmp, ga, gs, h->sc);
         }
         {
@@ -790,11 +801,11 @@ static int32_t chenliu_stage(pf_handle h, int s, const double *y_dev, const doub
     return PF_OK;
 }
 
-template <int D>
+template <int D, typename R>
 static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_dev /* 2N or null */, StepLog *log_dev)
 {
     for (int s = 0; s < 6; s++) {
-        int32_t rc = chenliu_stage<D>(h, s, y_dev, u_dev, log_dev);
+        int32_t rc = chenliu_stage<D, R>(h, s, y_dev, u_dev, log_dev);
         if (rc != PF_OK) return rc;
     }
     return PF_OK;
@@ -890,7 +901,7 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
                 // genealogy row available)
                 const bool next_ok = h->pipeline && t + 1 < T && !(labels && (labels[t] >= 0 || labels[t + 1] >= 0)) &&
                                      (!h->hist_cap || h->steps + 1 < h->hist_cap);
-                DISPATCH_D(d, rc = fearnhead_step<D>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t,
+                DISPATCH_D(d, rc = fearnhead_step<D, R>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t,
                                                      next_ok ? h->ys_dev + (t + 1) * d : nullptr, next_ok ? h->u_dev + t + 1 : nullptr));
                 h->redo = 0; h->retries = SEL_RETRIES; h->cur_label = -1;
             } else {
@@ -899,7 +910,7 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
                     CUDA_TRY(cudaMemcpyAsync(h->u_dev, uniforms + t * ups, sizeof(double) * 2 * h->N, cudaMemcpyHostToDevice, h->stream));
                     ud = h->u_dev;
                 }
-                DISPATCH_D(d, rc = chenliu_step<D>(h, h->ys_dev + t * d, ud, h->slog + t));
+                DISPATCH_D(d, rc = chenliu_step<D, R>(h, h->ys_dev + t * d, ud, h->slog + t));
             }
             if (rc != PF_OK) { cudaStreamSynchronize(h->stream); return rc; }
         }
@@ -1041,9 +1052,11 @@ extern "C" int32_t pf_get_particle(pf_handle h, int64_t i, int32_t *K_out, doubl
     std::vector<double> rec((size_t)std::max(K, 1) * F);
     if (K > 0) {
         // strided gather: element (j*F+f) lives at S[(j*F+f)*cap + i]
-        CUDA_TRY(cudaMemcpy2DAsync(rec.data(), sizeof(double), h->S[h->cur] + i, sizeof(double) * h->cap, sizeof(double),
+        std::vector<float> recf(h->f32 ? rec.size() : 0);
+        CUDA_TRY(cudaMemcpy2DAsync(h->f32 ? (void *)recf.data() : (void *)rec.data(), h->esz, (const char *)h->S[h->cur] + i * h->esz, h->esz * h->cap, h->esz,
                                    (size_t)K * F, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (h->f32) for (size_t k = 0; k < rec.size(); k++) rec[k] = recf[k];
     }
     if (K_out) *K_out = K;
     for (int j = 0; j < K; j++) {
@@ -1175,15 +1188,15 @@ static int32_t summary_ready(pf_handle h, const char *who)
     return PF_OK;
 }
 
-template <int D>
+template <int D, typename R>
 static void launch_predictive(pf_handle h, int nb, const double *xs_dev, int nq, double *part)
 {
-    k_predictive<D><<<nb, SUM_THREADS, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->n_host, h->tab, h->pc, xs_dev, nq, part);
+    k_predictive<D, R><<<nb, SUM_THREADS, 0, h->stream>>>((const R *)h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->n_host, h->tab, h->pc, xs_dev, nq, part);
 }
-template <int D>
+template <int D, typename R>
 static void launch_pop_summary(pf_handle h, int nb, int slots, double *part)
 {
-    k_pop_summary<D><<<nb, SUM_THREADS, 0, h->stream>>>(h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->n_host, slots, h->pc, h->sp[h->cur],
+    k_pop_summary<D, R><<<nb, SUM_THREADS, 0, h->stream>>>((const R *)h->S[h->cur], h->logw[h->cur], h->Kc[h->cur], h->cap, h->n_host, slots, h->pc, h->sp[h->cur],
                                                          (double)h->steps, part);
 }
 
@@ -1208,7 +1221,7 @@ extern "C" int32_t pf_posterior_predictive(pf_handle h, const double *xs, int64_
     const double norm = (double)h->steps + h->cfg.alpha;  // sum_j N_j + alpha, the same for every particle under the CRP
     for (long long q0 = 0; q0 < Q; q0 += QB) {
         const int nq = (int)std::min<long long>(QB, Q - q0);
-        DISPATCH_D(d, launch_predictive<D>(h, (int)nb, dx.as<double>() + q0 * d, nq, dpart.as<double>()));
+        DISPATCH_D(d, launch_predictive<D, R>(h, (int)nb, dx.as<double>() + q0 * d, nq, dpart.as<double>()));
         k_sum_partials<<<nq + 1, SUM_THREADS, 0, h->stream>>>(dpart.as<double>(), nb, nq + 1, dout.as<double>());
         double res[QB + 1];
         CUDA_TRY(cudaMemcpyAsync(res, dout.p, sizeof(double) * (nq + 1), cudaMemcpyDeviceToHost, h->stream));
@@ -1228,7 +1241,7 @@ static int32_t pop_summary(pf_handle h, std::vector<double> &rec)
     DevBuf dpart, dout;
     CUDA_TRY(dpart.alloc(sizeof(double) * nb * ncol));
     CUDA_TRY(dout.alloc(sizeof(double) * ncol));
-    DISPATCH_D(h->d, launch_pop_summary<D>(h, (int)nb, slots, dpart.as<double>()));
+    DISPATCH_D(h->d, launch_pop_summary<D, R>(h, (int)nb, slots, dpart.as<double>()));
     k_sum_partials<<<ncol, SUM_THREADS, 0, h->stream>>>(dpart.as<double>(), nb, ncol, dout.as<double>());
     rec.resize(ncol);
     CUDA_TRY(cudaMemcpyAsync(rec.data(), dout.p, sizeof(double) * ncol, cudaMemcpyDeviceToHost, h->stream));
@@ -1399,7 +1412,7 @@ extern "C" int32_t pf_save(pf_handle h, const char *path)
     ok = ok && dump_dev(f, h->st, sizeof(StepState), stage) && dump_dev(f, h->res, sizeof(SelResult), stage) && dump_dev(f, h->sc, sizeof(SelScratch), stage);
     if (h->cl) ok = ok && dump_dev(f, h->cl, sizeof(ClState), stage);
     ok = ok && dump_dev(f, h->Kc[cur], sizeof(int) * n, stage) && dump_dev(f, h->logw[cur], sizeof(double) * n, stage);
-    for (long long r = 0; ok && r < (long long)max_k * h->F; r++) ok = dump_dev(f, h->S[cur] + r * cap, sizeof(double) * n, stage);
+    for (long long r = 0; ok && r < (long long)max_k * h->F; r++) ok = dump_dev(f, (const char *)h->S[cur] + r * cap * h->esz, h->esz * n, stage);
     if (h->sp_kind == PF_SP_STICKY) {
         for (long long r = 0; ok && r < max_k; r++) ok = dump_dev(f, h->sp[cur].N + r * cap, sizeof(double) * n, stage) && dump_dev(f, h->sp[cur].Nsame + r * cap, sizeof(double) * n, stage);
         ok = ok && dump_dev(f, h->sp[cur].last, sizeof(int) * n, stage);
@@ -1450,7 +1463,7 @@ extern "C" int32_t pf_load(const char *path, int32_t device, pf_handle *out)
     ok = load_dev(f, h->st, sizeof(StepState), stage) && load_dev(f, h->res, sizeof(SelResult), stage) && load_dev(f, h->sc, sizeof(SelScratch), stage);
     if (h->cl) ok = ok && load_dev(f, h->cl, sizeof(ClState), stage);
     ok = ok && load_dev(f, h->Kc[cur], sizeof(int) * n, stage) && load_dev(f, h->logw[cur], sizeof(double) * n, stage);
-    for (long long r = 0; ok && r < (long long)hd.max_k * h->F; r++) ok = load_dev(f, h->S[cur] + r * cap, sizeof(double) * n, stage);
+    for (long long r = 0; ok && r < (long long)hd.max_k * h->F; r++) ok = load_dev(f, (char *)h->S[cur] + r * cap * h->esz, h->esz * n, stage);
     if (h->sp_kind == PF_SP_STICKY) {
         for (long long r = 0; ok && r < hd.max_k; r++) ok = load_dev(f, h->sp[cur].N + r * cap, sizeof(double) * n, stage) && load_dev(f, h->sp[cur].Nsame + r * cap, sizeof(double) * n, stage);
         ok = ok && load_dev(f, h->sp[cur].last, sizeof(int) * n, stage);
@@ -1686,12 +1699,12 @@ extern "C" int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, 
         }
     }
     for (int b = 0; b < 2; b++) {
-        h->peers_host[b].S[peer] = (double *)a[b]; h->peers_host[b].Kc[peer] = (int *)a[2 + b];
+        h->peers_host[b].S[peer] = a[b]; h->peers_host[b].Kc[peer] = (int *)a[2 + b];
         h->peers_host[b].logw[peer] = (double *)a[4 + b];
         h->peers_host[b].gen_anc[peer] = (unsigned int *)a[6]; h->peers_host[b].gen_asg[peer] = (unsigned char *)a[7];
     }
     h->xch_host.reg[peer] = (XchRegion *)a[8];
-    for (int b = 0; b < 2; b++) { h->clp_host.S[b][peer] = (const double *)a[b]; h->clp_host.Kc[b][peer] = (const int *)a[2 + b]; }
+    for (int b = 0; b < 2; b++) { h->clp_host.S[b][peer] = a[b]; h->clp_host.Kc[b][peer] = (const int *)a[2 + b]; }
     h->clp_host.cum[peer] = (const u128 *)a[9]; h->clp_host.asg_tmp[peer] = (const unsigned char *)a[10];
     return PF_OK;
 }
@@ -1743,7 +1756,7 @@ extern "C" int32_t pf_mg_connect(pf_handle *hs, int32_t n_local)
 
 // ---- the stages of one sharded observation (each queues launches on the handle's stream)
 // A: roll the control block over (waits for every rank's previous generation), sample expansion, bracket
-template <int D>
+template <int D, typename R>
 static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev, int search_stage)
 {
     const long long cap = h->cap;
@@ -1756,7 +1769,7 @@ static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev,
         }
         LaunchTimer lt(h, KC_SELECT);
         const long long ns = 4 * ((cap + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride) + 1);      // groups of 4 particles (+1: the shard's phase)
-        k_expand<D, 1><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+        k_expand<D, 1, false, R><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                    h->stc, h->st, h->V, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr, nullptr);
     }
     SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
@@ -1767,7 +1780,7 @@ static int32_t mg_stage_a(pf_handle h, const double *y_dev, const double *u_dev,
 }
 
 // B: fused expansion (round 0) / classify pass (retry rounds), then the solve on the gathered candidates
-template <int D>
+template <int D, typename R>
 static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int search_stage)
 {
     const long long cap = h->cap;
@@ -1777,7 +1790,7 @@ static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int searc
     if (search_stage & SEL_ST_PUB) {
         if (!retry) {
             LaunchTimer lt(h, KC_EXPAND);
-            k_expand<D, 2><<<grid_for(cap, 256), 256, 0, h->stream>>>(h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+            k_expand<D, 2, false, R><<<grid_for(cap, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                         h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
         }
         LaunchTimer lt(h, KC_SELECT);
@@ -1803,7 +1816,7 @@ static int32_t mg_stage_c(pf_handle h)
 
 // D: global offsets from every rank's total, survivor scan, instantiate (children that change owner are
 // stored into their new owner's arrays), step record + "generation complete" signal
-template <int D>
+template <int D, typename R>
 static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
 {
     const int cur = h->cur, nxt = cur ^ 1;
@@ -1818,7 +1831,7 @@ static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
     }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
-        k_instantiate<D><<<grid_for(std::min<long long>(h->surv_cap, h->cap + h->cap / 4), 256), 256, 0, h->stream>>>(h->S[cur], h->Kc[cur], h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
+        k_instantiate<D, R><<<grid_for(std::min<long long>(h->surv_cap, h->cap + h->cap / 4), 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->Kc[cur], (R *)h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
                                                                               h->tab, h->pc, h->stc, h->st, h->res, h->V, h->surv_parent,
                                                                               h->surv_slot, ga, gs, h->ro, h->k_max, h->sc, &h->st->M_next, h->peers[nxt],
                                                                               (long long)h->steps * h->cap);
@@ -1881,7 +1894,7 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
         CUDA_TRY(cudaStreamSynchronize(h->stream));      // ubuf goes out of scope
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     }
-#define FOR_SHARDS(CALL) for (int i_ = 0; i_ < n_local && rc == PF_OK; i_++) { pf_handle h = hs[i_]; cudaSetDevice(h->cfg.device); DISPATCH_D(d, rc = CALL); }
+#define FOR_SHARDS(...) for (int i_ = 0; i_ < n_local && rc == PF_OK; i_++) { pf_handle h = hs[i_]; cudaSetDevice(h->cfg.device); DISPATCH_D(d, rc = __VA_ARGS__); }
     const int both = SEL_ST_PUB | SEL_ST_RUN;
     for (long long t = 0; t < T && rc == PF_OK; t++) {
         if (cl) {
@@ -1894,22 +1907,22 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
                     cudaMemcpyAsync(h->u_dev, ut + h->shard.goff, sizeof(double) * h->shard.n_loc, cudaMemcpyHostToDevice, h->stream);
                     cudaMemcpyAsync(h->u_dev + h->shard.n_loc, ut + h->N + h->shard.goff, sizeof(double) * h->shard.n_loc, cudaMemcpyHostToDevice, h->stream);
                 }
-            for (int st = 0; st < 6; st++) FOR_SHARDS((chenliu_stage<D>(h, st, h->ys_dev + t * d, uniforms ? h->u_dev : nullptr, h->slog + t)));
+            for (int st = 0; st < 6; st++) FOR_SHARDS((chenliu_stage<D, R>(h, st, h->ys_dev + t * d, uniforms ? h->u_dev : nullptr, h->slog + t)));
             continue;
         }
         if (lockstep) {
-            FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_PUB)));
-            FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_RUN)));
+            FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_PUB)));
+            FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_RUN)));
             for (int r = 0; r <= SEL_RETRIES; r++) {
-                FOR_SHARDS((mg_stage_b<D>(h, h->u_dev + t, r > 0, SEL_ST_PUB)));
-                FOR_SHARDS((mg_stage_b<D>(h, h->u_dev + t, r > 0, SEL_ST_RUN)));
+                FOR_SHARDS((mg_stage_b<D, R>(h, h->u_dev + t, r > 0, SEL_ST_PUB)));
+                FOR_SHARDS((mg_stage_b<D, R>(h, h->u_dev + t, r > 0, SEL_ST_RUN)));
             }
         } else {
-            FOR_SHARDS((mg_stage_a<D>(h, h->ys_dev + t * d, h->u_dev + t, both)));
-            for (int r = 0; r <= SEL_RETRIES; r++) FOR_SHARDS((mg_stage_b<D>(h, h->u_dev + t, r > 0, both)));
+            FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, both)));
+            for (int r = 0; r <= SEL_RETRIES; r++) FOR_SHARDS((mg_stage_b<D, R>(h, h->u_dev + t, r > 0, both)));
         }
         for (int i = 0; i < n_local && rc == PF_OK; i++) { cudaSetDevice(hs[i]->cfg.device); rc = mg_stage_c(hs[i]); }
-        FOR_SHARDS((mg_stage_d<D>(h, h->slog + t)));
+        FOR_SHARDS((mg_stage_d<D, R>(h, h->slog + t)));
     }
 #undef FOR_SHARDS
     // drain: every shard's records; a halted shard reports why

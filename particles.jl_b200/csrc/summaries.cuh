@@ -31,8 +31,8 @@ __device__ __forceinline__ double block_sum_double(double v, double *s_red /* >=
 // alpha / (t + alpha) under the CRP (t = observations so far, the same for every particle: the host divides);
 // t_ij = posterior_predictive of the component (src/component.jl:12-23).  The table row C(n) carries log N_j
 // (log alpha for n = 0).
-template <int D>
-__global__ void __launch_bounds__(SUM_THREADS) k_predictive(const double *__restrict__ S, const double *__restrict__ logw,
+template <int D, typename R = double>
+__global__ void __launch_bounds__(SUM_THREADS) k_predictive(const R *__restrict__ S, const double *__restrict__ logw,
                                                             const int *__restrict__ Kc, long long cap, long long n,
                                                             const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                             const double *__restrict__ xs, int Q, double *__restrict__ part)
@@ -69,10 +69,10 @@ __global__ void __launch_bounds__(SUM_THREADS) k_predictive(const double *__rest
 #pragma unroll
         for (int q = 0; q < PRED_QCHUNK; q++) acc[q] = q < nq ? s_new[q] : 0.0;
         for (int j = 0; j < K; j++) {
-            const double *base = S + ((long long)j * L::F) * cap + i;
+            const R *base = S + ((long long)j * L::F) * cap + i;
             double fl[L::F];
 #pragma unroll
-            for (int f = 0; f < L::F; f++) fl[f] = base[(long long)f * cap];
+            for (int f = 0; f < L::F; f++) fl[f] = (double)base[(long long)f * cap];
             const NRow row = tab[(int)fl[L::F_N]];
 #pragma unroll
             for (int q = 0; q < PRED_QCHUNK; q++) {
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(SUM_THREADS) k_sum_partials(const double *__re
 
 // state_entropy(p) = entropy(exp.(log_prior(p.stateprior))) (src/particle.jl:162, src/statepriors.jl:24-36): the
 // entropy of the NORMALISED prior over the candidate states of particle i
-template <int D>
-__device__ __forceinline__ double particle_state_entropy(const double *__restrict__ S, long long cap, long long i, int K,
+template <int D, typename R>
+__device__ __forceinline__ double particle_state_entropy(const R *__restrict__ S, long long cap, long long i, int K,
                                                          const PriorConst *__restrict__ pc, SpArrays sp, double t_obs)
 {
     using L = Layout<D>;
@@ -122,7 +122,7 @@ __device__ __forceinline__ double particle_state_entropy(const double *__restric
     }
     if (kind == SPK_NSTATE) {
         const double tot = pc->sp_total0 + t_obs;
-        for (int j = 0; j < K; j++) H -= xlogx((pc->sp_counts0[j] + S[((long long)j * L::F + L::F_N) * cap + i]) / tot);
+        for (int j = 0; j < K; j++) H -= xlogx((pc->sp_counts0[j] + (double)S[((long long)j * L::F + L::F_N) * cap + i]) / tot);
         return H;
     }
     if (kind == SPK_STICKY) {
@@ -136,7 +136,7 @@ __device__ __forceinline__ double particle_state_entropy(const double *__restric
     }
     const double tot = t_obs + pc->alpha;                            // CRP: N_j / (t + alpha), alpha / (t + alpha)
     H = -xlogx(pc->alpha / tot);
-    for (int j = 0; j < K; j++) H -= xlogx(S[((long long)j * L::F + L::F_N) * cap + i] / tot);
+    for (int j = 0; j < K; j++) H -= xlogx((double)S[((long long)j * L::F + L::F_N) * cap + i] / tot);
     return H;
 }
 
@@ -144,8 +144,8 @@ __device__ __forceinline__ double particle_state_entropy(const double *__restric
 //   [0] sum w   [1] sum w K   [2] sum w H(state prior)   [3 + k] sum of w over the block's particles with K = k
 // ncomponents_dist(ps) = fit(Categorical, ncomponents, weights) (src/filters.jl:36-37) is [3 + k] / [0];
 // mean(ncomponents, ps), state_entropy(ps) = mean(state_entropy, ps) (src/filters.jl:17-20) are [1] / [0], [2] / [0].
-template <int D>
-__global__ void __launch_bounds__(SUM_THREADS) k_pop_summary(const double *__restrict__ S, const double *__restrict__ logw,
+template <int D, typename R = double>
+__global__ void __launch_bounds__(SUM_THREADS) k_pop_summary(const R *__restrict__ S, const double *__restrict__ logw,
                                                              const int *__restrict__ Kc, long long cap, long long n, int slots,
                                                              const PriorConst *__restrict__ pc, SpArrays sp, double t_obs,
                                                              double *__restrict__ part)
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(SUM_THREADS) k_pop_summary(const double *__res
     const bool live = i < n;
     const int K = live ? min(Kc[i], slots - 1) : 0;
     const double w = live ? exp(logw[i]) : 0.0;
-    const double H = live ? particle_state_entropy<D>(S, cap, i, K, pc, sp, t_obs) : 0.0;
+    const double H = live ? particle_state_entropy<D, R>(S, cap, i, K, pc, sp, t_obs) : 0.0;
     double *rec = part + (long long)blockIdx.x * (3 + slots);
     double t = block_sum_double(w, s_red);
     if (threadIdx.x == 0) rec[0] = t;

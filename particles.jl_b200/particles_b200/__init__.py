@@ -176,7 +176,7 @@ class ParticleFilter:
     _kind = None
 
     def __init__(self, n, prior, stateprior, *, k_max=32, order=PF_ORDER_INDEX, history=-1, device=0, seed=0,
-                 rejuv=50.0, on_overflow="warn"):
+                 rejuv=50.0, on_overflow="warn", precision="f64"):
         if isinstance(prior, tuple):
             prior = NormalInverseChisq(*prior)                      # Component(params::NTuple), src/component.jl:8
         if not isinstance(stateprior, (ChineseRestaurantProcess, StickyCRP, ChangePoint, NStatePrior)):
@@ -190,7 +190,10 @@ class ParticleFilter:
         L = _lib.load()
         cfg = pf_config()
         cfg.filter_kind = self._kind
-        cfg.precision = 0
+        if precision not in ("f64", "f32"):
+            raise ValueError("precision must be 'f64' or 'f32'")
+        self.precision = precision
+        cfg.precision = _lib.PF_F32 if precision == "f32" else _lib.PF_F64      # storage type of the particle store
         cfg.n_particles = self.N
         cfg.k_max = self.k_max
         cfg.order = order
@@ -414,6 +417,7 @@ class ParticleFilter:
         self._h, self._L = h, L
         self.N, self.k_max, self.order, self.history, self.d = cfg.n_particles, cfg.k_max, cfg.order, cfg.history, cfg.d if cfg.prior_kind == PF_NIW else 1
         self.rejuvination_threshold = cfg.rejuv_threshold
+        self.precision = "f32" if cfg.precision == _lib.PF_F32 else "f64"
         self.on_overflow, self._overflow_seen = "warn", 0
         mu0, lam0, spc = np.empty(self.d), np.empty((self.d, self.d)), np.zeros(64)
         _lib.check(L.pf_get_prior(h, mu0.ctypes.data_as(_dp), lam0.ctypes.data_as(_dp), spc.ctypes.data_as(_dp)), h)

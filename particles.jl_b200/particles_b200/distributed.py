@@ -81,10 +81,10 @@ class LocalGroup:
 LocalComm = LocalGroup          # (name used by earlier tests)
 
 
-def _config(n, prior, stateprior, k_max, history, seed, keep, kind=PF_FEARNHEAD, rejuv=50.0):
+def _config(n, prior, stateprior, k_max, history, seed, keep, kind=PF_FEARNHEAD, rejuv=50.0, precision="f64"):
     from . import NormalInverseChisq, NormalInverseWishart
     cfg = pf_config()
-    cfg.filter_kind, cfg.precision, cfg.n_particles, cfg.k_max = kind, 0, int(n), int(k_max)
+    cfg.filter_kind, cfg.precision, cfg.n_particles, cfg.k_max = kind, (1 if precision == "f32" else 0), int(n), int(k_max)
     cfg.order, cfg.history = 0, int(history)
     cfg.alpha, cfg.rejuv_threshold, cfg.seed = stateprior.alpha, float(rejuv), seed
     if isinstance(prior, NormalInverseChisq):
@@ -109,13 +109,14 @@ class ShardedFearnheadParticles:
 
     _kind = PF_FEARNHEAD
 
-    def __init__(self, n, prior, stateprior, group, *, k_max=32, history=0, device=None, seed=0, on_overflow="warn", rejuv=50.0):
+    def __init__(self, n, prior, stateprior, group, *, k_max=32, history=0, device=None, seed=0, on_overflow="warn", rejuv=50.0,
+                 precision="f64"):
         self.group, self.N, self.k_max = group, int(n), int(k_max)
         self.on_overflow, self._overflow_seen = on_overflow, 0
         L = _lib.load()
         self.L = L
         self._keep = []
-        cfg = _config(n, prior, stateprior, k_max, history, seed, self._keep, self._kind, rejuv)
+        cfg = _config(n, prior, stateprior, k_max, history, seed, self._keep, self._kind, rejuv, precision)
         self.d = int(cfg.d)
         G = group.size
         if isinstance(group, LocalGroup):
