@@ -103,7 +103,16 @@ struct TileSum {           // survivor-scan record of one tile of SCAN_THREADS p
 //         bracket [lo, hi) (exact fixed-point mass below lo, count above hi, candidates in
 //         between appended densely), so the separate classify pass over V disappears; the
 //         block's sums are also the survivor scan's tile record (one block = one tile).
-#define EXP_CAND_CAP 1024          // MODE 2: candidates one block of 256 particles may stage
+// Block size of the full expansions (MODE 0 / 2).  The survivor scan's tile (SCAN_THREADS particles) is EXP_SUB such
+// blocks: a block leaves a SUB-tile record, k_tile_scan1 adds them up.  Smaller blocks shorten the tail in which a
+// block's finished warps wait for its slowest one (17 % of the stall samples at 256 threads), but every block ends with
+// ~15 atomics on the step's accumulators, and those serialise per address: measured at 2^24 particles the fused kernel
+// takes 3.83 ms with 256-thread blocks, 3.81 with 128, 5.50 with 64, 8.59 with 32 (profiles/r2/README.md).
+#ifndef EXP_THREADS
+#define EXP_THREADS 256
+#endif
+#define EXP_SUB (256 / EXP_THREADS)
+#define EXP_CAND_CAP (4 * EXP_THREADS)   // MODE 2: candidates one block may stage
 #define EXP_SAMPLE_THREADS 32      // MODE 1 runs one warp per block: at most 32 * PF_MAX_SLOTS sample values per block
 struct TileFuse {
     unsigned int cand_off, cand_cnt, n_plateau, pad;
@@ -142,7 +151,7 @@ struct InstArgs {
 // R: storage type of the particle store (double, or float under PF_F32: the arithmetic stays in double, every field
 // is rounded to R when it is stored, so the store traffic halves)
 template <int D, int MODE, bool INST = false, typename R = double>
-__global__ void __launch_bounds__(256, INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_MINBLOCKS) k_expand(const R *__restrict__ S, const double *__restrict__ logw,
+__global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_MINBLOCKS) * EXP_SUB) k_expand(const R *__restrict__ S, const double *__restrict__ logw,
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
@@ -559,7 +568,7 @@ __device__ __forceinline__ void thread_sums(const double *__restrict__ V, long l
     }
 }
 
-__global__ void __launch_bounds__(SUPER_TILES) k_tile_scan1(TileSum *__restrict__ tiles, const TileFuse *__restrict__ tfuse,
+__global__ void __launch_bounds__(SUPER_TILES) k_tile_scan1(TileSum *__restrict__ tiles, const TileSum *__restrict__ subs, const TileFuse *__restrict__ tfuse,
                                                            const double *__restrict__ list, const SelResult *__restrict__ res,
                                                            const SelScratch *__restrict__ sc, const long long *__restrict__ n_items_ptr,
                                                            const StepConst *__restrict__ scp, TileSum *__restrict__ supers, int mode,
@@ -577,23 +586,30 @@ __global__ void __launch_bounds__(SUPER_TILES) k_tile_scan1(TileSum *__restrict_
     u128 X = mk128(0, 0);
     unsigned int kept = 0;
     if (t < ntiles) {
-        X = tiles[t].X; kept = tiles[t].kept;
         if (tfuse && sc && sc->tiles_ok) {
-            // the fused expansion's record holds the tile's putatives outside the bracket: add its candidates
+            // the fused expansion left EXP_SUB sub-tile records holding the putatives outside the bracket: add them up
+            // and add each one's candidates
             const u64 thr = res->thr_bits;
             const int scale = res->scale;
-            const unsigned int off = tfuse[t].cand_off, n = tfuse[t].cand_cnt;
-            for (unsigned int k = 0; k < n; k++) {
-                const u64 b = (u64)__double_as_longlong(list[(long long)off + k]);
-                if (b >= thr) kept++;
-                else if (comb) X = add128(X, fx70(b, scale));
-            }
-            const unsigned int np = tfuse[t].n_plateau;
-            if (np) {
-                if (scp->plateau_bits >= thr) kept += np;
-                else if (comb) X = add128(X, mul128_64(fx70(scp->plateau_bits, scale), (u64)np));
+            for (int sb = 0; sb < EXP_SUB; sb++) {
+                const long long r = t * EXP_SUB + sb;
+                if (r * EXP_THREADS >= *n_items_ptr) break;
+                X = add128(X, subs[r].X); kept += subs[r].kept;
+                const unsigned int off = tfuse[r].cand_off, n = tfuse[r].cand_cnt;
+                for (unsigned int k = 0; k < n; k++) {
+                    const u64 b = (u64)__double_as_longlong(list[(long long)off + k]);
+                    if (b >= thr) kept++;
+                    else if (comb) X = add128(X, fx70(b, scale));
+                }
+                const unsigned int np = tfuse[r].n_plateau;
+                if (np) {
+                    if (scp->plateau_bits >= thr) kept += np;
+                    else if (comb) X = add128(X, mul128_64(fx70(scp->plateau_bits, scale), (u64)np));
+                }
             }
             if (!comb) X = mk128(0, 0);
+        } else {
+            X = tiles[t].X; kept = tiles[t].kept;
         }
     }
     u128 totX;

@@ -42,7 +42,8 @@ struct pf_filter_s {
     unsigned char *surv_slot = nullptr;
     TileSum *tiles = nullptr;
     TileSum *supers = nullptr;            // totals of SUPER_TILES consecutive tile records (level 2 of the survivor scan)
-    TileFuse *tfuse = nullptr;
+    TileFuse *tfuse = nullptr;            // per expansion block (EXP_SUB per tile)
+    TileSum *tsub = nullptr;              // sub-tile records of the fused expansion (EXP_SUB per tile)
     ScanRec srec = ScanRec{nullptr, nullptr};   // per-particle scan records of the fused expansion (PF_SCAN_REC)
     long long fuse_stride = 1;
     bool fused = true;                    // single-GPU index-order Fearnhead: classify inside the expansion
@@ -233,7 +234,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->V_alt, h->stc_alt, h->cnt, h->surv_parent,
-                    h->surv_slot, h->tiles, h->supers, h->tfuse, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
+                    h->surv_slot, h->tiles, h->supers, h->tfuse, h->tsub, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_tiles, h->clp, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
                     h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
                     h->sp[1].Nsame, h->sp[1].last};
@@ -350,7 +351,8 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     }
     CT(dmalloc(&h->tiles, ntiles));
     CT(dmalloc(&h->supers, ntiles / SUPER_TILES + 2));
-    CT(dmalloc(&h->tfuse, ntiles));
+    CT(dmalloc(&h->tfuse, ntiles * EXP_SUB));
+    CT(dmalloc(&h->tsub, ntiles * EXP_SUB));
     // per-particle scan records of the fused expansion (24 bytes per particle; PF_NO_SCAN_REC=1 disables them)
     if (cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_INDEX && !getenv("PF_NO_SCAN_REC")) {
         CT(dmalloc(&h->srec.x, (size_t)h->cap));
@@ -597,8 +599,8 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         }
         {
             LaunchTimer lt(h, KC_EXPAND);
-            k_expand<D, 2, false, R><<<grid_for(ub, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                       h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
+            k_expand<D, 2, false, R><<<grid_for(ub, EXP_THREADS), EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tsub, h->tfuse, h->srec);
         }
         {
             LaunchTimer lt(h, KC_SELECT, 2 * (h->retries + 1));
@@ -618,7 +620,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
                 k_expand_sp<D, R><<<grid_for(ub, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc, h->stc,
                                                                           h->st, h->V, h->cnt, h->sc, h->sp[cur], h->steps);
             else
-                k_expand<D, 0, false, R><<<grid_for(ub, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                k_expand<D, 0, false, R><<<grid_for(ub, EXP_THREADS), EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                            h->stc, h->st, h->V, h->cnt, h->sc, 1, nullptr, nullptr, nullptr);
         }
         {
@@ -643,14 +645,14 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         LaunchTimer lt(h, KC_SCAN, 9);
         const int gflat = grid_for(n_pad, SCAN_THREADS), gidx = grid_for(ub, SCAN_THREADS);
         k_tile_sums<<<std::min(gflat, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, 1, h->sc, nullptr);
-        k_tile_scan1<<<grid_for(gflat, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, nullptr, nullptr, h->res, nullptr, &h->st->M, h->stc, h->supers, 1, h->sc);
+        k_tile_scan1<<<grid_for(gflat, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, nullptr, nullptr, nullptr, h->res, nullptr, &h->st->M, h->stc, h->supers, 1, h->sc);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->M, h->st, 1, nullptr, 0, h->sc, 1);
         k_scan_apply<<<gflat, SCAN_THREADS, 0, h->stream>>>((const double *)h->keys, nullptr, n_pad, h->res, &h->st->M, h->tiles, h->supers,
                                                              h->pick_pos, h->surv_slot, 1, nullptr, h->sc, cap);
         k_sorted_finalize<<<grid_for(ub_next, 256), 256, 0, h->stream>>>(h->st, h->res, h->pick_pos, h->vals, slots, h->surv_parent,
                                                                            h->surv_slot, h->sc);
         k_tile_sums<<<std::min(gidx, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 2, h->sc, nullptr);
-        k_tile_scan1<<<grid_for(gidx, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, nullptr, nullptr, h->res, nullptr, &h->st->n_live, h->stc, h->supers, 2, h->sc);
+        k_tile_scan1<<<grid_for(gidx, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, nullptr, nullptr, nullptr, h->res, nullptr, &h->st->n_live, h->stc, h->supers, 2, h->sc);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 2, nullptr, 0, h->sc, 1);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
                                                             h->surv_slot, 2, nullptr, h->sc, cap);
@@ -658,7 +660,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         LaunchTimer lt(h, KC_SCAN, 4);
         const int gidx = grid_for(ub, SCAN_THREADS);
         k_tile_sums<<<std::min(gidx, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, fused ? h->sc : nullptr);
-        k_tile_scan1<<<grid_for(gidx, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, fused ? h->tfuse : nullptr, h->cand, h->res, h->sc, &h->st->n_live, h->stc,
+        k_tile_scan1<<<grid_for(gidx, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, h->tsub, fused ? h->tfuse : nullptr, h->cand, h->res, h->sc, &h->st->n_live, h->stc,
                                                                                      h->supers, 0, h->sc);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, nullptr, 0, h->sc, 1);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
@@ -696,8 +698,8 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         }
         {
             LaunchTimer lt(h, KC_INST_EXPAND);
-            k_expand<D, 2, true, R><<<grid_for(ub_next, 256), 256, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                       h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec, ia);
+            k_expand<D, 2, true, R><<<grid_for(ub_next, EXP_THREADS), EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, h->tsub, h->tfuse, h->srec, ia);
         }
         CUDA_TRY(cudaGetLastError());
         std::swap(h->V, h->V_alt);
@@ -1571,7 +1573,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
         rc = launch_classic_search(h, sel_args(h, Vsel, nullptr, M, &st->n_live, &st->M, &st->vmax_bits, N, dU, cand, cand_cap, sc, res));
         if (rc != PF_OK) { g_create_error = h->err; goto done; }
         k_tile_sums<<<std::min(grid_for(M, SCAN_THREADS), h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, 0, sc, nullptr);
-        k_tile_scan1<<<grid_for(ntiles, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(tiles, nullptr, nullptr, res, nullptr, &st->n_live, nullptr, supers, 0, sc);
+        k_tile_scan1<<<grid_for(ntiles, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(tiles, nullptr, nullptr, nullptr, res, nullptr, &st->n_live, nullptr, supers, 0, sc);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(supers, res, &st->n_live, st, 0, nullptr, 0, sc, 1);
         k_scan_apply<<<grid_for(M, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(Vsel, nullptr, M, res, &st->n_live, tiles, supers, sp, ss, 0, nullptr, sc, M);
         ST(cudaGetLastError());
@@ -1790,8 +1792,8 @@ static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int searc
     if (search_stage & SEL_ST_PUB) {
         if (!retry) {
             LaunchTimer lt(h, KC_EXPAND);
-            k_expand<D, 2, false, R><<<grid_for(cap, 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
-                                                                        h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tiles, h->tfuse, h->srec);
+            k_expand<D, 2, false, R><<<grid_for(cap, EXP_THREADS), EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                        h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tsub, h->tfuse, h->srec);
         }
         LaunchTimer lt(h, KC_SELECT);
         k_sel_classify<<<h->sel_grid, SEL_THREADS, 0, h->stream>>>(a);
@@ -1809,7 +1811,7 @@ static int32_t mg_stage_c(pf_handle h)
     const unsigned long long seq = (unsigned long long)h->steps + 1;
     LaunchTimer lt(h, KC_SCAN, 3);
     k_tile_sums<<<std::min(g, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, h->sc);
-    k_tile_scan1<<<grid_for(g, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc, h->supers, 0, h->sc);
+    k_tile_scan1<<<grid_for(g, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, h->tsub, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc, h->supers, 0, h->sc);
     k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, h->xch, seq, h->sc, 1);
     return PF_OK;
 }
