@@ -9,7 +9,7 @@
  * The reference is pure Julia and has no FFI of its own; the boundary it offers is its
  * generic-function surface.  Each entry point below names the reference method it stands
  * behind (file:line in the reference repository).  The Julia shim that binds these with
- * `ccall` is particles.jl_b200/julia/particles_b200.jl; the Python mirror used by the tests is
+ * `ccall` is particles.jl_b200/julia/device.jl; the Python mirror used by the tests is
  * particles.jl_b200/particles_b200/.
  *
  * Conventions

@@ -346,7 +346,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
         ntiles = (n_pad + SCAN_THREADS - 1) / SCAN_THREADS;
         CT(dmalloc(&h->keys, (size_t)n_pad)); CT(dmalloc(&h->keys2, (size_t)n_pad));
         CT(dmalloc(&h->vals, (size_t)n_pad)); CT(dmalloc(&h->vals2, (size_t)n_pad));
-        CT(dmalloc(&h->hist, (size_t)256 * ((n_pad + RS_TILE - 1) / RS_TILE) + 256));
+        CT(dmalloc(&h->hist, (size_t)(256 + 1) * ((n_pad + RS_TILE - 1) / RS_TILE) + 1024));
         CT(dmalloc(&h->pick_pos, (size_t)cap));
     }
     CT(dmalloc(&h->tiles, ntiles));
@@ -636,7 +636,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         const int slots = h->k_max + 1;
         const long long n_pad = ub * slots;
         {
-            LaunchTimer lt(h, KC_SORT, 1 + 1 + 3 * 8);
+            LaunchTimer lt(h, KC_SORT, 1 + 1 + 5 * 8);
             k_flat_keys<<<grid_for(n_pad, 256), 256, 0, h->stream>>>(h->V, h->cnt, cap, h->st, slots, n_pad, h->keys2);
             if (radix_sort_pairs(h->stream, h->keys2, h->keys, h->keys2, h->vals, h->vals2, h->hist, n_pad, nullptr))
                 return set_error(h, PF_ERR_CUDA, "radix sort launch failed");
@@ -1563,7 +1563,7 @@ extern "C" int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t
             ST(dmalloc(&keys, (size_t)M)); ST(dmalloc(&keys2, (size_t)M));
             ST(dmalloc(&vals, (size_t)M)); ST(dmalloc(&vals2, (size_t)M));
             int nblk = grid_for(M, RS_TILE);
-            ST(dmalloc(&hist, (size_t)256 * nblk + 256));
+            ST(dmalloc(&hist, (size_t)(256 + 1) * nblk + 1024));
             rc = radix_sort_pairs(h->stream, (const u64 *)dW, keys, keys2, vals, vals2, hist, M, &h->launches);
             if (rc != PF_OK) { rc = set_error(nullptr, PF_ERR_CUDA, "pf_select: radix sort failed"); goto done; }
             Vsel = (const double *)keys;           // sorted weights (bit patterns are the doubles)

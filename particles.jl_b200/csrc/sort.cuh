@@ -47,20 +47,62 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64 *__restrict__ 
     }
 }
 
-// exclusive scan of hist[256 * nblk] in place (digit-major), one block
-__global__ void __launch_bounds__(1024) k_rs_scan(unsigned int *hist, long long n)
+// exclusive scan of hist[256 * nblk] in place (digit-major): block sums, one block over the block sums, apply
+#define RS_SCAN_TILE 4096          // entries per block (1024 threads x 4)
+__device__ __forceinline__ unsigned int rs_block_excl_scan(unsigned int v, unsigned int *s_w /* >= 33 */, unsigned int *total)
 {
-    __shared__ unsigned int s_part[1024];
-    const long long per = (n + 1023) / 1024;
-    const long long b = (long long)threadIdx.x * per, e = b + per < n ? b + per : n;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = s_w[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
+        s_w[lane] = wi - w;
+        if (lane == 31) s_w[32] = wi;
+    }
+    __syncthreads();
+    const unsigned int r = s_w[wid] + inc - v;
+    *total = s_w[32];
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(1024) k_rs_scan_sums(const unsigned int *__restrict__ hist, long long n, unsigned int *__restrict__ part)
+{
+    __shared__ unsigned int s_w[33];
+    const long long b = (long long)blockIdx.x * RS_SCAN_TILE;
     unsigned int loc = 0;
-    for (long long i = b; i < e; i++) loc += hist[i];
-    s_part[threadIdx.x] = loc;
-    __syncthreads();
-    if (threadIdx.x == 0) { unsigned int run = 0; for (int t = 0; t < 1024; t++) { unsigned int x = s_part[t]; s_part[t] = run; run += x; } }
-    __syncthreads();
-    unsigned int run = s_part[threadIdx.x];
-    for (long long i = b; i < e; i++) { unsigned int x = hist[i]; hist[i] = run; run += x; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const long long i = b + k * 1024 + threadIdx.x; if (i < n) loc += hist[i]; }
+    unsigned int tot;
+    rs_block_excl_scan(loc, s_w, &tot);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) k_rs_scan_top(unsigned int *part, long long nb)
+{
+    __shared__ unsigned int s_w[33];
+    const long long per = (nb + 1023) / 1024;
+    const long long b = (long long)threadIdx.x * per, e = b + per < nb ? b + per : nb;
+    unsigned int loc = 0;
+    for (long long i = b; i < e; i++) loc += part[i];
+    unsigned int tot;
+    unsigned int run = rs_block_excl_scan(loc, s_w, &tot);
+    for (long long i = b; i < e; i++) { const unsigned int x = part[i]; part[i] = run; run += x; }
+}
+__global__ void __launch_bounds__(1024) k_rs_scan_apply(unsigned int *__restrict__ hist, long long n, const unsigned int *__restrict__ part)
+{
+    __shared__ unsigned int s_w[33];
+    const long long b = (long long)blockIdx.x * RS_SCAN_TILE + (long long)threadIdx.x * 4;
+    unsigned int v[4], loc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = b + k < n ? hist[b + k] : 0u; loc += v[k]; }
+    unsigned int tot;
+    unsigned int run = part[blockIdx.x] + rs_block_excl_scan(loc, s_w, &tot);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (b + k < n) hist[b + k] = run; run += v[k]; }
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict__ keys, const unsigned int *__restrict__ vals,
@@ -95,7 +137,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict
     }
 }
 
-// sorts M pairs; result in (keys, vals).  hist needs 256 * ceil(M / RS_TILE) entries.
+// sorts M pairs; result in (keys, vals).  hist needs 256 * nblk + nblk / 16 + 1024 entries, nblk = ceil(M / RS_TILE).
 static int radix_sort_pairs(cudaStream_t stream, const u64 *in, u64 *keys, u64 *keys2, unsigned int *vals, unsigned int *vals2,
                             unsigned int *hist, long long M, long long *launches)
 {
@@ -106,11 +148,17 @@ static int radix_sort_pairs(cudaStream_t stream, const u64 *in, u64 *keys, u64 *
     for (int pass = 0; pass < 8; pass++) {
         const int shift = 8 * pass;
         k_rs_hist<<<nblk, RS_THREADS, 0, stream>>>(ka, M, shift, nblk, hist);
-        k_rs_scan<<<1, 1024, 0, stream>>>(hist, 256ll * nblk);
+        {
+            const long long nh = 256ll * nblk, nb = (nh + RS_SCAN_TILE - 1) / RS_SCAN_TILE;
+            unsigned int *part = hist + nh;                    // (the caller allocates 256 * nblk + nblk / 16 + 1024 entries)
+            k_rs_scan_sums<<<(unsigned)nb, 1024, 0, stream>>>(hist, nh, part);
+            k_rs_scan_top<<<1, 1024, 0, stream>>>(part, nb);
+            k_rs_scan_apply<<<(unsigned)nb, 1024, 0, stream>>>(hist, nh, part);
+        }
         k_rs_scatter<<<nblk, RS_THREADS, 0, stream>>>(ka, va, kb, vb, M, shift, nblk, hist);
         u64 *tk = ka; ka = kb; kb = tk;
         unsigned int *tv = va; va = vb; vb = tv;
     }
-    if (launches) *launches += 1 + 3 * 8;
+    if (launches) *launches += 1 + 5 * 8;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -1,7 +1,7 @@
 """Host-side mirror of the Particles.jl API for the accelerated path.
 
 Julia is not available in this image, so the reference-facing host code is this Python
-module; the Julia shim with the same surface is particles.jl_b200/julia/Particles.jl.
+module; the Julia shim with the same surface is particles.jl_b200/julia/device.jl.
 Names and argument meaning follow the reference (src/Particles.jl:23-56); Julia's `fit!` /
 `filter!` are spelled `fit_` / `filter_` here.  All arithmetic happens in
 libparticles_b200.so on the GPU; nothing in this module computes the filter on the CPU.
