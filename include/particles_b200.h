@@ -149,6 +149,9 @@ int32_t pf_get_stateprior(pf_handle h, int64_t i, double *N, double *Nsame, int3
 /* assignments(ps), src/filters.jl:26-34: out[T x n] column-major (column = particle),
  * 0-based component labels.  Needs history >= steps. */
 int32_t pf_get_assignments(pf_handle h, int32_t *out);
+/* assignments(p) of ONE particle (src/particle.jl:25-32): out[T], 0-based.  Stays cheap when the T x n matrix of a long
+ * run over a large population is too big to bring to the host (2^24 particles x 10^4 observations = 1.7e11 labels). */
+int32_t pf_get_particle_assignments(pf_handle h, int64_t i, int32_t *out);
 int32_t pf_get_last_step(pf_handle h, pf_step_stats *out);
 
 /* ---- filter-level summaries, evaluated on the device-resident population ------------------ */

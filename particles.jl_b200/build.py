@@ -24,6 +24,8 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "--fmad=false" if os.environ.get("PF_NO_FMA") else "--fmad=true",
            "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC, "-lcudart"]
+    if os.environ.get("PF_CHECKED"):
+        cmd.insert(1, "-DPF_CHECKED")          # device-side index assertions (common.cuh)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd, cwd=HERE)

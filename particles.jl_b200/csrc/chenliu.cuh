@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) k_cl_propagate(R *S0, R *S1, const double
         int pick = 0;
         double cw = V[i];
         while (cw < t && pick < C - 1) { pick++; cw += V[(long long)pick * cap + i]; }
+        PF_ASSERT(pick >= 0 && pick <= K && pick < k_max && C >= 1);
         // instantiate in place (src/particle.jl:134-149)
         R *dst = S + ((long long)pick * L::F) * cap + i;
         if (pick == K) {
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(256) k_cl_finish(R *S0, R *S1, int *Kc0, int *
         if (lt128(thr, c)) hi = mid; else lo = mid + 1;
     }
     const long long a = lo;
+    PF_ASSERT(r >= 0 && r < nranks && n_r > 0 && a >= 0 && a < n_r);
     const R *S = static_cast<const R *>(peers->S[cur][r]);
     const int K = __ldcg(peers->Kc[cur][r] + a);
     Kc2[i] = K;

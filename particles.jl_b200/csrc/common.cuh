@@ -279,6 +279,23 @@ __host__ __device__ __forceinline__ u128 acc_value(const volatile acc128 *a)
     return r;
 }
 
+// Checked build (-DPF_CHECKED, `PF_CHECKED=1 python build.py`): index invariants of the gathers / scatters are
+// asserted on the device; a violation prints its site and traps (every later CUDA call then fails, so the tests fail
+// loudly).  compute-sanitizer is closed on the GPU pool this was developed on; the parity suite run against the checked
+// build (profiles/r2/checked_build.log) is the substitute.
+#ifdef PF_CHECKED
+#include <cstdio>
+#define PF_ASSERT(cond)                                                                                          \
+    do {                                                                                                         \
+        if (!(cond)) {                                                                                           \
+            printf("PF_ASSERT failed: %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                                            \
+        }                                                                                                        \
+    } while (0)
+#else
+#define PF_ASSERT(cond) ((void)0)
+#endif
+
 #define CUDA_TRY(x)                                                                      \
     do {                                                                                 \
         cudaError_t e_ = (x);                                                            \

@@ -125,6 +125,7 @@ struct TileFuse {
 struct ScanRec {
     ulonglong2 *x;
     unsigned long long *m;
+    unsigned long long *h;     // mask of the slots ABOVE the bracket (kept whatever the threshold turns out to be)
 };
 
 #ifndef PF_EXPAND_MINBLOCKS
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
                                                 double *__restrict__ V, unsigned char *__restrict__ cnt,
                                                 SelScratch *sc, long long stride, double *__restrict__ list,
                                                 TileSum *__restrict__ tiles, TileFuse *__restrict__ tfuse,
-                                                ScanRec rec = ScanRec{nullptr, nullptr}, InstArgs ia = InstArgs{})
+                                                ScanRec rec = ScanRec{nullptr, nullptr, nullptr}, InstArgs ia = InstArgs{})
 {
     using L = Layout<D>;
     if (sc && sc->halt) return;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
     long long myM = 0, myOvf = 0;
     u128 B_lo = mk128(0, 0), Tot = mk128(0, 0);
     unsigned int kept_hi = 0, n_plat = 0;
-    unsigned long long in_mask = 0;
+    unsigned long long in_mask = 0, hi_mask = 0;
     const u64 plateau = scp->plateau_bits;
     // what happens to one putative weight
     auto emit = [&](int j, double v) {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
         V[(long long)j * cap + i] = v;
         if (MODE == 2 && fused) {
             if (b >= hi) {
-                kept_hi++;
+                hi_mask |= 1ull << j;
                 Tot = add128(Tot, fx128(b, tscale));              // < 2^99 each by the 28-binade guard of the search
             } else if (b < lo) {
                 B_lo = add128(B_lo, fx70(b, scale));
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
             const unsigned char sl = ia.surv_slot[i];
             jsel = sl & 0x7F;
             K = Kc[par];
+            PF_ASSERT((long long)par < cap && K >= 0 && K <= k_max && jsel <= K && jsel < k_max && i < cap);
             const double v = ia.V_prev[(long long)jsel * cap + par];
             lw0 = (sl & 0x80) ? scp->prev_lw_resamp : (log(v) - scp->prev_log_total);      // src/fearnhead.jl:172-179
             src = par;
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
             }
         } else {
             K = Kc[i]; lw0 = logw[i];
+            PF_ASSERT(K >= 0 && K <= k_max);
         }
         // software pipeline: the fields of slot j+1 are in flight while slot j is evaluated
         double fcur[L::F], fnxt[L::F];
@@ -291,9 +294,11 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
         else myOvf = 1;
         if (MODE != 1) cnt[i] = (unsigned char)c;
         myM = c;
+        kept_hi = (unsigned int)__popcll(hi_mask);
         if (MODE == 2 && fused && rec.x) {
             rec.x[i] = make_ulonglong2(B_lo.lo, B_lo.hi | ((u64)kept_hi << 56));
             rec.m[i] = in_mask;
+            rec.h[i] = hi_mask;
         }
     }
     // ---- block epilogue
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
             unsigned int n = s_ncand;
             if (n > CAND_CAP) { n = CAND_CAP; if (MODE == 2) sc->fuse_overflow = 1; }
             s_goff = n ? (unsigned int)atomicAdd((unsigned long long *)&sc->list_n, (unsigned long long)n) : 0u;
+            PF_ASSERT((long long)s_goff + n <= (long long)cap * (k_max + 1));
             s_ncand = n;
         }
     }
@@ -596,6 +602,7 @@ __global__ void __launch_bounds__(SUPER_TILES) k_tile_scan1(TileSum *__restrict_
                 if (r * EXP_THREADS >= *n_items_ptr) break;
                 X = add128(X, subs[r].X); kept += subs[r].kept;
                 const unsigned int off = tfuse[r].cand_off, n = tfuse[r].cand_cnt;
+                PF_ASSERT((long long)off + n <= sc->list_n);
                 for (unsigned int k = 0; k < n; k++) {
                     const u64 b = (u64)__double_as_longlong(list[(long long)off + k]);
                     if (b >= thr) kept++;
@@ -728,107 +735,19 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelR
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
-                                                             long long cap, const SelResult *__restrict__ res,
-                                                             const long long *__restrict__ n_items_ptr,
-                                                             const TileSum *__restrict__ tiles, const TileSum *__restrict__ supers,
-                                                             unsigned int *__restrict__ surv_parent,
-                                                             unsigned char *__restrict__ surv_slot, int mode,
-                                                             const RankOff *__restrict__ ro, const SelScratch *guard,
-                                                             long long surv_cap, ScanRec rec = ScanRec{nullptr, nullptr},
-                                                             const SelScratch *recsc = nullptr)
+// The walk over one particle's putatives (one lane per particle; all 32 lanes of the warp call it, idle lanes with
+// c = 0): kept ones are listed; for the low ones the question "has the running mass passed the next tooth?" is
+// Q - S_particle < (sum of the q_j so far).  It is asked in double precision first -- the items' values scaled by
+// 2^scale, summed with DADD, against D = (double)(Q - S_particle) -- and the answer is taken only when it clears the
+// rounding error by a wide margin (the integer q_j = floor(v_j 2^scale) differ from the scaled doubles by < 1 each, the
+// doubles by 2^-53 relative); a lane that comes closer than that (or meets a subnormal weight) redoes its particle in
+// exact 128-bit arithmetic.  Decisions are those of the exact walk; the common case costs one DADD per putative instead
+// of a 128-bit conversion, add and compare.  The putatives are fetched eight at a time (independent loads in flight).
+__device__ __forceinline__ void walk_particle(const double *__restrict__ V, long long cap, long long i, int c, u64 thr, int scale,
+                                              int mode, u128 S, long long kcount, u64 t, u128 Q, unsigned int R, bool tooth_inside,
+                                              u128 Tq, unsigned int Tr, unsigned int n32, unsigned int *__restrict__ surv_parent,
+                                              unsigned char *__restrict__ surv_slot, long long surv_cap)
 {
-    if (guard && (guard->phase != 4 || guard->halt)) return;
-    if (scan_mode_skips(mode, res)) return;
-    __shared__ u128 s_warp[33];
-    __shared__ unsigned int s_wc[33];
-    const long long n_items = *n_items_ptr;
-    const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
-    if (blockIdx.x >= ntiles) return;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long i = (long long)blockIdx.x * SCAN_THREADS + tid;
-    const u64 thr = res->thr_bits;
-    const int scale = res->scale;
-    const u64 n = (u64)res->n;
-    const u128 T = res->T, U = res->Uoff;
-    const bool comb = n > 0 && !isz128(T);
-    const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
-    __shared__ u128 s_S0, s_Q0;
-    __shared__ unsigned int s_R0;
-    __shared__ u64 s_t0;
-    __shared__ long long s_k0;
-    __shared__ double s_inv;
-    if (tid == 0) {
-        u128 S0 = add128(tiles[blockIdx.x].X, supers[blockIdx.x / SUPER_TILES].X);      // prefix within the supertile + prefix of the supertiles
-        long long k0 = (long long)tiles[blockIdx.x].kept + (long long)supers[blockIdx.x / SUPER_TILES].kept;
-        if (ro) { S0 = add128(S0, ro->S_off); k0 += ro->kept_off - ro->g_first; }   // positions relative to this rank's first survivor
-        s_S0 = S0; s_k0 = k0;
-        if (comb) {
-            const ToothBase b = tooth_base(S0, n, U, T);
-            s_Q0 = b.Q0; s_R0 = b.R0; s_t0 = b.t0; s_inv = b.inv;
-        }
-    }
-    u128 myX; unsigned int myKept;
-    if (rec.x && recsc->tiles_ok) {
-        // the fused expansion left (mass below the bracket, in-bracket slots, count above the bracket):
-        // only the in-bracket slots (~0.5 % of all putatives) are read again
-        myX = mk128(0, 0); myKept = 0;
-        if (c) {
-            const ulonglong2 x = rec.x[i];
-            unsigned long long m = rec.m[i];
-            myKept = (unsigned int)(x.y >> 56);
-            if (comb) myX = mk128(x.x, x.y & 0x00FFFFFFFFFFFFFFull);
-            while (m) {
-                const int j = __ffsll((long long)m) - 1; m &= m - 1;
-                const u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
-                if (bits >= thr) myKept++;
-                else if (comb) myX = add128(myX, fx70(bits, scale));
-            }
-        }
-    } else {
-        thread_sums(V, cap, i, c, thr, scale, comb, myX, myKept);
-    }
-    u128 totX;
-    u128 exX = block_excl_scan128(myX, s_warp, &totX);
-    unsigned int incK = myKept;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, incK, d); if (lane >= d) incK += o; }
-    if (lane == 31) s_wc[wid] = incK;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned int w = lane < (SCAN_THREADS / 32) ? s_wc[lane] : 0, wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
-        s_wc[lane] = wi - w;
-    }
-    __syncthreads();
-    const unsigned int exK = s_wc[wid] + incK - myKept;
-    // running low-partition mass S (fixed point) and the next tooth k: tooth k is passed by S
-    // <=> Uoff + k T < n S <=> floor((Uoff + k T) / n) < S; (Q, R) = divmod(Uoff + k T, n) steps
-    // by (Tq, Tr) = divmod(T, n) from tooth to tooth.  The tile's first tooth (t0, Q0, R0) is
-    // found once per block (the one 128-bit division); a thread reaches its own tooth
-    // t0 + k with Q = Q0 + k Tq + floor((R0 + k Tr) / n), k from an FP estimate corrected exactly.
-    u128 S = add128(s_S0, exX);
-    long long kcount = s_k0 + exK;
-    u64 t = 0;
-    u128 Q = mk128(0, 0);
-    unsigned int R = 0;
-    const unsigned int n32 = (unsigned int)n, Tr = res->Tr;
-    const u128 Tq = res->Tq;
-    bool tooth_inside = false;
-    if (comb) {
-        t = s_t0 + tooth_seek(s_Q0, s_R0, s_inv, S, Tq, Tr, n32, Q, R);
-        tooth_inside = lt128(Q, add128(S, myX));
-    }
-    if (!__any_sync(0xffffffffu, tooth_inside) && (mode == 1 || !__any_sync(0xffffffffu, myKept != 0))) return;      // nothing to list in this warp
-    // The walk over the particle's putatives: kept ones are listed; for the low ones the question "has the running
-    // mass passed the next tooth?" is Q - S_particle < (sum of the q_j so far).  It is asked in double precision
-    // first -- the items' values scaled by 2^scale, summed with DADD, against D = (double)(Q - S_particle) -- and the
-    // answer is taken only when it clears the rounding error by a wide margin (the integer q_j = floor(v_j 2^scale)
-    // differ from the scaled doubles by < 1 each, the doubles by 2^-53 relative); a lane that comes closer than
-    // that (or meets a subnormal weight) redoes its particle in exact 128-bit arithmetic.  Decisions are those of
-    // the exact walk; the common case costs one DADD per putative instead of a 128-bit conversion, add and compare.
-    // The putatives are fetched eight at a time (independent loads in flight: the pass streams V from HBM once).
     const long long kcount0 = kcount;
     const u64 t_first = t;
     const u128 Q_first = Q; const unsigned int R_first = R;
@@ -852,6 +771,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                 if (bits >= thr) {
                     if (mode != 1) {
                         long long pos = kcount + (long long)t;
+                        PF_ASSERT(pos >= 0 && pos < surv_cap);
                         if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
                     }
                     kcount++;
@@ -864,6 +784,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
                         const double tol = 64.0 + (cum + Dd) * 2.8421709430404007e-14;   // 2^-45 relative + the floors
                         if (diff > tol) {
                             long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
+                            PF_ASSERT(pos >= 0 && pos < surv_cap);
                             if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)(j | 0x80); }
                             t++;
                             tooth_step(Q, R, Tq, Tr, n32);
@@ -901,6 +822,149 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__res
     }
 }
 
+// a particle that has a comb tooth inside its low mass, parked for the compacted walk
+struct __align__(16) WalkItem {
+    u128 S, Q;
+    long long kcount;
+    u64 t;
+    unsigned int R;
+    int tid, c, pad;
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
+                                                             long long cap, const SelResult *__restrict__ res,
+                                                             const long long *__restrict__ n_items_ptr,
+                                                             const TileSum *__restrict__ tiles, const TileSum *__restrict__ supers,
+                                                             unsigned int *__restrict__ surv_parent,
+                                                             unsigned char *__restrict__ surv_slot, int mode,
+                                                             const RankOff *__restrict__ ro, const SelScratch *guard,
+                                                             long long surv_cap, ScanRec rec = ScanRec{nullptr, nullptr, nullptr},
+                                                             const SelScratch *recsc = nullptr)
+{
+    if (guard && (guard->phase != 4 || guard->halt)) return;
+    if (scan_mode_skips(mode, res)) return;
+    __shared__ u128 s_warp[33];
+    __shared__ unsigned int s_wc[33];
+    const long long n_items = *n_items_ptr;
+    const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
+    if (blockIdx.x >= ntiles) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long i = (long long)blockIdx.x * SCAN_THREADS + tid;
+    const u64 thr = res->thr_bits;
+    const int scale = res->scale;
+    const u64 n = (u64)res->n;
+    const u128 T = res->T, U = res->Uoff;
+    const bool comb = n > 0 && !isz128(T);
+    const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
+    __shared__ u128 s_S0, s_Q0;
+    __shared__ unsigned int s_R0;
+    __shared__ u64 s_t0;
+    __shared__ long long s_k0;
+    __shared__ double s_inv;
+    __shared__ unsigned int s_nq;
+    if (tid == 0) {
+        u128 S0 = add128(tiles[blockIdx.x].X, supers[blockIdx.x / SUPER_TILES].X);      // prefix within the supertile + prefix of the supertiles
+        long long k0 = (long long)tiles[blockIdx.x].kept + (long long)supers[blockIdx.x / SUPER_TILES].kept;
+        if (ro) { S0 = add128(S0, ro->S_off); k0 += ro->kept_off - ro->g_first; }   // positions relative to this rank's first survivor
+        s_S0 = S0; s_k0 = k0; s_nq = 0;
+        if (comb) {
+            const ToothBase b = tooth_base(S0, n, U, T);
+            s_Q0 = b.Q0; s_R0 = b.R0; s_t0 = b.t0; s_inv = b.inv;
+        }
+    }
+    // the fused expansion left, per particle: mass below the bracket, the slots inside the bracket (the only ones whose
+    // side of the threshold was open: ~0.5 % of the putatives) and the slots above it
+    const bool use_rec = rec.x && recsc->tiles_ok;
+    u128 myX; unsigned int myKept;
+    unsigned long long in_mask = 0, hi_mask = 0;
+    if (use_rec) {
+        myX = mk128(0, 0); myKept = 0;
+        if (c) {
+            const ulonglong2 x = rec.x[i];
+            in_mask = rec.m[i]; hi_mask = rec.h[i];
+            myKept = (unsigned int)(x.y >> 56);
+            if (comb) myX = mk128(x.x, x.y & 0x00FFFFFFFFFFFFFFull);
+            unsigned long long m = in_mask, kept_in = 0;
+            while (m) {
+                const int j = __ffsll((long long)m) - 1; m &= m - 1;
+                const u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
+                if (bits >= thr) { myKept++; kept_in |= 1ull << j; }
+                else if (comb) myX = add128(myX, fx70(bits, scale));
+            }
+            hi_mask |= kept_in;                    // from here: the particle's kept slots
+        }
+    } else {
+        thread_sums(V, cap, i, c, thr, scale, comb, myX, myKept);
+    }
+    u128 totX;
+    u128 exX = block_excl_scan128(myX, s_warp, &totX);
+    unsigned int incK = myKept;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, incK, d); if (lane >= d) incK += o; }
+    if (lane == 31) s_wc[wid] = incK;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = lane < (SCAN_THREADS / 32) ? s_wc[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
+        s_wc[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned int exK = s_wc[wid] + incK - myKept;
+    // running low-partition mass S (fixed point) and the next tooth k: tooth k is passed by S
+    // <=> Uoff + k T < n S <=> floor((Uoff + k T) / n) < S; (Q, R) = divmod(Uoff + k T, n) steps
+    // by (Tq, Tr) = divmod(T, n) from tooth to tooth.  The tile's first tooth (t0, Q0, R0) is
+    // found once per block (the one 128-bit division); a thread reaches its own tooth
+    // t0 + k with Q = Q0 + k Tq + floor((R0 + k Tr) / n), k from an FP estimate corrected exactly.
+    const u128 S = add128(s_S0, exX);
+    const long long kcount = s_k0 + exK;
+    u64 t = 0;
+    u128 Q = mk128(0, 0);
+    unsigned int R = 0;
+    const unsigned int n32 = (unsigned int)n, Tr = res->Tr;
+    const u128 Tq = res->Tq;
+    bool tooth_inside = false;
+    if (comb) {
+        t = s_t0 + tooth_seek(s_Q0, s_R0, s_inv, S, Tq, Tr, n32, Q, R);
+        tooth_inside = lt128(Q, add128(S, myX));
+    }
+    if (!use_rec) {
+        if (!__any_sync(0xffffffffu, tooth_inside) && (mode == 1 || !__any_sync(0xffffffffu, myKept != 0))) return;      // nothing to list in this warp
+        walk_particle(V, cap, i, c, thr, scale, mode, S, kcount, t, Q, R, tooth_inside, Tq, Tr, n32, surv_parent, surv_slot, surv_cap);
+        return;
+    }
+    // With the records: a particle without a tooth only lists its kept slots (known as a mask: no pass over its
+    // putatives); the particles with a tooth (about a third) are parked and walked by densely packed warps, so a warp
+    // does not run the full walk for a few of its lanes.
+    __shared__ WalkItem s_q[SCAN_THREADS];
+    if (tooth_inside) {
+        const unsigned int slot = atomicAdd(&s_nq, 1u);
+        PF_ASSERT(slot < SCAN_THREADS);
+        WalkItem it;
+        it.S = S; it.Q = Q; it.kcount = kcount; it.t = t; it.R = R; it.tid = tid; it.c = c; it.pad = 0;
+        s_q[slot] = it;
+    } else {
+        unsigned long long m = hi_mask;
+        long long pos = kcount + (long long)t;
+        while (m) {
+            const int j = __ffsll((long long)m) - 1; m &= m - 1;
+            PF_ASSERT(pos >= 0 && pos < surv_cap && j < c);
+            if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
+            pos++;
+        }
+    }
+    __syncthreads();
+    const unsigned int nq = s_nq;
+    for (unsigned int base = (unsigned int)wid * 32; base < nq; base += SCAN_THREADS) {
+        const unsigned int q = base + lane;
+        WalkItem it;
+        it.c = 0; it.tid = 0; it.S = mk128(0, 0); it.Q = mk128(0, 0); it.kcount = 0; it.t = 0; it.R = 0;
+        if (q < nq) it = s_q[q];
+        walk_particle(V, cap, (long long)blockIdx.x * SCAN_THREADS + it.tid, it.c, thr, scale, mode, it.S, it.kcount, it.t, it.Q, it.R, q < nq,
+                      Tq, Tr, n32, surv_parent, surv_slot, surv_cap);
+    }
+}
+
 // ------------------------------------------------------------------ k_instantiate
 // instantiate.(survivors) (src/particle.jl:134-149): thread t builds particle t of the new
 // population from its parent's slots (copy), applies add(comp, y) to the chosen slot as a
@@ -928,6 +992,7 @@ __device__ __forceinline__ void instantiate_one(const long long t, const R *__re
     if (ro) {
         const long long g = ro->g_first + t;
         const int dest = (int)(g / ro->q);
+        PF_ASSERT(dest >= 0 && dest < ro->nranks);
         anc_off = (unsigned int)ro->goff_prev;
         idx = g - (long long)dest * ro->q;
         if (dest != ro->rank) {
@@ -944,6 +1009,7 @@ __device__ __forceinline__ void instantiate_one(const long long t, const R *__re
     const int jj = sl & 0x7F;                    // putative index = row of V
     const bool picked = sl & 0x80;
     const int K = Kc[par];
+    PF_ASSERT((long long)par < cap && idx >= 0 && idx < cap && K >= 0 && K <= k_max && jj <= K + 1);
     // the component the putative assigns y to (state_to_index, src/statepriors.jl:22,103; k_expand_sp's table)
     int j = jj;
     bool sticky = false;

@@ -44,7 +44,7 @@ struct pf_filter_s {
     TileSum *supers = nullptr;            // totals of SUPER_TILES consecutive tile records (level 2 of the survivor scan)
     TileFuse *tfuse = nullptr;            // per expansion block (EXP_SUB per tile)
     TileSum *tsub = nullptr;              // sub-tile records of the fused expansion (EXP_SUB per tile)
-    ScanRec srec = ScanRec{nullptr, nullptr};   // per-particle scan records of the fused expansion (PF_SCAN_REC)
+    ScanRec srec = ScanRec{nullptr, nullptr, nullptr};   // per-particle scan records of the fused expansion (PF_SCAN_REC)
     long long fuse_stride = 1;
     bool fused = true;                    // single-GPU index-order Fearnhead: classify inside the expansion
     int sel_margin = 8;                   // half-width of the sample bracket in sigmas (PF_SEL_MARGIN; tests shrink it)
@@ -236,7 +236,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->V_alt, h->stc_alt, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->supers, h->tfuse, h->tsub, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_tiles, h->clp, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
-                    h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
+                    h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->srec.h, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
                     h->sp[1].Nsame, h->sp[1].last};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -357,6 +357,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     if (cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_INDEX && !getenv("PF_NO_SCAN_REC")) {
         CT(dmalloc(&h->srec.x, (size_t)h->cap));
         CT(dmalloc(&h->srec.m, (size_t)h->cap));
+        CT(dmalloc(&h->srec.h, (size_t)h->cap));
     }
     h->fuse_stride = std::max<long long>(1, (h->N * (h->k_max + 1) + 2 * SEL_SAMPLE_TARGET - 1) / (2 * SEL_SAMPLE_TARGET));
     h->fused = getenv("PF_NO_FUSE") == nullptr;
@@ -664,7 +665,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
                                                                                      h->supers, 0, h->sc);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, nullptr, 0, h->sc, 1);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
-                                                            h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr}, h->sc);
+                                                            h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr, nullptr}, h->sc);
     }
     if (fused && y_next && h->pipeline) {
         // pipelined tail: close this step's record, then build the children WHILE expanding them for the next observation
@@ -689,7 +690,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
             const long long ns = 4 * ((ub_next + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride));
             k_expand<D, 1, true, R><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,
-                                                                       nullptr, ScanRec{nullptr, nullptr}, ia);
+                                                                       nullptr, ScanRec{nullptr, nullptr, nullptr}, ia);
             std::swap(h->stc, h->stc_alt);            // (sel_args points the search at the next step's plateau value)
             SelArgs a = sel_args(h, h->V_alt, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_next, h->cand, h->cand_cap, h->sc, h->res);
             std::swap(h->stc, h->stc_alt);
@@ -1076,6 +1077,13 @@ extern "C" int32_t pf_get_particle(pf_handle h, int64_t i, int32_t *K_out, doubl
     return PF_OK;
 }
 
+struct DevBuf {                  // scoped device allocation
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
 // assignments(ps), src/filters.jl:26-34: the genealogy is walked on the device into a byte-wide time-major block for
 // a slice of the particles at a time (k_backtrack8), the slices are widened / transposed on the host
 static long long assign_chunk(long long T, long long n)
@@ -1108,6 +1116,27 @@ extern "C" int32_t pf_get_assignments(pf_handle h, int32_t *out)
             for (long long t = 0; t < T; t++) out[(i0 + c) * T + t] = host[(size_t)t * nc + c];
     }
     cudaFree(tmp);
+    return PF_OK;
+}
+
+// assignments(p) of ONE particle (src/particle.jl:25-32): its ancestor chain, T labels -- the read-out that stays cheap when
+// the full T x n matrix is too large to bring to the host
+extern "C" int32_t pf_get_particle_assignments(pf_handle h, int64_t i, int32_t *out)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    if (!h->hist_cap) return set_error(h, PF_ERR_HISTORY, "pf_get_particle_assignments: history is disabled (pf_config.history = 0)");
+    if (h->nranks > 1) return set_error(h, PF_ERR_STATE, "pf_get_particle_assignments: use pf_mg_get_assignments on a sharded handle");
+    if (i < 0 || i >= h->n_host) return set_error(h, PF_ERR_ARG, "pf_get_particle_assignments: index out of range");
+    const long long T = h->steps;
+    if (T == 0) return PF_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DevBuf tmp;
+    CUDA_TRY(tmp.alloc((size_t)T));
+    k_backtrack8<<<1, 32, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i, 1, tmp.as<unsigned char>());
+    std::vector<unsigned char> host((size_t)T);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), tmp.p, (size_t)T, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (long long t = 0; t < T; t++) out[t] = host[t];
     return PF_OK;
 }
 
@@ -1176,12 +1205,6 @@ extern "C" int32_t pf_get_last_assignments(pf_handle h, int32_t *out)
 
 // ------------------------------------------------------------------ filter-level summaries on the device
 // (src/filters.jl:17-42, 53-80; kernels in summaries.cuh)
-struct DevBuf {                  // scoped device allocation
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    template <typename T> T *as() { return static_cast<T *>(p); }
-};
 
 static int32_t summary_ready(pf_handle h, const char *who)
 {

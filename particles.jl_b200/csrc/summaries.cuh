@@ -187,6 +187,7 @@ __global__ void k_backtrack8(const unsigned int *__restrict__ gen_anc, const uns
     if (c >= nc) return;
     long long k = i0 + c;
     for (long long t = T - 1; t >= 0; t--) {
+        PF_ASSERT(k >= 0 && k < cap);
         out8[t * nc + c] = gen_asg[t * cap + k];
         k = gen_anc[t * cap + k];
     }

@@ -429,6 +429,12 @@ class ParticleFilter:
                            NStatePrior(spc[:cfg.sp_n]) if k == _lib.PF_SP_NSTATE else ChineseRestaurantProcess(cfg.alpha))
         return self
 
+    def particle_assignments(self, i):
+        """assignments(particles(ps)[i]) (src/particle.jl:25-32): the 1-based labels along particle i's ancestor chain."""
+        out = np.empty(self.n_steps, dtype=np.int32)
+        _lib.check(self._L.pf_get_particle_assignments(self._h, int(i), out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
+        return out.astype(np.int64) + 1
+
     def last_step(self):
         s = pf_step_stats()
         _lib.check(self._L.pf_get_last_step(self._h, C.byref(s)), self._h)

@@ -67,6 +67,9 @@ def test_summaries_match_oracle(kind, d, n, T):
     assert pb.state_entropy(dev) == pytest.approx(ref.state_entropy(), rel=RTOL)
     assert pb.mean(pb.ncomponents, dev) == pytest.approx(ref.mean_ncomponents(), rel=RTOL)
     np.testing.assert_allclose(pb.ncomponents_dist(dev), ref.ncomponents_dist(), rtol=RTOL, atol=1e-300)
+    A = dev.assignments()
+    for i in (0, len(dev) // 3, len(dev) - 1):
+        assert np.array_equal(dev.particle_assignments(i), A[:, i])
     # the similarity counts are integers: the matrix is exact
     assert np.array_equal(pb.assignment_similarity(dev), ref.assignment_similarity())
     truth = np.random.default_rng(2).integers(0, 4, T)
