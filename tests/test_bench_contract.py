@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-n", "512"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--cpu-n", "512", "--cpu-n2", "2048", "--cpu-burn2", "8", "--cpu-steps2", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [l for l in r.stdout.strip().splitlines() if l.strip()]
     assert len(lines) == 1
@@ -20,6 +20,8 @@ def test_reference_arm_prints_one_contract_line():
     assert j["cpu_baseline"]["value"] == j["value"] and j["cpu_baseline"]["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"] and j["vs_baseline"] is None and j["dtype"] == "f64" and j["data"] == "synthetic"
+    # the CPU arm says which population it really ran, and carries the second (larger) sample
+    assert j["config"]["n_particles_run"] == 512 and j["cpu_baseline_out_of_cache"]["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
