@@ -210,7 +210,7 @@ int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t N, double 
  * integer arithmetic on the gathered data, so every rank reaches the same threshold and a G-rank
  * run reproduces the 1-rank run bit for bit (src/fearnhead.jl:130-184 on the whole population).
  *
- * One process per GPU (e.g. under torchrun / MPI; any side channel can carry the 704-byte blobs):
+ * One process per GPU (e.g. under torchrun / MPI; any side channel can carry the 1088-byte blobs):
  *     pf_create(cfg with rank, nranks)            on every rank
  *     pf_mg_ipc_handles(h, blob)                  -> all-gather the blobs (host side, once)
  *     pf_mg_set_peer(h, r, NULL, blob_r)          for every other rank r
@@ -220,7 +220,8 @@ int32_t pf_select(int32_t device, const double *w, int64_t M, int64_t N, double 
  *     pf_mg_create_local(cfg, devices, n, handles) ;  pf_mg_filter(handles, n, ...)
  * Read-outs (pf_get_logweights, pf_get_ncomponents, pf_get_last_ancestors, ...) return each shard's
  * part; concatenated in rank order they are the global arrays (ancestors are global indices).     */
-#define PF_MG_NARRAYS 11        /* S[0], S[1], K[0], K[1], logw[0], logw[1], gen_anc, gen_asg, exchange region, Chen-Liu prefix array, Chen-Liu assignments */
+#define PF_MG_NARRAYS 17        /* S[0], S[1], K[0], K[1], logw[0], logw[1], gen_anc, gen_asg, exchange region, Chen-Liu prefix array and
+                                   assignments, V[0], V[1], putative counts, scan records (x, m, h) */
 #define PF_MG_IPC_BYTES 64      /* sizeof(cudaIpcMemHandle_t) */
 int32_t pf_set_stream(pf_handle h, void *cuda_stream);    /* run on the caller's stream */
 int32_t pf_mg_local_arrays(pf_handle h, void **out /* [PF_MG_NARRAYS] */);

@@ -134,6 +134,39 @@ struct ScanRec {
 #ifndef PF_INST_MINBLOCKS
 #define PF_INST_MINBLOCKS 1
 #endif
+// Sharded run (particles block-sharded over ranks, global order = rank-major): where this
+// rank's survivors sit in the global survivor order.  The new population is re-partitioned into
+// equal blocks of q = ceil(n / G) particles at EVERY step (rank r owns global [r q, (r+1) q)):
+// k_instantiate stores a child that changes owner straight into its new owner's arrays.
+struct RankOff {
+    u128 S_off;                    // fixed-point low mass of all lower ranks
+    long long kept_off;            // survivors kept on all lower ranks
+    long long g_first;             // global index of this rank's first survivor
+    long long n_local;             // survivors produced by this rank
+    long long n_mine;              // particles this rank owns after re-partitioning
+    long long n_global, q;
+    long long goff_prev;           // global index of this rank's first PARENT (genealogy)
+    long long goff_next;           // global index of this rank's first particle after the step
+    int rank, nranks;
+};
+
+// Every rank's next-generation arrays mapped into this process (cudaIpc, or plain pointers when
+// the ranks live in one process): k_instantiate stores a child that changes owner straight into
+// its new owner's store over NVLink -- no packing, no send/recv buffers, no host-known sizes.
+struct PeerTable {
+    void *S[PF_MAX_RANKS];                 // (elements of the handle's storage type)
+    int *Kc[PF_MAX_RANKS];
+    double *logw[PF_MAX_RANKS];
+    unsigned int *gen_anc[PF_MAX_RANKS];
+    unsigned char *gen_asg[PF_MAX_RANKS];
+    // pipelined sharded steps: the parent's owner also expands the child for the next observation and delivers the
+    // putative weights (two alternating buffers), their count and the per-particle scan record with the child
+    double *V[2][PF_MAX_RANKS];
+    unsigned char *cnt[PF_MAX_RANKS];
+    ulonglong2 *recx[PF_MAX_RANKS];
+    unsigned long long *recm[PF_MAX_RANKS], *rech[PF_MAX_RANKS];
+};
+
 // INST (pipelined step): particle i is child i of the PREVIOUS step's survivor list.  Its record does not exist yet:
 // the thread gathers the parent's slots, applies add(comp, y_prev) to the chosen one in registers
 // (instantiate, src/particle.jl:131-149), stores the child (MODE 2) and evaluates the child's putatives for THIS
@@ -145,14 +178,24 @@ struct InstArgs {
     const StepConst *scp_prev;             // ... observation and new-cluster slot
     void *S2; int *Kc2; double *logw2;     // the children's store (MODE 2; elements of the kernel's storage type)
     unsigned int *gen_anc; unsigned char *gen_asg;
+    // sharded run: child t of this rank's survivor list is global particle ro->g_first + t of the next generation and is
+    // delivered to its new owner (peer memory over NVLink) together with its putatives for the next observation
+    const RankOff *ro;
+    const PeerTable *peers;                // tables of the store buffer the children are written to
+    int vnext;                             // which of the two V buffers receives the next observation's putatives
+    long long gen_off;                     // offset of this generation's row in the genealogy arrays
 };
 #ifndef PF_INSTEXP_MINBLOCKS
 #define PF_INSTEXP_MINBLOCKS 3
 #endif
+#ifndef PF_INSTEXP_REMOTE_MINBLOCKS
+#define PF_INSTEXP_REMOTE_MINBLOCKS 3      // (the sharded variant carries the destination pointers: 208 bytes of spills at 80 registers)
+#endif
 // R: storage type of the particle store (double, or float under PF_F32: the arithmetic stays in double, every field
 // is rounded to R when it is stored, so the store traffic halves)
-template <int D, int MODE, bool INST = false, typename R = double>
-__global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF_EXPAND_MINBLOCKS) * EXP_SUB) k_expand(const R *__restrict__ S, const double *__restrict__ logw,
+// REMOTE (sharded INST): the child and its putatives are delivered to the child's new owner (InstArgs.ro / peers).
+template <int D, int MODE, bool INST = false, typename R = double, bool REMOTE = false>
+__global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMOTE_MINBLOCKS : PF_INSTEXP_MINBLOCKS) : PF_EXPAND_MINBLOCKS) * EXP_SUB) k_expand(const R *__restrict__ S, const double *__restrict__ logw,
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
@@ -171,15 +214,35 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
     __shared__ u128 s_tot[8];                    // kept-side total per warp
     __shared__ u128 s_red[8];
     __shared__ unsigned int s_redk[8], s_redp[8];
-    const long long n_live = st->n_live;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr bool remote = INST && REMOTE;
+    const long long n_live = remote ? ia.ro->n_local : st->n_live;
+    // (sharded INST expansion: a rank may produce more survivors than its grid was sized for -- blocks stride over tiles)
+    constexpr bool strided = remote && MODE == 2;
+    const long long vb_end = strided ? (n_live + blockDim.x - 1) / blockDim.x : 0;
+    // Sharded: the children that change owner sit at the two ENDS of this rank's survivor range (they go to the ranks
+    // before / after it), and their stores travel over NVLink at a fraction of the HBM rate.  The tiles are therefore
+    // visited from both ends towards the middle, so that the remote stores drain while the local tiles are computed
+    // instead of forming the kernel's tail.
+    long long lvb = blockIdx.x;                        // logical tile counter
+    long long vb = lvb;
+    if (strided) {
+        if (lvb >= vb_end) return;
+        vb = (lvb & 1) ? vb_end - 1 - (lvb >> 1) : (lvb >> 1);
+    }
+  do {
+    const long long gid = vb * blockDim.x + threadIdx.x;
     // MODE 1 samples aligned groups of 4 consecutive particles (one 32-byte sector per field row):
     // GLOBAL particle g is in the sample iff (g / 4) % stride == 0; a shard starts at global index st->goff
     long long i = gid;
     if (MODE == 1) {
-        const long long goff = st->goff;
+        const long long goff = remote ? ia.ro->g_first : st->goff;
         i = (goff / (4 * stride) + (gid >> 2)) * (4 * stride) + (gid & 3) - goff;
     }
+    // where particle i's outputs go (sharded INST: the arrays of the child's new owner `dest`; -1 = this rank's own)
+    long long di = i;
+    double *Vd = V;
+    R *S2d = static_cast<R *>(ia.S2);
+    int dest = -1;
     const bool fused = (MODE == 2) && sc->fuse_valid;
     u64 lo = 0, hi = 0; int scale = 0, tscale = 0;
     if (fused) { lo = sc->lo; hi = sc->hi; scale = sc->fuse_scale; tscale = sc->fuse_tot_scale; }
@@ -201,7 +264,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
             if (b != 0) { unsigned int pos = atomicAdd(&s_ncand, 1u); if (pos < CAND_CAP) s_cand[pos] = b; }
             return;
         }
-        V[(long long)j * cap + i] = v;
+        Vd[(long long)j * cap + di] = v;
         if (MODE == 2 && fused) {
             if (b >= hi) {
                 hi_mask |= 1ull << j;
@@ -234,9 +297,26 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
             const double v = ia.V_prev[(long long)jsel * cap + par];
             lw0 = (sl & 0x80) ? scp->prev_lw_resamp : (log(v) - scp->prev_log_total);      // src/fearnhead.jl:172-179
             src = par;
+            int *Kc2d = ia.Kc2; double *logw2d = ia.logw2;
+            unsigned int *gen_ancd = ia.gen_anc; unsigned char *gen_asgd = ia.gen_asg;
+            unsigned int anc_off = 0;
+            if (remote) {
+                const long long g = ia.ro->g_first + i;
+                const int dr = (int)(g / ia.ro->q);
+                PF_ASSERT(dr >= 0 && dr < ia.ro->nranks);
+                di = g - (long long)dr * ia.ro->q;
+                anc_off = (unsigned int)ia.ro->goff_prev;
+                if (MODE == 2 && dr != ia.ro->rank) {
+                    dest = dr;
+                    S2d = static_cast<R *>(ia.peers->S[dr]); Kc2d = ia.peers->Kc[dr]; logw2d = ia.peers->logw[dr];
+                    gen_ancd = ia.peers->gen_anc[dr] ? ia.peers->gen_anc[dr] + ia.gen_off : nullptr;
+                    gen_asgd = ia.peers->gen_asg[dr] ? ia.peers->gen_asg[dr] + ia.gen_off : nullptr;
+                    Vd = ia.peers->V[ia.vnext][dr];
+                }
+            }
             if (MODE == 2) {
-                ia.logw2[i] = lw0; ia.Kc2[i] = K + (jsel == K ? 1 : 0);
-                if (ia.gen_anc) { ia.gen_anc[i] = par; ia.gen_asg[i] = (unsigned char)jsel; }
+                logw2d[di] = lw0; Kc2d[di] = K + (jsel == K ? 1 : 0);
+                if (gen_ancd) { gen_ancd[di] = par + anc_off; gen_asgd[di] = (unsigned char)jsel; }
             }
         } else {
             K = Kc[i]; lw0 = logw[i];
@@ -256,7 +336,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
             emit(j, exp(lw));
         };
         auto store_child = [&](const double *fl, int j) {
-            R *dst = static_cast<R *>(ia.S2) + ((long long)j * L::F) * cap + i;
+            R *dst = S2d + ((long long)j * L::F) * cap + di;
 #pragma unroll
             for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = (R)fl[f];
         };
@@ -292,13 +372,14 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
         int c = Kn;
         if (Kn < k_max) { emit(Kn, exp(lw0 + scp->lw_new)); c = Kn + 1; }
         else myOvf = 1;
-        if (MODE != 1) cnt[i] = (unsigned char)c;
+        if (MODE != 1) ((remote && dest >= 0) ? ia.peers->cnt[dest] : cnt)[di] = (unsigned char)c;
         myM = c;
         kept_hi = (unsigned int)__popcll(hi_mask);
         if (MODE == 2 && fused && rec.x) {
-            rec.x[i] = make_ulonglong2(B_lo.lo, B_lo.hi | ((u64)kept_hi << 56));
-            rec.m[i] = in_mask;
-            rec.h[i] = hi_mask;
+            const bool far = remote && dest >= 0;
+            (far ? ia.peers->recx[dest] : rec.x)[di] = make_ulonglong2(B_lo.lo, B_lo.hi | ((u64)kept_hi << 56));
+            (far ? ia.peers->recm[dest] : rec.m)[di] = in_mask;
+            (far ? ia.peers->rech[dest] : rec.h)[di] = hi_mask;
         }
     }
     // ---- block epilogue
@@ -346,8 +427,10 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
                 u128 B = s_red[0], C2 = s_sc[0], tot = s_tot[0];
                 unsigned int kh = s_redk[0], np = s_redp[0];
                 for (int w = 1; w < (int)(blockDim.x >> 5); w++) { B = add128(B, s_red[w]); C2 = add128(C2, s_sc[w]); tot = add128(tot, s_tot[w]); kh += s_redk[w]; np += s_redp[w]; }
-                tiles[blockIdx.x].X = B; tiles[blockIdx.x].kept = kh;
-                tfuse[blockIdx.x].cand_off = goff; tfuse[blockIdx.x].cand_cnt = n; tfuse[blockIdx.x].n_plateau = np;
+                if (tiles) {           // (sharded INST expansion: the children's new owners form their own tile records)
+                    tiles[vb].X = B; tiles[vb].kept = kh;
+                    tfuse[vb].cand_off = goff; tfuse[vb].cand_cnt = n; tfuse[vb].n_plateau = np;
+                }
                 if (np) atomicAdd(&sc->n_plateau, (unsigned long long)np);
                 if (kh) atomicAdd(&sc->A_hi, (unsigned long long)kh);
                 if (n) atomicAdd(&sc->n_cand, (unsigned long long)n);
@@ -357,6 +440,12 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? PF_INSTEXP_MINBLOCKS : PF
             }
         }
     }
+    if (!strided) break;                               // (a compile-time constant: no loop on the unsharded path)
+    lvb += gridDim.x;
+    if (lvb >= vb_end) break;
+    vb = (lvb & 1) ? vb_end - 1 - (lvb >> 1) : (lvb >> 1);
+    __syncthreads();                                   // (the next tile re-uses the block's shared scratch)
+  } while (true);
 }
 
 // ------------------------------------------------------------------ k_expand_sp
@@ -489,32 +578,6 @@ __global__ void __launch_bounds__(256) k_expand_sp(const R *__restrict__ S, cons
 // -- one exclusive scan of (X, kept), no second dependent scan.  Three launches, no
 // spinning: per-tile sums, one-block prefix over the tiles, apply.
 
-// Sharded run (particles block-sharded over ranks, global order = rank-major): where this
-// rank's survivors sit in the global survivor order.  The new population is re-partitioned into
-// equal blocks of q = ceil(n / G) particles at EVERY step (rank r owns global [r q, (r+1) q)):
-// k_instantiate stores a child that changes owner straight into its new owner's arrays.
-struct RankOff {
-    u128 S_off;                    // fixed-point low mass of all lower ranks
-    long long kept_off;            // survivors kept on all lower ranks
-    long long g_first;             // global index of this rank's first survivor
-    long long n_local;             // survivors produced by this rank
-    long long n_mine;              // particles this rank owns after re-partitioning
-    long long n_global, q;
-    long long goff_prev;           // global index of this rank's first PARENT (genealogy)
-    long long goff_next;           // global index of this rank's first particle after the step
-    int rank, nranks;
-};
-
-// Every rank's next-generation arrays mapped into this process (cudaIpc, or plain pointers when
-// the ranks live in one process): k_instantiate stores a child that changes owner straight into
-// its new owner's store over NVLink -- no packing, no send/recv buffers, no host-known sizes.
-struct PeerTable {
-    void *S[PF_MAX_RANKS];                 // (elements of the handle's storage type)
-    int *Kc[PF_MAX_RANKS];
-    double *logw[PF_MAX_RANKS];
-    unsigned int *gen_anc[PF_MAX_RANKS];
-    unsigned char *gen_asg[PF_MAX_RANKS];
-};
 
 // one thread: wait for every rank's survivor-scan total (exchange kind C), turn the totals (mass of the
 // low partition, kept count) into this rank's offsets and the new ownership
@@ -553,6 +616,19 @@ __global__ void k_rank_offsets(const Xch *x, unsigned long long seq, long long s
     ro->rank = rank; ro->nranks = nranks; ro->goff_prev = st->goff;
     st->n_kept = my_kept; st->n_picked = my_picked; st->n_next = ro->n_mine; st->n_global = n_global;
     if (my_n > surv_cap) { sel_halt(guard, step, PF_HALT_SURVIVORS); ro->n_local = 0; }
+}
+
+// pipelined sharded steps: "this rank has delivered every child of the generation" (exchange kind D) is raised after the
+// fused instantiate + expansion, and awaited before the next step reads what the peers delivered
+__global__ void k_mg_signal_generation(const Xch *x, unsigned long long seq, const SelScratch *guard)
+{
+    if (threadIdx.x || blockIdx.x || guard->halt) return;
+    xch_signal(x, XCH_D, seq);
+}
+__global__ void k_mg_await_generation(const Xch *x, unsigned long long seq, long long step, SelScratch *guard)
+{
+    if (threadIdx.x || blockIdx.x || guard->halt) return;
+    if (!xch_wait(x, XCH_D, seq)) sel_halt(guard, step, PF_HALT_TIMEOUT);
 }
 
 // mode 0: index-order step (always runs); mode 1: flat sorted list, runs only when the step
@@ -641,10 +717,14 @@ __global__ void __launch_bounds__(SUPER_TILES) k_tile_scan1(TileSum *__restrict_
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
                                                             long long cap, const SelResult *__restrict__ res,
                                                             const long long *__restrict__ n_items_ptr, TileSum *__restrict__ tiles,
-                                                            int mode, const SelScratch *guard, const SelScratch *fusedsc)
+                                                            int mode, const SelScratch *guard, const SelScratch *fusedsc,
+                                                            ScanRec rec = ScanRec{nullptr, nullptr, nullptr}, const SelScratch *recsc = nullptr)
 {
     if (guard && (guard->phase != 4 || guard->halt)) return;
     if (fusedsc && fusedsc->tiles_ok) return;              // the fused expansion already wrote the tile records
+    // (pipelined sharded steps: the particles were expanded by their parents' owners, which delivered the per-particle
+    // scan records but could not form this shard's tile records: sum the records instead of the putatives)
+    const bool use_rec = rec.x && recsc && recsc->tiles_ok;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_x[SCAN_THREADS / 32];
     __shared__ unsigned int s_k[SCAN_THREADS / 32];
@@ -657,7 +737,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const double *__rest
         const long long i = tile * SCAN_THREADS + threadIdx.x;
         const int c = (i < n_items) ? (cnt ? cnt[i] : 1) : 0;
         u128 X; unsigned int kept;
-        thread_sums(V, cap, i, c, res->thr_bits, res->scale, comb, X, kept);
+        if (use_rec) {
+            X = mk128(0, 0); kept = 0;
+            if (c) {
+                const ulonglong2 x = rec.x[i];
+                kept = (unsigned int)(x.y >> 56);
+                if (comb) X = mk128(x.x, x.y & 0x00FFFFFFFFFFFFFFull);
+                unsigned long long m = rec.m[i];
+                while (m) {
+                    const int j = __ffsll((long long)m) - 1; m &= m - 1;
+                    const u64 bits = (u64)__double_as_longlong(V[(long long)j * cap + i]);
+                    if (bits >= res->thr_bits) kept++;
+                    else if (comb) X = add128(X, fx70(bits, res->scale));
+                }
+            }
+        } else {
+            thread_sums(V, cap, i, c, res->thr_bits, res->scale, comb, X, kept);
+        }
         X = warp_sum128(X);
         kept = (unsigned int)warp_sum64(kept);
         if (lane == 0) { s_x[wid] = X; s_k[wid] = kept; }
@@ -1098,10 +1194,10 @@ __global__ void __launch_bounds__(256, PF_INST_MINBLOCKS) k_instantiate(const R 
 // "keep everything" and scales the sample bracket), from the survivor list alone
 __global__ void __launch_bounds__(256) k_count_next(const StepState *__restrict__ st, const int *__restrict__ Kc,
                                                     const unsigned int *__restrict__ surv_parent, const unsigned char *__restrict__ surv_slot,
-                                                    int k_max, long long *m_pred, const SelScratch *guard)
+                                                    int k_max, long long *m_pred, const SelScratch *guard, const RankOff *ro = nullptr)
 {
     if (guard->halt) return;
-    const long long n = st->n_live;
+    const long long n = ro ? ro->n_local : st->n_live;      // (sharded: the survivors this rank produced)
     unsigned int c = 0;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const int K = Kc[surv_parent[t]];

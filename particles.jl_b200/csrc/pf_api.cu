@@ -35,6 +35,9 @@ struct pf_filter_s {
     double *V = nullptr;                  // putative weights of the current step
     double *V_alt = nullptr;              // pipelined steps: the buffer the NEXT step's putatives are written to (swapped with V)
     StepConst *stc_alt = nullptr;         // ... and its per-observation constants (swapped with stc)
+    double *Vbuf[2] = {nullptr, nullptr}; // the two V buffers by identity (peers address them by index); V == Vbuf[vcur]
+    int vcur = 0;
+    bool pipeline_mg = false;             // ... the same fusion on the sharded path (children and their putatives go to the new owner)
     bool pipeline = false;                // instantiate of step t fused with the expansion of step t + 1 inside pf_filter
     bool pre_expanded = false;            // the step about to run was expanded by the previous step's pipelined tail
     unsigned char *cnt = nullptr;
@@ -331,7 +334,10 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     // single-GPU index-order CRP Fearnhead filter: instantiate of one observation is fused with the expansion of the next
     h->pipeline = cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_INDEX && h->nranks == 1 && spk == PF_SP_CRP &&
                   !getenv("PF_NO_PIPELINE") && !getenv("PF_NO_FUSE");
-    if (h->pipeline) { CT(dmalloc(&h->V_alt, (size_t)(h->k_max + 2) * cap)); CT(dmalloc(&h->stc_alt, 1)); }
+    h->pipeline_mg = cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_INDEX && h->nranks > 1 && spk == PF_SP_CRP &&
+                     !getenv("PF_NO_PIPELINE") && !getenv("PF_NO_FUSE") && !getenv("PF_NO_SCAN_REC");
+    if (h->pipeline || h->pipeline_mg) { CT(dmalloc(&h->V_alt, (size_t)(h->k_max + 2) * cap)); CT(dmalloc(&h->stc_alt, 1)); }
+    h->Vbuf[0] = h->V; h->Vbuf[1] = h->V_alt; h->vcur = 0;
     CT(dmalloc(&h->cnt, cap));
     h->surv_cap = h->nranks > 1 ? std::min<long long>(h->N, cap * (h->k_max + 1)) + 1024 : cap;
     CT(dmalloc(&h->surv_parent, h->surv_cap));
@@ -682,7 +688,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
             k_count_next<<<std::min(grid_for(ub_next, 256), h->num_sms * 8), 256, 0, h->stream>>>(h->st, h->Kc[cur], h->surv_parent, h->surv_slot, h->k_max,
                                                                                                  &h->st->M_pred, h->sc);
         }
-        InstArgs ia;
+        InstArgs ia{};
         ia.surv_parent = h->surv_parent; ia.surv_slot = h->surv_slot; ia.V_prev = h->V; ia.scp_prev = h->stc;
         ia.S2 = h->S[nxt]; ia.Kc2 = h->Kc[nxt]; ia.logw2 = h->logw[nxt]; ia.gen_anc = ga; ia.gen_asg = gs;
         {
@@ -703,7 +709,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
                                                                        h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, h->tsub, h->tfuse, h->srec, ia);
         }
         CUDA_TRY(cudaGetLastError());
-        std::swap(h->V, h->V_alt);
+        std::swap(h->V, h->V_alt); h->vcur ^= 1;
         std::swap(h->stc, h->stc_alt);
         h->cur = nxt;
         h->pre_expanded = true;
@@ -1682,8 +1688,10 @@ static void *peer_array(pf_handle h, int k)
     switch (k) {
     case 0: return h->S[0]; case 1: return h->S[1]; case 2: return h->Kc[0]; case 3: return h->Kc[1];
     case 4: return h->logw[0]; case 5: return h->logw[1]; case 6: return h->gen_anc; case 7: return h->gen_asg;
-    case 8: return h->xreg; case 9: return h->cum;
-    default: return h->asg_tmp;
+    case 8: return h->xreg; case 9: return h->cum; case 10: return h->asg_tmp;
+    case 11: return h->Vbuf[0]; case 12: return h->Vbuf[1]; case 13: return h->cnt;
+    case 14: return h->srec.x; case 15: return h->srec.m;
+    default: return h->srec.h;
     }
 }
 
@@ -1727,6 +1735,10 @@ extern "C" int32_t pf_mg_set_peer(pf_handle h, int32_t peer, void *const *ptrs, 
         h->peers_host[b].S[peer] = a[b]; h->peers_host[b].Kc[peer] = (int *)a[2 + b];
         h->peers_host[b].logw[peer] = (double *)a[4 + b];
         h->peers_host[b].gen_anc[peer] = (unsigned int *)a[6]; h->peers_host[b].gen_asg[peer] = (unsigned char *)a[7];
+        h->peers_host[b].V[0][peer] = (double *)a[11]; h->peers_host[b].V[1][peer] = (double *)a[12];
+        h->peers_host[b].cnt[peer] = (unsigned char *)a[13];
+        h->peers_host[b].recx[peer] = (ulonglong2 *)a[14]; h->peers_host[b].recm[peer] = (unsigned long long *)a[15];
+        h->peers_host[b].rech[peer] = (unsigned long long *)a[16];
     }
     h->xch_host.reg[peer] = (XchRegion *)a[8];
     for (int b = 0; b < 2; b++) { h->clp_host.S[b][peer] = a[b]; h->clp_host.Kc[b][peer] = (const int *)a[2 + b]; }
@@ -1813,7 +1825,7 @@ static int32_t mg_stage_b(pf_handle h, const double *u_dev, int retry, int searc
     SelArgs a = sel_args(h, h->V, h->cnt, cap, &h->st->n_live, &h->st->M, &h->st->vmax_bits, h->N, u_dev, h->cand, h->cand_cap, h->sc, h->res);
     a.external_sample = 1; a.preclassified = 1; a.x = h->xch; a.retry = retry;
     if (search_stage & SEL_ST_PUB) {
-        if (!retry) {
+        if (!retry && !h->pre_expanded) {
             LaunchTimer lt(h, KC_EXPAND);
             k_expand<D, 2, false, R><<<grid_for(cap, EXP_THREADS), EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], h->logw[cur], h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                         h->stc, h->st, h->V, h->cnt, h->sc, 1, h->cand, h->tsub, h->tfuse, h->srec);
@@ -1833,14 +1845,32 @@ static int32_t mg_stage_c(pf_handle h)
     const int g = grid_for(h->cap, SCAN_THREADS);
     const unsigned long long seq = (unsigned long long)h->steps + 1;
     LaunchTimer lt(h, KC_SCAN, 3);
-    k_tile_sums<<<std::min(g, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, h->sc);
-    k_tile_scan1<<<grid_for(g, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, h->tsub, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc, h->supers, 0, h->sc);
+    if (h->pre_expanded) {
+        // the particles were expanded by their parents' owners: tile records from the delivered per-particle records
+        k_tile_sums<<<std::min(g, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, nullptr,
+                                                                                  h->srec, h->sc);
+        k_tile_scan1<<<grid_for(g, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, nullptr, nullptr, nullptr, h->res, h->sc, &h->st->n_live, h->stc, h->supers, 0, h->sc);
+    } else {
+        k_tile_sums<<<std::min(g, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, h->sc);
+        k_tile_scan1<<<grid_for(g, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, h->tsub, h->tfuse, h->cand, h->res, h->sc, &h->st->n_live, h->stc, h->supers, 0, h->sc);
+    }
     k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, h->xch, seq, h->sc, 1);
     return PF_OK;
 }
 
-// D: global offsets from every rank's total, survivor scan, instantiate (children that change owner are
-// stored into their new owner's arrays), step record + "generation complete" signal
+// D: global offsets from every rank's total, survivor scan; then either the classic tail -- instantiate (children that
+// change owner are stored into their new owner's arrays), step record + "generation complete" signal -- or the
+// pipelined one (mg_tail): the children are instantiated WHILE they are expanded for the next observation
+static int32_t mg_stage_d_scan(pf_handle h)
+{
+    const unsigned long long seq = (unsigned long long)h->steps + 1;
+    LaunchTimer lt(h, KC_SCAN, 2);            // (k_rank_offsets includes the wait for every rank's total)
+    k_rank_offsets<<<1, 32, 0, h->stream>>>(h->xch, seq, h->steps, h->res, h->st, h->ro, h->sc, h->surv_cap);
+    k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, h->supers,
+                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap, h->srec, h->sc);
+    return PF_OK;
+}
+
 template <int D, typename R>
 static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
 {
@@ -1848,12 +1878,6 @@ static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
     const unsigned long long seq = (unsigned long long)h->steps + 1;
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * h->cap; gs = h->gen_asg + (size_t)h->steps * h->cap; }
-    {
-        LaunchTimer lt(h, KC_SCAN, 2);            // (k_rank_offsets includes the wait for every rank's total)
-        k_rank_offsets<<<1, 32, 0, h->stream>>>(h->xch, seq, h->steps, h->res, h->st, h->ro, h->sc, h->surv_cap);
-        k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, h->supers,
-                                                                                      h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap, h->srec, h->sc);
-    }
     {
         LaunchTimer lt(h, KC_INSTANTIATE);
         k_instantiate<D, R><<<grid_for(std::min<long long>(h->surv_cap, h->cap + h->cap / 4), 256), 256, 0, h->stream>>>((const R *)h->S[cur], h->Kc[cur], (R *)h->S[nxt], h->Kc[nxt], h->logw[nxt], h->cap,
@@ -1868,6 +1892,70 @@ static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
     CUDA_TRY(cudaGetLastError());
     h->cur = nxt;
     h->steps++;
+    h->pre_expanded = false;
+    return PF_OK;
+}
+
+// Pipelined tail of a sharded step, in three phases (a lock-step group queues each phase for all its shards before
+// the next: the bracket's exchange is published in phase 1 and awaited in phase 2):
+//   1  step record; roll the control block to the next observation; count its putatives; sample expansion of this
+//      rank's sampled children; publish the sample
+//   2  bracket on the gathered sample
+//   3  instantiate + expansion + classification of every child this rank produced, each delivered with its putatives
+//      and scan record to its new owner; "generation delivered"
+template <int D, typename R>
+static int32_t mg_tail(pf_handle h, int phase, StepLog *log_dev, const double *y_next, const double *u_next, int search_stage)
+{
+    const long long cap = h->cap;
+    if (phase == 1) {
+        {
+            LaunchTimer lt(h, KC_STEPLOG);
+            k_steplog<<<1, 32, 0, h->stream>>>(h->st, h->res, log_dev, h->sc, h->steps, h->dbg_status, h->ro, nullptr, 0);
+        }
+        h->steps++;                                   // the host mirrors now describe the next step; h->cur still names the parents' store
+        LaunchTimer lt(h, KC_PRESTEP, 2);
+        k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_next, h->stc_alt, 3, h->sc, h->res, nullptr, 0, h->steps, -1);
+        k_count_next<<<std::min(grid_for(cap, 256), h->num_sms * 8), 256, 0, h->stream>>>(h->st, h->Kc[h->cur], h->surv_parent, h->surv_slot, h->k_max,
+                                                                                          &h->st->M_pred, h->sc, h->ro);
+    }
+    const int cur = h->cur, nxt = cur ^ 1;
+    InstArgs ia{};
+    ia.surv_parent = h->surv_parent; ia.surv_slot = h->surv_slot; ia.V_prev = h->V; ia.scp_prev = h->stc;
+    ia.S2 = h->S[nxt]; ia.Kc2 = h->Kc[nxt]; ia.logw2 = h->logw[nxt];
+    ia.gen_off = (long long)(h->steps - 1) * cap;
+    if (h->hist_cap) { ia.gen_anc = h->gen_anc + ia.gen_off; ia.gen_asg = h->gen_asg + ia.gen_off; }
+    ia.ro = h->ro; ia.peers = h->peers[nxt]; ia.vnext = h->vcur ^ 1;
+    if (phase == 1 || phase == 2) {
+        LaunchTimer lt(h, KC_SELECT, phase == 1 ? 2 : 1);
+        if (phase == 1) {
+            const long long ns = 4 * ((h->surv_cap + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride) + 1);      // groups of 4 children (+1: the shard's phase)
+            k_expand<D, 1, true, R, true><<<grid_for(ns, EXP_SAMPLE_THREADS), EXP_SAMPLE_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                       h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, h->fuse_stride, h->cand, nullptr,
+                                                                       nullptr, ScanRec{nullptr, nullptr, nullptr}, ia);
+        }
+        if ((phase == 1 && (search_stage & SEL_ST_PUB)) || (phase == 2 && search_stage == SEL_ST_RUN)) {
+            std::swap(h->stc, h->stc_alt);            // (sel_args points the search at the next step's plateau value)
+            SelArgs a = sel_args(h, h->V_alt, h->cnt, cap, &h->st->n_live, &h->st->M_pred, &h->st->vmax_sample, h->N, u_next, h->cand, h->cand_cap, h->sc, h->res);
+            std::swap(h->stc, h->stc_alt);
+            a.external_sample = 1; a.x = h->xch; a.stage = search_stage;
+            CUDA_TRY(launch_coop(k_sel_bracket, h->coop_grid, h->stream, a));
+        }
+        return PF_OK;
+    }
+    {
+        LaunchTimer lt(h, KC_INST_EXPAND);
+        k_expand<D, 2, true, R, true><<<grid_for(std::min<long long>(h->surv_cap, cap + cap / 4), EXP_THREADS), EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+                                                                   h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, nullptr, nullptr, h->srec, ia);
+    }
+    {
+        LaunchTimer lt(h, KC_STEPLOG);
+        k_mg_signal_generation<<<1, 32, 0, h->stream>>>(h->xch, (unsigned long long)h->steps, h->sc);
+    }
+    CUDA_TRY(cudaGetLastError());
+    std::swap(h->V, h->V_alt); h->vcur ^= 1;
+    std::swap(h->stc, h->stc_alt);
+    h->cur = nxt;
+    h->pre_expanded = true;
     return PF_OK;
 }
 
@@ -1935,19 +2023,44 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
             for (int st = 0; st < 6; st++) FOR_SHARDS((chenliu_stage<D, R>(h, st, h->ys_dev + t * d, uniforms ? h->u_dev : nullptr, h->slog + t)));
             continue;
         }
+        // A step whose expansion ran in the previous step's pipelined tail starts at the search, once every rank's
+        // children (with their putatives and scan records) have been delivered
+        const bool pre = hs[0]->pre_expanded;
+        if (pre) {
+            for (int i = 0; i < n_local && rc == PF_OK; i++) {
+                pf_handle h = hs[i];
+                cudaSetDevice(h->cfg.device);
+                LaunchTimer lt(h, KC_PRESTEP);
+                k_mg_await_generation<<<1, 32, 0, h->stream>>>(h->xch, (unsigned long long)h->steps, h->steps, h->sc);
+            }
+        }
         if (lockstep) {
-            FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_PUB)));
-            FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_RUN)));
+            if (!pre) {
+                FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_PUB)));
+                FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, SEL_ST_RUN)));
+            }
             for (int r = 0; r <= SEL_RETRIES; r++) {
                 FOR_SHARDS((mg_stage_b<D, R>(h, h->u_dev + t, r > 0, SEL_ST_PUB)));
                 FOR_SHARDS((mg_stage_b<D, R>(h, h->u_dev + t, r > 0, SEL_ST_RUN)));
             }
         } else {
-            FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, both)));
+            if (!pre) FOR_SHARDS((mg_stage_a<D, R>(h, h->ys_dev + t * d, h->u_dev + t, both)));
             for (int r = 0; r <= SEL_RETRIES; r++) FOR_SHARDS((mg_stage_b<D, R>(h, h->u_dev + t, r > 0, both)));
         }
         for (int i = 0; i < n_local && rc == PF_OK; i++) { cudaSetDevice(hs[i]->cfg.device); rc = mg_stage_c(hs[i]); }
-        FOR_SHARDS((mg_stage_d<D, R>(h, h->slog + t)));
+        for (int i = 0; i < n_local && rc == PF_OK; i++) { cudaSetDevice(hs[i]->cfg.device); rc = mg_stage_d_scan(hs[i]); }
+        const bool next_ok = hs[0]->pipeline_mg && t + 1 < T;
+        if (next_ok) {
+            if (lockstep) {
+                FOR_SHARDS((mg_tail<D, R>(h, 1, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, SEL_ST_PUB)));
+                FOR_SHARDS((mg_tail<D, R>(h, 2, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, SEL_ST_RUN)));
+            } else {
+                FOR_SHARDS((mg_tail<D, R>(h, 1, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, both)));
+            }
+            FOR_SHARDS((mg_tail<D, R>(h, 3, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, both)));
+        } else {
+            FOR_SHARDS((mg_stage_d<D, R>(h, h->slog + t)));
+        }
     }
 #undef FOR_SHARDS
     // drain: every shard's records; a halted shard reports why

@@ -5,7 +5,7 @@ libparticles_b200.so: the kernels write what other ranks need straight into the 
 memory over NVLink and synchronise through sequence flags (include/particles_b200.h,
 "multi-GPU").  This module only does the one-time plumbing a host program owes the library:
 
-  * one process per GPU (torchrun / mpirun ...): all-gather the 704-byte CUDA-IPC blobs of
+  * one process per GPU (torchrun / mpirun ...): all-gather the 1088-byte CUDA-IPC blobs of
     `pf_mg_ipc_handles` once (any side channel; `TorchGroup` uses torch.distributed, which is
     also what the tests use over gloo for the host-side logic), `pf_mg_set_peer`, `pf_mg_connect`;
   * one process driving several GPUs (`LocalGroup`): `pf_mg_create_local` does all of it.
