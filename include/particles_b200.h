@@ -62,8 +62,9 @@ typedef struct {
     int32_t k_max;            /* cluster slots per particle (reference: unbounded, src/particle.jl:142-143);
                                  at K == k_max the new-cluster candidate is dropped and counted */
     int32_t order;            /* PF_ORDER_INDEX | PF_ORDER_SORTED (Fearnhead only) */
-    int64_t history;          /* generations of (ancestor, assignment) kept for assignments(): > 0 fixed capacity, 0 none,
-                                 < 0 grows on demand (the reference's ancestor chain, src/particle.jl:25-32, is unbounded) */
+    int64_t history;          /* generations of (ancestor, assignment) kept for assignments(): > 0 fixed capacity (dense), 0 none,
+                                 < 0 grows on demand (the reference's ancestor chain, src/particle.jl:25-32, is unbounded): on
+                                 a single GPU an arena pruned of dead lineages (pf_genealogy_info), sharded a dense log */
     int32_t device;           /* CUDA device ordinal */
     int32_t stateprior_kind;  /* PF_SP_* */
     int32_t rank, nranks;     /* sharded run: this handle owns shard `rank` of `nranks` (0, 0 or 0, 1: unsharded) */
@@ -152,6 +153,11 @@ int32_t pf_get_assignments(pf_handle h, int32_t *out);
 /* assignments(p) of ONE particle (src/particle.jl:25-32): out[T], 0-based.  Stays cheap when the T x n matrix of a long
  * run over a large population is too big to bring to the host (2^24 particles x 10^4 observations = 1.7e11 labels). */
 int32_t pf_get_particle_assignments(pf_handle h, int64_t i, int32_t *out);
+/* The genealogy log: out[0] generations stored, out[1] nodes stored, out[2] capacity in nodes, out[3] pruning passes so
+ * far.  With history < 0 on a single GPU the log is an arena that is pruned of dead lineages when it fills up (the
+ * reference's ancestor chain is pruned by the garbage collector, src/particle.jl:25-32): a generation then keeps only
+ * the nodes that are still an ancestor of somebody in the current population. */
+int32_t pf_genealogy_info(pf_handle h, int64_t *out /* [4] */);
 int32_t pf_get_last_step(pf_handle h, pf_step_stats *out);
 
 /* ---- filter-level summaries, evaluated on the device-resident population ------------------ */

@@ -103,6 +103,14 @@ struct pf_filter_s {
     unsigned char *gen_asg = nullptr;
     long long hist_cap = 0;
     bool hist_auto = false;               // pf_config.history < 0: the genealogy grows on demand
+    // history < 0 on a single GPU: the log is an ARENA of generations of varying length (gen_off / gen_n), appended
+    // densely and pruned of dead lineages when it fills up (prune_genealogy)
+    bool arena = false;
+    long long arena_cap = 0, arena_used = 0, arena_budget = 0;     // entries
+    std::vector<long long> gen_off, gen_n;
+    long long *gen_off_dev = nullptr;     // device copy of gen_off (uploaded before a backtrack)
+    long long gen_off_dev_cap = 0;
+    long long n_prunes = 0, last_prune_step = 0;
     std::vector<long long> gen_q;         // sharded run: block length q = ceil(n / G) of the population after each step
     // host mirrors
     long long steps = 0;
@@ -238,7 +246,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->V_alt, h->stc_alt, h->cnt, h->surv_parent,
                     h->surv_slot, h->tiles, h->supers, h->tfuse, h->tsub, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
-                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->cl, h->W, h->cum, h->asg_tmp, h->cl_tiles, h->clp, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
+                    h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->gen_off_dev, h->cl, h->W, h->cum, h->asg_tmp, h->cl_tiles, h->clp, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
                     h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->srec.h, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
                     h->sp[1].Nsame, h->sp[1].last};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -403,6 +411,16 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     }
     CT(dmalloc(&h->cand, (size_t)h->cand_cap));
     h->hist_auto = cfg->history < 0;
+    if (h->hist_auto && h->nranks == 1) {
+        // arena mode: budget = a share of what is free now (the filter's own arrays are allocated), PF_GENEALOGY_BYTES overrides
+        size_t free_b = 0, total_b = 0;
+        CT(cudaMemGetInfo(&free_b, &total_b));
+        double bytes = std::min(0.45 * (double)free_b, 64e9);
+        if (getenv("PF_GENEALOGY_BYTES")) bytes = atof(getenv("PF_GENEALOGY_BYTES"));
+        h->arena = true;
+        h->arena_budget = std::max<long long>((long long)(bytes / 5.0), 4 * cap);
+        h->hist_cap = 1ll << 40;                          // (rows are not the limit in this mode)
+    }
     if (cfg->history > 0) {
         h->hist_cap = cfg->history;
         CT(dmalloc(&h->gen_anc, (size_t)h->hist_cap * cap));
@@ -492,6 +510,9 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
 }
 
 // ------------------------------------------------------------------ the step sequences
+// offset of generation t in the genealogy arrays
+static inline size_t gen_row(const pf_filter_s *h, long long t) { return h->arena ? (size_t)h->gen_off[t] : (size_t)t * h->cap; }
+
 static inline int grid_for(long long n, int bs) { long long g = (n + bs - 1) / bs; return (int)(g < 1 ? 1 : g); }
 
 // ---- the threshold search: cooperative launches, argument block, launch sequences
@@ -569,7 +590,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
     unsigned int *ga = nullptr; unsigned char *gs = nullptr;
     if (h->hist_cap) {
         if (h->steps >= h->hist_cap) return set_error(h, PF_ERR_HISTORY, "history capacity exhausted (pf_config.history)");
-        ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap;
+        ga = h->gen_anc + gen_row(h, h->steps); gs = h->gen_asg + gen_row(h, h->steps);
     }
     h->epoch++;
     const int forced = h->cur_label;
@@ -791,7 +812,7 @@ static int32_t chenliu_stage(pf_handle h, int s, const double *y_dev, const doub
     }
     default: {
         unsigned int *ga = nullptr; unsigned char *gs = nullptr;
-        if (h->hist_cap) { ga = h->gen_anc + (size_t)h->steps * cap; gs = h->gen_asg + (size_t)h->steps * cap; }
+        if (h->hist_cap) { ga = h->gen_anc + gen_row(h, h->steps); gs = h->gen_asg + gen_row(h, h->steps); }
         {
             LaunchTimer lt(h, KC_CL_FINISH);
             if (x && split) { k_cl_x_ready<<<1, 32, 0, h->stream>>>(h->cl, x, seq, h->steps, SEL_ST_RUN, h->sc); h->launches++; }
@@ -820,10 +841,142 @@ static int32_t chenliu_step(pf_handle h, const double *y_dev, const double *u_de
     return PF_OK;
 }
 
-// history < 0: make room for `need` generations (doubling; the old generations are copied over)
+struct DevBuf {                  // scoped device allocation
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+// device copy of the generations' offsets for the backtrack kernels (null: dense log)
+static int32_t upload_gen_off(pf_handle h, const long long **out)
+{
+    *out = nullptr;
+    if (!h->arena) return PF_OK;
+    const long long T = h->steps;
+    if (T > h->gen_off_dev_cap) {
+        if (h->gen_off_dev) cudaFree(h->gen_off_dev);
+        h->gen_off_dev = nullptr; h->gen_off_dev_cap = 0;
+        CUDA_TRY(dmalloc(&h->gen_off_dev, (size_t)std::max<long long>(2 * T, 64)));
+        h->gen_off_dev_cap = std::max<long long>(2 * T, 64);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->gen_off_dev, h->gen_off.data(), sizeof(long long) * T, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));        // (gen_off may be edited by the host right after)
+    *out = h->gen_off_dev;
+    return PF_OK;
+}
+
+// Arena mode: drop the nodes that are no longer an ancestor of the current population (summaries.cuh, "genealogy
+// pruning") and pack the generations.  Newest generation first; all lengths the kernels need that changed in this pass
+// are read on the device (n_dev), the host learns them once at the end.
+static int32_t prune_genealogy(pf_handle h)
+{
+    const long long G = h->steps;
+    if (!h->arena || G < 2) return PF_OK;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    long long maxn = 1;
+    for (long long g = 0; g < G; g++) maxn = std::max(maxn, h->gen_n[g]);
+    DevBuf dmark, didx, dpart, dtanc, dtasg, dn;
+    CUDA_TRY(dmark.alloc(sizeof(unsigned int) * maxn));
+    CUDA_TRY(didx.alloc(sizeof(unsigned int) * maxn));
+    CUDA_TRY(dpart.alloc(sizeof(unsigned int) * (maxn / RS_SCAN_TILE + 1024)));
+    CUDA_TRY(dtanc.alloc(sizeof(unsigned int) * maxn));
+    CUDA_TRY(dtasg.alloc((size_t)maxn));
+    CUDA_TRY(dn.alloc(sizeof(long long) * G));
+    CUDA_TRY(cudaMemcpyAsync(dn.p, h->gen_n.data(), sizeof(long long) * G, cudaMemcpyHostToDevice, h->stream));
+    long long *n_dev = dn.as<long long>();
+    unsigned int *mark = dmark.as<unsigned int>(), *idx = didx.as<unsigned int>(), *part = dpart.as<unsigned int>();
+    const int gmax = h->num_sms * 8;
+    for (long long g = G - 1; g >= 1; g--) {
+        const long long p = g - 1, np_old = h->gen_n[p], ng_old = h->gen_n[g];
+        if (np_old == 0 || ng_old == 0) continue;
+        unsigned int *anc_g = h->gen_anc + h->gen_off[g];
+        unsigned int *anc_p = h->gen_anc + h->gen_off[p];
+        unsigned char *asg_p = h->gen_asg + h->gen_off[p];
+        CUDA_TRY(cudaMemsetAsync(mark, 0, sizeof(unsigned int) * np_old, h->stream));
+        k_gen_mark<<<std::min(grid_for(ng_old, 256), gmax), 256, 0, h->stream>>>(anc_g, n_dev + g, mark);
+        CUDA_TRY(cudaMemcpyAsync(idx, mark, sizeof(unsigned int) * np_old, cudaMemcpyDeviceToDevice, h->stream));
+        const long long nb = (np_old + RS_SCAN_TILE - 1) / RS_SCAN_TILE;
+        k_rs_scan_sums<<<(unsigned)nb, 1024, 0, h->stream>>>(idx, np_old, part);
+        k_rs_scan_top<<<1, 1024, 0, h->stream>>>(part, nb);
+        k_rs_scan_apply<<<(unsigned)nb, 1024, 0, h->stream>>>(idx, np_old, part);
+        k_gen_count<<<1, 32, 0, h->stream>>>(mark, idx, np_old, n_dev + p);
+        k_gen_compact<<<std::min(grid_for(np_old, 256), gmax), 256, 0, h->stream>>>(anc_p, asg_p, np_old, mark, idx, dtanc.as<unsigned int>(), dtasg.as<unsigned char>());
+        k_gen_copy<<<std::min(grid_for(np_old, 256), gmax), 256, 0, h->stream>>>(dtanc.as<unsigned int>(), dtasg.as<unsigned char>(), n_dev + p, anc_p, asg_p);
+        k_gen_rewrite<<<std::min(grid_for(ng_old, 256), gmax), 256, 0, h->stream>>>(anc_g, n_dev + g, idx);
+    }
+    std::vector<long long> n_new(G);
+    CUDA_TRY(cudaMemcpyAsync(n_new.data(), dn.p, sizeof(long long) * G, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // pack: oldest first, every generation moves towards the start of the arena (through the scratch when it overlaps)
+    long long run = 0;
+    for (long long g = 0; g < G; g++) {
+        const long long n = n_new[g], src = h->gen_off[g];
+        if (src != run && n > 0) {
+            if (run + n <= src) {
+                CUDA_TRY(cudaMemcpyAsync(h->gen_anc + run, h->gen_anc + src, sizeof(unsigned int) * n, cudaMemcpyDeviceToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(h->gen_asg + run, h->gen_asg + src, (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(dtanc.p, h->gen_anc + src, sizeof(unsigned int) * n, cudaMemcpyDeviceToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(dtasg.p, h->gen_asg + src, (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(h->gen_anc + run, dtanc.p, sizeof(unsigned int) * n, cudaMemcpyDeviceToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(h->gen_asg + run, dtasg.p, (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+            }
+        }
+        h->gen_off[g] = run; h->gen_n[g] = n;
+        run += n;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->arena_used = run;
+    h->n_prunes++; h->last_prune_step = G;
+    return PF_OK;
+}
+
+// arena: room for `want` more entries behind arena_used (doubling up to the budget, then exactly what is needed)
+static int32_t arena_reserve(pf_handle h, long long want)
+{
+    if (h->arena_used + want <= h->arena_cap) return PF_OK;
+    long long ncap = std::max<long long>(h->arena_used + want, std::min<long long>(2 * h->arena_cap, h->arena_budget));
+    ncap = std::max<long long>(ncap, 16 * h->cap);
+    unsigned int *na = nullptr; unsigned char *ns = nullptr;
+    cudaError_t e = dmalloc(&na, (size_t)ncap);
+    if (e == cudaSuccess) e = dmalloc(&ns, (size_t)ncap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (na) cudaFree(na);
+        return set_error(h, PF_ERR_HISTORY, "the genealogy no longer fits in device memory: create the filter with history = 0 (none) or a fixed capacity");
+    }
+    if (h->arena_used > 0) {
+        CUDA_TRY(cudaMemcpyAsync(na, h->gen_anc, sizeof(unsigned int) * (size_t)h->arena_used, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(ns, h->gen_asg, (size_t)h->arena_used, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (h->gen_anc) cudaFree(h->gen_anc);
+    if (h->gen_asg) cudaFree(h->gen_asg);
+    h->gen_anc = na; h->gen_asg = ns; h->arena_cap = ncap;
+    return PF_OK;
+}
+
+// history < 0: make room for the generations [steps, need).  Dense (sharded) log: rows double, the old generations are
+// copied over.  Arena: prune the dead lineages when the arena is full, grow it (up to the budget) when that is not enough.
 static int32_t ensure_history(pf_handle h, long long need)
 {
-    if (!h->hist_auto || need <= h->hist_cap) return PF_OK;
+    if (!h->hist_auto) return PF_OK;
+    if (h->arena) {
+        const long long rows = need - h->steps;
+        if (rows <= 0) return PF_OK;
+        const long long want = rows * h->cap;
+        if (h->arena_used + want > h->arena_cap && h->steps - h->last_prune_step >= 4) {
+            int32_t rc = prune_genealogy(h);
+            if (rc != PF_OK) return rc;
+        }
+        int32_t rc2 = arena_reserve(h, want);
+        if (rc2 != PF_OK) return rc2;
+        h->gen_off.resize(need); h->gen_n.resize(need);
+        for (long long t = h->steps; t < need; t++) { h->gen_off[t] = h->arena_used; h->gen_n[t] = h->cap; h->arena_used += h->cap; }
+        return PF_OK;
+    }
+    if (need <= h->hist_cap) return PF_OK;
     long long ncap = std::max<long long>(std::max<long long>(need, 2 * h->hist_cap), 16);
     unsigned int *na = nullptr; unsigned char *ns = nullptr;
     cudaError_t e = dmalloc(&na, (size_t)ncap * h->cap);
@@ -956,6 +1109,12 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
     collect_profile(h);
     h->last = h->logs.back(); h->have_last = true;
     h->n_host = h->last.n_out;
+    if (h->arena) {
+        // the generations of this call were appended at a stride of `cap`; their true lengths are known now, and what the
+        // last one left unused goes back to the arena
+        for (long long t = 0; t < T; t++) h->gen_n[steps0 + t] = h->logs[t].n_out;
+        h->arena_used = h->gen_off[steps0 + T - 1] + h->gen_n[steps0 + T - 1];
+    }
     if (!fh) {
         ClState cs;
         CUDA_TRY(cudaMemcpy(&cs, h->cl, sizeof cs, cudaMemcpyDeviceToHost));
@@ -970,16 +1129,33 @@ extern "C" int32_t pf_step(pf_handle h, const double *y, const double *uniforms,
     return run_steps(h, y, 1, uniforms, n_uniforms, nullptr);
 }
 
+// Arena mode: a call's generations are appended densely before they can be pruned, so a long stream is filtered in
+// chunks whose rows fit in half the genealogy budget (the pipelining of the steps only breaks at the chunk boundaries)
+static int32_t run_chunked(pf_handle h, const double *ys, long long T, const double *uniforms, long long ups, double *log_evidence,
+                           const int32_t *labels)
+{
+    if (!h) return PF_ERR_ARG;
+    if (!h->arena || T <= 0) return run_steps(h, ys, T, uniforms, ups, log_evidence, labels);
+    const long long chunk = std::max<long long>(4, h->arena_budget / (2 * h->cap));
+    for (long long t0 = 0; t0 < T; t0 += chunk) {
+        const long long n = std::min(chunk, T - t0);
+        int32_t rc = run_steps(h, ys + t0 * h->d, n, uniforms ? uniforms + t0 * ups : nullptr, ups, log_evidence ? log_evidence + t0 : nullptr,
+                               labels ? labels + t0 : nullptr);
+        if (rc != PF_OK) return rc;
+    }
+    return PF_OK;
+}
+
 extern "C" int32_t pf_filter(pf_handle h, const double *ys, int64_t T, const double *uniforms, int64_t uniforms_per_step,
                              double *log_evidence)
 {
-    return run_steps(h, ys, T, uniforms, uniforms_per_step, log_evidence);
+    return run_chunked(h, ys, T, uniforms, uniforms_per_step, log_evidence, nullptr);
 }
 
 extern "C" int32_t pf_filter_labeled(pf_handle h, const double *ys, const int32_t *labels, int64_t T, const double *uniforms,
                                      int64_t uniforms_per_step, double *log_evidence)
 {
-    return run_steps(h, ys, T, uniforms, uniforms_per_step, log_evidence, labels);
+    return run_chunked(h, ys, T, uniforms, uniforms_per_step, log_evidence, labels);
 }
 
 extern "C" int32_t pf_get_stateprior(pf_handle h, int64_t i, double *N, double *Nsame, int32_t *last)
@@ -1083,12 +1259,6 @@ extern "C" int32_t pf_get_particle(pf_handle h, int64_t i, int32_t *K_out, doubl
     return PF_OK;
 }
 
-struct DevBuf {                  // scoped device allocation
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    template <typename T> T *as() { return static_cast<T *>(p); }
-};
 
 // assignments(ps), src/filters.jl:26-34: the genealogy is walked on the device into a byte-wide time-major block for
 // a slice of the particles at a time (k_backtrack8), the slices are widened / transposed on the host
@@ -1109,12 +1279,14 @@ extern "C" int32_t pf_get_assignments(pf_handle h, int32_t *out)
     if (T == 0 || n == 0) return PF_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const long long nc_max = assign_chunk(T, n);
+    const long long *goff = nullptr;
+    { int32_t rc = upload_gen_off(h, &goff); if (rc != PF_OK) return rc; }
     unsigned char *tmp = nullptr;
     CUDA_TRY(dmalloc(&tmp, (size_t)T * nc_max));
     std::vector<unsigned char> host((size_t)T * nc_max);
     for (long long i0 = 0; i0 < n; i0 += nc_max) {
         const long long nc = std::min(nc_max, n - i0);
-        k_backtrack8<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i0, nc, tmp);
+        k_backtrack8<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i0, nc, tmp, goff);
         cudaError_t e = cudaMemcpyAsync(host.data(), tmp, (size_t)T * nc, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { cudaFree(tmp); return set_cuda_error(h, e, "pf_get_assignments", __LINE__); }
@@ -1138,11 +1310,23 @@ extern "C" int32_t pf_get_particle_assignments(pf_handle h, int64_t i, int32_t *
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     DevBuf tmp;
     CUDA_TRY(tmp.alloc((size_t)T));
-    k_backtrack8<<<1, 32, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i, 1, tmp.as<unsigned char>());
+    const long long *goff = nullptr;
+    { int32_t rc = upload_gen_off(h, &goff); if (rc != PF_OK) return rc; }
+    k_backtrack8<<<1, 32, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i, 1, tmp.as<unsigned char>(), goff);
     std::vector<unsigned char> host((size_t)T);
     CUDA_TRY(cudaMemcpyAsync(host.data(), tmp.p, (size_t)T, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (long long t = 0; t < T; t++) out[t] = host[t];
+    return PF_OK;
+}
+
+extern "C" int32_t pf_genealogy_info(pf_handle h, int64_t *out /* [4] */)
+{
+    if (!h || !out) return PF_ERR_ARG;
+    long long nodes = 0;
+    if (h->arena) for (long long t = 0; t < h->steps; t++) nodes += h->gen_n[t];
+    else if (h->hist_cap) nodes = h->steps * h->cap;
+    out[0] = h->hist_cap ? h->steps : 0; out[1] = nodes; out[2] = h->arena ? h->arena_cap : (h->hist_cap ? h->hist_cap * h->cap : 0); out[3] = h->n_prunes;
     return PF_OK;
 }
 
@@ -1192,7 +1376,7 @@ extern "C" int32_t pf_get_last_ancestors(pf_handle h, int32_t *out)
     if (!h->hist_cap || h->steps == 0) return set_error(h, PF_ERR_HISTORY, "pf_get_last_ancestors: needs history >= 1 and one step");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     static_assert(sizeof(int32_t) == sizeof(unsigned int), "");
-    CUDA_TRY(cudaMemcpyAsync(out, h->gen_anc + (size_t)(h->steps - 1) * h->cap, sizeof(int) * h->n_host, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(out, h->gen_anc + gen_row(h, h->steps - 1), sizeof(int) * h->n_host, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PF_OK;
 }
@@ -1203,7 +1387,7 @@ extern "C" int32_t pf_get_last_assignments(pf_handle h, int32_t *out)
     if (!h->hist_cap || h->steps == 0) return set_error(h, PF_ERR_HISTORY, "pf_get_last_assignments: needs history >= 1 and one step");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     std::vector<unsigned char> a(h->n_host);
-    CUDA_TRY(cudaMemcpyAsync(a.data(), h->gen_asg + (size_t)(h->steps - 1) * h->cap, h->n_host, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(a.data(), h->gen_asg + gen_row(h, h->steps - 1), h->n_host, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (long long i = 0; i < h->n_host; i++) out[i] = a[i];
     return PF_OK;
@@ -1314,6 +1498,8 @@ static int32_t similarity_counts(pf_handle h, std::vector<unsigned long long> &c
     if (T == 0) return PF_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const long long nc_max = assign_chunk(T, n);
+    const long long *goff = nullptr;
+    { int32_t rc = upload_gen_off(h, &goff); if (rc != PF_OK) return rc; }
     DevBuf dA, dC;
     CUDA_TRY(dA.alloc((size_t)T * nc_max));
     CUDA_TRY(dC.alloc(sizeof(unsigned long long) * T * T));
@@ -1322,7 +1508,7 @@ static int32_t similarity_counts(pf_handle h, std::vector<unsigned long long> &c
     if (npair > 0x7fffffffll) return set_error(h, PF_ERR_ARG, "assignment_similarity: too many observations");
     for (long long i0 = 0; i0 < n; i0 += nc_max) {
         const long long nc = std::min(nc_max, n - i0);
-        k_backtrack8<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i0, nc, dA.as<unsigned char>());
+        k_backtrack8<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->gen_anc, h->gen_asg, h->cap, T, i0, nc, dA.as<unsigned char>(), goff);
         long long gy = std::max<long long>(1, std::min<long long>((nc / 16 + SUM_THREADS * 4 - 1) / (SUM_THREADS * 4), 4096));
         if (npair * gy < 2 * h->num_sms) gy = std::min<long long>((2 * h->num_sms + npair - 1) / npair, std::max<long long>(1, (nc + SUM_THREADS - 1) / SUM_THREADS));
         k_similarity<<<dim3((unsigned)npair, (unsigned)gy), SUM_THREADS, 0, h->stream>>>(dA.as<unsigned char>(), T, nc, dC.as<unsigned long long>());
@@ -1380,7 +1566,7 @@ extern "C" int32_t pf_randindex(pf_handle h, const int32_t *truth, int64_t T, in
 // The population (live slots only), the control blocks, the genealogy and the host mirrors of a single-GPU handle
 // go to one file; pf_load builds a handle that continues bit for bit (same seed and step counter => same device
 // uniforms).  Layout: header, pf_config + prior arrays, mirrors, device control blocks, arrays.
-static const char CKPT_MAGIC[8] = {'P', 'F', 'B', '2', '0', '0', 'C', '2'};
+static const char CKPT_MAGIC[8] = {'P', 'F', 'B', '2', '0', '0', 'C', '3'};
 struct CkptHeader {
     char magic[8];
     uint32_t sz_cfg, sz_st, sz_res, sz_sc, sz_cl, sz_log;
@@ -1448,8 +1634,11 @@ extern "C" int32_t pf_save(pf_handle h, const char *path)
         for (long long r = 0; ok && r < max_k; r++) ok = dump_dev(f, h->sp[cur].N + r * cap, sizeof(double) * n, stage) && dump_dev(f, h->sp[cur].Nsame + r * cap, sizeof(double) * n, stage);
         ok = ok && dump_dev(f, h->sp[cur].last, sizeof(int) * n, stage);
     }
-    for (long long t = 0; ok && t < hd.hist_rows; t++)
-        ok = dump_dev(f, h->gen_anc + t * cap, sizeof(unsigned int) * cap, stage) && dump_dev(f, h->gen_asg + t * cap, (size_t)cap, stage);
+    for (long long t = 0; ok && t < hd.hist_rows; t++) {          // every generation with its own length (pruned arena) or `cap` (dense log)
+        const int64_t nt = h->arena ? h->gen_n[t] : cap;
+        ok = fwrite(&nt, sizeof nt, 1, f) == 1 && dump_dev(f, h->gen_anc + gen_row(h, t), sizeof(unsigned int) * nt, stage) &&
+             dump_dev(f, h->gen_asg + gen_row(h, t), (size_t)nt, stage);
+    }
     ok = (fclose(f) == 0) && ok;
     if (!ok) { cudaGetLastError(); return set_error(h, PF_ERR_STATE, std::string("pf_save: write to ") + path + " failed"); }
     return PF_OK;
@@ -1487,7 +1676,7 @@ extern "C" int32_t pf_load(const char *path, int32_t device, pf_handle *out)
     h->steps = hd.steps; h->n_host = hd.n_host; h->ub_live = hd.ub_live; h->cur = hd.cur; h->epoch = (unsigned int)hd.epoch;
     h->last = last; h->have_last = hd.have_last != 0;
     if (ensure_table(h, h->steps + 4096) != PF_OK) return fail("pf_load: table allocation failed");
-    if (hd.has_hist && ensure_history(h, hd.steps) != PF_OK) return fail("pf_load: the genealogy does not fit in device memory");
+    if (hd.has_hist && !h->arena && ensure_history(h, hd.steps) != PF_OK) return fail("pf_load: the genealogy does not fit in device memory");
     std::vector<char> stage((size_t)64 << 20);
     const long long n = hd.n_host, cap = hd.cap;
     const int cur = hd.cur;
@@ -1500,8 +1689,15 @@ extern "C" int32_t pf_load(const char *path, int32_t device, pf_handle *out)
         ok = ok && load_dev(f, h->sp[cur].last, sizeof(int) * n, stage);
     }
     if (hd.has_hist && h->hist_cap < hd.hist_rows) ok = false;
-    for (long long t = 0; ok && hd.has_hist && t < hd.hist_rows; t++)
-        ok = load_dev(f, h->gen_anc + t * cap, sizeof(unsigned int) * cap, stage) && load_dev(f, h->gen_asg + t * cap, (size_t)cap, stage);
+    for (long long t = 0; ok && hd.has_hist && t < hd.hist_rows; t++) {
+        int64_t nt = 0;
+        ok = fread(&nt, sizeof nt, 1, f) == 1 && nt >= 0 && nt <= cap;
+        if (ok && h->arena) {
+            ok = arena_reserve(h, nt) == PF_OK;
+            if (ok) { h->gen_off.push_back(h->arena_used); h->gen_n.push_back(nt); h->arena_used += nt; }
+        } else if (ok && nt != cap) ok = false;
+        ok = ok && load_dev(f, h->gen_anc + gen_row(h, t), sizeof(unsigned int) * nt, stage) && load_dev(f, h->gen_asg + gen_row(h, t), (size_t)nt, stage);
+    }
     if (!ok) return fail("pf_load: truncated checkpoint or device copy failed");
     fclose(f);
     *out = h;

@@ -180,17 +180,56 @@ __global__ void __launch_bounds__(SUM_THREADS) k_pop_summary(const R *__restrict
 
 // assignments as bytes, time-major: out8[t * nc + (i - i0)] = label (0-based) of observation t in particle i,
 // for the particles [i0, i0 + nc) (assignments(p), src/particle.jl:25-32)
+// off == NULL: dense log, generation t at t * cap; else generation t at off[t] (pruned arena: the stored nodes of a
+// generation are the ancestors of the current population, renumbered densely)
 __global__ void k_backtrack8(const unsigned int *__restrict__ gen_anc, const unsigned char *__restrict__ gen_asg, long long cap,
-                             long long T, long long i0, long long nc, unsigned char *__restrict__ out8)
+                             long long T, long long i0, long long nc, unsigned char *__restrict__ out8,
+                             const long long *__restrict__ off = nullptr)
 {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
     long long k = i0 + c;
     for (long long t = T - 1; t >= 0; t--) {
         PF_ASSERT(k >= 0 && k < cap);
-        out8[t * nc + c] = gen_asg[t * cap + k];
-        k = gen_anc[t * cap + k];
+        const long long o = off ? off[t] : t * cap;
+        out8[t * nc + c] = gen_asg[o + k];
+        k = gen_anc[o + k];
     }
+}
+
+// ------------------------------------------------------------------ genealogy pruning
+// The reference's ancestor chain (src/particle.jl:25-32) is an implicit tree pruned by the garbage collector: a
+// particle that leaves no descendant in the current population disappears with its history.  The device log does the
+// same explicitly: from the newest generation backwards, the nodes of generation g - 1 that are still an ancestor of
+// somebody are marked, renumbered densely (exclusive scan of the marks), compacted, and the parent indices of
+// generation g are rewritten to the new numbering.  Coalescence makes the live history O(N log T) nodes instead of N T.
+__global__ void k_gen_mark(const unsigned int *__restrict__ anc, const long long *__restrict__ n_ptr, unsigned int *__restrict__ mark)
+{
+    const long long n = *n_ptr;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) mark[anc[k]] = 1u;
+}
+__global__ void k_gen_count(const unsigned int *__restrict__ mark, const unsigned int *__restrict__ idx, long long n_old, long long *n_new)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    *n_new = n_old > 0 ? (long long)idx[n_old - 1] + mark[n_old - 1] : 0;
+}
+__global__ void k_gen_compact(const unsigned int *__restrict__ anc, const unsigned char *__restrict__ asg, long long n_old,
+                              const unsigned int *__restrict__ mark, const unsigned int *__restrict__ idx,
+                              unsigned int *__restrict__ tmp_anc, unsigned char *__restrict__ tmp_asg)
+{
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_old; j += (long long)gridDim.x * blockDim.x)
+        if (mark[j]) { tmp_anc[idx[j]] = anc[j]; tmp_asg[idx[j]] = asg[j]; }
+}
+__global__ void k_gen_copy(const unsigned int *__restrict__ src_anc, const unsigned char *__restrict__ src_asg,
+                           const long long *__restrict__ n_ptr, unsigned int *__restrict__ anc, unsigned char *__restrict__ asg)
+{
+    const long long n = *n_ptr;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) { anc[j] = src_anc[j]; asg[j] = src_asg[j]; }
+}
+__global__ void k_gen_rewrite(unsigned int *__restrict__ anc, const long long *__restrict__ n_ptr, const unsigned int *__restrict__ idx)
+{
+    const long long n = *n_ptr;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) anc[k] = idx[anc[k]];
 }
 
 // assignment_similarity(ps) (src/filters.jl:39-42): sim[s, t] = 1 - Hamming(A[s, :], A[t, :]) / n, i.e. the fraction of

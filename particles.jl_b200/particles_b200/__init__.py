@@ -435,6 +435,12 @@ class ParticleFilter:
         _lib.check(self._L.pf_get_particle_assignments(self._h, int(i), out.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
         return out.astype(np.int64) + 1
 
+    def genealogy_info(self):
+        """{generations, nodes, capacity, prunes} of the genealogy log (pf_genealogy_info)."""
+        out = (C.c_int64 * 4)()
+        _lib.check(self._L.pf_genealogy_info(self._h, out), self._h)
+        return dict(zip(("generations", "nodes", "capacity", "prunes"), (int(x) for x in out)))
+
     def last_step(self):
         s = pf_step_stats()
         _lib.check(self._L.pf_get_last_step(self._h, C.byref(s)), self._h)

@@ -64,6 +64,7 @@ SYMBOLS = [
     ("pf_get_particle", C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), _dp, _dp, _dp, _dp]),
     ("pf_get_assignments", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     ("pf_get_particle_assignments", C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
+    ("pf_genealogy_info", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("pf_get_last_step", C.c_int32, [C.c_void_p, C.POINTER(pf_step_stats)]),
     ("pf_posterior_predictive", C.c_int32, [C.c_void_p, _dp, C.c_int64, _dp]),
     ("pf_weighted_mean", C.c_int32, [C.c_void_p, C.c_int32, _dp]),
