@@ -1199,10 +1199,21 @@ __global__ void __launch_bounds__(256) k_count_next(const StepState *__restrict_
     if (guard->halt) return;
     const long long n = ro ? ro->n_local : st->n_live;      // (sharded: the survivors this rank produced)
     unsigned int c = 0;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const int K = Kc[surv_parent[t]];
-        const int Kn = K + (((int)(surv_slot[t] & 0x7F) == K) ? 1 : 0);
-        c += (unsigned int)(Kn + (Kn < k_max ? 1 : 0));
+    // four independent (list, gather) chains per thread in flight
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < n; t0 += 4 * nth) {
+        unsigned int par[4]; unsigned char sl[4]; int K[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const long long t = t0 + k * nth; par[k] = t < n ? surv_parent[t] : 0u; sl[k] = t < n ? surv_slot[t] : 0; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) K[k] = (t0 + k * nth < n) ? Kc[par[k]] : 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (t0 + k * nth < n) {
+                const int Kn = K[k] + (((int)(sl[k] & 0x7F) == K[k]) ? 1 : 0);
+                c += (unsigned int)(Kn + (Kn < k_max ? 1 : 0));
+            }
+        }
     }
     c = __reduce_add_sync(0xffffffffu, c);
     __shared__ unsigned int s_c[8];

@@ -706,7 +706,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         {
             LaunchTimer lt(h, KC_PRESTEP, 2);
             k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_next, h->stc_alt, 3, h->sc, h->res, nullptr, 0, h->steps, -1);
-            k_count_next<<<std::min(grid_for(ub_next, 256), h->num_sms * 8), 256, 0, h->stream>>>(h->st, h->Kc[cur], h->surv_parent, h->surv_slot, h->k_max,
+            k_count_next<<<std::min(grid_for(ub_next, 1024), h->num_sms * 16), 256, 0, h->stream>>>(h->st, h->Kc[cur], h->surv_parent, h->surv_slot, h->k_max,
                                                                                                  &h->st->M_pred, h->sc);
         }
         InstArgs ia{};
@@ -1074,7 +1074,22 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
                 }
                 DISPATCH_D(d, rc = chenliu_step<D, R>(h, h->ys_dev + t * d, ud, h->slog + t));
             }
-            if (rc != PF_OK) { cudaStreamSynchronize(h->stream); return rc; }
+            if (rc != PF_OK) {
+                // an error while queuing observation t (e.g. the fixed history is exhausted): the observations queued before
+                // it have run; bring the host mirrors in line with the device before reporting
+                cudaStreamSynchronize(h->stream);
+                const long long done = h->steps - steps0;
+                if (done > 0) {
+                    h->logs.resize(done);
+                    if (cudaMemcpy(h->logs.data(), h->slog, sizeof(StepLog) * done, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                        h->last = h->logs.back(); h->have_last = true; h->n_host = h->last.n_out;
+                        if (h->arena) for (long long k = 0; k < done; k++) h->gen_n[steps0 + k] = h->logs[k].n_out;
+                        if (log_evidence) for (long long k = 0; k < done; k++) log_evidence[k] = h->logs[k].log_total;
+                    }
+                    if (!fh) { ClState cs; if (cudaMemcpy(&cs, h->cl, sizeof cs, cudaMemcpyDeviceToHost) == cudaSuccess) h->cur = cs.cur; }
+                }
+                return rc;
+            }
         }
         long long halt[2] = {0, 0};
         if (fh) CUDA_TRY(cudaMemcpyAsync(halt, &h->sc->halt, sizeof halt, cudaMemcpyDeviceToHost, h->stream));
@@ -2111,7 +2126,7 @@ static int32_t mg_tail(pf_handle h, int phase, StepLog *log_dev, const double *y
         h->steps++;                                   // the host mirrors now describe the next step; h->cur still names the parents' store
         LaunchTimer lt(h, KC_PRESTEP, 2);
         k_prestep<D><<<1, 32, 0, h->stream>>>(h->st, h->pc, y_next, h->stc_alt, 3, h->sc, h->res, nullptr, 0, h->steps, -1);
-        k_count_next<<<std::min(grid_for(cap, 256), h->num_sms * 8), 256, 0, h->stream>>>(h->st, h->Kc[h->cur], h->surv_parent, h->surv_slot, h->k_max,
+        k_count_next<<<std::min(grid_for(cap, 1024), h->num_sms * 16), 256, 0, h->stream>>>(h->st, h->Kc[h->cur], h->surv_parent, h->surv_slot, h->k_max,
                                                                                           &h->st->M_pred, h->sc, h->ro);
     }
     const int cur = h->cur, nxt = cur ^ 1;

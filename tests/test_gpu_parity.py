@@ -381,3 +381,23 @@ def test_pipelined_filter_equals_stepwise(d, N, T, monkeypatch):
     monkeypatch.setenv("PF_NO_PIPELINE", "1")
     ps, le = run("one_call")
     assert np.array_equal(le, le_ref) and np.array_equal(ps.assignments(), ref.assignments())
+
+
+def test_history_exhausted_mid_call_leaves_a_consistent_filter():
+    """A fixed genealogy capacity that runs out in the middle of a pf_filter call: the error is PF_ERR_HISTORY, the
+    observations before it have been filtered, and every read-out describes that state (stale host mirrors)."""
+    rng = np.random.default_rng(8)
+    T, cap_hist = 30, 17
+    ys, us = _mixture_nd(rng, T, 2, 4), rng.random(T)
+    pprior, _ = _priors("niw", 2)
+    crp = pb.ChineseRestaurantProcess(1.0)
+    ps = pb.FearnheadParticles(2000, pprior, crp, history=cap_hist, k_max=40)
+    with pytest.raises(pb.PFError) as e:
+        ps.filter_(ys, uniforms=us)
+    assert e.value.code == 4
+    ref = pb.FearnheadParticles(2000, pprior, crp, history=cap_hist, k_max=40)
+    ref.filter_(ys[:cap_hist], uniforms=us[:cap_hist])
+    assert ps.n_steps == cap_hist and len(ps) == len(ref)
+    assert np.array_equal(ps.logweights(), ref.logweights())
+    assert np.array_equal(ps.assignments(), ref.assignments())
+    assert ps.last_step()["n_out"] == ref.last_step()["n_out"]
