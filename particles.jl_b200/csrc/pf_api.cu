@@ -887,8 +887,20 @@ static int32_t prune_genealogy(pf_handle h)
     long long *n_dev = dn.as<long long>();
     unsigned int *mark = dmark.as<unsigned int>(), *idx = didx.as<unsigned int>(), *part = dpart.as<unsigned int>();
     const int gmax = h->num_sms * 8;
+    DevBuf doff;
+    CUDA_TRY(doff.alloc(sizeof(long long) * G));
+    CUDA_TRY(cudaMemcpyAsync(doff.p, h->gen_off.data(), sizeof(long long) * G, cudaMemcpyHostToDevice, h->stream));
     for (long long g = G - 1; g >= 1; g--) {
         const long long p = g - 1, np_old = h->gen_n[p], ng_old = h->gen_n[g];
+        if (ng_old <= GEN_SMALL) {
+            // the stored nodes only get fewer with age: from here on every generation is short -- one launch for the rest
+            bool monotone = true;
+            for (long long q = 0; q < g && monotone; q++) monotone = h->gen_n[q] <= GEN_SMALL;
+            if (monotone) {
+                k_gen_prune_small<<<1, 1024, 0, h->stream>>>(h->gen_anc, h->gen_asg, doff.as<long long>(), n_dev, g);
+                break;
+            }
+        }
         if (np_old == 0 || ng_old == 0) continue;
         unsigned int *anc_g = h->gen_anc + h->gen_off[g];
         unsigned int *anc_p = h->gen_anc + h->gen_off[p];

@@ -232,6 +232,65 @@ __global__ void k_gen_rewrite(unsigned int *__restrict__ anc, const long long *_
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) anc[k] = idx[anc[k]];
 }
 
+// The same pass for a RUN of short generations (<= GEN_SMALL stored nodes each: all the old ones, since the live nodes
+// only get fewer with age) in ONE launch: one block walks the generations g_hi, g_hi - 1, ..., 1 with the marks, their
+// prefix and the compacted rows in shared memory.  n[] holds the old lengths on entry and the new ones on return.
+#define GEN_SMALL 4096
+__global__ void __launch_bounds__(1024) k_gen_prune_small(unsigned int *__restrict__ gen_anc, unsigned char *__restrict__ gen_asg,
+                                                          const long long *__restrict__ off, long long *__restrict__ n, long long g_hi)
+{
+    __shared__ unsigned int s_idx[GEN_SMALL];          // (exclusive prefix << 1) | mark
+    __shared__ unsigned int s_anc[GEN_SMALL];
+    __shared__ unsigned char s_asg[GEN_SMALL];
+    __shared__ unsigned int s_w[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int PER = GEN_SMALL / 1024;
+    for (long long g = g_hi; g >= 1; g--) {
+        const long long p = g - 1;
+        const int ng = (int)n[g], np_old = (int)n[p];
+        unsigned int *anc_g = gen_anc + off[g];
+        unsigned int *anc_p = gen_anc + off[p];
+        unsigned char *asg_p = gen_asg + off[p];
+        for (int j = tid; j < np_old; j += 1024) s_idx[j] = 0u;
+        __syncthreads();
+        for (int k = tid; k < ng; k += 1024) s_idx[anc_g[k]] = 1u;
+        __syncthreads();
+        unsigned int m[PER], loc = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { const int j = tid * PER + k; m[k] = j < np_old ? s_idx[j] : 0u; loc += m[k]; }
+        unsigned int inc = loc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int w = s_w[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
+            s_w[lane] = wi - w;
+            if (lane == 31) s_w[32] = wi;
+        }
+        __syncthreads();
+        unsigned int run = s_w[wid] + inc - loc;
+        const int np_new = (int)s_w[32];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int j = tid * PER + k;
+            if (j < np_old) {
+                s_idx[j] = (run << 1) | m[k];
+                if (m[k]) { s_anc[run] = anc_p[j]; s_asg[run] = asg_p[j]; }
+                run += m[k];
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < np_new; j += 1024) { anc_p[j] = s_anc[j]; asg_p[j] = s_asg[j]; }
+        for (int k = tid; k < ng; k += 1024) anc_g[k] = s_idx[anc_g[k]] >> 1;
+        __syncthreads();
+        if (tid == 0) n[p] = np_new;
+        __syncthreads();
+    }
+}
+
 // assignment_similarity(ps) (src/filters.jl:39-42): sim[s, t] = 1 - Hamming(A[s, :], A[t, :]) / n, i.e. the fraction of
 // particles that give observations s and t the same label.  counts[s * T + t] accumulates the number of agreeing
 // particles (integer atomics: order-free).  A block owns a tile of SIM_TILE x SIM_TILE observation pairs and a slice of
