@@ -978,7 +978,9 @@ static int32_t ensure_history(pf_handle h, long long need)
         const long long rows = need - h->steps;
         if (rows <= 0) return PF_OK;
         const long long want = rows * h->cap;
-        if (h->arena_used + want > h->arena_cap && h->steps - h->last_prune_step >= 4) {
+        // (a pruning pass walks every stored generation: passes are spaced geometrically -- at least steps / 8 observations
+        // apart -- so that their total cost stays O(T log T) whatever the budget; in between, the arena grows instead)
+        if (h->arena_used + want > h->arena_cap && h->steps - h->last_prune_step >= std::max<long long>(4, h->steps / 8)) {
             int32_t rc = prune_genealogy(h);
             if (rc != PF_OK) return rc;
         }

