@@ -185,6 +185,9 @@ struct InstArgs {
     int vnext;                             // which of the two V buffers receives the next observation's putatives
     long long gen_off;                     // offset of this generation's row in the genealogy arrays
     long long vb0;                         // STRIDED launch: first tile (= number of tiles the main launch covered)
+    // the two observations and the prior mean BY VALUE: kernel parameters live in the constant bank and are used as
+    // operands directly, which frees the registers the fused kernel would otherwise spend on copies of them
+    double yc[PF_MAX_D], y_prev[PF_MAX_D], mu0c[PF_MAX_D];
 };
 #ifndef PF_INSTEXP_MINBLOCKS
 #define PF_INSTEXP_MINBLOCKS 3
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
     if (i >= 0 && i < n_live) {
         double y[D], mu0[D];
 #pragma unroll
-        for (int k = 0; k < D; k++) { y[k] = scp->y[k]; mu0[k] = pc->mu0[k]; }
+        for (int k = 0; k < D; k++) { y[k] = INST ? ia.yc[k] : scp->y[k]; mu0[k] = INST ? ia.mu0c[k] : pc->mu0[k]; }
         long long src = i;                   // the particle whose slots are read
         int jsel = -1;                       // INST: the slot that receives the previous observation
         int K; double lw0;
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
                 if (j == jsel) {
                     double yp[D];
 #pragma unroll
-                    for (int k = 0; k < D; k++) yp[k] = ia.scp_prev->y[k];
+                    for (int k = 0; k < D; k++) yp[k] = ia.y_prev[k];
                     slot_add<D>(fcur, tab[(int)fcur[L::F_N]], yp, mu0);
 #pragma unroll
                     for (int f = 0; f < L::F; f++) fcur[f] = (double)(R)fcur[f];      // what the stored child holds (no-op for R = double)

@@ -579,7 +579,7 @@ static int32_t launch_classic_search(pf_handle h, SelArgs a)
 // with the next expansion), else null
 template <int D, typename R>
 static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_dev, StepLog *log_dev,
-                              const double *y_next = nullptr, const double *u_next = nullptr)
+                              const double *y_next = nullptr, const double *u_next = nullptr, const double *y_host = nullptr)
 {
     const long long cap = h->cap;
     const int cur = h->cur, nxt = cur ^ 1;
@@ -694,7 +694,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
                                                             h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr, nullptr}, h->sc);
     }
-    if (fused && y_next && h->pipeline) {
+    if (fused && y_next && y_host && h->pipeline) {
         // pipelined tail: close this step's record, then build the children WHILE expanding them for the next observation
         {
             LaunchTimer lt(h, KC_STEPLOG);
@@ -712,6 +712,7 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         InstArgs ia{};
         ia.surv_parent = h->surv_parent; ia.surv_slot = h->surv_slot; ia.V_prev = h->V; ia.scp_prev = h->stc;
         ia.S2 = h->S[nxt]; ia.Kc2 = h->Kc[nxt]; ia.logw2 = h->logw[nxt]; ia.gen_anc = ga; ia.gen_asg = gs;
+        for (int k = 0; k < h->d; k++) { ia.y_prev[k] = y_host[k]; ia.yc[k] = y_host[h->d + k]; ia.mu0c[k] = h->mu0[k]; }
         {
             LaunchTimer lt(h, KC_SELECT, 2);
             const long long ns = 4 * ((ub_next + 4 * h->fuse_stride - 1) / (4 * h->fuse_stride));
@@ -1078,7 +1079,7 @@ static int32_t run_steps(pf_handle h, const double *ys, long long T, const doubl
                 const bool next_ok = h->pipeline && t + 1 < T && !(labels && (labels[t] >= 0 || labels[t + 1] >= 0)) &&
                                      (!h->hist_cap || h->steps + 1 < h->hist_cap);
                 DISPATCH_D(d, rc = fearnhead_step<D, R>(h, h->ys_dev + t * d, h->u_dev + t, h->slog + t,
-                                                     next_ok ? h->ys_dev + (t + 1) * d : nullptr, next_ok ? h->u_dev + t + 1 : nullptr));
+                                                     next_ok ? h->ys_dev + (t + 1) * d : nullptr, next_ok ? h->u_dev + t + 1 : nullptr, ys + t * d));
                 h->redo = 0; h->retries = SEL_RETRIES; h->cur_label = -1;
             } else {
                 const double *ud = nullptr;
@@ -2129,7 +2130,8 @@ static int32_t mg_stage_d(pf_handle h, StepLog *log_dev)
 //   3  instantiate + expansion + classification of every child this rank produced, each delivered with its putatives
 //      and scan record to its new owner; "generation delivered"
 template <int D, typename R>
-static int32_t mg_tail(pf_handle h, int phase, StepLog *log_dev, const double *y_next, const double *u_next, int search_stage)
+static int32_t mg_tail(pf_handle h, int phase, StepLog *log_dev, const double *y_next, const double *u_next, int search_stage,
+                       const double *y_host /* this observation and the next */)
 {
     const long long cap = h->cap;
     if (phase == 1) {
@@ -2150,6 +2152,7 @@ static int32_t mg_tail(pf_handle h, int phase, StepLog *log_dev, const double *y
     ia.gen_off = (long long)(h->steps - 1) * cap;
     if (h->hist_cap) { ia.gen_anc = h->gen_anc + ia.gen_off; ia.gen_asg = h->gen_asg + ia.gen_off; }
     ia.ro = h->ro; ia.peers = h->peers[nxt]; ia.vnext = h->vcur ^ 1;
+    for (int k = 0; k < h->d; k++) { ia.y_prev[k] = y_host[k]; ia.yc[k] = y_host[h->d + k]; ia.mu0c[k] = h->mu0[k]; }
     if (phase == 1 || phase == 2) {
         LaunchTimer lt(h, KC_SELECT, phase == 1 ? 2 : 1);
         if (phase == 1) {
@@ -2285,12 +2288,12 @@ extern "C" int32_t pf_mg_filter(pf_handle *hs, int32_t n_local, const double *ys
         const bool next_ok = hs[0]->pipeline_mg && t + 1 < T;
         if (next_ok) {
             if (lockstep) {
-                FOR_SHARDS((mg_tail<D, R>(h, 1, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, SEL_ST_PUB)));
-                FOR_SHARDS((mg_tail<D, R>(h, 2, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, SEL_ST_RUN)));
+                FOR_SHARDS((mg_tail<D, R>(h, 1, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, SEL_ST_PUB, ys + t * d)));
+                FOR_SHARDS((mg_tail<D, R>(h, 2, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, SEL_ST_RUN, ys + t * d)));
             } else {
-                FOR_SHARDS((mg_tail<D, R>(h, 1, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, both)));
+                FOR_SHARDS((mg_tail<D, R>(h, 1, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, both, ys + t * d)));
             }
-            FOR_SHARDS((mg_tail<D, R>(h, 3, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, both)));
+            FOR_SHARDS((mg_tail<D, R>(h, 3, h->slog + t, h->ys_dev + (t + 1) * d, h->u_dev + t + 1, both, ys + t * d)));
         } else {
             FOR_SHARDS((mg_stage_d<D, R>(h, h->slog + t)));
         }

@@ -11,10 +11,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "particles.jl_b200", "libparticles_b200.so")
 KERNELS = {
-    "k_expand<2,2,INST,double> (instantiate + next expansion)": r"k_expandILi2ELi2ELb1EdLb0EE",
-    "k_expand<2,2,INST,float> (PF_F32)": r"k_expandILi2ELi2ELb1EfLb0EE",
-    "k_expand<2,2,INST,double,REMOTE> (sharded: children delivered to their new owners)": r"k_expandILi2ELi2ELb1EdLb1EE",
-    "k_expand<2,2,false,double> (expansion from the store)": r"k_expandILi2ELi2ELb0EdLb0EE",
+    "k_expand<2,2,INST,double> (instantiate + next expansion)": r"k_expandILi2ELi2ELb1EdLb0ELb0EE",
+    "k_expand<2,2,INST,float> (PF_F32)": r"k_expandILi2ELi2ELb1EfLb0ELb0EE",
+    "k_expand<2,2,INST,double,REMOTE> (sharded: children delivered to their new owners)": r"k_expandILi2ELi2ELb1EdLb1ELb0EE",
+    "k_expand<2,2,false,double> (expansion from the store)": r"k_expandILi2ELi2ELb0EdLb0ELb0EE",
     "k_instantiate<2,double>": r"k_instantiateILi2EdE",
     "k_scan_apply": r"k_scan_apply",
     "k_sel_bracket": r"k_sel_bracket",

@@ -1,7 +1,9 @@
 /* abi_smoke.c -- drives libparticles_b200.so exactly as the Julia `ccall`s of
- * particles.jl_b200/julia/particles_b200.jl do (plain C, no Python, no torch):
+ * particles.jl_b200/julia/device.jl do (plain C, no Python, no torch):
  *   pf_create -> pf_filter -> pf_n_particles / pf_get_logweights / pf_get_ncomponents ->
- *   pf_get_assignments -> pf_get_particle -> pf_get_last_step -> pf_destroy
+ *   pf_get_assignments -> pf_get_particle -> pf_get_last_step -> the device summaries (pf_weighted_mean,
+ *   pf_ncomponents_dist, pf_posterior_predictive, pf_assignment_similarity, pf_randindex, pf_get_particle_assignments,
+ *   pf_genealogy_info) -> pf_save / pf_load (the loaded handle continues identically) -> pf_destroy
  * and checks the invariants the reference's own test asserts on the result
  * (test/clustering.jl:9-13: every column of the assignment matrix starts at label 1, its maximum is
  * the particle's component count) plus weight normalisation.  Compiled with gcc and run by
@@ -77,6 +79,39 @@ int main(int argc, char **argv)
     pf_step_stats st;
     CHECK(pf_get_last_step(h, &st));
     if (st.step != T || st.n_out != n || st.overflow != 0) { fprintf(stderr, "bad step stats\n"); return 1; }
+    /* filter-level summaries on the device */
+    double meanK = 0.0, H = 0.0, dist[25], dens[3], xs[6] = {6.0, 0.0, 0.0, 6.0, 40.0, 40.0}, ri = 0.0;
+    CHECK(pf_weighted_mean(h, PF_MEAN_NCOMPONENTS, &meanK));
+    CHECK(pf_weighted_mean(h, PF_MEAN_STATE_ENTROPY, &H));
+    CHECK(pf_ncomponents_dist(h, dist));
+    double sd = 0.0, mk = 0.0;
+    for (int k = 0; k <= 24; k++) { sd += dist[k]; mk += k * dist[k]; }
+    if (fabs(sd - 1.0) > 1e-9 || fabs(mk - meanK) > 1e-9 || !(H > 0.0)) { fprintf(stderr, "summaries: sum %.17g mean %.17g / %.17g H %.17g\n", sd, mk, meanK, H); return 1; }
+    CHECK(pf_posterior_predictive(h, xs, 3, dens));
+    if (!(dens[0] > dens[2] && dens[1] > dens[2] && dens[2] > 0.0)) { fprintf(stderr, "predictive density: %g %g %g\n", dens[0], dens[1], dens[2]); return 1; }
+    double *sim = malloc(sizeof(double) * T * T);
+    CHECK(pf_assignment_similarity(h, sim));
+    for (int t = 0; t < T; t++) if (sim[t * T + t] != 1.0 || sim[t * T] != sim[t]) { fprintf(stderr, "similarity matrix\n"); return 1; }
+    int32_t truth[60], chain[60];
+    CHECK(pf_get_particle_assignments(h, 0, chain));
+    for (int t = 0; t < T; t++) { truth[t] = chain[t]; if (chain[t] != A[t]) { fprintf(stderr, "chain of particle 0\n"); return 1; } }
+    CHECK(pf_randindex(h, truth, T, 1, &ri));
+    if (!(ri > 0.0 && ri <= 1.0 + 1e-12)) { fprintf(stderr, "rand index %g\n", ri); return 1; }
+    int64_t ginfo[4];
+    CHECK(pf_genealogy_info(h, ginfo));
+    if (ginfo[0] != T || ginfo[1] < T) { fprintf(stderr, "genealogy info\n"); return 1; }
+    /* checkpoint: a loaded handle filters the next observations exactly like the original */
+    const char *path = argc > 3 ? argv[3] : "/tmp/abi_smoke.ckpt";
+    CHECK(pf_save(h, path));
+    pf_handle h2 = NULL;
+    if (pf_load(path, 0, &h2) != PF_OK) { fprintf(stderr, "pf_load: %s\n", pf_last_error(NULL)); return 1; }
+    double le1[5], le2[5];
+    CHECK(pf_filter(h, ys, 5, NULL, 0, le1));
+    if (pf_filter(h2, ys, 5, NULL, 0, le2) != PF_OK) { fprintf(stderr, "pf_filter on the loaded handle: %s\n", pf_last_error(h2)); return 1; }
+    for (int t = 0; t < 5; t++) if (le1[t] != le2[t]) { fprintf(stderr, "the loaded handle diverges at observation %d\n", t); return 1; }
+    pf_destroy(h2);
+    remove(path);
+    free(sim);
     double ev = 0.0;
     for (int t = 0; t < T; t++) ev += le[t];
     printf("abi_smoke ok: kind=%d n=%lld K[0]=%d log-evidence=%.6f %s\n", kind, n, Kp, ev, pf_version());
