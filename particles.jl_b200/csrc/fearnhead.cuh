@@ -924,7 +924,10 @@ struct __align__(16) WalkItem {
     int tid, c, pad;
 };
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
+#ifndef PF_SCAN_MINBLOCKS
+#define PF_SCAN_MINBLOCKS 4       // (64 registers; measured at 2^24: 4 -> 1.05 ms, 5 -> 1.06, 6 -> 1.19, unconstrained 1 -> 1.81)
+#endif
+__global__ void __launch_bounds__(SCAN_THREADS, PF_SCAN_MINBLOCKS) k_scan_apply(const double *__restrict__ V, const unsigned char *__restrict__ cnt,
                                                              long long cap, const SelResult *__restrict__ res,
                                                              const long long *__restrict__ n_items_ptr,
                                                              const TileSum *__restrict__ tiles, const TileSum *__restrict__ supers,
