@@ -248,6 +248,12 @@ int64_t pf_mg_n_global(pf_handle h);          /* population over all shards */
  * A particle's ancestor chain is followed through the genealogy arrays of whichever rank owned each ancestor (peer
  * memory); the shards' blocks concatenated in rank order are the unsharded filter's matrix.  Needs history. */
 int32_t pf_mg_get_assignments(pf_handle h, int32_t *out);
+/* Filter-level summaries of a sharded population (src/filters.jl:17-42, 53-80): this shard's UNNORMALISED sums; added
+ * over the shards they give pred[q] / pred[Q] / (steps + alpha) = pdf of posterior_predictive(ps) at xs[:, q];
+ * pop[1] / pop[0] = mean(ncomponents, ps), pop[2] / pop[0] = state_entropy(ps), pop[3 + k] / pop[0] = ncomponents_dist(ps);
+ * sim[s * T + t] / n = assignment_similarity(ps) (counts of particles that agree; chains cross the shards through peer
+ * memory).  pred [Q + 1] (with xs [d x Q]), pop [3 + k_max + 1], sim [T x T]: any of them may be NULL. */
+int32_t pf_mg_summary_partials(pf_handle h, const double *xs, int64_t Q, double *pred, double *pop, uint64_t *sim);
 int32_t pf_mg_create_local(const pf_config *cfg, const int32_t *devices, int32_t n, pf_handle *out /* [n] */);
 /* Raw control-block words of the last threshold search / survivor scan (debugging aid). */
 int32_t pf_debug_dump(pf_handle h, int64_t *out /* [24] */);

@@ -1445,25 +1445,23 @@ static void launch_pop_summary(pf_handle h, int nb, int slots, double *part)
                                                          (double)h->steps, part);
 }
 
-extern "C" int32_t pf_posterior_predictive(pf_handle h, const double *xs, int64_t Q, double *out)
+// sums[q] = sum over this handle's particles of w_i sum_j (N_ij or alpha) t_ij(x_q), sums[Q] = sum of w_i
+static int32_t predictive_sums(pf_handle h, const double *xs, int64_t Q, double *sums)
 {
-    if (!h || (Q > 0 && (!xs || !out)) || Q < 0) return PF_ERR_ARG;
-    int32_t rc = summary_ready(h, "pf_posterior_predictive");
-    if (rc != PF_OK) return rc;
     if (h->sp_kind != PF_SP_CRP)      // components(p) has K + 1 entries, weights(p) one per candidate state: only the CRP lines them up
         return set_error(h, PF_ERR_STATE, "pf_posterior_predictive: defined for the ChineseRestaurantProcess state prior (src/particle.jl:156-172)");
-    if (Q == 0) return PF_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int d = h->d;
     const long long n = h->n_host;
     const int QB = 64;                                    // query points per pass over the store
     const long long nb = grid_for(n, SUM_THREADS);
+    for (int64_t q = 0; q <= Q; q++) sums[q] = 0.0;
+    if (n == 0) return PF_OK;
     DevBuf dx, dpart, dout;
-    CUDA_TRY(dx.alloc(sizeof(double) * Q * d));
+    CUDA_TRY(dx.alloc(sizeof(double) * std::max<int64_t>(Q, 1) * d));
     CUDA_TRY(dpart.alloc(sizeof(double) * nb * (QB + 1)));
     CUDA_TRY(dout.alloc(sizeof(double) * (QB + 1)));
     CUDA_TRY(cudaMemcpyAsync(dx.p, xs, sizeof(double) * Q * d, cudaMemcpyHostToDevice, h->stream));
-    const double norm = (double)h->steps + h->cfg.alpha;  // sum_j N_j + alpha, the same for every particle under the CRP
     for (long long q0 = 0; q0 < Q; q0 += QB) {
         const int nq = (int)std::min<long long>(QB, Q - q0);
         DISPATCH_D(d, launch_predictive<D, R>(h, (int)nb, dx.as<double>() + q0 * d, nq, dpart.as<double>()));
@@ -1471,8 +1469,23 @@ extern "C" int32_t pf_posterior_predictive(pf_handle h, const double *xs, int64_
         double res[QB + 1];
         CUDA_TRY(cudaMemcpyAsync(res, dout.p, sizeof(double) * (nq + 1), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
-        for (int q = 0; q < nq; q++) out[q0 + q] = res[q] / res[nq] / norm;
+        for (int q = 0; q < nq; q++) sums[q0 + q] = res[q];
+        sums[Q] = res[nq];
     }
+    return PF_OK;
+}
+
+extern "C" int32_t pf_posterior_predictive(pf_handle h, const double *xs, int64_t Q, double *out)
+{
+    if (!h || (Q > 0 && (!xs || !out)) || Q < 0) return PF_ERR_ARG;
+    int32_t rc = summary_ready(h, "pf_posterior_predictive");
+    if (rc != PF_OK) return rc;
+    if (Q == 0) return PF_OK;
+    std::vector<double> sums(Q + 1);
+    rc = predictive_sums(h, xs, Q, sums.data());
+    if (rc != PF_OK) return rc;
+    const double norm = (double)h->steps + h->cfg.alpha;  // sum_j N_j + alpha, the same for every particle under the CRP
+    for (int64_t q = 0; q < Q; q++) out[q] = sums[q] / sums[Q] / norm;
     return PF_OK;
 }
 
@@ -2389,6 +2402,63 @@ extern "C" int32_t pf_mg_get_assignments(pf_handle h, int32_t *out)
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         for (long long c = 0; c < nc; c++)
             for (long long t = 0; t < T; t++) out[(i0 + c) * T + t] = host[(size_t)t * nc + c];
+    }
+    return PF_OK;
+}
+
+// Filter-level summaries of a SHARDED population (src/filters.jl:17-42, 53-80): every shard returns the unnormalised
+// sums over its own particles; added up over the shards (any order: the caller's host-side gather) they give
+//   pred[q] / pred[Q] / (steps + alpha)        pdf of posterior_predictive(ps) at x_q          (pred[Q] = sum of weights)
+//   pop[1] / pop[0], pop[2] / pop[0]           mean(ncomponents, ps), state_entropy(ps)        (pop[0] = sum of weights)
+//   pop[3 + k] / pop[0]                        ncomponents_dist(ps)
+//   sim[s * T + t] / n                         assignment_similarity(ps)                        (counts of agreeing particles)
+// Any of pred (with xs, Q), pop, sim may be NULL.
+extern "C" int32_t pf_mg_summary_partials(pf_handle h, const double *xs, int64_t Q, double *pred /* [Q + 1] */, double *pop /* [3 + k_max + 1] */,
+                                          uint64_t *sim /* [T x T] */)
+{
+    MG_CHECK(h);
+    if (!h->connected) return set_error(h, PF_ERR_STATE, "pf_mg_summary_partials: pf_mg_connect has not been called");
+    int32_t rc = PF_OK;
+    if (pred) {
+        if (Q < 0 || (Q > 0 && !xs)) return PF_ERR_ARG;
+        rc = predictive_sums(h, xs, Q, pred);
+        if (rc != PF_OK) return rc;
+    }
+    if (pop) {
+        std::vector<double> rec(3 + h->k_max + 1, 0.0);
+        if (h->n_host > 0) { rc = pop_summary(h, rec); if (rc != PF_OK) return rc; }
+        std::copy(rec.begin(), rec.end(), pop);
+    }
+    if (sim) {
+        if (!h->hist_cap) return set_error(h, PF_ERR_HISTORY, "pf_mg_summary_partials: history is disabled (pf_config.history = 0)");
+        const long long T = h->steps, n = h->n_host;
+        if ((long long)h->gen_q.size() != T) return set_error(h, PF_ERR_STATE, "pf_mg_summary_partials: the last sharded call did not complete");
+        for (long long k = 0; k < T * T; k++) sim[k] = 0;
+        if (T == 0 || n == 0) return PF_OK;
+        CUDA_TRY(cudaSetDevice(h->cfg.device));
+        const long long nc_max = assign_chunk(T, n);
+        DevBuf dq, dA, dC, dok;
+        CUDA_TRY(dq.alloc(sizeof(long long) * T));
+        CUDA_TRY(dA.alloc((size_t)T * nc_max));
+        CUDA_TRY(dC.alloc(sizeof(unsigned long long) * T * T));
+        CUDA_TRY(dok.alloc(sizeof(int)));
+        CUDA_TRY(cudaMemcpyAsync(dq.p, h->gen_q.data(), sizeof(long long) * T, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemsetAsync(dC.p, 0, sizeof(unsigned long long) * T * T, h->stream));
+        k_mg_wait_generation<<<1, 32, 0, h->stream>>>(h->xch, (unsigned long long)T, dok.as<int>());
+        int ok = 0;
+        CUDA_TRY(cudaMemcpyAsync(&ok, dok.p, sizeof ok, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (!ok) return set_error(h, PF_ERR_STATE, "pf_mg_summary_partials: a peer has not finished its last generation");
+        const long long ntile = (T + SIM_TILE - 1) / SIM_TILE, npair = ntile * (ntile + 1) / 2;
+        for (long long i0 = 0; i0 < n; i0 += nc_max) {
+            const long long nc = std::min(nc_max, n - i0);
+            k_backtrack8_mg<<<grid_for(nc, 256), 256, 0, h->stream>>>(h->peers[0], h->cap, T, dq.as<long long>(), h->rank, i0, nc, dA.as<unsigned char>());
+            long long gy = std::max<long long>(1, std::min<long long>((nc / 16 + SUM_THREADS * 4 - 1) / (SUM_THREADS * 4), 4096));
+            k_similarity<<<dim3((unsigned)npair, (unsigned)gy), SUM_THREADS, 0, h->stream>>>(dA.as<unsigned char>(), T, nc, dC.as<unsigned long long>());
+        }
+        static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "");
+        CUDA_TRY(cudaMemcpyAsync(sim, dC.p, sizeof(unsigned long long) * T * T, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
     return PF_OK;
 }

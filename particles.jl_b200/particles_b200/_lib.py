@@ -88,6 +88,7 @@ SYMBOLS = [
     ("pf_mg_filter", C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, _dp, C.c_int64, _dp, C.c_int64, _dp]),
     ("pf_mg_n_global", C.c_int64, [C.c_void_p]),
     ("pf_mg_get_assignments", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
+    ("pf_mg_summary_partials", C.c_int32, [C.c_void_p, _dp, C.c_int64, _dp, _dp, C.POINTER(C.c_uint64)]),
     ("pf_mg_create_local", C.c_int32, [C.POINTER(pf_config), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
     ("pf_debug_dump", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("pf_last_timing", C.c_int32, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),

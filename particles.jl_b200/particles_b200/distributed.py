@@ -118,6 +118,7 @@ class ShardedFearnheadParticles:
         self._keep = []
         cfg = _config(n, prior, stateprior, k_max, history, seed, self._keep, self._kind, rejuv, precision)
         self.d = int(cfg.d)
+        self._alpha = float(stateprior.alpha)
         G = group.size
         if isinstance(group, LocalGroup):
             devs = group.devices if group.devices is not None else [0 if device is None else int(device)] * G
@@ -233,6 +234,47 @@ class ShardedFearnheadParticles:
         if len(outs) > 1:
             outs = [np.concatenate(outs, axis=0)]
         return np.concatenate(self.group.gather_host(outs), axis=0).T.astype(np.int64) + 1
+
+    # ---- filter-level summaries (src/filters.jl:17-42, 53-80): per-shard sums on the device, added up on the host
+    def _partials(self, xs=None, pop=False, sim=False):
+        Q = 0 if xs is None else len(xs)
+        T = self.n_steps
+        pred = np.zeros(Q + 1)
+        popv = np.zeros(3 + self.k_max + 1)
+        simv = np.zeros((T, T), dtype=np.uint64)
+        for h in self.handles:
+            p1, p2, p3 = np.zeros(Q + 1), np.zeros(3 + self.k_max + 1), np.zeros((T, T), dtype=np.uint64)
+            _lib.check(self.L.pf_mg_summary_partials(h, None if xs is None else xs.ctypes.data_as(_dp), Q,
+                                                     p1.ctypes.data_as(_dp) if xs is not None else None,
+                                                     p2.ctypes.data_as(_dp) if pop else None,
+                                                     p3.ctypes.data_as(C.POINTER(C.c_uint64)) if sim else None), h)
+            pred += p1; popv += p2; simv += p3
+        parts = self.group.gather_host([(pred, popv, simv)])
+        return (sum(p[0] for p in parts), sum(p[1] for p in parts), sum(p[2] for p in parts))
+
+    def posterior_predictive(self, xs):
+        xs = np.ascontiguousarray(np.asarray(xs, dtype=np.float64).reshape(-1, self.d))
+        pred, _, _ = self._partials(xs=xs)
+        return pred[:-1] / pred[-1] / (self.n_steps + self._alpha)
+
+    def state_entropy(self):
+        _, pop, _ = self._partials(pop=True)
+        return float(pop[2] / pop[0])
+
+    def mean_ncomponents(self):
+        _, pop, _ = self._partials(pop=True)
+        return float(pop[1] / pop[0])
+
+    def ncomponents_dist(self):
+        _, pop, _ = self._partials(pop=True)
+        p = pop[3:] / pop[0]
+        kmax = int(np.nonzero(p)[0].max()) if p.any() else 0
+        return p[1:kmax + 1].copy()
+
+    def assignment_similarity(self):
+        _, _, sim = self._partials(sim=True)
+        n = len(self)
+        return 1.0 - (n - sim.astype(np.float64)) / n
 
     def last_step(self):
         st = pf_step_stats()

@@ -62,6 +62,14 @@ def test_sharded_equals_unsharded_one_call(G, N, T, alpha):
     assert np.array_equal(sh.log_evidence, ref.log_evidence)
     # the ancestor chains cross the shards: every shard walks them through the peers' genealogy arrays
     assert np.array_equal(sh.assignments(), ref.assignments())
+    # filter-level summaries from per-shard sums: integer similarity counts are exact, the floating-point sums differ from
+    # the unsharded reduction only in the order of their block partials
+    assert np.array_equal(sh.assignment_similarity(), ref.assignment_similarity())
+    xs = np.concatenate([ys[:5], 9.0 * rng.standard_normal((6, 2))])
+    np.testing.assert_allclose(sh.posterior_predictive(xs), ref.posterior_predictive(xs), rtol=1e-12)
+    assert sh.state_entropy() == pytest.approx(pb.state_entropy(ref), rel=1e-12)
+    assert sh.mean_ncomponents() == pytest.approx(pb.mean(pb.ncomponents, ref), rel=1e-12)
+    np.testing.assert_allclose(sh.ncomponents_dist(), ref.ncomponents_dist(), rtol=1e-12)
 
 
 def test_sharded_1d_nix2():
@@ -170,3 +178,5 @@ def test_sharded_chenliu_one_call_device_uniforms(G, N, T):
     _same_chenliu(sh, ref, "after the stream")
     assert np.array_equal(sh.log_evidence, ref.log_evidence)
     assert np.array_equal(sh.assignments(), ref.assignments())
+    assert np.array_equal(sh.assignment_similarity(), ref.assignment_similarity())
+    np.testing.assert_allclose(sh.posterior_predictive(ys[:4]), ref.posterior_predictive(ys[:4]), rtol=1e-12)
