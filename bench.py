@@ -400,11 +400,13 @@ def main():
         ms, n = kt.get(name, (0.0, 0))
         if n:
             avg = ms / n
-            # a class may have several launches per step: its algorithmic bytes are per STEP, so the rate
-            # divides by the class's time per step; avg_ms stays the mean duration of one launch
+            # a class may have several launches per step: its algorithmic bytes are per STEP IN WHICH IT RAN, so the
+            # rate divides those bytes by the class's time in those steps (the separate expand / instantiate kernels
+            # run only in the first / last step of a pipelined call); avg_ms stays the mean duration of one launch
+            steps_active = min(n, K)
             per_kernel[name] = {"avg_ms": avg, "launches_per_step": n / K, "ms_per_step": ms / K, "share": ms / prof_ms,
-                                "alg_bytes_per_step": kb[name] * n_live0,
-                                "achieved_gbs": kb[name] * n_live0 / (ms / K * 1e-3) / 1e9}
+                                "steps_active": steps_active, "alg_bytes_per_active_step": kb[name] * n_live0,
+                                "achieved_gbs": kb[name] * n_live0 * steps_active / (ms * 1e-3) / 1e9}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])      # (a single-launch class on this path)
     traffic, traffic_src = ncu_traffic("k_" + dom)
     kname = {"inst_expand": "k_expand<2,2,INST> (instantiate fused with the next observation's expansion)"}.get(dom, "k_" + dom)

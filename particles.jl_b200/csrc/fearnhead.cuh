@@ -128,6 +128,9 @@ struct ScanRec {
     unsigned long long *h;     // mask of the slots ABOVE the bracket (kept whatever the threshold turns out to be)
 };
 
+#ifndef PF_UNROLL2
+#define PF_UNROLL2 1                       // slot loop of the INST kernels on two alternating register sets
+#endif
 #ifndef PF_EXPAND_MINBLOCKS
 #define PF_EXPAND_MINBLOCKS 4
 #endif
@@ -338,6 +341,40 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
 #pragma unroll
             for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = (R)fl[f];
         };
+#if PF_UNROLL2
+      if constexpr (INST) {
+        // two register sets take turns (slots j, j + 1): the fields that arrive for the next slot stay where they were
+        // loaded -- no copy from "next" to "current" (14 moves per slot) and fewer values live across the slot's
+        // arithmetic (spills of the fused kernel: 108 -> 24 bytes stored per thread).  Measured at 2^24: fused kernel
+        // 3.84 -> 3.74 ms; the plain expansions (64 registers, 4 blocks per SM) lose 11 % with it and keep the copy.
+        auto load_slot = [&](double *fl, int j) {
+            const R *base = S + ((long long)j * L::F) * cap + src;
+#pragma unroll
+            for (int f = 0; f < L::F; f++) fl[f] = (double)base[(long long)f * cap];
+        };
+        auto process = [&](double *fl, int j) {
+            if (j == jsel) {
+                double yp[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) yp[k] = ia.y_prev[k];
+                slot_add<D>(fl, tab[(int)fl[L::F_N]], yp, mu0);
+#pragma unroll
+                for (int f = 0; f < L::F; f++) fl[f] = (double)(R)fl[f];          // what the stored child holds (no-op for R = double)
+            }
+            if (MODE == 2) store_child(fl, j);
+            eval(fl, j);
+        };
+        for (int j = 0; j < K; j += 2) {
+            if (j + 1 < K) load_slot(fnxt, j + 1);
+            process(fcur, j);
+            if (j + 1 < K) {
+                if (j + 2 < K) load_slot(fcur, j + 2);
+                process(fnxt, j + 1);
+            }
+        }
+      } else
+#endif
+      {
         for (int j = 0; j < K; j++) {
             if (j + 1 < K) {
                 const R *base = S + ((long long)(j + 1) * L::F) * cap + src;
@@ -359,6 +396,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
 #pragma unroll
             for (int f = 0; f < L::F; f++) fcur[f] = fnxt[f];
         }
+      }
         int Kn = K;
         if (INST && jsel == K) {             // the previous observation opened a new cluster (src/particle.jl:141-146)
 #pragma unroll
@@ -828,6 +866,40 @@ __global__ void __launch_bounds__(1024) k_tile_prefix(TileSum *tiles, const SelR
     }
 }
 
+// Every tile's starting point of the comb, one THREAD per tile: running mass and kept count before the tile, and its first
+// tooth (the one 128-bit division of tooth_base), so that thread 0 of a k_scan_apply block does not run that serial
+// chain of ~600 instructions while the other 255 wait at the scan's barrier.
+struct __align__(16) TileTooth {
+    u128 S0, Q0;
+    long long k0;
+    u64 t0;
+    double inv;
+    unsigned int R0, pad;
+};
+__global__ void __launch_bounds__(256) k_tooth_bases(const TileSum *__restrict__ tiles, const TileSum *__restrict__ supers,
+                                                     const SelResult *__restrict__ res, const long long *__restrict__ n_items_ptr,
+                                                     const RankOff *__restrict__ ro, TileTooth *__restrict__ out, int mode,
+                                                     const SelScratch *guard)
+{
+    if (guard && (guard->phase != 4 || guard->halt)) return;
+    if (scan_mode_skips(mode, res)) return;
+    const long long ntiles = (*n_items_ptr + SCAN_THREADS - 1) / SCAN_THREADS;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const u64 n = (u64)res->n;
+    const u128 T = res->T;
+    TileTooth tt;
+    tt.S0 = add128(tiles[t].X, supers[t / SUPER_TILES].X);          // prefix within the supertile + prefix of the supertiles
+    tt.k0 = (long long)tiles[t].kept + (long long)supers[t / SUPER_TILES].kept;
+    if (ro) { tt.S0 = add128(tt.S0, ro->S_off); tt.k0 += ro->kept_off - ro->g_first; }   // positions relative to this rank's first survivor
+    tt.Q0 = mk128(0, 0); tt.t0 = 0; tt.inv = 0.0; tt.R0 = 0; tt.pad = 0;
+    if (n > 0 && !isz128(T)) {
+        const ToothBase b = tooth_base(tt.S0, n, res->Uoff, T);
+        tt.Q0 = b.Q0; tt.R0 = b.R0; tt.t0 = b.t0; tt.inv = b.inv;
+    }
+    out[t] = tt;
+}
+
 // The walk over one particle's putatives (one lane per particle; all 32 lanes of the warp call it, idle lanes with
 // c = 0): kept ones are listed; for the low ones the question "has the running mass passed the next tooth?" is
 // Q - S_particle < (sum of the q_j so far).  It is asked in double precision first -- the items' values scaled by
@@ -847,15 +919,21 @@ __device__ __forceinline__ void walk_particle(const double *__restrict__ V, long
     bool amb = false;
     {
         double cum = 0.0;
-        double Dd = tooth_inside ? to_double128(sub128(Q, S)) : 0.0;
+        // distance to the next tooth; a lane without a tooth inside its particle gets one it cannot reach (finite, so that
+        // the comparisons below stay ordinary: no per-slot test of `tooth_inside`)
+        double Dd = tooth_inside ? to_double128(sub128(Q, S)) : 1e300;
+        // below Dlo the running mass has certainly not reached the tooth and is not within the rounding margin of it
+        // (margin = 64 + (cum + Dd) 2^-45 < 64 + Dd 2^-44 while cum < Dd): one comparison per putative in the common case
+        double Dlo = Dd - (128.0 + Dd * 1.1368683772161603e-13);         // (2^-43: twice the margin)
         const long long sadd = (long long)scale << 52;
         int cmax = c;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
+        const double *__restrict__ pv = V + i;
         for (int j0 = 0; j0 < cmax; j0 += 8) {
             u64 vb[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) vb[k] = (j0 + k < c) ? (u64)__double_as_longlong(V[(long long)(j0 + k) * cap + i]) : 0ull;
+            for (int k = 0; k < 8; k++) { vb[k] = (j0 + k < c) ? (u64)__double_as_longlong(*pv) : 0ull; pv += cap; }
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int j = j0 + k;
@@ -868,10 +946,11 @@ __device__ __forceinline__ void walk_particle(const double *__restrict__ V, long
                         if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)j; }
                     }
                     kcount++;
-                } else if (tooth_inside && bits != 0) {
-                    const long long eb = (long long)(bits >> 52) + scale;           // exponent field of v 2^scale
-                    if ((bits >> 52) == 0 || eb <= 0 || eb >= 2046) { amb = true; continue; }
+                } else if (bits != 0) {
+                    const int eb = (int)(bits >> 52) + scale;                       // exponent field of v 2^scale
+                    if ((bits >> 52) == 0 || (unsigned int)(eb - 1) >= 2045u) { amb = tooth_inside; continue; }      // subnormal, or v 2^scale not a normal double (matters to a lane with a tooth only)
                     cum += __longlong_as_double((long long)bits + sadd);              // v_j 2^scale, exact
+                    if (cum < Dlo) continue;
                     for (;;) {
                         const double diff = cum - Dd;
                         const double tol = 64.0 + (cum + Dd) * 2.8421709430404007e-14;   // 2^-45 relative + the floors
@@ -882,6 +961,7 @@ __device__ __forceinline__ void walk_particle(const double *__restrict__ V, long
                             t++;
                             tooth_step(Q, R, Tq, Tr, n32);
                             Dd = to_double128(sub128(Q, S));
+                            Dlo = Dd - (128.0 + Dd * 1.1368683772161603e-13);
                             continue;
                         }
                         if (diff >= -tol) amb = true;
@@ -935,7 +1015,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, PF_SCAN_MINBLOCKS) k_scan_apply(
                                                              unsigned char *__restrict__ surv_slot, int mode,
                                                              const RankOff *__restrict__ ro, const SelScratch *guard,
                                                              long long surv_cap, ScanRec rec = ScanRec{nullptr, nullptr, nullptr},
-                                                             const SelScratch *recsc = nullptr)
+                                                             const SelScratch *recsc = nullptr, const TileTooth *__restrict__ tooth = nullptr)
 {
     if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
@@ -958,7 +1038,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, PF_SCAN_MINBLOCKS) k_scan_apply(
     __shared__ long long s_k0;
     __shared__ double s_inv;
     __shared__ unsigned int s_nq;
-    if (tid == 0) {
+    if (tid == 0 && tooth) {
+        const TileTooth tt = tooth[blockIdx.x];                  // (k_tooth_bases)
+        s_S0 = tt.S0; s_k0 = tt.k0; s_nq = 0;
+        s_Q0 = tt.Q0; s_R0 = tt.R0; s_t0 = tt.t0; s_inv = tt.inv;
+    } else if (tid == 0) {
         u128 S0 = add128(tiles[blockIdx.x].X, supers[blockIdx.x / SUPER_TILES].X);      // prefix within the supertile + prefix of the supertiles
         long long k0 = (long long)tiles[blockIdx.x].kept + (long long)supers[blockIdx.x / SUPER_TILES].kept;
         if (ro) { S0 = add128(S0, ro->S_off); k0 += ro->kept_off - ro->g_first; }   // positions relative to this rank's first survivor

@@ -46,6 +46,7 @@ struct pf_filter_s {
     TileSum *tiles = nullptr;
     TileSum *supers = nullptr;            // totals of SUPER_TILES consecutive tile records (level 2 of the survivor scan)
     TileFuse *tfuse = nullptr;            // per expansion block (EXP_SUB per tile)
+    TileTooth *ttooth = nullptr;          // per tile of the index-order survivor scan: offsets and first comb tooth (k_tooth_bases)
     TileSum *tsub = nullptr;              // sub-tile records of the fused expansion (EXP_SUB per tile)
     ScanRec srec = ScanRec{nullptr, nullptr, nullptr};   // per-particle scan records of the fused expansion (PF_SCAN_REC)
     long long fuse_stride = 1;
@@ -245,7 +246,7 @@ extern "C" int32_t pf_destroy(pf_handle h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->S[0], h->S[1], h->logw[0], h->logw[1], h->Kc[0], h->Kc[1], h->V, h->V_alt, h->stc_alt, h->cnt, h->surv_parent,
-                    h->surv_slot, h->tiles, h->supers, h->tfuse, h->tsub, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
+                    h->surv_slot, h->tiles, h->supers, h->tfuse, h->tsub, h->ttooth, h->cand, h->sc, h->res, h->st, h->pc, h->stc, h->tab, h->slog,
                     h->ys_dev, h->u_dev, h->gen_anc, h->gen_asg, h->gen_off_dev, h->cl, h->W, h->cum, h->asg_tmp, h->cl_tiles, h->clp, h->keys, h->keys2, h->vals, h->vals2, h->hist, h->pick_pos, h->ro, h->xreg, h->xch,
                     h->peers[0], h->peers[1], h->srec.x, h->srec.m, h->srec.h, h->sp[0].N, h->sp[0].Nsame, h->sp[0].last, h->sp[1].N,
                     h->sp[1].Nsame, h->sp[1].last};
@@ -367,6 +368,7 @@ extern "C" int32_t pf_create(const pf_config *cfg, pf_handle *out)
     CT(dmalloc(&h->supers, ntiles / SUPER_TILES + 2));
     CT(dmalloc(&h->tfuse, ntiles * EXP_SUB));
     CT(dmalloc(&h->tsub, ntiles * EXP_SUB));
+    if (cfg->filter_kind == PF_FEARNHEAD && !getenv("PF_NO_TOOTH_BASES")) CT(dmalloc(&h->ttooth, (cap + SCAN_THREADS - 1) / SCAN_THREADS));
     // per-particle scan records of the fused expansion (24 bytes per particle; PF_NO_SCAN_REC=1 disables them)
     if (cfg->filter_kind == PF_FEARNHEAD && cfg->order == PF_ORDER_INDEX && !getenv("PF_NO_SCAN_REC")) {
         CT(dmalloc(&h->srec.x, (size_t)h->cap));
@@ -685,14 +687,15 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
                                                             h->surv_slot, 2, nullptr, h->sc, cap);
     } else {
-        LaunchTimer lt(h, KC_SCAN, 4);
+        LaunchTimer lt(h, KC_SCAN, h->ttooth ? 5 : 4);
         const int gidx = grid_for(ub, SCAN_THREADS);
         k_tile_sums<<<std::min(gidx, h->num_sms * 8), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, 0, h->sc, fused ? h->sc : nullptr);
         k_tile_scan1<<<grid_for(gidx, SUPER_TILES), SUPER_TILES, 0, h->stream>>>(h->tiles, h->tsub, fused ? h->tfuse : nullptr, h->cand, h->res, h->sc, &h->st->n_live, h->stc,
                                                                                      h->supers, 0, h->sc);
         k_tile_prefix<<<1, 1024, 0, h->stream>>>(h->supers, h->res, &h->st->n_live, h->st, 0, nullptr, 0, h->sc, 1);
+        if (h->ttooth) k_tooth_bases<<<grid_for(gidx, 256), 256, 0, h->stream>>>(h->tiles, h->supers, h->res, &h->st->n_live, nullptr, h->ttooth, 0, h->sc);
         k_scan_apply<<<gidx, SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, cap, h->res, &h->st->n_live, h->tiles, h->supers, h->surv_parent,
-                                                            h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr, nullptr}, h->sc);
+                                                            h->surv_slot, 0, nullptr, h->sc, cap, fused ? h->srec : ScanRec{nullptr, nullptr, nullptr}, h->sc, h->ttooth);
     }
     if (fused && y_next && y_host && h->pipeline) {
         // pipelined tail: close this step's record, then build the children WHILE expanding them for the next observation
@@ -2103,10 +2106,11 @@ static int32_t mg_stage_c(pf_handle h)
 static int32_t mg_stage_d_scan(pf_handle h)
 {
     const unsigned long long seq = (unsigned long long)h->steps + 1;
-    LaunchTimer lt(h, KC_SCAN, 2);            // (k_rank_offsets includes the wait for every rank's total)
+    LaunchTimer lt(h, KC_SCAN, h->ttooth ? 3 : 2);            // (k_rank_offsets includes the wait for every rank's total)
     k_rank_offsets<<<1, 32, 0, h->stream>>>(h->xch, seq, h->steps, h->res, h->st, h->ro, h->sc, h->surv_cap);
+    if (h->ttooth) k_tooth_bases<<<grid_for(grid_for(h->cap, SCAN_THREADS), 256), 256, 0, h->stream>>>(h->tiles, h->supers, h->res, &h->st->n_live, h->ro, h->ttooth, 0, h->sc);
     k_scan_apply<<<grid_for(h->cap, SCAN_THREADS), SCAN_THREADS, 0, h->stream>>>(h->V, h->cnt, h->cap, h->res, &h->st->n_live, h->tiles, h->supers,
-                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap, h->srec, h->sc);
+                                                                                  h->surv_parent, h->surv_slot, 0, h->ro, h->sc, h->surv_cap, h->srec, h->sc, h->ttooth);
     return PF_OK;
 }
 
