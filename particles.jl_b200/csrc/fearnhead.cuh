@@ -1020,7 +1020,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, PF_SCAN_MINBLOCKS) k_scan_apply(
     if (guard && (guard->phase != 4 || guard->halt)) return;
     if (scan_mode_skips(mode, res)) return;
     __shared__ u128 s_warp[33];
-    __shared__ unsigned int s_wc[33];
     const long long n_items = *n_items_ptr;
     const long long ntiles = (n_items + SCAN_THREADS - 1) / SCAN_THREADS;
     if (blockIdx.x >= ntiles) return;
@@ -1076,21 +1075,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, PF_SCAN_MINBLOCKS) k_scan_apply(
     } else {
         thread_sums(V, cap, i, c, thr, scale, comb, myX, myKept);
     }
-    u128 totX;
-    u128 exX = block_excl_scan128(myX, s_warp, &totX);
-    unsigned int incK = myKept;
+    // ONE exclusive scan over the block for both quantities: the kept count rides in bits 104.. of the 128-bit mass (a
+    // tile's mass is < 2^86, its kept count < 2^15), and with 8 warps every warp adds up the totals of the warps before
+    // it by itself -- one block barrier instead of the five of two separate two-level scans
+    u128 pk = mk128(myX.lo, myX.hi | ((u64)myKept << 40));
+    u128 inc = pk;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, incK, d); if (lane >= d) incK += o; }
-    if (lane == 31) s_wc[wid] = incK;
+    for (int d = 1; d < 32; d <<= 1) { u128 o = shfl_up128(inc, d); if (lane >= d) inc = add128(inc, o); }
+    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    if (wid == 0) {
-        unsigned int w = lane < (SCAN_THREADS / 32) ? s_wc[lane] : 0, wi = w;
+    u128 ex = sub128(inc, pk);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned int o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
-        s_wc[lane] = wi - w;
-    }
-    __syncthreads();
-    const unsigned int exK = s_wc[wid] + incK - myKept;
+    for (int w = 0; w < SCAN_THREADS / 32 - 1; w++) if (w < wid) ex = add128(ex, s_warp[w]);
+    const u128 exX = mk128(ex.lo, ex.hi & ((1ull << 40) - 1));
+    const unsigned int exK = (unsigned int)(ex.hi >> 40);
     // running low-partition mass S (fixed point) and the next tooth k: tooth k is passed by S
     // <=> Uoff + k T < n S <=> floor((Uoff + k T) / n) < S; (Q, R) = divmod(Uoff + k T, n) steps
     // by (Tq, Tr) = divmod(T, n) from tooth to tooth.  The tile's first tooth (t0, Q0, R0) is
