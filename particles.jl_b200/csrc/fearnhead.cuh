@@ -128,6 +128,31 @@ struct ScanRec {
     unsigned long long *h;     // mask of the slots ABOVE the bracket (kept whatever the threshold turns out to be)
 };
 
+#ifndef PF_CPASYNC_DEPTH
+#define PF_CPASYNC_DEPTH 1                 // slots in flight as asynchronous global -> shared copies (0: register prefetch)
+#endif
+#ifndef PF_CPASYNC_STAGES
+#define PF_CPASYNC_STAGES (PF_CPASYNC_DEPTH + 1)   // staging slots; 1 (with depth 1): the slot is refilled right after it has been read
+#endif
+#ifndef PF_CPASYNC_SMEM_MAX
+#define PF_CPASYNC_SMEM_MAX (60 * 1024)    // staging buffer per block; larger records keep the register prefetch
+#endif
+// dynamic shared memory of the single-GPU fused kernel k_expand<D, 2, true, R>: (depth + 1) slots x F fields x block
+template <int D, typename R>
+__host__ __device__ constexpr size_t instexp_staging_bytes()
+{
+    return PF_CPASYNC_DEPTH > 0 && (size_t)PF_CPASYNC_STAGES * Layout<D>::F * EXP_THREADS * sizeof(R) <= PF_CPASYNC_SMEM_MAX
+               ? (size_t)PF_CPASYNC_STAGES * Layout<D>::F * EXP_THREADS * sizeof(R) : 0;
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void *smem_dst, const void *gsrc)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gsrc), "n"(BYTES));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #ifndef PF_UNROLL2
 #define PF_UNROLL2 1                       // slot loop of the INST kernels on two alternating register sets
 #endif
@@ -224,6 +249,10 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
     __shared__ u128 s_tot[8];                    // kept-side total per warp
     __shared__ u128 s_red[8];
     __shared__ unsigned int s_redk[8], s_redp[8];
+    // asynchronous-copy form of the slot loop (single-GPU fused kernel, records small enough for the staging buffer)
+    constexpr bool CPA = MODE == 2 && INST && !REMOTE && instexp_staging_bytes<D, R>() > 0;
+    extern __shared__ __align__(16) unsigned char s_dyn[];      // (the launch passes instexp_staging_bytes<D, R>())
+    R *const s_pre = reinterpret_cast<R *>(s_dyn);
     constexpr bool remote = INST && REMOTE;
     const long long n_live = remote ? ia.ro->n_local : st->n_live;
     constexpr bool strided = STRIDED;
@@ -325,7 +354,7 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
         }
         // software pipeline: the fields of slot j+1 are in flight while slot j is evaluated
         double fcur[L::F], fnxt[L::F];
-        if (K > 0) {
+        if (K > 0 && !CPA) {
             const R *base = S + src;
 #pragma unroll
             for (int f = 0; f < L::F; f++) fcur[f] = (double)base[(long long)f * cap];
@@ -341,6 +370,51 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
 #pragma unroll
             for (int f = 0; f < L::F; f++) dst[(long long)f * cap] = (R)fl[f];
         };
+      if constexpr (CPA) {
+        // the fields of the next slots travel global -> shared memory as asynchronous copies (LDGSTS, per-thread commit
+        // groups): nothing of a slot that is still in flight occupies a register, and the copies run PF_CPASYNC_DEPTH
+        // slots ahead of the arithmetic.  A thread reads back only what it copied itself: no barrier.
+        constexpr int NS = PF_CPASYNC_STAGES;
+        auto prefetch = [&](int j) {
+            const R *base = S + ((long long)j * L::F) * cap + src;
+            R *dst = s_pre + ((j % NS) * L::F) * EXP_THREADS + threadIdx.x;
+#pragma unroll
+            for (int f = 0; f < L::F; f++) cp_async_elem<sizeof(R)>(dst + f * EXP_THREADS, base + (long long)f * cap);
+        };
+#pragma unroll
+        for (int p = 0; p < PF_CPASYNC_DEPTH; p++) { if (p < K) prefetch(p); cp_async_commit(); }
+        for (int j = 0; j < K; j++) {
+            if (NS > 1) {
+                if (j + PF_CPASYNC_DEPTH < K) prefetch(j + PF_CPASYNC_DEPTH);
+                cp_async_commit();
+                cp_async_wait<PF_CPASYNC_DEPTH>();              // all but the newest DEPTH groups have landed: slot j is here
+            } else {
+                cp_async_wait<0>();
+            }
+            const R *srcs = s_pre + ((j % NS) * L::F) * EXP_THREADS + threadIdx.x;
+#pragma unroll
+            for (int f = 0; f < L::F; f++) fcur[f] = (double)srcs[f * EXP_THREADS];
+            if (NS == 1) {
+                // one staging slot: it is refilled as soon as its content sits in registers (the empty asm makes the
+                // shared-memory loads complete before the copies that overwrite their source are issued)
+#pragma unroll
+                for (int f = 0; f < L::F; f++) asm volatile("" ::"d"(fcur[f]) : "memory");
+                if (j + 1 < K) prefetch(j + 1);
+                cp_async_commit();
+            }
+            if (j == jsel) {
+                double yp[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) yp[k] = ia.y_prev[k];
+                slot_add<D>(fcur, tab[(int)fcur[L::F_N]], yp, mu0);
+#pragma unroll
+                for (int f = 0; f < L::F; f++) fcur[f] = (double)(R)fcur[f];          // what the stored child holds (no-op for R = double)
+            }
+            store_child(fcur, j);
+            eval(fcur, j);
+        }
+        cp_async_wait<0>();
+      } else
 #if PF_UNROLL2
       if constexpr (INST) {
         // two register sets take turns (slots j, j + 1): the fields that arrive for the next slot stay where they were

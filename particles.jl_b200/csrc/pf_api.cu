@@ -38,6 +38,7 @@ struct pf_filter_s {
     double *Vbuf[2] = {nullptr, nullptr}; // the two V buffers by identity (peers address them by index); V == Vbuf[vcur]
     int vcur = 0;
     bool pipeline_mg = false;             // ... the same fusion on the sharded path (children and their putatives go to the new owner)
+    bool instexp_attr = false;            // the fused kernel's dynamic shared memory limit has been raised
     bool pipeline = false;                // instantiate of step t fused with the expansion of step t + 1 inside pf_filter
     bool pre_expanded = false;            // the step about to run was expanded by the previous step's pipelined tail
     unsigned char *cnt = nullptr;
@@ -730,7 +731,12 @@ static int32_t fearnhead_step(pf_handle h, const double *y_dev, const double *u_
         }
         {
             LaunchTimer lt(h, KC_INST_EXPAND);
-            k_expand<D, 2, true, R><<<grid_for(ub_next, EXP_THREADS), EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+            constexpr size_t stage_bytes = instexp_staging_bytes<D, R>();      // asynchronous-copy staging of the slot loop
+            if (stage_bytes && !h->instexp_attr) {
+                CUDA_TRY(cudaFuncSetAttribute(k_expand<D, 2, true, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+                h->instexp_attr = true;
+            }
+            k_expand<D, 2, true, R><<<grid_for(ub_next, EXP_THREADS), EXP_THREADS, stage_bytes, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                        h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, h->tsub, h->tfuse, h->srec, ia);
         }
         CUDA_TRY(cudaGetLastError());
