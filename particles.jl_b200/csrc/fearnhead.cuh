@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMO
     __shared__ u128 s_tot[8];                    // kept-side total per warp
     __shared__ u128 s_red[8];
     __shared__ unsigned int s_redk[8], s_redp[8];
-    // asynchronous-copy form of the slot loop (single-GPU fused kernel, records small enough for the staging buffer)
-    constexpr bool CPA = MODE == 2 && INST && !REMOTE && instexp_staging_bytes<D, R>() > 0;
+    // asynchronous-copy form of the slot loop (fused kernels, records small enough for the staging buffer)
+    constexpr bool CPA = MODE == 2 && INST && instexp_staging_bytes<D, R>() > 0;
     extern __shared__ __align__(16) unsigned char s_dyn[];      // (the launch passes instexp_staging_bytes<D, R>())
     R *const s_pre = reinterpret_cast<R *>(s_dyn);
     constexpr bool remote = INST && REMOTE;

@@ -2197,11 +2197,17 @@ static int32_t mg_tail(pf_handle h, int phase, StepLog *log_dev, const double *y
         LaunchTimer lt(h, KC_INST_EXPAND);
         // main launch: the tiles a balanced share needs (+ 25 %); a small strided launch takes whatever lies beyond
         const int gmain = grid_for(std::min<long long>(h->surv_cap, cap + cap / 4), EXP_THREADS);
-        k_expand<D, 2, true, R, true><<<gmain, EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+        constexpr size_t stage_bytes = instexp_staging_bytes<D, R>();          // asynchronous-copy staging of the slot loop
+        if (stage_bytes && !h->instexp_attr) {
+            CUDA_TRY(cudaFuncSetAttribute(k_expand<D, 2, true, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(k_expand<D, 2, true, R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+            h->instexp_attr = true;
+        }
+        k_expand<D, 2, true, R, true><<<gmain, EXP_THREADS, stage_bytes, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                    h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, nullptr, nullptr, h->srec, ia);
         if ((long long)gmain * EXP_THREADS < h->surv_cap) {
             ia.vb0 = gmain;
-            k_expand<D, 2, true, R, true, true><<<h->num_sms, EXP_THREADS, 0, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
+            k_expand<D, 2, true, R, true, true><<<h->num_sms, EXP_THREADS, stage_bytes, h->stream>>>((const R *)h->S[cur], nullptr, h->Kc[cur], cap, h->k_max, h->tab, h->pc,
                                                                    h->stc_alt, h->st, h->V_alt, h->cnt, h->sc, 1, h->cand, nullptr, nullptr, h->srec, ia);
             h->launches++;
         }
