@@ -106,10 +106,11 @@ struct TileSum {           // survivor-scan record of one tile of SCAN_THREADS p
 // Block size of the full expansions (MODE 0 / 2).  The survivor scan's tile (SCAN_THREADS particles) is EXP_SUB such
 // blocks: a block leaves a SUB-tile record, k_tile_scan1 adds them up.  Smaller blocks shorten the tail in which a
 // block's finished warps wait for its slowest one (17 % of the stall samples at 256 threads), but every block ends with
-// ~15 atomics on the step's accumulators, and those serialise per address: measured at 2^24 particles the fused kernel
-// takes 3.83 ms with 256-thread blocks, 3.81 with 128, 5.50 with 64, 8.59 with 32 (profiles/r2/README.md).
+// ~15 atomics on the step's accumulators, and those serialise per address.  Measured at 2^24 particles, fused kernel:
+// register-prefetch form 3.83 ms with 256-thread blocks, 3.81 with 128, 5.50 with 64, 8.59 with 32; asynchronous-copy
+// form (below) 3.48 with 256, 3.40 with 128 (profiles/r2/README.md, ab_cpa_4.jsonl).
 #ifndef EXP_THREADS
-#define EXP_THREADS 256
+#define EXP_THREADS 128
 #endif
 #define EXP_SUB (256 / EXP_THREADS)
 #define EXP_CAND_CAP (4 * EXP_THREADS)   // MODE 2: candidates one block may stage
