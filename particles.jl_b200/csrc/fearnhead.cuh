@@ -136,7 +136,8 @@ struct ScanRec {
 #define PF_CPASYNC_STAGES (PF_CPASYNC_DEPTH + 1)   // staging slots; 1 (with depth 1): the slot is refilled right after it has been read
 #endif
 #ifndef PF_CPASYNC_SMEM_MAX
-#define PF_CPASYNC_SMEM_MAX (60 * 1024)    // staging buffer per block; larger records keep the register prefetch
+#define PF_CPASYNC_SMEM_MAX (16 * 1024)    // staging buffer per block (14 KB for the 2-D FP64 record); larger records keep the register
+                                           // prefetch: shared memory is taken from the L1 the parent gather lives on (deeper pipelines lost to it)
 #endif
 // dynamic shared memory of the single-GPU fused kernel k_expand<D, 2, true, R>: (depth + 1) slots x F fields x block
 template <int D, typename R>
