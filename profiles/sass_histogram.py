@@ -43,6 +43,7 @@ def main():
         res[label] = {"instructions": n, "top": {k: v for k, v in ops.most_common(14)},
                       "local_memory": {k: ops[k] for k in ("LDL", "STL") if ops[k]},
                       "fp64": sum(v for k, v in ops.items() if k in ("DFMA", "DADD", "DMUL", "DSETP", "MUFU")),
+                      "async_copy": {k: ops[k] for k in ("LDGSTS", "LDGDEPBAR", "DEPBAR") if ops[k]},
                       "blackwell_specific": {k: ops[k] for k in ("UTMALDG", "UTMASTG", "UTCMMA", "UTCHMMA", "SYNCS", "UBLKCP") if ops[k]}}
     os.makedirs(os.path.join(ROOT, "profiles", "r2"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "profiles", "r2", "sass_histograms.json"), "w"), indent=1)
