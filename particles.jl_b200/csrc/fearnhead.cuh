@@ -231,8 +231,24 @@ struct InstArgs {
 // STRIDED (a second, small launch of the sharded variant): the tiles from InstArgs.vb0 on, blocks striding over them -- a
 // rank may produce more survivors than the main launch's grid covers; keeping the loop out of the main launch is worth
 // 11 % of its time.
+// (records larger than the 2-D one: the fused kernels trade occupancy for registers -- at 80 registers the 8-D kernel
+// spills 2.6 KB per thread; PF_INSTEXP_BY_DIM=0 keeps the 2-D setting for every d)
+#ifndef PF_INSTEXP_BY_DIM
+#define PF_INSTEXP_BY_DIM 1
+#endif
+template <int D, bool REMOTE>
+__host__ __device__ constexpr int instexp_minblocks()
+{
+    const int base = REMOTE ? PF_INSTEXP_REMOTE_MINBLOCKS : PF_INSTEXP_MINBLOCKS;
+    return !PF_INSTEXP_BY_DIM || D <= 2 ? base : (D <= 4 ? 2 : 1);
+}
+template <int D>
+__host__ __device__ constexpr int expand_minblocks()          // the expansions from the store (64 registers at d <= 2)
+{
+    return !PF_INSTEXP_BY_DIM || D <= 2 ? PF_EXPAND_MINBLOCKS : (D <= 4 ? 2 : 1);
+}
 template <int D, int MODE, bool INST = false, typename R = double, bool REMOTE = false, bool STRIDED = false>
-__global__ void __launch_bounds__(EXP_THREADS, (INST ? (REMOTE ? PF_INSTEXP_REMOTE_MINBLOCKS : PF_INSTEXP_MINBLOCKS) : PF_EXPAND_MINBLOCKS) * EXP_SUB) k_expand(const R *__restrict__ S, const double *__restrict__ logw,
+__global__ void __launch_bounds__(EXP_THREADS, (INST ? instexp_minblocks<D, REMOTE>() : expand_minblocks<D>()) * EXP_SUB) k_expand(const R *__restrict__ S, const double *__restrict__ logw,
                                                 const int *__restrict__ Kc, long long cap, int k_max,
                                                 const NRow *__restrict__ tab, const PriorConst *__restrict__ pc,
                                                 const StepConst *__restrict__ scp, StepState *st,
@@ -1154,6 +1170,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, PF_SCAN_MINBLOCKS) k_scan_apply(
     // ONE exclusive scan over the block for both quantities: the kept count rides in bits 104.. of the 128-bit mass (a
     // tile's mass is < 2^86, its kept count < 2^15), and with 8 warps every warp adds up the totals of the warps before
     // it by itself -- one block barrier instead of the five of two separate two-level scans
+    PF_ASSERT(myX.hi < (1ull << 22) && myKept <= PF_MAX_SLOTS + 1);
     u128 pk = mk128(myX.lo, myX.hi | ((u64)myKept << 40));
     u128 inc = pk;
 #pragma unroll
