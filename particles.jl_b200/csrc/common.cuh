@@ -214,6 +214,24 @@ __host__ __device__ __forceinline__ u64 tooth_seek(u128 Q0, unsigned int R0, dou
     return k;
 }
 
+// The survivor scan's fast walk asks "has the running low mass of this particle passed the next tooth?" in double
+// precision: cum = sum of the items' values scaled by 2^scale (exact doubles; the integer masses floor(v 2^scale) differ
+// from them by < 1 each, at most 64 items), Dd = (double)(Q - S) (one rounding).  The answer is taken only when it
+// clears the error bound by a wide margin; otherwise the particle is redone in exact 128-bit arithmetic.
+//   walk_compare: +1 passed, -1 not passed, 0 too close to tell.
+//   walk_reject_below(Dd): a bound below which cum is certainly "not passed" (cum < Dd there, so the margin
+//   64 + (cum + Dd) 2^-45 is < 64 + Dd 2^-44; the bound uses twice that) -- one comparison per item in the common case.
+__host__ __device__ __forceinline__ int walk_compare(double cum, double Dd)
+{
+    const double diff = cum - Dd;
+    const double tol = 64.0 + (cum + Dd) * 2.8421709430404007e-14;          // 2^-45 relative + the floors
+    return diff > tol ? 1 : (diff >= -tol ? 0 : -1);
+}
+__host__ __device__ __forceinline__ double walk_reject_below(double Dd)
+{
+    return Dd - (128.0 + Dd * 1.1368683772161603e-13);                       // 2^-43
+}
+
 // ------------------------------------------------------------------ warp / block helpers
 __device__ __forceinline__ u128 shfl_up128(u128 v, int d)
 {

@@ -1016,7 +1016,7 @@ __device__ __forceinline__ void walk_particle(const double *__restrict__ V, long
         double Dd = tooth_inside ? to_double128(sub128(Q, S)) : 1e300;
         // below Dlo the running mass has certainly not reached the tooth and is not within the rounding margin of it
         // (margin = 64 + (cum + Dd) 2^-45 < 64 + Dd 2^-44 while cum < Dd): one comparison per putative in the common case
-        double Dlo = Dd - (128.0 + Dd * 1.1368683772161603e-13);         // (2^-43: twice the margin)
+        double Dlo = walk_reject_below(Dd);
         const long long sadd = (long long)scale << 52;
         int cmax = c;
 #pragma unroll
@@ -1044,19 +1044,18 @@ __device__ __forceinline__ void walk_particle(const double *__restrict__ V, long
                     cum += __longlong_as_double((long long)bits + sadd);              // v_j 2^scale, exact
                     if (cum < Dlo) continue;
                     for (;;) {
-                        const double diff = cum - Dd;
-                        const double tol = 64.0 + (cum + Dd) * 2.8421709430404007e-14;   // 2^-45 relative + the floors
-                        if (diff > tol) {
+                        const int passed = walk_compare(cum, Dd);
+                        if (passed > 0) {
                             long long pos = (mode == 1 ? 0 : kcount) + (long long)t;
                             PF_ASSERT(pos >= 0 && pos < surv_cap);
                             if (pos >= 0 && pos < surv_cap) { surv_parent[pos] = (unsigned int)i; surv_slot[pos] = (unsigned char)(j | 0x80); }
                             t++;
                             tooth_step(Q, R, Tq, Tr, n32);
                             Dd = to_double128(sub128(Q, S));
-                            Dlo = Dd - (128.0 + Dd * 1.1368683772161603e-13);
+                            Dlo = walk_reject_below(Dd);
                             continue;
                         }
-                        if (diff >= -tol) amb = true;
+                        if (passed == 0) amb = true;
                         break;
                     }
                 }

@@ -1,6 +1,7 @@
 // Host-side harness for the __host__ __device__ integer arithmetic of csrc/common.cuh: the same
 // source the kernels compile, built for the CPU so that tests/test_host_arith.py can check it
 // against Python's exact integers without a GPU.  Test infrastructure only.
+#include <cstring>
 #include "../../particles.jl_b200/csrc/common.cuh"
 
 extern "C" {
@@ -30,6 +31,46 @@ int h_mul_gt256(const u64 *a, const u64 *b, const u64 *c, const u64 *d, u64 *pro
     mul128x128(mk128(c[0], c[1]), mk128(d[0], d[1]), y);
     for (int k = 0; k < 4; k++) prod[k] = x[k];
     return gt256(x, y) ? 1 : 0;
+}
+
+// The fast walk of one particle (walk_particle of csrc/fearnhead.cuh, the double-precision path) on the host, with the
+// kernel's own decision helpers walk_compare / walk_reject_below / tooth_step: `c` low items given by their bit patterns,
+// S = running fixed-point mass before the particle, (Q, R) = the first tooth not passed by S, (Tq, Tr, n32) the comb step.
+// Returns -1 when the walk would hand the particle to the exact path (a comparison too close to tell, a subnormal or an
+// item whose scaled value is not a normal double), else the number of teeth found; tooth_slot[k] = slot of tooth k.
+int h_fast_walk(const u64 *bits, int c, int scale, const u64 *Sv, const u64 *Qv, unsigned int R, const u64 *Tqv, unsigned int Tr,
+                unsigned int n32, int *tooth_slot, int use_reject_bound)
+{
+    const u128 S = mk128(Sv[0], Sv[1]), Tq = mk128(Tqv[0], Tqv[1]);
+    u128 Q = mk128(Qv[0], Qv[1]);
+    double cum = 0.0;
+    double Dd = to_double128(sub128(Q, S));
+    double Dlo = walk_reject_below(Dd);
+    const long long sadd = (long long)scale << 52;
+    int nt = 0;
+    for (int j = 0; j < c; j++) {
+        const u64 b = bits[j];
+        if (b == 0) continue;
+        const int eb = (int)(b >> 52) + scale;
+        if ((b >> 52) == 0 || (unsigned int)(eb - 1) >= 2045u) return -1;
+        long long sb = (long long)b + sadd;
+        double v; memcpy(&v, &sb, 8);
+        cum += v;
+        if (use_reject_bound && cum < Dlo) continue;
+        for (;;) {
+            const int passed = walk_compare(cum, Dd);
+            if (passed > 0) {
+                tooth_slot[nt++] = j;
+                tooth_step(Q, R, Tq, Tr, n32);
+                Dd = to_double128(sub128(Q, S));
+                Dlo = walk_reject_below(Dd);
+                continue;
+            }
+            if (passed == 0) return -1;
+            break;
+        }
+    }
+    return nt;
 }
 
 // The survivor scan's comb (k_scan_apply) on the host: `m` items with fixed-point masses q (lo, hi)

@@ -157,3 +157,63 @@ def test_comb_tiles_and_threads_equal_direct_comb(H, seed, m, n, tile, per, spre
     assert tot == exp_copies.sum() == n                 # every tooth lands on exactly one item
     assert np.array_equal(copies, exp_copies)
     assert np.array_equal(first, exp_first)
+
+
+def _first_tooth(S, n, U, T):
+    """(k, Q_k, R_k) of the first comb tooth not passed by the running mass S: tooth k is passed iff floor((U + k T) / n) < S."""
+    k = _teeth_below(n * S, U, T)
+    return (k,) + divmod(U + k * T, n)
+
+
+@pytest.mark.parametrize("seed,near", [(0, False), (1, False), (2, True), (3, True)])
+def test_fast_walk_decides_like_the_exact_walk_or_hands_over(H, seed, near):
+    """The survivor scan's fast walk (double precision, walk_compare / walk_reject_below of csrc/common.cuh) against the
+    exact integer walk: whenever it answers, its teeth land in the same slots; with the running mass steered to within a
+    few units of a tooth (`near`) it may only answer correctly or hand the particle over -- and the one-comparison
+    rejection bound never changes an answer."""
+    import random
+    rnd = random.Random(100 + seed)
+    H.h_fast_walk.restype = C.c_int
+    answered = handed = 0
+    for _ in range(1500):
+        c = rnd.randrange(1, 26)
+        top = rnd.uniform(-30.0, 30.0)
+        w = [2.0 ** (top - rnd.expovariate(0.25)) * rnd.uniform(1.0, 2.0) for _ in range(c)]
+        scale = 69 - int(np.floor(np.log2(max(w)))) - rnd.randrange(0, 12)      # (the bracket's top is at or above the items)
+        q = [_exact_fx(v, scale) for v in w]
+        n = rnd.randrange(1, 1 << 24)
+        tot_p = sum(q)
+        # the comb: spacing c = T / n around the particle's own mass, so that 0 .. 3 teeth fall inside it
+        T = max(n, int(tot_p * n * rnd.uniform(0.3, 4.0)))
+        S = rnd.randrange(0, 1 << 80)
+        U = rnd.randrange(0, T)
+        if near:
+            # put a tooth within a few units of the running mass after a random item
+            j = rnd.randrange(0, c)
+            target = S + sum(q[:j + 1]) + rnd.choice([-1, 1]) * rnd.choice([rnd.randrange(0, 4), rnd.randrange(40, 300), rnd.randrange(10 ** 3, 10 ** 6)])
+            k0 = max(0, (n * target - U) // T)
+            U = (n * target - k0 * T) % T if n * target >= k0 * T else U
+        k, Q, R = _first_tooth(S, n, U, T)
+        Tq, Tr = divmod(T, n)
+        bits = (U64 * c)(*[_bits(v) for v in w])
+        res = []
+        for use_bound in (1, 0):
+            slots = (C.c_int * 64)()
+            nt = H.h_fast_walk(bits, c, scale, _pair(S), _pair(Q), C.c_uint(R), _pair(Tq), C.c_uint(Tr), C.c_uint(n), slots, use_bound)
+            res.append((nt, list(slots[:max(nt, 0)])))
+        assert res[0] == res[1]                          # the rejection bound is only a shortcut
+        nt, slots = res[0]
+        # exact walk
+        exp, run, kk = [], S, k
+        for j in range(c):
+            run += q[j]
+            while (U + kk * T) // n < run:
+                exp.append(j); kk += 1
+        if nt < 0:
+            handed += 1
+        else:
+            answered += 1
+            assert slots == exp
+    assert answered > 0
+    if not near:
+        assert handed < 0.02 * (answered + handed)       # the exact path is the rare case
