@@ -139,7 +139,7 @@ struct ScanRec {
 #define PF_CPASYNC_SMEM_MAX (16 * 1024)    // staging buffer per block (14 KB for the 2-D FP64 record); larger records keep the register
                                            // prefetch: shared memory is taken from the L1 the parent gather lives on (deeper pipelines lost to it)
 #endif
-// dynamic shared memory of the single-GPU fused kernel k_expand<D, 2, true, R>: (depth + 1) slots x F fields x block
+// dynamic shared memory of the fused kernels k_expand<D, 2, true, R, ...> (single GPU and sharded): staging slots x F fields x block
 template <int D, typename R>
 __host__ __device__ constexpr size_t instexp_staging_bytes()
 {
